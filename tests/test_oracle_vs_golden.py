@@ -1,0 +1,117 @@
+"""CPU: the oracle restatement (oracle/gpmdm_oracle.py) against golden vectors recorded from the
+UNMODIFIED reference (oracle/make_golden.py).  Stage-wise: every stage is fed the reference's own
+inputs for that stage, as SURVEY.md section 8c/7.2 prescribes.
+
+Tolerances: integer outputs (classes, ancestors, argmax) bit-exact.  Means / ll / weights 1e-9
+relative (north_star).  Variances 1e-9 of the PRIOR variance (the reference's own variance is only
+reproducible to ~1e-7 relative near training data -- SURVEY fact 8 -- because of the 1 - k^T K^-1 k
+cancellation)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import gpmdm_oracle as orc
+from tests.helpers import GOLDEN_CASES, Golden, rel_err, scaled_err, t64
+
+TOL = 1e-9
+
+
+@pytest.fixture(scope="module", params=GOLDEN_CASES)
+def gold(request):
+    return Golden(request.param)
+
+
+def test_golden_cases_exist():
+    assert len(GOLDEN_CASES) >= 4
+
+
+def test_init_particles(gold):
+    f = gold.reference_factors()
+    o = orc.FilterOracle(gold.spec, gold.T, gold.P, gold.init_idx, f)
+    assert torch.equal(o.classes, torch.as_tensor(gold.z["init_classes"]))
+    assert torch.equal(o.states, t64(gold.z["init_states"]))
+
+
+def test_stagewise_against_reference(gold):
+    m, f = gold.spec, gold.reference_factors()
+    states, classes = t64(gold.z["init_states"]), torch.as_tensor(gold.z["init_classes"])
+    T = gold.T.to(torch.float64)
+    lam_x = torch.exp(m.x_log_lambdas) ** -2
+    for t in range(gold.steps):
+        s = gold.step(t)
+        E, eps, u = t64(s["E"]), t64(s["eps"]), t64(s["u"])
+        # transition: bit-exact
+        c_new = orc.transition(classes, T, E)
+        assert torch.equal(c_new, torch.as_tensor(s["c_new"]))
+        # dynamics GP: mean 1e-9 rel (scaled by the row's magnitude), var 1e-9 of prior
+        x_new, dmean, dvar = orc.dynamics_draw(m, f, states, c_new, eps)
+        scale = torch.clamp(torch.abs(t64(s["dyn_mean"])).max(dim=1, keepdim=True).values, min=1e-3)
+        assert scaled_err(dmean, s["dyn_mean"], scale) < TOL
+        prior = orc.x_diag_kernel(m, states).unsqueeze(1) * lam_x.unsqueeze(0)
+        assert scaled_err(dvar, t64(s["dyn_std"]) ** 2, prior) < TOL
+        # observation GP on the REFERENCE's post-dynamics states (stage-wise)
+        # (reference states before resampling are not stored; rebuild them from its mean/std + eps)
+        x_ref = eps * t64(s["dyn_std"]) + t64(s["dyn_mean"])
+        mu, var, v = orc.map_x_to_y(m, f, x_ref)
+        assert scaled_err(mu, s["mu"], torch.clamp(torch.abs(t64(s["mu"])).max(dim=1, keepdim=True).values, min=1e-3)) < TOL
+        lam_y = torch.exp(m.y_log_lambdas) ** -2
+        assert scaled_err(var, s["var"], lam_y.unsqueeze(0).expand_as(var)) < TOL
+        # ll from the REFERENCE's mu / var: loop restatement and fused closed form
+        v_ref = t64(s["var"])[:, 0] / lam_y[0]
+        ll_loop = orc.log_likelihoods_loop(t64(s["mu"]), t64(s["var"]), t64(s["z"]), m.D)
+        assert rel_err(ll_loop, s["ll"]) < 1e-12
+        ll_fused = orc.log_likelihoods_fused(t64(s["mu"]), v_ref, t64(s["z"]), m.y_log_lambdas)
+        assert rel_err(ll_fused, s["ll"]) < TOL
+        # weights from the reference's ll
+        lw, w = orc.normalize(t64(s["ll"]))
+        assert torch.equal(lw, t64(s["lw"]))
+        assert rel_err(w, s["w"]) < 1e-14
+        # resampling from the reference's w: bit-exact cdf and ancestors
+        assert torch.equal(orc.sequential_cdf(t64(s["w"])), t64(s["cdf"]))
+        anc = orc.resample(t64(s["w"]), u)
+        assert torch.equal(anc, torch.as_tensor(s["anc"]))
+        states, classes = x_ref[anc], c_new[anc]
+        assert torch.equal(states, t64(s["states_post"]))
+        assert torch.equal(classes, torch.as_tensor(s["classes_post"]))
+        # queries
+        cp = orc.class_probabilities(t64(s["ll"]), t64(s["lw"]), classes, m.n_classes)
+        assert rel_err(cp, s["class_prob"]) < 1e-13
+        assert int(torch.argmax(cp)) == int(s["argmax"])
+        assert rel_err(orc.current_state_mean(states, t64(s["w"])), s["state_mean"]) < 1e-12
+        assert abs(float(orc.weighted_log_sum(t64(s["ll"]), t64(s["lw"]))) - float(s["log_likelihood"])) \
+            <= 1e-13 * abs(float(s["log_likelihood"]))
+
+
+def test_end_to_end_filter_matches_reference(gold):
+    """Free-running oracle filter (own factors from the reference's inverses) over all golden steps:
+    classes / ancestors / argmax identical, states to 1e-9."""
+    f = gold.reference_factors()
+    o = orc.FilterOracle(gold.spec, gold.T, gold.P, gold.init_idx, f)
+    for t in range(gold.steps):
+        s = gold.step(t)
+        o.update(s["z"], t64(s["E"]), t64(s["eps"]), t64(s["u"]))
+        assert torch.equal(o.trace["c_new"], torch.as_tensor(s["c_new"]))
+        assert torch.equal(o.trace["anc"], torch.as_tensor(s["anc"]))
+        assert o.get_most_likely_class() == int(s["argmax"])
+        assert rel_err(o.trace["ll"], s["ll"]) < 1e-6  # inherits the variance noise floor
+        assert float(torch.max(torch.abs(o.states - t64(s["states_post"])))) < 1e-8
+
+
+def test_own_inverses_close_to_reference(gold):
+    """Block inverses computed by the oracle (same op sequence on the N_c x N_c block) vs the blocks
+    cut from the reference's dense per-class inverses."""
+    f_own = orc.precompute_factors(gold.spec)
+    f_ref = gold.reference_factors()
+    assert torch.equal(f_own.Ky_inv, f_ref.Ky_inv) or rel_err(f_own.alpha_y, f_ref.alpha_y) < 1e-6
+    for a, b in zip(f_own.Kx_inv_blocks, f_ref.Kx_inv_blocks):
+        assert float(torch.max(torch.abs(a - b)) / torch.max(torch.abs(b))) < 1e-6
+
+
+def test_c32_constant():
+    assert orc.c32_constant(62) == 56.97418975830078
+    assert orc.c32_constant(62) != 0.5 * 62 * np.log(2 * np.pi)
+
+
+def test_divide_into_n_parts():
+    assert orc.divide_into_n_parts(64, 3) == [22, 21, 21]
+    assert orc.divide_into_n_parts(100, 2) == [50, 50]
