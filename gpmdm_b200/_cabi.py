@@ -1,0 +1,100 @@
+"""ctypes binding of libgpmdm_sm100a.so (include/gpmdm_b200.h).
+
+The library is the only implementation of the filter step: if it is missing or a call fails the
+caller gets an exception -- there is no CPU or torch fallback behind any of these functions.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+import torch
+
+from . import build as _build
+
+_i32, _i64, _u64, _f64, _ptr = ctypes.c_int32, ctypes.c_int64, ctypes.c_uint64, ctypes.c_double, ctypes.c_void_p
+
+TILE = 128
+MAX_LATENT = 8
+
+
+class GpModel(ctypes.Structure):
+    """struct gpmdm_gp_model"""
+    _fields_ = [("blocks", _ptr), ("n_blocks", _i32), ("d", _i32), ("dout", _i32), ("alpha_ld", _i32),
+                ("kind", _i32), ("tri", _i32), ("lengthscales", _ptr), ("lin_c2", _ptr), ("lambdas", _ptr)]
+
+
+_SIGNATURES = {
+    "gpmdm_abi_version": (ctypes.c_int, []),
+    "gpmdm_last_error": (ctypes.c_char_p, []),
+    "gpmdm_pack_quadform_f64": (ctypes.c_int, [_ptr, _i64, _i64, ctypes.c_int, _ptr, _ptr]),
+    "gpmdm_pf_transition_f64": (ctypes.c_int, [_ptr, _ptr, _ptr, _i64, _i32, _ptr, _ptr]),
+    "gpmdm_pf_bucket_by_class": (ctypes.c_int, [_ptr, _i64, _i32, _ptr, _ptr, _ptr, _ptr, _ptr]),
+    "gpmdm_pf_propagate_f64": (ctypes.c_int, [ctypes.POINTER(GpModel), _ptr, _ptr, _ptr, _ptr, _i64, _ptr, _ptr,
+                                              _ptr, _ptr, _ptr, _ptr]),
+    "gpmdm_pf_observe_f64": (ctypes.c_int, [ctypes.POINTER(GpModel), _ptr, _i64, _ptr, _f64, _ptr, _ptr, _ptr,
+                                            _ptr, _ptr]),
+    "gpmdm_pf_normalize_f64": (ctypes.c_int, [_ptr, _i64, _ptr, _ptr, _ptr, _ptr, _ptr]),
+    "gpmdm_pf_cdf_f64": (ctypes.c_int, [_ptr, _i64, _i32, _ptr, _ptr, _ptr]),
+    "gpmdm_pf_resample_f64": (ctypes.c_int, [_ptr, _i64, _ptr, _i64, _ptr, _ptr, _i32, _ptr, _ptr, _ptr, _ptr]),
+    "gpmdm_pf_summaries_f64": (ctypes.c_int, [_ptr, _ptr, _ptr, _ptr, _ptr, _i64, _i32, _i32, _ptr, _ptr, _ptr]),
+    "gpmdm_pf_draws_philox": (ctypes.c_int, [_u64, _u64, _i64, _i64, _i64, _i32, _i32, _i32, _ptr, _ptr, _ptr,
+                                             _ptr]),
+    "gpmdm_workspace_bytes": (_i64, [_i64, _i32]),
+    "gpmdm_kernel_build_f64": (ctypes.c_int, [_ptr, _i64, _i32, _i32, _ptr, _ptr, _f64, _ptr, _i32, _ptr, _ptr]),
+    "gpmdm_kernel_grad_f64": (ctypes.c_int, [_ptr, _ptr, _i64, _i32, _i32, _ptr, _ptr, _f64, _ptr, _i32, _ptr, _ptr,
+                                             _ptr, _ptr, _ptr, _ptr]),
+    "gpmdm_kernel_grad_workspace_bytes": (_i64, [_i64, _i32]),
+    "gpmdm_probe_dmma_tflops": (ctypes.c_int, [_i32, ctypes.POINTER(_f64)]),
+}
+
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+_lib = None
+
+
+def library_path() -> str:
+    return _build.LIB_PATH
+
+
+def lib() -> ctypes.CDLL:
+    """Load (once) the CUDA extension.  Raises if it has not been built."""
+    global _lib
+    if _lib is None:
+        path = library_path()
+        if not os.path.exists(path):
+            raise RuntimeError(f"{path} is missing: run `python -m gpmdm_b200.build` (needs nvcc). "
+                               "gpmdm_b200 has no CPU or torch fallback for the filter step.")
+        handle = ctypes.CDLL(path)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(handle, name)  # AttributeError if the build is stale
+            fn.restype, fn.argtypes = res, args
+        if handle.gpmdm_abi_version() != 1:
+            raise RuntimeError("libgpmdm_sm100a.so ABI version mismatch; rebuild")
+        _lib = handle
+    return _lib
+
+
+def check(rc: int, what: str) -> None:
+    """Map the C ABI's return convention onto the reference's exception behaviour."""
+    if rc == 0:
+        return
+    msg = lib().gpmdm_last_error().decode(errors="replace")
+    if rc < 0:
+        raise ValueError(f"{what}: {msg}")
+    raise RuntimeError(f"{what}: CUDA error {rc}: {msg}")
+
+
+def ptr(t):
+    """Device pointer of a tensor (or NULL).  The tensor must be a contiguous CUDA tensor."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError("gpmdm_b200 kernels need CUDA tensors (there is no CPU path)")
+    if not t.is_contiguous():
+        raise RuntimeError("non-contiguous tensor passed to the C ABI")
+    return t.data_ptr()
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream

@@ -1,0 +1,554 @@
+// The HBM-bound stages of the filter step: class transition, class bucketing, weight normalisation,
+// cdf, resampling search + gather, class/state summaries, and the Philox draw generator.
+//
+// Replaces (reference paths): gpmdm/gpmdm_pf.py:137-151 (_propogate_markov_switching), :161 (mask
+// gather), :200-204 (normalisation), :206-213 (_resample), :215-262 (queries).
+//
+// Every floating-point reduction here runs in a FIXED order that depends only on the particle count
+// (1024-element blocks, 256 threads x 4 consecutive elements, shuffle tree, then a serial pass over
+// block partials), never on the grid size or the number of GPUs: a G-GPU run reproduces the 1-GPU
+// run bit for bit.
+#include <math.h>
+
+#include "common.cuh"
+
+namespace gpmdm {
+
+constexpr int RB = 1024;  // elements per reduction block
+constexpr int RT = 256;   // threads per reduction block
+
+// Block-wide sum in a fixed order: lane tree inside each warp, then warp 0 adds the 8 warp totals
+// serially.  All threads receive the result.
+__device__ __forceinline__ double block_sum_fixed(double v, double* sh /*[RT/32 + 1]*/) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if (lane == 0) sh[warp] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < RT / 32; w++) t += sh[w];
+        sh[RT / 32] = t;
+    }
+    __syncthreads();
+    const double out = sh[RT / 32];
+    __syncthreads();
+    return out;
+}
+__device__ __forceinline__ double block_max(double v, double* sh) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    v = warp_max(v);
+    if (lane == 0) sh[warp] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = sh[0];
+        for (int w = 1; w < RT / 32; w++) t = fmax(t, sh[w]);
+        sh[RT / 32] = t;
+    }
+    __syncthreads();
+    const double out = sh[RT / 32];
+    __syncthreads();
+    return out;
+}
+
+// serial, fixed-order combination of per-block partials by one block (n_part <= a few thousand)
+template <bool IS_MAX>
+__global__ void __launch_bounds__(RT) combine_partials_kernel(const double* __restrict__ part, long long n_part,
+                                                              double* __restrict__ out) {
+    __shared__ double sh[RT / 32 + 1];
+    // thread t owns the contiguous slice [t*per, (t+1)*per): order fixed by n_part alone
+    const long long per = (n_part + RT - 1) / RT;
+    const long long a = threadIdx.x * per, b = (a + per < n_part) ? a + per : n_part;
+    double v = IS_MAX ? -INFINITY : 0.0;
+    for (long long i = a; i < b; i++) v = IS_MAX ? fmax(v, part[i]) : v + part[i];
+    const double r = IS_MAX ? block_max(v, sh) : block_sum_fixed(v, sh);
+    if (threadIdx.x == 0) out[0] = r;
+}
+
+// ---- class transition ----------------------------------------------------------------------------------
+__global__ void transition_kernel(const int64_t* __restrict__ c_prev, const double* __restrict__ T,
+                                  const double* __restrict__ E, long long P, int C, int64_t* __restrict__ c_new) {
+    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P) return;
+    const double* row = T + c_prev[p] * C;
+    const double* e = E + p * C;
+    double best = row[0] / e[0];
+    int arg = 0;
+    for (int j = 1; j < C; j++) {
+        const double q = row[j] / e[j];  // IEEE division, as torch's `dist / q`
+        if (q > best) {                  // first maximum wins, as torch.argmax
+            best = q;
+            arg = j;
+        }
+    }
+    c_new[p] = arg;
+}
+
+// ---- bucket by class (stable counting sort) ---------------------------------------------------------------
+__global__ void __launch_bounds__(RB) bucket_count_kernel(const int64_t* __restrict__ cls, long long P, int C,
+                                                          int nb, int32_t* __restrict__ counts /*[C][nb]*/) {
+    extern __shared__ int sh_cnt[];
+    for (int i = threadIdx.x; i < C; i += blockDim.x) sh_cnt[i] = 0;
+    __syncthreads();
+    const long long p = (long long)blockIdx.x * RB + threadIdx.x;
+    if (p < P) atomicAdd(&sh_cnt[(int)cls[p]], 1);
+    __syncthreads();
+    for (int i = threadIdx.x; i < C; i += blockDim.x) counts[(long long)i * nb + blockIdx.x] = sh_cnt[i];
+}
+
+__global__ void __launch_bounds__(1024) bucket_scan_kernel(int32_t* __restrict__ counts /*in: counts, out: offsets*/,
+                                                           int C, int nb, int32_t* __restrict__ tiles,
+                                                           int32_t* __restrict__ n_tiles) {
+    // exclusive scan over the class-major [C][nb] array, chunk by chunk (1024 entries per pass)
+    __shared__ int sh[1024];
+    __shared__ int carry;
+    extern __shared__ int cls_start[];  // [C + 1] class start offsets, then [C + 1] tile starts
+    int* tile_start = cls_start + (C + 1);
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    const long long total = (long long)C * nb;
+    for (long long base = 0; base < total; base += 1024) {
+        const long long i = base + threadIdx.x;
+        const int v = i < total ? counts[i] : 0;
+        sh[threadIdx.x] = v;
+        __syncthreads();
+        for (int o = 1; o < 1024; o <<= 1) {
+            const int add = threadIdx.x >= o ? sh[threadIdx.x - o] : 0;
+            __syncthreads();
+            sh[threadIdx.x] += add;
+            __syncthreads();
+        }
+        const int excl = carry + sh[threadIdx.x] - v;
+        if (i < total) {
+            counts[i] = excl;
+            if (i % nb == 0) cls_start[i / nb] = excl;
+        }
+        __syncthreads();
+        if (threadIdx.x == 1023) carry += sh[1023];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        cls_start[C] = carry;
+        int t = 0;
+        for (int c = 0; c < C; c++) {
+            tile_start[c] = t;
+            t += (cls_start[c + 1] - cls_start[c] + GPMDM_TILE - 1) / GPMDM_TILE;
+        }
+        tile_start[C] = t;
+        n_tiles[0] = t;
+    }
+    __syncthreads();
+    for (int c = 0; c < C; c++) {
+        const int nt = tile_start[c + 1] - tile_start[c];
+        const int cnt = cls_start[c + 1] - cls_start[c];
+        for (int t = threadIdx.x; t < nt; t += blockDim.x) {
+            int32_t* d = tiles + 4ll * (tile_start[c] + t);
+            d[0] = c;
+            d[1] = cls_start[c] + t * GPMDM_TILE;
+            d[2] = min(GPMDM_TILE, cnt - t * GPMDM_TILE);
+            d[3] = 0;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(RB) bucket_scatter_kernel(const int64_t* __restrict__ cls, long long P, int C,
+                                                            int nb, const int32_t* __restrict__ offsets,
+                                                            int32_t* __restrict__ perm) {
+    extern __shared__ int wc[];  // [32 warps][C]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < 32 * C; i += blockDim.x) wc[i] = 0;
+    __syncthreads();
+    const long long p = (long long)blockIdx.x * RB + threadIdx.x;
+    const int c = p < P ? (int)cls[p] : -1;
+    const unsigned peers = __match_any_sync(0xffffffffu, c);
+    const int rank = __popc(peers & ((1u << lane) - 1u));
+    if (c >= 0 && rank == 0) wc[warp * C + c] = __popc(peers);
+    __syncthreads();
+    // exclusive scan over warps, one thread per class
+    for (int k = threadIdx.x; k < C; k += blockDim.x) {
+        int run = 0;
+        for (int w = 0; w < 32; w++) {
+            const int v = wc[w * C + k];
+            wc[w * C + k] = run;
+            run += v;
+        }
+    }
+    __syncthreads();
+    if (c >= 0) perm[offsets[(long long)c * nb + blockIdx.x] + wc[warp * C + c] + rank] = (int32_t)p;
+}
+
+// ---- normalisation -------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(RT) block_max_kernel(const double* __restrict__ a, const double* __restrict__ b,
+                                                       long long n, double* __restrict__ part) {
+    __shared__ double sh[RT / 32 + 1];
+    const long long base = (long long)blockIdx.x * RB + threadIdx.x * 4;
+    double v = -INFINITY;
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+        if (base + k < n) v = fmax(v, b ? a[base + k] + b[base + k] : a[base + k]);
+    v = block_max(v, sh);
+    if (threadIdx.x == 0) part[blockIdx.x] = v;
+}
+
+__global__ void __launch_bounds__(RT) exp_sum_kernel(const double* __restrict__ ll, long long n,
+                                                     const double* __restrict__ mx, double* __restrict__ lw,
+                                                     double* __restrict__ w, double* __restrict__ part) {
+    __shared__ double sh[RT / 32 + 1];
+    const long long base = (long long)blockIdx.x * RB + threadIdx.x * 4;
+    const double m = mx[0];
+    double acc = 0.0;
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+        if (base + k < n) {
+            const double l = ll[base + k] - m;
+            const double e = exp(l);
+            lw[base + k] = l;
+            w[base + k] = e;
+            acc += e;
+        }
+    acc = block_sum_fixed(acc, sh);
+    if (threadIdx.x == 0) part[blockIdx.x] = acc;
+}
+
+__global__ void divide_kernel(double* __restrict__ w, long long n, const double* __restrict__ total) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) w[i] = w[i] / total[0];
+}
+
+// ---- cdf ---------------------------------------------------------------------------------------------------
+// mode 0: the reference's order (ATen CPU cumsum: one running sum in index order).
+__global__ void cdf_sequential_kernel(const double* __restrict__ w, long long n, double* __restrict__ cdf,
+                                      double* __restrict__ total) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    double run = 0.0;
+    long long i = 0;
+    for (; i + 8 <= n; i += 8) {
+        double v[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) v[k] = w[i + k];
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            run = __dadd_rn(run, v[k]);
+            cdf[i + k] = run;
+        }
+    }
+    for (; i < n; i++) {
+        run = __dadd_rn(run, w[i]);
+        cdf[i] = run;
+    }
+    total[0] = run;
+}
+
+// mode 1: blocked scan.  Pass A: inclusive scan inside each 1024-element block + block total.
+__global__ void __launch_bounds__(RT) cdf_block_scan_kernel(const double* __restrict__ w, long long n,
+                                                            double* __restrict__ cdf, double* __restrict__ part) {
+    __shared__ double wsum[RT / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long base = (long long)blockIdx.x * RB + threadIdx.x * 4;
+    double v[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) v[k] = base + k < n ? w[base + k] : 0.0;
+    v[1] += v[0];
+    v[2] += v[1];
+    v[3] += v[2];
+    double incl = v[3];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const double t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) wsum[warp] = incl;
+    __syncthreads();
+    double off = incl - v[3];  // exclusive prefix inside the warp
+    for (int k = 0; k < warp; k++) off += wsum[k];
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+        if (base + k < n) cdf[base + k] = off + v[k];
+    if (threadIdx.x == RT - 1) part[blockIdx.x] = off + v[3];
+}
+// Pass B: serial exclusive scan of block totals (one thread; <= P/1024 entries).
+__global__ void cdf_scan_partials_kernel(double* __restrict__ part, long long nb, double* __restrict__ total) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    double run = 0.0;
+    for (long long i = 0; i < nb; i++) {
+        const double v = part[i];
+        part[i] = run;
+        run += v;
+    }
+    total[0] = run;
+}
+// Pass C: add the block prefix, divide by the total, force the last entry to 1.
+__global__ void cdf_finish_kernel(double* __restrict__ cdf, long long n, const double* __restrict__ part,
+                                  const double* __restrict__ total) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double v = cdf[i];
+    if (part) v = part[i / RB] + v;
+    cdf[i] = (i == n - 1) ? 1.0 : v / total[0];
+}
+
+// ---- resampling search + gather -----------------------------------------------------------------------------
+__global__ void resample_kernel(const double* __restrict__ cdf, long long P, const double* __restrict__ u,
+                                long long n_out, const double* __restrict__ x_in, const int64_t* __restrict__ c_in,
+                                int d, int64_t* __restrict__ anc, double* __restrict__ x_out,
+                                int64_t* __restrict__ c_out) {
+    const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_out) return;
+    const double us = u[s];
+    long long left = 0, right = P;  // ATen MultinomialKernel.cpp binary search: first j with cdf[j] >= u
+    while (right - left > 0) {
+        const long long mid = left + (right - left) / 2;
+        if (cdf[mid] < us) left = mid + 1;
+        else right = mid;
+    }
+    if (left >= P) left = P - 1;
+    if (anc) anc[s] = left;
+    if (x_out)
+        for (int k = 0; k < d; k++) x_out[s * d + k] = x_in[left * d + k];
+    if (c_out) c_out[s] = c_in[left];
+}
+
+// ---- summaries --------------------------------------------------------------------------------------------
+// part [nb][C + d + 1]: per-block class sums of exp(g - max), state-mean partials, total.
+__global__ void __launch_bounds__(RT) summaries_block_kernel(const double* __restrict__ ll,
+                                                             const double* __restrict__ lw,
+                                                             const double* __restrict__ w,
+                                                             const int64_t* __restrict__ c_post,
+                                                             const double* __restrict__ x_post, long long n, int C,
+                                                             int d, const double* __restrict__ gmax,
+                                                             double* __restrict__ part) {
+    __shared__ double sh[RT / 32 + 1];
+    const long long base = (long long)blockIdx.x * RB + threadIdx.x * 4;
+    const double m = gmax[0];
+    double e[4], ww[4];
+    int cc[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const bool ok = base + k < n;
+        e[k] = ok ? exp((ll[base + k] + lw[base + k]) - m) : 0.0;
+        ww[k] = ok ? w[base + k] : 0.0;
+        cc[k] = ok ? (int)c_post[base + k] : -1;
+    }
+    double* out = part + (long long)blockIdx.x * (C + d + 1);
+    for (int c = 0; c < C; c++) {
+        double v = 0.0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) v += cc[k] == c ? e[k] : 0.0;
+        v = block_sum_fixed(v, sh);
+        if (threadIdx.x == 0) out[c] = v;
+    }
+    for (int j = 0; j < d; j++) {
+        double v = 0.0;
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+            if (base + k < n) v += x_post[(base + k) * d + j] * ww[k];
+        v = block_sum_fixed(v, sh);
+        if (threadIdx.x == 0) out[C + j] = v;
+    }
+    double v = (e[0] + e[1]) + (e[2] + e[3]);
+    v = block_sum_fixed(v, sh);
+    if (threadIdx.x == 0) out[C + d] = v;
+}
+
+__global__ void __launch_bounds__(RT) summaries_final_kernel(const double* __restrict__ part, long long nb, int C,
+                                                             int d, double* __restrict__ out) {
+    __shared__ double sh[RT / 32 + 1];
+    __shared__ double cls[64 + GPMDM_MAX_LATENT + 1];
+    const int ncol = C + d + 1;
+    const long long per = (nb + RT - 1) / RT;
+    const long long a = threadIdx.x * per, b = (a + per < nb) ? a + per : nb;
+    for (int col = 0; col < ncol; col++) {
+        double v = 0.0;
+        for (long long i = a; i < b; i++) v += part[i * ncol + col];
+        v = block_sum_fixed(v, sh);
+        if (threadIdx.x == 0) cls[col] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double tot = 0.0;
+        for (int c = 0; c < C; c++) tot += cls[c];
+        for (int c = 0; c < C; c++) out[c] = cls[c] / tot;  // class_likelihoods / sum (gpmdm_pf.py:246)
+        for (int j = 0; j < d; j++) out[C + j] = cls[C + j];
+        out[C + d] = cls[C + d];
+    }
+}
+
+// ---- Philox4x32-10 draws ------------------------------------------------------------------------------------
+__device__ __forceinline__ void philox4x32_10(uint32_t (&ctr)[4], uint32_t k0, uint32_t k1) {
+#pragma unroll
+    for (int i = 0; i < 10; i++) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, ctr[0]), lo0 = 0xD2511F53u * ctr[0];
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, ctr[2]), lo1 = 0xCD9E8D57u * ctr[2];
+        const uint32_t n0 = hi1 ^ ctr[1] ^ k0, n1 = lo1, n2 = hi0 ^ ctr[3] ^ k1, n3 = lo0;
+        ctr[0] = n0;
+        ctr[1] = n1;
+        ctr[2] = n2;
+        ctr[3] = n3;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+}
+// two uniforms in [0,1) with 53 random bits each
+__device__ __forceinline__ void philox_u2(unsigned long long seed, unsigned long long step, unsigned long long p,
+                                          uint32_t draw, double& a, double& b) {
+    uint32_t ctr[4] = {(uint32_t)p, (uint32_t)(p >> 32), (uint32_t)step, draw};
+    philox4x32_10(ctr, (uint32_t)seed, (uint32_t)(seed >> 32) ^ (uint32_t)(step >> 32));
+    const unsigned long long x = ((unsigned long long)ctr[1] << 32) | ctr[0];
+    const unsigned long long y = ((unsigned long long)ctr[3] << 32) | ctr[2];
+    a = (double)(x >> 11) * 0x1.0p-53;
+    b = (double)(y >> 11) * 0x1.0p-53;
+}
+
+__global__ void philox_draws_kernel(unsigned long long seed, unsigned long long step, long long first, long long n,
+                                    long long P_total, int C, int d, int systematic, double* __restrict__ E,
+                                    double* __restrict__ eps, double* __restrict__ u) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned long long p = (unsigned long long)(first + i);
+    uint32_t draw = 0;
+    double a, b;
+    if (E) {
+        for (int j = 0; j < C; j += 2) {
+            philox_u2(seed, step, p, draw++, a, b);
+            E[i * C + j] = -log1p(-a);  // Exp(1), as torch's exponential_()
+            if (j + 1 < C) E[i * C + j + 1] = -log1p(-b);
+        }
+    }
+    draw = 0x1000;
+    if (eps) {
+        for (int j = 0; j < d; j += 2) {
+            philox_u2(seed, step, p, draw++, a, b);
+            const double rad = sqrt(-2.0 * log(1.0 - a));  // 1 - a in (0, 1]
+            double sn, cs;
+            sincospi(2.0 * b, &sn, &cs);
+            eps[i * d + j] = rad * cs;
+            if (j + 1 < d) eps[i * d + j + 1] = rad * sn;
+        }
+    }
+    if (u) {
+        if (systematic) {
+            philox_u2(seed, step, 0xffffffffffffffffull, 0x2000, a, b);  // one shared offset u0
+            u[i] = (a + (double)p) / (double)P_total;
+        } else {
+            philox_u2(seed, step, p, 0x2000, a, b);
+            u[i] = a;
+        }
+    }
+}
+
+static inline int nblocks(long long n, int per) { return (int)((n + per - 1) / per); }
+
+}  // namespace gpmdm
+
+using namespace gpmdm;
+
+// workspace layout (bytes): [0, 64) scalars {max, sum, ...}; then partials
+extern "C" int64_t gpmdm_workspace_bytes(int64_t P, int32_t C) {
+    const int64_t nb = (P + RB - 1) / RB;
+    const int64_t part = nb * (int64_t)(C + GPMDM_MAX_LATENT + 1) * 8;  // summaries partials (largest user)
+    const int64_t counts = (int64_t)C * nb * 4;
+    return 256 + round_up(part > counts ? part : counts, 256) + round_up(nb * 8, 256);
+}
+
+extern "C" int gpmdm_pf_transition_f64(const int64_t* c_prev, const double* T, const double* E, int64_t P, int32_t C,
+                                       int64_t* c_new, void* stream) {
+    GPMDM_REQUIRE(P >= 0 && C >= 1, GPMDM_E_INVALID, "bad sizes P=%lld C=%d", (long long)P, C);
+    if (P == 0) return 0;
+    GPMDM_REQUIRE(c_prev && T && E && c_new, GPMDM_E_INVALID, "null argument");
+    transition_kernel<<<nblocks(P, 256), 256, 0, (cudaStream_t)stream>>>(c_prev, T, E, P, C, c_new);
+    return check_launch("transition_kernel");
+}
+
+extern "C" int gpmdm_pf_bucket_by_class(const int64_t* classes, int64_t P, int32_t C, int32_t* perm, int32_t* tiles,
+                                        int32_t* n_tiles, void* workspace, void* stream) {
+    GPMDM_REQUIRE(P > 0 && P < (1ll << 31) && C >= 1 && C <= 1024, GPMDM_E_INVALID, "bad sizes P=%lld C=%d",
+                  (long long)P, C);
+    GPMDM_REQUIRE(classes && perm && tiles && n_tiles && workspace, GPMDM_E_INVALID, "null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int nb = nblocks(P, RB);
+    int32_t* counts = reinterpret_cast<int32_t*>(static_cast<char*>(workspace) + 256);
+    bucket_count_kernel<<<nb, RB, C * sizeof(int), st>>>(classes, P, C, nb, counts);
+    bucket_scan_kernel<<<1, 1024, 2 * (C + 1) * sizeof(int), st>>>(counts, C, nb, tiles, n_tiles);
+    bucket_scatter_kernel<<<nb, RB, 32 * C * sizeof(int), st>>>(classes, P, C, nb, counts, perm);
+    return check_launch("bucket_by_class");
+}
+
+extern "C" int gpmdm_pf_normalize_f64(const double* ll, int64_t P, double* lw, double* w, double* stats_out,
+                                      void* workspace, void* stream) {
+    GPMDM_REQUIRE(P > 0, GPMDM_E_INVALID, "P must be positive");
+    GPMDM_REQUIRE(ll && lw && w && workspace, GPMDM_E_INVALID, "null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int nb = nblocks(P, RB);
+    double* scal = static_cast<double*>(workspace);  // [0]=max [1]=sum
+    double* part = reinterpret_cast<double*>(static_cast<char*>(workspace) + 256);
+    block_max_kernel<<<nb, RT, 0, st>>>(ll, nullptr, P, part);
+    combine_partials_kernel<true><<<1, RT, 0, st>>>(part, nb, scal);
+    exp_sum_kernel<<<nb, RT, 0, st>>>(ll, P, scal, lw, w, part);
+    combine_partials_kernel<false><<<1, RT, 0, st>>>(part, nb, scal + 1);
+    divide_kernel<<<nblocks(P, 256), 256, 0, st>>>(w, P, scal + 1);
+    if (stats_out) {
+        cudaError_t e = cudaMemcpyAsync(stats_out, scal, 16, cudaMemcpyDeviceToDevice, st);
+        GPMDM_REQUIRE(e == cudaSuccess, (int)e, "cudaMemcpyAsync: %s", cudaGetErrorString(e));
+    }
+    return check_launch("normalize");
+}
+
+extern "C" int gpmdm_pf_cdf_f64(const double* w, int64_t P, int32_t mode, double* cdf, void* workspace,
+                                void* stream) {
+    GPMDM_REQUIRE(P > 0 && (mode == 0 || mode == 1), GPMDM_E_INVALID, "bad arguments P=%lld mode=%d", (long long)P,
+                  mode);
+    GPMDM_REQUIRE(w && cdf && workspace, GPMDM_E_INVALID, "null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    double* scal = static_cast<double*>(workspace) + 2;  // total
+    double* part = reinterpret_cast<double*>(static_cast<char*>(workspace) + 256);
+    if (mode == 0) {
+        cdf_sequential_kernel<<<1, 32, 0, st>>>(w, P, cdf, scal);
+        cdf_finish_kernel<<<nblocks(P, 256), 256, 0, st>>>(cdf, P, nullptr, scal);
+    } else {
+        const int nb = nblocks(P, RB);
+        cdf_block_scan_kernel<<<nb, RT, 0, st>>>(w, P, cdf, part);
+        cdf_scan_partials_kernel<<<1, 32, 0, st>>>(part, nb, scal);
+        cdf_finish_kernel<<<nblocks(P, 256), 256, 0, st>>>(cdf, P, part, scal);
+    }
+    return check_launch("cdf");
+}
+
+extern "C" int gpmdm_pf_resample_f64(const double* cdf, int64_t P, const double* u, int64_t n_out,
+                                     const double* x_in, const int64_t* c_in, int32_t d, int64_t* anc, double* x_out,
+                                     int64_t* c_out, void* stream) {
+    GPMDM_REQUIRE(P > 0 && n_out >= 0 && d >= 0, GPMDM_E_INVALID, "bad sizes");
+    if (n_out == 0) return 0;
+    GPMDM_REQUIRE(cdf && u, GPMDM_E_INVALID, "null argument");
+    GPMDM_REQUIRE((x_out == nullptr || x_in != nullptr) && (c_out == nullptr || c_in != nullptr), GPMDM_E_INVALID,
+                  "gather output without input");
+    resample_kernel<<<nblocks(n_out, 256), 256, 0, (cudaStream_t)stream>>>(cdf, P, u, n_out, x_in, c_in, d, anc,
+                                                                           x_out, c_out);
+    return check_launch("resample_kernel");
+}
+
+extern "C" int gpmdm_pf_summaries_f64(const double* ll, const double* lw, const double* w, const int64_t* c_post,
+                                      const double* x_post, int64_t P, int32_t C, int32_t d, double* out,
+                                      void* workspace, void* stream) {
+    GPMDM_REQUIRE(P > 0 && C >= 1 && C <= 64 && d >= 1 && d <= GPMDM_MAX_LATENT, GPMDM_E_INVALID,
+                  "bad sizes P=%lld C=%d d=%d", (long long)P, C, d);
+    GPMDM_REQUIRE(ll && lw && w && c_post && x_post && out && workspace, GPMDM_E_INVALID, "null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int nb = nblocks(P, RB);
+    double* scal = static_cast<double*>(workspace) + 3;  // max of ll + lw
+    double* part = reinterpret_cast<double*>(static_cast<char*>(workspace) + 256);
+    block_max_kernel<<<nb, RT, 0, st>>>(ll, lw, P, part);
+    combine_partials_kernel<true><<<1, RT, 0, st>>>(part, nb, scal);
+    summaries_block_kernel<<<nb, RT, 0, st>>>(ll, lw, w, c_post, x_post, P, C, d, scal, part);
+    summaries_final_kernel<<<1, RT, 0, st>>>(part, nb, C, d, out);
+    return check_launch("summaries");
+}
+
+extern "C" int gpmdm_pf_draws_philox(uint64_t seed, uint64_t step, int64_t first, int64_t n, int64_t P_total,
+                                     int32_t C, int32_t d, int32_t systematic, double* E, double* eps, double* u,
+                                     void* stream) {
+    GPMDM_REQUIRE(n >= 0 && first >= 0 && P_total >= first + n, GPMDM_E_INVALID, "bad particle range");
+    if (n == 0) return 0;
+    philox_draws_kernel<<<nblocks(n, 256), 256, 0, (cudaStream_t)stream>>>(seed, step, first, n, P_total, C, d,
+                                                                          systematic, E, eps, u);
+    return check_launch("philox_draws_kernel");
+}

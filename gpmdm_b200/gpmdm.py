@@ -1,0 +1,576 @@
+"""`GPMDM` -- the model class of the reference (`gpmdm/gpmdm.py`) with the same constructor, data,
+training, prediction and save/load API, whose arithmetic on the filter / training hot paths runs in
+libgpmdm_sm100a.so (hand-written CUDA for B200) instead of dense torch-CPU expressions.
+
+What is kept verbatim from the reference surface (file:line of the reference):
+  ctor :96-237 | set_evaluation_mode :239 | set_training_mode :247 | add_data :281 |
+  observations_list :301 | get_y_kernel / get_x_kernel / get_rbf_kernel / get_lin_kernel :381-548 |
+  get_y_neg_log_likelihood :550 | get_x_neg_log_likelihood :591 | get_Xin_Xout_matrices :630 |
+  gpdm_loss :721 | init_X :762 | get_Y :779 | train_adam :817 | get_latent_sequences :887 |
+  get_X_for_class :906 | map_x_to_y :923 | map_x_dynamics_for_class :1032 | save :1307 | load :1350
+
+What differs by design (B200-first):
+  * tensors live on the CUDA device; there is no CPU path;
+  * the dense 0/1 masks `M`, `M_class[c]` (C+1 dense Nx x Nx matrices, :311-378) are never built --
+    class structure is carried as row offsets; `Kx_inv_class[c]` holds the N_c x N_c diagonal block
+    of the reference's dense matrix (whose off-class part is exactly 1e6*I and is multiplied by an
+    exactly-zero masked cross-kernel, :1061);
+  * prediction never materialises the P x N cross-covariance (fused kernels, csrc/gp_predict.cu);
+  * `Xin/Xout`, `Y`, `alpha = K^-1 targets` are computed once per precompute, not per call.
+"""
+from __future__ import annotations
+
+import ctypes
+import time
+from pathlib import Path
+from typing import List, Optional
+
+import numpy as np
+import torch
+
+from . import _cabi
+from ._cabi import TILE, GpModel, check, ptr, stream
+
+
+def to_tensor(input_array, dtype, device):
+    if isinstance(input_array, torch.Tensor):
+        return input_array.to(dtype=dtype, device=device)
+    return torch.tensor(np.asarray(input_array), dtype=dtype, device=device).clone().detach()
+
+
+def _default_device():
+    if not torch.cuda.is_available():
+        raise RuntimeError("gpmdm_b200 needs a CUDA device (B200, sm_100a); there is no CPU path")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _round_up(n: int, m: int) -> int:
+    return (n + m - 1) // m * m
+
+
+# ------------------------------------------------------------------------------------------------
+# CUDA kernel-matrix build with hand-written backward (csrc/train_kernels.cu)
+# ------------------------------------------------------------------------------------------------
+class _KernelBuild(torch.autograd.Function):
+    """K = rbf(X, X; l) [+ lin(X, X; c)] + (sigma_n^2 + sigma_num^2) I, optionally * class mask.
+    forward: gpmdm_kernel_build_f64; backward: gpmdm_kernel_grad_f64 (closed forms)."""
+
+    @staticmethod
+    def forward(ctx, X, log_ls, log_sigma_n, log_lin_coeff, sigma_n_num, class_offsets, flg_noise):
+        lib = _cabi.lib()
+        X = X.contiguous()
+        n, d = X.shape
+        kind = 0 if log_lin_coeff is None else 1
+        ls = torch.exp(log_ls).contiguous()
+        c2 = (torch.exp(log_lin_coeff) ** 2).contiguous() if kind else None
+        sigma2 = float(torch.exp(log_sigma_n) ** 2) if flg_noise else 0.0
+        noise2 = sigma2 + (float(sigma_n_num) ** 2 if flg_noise else 0.0)
+        K = torch.empty(n, n, dtype=X.dtype, device=X.device)
+        ncls = 0 if class_offsets is None else class_offsets.numel() - 1
+        check(lib.gpmdm_kernel_build_f64(ptr(X), n, d, kind, ptr(ls), ptr(c2), noise2, ptr(class_offsets), ncls,
+                                         ptr(K), stream()), "gpmdm_kernel_build_f64")
+        ctx.save_for_backward(X, ls, c2 if kind else X.new_empty(0), class_offsets if ncls else X.new_empty(0))
+        ctx.meta = (kind, sigma2, ncls, log_sigma_n is not None)
+        return K
+
+    @staticmethod
+    def backward(ctx, G):
+        lib = _cabi.lib()
+        X, ls, c2, offs = ctx.saved_tensors
+        kind, sigma2, ncls, _ = ctx.meta
+        n, d = X.shape
+        G = G.contiguous()
+        gX = torch.empty_like(X)
+        g_ls = torch.empty(d, dtype=X.dtype, device=X.device)
+        g_sig = torch.empty((), dtype=X.dtype, device=X.device)
+        g_c = torch.empty(d + 1, dtype=X.dtype, device=X.device) if kind else None
+        ws = torch.empty(lib.gpmdm_kernel_grad_workspace_bytes(n, d) // 8 + 1, dtype=torch.float64, device=X.device)
+        check(lib.gpmdm_kernel_grad_f64(ptr(X), ptr(G), n, d, kind, ptr(ls), ptr(c2) if kind else None, sigma2,
+                                        ptr(offs) if ncls else None, ncls, ptr(gX), ptr(g_ls), ptr(g_sig),
+                                        ptr(g_c) if kind else None, ptr(ws), stream()), "gpmdm_kernel_grad_f64")
+        return gX, g_ls, g_sig, g_c, None, None, None
+
+
+class GPMDM(torch.nn.Module):
+    """Gaussian Process Multi-Dynamical Model (reference gpmdm.py:18), B200-native."""
+
+    def __init__(self, D, d, n_classes, dyn_target, dyn_back_step,
+                 y_lambdas_init, y_lengthscales_init, y_sigma_n_init,
+                 x_lambdas_init, x_lengthscales_init, x_sigma_n_init, x_lin_coeff_init,
+                 flg_train_y_lambdas=True, flg_train_y_lengthscales=True, flg_train_y_sigma_n=True,
+                 flg_train_x_lambdas=True, flg_train_x_lengthscales=True,
+                 flg_train_x_sigma_n=True, flg_train_x_lin_coeff=True,
+                 sigma_n_num_Y=0., sigma_n_num_X=0.,
+                 dtype=torch.float64, device=None):
+        super().__init__()
+        if dtype != torch.float64:
+            raise ValueError("this build implements the fp64 (exact) path only")
+        self.dtype = dtype
+        self.device = torch.device(device) if device is not None else _default_device()
+        if self.device.type != "cuda":
+            raise RuntimeError("gpmdm_b200 needs a CUDA device; there is no CPU path")
+        self.D, self.d, self.n_classes = D, d, n_classes
+        self.dyn_target, self.dyn_back_step = dyn_target, dyn_back_step
+
+        def par(init, flag):
+            return torch.nn.Parameter(torch.log(to_tensor(init, self.dtype, self.device)), requires_grad=flag)
+
+        self.y_log_lengthscales = par(y_lengthscales_init, flg_train_y_lengthscales)
+        self.y_log_lambdas = par(y_lambdas_init, flg_train_y_lambdas)
+        self.y_log_sigma_n = par(y_sigma_n_init, flg_train_y_sigma_n)
+        self.x_log_lengthscales = par(x_lengthscales_init, flg_train_x_lengthscales)
+        self.x_log_lambdas = par(x_lambdas_init, flg_train_x_lambdas)
+        self.x_log_sigma_n = par(x_sigma_n_init, flg_train_x_sigma_n)
+        self.x_log_lin_coeff = par(x_lin_coeff_init, flg_train_x_lin_coeff)
+        self.sigma_n_num_Y = sigma_n_num_Y
+        self.sigma_n_num_X = sigma_n_num_X
+        self.class_aware_observations_list = [[] for _ in range(self.n_classes)]
+        self.meanY = 0
+        self._Y_dev = None
+        self._factors_version = 0
+
+    # ---- modes (gpmdm.py:239-279) ------------------------------------------------------------------
+    def set_evaluation_mode(self):
+        self.flg_trainable_list = []
+        for p in self.parameters():
+            p.requires_grad = False
+
+    def set_training_mode(self, model='all'):
+        y = (self.y_log_lengthscales, self.y_log_lambdas, self.y_log_sigma_n)
+        x = (self.x_log_lengthscales, self.x_log_lambdas, self.x_log_sigma_n, self.x_log_lin_coeff)
+        if model == 'all':
+            for p in self.parameters():
+                p.requires_grad = True
+        elif model == 'latent':
+            for p in y:
+                p.requires_grad = True
+            for p in x:
+                p.requires_grad = False
+        elif model == 'dynamics':
+            for p in y:
+                p.requires_grad = False
+            for p in x:
+                p.requires_grad = True
+        else:
+            raise ValueError('model must be \'all\', \'latent\' or \'dynamics\'')
+
+    # ---- data (gpmdm.py:281-309, 779-815) ----------------------------------------------------------
+    def add_data(self, Y, class_index: int):
+        if Y.shape[1] != self.D:
+            raise ValueError('Y must be a N x D matrix collecting observation data!')
+        self.class_aware_observations_list[class_index].append(Y)
+        self._Y_dev = None
+
+    @property
+    def observations_list(self):
+        return [seq for class_seqs in self.class_aware_observations_list for seq in class_seqs]
+
+    def get_Y(self) -> np.ndarray:
+        observation = np.concatenate(self.observations_list, 0)
+        self.meanY = 0
+        return observation - self.meanY
+
+    def get_Y_for_class(self, class_index: int) -> np.ndarray:
+        observation = np.concatenate(self.class_aware_observations_list[class_index], 0)
+        self.meanY = 0
+        return observation - self.meanY
+
+    def _Y_device(self):
+        if self._Y_dev is None:
+            self._Y_dev = torch.tensor(self.get_Y(), dtype=self.dtype, device=self.device)
+        return self._Y_dev
+
+    # ---- class structure as offsets (replaces get_M / get_M_for_class, gpmdm.py:311-378) -------------
+    def class_frame_offsets(self) -> List[int]:
+        out = [0]
+        for cls in self.class_aware_observations_list:
+            out.append(out[-1] + sum(len(s) for s in cls))
+        return out
+
+    def class_pair_offsets(self, back_step: Optional[int] = None) -> List[int]:
+        b = self.dyn_back_step if back_step is None else back_step
+        out = [0]
+        for cls in self.class_aware_observations_list:
+            out.append(out[-1] + sum(len(s) - b for s in cls))
+        return out
+
+    def _pair_offsets_dev(self):
+        return torch.tensor(self.class_pair_offsets(), dtype=torch.int64, device=self.device)
+
+    def get_M(self):
+        """Dense class mask (gpmdm.py:311-340).  Provided for API parity / small N; unused internally."""
+        offs = self.class_pair_offsets()
+        M = torch.zeros(offs[-1], offs[-1], dtype=self.dtype, device=self.device)
+        for a, b in zip(offs[:-1], offs[1:]):
+            M[a:b, a:b] = 1
+        return M
+
+    def get_M_for_class(self, class_index: int):
+        offs = self.class_pair_offsets()
+        M = torch.zeros(offs[-1], offs[-1], dtype=self.dtype, device=self.device)
+        a, b = offs[class_index], offs[class_index + 1]
+        M[a:b, a:b] = 1
+        return M
+
+    # ---- kernels (gpmdm.py:381-548) ------------------------------------------------------------------
+    def get_y_kernel(self, X1, X2, flg_noise=True):
+        return self.get_rbf_kernel(X1, X2, self.y_log_lengthscales, self.y_log_sigma_n, self.sigma_n_num_Y, flg_noise)
+
+    def get_x_kernel(self, X1, X2, flg_noise=True):
+        if X1 is X2:
+            return _KernelBuild.apply(X1, self.x_log_lengthscales, self.x_log_sigma_n, self.x_log_lin_coeff,
+                                      self.sigma_n_num_X, None, flg_noise)
+        return self.get_rbf_kernel(X1, X2, self.x_log_lengthscales, self.x_log_sigma_n, self.sigma_n_num_X, flg_noise) \
+            + self.get_lin_kernel(X1, X2, self.x_log_lin_coeff)
+
+    def get_rbf_kernel(self, X1, X2, log_lengthscales_par, log_sigma_n_par, sigma_n_num=0, flg_noise=True):
+        if X1 is X2:  # training-side symmetric build: CUDA kernel with hand-written backward
+            return _KernelBuild.apply(X1, log_lengthscales_par, log_sigma_n_par, None, sigma_n_num, None, flg_noise)
+        # rectangular cross-kernels are not on any hot path here (the filter never materialises them);
+        # kept as plain device expressions for API parity with gpmdm.py:474-481
+        K = torch.exp(-self.get_weighted_distances(X1, X2, log_lengthscales_par))
+        if flg_noise:
+            N = X1.shape[0]
+            eye = torch.eye(N, dtype=self.dtype, device=self.device)
+            K = K + torch.exp(log_sigma_n_par) ** 2 * eye + sigma_n_num ** 2 * eye
+        return K
+
+    def get_weighted_distances(self, X1, X2, log_lengthscales_par):
+        lengthscales = torch.exp(log_lengthscales_par)
+        A = X1 / lengthscales
+        A2 = torch.sum(A.mul(A), dim=1, keepdim=True)
+        B = X2 / lengthscales
+        B2 = torch.sum(B.mul(B), dim=1, keepdim=True)
+        return A2 + B2.transpose(0, 1) - 2 * torch.matmul(A, B.transpose(0, 1))
+
+    def get_lin_kernel(self, X1, X2, log_lin_coeff_par):
+        Sigma = torch.diag(torch.exp(log_lin_coeff_par) ** 2)
+        X1 = torch.cat([X1, torch.ones(X1.shape[0], 1, dtype=self.dtype, device=self.device)], 1)
+        X2 = torch.cat([X2, torch.ones(X2.shape[0], 1, dtype=self.dtype, device=self.device)], 1)
+        return torch.matmul(X1, torch.matmul(Sigma, X2.transpose(0, 1)))
+
+    def get_masked_x_kernel(self, Xin):
+        """`get_x_kernel(Xin, Xin) * self.M` (gpmdm.py:616, 1292) without the dense mask."""
+        return _KernelBuild.apply(Xin, self.x_log_lengthscales, self.x_log_sigma_n, self.x_log_lin_coeff,
+                                  self.sigma_n_num_X, self._pair_offsets_dev(), True)
+
+    def get_x_diag_kernel(self, X, flg_noise=False):
+        c2 = torch.exp(self.x_log_lin_coeff) ** 2
+        Xa = torch.cat([X, torch.ones(X.shape[0], 1, dtype=self.dtype, device=self.device)], 1)
+        out = torch.ones(X.shape[0], dtype=self.dtype, device=self.device) + torch.sum((Xa * c2) * Xa, dim=1)
+        if flg_noise:
+            out = out + torch.exp(self.x_log_sigma_n) ** 2 + self.sigma_n_num_X ** 2
+        return out
+
+    def get_y_diag_kernel(self, X, flg_noise=False):
+        out = torch.ones(X.shape[0], dtype=self.dtype, device=self.device)
+        if flg_noise:
+            out = out + torch.exp(self.y_log_sigma_n) ** 2 + self.sigma_n_num_Y ** 2
+        return out
+
+    # ---- NLL (gpmdm.py:550-628, 721-760) --------------------------------------------------------------
+    @staticmethod
+    def _logdet_and_trace(K, T):
+        """log det K and tr(K^-1 T T^T) through one upper Cholesky factor (torch.linalg / cuSOLVER)."""
+        U, _info = torch.linalg.cholesky_ex(K, upper=True)
+        logdet = 2 * torch.sum(torch.log(torch.diagonal(U)))
+        Z = torch.linalg.solve_triangular(U.transpose(0, 1), T, upper=False)  # U^-T T
+        return logdet, torch.sum(Z * Z)
+
+    def get_y_neg_log_likelihood(self, Y, X, N):
+        K_y = self.get_y_kernel(X, X)
+        logdet, tr = self._logdet_and_trace(K_y, Y * torch.exp(self.y_log_lambdas))
+        log_det_W = 2 * torch.sum(self.y_log_lambdas)
+        return self.D / 2 * logdet + 1 / 2 * tr - N * log_det_W
+
+    def get_x_neg_log_likelihood(self, Xout, Xin):
+        K_x = self.get_masked_x_kernel(Xin)
+        logdet, tr = self._logdet_and_trace(K_x, Xout * torch.exp(self.x_log_lambdas))
+        log_det_W = 2 * torch.sum(self.x_log_lambdas)
+        return self.d / 2 * logdet + 1 / 2 * tr - Xin.shape[0] * log_det_W
+
+    def _pair_index(self, target=None, back_step=None):
+        """Row indices realising `get_Xin_Xout_matrices` (gpmdm.py:630-718) as gathers."""
+        target = self.dyn_target if target is None else target
+        b = self.dyn_back_step if back_step is None else back_step
+        if target not in ('full', 'delta') or b not in (1, 2):
+            raise ValueError('target must be either \'full\' or \'delta\' \n back_step must be either 1 or 2')
+        idx_in, idx_prev, idx_out, starts, s = [], [], [], [], 0
+        for seq in self.observations_list:
+            L = seq.shape[0]
+            starts.append(s)
+            r = np.arange(s + b - 1, s + L - 1)
+            idx_in.append(r)
+            idx_prev.append(r - 1)
+            idx_out.append(r + 1)
+            s += L
+        cat = lambda v: torch.as_tensor(np.concatenate(v), device=self.device)
+        return cat(idx_in), cat(idx_prev), cat(idx_out), starts, target, b
+
+    def get_Xin_Xout_matrices(self, X=None, target=None, back_step=None):
+        if X is None:
+            X = self.X
+        i_in, i_prev, i_out, starts, target, b = self._pair_index(target, back_step)
+        Xin = X[i_in] if b == 1 else torch.cat((X[i_in], X[i_prev]), 1)
+        Xout = X[i_out] if target == 'full' else X[i_out] - X[i_in]
+        return Xin, Xout, starts
+
+    def gpdm_loss(self, Y, N, M=None, balance=1):
+        Xin, Xout, _ = self.get_Xin_Xout_matrices()
+        lossY = self.get_y_neg_log_likelihood(Y, self.X, N)
+        lossX = self.get_x_neg_log_likelihood(Xout, Xin)
+        return lossY + balance * lossX
+
+    # ---- init / train (gpmdm.py:762-885) ---------------------------------------------------------------
+    def init_X(self):
+        from sklearn.decomposition import PCA
+
+        Y = self.get_Y()
+        X0 = PCA(n_components=self.d).fit_transform(Y)
+        self._precompute_class_matrices()
+        self.X = torch.nn.Parameter(torch.tensor(X0, dtype=self.dtype, device=self.device), requires_grad=True)
+        self._precompute_kernel_inverses()
+
+    def train_adam(self, num_opt_steps, num_print_steps=0, lr=0.01, balance=1):
+        if num_print_steps != 0:
+            print('\n### Model Training (Adam) ###')
+        Y = self._Y_device()
+        N = Y.shape[0]
+        self.set_training_mode('all')
+        optimizer = torch.optim.Adam(self.parameters(), lr=lr)
+        t_start = time.time()
+        losses = []
+        for epoch in range(num_opt_steps):
+            optimizer.zero_grad()
+            # NB the reference passes `balance` in the position of the unused `M` argument
+            # (gpmdm.py:866 vs :721-726), so its balance is always 1; reproduced.
+            loss = self.gpdm_loss(Y, N, balance)
+            loss.backward()
+            if torch.isnan(loss):
+                print('Loss is nan')
+                break
+            optimizer.step()
+            losses.append(loss.item())
+            if (num_print_steps != 0) and epoch % num_print_steps == 0:
+                print('\nGPDM Opt. EPOCH:', epoch)
+                print('Running loss:', "{:.4e}".format(loss.item()))
+                t_stop = time.time()
+                print('Update time:', t_stop - t_start)
+                t_start = t_stop
+        self._precompute_kernel_inverses()
+        return losses
+
+    def get_latent_sequences(self):
+        X_np = self.X.clone().detach().cpu().numpy()
+        out, s = [], 0
+        for seq in self.observations_list:
+            out.append(X_np[s:s + seq.shape[0], :])
+            s += seq.shape[0]
+        return out
+
+    def get_X_for_class(self, class_index: int):
+        offs = self.class_frame_offsets()
+        return self.X[offs[class_index]:offs[class_index + 1], :]
+
+    # ---- precompute (gpmdm.py:1275-1305) -----------------------------------------------------------------
+    def _precompute_class_matrices(self):
+        # the reference builds C+1 dense Nx x Nx masks here; offsets carry the same information
+        self.class_offsets = self.class_pair_offsets()
+
+    @staticmethod
+    def _inverse_via_upper_cholesky(K):
+        """U = chol_upper(K); K^-1 = U^-1 U^-T (gpmdm.py:1287-1289), with a triangular solve for U^-1."""
+        U, _info = torch.linalg.cholesky_ex(K, upper=True)
+        eye = torch.eye(K.shape[0], dtype=K.dtype, device=K.device)
+        U_inv = torch.linalg.solve_triangular(U, eye, upper=True)
+        return torch.matmul(U_inv, U_inv.t())
+
+    @torch.no_grad()
+    def _precompute_kernel_inverses(self):
+        """Ky_inv, per-class Kx_inv_class[c] (N_c x N_c blocks) and the alpha vectors.  The reference's
+        dense `Kx_inv` (:1291-1295) is only used by the class-agnostic `map_x_dynamics`, which the filter
+        never calls; it is built lazily by `Kx_inv` below."""
+        X = self.X.detach()
+        self.Ky_inv = self._inverse_via_upper_cholesky(self.get_y_kernel(X, X))
+        Xin, Xout, _ = self.get_Xin_Xout_matrices(X)
+        self._Xin, self._Xout = Xin.contiguous(), Xout.contiguous()
+        self.Kx_inv_class = []
+        offs = self.class_pair_offsets()
+        for c in range(self.n_classes):
+            a, b = offs[c], offs[c + 1]
+            Xc = Xin[a:b].contiguous()
+            Kc = _KernelBuild.apply(Xc, self.x_log_lengthscales, self.x_log_sigma_n, self.x_log_lin_coeff,
+                                    self.sigma_n_num_X, None, True)
+            Kc = Kc + 1e-6 * torch.eye(b - a, dtype=self.dtype, device=self.device)  # gpmdm.py:1302
+            self.Kx_inv_class.append(self._inverse_via_upper_cholesky(Kc))
+        self._Kx_inv_full = None
+        self._factors_version += 1
+        self._packed = None
+
+    @property
+    def Kx_inv(self):
+        if getattr(self, "_Kx_inv_full", None) is None:
+            with torch.no_grad():
+                self._Kx_inv_full = self._inverse_via_upper_cholesky(self.get_masked_x_kernel(self._Xin))
+        return self._Kx_inv_full
+
+    def set_inverses(self, Ky_inv=None, Kx_inv_blocks=None):
+        """Inject precomputed inverses (e.g. the reference's own `Ky_inv` and the diagonal blocks of its
+        `Kx_inv_class[c]`) -- used by the parity tests to compare kernels on identical factors."""
+        if Ky_inv is not None:
+            self.Ky_inv = to_tensor(Ky_inv, self.dtype, self.device).contiguous()
+        if Kx_inv_blocks is not None:
+            self.Kx_inv_class = [to_tensor(b, self.dtype, self.device).contiguous() for b in Kx_inv_blocks]
+        self._factors_version += 1
+        self._packed = None
+
+    # ---- packing for the fused predict kernels ---------------------------------------------------------------
+    def _pack_block(self, Xtrain, log_ls, Kinv, targets, alpha_ld, lin_c2, tri):
+        lib = _cabi.lib()
+        n, d = Xtrain.shape
+        n_pad = _round_up(n, TILE)
+        a = Xtrain / torch.exp(log_ls)
+        cols = [2.0 * a, -torch.sum(a * a, dim=1, keepdim=True)]
+        if lin_c2 is not None:
+            cols.append(Xtrain * lin_c2[:d])
+        rec = torch.cat(cols, 1)
+        coords = torch.zeros(n_pad, rec.shape[1], dtype=self.dtype, device=self.device)
+        coords[:n] = rec
+        L = torch.empty(n_pad, n_pad, dtype=self.dtype, device=self.device)
+        Kinv = Kinv.contiguous()
+        check(lib.gpmdm_pack_quadform_f64(ptr(Kinv), n, n_pad, int(tri), ptr(L), stream()), "gpmdm_pack_quadform_f64")
+        alpha = torch.zeros(n_pad, alpha_ld, dtype=self.dtype, device=self.device)
+        alpha[:n, :targets.shape[1]] = torch.matmul(Kinv.t(), targets)
+        return dict(coords=coords, L=L, alpha=alpha, n=n, n_pad=n_pad)
+
+    @torch.no_grad()
+    def packed_models(self, tri: bool = True):
+        """Device-resident operands of the fused kernels (include/gpmdm_b200.h: gpmdm_gp_model)."""
+        if getattr(self, "_packed", None) is not None and self._packed["tri"] == tri:
+            return self._packed
+        X = self.X.detach()
+        dev = self.device
+        keep = []  # tensors that must outlive the C structs
+
+        def model(blocks, d, dout, alpha_ld, kind, ls, c2, lam):
+            table = torch.tensor([[b["coords"].data_ptr(), b["L"].data_ptr(), b["alpha"].data_ptr(), b["n"], b["n_pad"]]
+                                  for b in blocks], dtype=torch.int64, device=dev)
+            keep.extend([table, ls, c2, lam, blocks])
+            return GpModel(blocks=table.data_ptr(), n_blocks=len(blocks), d=d, dout=dout, alpha_ld=alpha_ld, kind=kind,
+                           tri=int(tri), lengthscales=ls.data_ptr(), lin_c2=c2.data_ptr() if c2 is not None else None,
+                           lambdas=lam.data_ptr())
+
+        # observation GP: one block over all frames
+        ald_y = _round_up(self.D, TILE)
+        oblk = self._pack_block(X, self.y_log_lengthscales.detach(), self.Ky_inv, self._Y_device(), ald_y, None, tri)
+        ls_y = torch.exp(self.y_log_lengthscales.detach()).contiguous()
+        lam2_y = (torch.exp(self.y_log_lambdas.detach()) ** 2).contiguous()
+        obs = model([oblk], self.d, self.D, ald_y, 0, ls_y, None, lam2_y)
+        # dynamics GP: one block per class ('full', back_step 1 -- the only mode the filter supports)
+        Xin, Xout = self._Xin, self._Xout
+        if self.dyn_back_step == 1:
+            c2 = (torch.exp(self.x_log_lin_coeff.detach()) ** 2).contiguous()
+            ls_x = torch.exp(self.x_log_lengthscales.detach()).contiguous()
+            lam_x = (torch.exp(self.x_log_lambdas.detach()) ** -2).contiguous()
+            offs = self.class_pair_offsets()
+            dblks = [self._pack_block(Xin[offs[c]:offs[c + 1]], self.x_log_lengthscales.detach(), self.Kx_inv_class[c],
+                                      Xout[offs[c]:offs[c + 1]], TILE, c2, tri) for c in range(self.n_classes)]
+            dyn = model(dblks, self.d, self.d, TILE, 1, ls_x, c2, lam_x)
+        else:
+            dyn = None
+        self._packed = dict(tri=tri, obs=obs, dyn=dyn, keep=keep,
+                            ll_const_terms=(2.0 * torch.sum(self.y_log_lambdas.detach())).item())
+        return self._packed
+
+    # ---- prediction (gpmdm.py:923-963, 1032-1068) ----------------------------------------------------------
+    def _scratch_counter(self):
+        if getattr(self, "_counter", None) is None:
+            self._counter = torch.zeros(1, dtype=torch.int32, device=self.device)
+        return self._counter
+
+    @torch.no_grad()
+    def map_x_to_y(self, Xstar, flg_noise=False):
+        lib = _cabi.lib()
+        pk = self.packed_models()
+        Xs = to_tensor(Xstar, self.dtype, self.device).contiguous()
+        P = Xs.shape[0]
+        mu = torch.empty(P, self.D, dtype=self.dtype, device=self.device)
+        v = torch.empty(P, dtype=self.dtype, device=self.device)
+        check(lib.gpmdm_pf_observe_f64(ctypes.byref(pk["obs"]), ptr(Xs), P, None, 0.0, None, ptr(mu), ptr(v),
+                                       ptr(self._scratch_counter()), stream()), "gpmdm_pf_observe_f64")
+        if flg_noise:
+            v = v + torch.exp(self.y_log_sigma_n) ** 2 + self.sigma_n_num_Y ** 2
+        var = v.unsqueeze(1) * (torch.exp(self.y_log_lambdas) ** -2).unsqueeze(0)
+        return mu + torch.tensor(self.meanY, dtype=self.dtype, device=self.device), var
+
+    @torch.no_grad()
+    def map_x_dynamics_for_class(self, Xstar, class_index: int, flg_noise=False):
+        lib = _cabi.lib()
+        pk = self.packed_models()
+        if pk["dyn"] is None:
+            raise ValueError("fused dynamics prediction supports dyn_back_step == 1 only")
+        Xs = to_tensor(Xstar, self.dtype, self.device).contiguous()
+        P = Xs.shape[0]
+        mean = torch.empty(P, self.d, dtype=self.dtype, device=self.device)
+        var = torch.empty(P, self.d, dtype=self.dtype, device=self.device)
+        if P == 0:
+            return mean, var
+        perm = torch.arange(P, dtype=torch.int32, device=self.device)
+        nt = (P + TILE - 1) // TILE
+        t = torch.arange(nt, dtype=torch.int32, device=self.device)
+        tiles = torch.stack([torch.full_like(t, class_index), t * TILE, torch.clamp(P - t * TILE, max=TILE),
+                             torch.zeros_like(t)], 1).contiguous()
+        n_tiles = torch.tensor([nt], dtype=torch.int32, device=self.device)
+        check(lib.gpmdm_pf_propagate_f64(ctypes.byref(pk["dyn"]), ptr(Xs), ptr(perm), ptr(tiles), ptr(n_tiles), P, None,
+                                         None, ptr(mean), ptr(var), ptr(self._scratch_counter()), stream()),
+              "gpmdm_pf_propagate_f64")
+        if flg_noise:
+            var = var + (torch.exp(self.x_log_sigma_n) ** 2 + self.sigma_n_num_X ** 2) \
+                * (torch.exp(self.x_log_lambdas) ** -2).unsqueeze(0)
+        return mean, var
+
+    # ---- save / load (gpmdm.py:1307-1414); same on-disk format ---------------------------------------------------
+    def save(self, file_path):
+        config_dict = {
+            'class_aware_observations_list': self.class_aware_observations_list,
+            'dyn_target': self.dyn_target, 'dyn_back_step': self.dyn_back_step,
+            'D': self.D, 'd': self.d, 'n_classes': self.n_classes,
+            'sigma_n_num_X': self.sigma_n_num_X, 'sigma_n_num_Y': self.sigma_n_num_Y,
+            'dtype': str(self.dtype), 'device': str(self.device),
+            'y_lengthscales_init': self.y_log_lengthscales.detach().exp().tolist(),
+            'y_lambdas_init': self.y_log_lambdas.detach().exp().tolist(),
+            'y_sigma_n_init': self.y_log_sigma_n.detach().exp().item(),
+            'x_lengthscales_init': self.x_log_lengthscales.detach().exp().tolist(),
+            'x_lambdas_init': self.x_log_lambdas.detach().exp().tolist(),
+            'x_sigma_n_init': self.x_log_sigma_n.detach().exp().item(),
+            'x_lin_coeff_init': self.x_log_lin_coeff.detach().exp().tolist(),
+        }
+        state = {k: v.detach().cpu() for k, v in self.state_dict().items()}
+        torch.save({'state_dict': state, 'config_dict': config_dict}, file_path)
+        print(f"Model and hyperparameters saved to {file_path}")
+
+    @classmethod
+    def load(cls, file_path, flg_print: bool = False, device=None) -> 'GPMDM':
+        # weights_only=False: the config holds numpy arrays (the reference's plain torch.load fails on torch>=2.6)
+        save_dict = torch.load(file_path, weights_only=False, map_location="cpu")
+        cfg, state_dict = save_dict['config_dict'], save_dict['state_dict']
+        dtype = cfg['dtype'][6:] if cfg['dtype'].startswith('torch.') else cfg['dtype']
+        model = cls(
+            D=cfg['D'], d=cfg['d'], n_classes=cfg['n_classes'], dyn_target=cfg['dyn_target'],
+            dyn_back_step=cfg['dyn_back_step'],
+            y_lambdas_init=torch.tensor(cfg['y_lambdas_init']), y_lengthscales_init=torch.tensor(cfg['y_lengthscales_init']),
+            y_sigma_n_init=cfg['y_sigma_n_init'], x_lambdas_init=torch.tensor(cfg['x_lambdas_init']),
+            x_lengthscales_init=torch.tensor(cfg['x_lengthscales_init']), x_sigma_n_init=cfg['x_sigma_n_init'],
+            x_lin_coeff_init=torch.tensor(cfg['x_lin_coeff_init']),
+            sigma_n_num_X=cfg['sigma_n_num_X'], sigma_n_num_Y=cfg['sigma_n_num_Y'],
+            dtype=getattr(torch, dtype), device=device)  # files written on 'cpu' load onto the CUDA device
+        model.class_aware_observations_list = cfg['class_aware_observations_list']
+        model.init_X()
+        model.load_state_dict(state_dict)
+        model._precompute_kernel_inverses()
+        print("\nModel and hyperparameters correctly loaded")
+        if flg_print:
+            print("Loaded params:")
+            for name, val in model.state_dict().items():
+                print(name, "\t", val)
+        return model

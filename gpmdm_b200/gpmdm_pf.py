@@ -1,0 +1,262 @@
+"""`GPMDM_PF` -- the particle filter of the reference (`gpmdm/gpmdm_pf.py`) with the same constructor
+and step API, every stage of `update(z)` running as CUDA kernels of libgpmdm_sm100a.so.
+
+Reference surface kept (file:line of the reference): ctor :47-85 | update :117 | log_likelihood :215 |
+class_probabilities :224 | get_most_likely_class :250 | current_state_mean :256 | reset :264 |
+properties :267-285 | state attributes `_particle_states`, `_particle_classes`, `_log_weights`,
+`_weights`, `_log_likelihoods` :78-82.
+
+Step pipeline (all asynchronous on the current CUDA stream, no host synchronisation inside):
+    draws (Philox on device, or injected)            gpmdm_pf_draws_philox
+    class transition                                 gpmdm_pf_transition_f64      gpmdm_pf.py:137-151
+    bucket particles by class                        gpmdm_pf_bucket_by_class     gpmdm_pf.py:161
+    dynamics GP + draw  (DMMA, fused)                gpmdm_pf_propagate_f64       gpmdm_pf.py:153-168
+    observation GP + log-likelihood (DMMA, fused)    gpmdm_pf_observe_f64         gpmdm_pf.py:170-192
+    [G > 1: all-gather of (x', c', ll) over NCCL]
+    normalise weights                                gpmdm_pf_normalize_f64       gpmdm_pf.py:200-204
+    cdf + resampling search + gather                 gpmdm_pf_cdf/resample_f64    gpmdm_pf.py:206-213
+    class posteriors / state mean (on demand)        gpmdm_pf_summaries_f64       gpmdm_pf.py:215-262
+
+Randomness.  The reference draws from torch's global CPU generator.  Here the raw draws are explicit:
+`update(z)` generates them on the device with Philox keyed by (seed, step, global particle index), and
+`update(z, draws=(E, eps, u))` consumes caller-supplied draws with exactly the semantics torch's CPU
+samplers have -- the parity tests inject the same arrays into the reference.
+
+Multi-GPU.  With `torch.distributed` initialised (one process per GPU, NCCL) particles are sharded by
+contiguous index range; factors are replicated.  The one exchange per step is an all-gather of the
+per-particle (state, class, log-likelihood) records; every rank then runs the same fixed-order
+normalise / cdf / search over all P particles, so a G-GPU run equals the 1-GPU run bit for bit.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _cabi
+from ._cabi import check, ptr, stream
+from .gpmdm import GPMDM
+
+_LOG_2PI = torch.log(torch.tensor(2 * 3.14159265358979323846))  # float32, as gpmdm_pf.py:5
+
+
+class GPMDM_PF:
+    """GPMDM particle filter (reference gpmdm_pf.py:7), B200-native."""
+
+    def __init__(self, gpmdm: GPMDM, markov_switching_model, num_particles: int, *,
+                 seed: int = 0, resampling: str = "multinomial", cdf_order: str = "sequential",
+                 tri: bool = True, init_indices: Optional[Sequence] = None, process_group=None,
+                 distributed: Optional[bool] = None):
+        """
+        gpmdm, markov_switching_model [C, C], num_particles: as the reference (:47-50).
+        seed            Philox key for device-side draws (the reference has no seed argument)
+        resampling      'multinomial' (reference, :211) or 'systematic' (one uniform, comb of P points)
+        cdf_order       'sequential' = the reference's running sum, bit-identical cdf; 'blocked' = parallel
+                        scan in fixed 1024-element blocks
+        tri             use the triangular packing of K^-1 (half the flops of the dense quadratic form)
+        init_indices    optional per-class index tensors replacing torch.randint in _init_particles (:113)
+        """
+        self._lib = _cabi.lib()
+        self._gpmdm = gpmdm
+        self._gpmdm.set_evaluation_mode()
+        self._markov_switching_model = torch.as_tensor(markov_switching_model).type(self.dtype).to(self.device).contiguous()
+        self._num_particles = int(num_particles)
+        if self._gpmdm.n_classes != self._markov_switching_model.size(0):
+            raise ValueError("Number of classes in the GPMDM model and the Markov model do not match")
+        if resampling not in ("multinomial", "systematic"):
+            raise ValueError("resampling must be 'multinomial' or 'systematic'")
+        if cdf_order not in ("sequential", "blocked"):
+            raise ValueError("cdf_order must be 'sequential' or 'blocked'")
+        if gpmdm.dyn_back_step != 1:
+            raise ValueError("the particle filter uses the dynamics GP output as the next state: dyn_back_step must be 1")
+        self._seed, self._step = int(seed), 0
+        self._systematic = resampling == "systematic"
+        self._cdf_mode = 0 if cdf_order == "sequential" else 1
+        self._tri = bool(tri)
+
+        # one process per GPU; contiguous particle ranges
+        import torch.distributed as dist
+        use_dist = dist.is_available() and dist.is_initialized() if distributed is None else distributed
+        self._pg = process_group
+        self._world = dist.get_world_size(process_group) if use_dist else 1
+        self._rank = dist.get_rank(process_group) if use_dist else 0
+        P, G = self._num_particles, self._world
+        if P % G != 0:
+            raise ValueError(f"num_particles ({P}) must be divisible by the number of ranks ({G})")
+        self._lo, self._hi = self._rank * (P // G), (self._rank + 1) * (P // G)
+
+        self._packed = gpmdm.packed_models(self._tri)
+        c32 = float(0.5 * self._gpmdm.D * _LOG_2PI)  # fp32 product, as gpmdm_pf.py:191
+        self._ll_const = self._packed["ll_const_terms"] - c32
+        self._alloc()
+        self._init_particles(init_indices)
+
+    # ---- buffers ------------------------------------------------------------------------------------------
+    def _alloc(self):
+        P, d, C, dev, f64 = self._num_particles, self.latent_dim, self.num_classes, self.device, self.dtype
+        Pl = self._hi - self._lo
+        e = lambda *s, dt=f64: torch.empty(*s, dtype=dt, device=dev)
+        self._x_new, self._c_new, self._ll_all = e(P, d), e(P, dt=torch.int64), e(P)
+        self._cdf, self._anc = e(P), e(P, dt=torch.int64)
+        self._states_alt, self._classes_alt = e(P, d), e(P, dt=torch.int64)
+        self._perm, self._tiles = e(Pl, dt=torch.int32), e(Pl // _cabi.TILE + C + 1, 4, dt=torch.int32)
+        self._n_tiles, self._counter = e(1, dt=torch.int32), torch.zeros(1, dtype=torch.int32, device=dev)
+        self._E, self._eps, self._u = e(Pl, C), e(Pl, d), e(P)
+        self._stats = e(2)
+        self._summary = e(C + d + 1)
+        self._summary_step = -1
+        ws = int(self._lib.gpmdm_workspace_bytes(P, C))
+        self._ws = torch.empty(ws // 8 + 1, dtype=torch.float64, device=dev)
+
+    # ---- initialisation (gpmdm_pf.py:87-115) -------------------------------------------------------------------
+    def _init_particles(self, init_indices=None):
+        P, C = self._num_particles, self.num_classes
+        n_per_class = self._divide_into_n_parts(P, C)
+        parts, classes = [], []
+        for i in range(C):
+            class_data = self._gpmdm.get_X_for_class(i)
+            if init_indices is not None:
+                idx = torch.as_tensor(init_indices[i]).to(self.device)
+                if idx.numel() != n_per_class[i]:
+                    raise ValueError("init_indices[%d] must hold %d indices" % (i, n_per_class[i]))
+            else:
+                idx = torch.randint(0, class_data.size(0), (n_per_class[i],), device=self.device)
+            parts.append(class_data[idx].detach().clone())
+            classes += [i] * n_per_class[i]
+        self._particle_states = torch.cat(parts, dim=0).contiguous()
+        self._particle_classes = torch.tensor(classes, dtype=torch.int64, device=self.device)
+        self._log_likelihoods = torch.zeros(P, dtype=self.dtype, device=self.device)
+        self._log_weights = torch.zeros(P, dtype=self.dtype, device=self.device)
+        self._weights = torch.ones(P, dtype=self.dtype, device=self.device) / P
+        self._summary_step = -1
+
+    # ---- the filter step (gpmdm_pf.py:117-135) -----------------------------------------------------------------
+    def update(self, z, draws=None):
+        """Update the particle filter with a new observation z [D] (numpy / sequence / tensor).
+        draws: optional (E [P,C] Exp(1), eps [P,d] N(0,1), u [P] U(0,1)) raw draws for ALL particles."""
+        z = torch.as_tensor(np.asarray(z) if not isinstance(z, torch.Tensor) else z).to(device=self.device, dtype=self.dtype)
+        self._update(z.contiguous(), draws)
+
+    def _update(self, z, draws=None):
+        lib, st = self._lib, stream()
+        P, d, C = self._num_particles, self.latent_dim, self.num_classes
+        lo, hi = self._lo, self._hi
+        Pl = hi - lo
+        if z.numel() != self.observation_dim:
+            raise ValueError("z must have D = %d entries" % self.observation_dim)
+        # -- raw draws
+        if draws is None:
+            check(lib.gpmdm_pf_draws_philox(self._seed, self._step, lo, Pl, P, C, d, 0, ptr(self._E), ptr(self._eps),
+                                            None, st), "gpmdm_pf_draws_philox")
+            check(lib.gpmdm_pf_draws_philox(self._seed, self._step, 0, P, P, C, d, int(self._systematic), None, None,
+                                            ptr(self._u), st), "gpmdm_pf_draws_philox")
+            E, eps, u = self._E, self._eps, self._u
+        else:
+            E, eps, u = (torch.as_tensor(a).to(device=self.device, dtype=self.dtype) for a in draws)
+            if E.shape != (P, C) or eps.shape != (P, d) or u.shape != (P,):
+                raise ValueError("draws must be (E [P,C], eps [P,d], u [P])")
+            E, eps, u = E[lo:hi].contiguous(), eps[lo:hi].contiguous(), u.contiguous()
+        x_prev = self._particle_states[lo:hi]
+        c_prev = self._particle_classes[lo:hi]
+        x_new_l, c_new_l, ll_l = self._x_new[lo:hi], self._c_new[lo:hi], self._ll_all[lo:hi]
+        # -- class transition, bucketing, dynamics draw, observation likelihood (local particles)
+        check(lib.gpmdm_pf_transition_f64(ptr(c_prev), ptr(self._markov_switching_model), ptr(E), Pl, C, ptr(c_new_l), st),
+              "gpmdm_pf_transition_f64")
+        check(lib.gpmdm_pf_bucket_by_class(ptr(c_new_l), Pl, C, ptr(self._perm), ptr(self._tiles), ptr(self._n_tiles),
+                                           ptr(self._ws), st), "gpmdm_pf_bucket_by_class")
+        check(lib.gpmdm_pf_propagate_f64(ctypes.byref(self._packed["dyn"]), ptr(x_prev), ptr(self._perm), ptr(self._tiles),
+                                         ptr(self._n_tiles), Pl, ptr(eps), ptr(x_new_l), None, None, ptr(self._counter),
+                                         st), "gpmdm_pf_propagate_f64")
+        check(lib.gpmdm_pf_observe_f64(ctypes.byref(self._packed["obs"]), ptr(x_new_l), Pl, ptr(z), self._ll_const,
+                                       ptr(ll_l), None, None, ptr(self._counter), st), "gpmdm_pf_observe_f64")
+        # -- the one exchange step: every rank gets every particle's (x', c', ll)
+        if self._world > 1:
+            import torch.distributed as dist
+            dist.all_gather_into_tensor(self._ll_all, ll_l.clone(), group=self._pg)
+            dist.all_gather_into_tensor(self._x_new, x_new_l.clone(), group=self._pg)
+            dist.all_gather_into_tensor(self._c_new, c_new_l.clone(), group=self._pg)
+        # -- weights, cdf, resampling over all P particles (fixed order => identical on every rank)
+        ll_new, lw_new, w_new = self._ll_all, self._log_weights_buf(), self._weights_buf()
+        check(lib.gpmdm_pf_normalize_f64(ptr(ll_new), P, ptr(lw_new), ptr(w_new), ptr(self._stats), ptr(self._ws), st),
+              "gpmdm_pf_normalize_f64")
+        check(lib.gpmdm_pf_cdf_f64(ptr(w_new), P, self._cdf_mode, ptr(self._cdf), ptr(self._ws), st), "gpmdm_pf_cdf_f64")
+        check(lib.gpmdm_pf_resample_f64(ptr(self._cdf), P, ptr(u), P, ptr(self._x_new), ptr(self._c_new), d,
+                                        ptr(self._anc), ptr(self._states_alt), ptr(self._classes_alt), st),
+              "gpmdm_pf_resample_f64")
+        # publish (swap buffers; no copies)
+        self._particle_states, self._states_alt = self._states_alt, self._particle_states
+        self._particle_classes, self._classes_alt = self._classes_alt, self._particle_classes
+        self._log_likelihoods = ll_new.clone()
+        self._log_weights, self._weights = lw_new, w_new
+        self._step += 1
+
+    def _log_weights_buf(self):
+        return torch.empty(self._num_particles, dtype=self.dtype, device=self.device)
+
+    _weights_buf = _log_weights_buf
+
+    # ---- queries (gpmdm_pf.py:215-262) ---------------------------------------------------------------------------
+    def _summaries(self):
+        if self._summary_step != self._step:
+            check(self._lib.gpmdm_pf_summaries_f64(ptr(self._log_likelihoods), ptr(self._log_weights), ptr(self._weights),
+                                                   ptr(self._particle_classes), ptr(self._particle_states),
+                                                   self._num_particles, self.num_classes, self.latent_dim,
+                                                   ptr(self._summary), ptr(self._ws), stream()), "gpmdm_pf_summaries_f64")
+            self._summary_step = self._step
+        return self._summary
+
+    def log_likelihood(self) -> float:
+        return self._summaries()[self.num_classes + self.latent_dim].item()
+
+    def class_probabilities(self):
+        return self._summaries()[:self.num_classes].clone()
+
+    def get_most_likely_class(self) -> int:
+        return torch.argmax(self.class_probabilities()).item()
+
+    def current_state_mean(self):
+        C = self.num_classes
+        return self._summaries()[C:C + self.latent_dim].clone()
+
+    def reset(self):
+        self._init_particles()
+
+    # ---- stage outputs of the last step (for tests / diagnostics) ------------------------------------------------
+    @property
+    def last_ancestors(self):
+        return self._anc
+
+    @property
+    def last_pre_resample_states(self):
+        return self._x_new
+
+    @property
+    def last_pre_resample_classes(self):
+        return self._c_new
+
+    # ---- properties (gpmdm_pf.py:267-285) ----------------------------------------------------------------------
+    @property
+    def latent_dim(self):
+        return self._gpmdm.d
+
+    @property
+    def observation_dim(self):
+        return self._gpmdm.D
+
+    @property
+    def num_classes(self):
+        return self._gpmdm.n_classes
+
+    @property
+    def dtype(self):
+        return self._gpmdm.dtype
+
+    @property
+    def device(self):
+        return self._gpmdm.device
+
+    def _divide_into_n_parts(self, x: int, n: int):
+        group, remainder = divmod(x, n)
+        return [group + (1 if i < remainder else 0) for i in range(n)]

@@ -1,0 +1,181 @@
+/*
+ * gpmdm_b200.h -- C ABI of libgpmdm_sm100a.so: the GPMDM particle-filter step and the GP kernel
+ * machinery beneath it, as hand-written CUDA for NVIDIA B200 (sm_100a).
+ *
+ * The reference (Priyanshu4/gpmdm) is pure Python on torch and has no FFI; the boundary these entry
+ * points replace is the body of the Python methods cited on each function (paths relative to the
+ * reference root).  The host side (gpmdm_b200/gpmdm_pf.py, gpmdm_b200/gpmdm.py) keeps the reference's
+ * class surface and binds this library with ctypes.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host; arrays are dense row-major;
+ *     sizes are int64_t; floating point is IEEE binary64; class ids / ancestors are int64 (as the
+ *     reference's torch.int64 tensors, gpmdm_pf.py:101,211).
+ *   - calls are asynchronous on `stream` (a cudaStream_t passed as void*); the library never
+ *     synchronises, allocates or keeps references to caller memory.  Scratch comes from the caller
+ *     (`workspace`, size from gpmdm_workspace_bytes()).
+ *   - return value: 0 ok; <0 invalid argument (GPMDM_E_*); >0 a cudaError_t.  gpmdm_last_error()
+ *     returns a thread-local message for the last non-zero return.  No exceptions cross the ABI.
+ *   - there is no CPU implementation behind any entry point.
+ */
+#ifndef GPMDM_B200_H_
+#define GPMDM_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GPMDM_ABI_VERSION 1
+
+#define GPMDM_E_INVALID (-1)     /* bad size / null pointer / unsupported dimension            */
+#define GPMDM_E_UNSUPPORTED (-2) /* valid request outside this build's limits (d > 8, ...)      */
+#define GPMDM_E_NODEVICE (-3)    /* no sm_100 device                                            */
+
+#define GPMDM_TILE 128     /* particle-tile height, column-tile width and row padding of factors */
+#define GPMDM_MAX_LATENT 8 /* latent dimension limit of the kernels                             */
+
+/* One GP "block": the observation GP is a single block over all N training frames; the dynamics GP
+ * has one block per class over that class' N_c (x_t -> x_t+1) pairs -- the block-diagonal structure
+ * the reference expresses with dense 0/1 masks (gpmdm.py:311-378, 1299-1305).
+ *
+ *   coords [n_pad, rec]  per training row i:  2*a_i[0..d) , -|a_i|^2 , (dynamics only) c_k^2 * x_i[k]
+ *                        with a_i = x_i / lengthscale  (gpmdm.py:508-517, 545-548); zero rows pad.
+ *   L      [n_pad, n_pad] quadratic-form matrix such that  k^T K^-1 k == k^T L k :
+ *                        tri = 1:  L[i][j] = Kinv[i][j] + Kinv[j][i] (i > j), Kinv[i][i], 0 (i < j)
+ *                        tri = 0:  L = Kinv.   Zero padded.  (written by gpmdm_pack_quadform_f64)
+ *   alpha  [n_pad, alpha_ld] = Kinv^T * targets (Y for the observation GP, Xout_c for dynamics),
+ *                        zero padded to alpha_ld = multiple of GPMDM_TILE columns.
+ */
+typedef struct gpmdm_gp_block {
+    const double* coords;
+    const double* L;
+    const double* alpha;
+    int64_t n;     /* real training rows of the block            */
+    int64_t n_pad; /* rows padded to a multiple of GPMDM_TILE    */
+} gpmdm_gp_block;
+
+/* A GP model as consumed by the predict kernels.  `blocks` is a DEVICE array of n_blocks structs. */
+typedef struct gpmdm_gp_model {
+    const gpmdm_gp_block* blocks; /* device */
+    int32_t n_blocks;
+    int32_t d;        /* latent dimension (<= GPMDM_MAX_LATENT)                                   */
+    int32_t dout;     /* D for the observation GP, d for the dynamics GP                          */
+    int32_t alpha_ld; /* columns of alpha (multiple of GPMDM_TILE, >= dout)                       */
+    int32_t kind;     /* 0 = RBF (gpmdm.py:381 get_y_kernel), 1 = RBF + linear (:408 get_x_kernel) */
+    int32_t tri;      /* layout of L, see above                                                   */
+    const double* lengthscales; /* device [d]   exp(log_lengthscales)                             */
+    const double* lin_c2;       /* device [d+1] exp(x_log_lin_coeff)^2 (kind 1) or NULL           */
+    const double* lambdas;      /* device [dout] observation GP: exp(y_log_lambdas)^2 ;
+                                   dynamics GP: exp(x_log_lambdas)^-2 (gpmdm.py:960, 1066)         */
+} gpmdm_gp_model;
+
+int gpmdm_abi_version(void);
+const char* gpmdm_last_error(void);
+
+/* ---- factor packing ------------------------------------------------------------------------------
+ * Kinv [n, n] (e.g. the reference's Ky_inv, or a diagonal block of Kx_inv_class[c],
+ * gpmdm.py:1289,1305) -> L [n_pad, n_pad] as described on gpmdm_gp_block. */
+int gpmdm_pack_quadform_f64(const double* Kinv, int64_t n, int64_t n_pad, int tri, double* L, void* stream);
+
+/* ---- filter step ------------------------------------------------------------------------------ */
+
+/* GPMDM_PF._propogate_markov_switching (gpmdm_pf.py:137-151): c_new[p] = argmax_j T[c_prev[p]][j] / E[p][j]
+ * where E are Exp(1) draws -- bit-exactly what torch.multinomial(dist, 1) computes from its uniforms
+ * (E = -log1p(-U)).  T [C, C] row-major, not normalised (as the reference). */
+int gpmdm_pf_transition_f64(const int64_t* c_prev, const double* T, const double* E, int64_t P, int32_t C,
+                            int64_t* c_new, void* stream);
+
+/* Groups particles by class so that every 128-particle tile of the dynamics kernel is class
+ * homogeneous (the reference's boolean-mask gather, gpmdm_pf.py:161).  Stable counting sort.
+ *   perm  [P]            particle indices ordered by (class, index)
+ *   tiles [P/128 + C, 4] {block, first position in perm, count, 0} per tile, int32
+ *   n_tiles [1]          int32
+ * workspace: gpmdm_workspace_bytes(P, C). */
+int gpmdm_pf_bucket_by_class(const int64_t* classes, int64_t P, int32_t C, int32_t* perm, int32_t* tiles,
+                             int32_t* n_tiles, void* workspace, void* stream);
+
+/* GPMDM_PF._propogate_dynamics + GPMDM.map_x_dynamics_for_class (gpmdm_pf.py:153-168,
+ * gpmdm.py:1032-1068): for particle p of class c (block c of `dyn`)
+ *     k_i  = exp(-|(xin_i - x_p)/l|^2) + [xin_i,1] diag(c^2) [x_p,1]^T          (never stored)
+ *     mean = k^T alpha_c ; var_k = (1 + [x,1]diag(c^2)[x,1]^T - k^T L_c k) * lambda_k^-2
+ *     x_new = eps * sqrt(var) + mean                                   (mul, then add -- :168)
+ * perm/tiles/n_tiles from gpmdm_pf_bucket_by_class.  eps [P, d] is indexed by particle.
+ * mean_out / var_out ([P, d], may be NULL) expose the GP prediction (map_x_dynamics_for_class).
+ * x_new may be NULL when only the prediction is wanted.  tile_counter: device int32 scratch [1]. */
+int gpmdm_pf_propagate_f64(const gpmdm_gp_model* dyn, const double* x_prev, const int32_t* perm,
+                           const int32_t* tiles, const int32_t* n_tiles, int64_t P, const double* eps,
+                           double* x_new, double* mean_out, double* var_out, int32_t* tile_counter,
+                           void* stream);
+
+/* GPMDM_PF._update_weights (first half) + GPMDM.map_x_to_y (gpmdm_pf.py:170-192, gpmdm.py:923-963):
+ *     k_i = exp(-|(X_i - x_p)/l_y|^2);  mu = k^T alpha_y;  v = 1 - k^T L k;  var_j = v * lambda_j^-2
+ *     ll_p = -(1/(2v)) sum_j lambda_j^2 (z_j - mu_j)^2 - D log v + 2 sum_j log lambda_j - c32
+ * which is the reference's per-particle loop (:188-192) in closed form, including its double-counted
+ * log-variance term.  ll_const = 2 sum_j log lambda_j - c32 is computed by the host, with
+ * c32 = fp32(0.5*D*log(2 pi)) evaluated in float32 exactly as gpmdm_pf.py:5,191 does.
+ * z [D] device.  ll [P] may be NULL; mu_out [P, D] and v_out [P] may be NULL. */
+int gpmdm_pf_observe_f64(const gpmdm_gp_model* obs, const double* x, int64_t P, const double* z, double ll_const,
+                         double* ll, double* mu_out, double* v_out, int32_t* tile_counter, void* stream);
+
+/* GPMDM_PF._update_weights (second half, gpmdm_pf.py:200-204): lw = ll - max(ll); w = exp(lw)/sum.
+ * Reductions run in a fixed blocked order independent of the GPU count.  stats_out [2] = {max, sum}. */
+int gpmdm_pf_normalize_f64(const double* ll, int64_t P, double* lw, double* w, double* stats_out,
+                           void* workspace, void* stream);
+
+/* cdf of torch.multinomial's CPU kernel (gpmdm_pf.py:211): running sum of w in index order, divided
+ * by the total, last entry forced to 1.  mode 0: sequential single-thread order (bit-identical to the
+ * reference's cumsum); mode 1: blocked parallel scan (fixed 1024-element blocks, deterministic). */
+int gpmdm_pf_cdf_f64(const double* w, int64_t P, int32_t mode, double* cdf, void* workspace, void* stream);
+
+/* GPMDM_PF._resample (gpmdm_pf.py:206-213): anc[s] = min{ j : cdf[j] >= u[s] }, then the gathers
+ * x_out[s] = x_in[anc[s]], c_out[s] = c_in[anc[s]].  cdf/x_in/c_in span all P particles (all ranks);
+ * u/anc/x_out/c_out span the n_out output slots of the calling rank. */
+int gpmdm_pf_resample_f64(const double* cdf, int64_t P, const double* u, int64_t n_out, const double* x_in,
+                          const int64_t* c_in, int32_t d, int64_t* anc, double* x_out, int64_t* c_out,
+                          void* stream);
+
+/* GPMDM_PF.class_probabilities / current_state_mean / log_likelihood (gpmdm_pf.py:215-262), with the
+ * reference's mix of post-resample classes/states and pre-resample weights:
+ *   g = ll + lw - max(ll + lw);  class_prob[i] = sum_{c_post=i} exp(g) / sum exp(g)
+ *   state_mean = sum_p x_post[p] * w[p];  loglik = sum exp(g)
+ * out [C + d + 1] = {class_prob, state_mean, loglik}. */
+int gpmdm_pf_summaries_f64(const double* ll, const double* lw, const double* w, const int64_t* c_post,
+                           const double* x_post, int64_t P, int32_t C, int32_t d, double* out,
+                           void* workspace, void* stream);
+
+/* Device-side raw draws (throughput mode; parity mode injects host draws instead): Philox4x32-10
+ * keyed by (seed, step) and counter = global particle index, so results do not depend on how
+ * particles are sharded.  E [n, C] Exp(1); eps [n, d] N(0,1); u [n] U(0,1), or the systematic comb
+ * u[s] = (u0 + first + s) / P_total when systematic != 0. */
+int gpmdm_pf_draws_philox(uint64_t seed, uint64_t step, int64_t first, int64_t n, int64_t P_total, int32_t C,
+                          int32_t d, int32_t systematic, double* E, double* eps, double* u, void* stream);
+
+int64_t gpmdm_workspace_bytes(int64_t P, int32_t C);
+
+/* ---- training-side kernel matrices (gpmdm.py:381-548, 311-340, 550-628) ------------------------
+ * K = exp(-|(x_i-x_j)/l|^2) [+ [x_i,1]diag(c^2)[x_j,1]^T if kind 1] [+ noise2 on the diagonal],
+ * multiplied by the class-block mask given as row offsets (class_offsets [n_classes+1], device int64;
+ * NULL = no mask) -- `get_x_kernel(Xin,Xin) * self.M` without the dense M. */
+int gpmdm_kernel_build_f64(const double* X, int64_t n, int32_t d, int32_t kind, const double* lengthscales,
+                           const double* lin_c2, double noise2, const int64_t* class_offsets, int32_t n_classes,
+                           double* K, void* stream);
+
+/* Gradient terms of a scalar loss through the kernel build above, given G = dLoss/dK [n, n]
+ * (SURVEY.md App. A.5): gX [n, d], g_log_ls [d], g_log_sigma [1], g_log_c [d+1] (kind 1).
+ * Deterministic two-stage reduction; workspace >= gpmdm_kernel_grad_workspace_bytes(n, d). */
+int gpmdm_kernel_grad_f64(const double* X, const double* G, int64_t n, int32_t d, int32_t kind,
+                          const double* lengthscales, const double* lin_c2, double sigma2,
+                          const int64_t* class_offsets, int32_t n_classes, double* gX, double* g_log_ls,
+                          double* g_log_sigma, double* g_log_c, void* workspace, void* stream);
+int64_t gpmdm_kernel_grad_workspace_bytes(int64_t n, int32_t d);
+
+/* ---- measurement helper: sustained fp64 mma.sync (DMMA m8n8k4) rate of this device, TFLOP/s, the
+ * denominator of the contraction roofline (bench.py).  Synchronous. */
+int gpmdm_probe_dmma_tflops(int32_t iters, double* tflops_host);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GPMDM_B200_H_ */

@@ -54,3 +54,53 @@ def rel_err(a, b):
 def scaled_err(a, b, scale):
     a, b = t64(a), t64(b)
     return float(torch.max(torch.abs(a - b) / t64(scale)))
+
+
+# ---- product-side helpers (GPU tests) -----------------------------------------------------------------
+def product_model_from_spec(spec, Ky_inv=None, Kx_inv_blocks=None):
+    """Build the product `GPMDM` (CUDA) holding exactly the latents / hyper-parameters of an oracle
+    ModelSpec, optionally with injected inverses (the reference's own, for stage-wise parity)."""
+    from gpmdm_b200 import GPMDM
+
+    d, D, C = spec.d, spec.D, spec.n_classes
+    ones = lambda n: np.ones(n)
+    m = GPMDM(D=D, d=d, n_classes=C, dyn_target="full", dyn_back_step=1,
+              y_lambdas_init=ones(D), y_lengthscales_init=ones(d), y_sigma_n_init=1.0,
+              x_lambdas_init=ones(d), x_lengthscales_init=ones(d), x_sigma_n_init=1.0,
+              x_lin_coeff_init=ones(d + 1))
+    Y = spec.Y.numpy().astype(np.float32)
+    s = 0
+    for c, lens in enumerate(spec.seq_lengths):
+        for L in lens:
+            m.add_data(Y[s:s + L], c)
+            s += L
+    with torch.no_grad():
+        for k in ("y_log_lengthscales", "y_log_lambdas", "y_log_sigma_n", "x_log_lengthscales",
+                  "x_log_lambdas", "x_log_sigma_n", "x_log_lin_coeff"):
+            getattr(m, k).data.copy_(getattr(spec, k).to(m.device))
+    m._precompute_class_matrices()
+    m.X = torch.nn.Parameter(spec.X.to(m.device).clone(), requires_grad=False)
+    m._precompute_kernel_inverses()
+    if Ky_inv is not None or Kx_inv_blocks is not None:
+        m.set_inverses(Ky_inv, Kx_inv_blocks)
+    return m
+
+
+def synthetic_spec(C, d, D, seqs_per_class, frames, sigma_n=1e-1, seed=0):
+    """Oracle ModelSpec on seeded synthetic sequences with PCA latents (no reference needed)."""
+    from sklearn.decomposition import PCA
+
+    from gpmdm_b200 import synthetic
+
+    wl = synthetic.make_sequences(C, D, seqs_per_class, frames, seed=seed, n_test_trials=2, test_frames=8)
+    Y = np.concatenate([s for cls in wl.sequences for s in cls], 0)
+    X0 = PCA(n_components=d).fit_transform(Y)
+    hp = synthetic.notebook_hyperparameters(D, d, sigma_n)
+    lg = lambda v: torch.log(t64(v))
+    spec = orc.ModelSpec(
+        X=t64(X0), Y=t64(Y), seq_lengths=[[frames] * seqs_per_class for _ in range(C)],
+        y_log_lengthscales=lg(hp["y_lengthscales_init"]), y_log_lambdas=lg(hp["y_lambdas_init"]),
+        y_log_sigma_n=lg(hp["y_sigma_n_init"]), x_log_lengthscales=lg(hp["x_lengthscales_init"]),
+        x_log_lambdas=lg(hp["x_lambdas_init"]), x_log_sigma_n=lg(hp["x_sigma_n_init"]),
+        x_log_lin_coeff=lg(hp["x_lin_coeff_init"]))
+    return spec, wl

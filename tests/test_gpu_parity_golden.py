@@ -1,0 +1,191 @@
+"""GPU: the CUDA path (through the C ABI, via the host classes) against golden vectors recorded from
+the UNMODIFIED reference.  Stage-wise, each stage fed the reference's own inputs and the reference's own
+inverses: integer outputs bit-exact; means / log-likelihoods / weights 1e-9
+relative; variances 1e-9 of the prior variance."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+from tests.helpers import GOLDEN_CASES, Golden, product_model_from_spec, rel_err, scaled_err, t64
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-9
+
+
+@pytest.fixture(scope="module", params=GOLDEN_CASES)
+def case(request):
+    g = Golden(request.param)
+    model = product_model_from_spec(g.spec, Ky_inv=t64(g.z["Ky_inv"]),
+                                    Kx_inv_blocks=[t64(g.z[f"Kx_inv_block_{c}"]) for c in range(g.C)])
+    return g, model
+
+
+def dev(a, dtype=torch.float64):
+    return torch.as_tensor(np.asarray(a)).to("cuda", dtype).contiguous()
+
+
+@pytest.mark.parametrize("tri", [True, False])
+def test_map_x_to_y_matches_reference(case, tri):
+    g, model = case
+    model._packed = None
+    model.packed_models(tri)
+    s = g.step(0)
+    x_ref = t64(s["eps"]) * t64(s["dyn_std"]) + t64(s["dyn_mean"])
+    mu, var = model.map_x_to_y(x_ref.cuda())
+    scale = torch.clamp(torch.abs(t64(s["mu"])).max(dim=1, keepdim=True).values, min=1e-3)
+    assert scaled_err(mu.cpu(), s["mu"], scale) < TOL
+    lam = (torch.exp(g.spec.y_log_lambdas) ** -2).unsqueeze(0).expand(var.shape)
+    assert scaled_err(var.cpu(), s["var"], lam) < TOL
+    model._packed = None
+
+
+def test_map_x_dynamics_for_class_matches_reference(case):
+    g, model = case
+    s = g.step(0)
+    states = t64(g.z["init_states"])
+    c_new = torch.as_tensor(s["c_new"])
+    lam_x = torch.exp(g.spec.x_log_lambdas) ** -2
+    from oracle import gpmdm_oracle as orc
+    for c in range(g.C):
+        rows = torch.nonzero(c_new == c).squeeze(-1)
+        if rows.numel() == 0:
+            continue
+        mean, var = model.map_x_dynamics_for_class(states[rows].cuda(), c)
+        ref_mean, ref_var = t64(s["dyn_mean"])[rows], t64(s["dyn_std"])[rows] ** 2
+        scale = torch.clamp(torch.abs(ref_mean).max(dim=1, keepdim=True).values, min=1e-3)
+        assert scaled_err(mean.cpu(), ref_mean, scale) < TOL
+        prior = orc.x_diag_kernel(g.spec, states[rows]).unsqueeze(1) * lam_x.unsqueeze(0)
+        assert scaled_err(var.cpu(), ref_var, prior) < TOL
+
+
+def test_filter_stagewise_against_reference(case):
+    """Drive the product filter with the reference's draws; before every step force its state to the
+    reference's state, so each step is a stage-wise comparison."""
+    from gpmdm_b200 import GPMDM_PF
+
+    g, model = case
+    pf = GPMDM_PF(model, g.T, g.P, init_indices=g.init_idx, cdf_order="sequential")
+    assert torch.equal(pf._particle_classes.cpu(), torch.as_tensor(g.z["init_classes"]))
+    assert torch.equal(pf._particle_states.cpu(), t64(g.z["init_states"]))
+    lam_y = torch.exp(g.spec.y_log_lambdas) ** -2
+    for t in range(g.steps):
+        s = g.step(t)
+        pf.update(s["z"], draws=(s["E"], s["eps"], s["u"]))
+        torch.cuda.synchronize()
+        # transition: bit-exact
+        assert torch.equal(pf.last_pre_resample_classes.cpu(), torch.as_tensor(s["c_new"]))
+        # dynamics draw vs the reference's x' = eps*std + mean
+        x_ref = t64(s["eps"]) * t64(s["dyn_std"]) + t64(s["dyn_mean"])
+        assert float(torch.max(torch.abs(pf.last_pre_resample_states.cpu() - x_ref))) < 1e-8
+        # log-likelihoods: v carries the reference's own cancellation noise; compare through v-scaled bound
+        v_ref = t64(s["var"])[:, 0] / lam_y[0]
+        ll, ll_ref = pf._log_likelihoods.cpu(), t64(s["ll"])
+        bound = 1e-6 * torch.abs(ll_ref) + 1e-6
+        assert bool(torch.all(torch.abs(ll - ll_ref) <= bound)), float(torch.max(torch.abs(ll - ll_ref)))
+        assert pf.get_most_likely_class() == int(s["argmax"])
+        # continue from the reference's post-resample state
+        pf._particle_states = dev(s["states_post"])
+        pf._particle_classes = dev(s["classes_post"], torch.int64)
+
+
+def test_observe_loglik_on_reference_states(case):
+    """gpmdm_pf_observe_f64 on the reference's exact post-dynamics states: ll within 1e-9 of the fused
+    closed form evaluated on the reference's (mu, v) up to the variance noise floor, and within 1e-9
+    relative of the reference when its v is well above the noise floor."""
+    from gpmdm_b200 import _cabi
+    from oracle import gpmdm_oracle as orc
+
+    g, model = case
+    lib = _cabi.lib()
+    pk = model.packed_models(True)
+    s = g.step(0)
+    x_ref = (t64(s["eps"]) * t64(s["dyn_std"]) + t64(s["dyn_mean"])).cuda().contiguous()
+    P = x_ref.shape[0]
+    z = dev(s["z"])
+    ll = torch.empty(P, dtype=torch.float64, device="cuda")
+    mu = torch.empty(P, g.spec.D, dtype=torch.float64, device="cuda")
+    v = torch.empty(P, dtype=torch.float64, device="cuda")
+    counter = torch.zeros(1, dtype=torch.int32, device="cuda")
+    ll_const = float(2.0 * torch.sum(g.spec.y_log_lambdas)) - orc.c32_constant(g.spec.D)
+    _cabi.check(lib.gpmdm_pf_observe_f64(ctypes.byref(pk["obs"]), x_ref.data_ptr(), P, z.data_ptr(), ll_const,
+                                         ll.data_ptr(), mu.data_ptr(), v.data_ptr(), counter.data_ptr(),
+                                         _cabi.stream()), "observe")
+    torch.cuda.synchronize()
+    # the epilogue formula, evaluated by the oracle on OUR (mu, v): isolates the fused-ll arithmetic
+    ll_formula = orc.log_likelihoods_fused(mu.cpu(), v.cpu(), t64(s["z"]), g.spec.y_log_lambdas)
+    assert rel_err(ll.cpu(), ll_formula) < 1e-12
+    lam_y = torch.exp(g.spec.y_log_lambdas) ** -2
+    v_ref = t64(s["var"])[:, 0] / lam_y[0]
+    assert float(torch.max(torch.abs(v.cpu() - v_ref))) < TOL  # prior variance is 1
+    good = v_ref > 1e-2
+    if bool(good.any()):
+        assert rel_err(ll.cpu()[good], t64(s["ll"])[good]) < 1e-6
+
+
+def test_normalize_cdf_resample_summaries_bit_level(case):
+    from gpmdm_b200 import _cabi
+
+    g, model = case
+    lib = _cabi.lib()
+    for t in range(g.steps):
+        s = g.step(t)
+        P, C, d = g.P, g.C, g.spec.d
+        ll = dev(s["ll"])
+        lw, w = torch.empty_like(ll), torch.empty_like(ll)
+        ws = torch.empty(int(lib.gpmdm_workspace_bytes(P, C)) // 8 + 1, dtype=torch.float64, device="cuda")
+        stats = torch.empty(2, dtype=torch.float64, device="cuda")
+        _cabi.check(lib.gpmdm_pf_normalize_f64(ll.data_ptr(), P, lw.data_ptr(), w.data_ptr(), stats.data_ptr(),
+                                               ws.data_ptr(), _cabi.stream()), "normalize")
+        assert torch.equal(lw.cpu(), t64(s["lw"]))  # ll - max: exact
+        assert rel_err(w.cpu(), s["w"]) < 1e-13
+        # cdf + ancestors from the REFERENCE's weights: bit-exact in sequential order
+        w_ref = dev(s["w"])
+        cdf = torch.empty_like(w_ref)
+        _cabi.check(lib.gpmdm_pf_cdf_f64(w_ref.data_ptr(), P, 0, cdf.data_ptr(), ws.data_ptr(), _cabi.stream()), "cdf")
+        assert torch.equal(cdf.cpu(), t64(s["cdf"]))
+        cdf_b = torch.empty_like(w_ref)
+        _cabi.check(lib.gpmdm_pf_cdf_f64(w_ref.data_ptr(), P, 1, cdf_b.data_ptr(), ws.data_ptr(), _cabi.stream()), "cdf")
+        assert float(torch.max(torch.abs(cdf_b.cpu() - t64(s["cdf"])))) < 1e-14
+        x_ref = (t64(s["eps"]) * t64(s["dyn_std"]) + t64(s["dyn_mean"])).cuda().contiguous()
+        c_new = dev(s["c_new"], torch.int64)
+        u = dev(s["u"])
+        for cdf_used in (cdf, cdf_b):
+            anc = torch.empty(P, dtype=torch.int64, device="cuda")
+            xo = torch.empty(P, d, dtype=torch.float64, device="cuda")
+            co = torch.empty(P, dtype=torch.int64, device="cuda")
+            _cabi.check(lib.gpmdm_pf_resample_f64(cdf_used.data_ptr(), P, u.data_ptr(), P, x_ref.data_ptr(),
+                                                  c_new.data_ptr(), d, anc.data_ptr(), xo.data_ptr(), co.data_ptr(),
+                                                  _cabi.stream()), "resample")
+            assert torch.equal(anc.cpu(), torch.as_tensor(s["anc"]))
+            assert torch.equal(xo.cpu(), t64(s["states_post"]))
+            assert torch.equal(co.cpu(), torch.as_tensor(s["classes_post"]))
+        # summaries from the reference's ll / lw / w and post-resample particles
+        out = torch.empty(C + d + 1, dtype=torch.float64, device="cuda")
+        _cabi.check(lib.gpmdm_pf_summaries_f64(dev(s["ll"]).data_ptr(), dev(s["lw"]).data_ptr(), w_ref.data_ptr(),
+                                               dev(s["classes_post"], torch.int64).data_ptr(),
+                                               dev(s["states_post"]).data_ptr(), P, C, d, out.data_ptr(), ws.data_ptr(),
+                                               _cabi.stream()), "summaries")
+        out = out.cpu()
+        assert rel_err(out[:C], s["class_prob"]) < 1e-12
+        assert int(torch.argmax(out[:C])) == int(s["argmax"])
+        assert float(torch.max(torch.abs(out[C:C + d] - t64(s["state_mean"])))) < 1e-12
+        assert abs(float(out[C + d]) - float(s["log_likelihood"])) <= 1e-12 * abs(float(s["log_likelihood"]))
+
+
+def test_transition_bit_exact(case):
+    from gpmdm_b200 import _cabi
+
+    g, model = case
+    lib = _cabi.lib()
+    classes = dev(g.z["init_classes"], torch.int64)
+    T = g.T.to(torch.float64).cuda().contiguous()
+    for t in range(g.steps):
+        s = g.step(t)
+        E = dev(s["E"])
+        out = torch.empty_like(classes)
+        _cabi.check(lib.gpmdm_pf_transition_f64(classes.data_ptr(), T.data_ptr(), E.data_ptr(), g.P, g.C, out.data_ptr(),
+                                                _cabi.stream()), "transition")
+        assert torch.equal(out.cpu(), torch.as_tensor(s["c_new"]))
+        classes = dev(s["classes_post"], torch.int64)

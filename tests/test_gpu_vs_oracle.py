@@ -1,0 +1,184 @@
+"""GPU: the CUDA path against the CPU oracle on seeded synthetic workloads of BASELINE config sizes the
+oracle finishes in seconds (N = 2000; P = 100 and P = 3000), plus size-independent properties."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+from gpmdm_b200 import synthetic
+from oracle import gpmdm_oracle as orc
+from tests.helpers import product_model_from_spec, rel_err, scaled_err, synthetic_spec, t64
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-9
+
+
+@pytest.fixture(scope="module")
+def cfg1():
+    """BASELINE config 1 shapes: C=2, d=3, D=62, N=2000 (20 x 100 frames)."""
+    spec, wl = synthetic_spec(2, 3, 62, 10, 100, sigma_n=1e-1, seed=3)
+    f = orc.precompute_factors(spec)
+    model = product_model_from_spec(spec, Ky_inv=f.Ky_inv, Kx_inv_blocks=f.Kx_inv_blocks)
+    return spec, wl, f, model
+
+
+def particles_near_data(spec, P, seed):
+    g = torch.Generator().manual_seed(seed)
+    idx = torch.randint(0, spec.N, (P,), generator=g)
+    return spec.X[idx] + 0.05 * torch.randn(P, spec.d, dtype=torch.float64, generator=g)
+
+
+@pytest.mark.parametrize("P", [1, 100, 129, 3000])
+def test_observation_gp_vs_oracle(cfg1, P):
+    spec, wl, f, model = cfg1
+    xs = particles_near_data(spec, P, 5)
+    mu, var = model.map_x_to_y(xs.cuda())
+    mu_o, var_o, v_o = orc.map_x_to_y(spec, f, xs)
+    scale = torch.clamp(torch.abs(mu_o).max(dim=1, keepdim=True).values, min=1e-3)
+    assert scaled_err(mu.cpu(), mu_o, scale) < TOL
+    lam = (torch.exp(spec.y_log_lambdas) ** -2).unsqueeze(0).expand(var_o.shape)
+    assert scaled_err(var.cpu(), var_o, lam) < TOL
+
+
+@pytest.mark.parametrize("P", [1, 100, 1000])
+def test_dynamics_gp_vs_oracle(cfg1, P):
+    spec, wl, f, model = cfg1
+    xs = particles_near_data(spec, P, 6)
+    lam_x = torch.exp(spec.x_log_lambdas) ** -2
+    for c in range(spec.n_classes):
+        mean, var = model.map_x_dynamics_for_class(xs.cuda(), c)
+        mean_o, var_o, q, prior = orc.map_x_dynamics_for_class(spec, f, xs, c)
+        scale = torch.clamp(torch.abs(mean_o).max(dim=1, keepdim=True).values, min=1e-3)
+        assert scaled_err(mean.cpu(), mean_o, scale) < TOL
+        assert scaled_err(var.cpu(), var_o, prior.unsqueeze(1) * lam_x.unsqueeze(0)) < TOL
+
+
+def test_tri_and_dense_packings_agree(cfg1):
+    spec, wl, f, model = cfg1
+    xs = particles_near_data(spec, 300, 7).cuda()
+    model._packed = None
+    model.packed_models(True)
+    mu_t, var_t = model.map_x_to_y(xs)
+    model._packed = None
+    model.packed_models(False)
+    mu_d, var_d = model.map_x_to_y(xs)
+    model._packed = None
+    assert float(torch.max(torch.abs(mu_t - mu_d))) == 0.0  # the mean tile is identical in both
+    assert float(torch.max(torch.abs(var_t - var_d))) < 1e-10
+
+
+@pytest.mark.parametrize("P", [100, 2500])
+def test_filter_trial_vs_oracle(cfg1, P):
+    """Free-running 12-frame trial, same injected draws on both sides: classes and ancestors identical,
+    argmax class identical, states to 1e-8 (BASELINE config 1 uses P = 100 over 150 frames; the oracle's
+    cost bounds the frame count here)."""
+    from gpmdm_b200 import GPMDM_PF
+
+    spec, wl, f, model = cfg1
+    C, d = spec.n_classes, spec.d
+    T = synthetic.markov_matrix(C)
+    parts = orc.divide_into_n_parts(P, C)
+    g = torch.Generator().manual_seed(9)
+    init_idx = [torch.randint(0, b - a, (parts[c],), generator=g) for c, (a, b) in enumerate(spec.class_row_ranges())]
+    o = orc.FilterOracle(spec, T, P, init_idx, f)
+    pf = GPMDM_PF(model, T, P, init_indices=init_idx, cdf_order="sequential")
+    cls_true, trial = wl.test_trials[0]
+    mism = 0
+    for t in range(min(8, trial.shape[0])):
+        E, eps, u = synthetic.raw_draws(P, C, d, 700 + t)
+        o.update(trial[t], E, eps, u)
+        pf.update(trial[t], draws=(E, eps, u))
+        assert torch.equal(pf.last_pre_resample_classes.cpu(), o.trace["c_new"])
+        mism += int((pf.last_ancestors.cpu() != o.trace["anc"]).sum())
+        assert rel_err(pf._log_likelihoods.cpu(), o.trace["ll"]) < 1e-6
+        assert pf.get_most_likely_class() == o.get_most_likely_class()
+        assert rel_err(pf.class_probabilities().cpu(), o.class_probabilities()) < 1e-6
+        # re-synchronise states so that a (legitimate) near-tie flip cannot cascade
+        pf._particle_states = o.states.cuda().contiguous()
+        pf._particle_classes = o.classes.cuda().contiguous()
+    assert mism == 0, f"{mism} ancestor mismatches"
+
+
+def test_bucket_by_class_is_a_stable_partition():
+    from gpmdm_b200 import _cabi
+
+    lib = _cabi.lib()
+    for P, C in ((1, 1), (100, 2), (5000, 8), (70000, 64)):
+        g = torch.Generator().manual_seed(P)
+        cls = torch.randint(0, C, (P,), generator=g)
+        if C > 2:
+            cls[cls == 1] = 0  # an empty class
+        cls_d = cls.cuda()
+        perm = torch.empty(P, dtype=torch.int32, device="cuda")
+        tiles = torch.zeros(P // 128 + C + 1, 4, dtype=torch.int32, device="cuda")
+        nt = torch.zeros(1, dtype=torch.int32, device="cuda")
+        ws = torch.empty(int(lib.gpmdm_workspace_bytes(P, C)) // 8 + 1, dtype=torch.float64, device="cuda")
+        _cabi.check(lib.gpmdm_pf_bucket_by_class(cls_d.data_ptr(), P, C, perm.data_ptr(), tiles.data_ptr(),
+                                                 nt.data_ptr(), ws.data_ptr(), _cabi.stream()), "bucket")
+        expect = torch.sort(cls, stable=True).indices.to(torch.int32)
+        assert torch.equal(perm.cpu(), expect)
+        n = int(nt.item())
+        tl = tiles.cpu()[:n]
+        covered = 0
+        for blk, first, count, _ in tl.tolist():
+            assert 1 <= count <= 128 and first == covered
+            assert bool((cls[expect[first:first + count].long()] == blk).all())
+            covered += count
+        assert covered == P
+
+
+def test_philox_draws_are_shard_independent_and_sane():
+    from gpmdm_b200 import _cabi
+
+    lib = _cabi.lib()
+    P, C, d = 200000, 3, 3
+
+    def draw(first, n, systematic=0, step=4):
+        E = torch.empty(n, C, dtype=torch.float64, device="cuda")
+        eps = torch.empty(n, d, dtype=torch.float64, device="cuda")
+        u = torch.empty(n, dtype=torch.float64, device="cuda")
+        _cabi.check(lib.gpmdm_pf_draws_philox(1234, step, first, n, P, C, d, systematic, E.data_ptr(), eps.data_ptr(),
+                                              u.data_ptr(), _cabi.stream()), "philox")
+        return E.cpu(), eps.cpu(), u.cpu()
+
+    E, eps, u = draw(0, P)
+    E2, eps2, u2 = draw(P // 2, P // 2)
+    assert torch.equal(E[P // 2:], E2) and torch.equal(eps[P // 2:], eps2) and torch.equal(u[P // 2:], u2)
+    assert abs(float(E.mean()) - 1.0) < 0.01 and abs(float(E.var()) - 1.0) < 0.03
+    assert abs(float(eps.mean())) < 0.01 and abs(float(eps.var()) - 1.0) < 0.01
+    assert abs(float(u.mean()) - 0.5) < 0.005 and float(u.min()) >= 0.0 and float(u.max()) < 1.0
+    assert abs(float((eps[:, 0] * eps[:, 1]).mean())) < 0.01
+    E3, _, _ = draw(0, P, step=5)
+    assert not torch.equal(E, E3)
+    _, _, us = draw(0, P, systematic=1)
+    diffs = us[1:] - us[:-1]
+    assert float(torch.max(torch.abs(diffs - 1.0 / P))) < 1e-12 and 0 <= float(us[0]) < 1.0 / P
+
+
+def test_filter_runs_with_device_draws_and_systematic_resampling(cfg1):
+    from gpmdm_b200 import GPMDM_PF
+
+    spec, wl, f, model = cfg1
+    T = synthetic.markov_matrix(2)
+    for kw in (dict(), dict(resampling="systematic", cdf_order="blocked")):
+        pf = GPMDM_PF(model, T, 1000, seed=5, **kw)
+        hits = 0
+        cls_true, trial = wl.test_trials[1]
+        for t in range(trial.shape[0]):
+            pf.update(trial[t])
+            hits += int(pf.get_most_likely_class() == cls_true)
+        p = pf.class_probabilities()
+        assert abs(float(p.sum()) - 1.0) < 1e-12 and bool(torch.isfinite(pf._particle_states).all())
+        assert hits >= trial.shape[0] - 2  # the synthetic classes are well separated
+
+
+def test_constructor_errors_match_reference():
+    from gpmdm_b200 import GPMDM, GPMDM_PF
+
+    spec, wl = synthetic_spec(2, 3, 10, 2, 20, seed=1)
+    model = product_model_from_spec(spec)
+    with pytest.raises(ValueError):
+        GPMDM_PF(model, synthetic.markov_matrix(3), 10)  # gpmdm_pf.py:74-75
+    with pytest.raises(ValueError):
+        model.add_data(np.zeros((5, 11), dtype=np.float32), 0)  # gpmdm.py:295-296
