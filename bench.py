@@ -1,0 +1,360 @@
+#!/usr/bin/env python
+"""bench.py -- particle-updates/sec of the GPMDM filter step (BASELINE.json metric) on 1..8 B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json configs[2], the configuration the metric is quoted on; it fits one GPU):
+8-class GPMDM, N_train = 20 000 frames (200 sequences x 100), D = 62, latent d = 3, P = 1 048 576
+particles in fp64, sharded by contiguous particle range over the ranks (strong scaling: P is fixed).
+A "step" is one full `GPMDM_PF.update(z)` -- class transition, dynamics-GP draw, observation-GP
+log-likelihood, weight normalisation, multinomial resampling -- plus the class-posterior query, on
+synthetic data (gpmdm_b200/synthetic.py), device-side Philox draws.
+
+Prints ONE JSON line (rank 0).  `value` is timed with inputs resident in HBM; `e2e` goes through the
+public API with the observation in pinned host memory and the class posterior read back to the host.
+`roofline` describes the dominant kernel (the observation-GP contraction, gp_predict_kernel<0,3>),
+`cpu_baseline` / `--impl reference` time the CPU oracle (a restatement of the reference's torch-CPU
+algorithm; the reference itself is Python and is not present on the GPU box) on a bounded particle sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np
+import torch
+
+METRIC = "particle_updates_per_sec"
+UNIT = "particle-updates/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--particles", type=int, default=1 << 20)
+    ap.add_argument("--classes", type=int, default=8)
+    ap.add_argument("--seqs-per-class", type=int, default=25)
+    ap.add_argument("--frames", type=int, default=100)
+    ap.add_argument("--latent", type=int, default=3)
+    ap.add_argument("--obs-dim", type=int, default=62)
+    ap.add_argument("--cpu-sample", type=int, default=2048, help="particles of the CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--dense", action="store_true", help="dense K^-1 instead of the triangular packing")
+    return ap.parse_args()
+
+
+def workload_name(a):
+    n = a.classes * a.seqs_per_class * a.frames
+    return (f"BASELINE configs[2]: {a.classes}-class GPMDM, N_train={n}, D={a.obs_dim}, d={a.latent}, "
+            f"P={a.particles} particles, fp64")
+
+
+# ---- synthetic model ------------------------------------------------------------------------------------
+def synthetic_inputs(a):
+    from sklearn.decomposition import PCA
+
+    from gpmdm_b200 import synthetic
+
+    wl = synthetic.make_sequences(a.classes, a.obs_dim, a.seqs_per_class, a.frames, seed=0, n_test_trials=1,
+                                  test_frames=64)
+    Y = np.concatenate([s for cls in wl.sequences for s in cls], 0)
+    X0 = PCA(n_components=a.latent).fit_transform(Y)
+    hp = synthetic.notebook_hyperparameters(a.obs_dim, a.latent, sigma_n=1e-1)
+    return wl, X0, hp
+
+
+def build_product_model(a, wl, X0, hp):
+    from gpmdm_b200 import GPMDM
+
+    m = GPMDM(D=a.obs_dim, d=a.latent, n_classes=a.classes, dyn_target="full", dyn_back_step=1, **hp)
+    for c in range(a.classes):
+        for s in wl.sequences[c]:
+            m.add_data(s, c)
+    m._precompute_class_matrices()
+    m.X = torch.nn.Parameter(torch.tensor(X0, dtype=torch.float64, device=m.device), requires_grad=False)
+    m._precompute_kernel_inverses()
+    return m
+
+
+# ---- clocks ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([t.strip() for t in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) >= 7 and r[3 + i].startswith("Active") for r in self.rows)]
+        pw = [float(r[2]) for r in self.rows if len(r) >= 7 and r[2].replace(".", "").isdigit()]
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "power_w_max": max(pw) if pw else None, "samples": len(sm)}
+
+
+# ---- CPU oracle timing ------------------------------------------------------------------------------------------
+def oracle_spec(a, wl, X0, hp):
+    from oracle import gpmdm_oracle as orc
+
+    t64 = lambda v: torch.as_tensor(np.asarray(v), dtype=torch.float64)
+    Y = np.concatenate([s for cls in wl.sequences for s in cls], 0)
+    lg = lambda v: torch.log(t64(v))
+    return orc.ModelSpec(
+        X=t64(X0), Y=t64(Y), seq_lengths=[[a.frames] * a.seqs_per_class for _ in range(a.classes)],
+        y_log_lengthscales=lg(hp["y_lengthscales_init"]), y_log_lambdas=lg(hp["y_lambdas_init"]),
+        y_log_sigma_n=lg(hp["y_sigma_n_init"]), x_log_lengthscales=lg(hp["x_lengthscales_init"]),
+        x_log_lambdas=lg(hp["x_lambdas_init"]), x_log_sigma_n=lg(hp["x_sigma_n_init"]),
+        x_log_lin_coeff=lg(hp["x_lin_coeff_init"]))
+
+
+def oracle_factors(spec, device):
+    """The oracle's factor recipe (oracle.precompute_factors) evaluated with plain torch on `device`
+    (setup only -- it is not part of any timed region), returned on the CPU."""
+    from oracle import gpmdm_oracle as orc
+
+    def inv(K):
+        U, _ = torch.linalg.cholesky_ex(K, upper=True)
+        Ui = torch.linalg.solve_triangular(U, torch.eye(K.shape[0], dtype=K.dtype, device=K.device), upper=True)
+        return Ui @ Ui.t()
+
+    ls = torch.exp(spec.y_log_lengthscales).to(device)
+    X = spec.X.to(device)
+    A = X / ls
+    A2 = (A * A).sum(1, keepdim=True)
+    Ky = torch.exp(-(A2 + A2.t() - 2 * A @ A.t()))
+    Ky.diagonal().add_(float(torch.exp(spec.y_log_sigma_n) ** 2 + spec.sigma_n_num_Y ** 2))
+    Ky_inv = inv(Ky).cpu()
+    del Ky
+    Xin, Xout = orc.xin_xout(spec)
+    blocks = []
+    for a, b in spec.class_pair_ranges():
+        Kc = orc.x_kernel(spec, Xin[a:b], Xin[a:b]).to(device)
+        Kc.diagonal().add_(1e-6)
+        blocks.append(inv(Kc).cpu())
+    return orc.precompute_factors(spec, Ky_inv=Ky_inv, Kx_inv_blocks=blocks)
+
+
+def time_oracle(a, wl, spec, factors, sample, steps, warmup):
+    """Times `FilterOracle.update` + class query (the region the reference's notebook times,
+    test_gpmdm_pf.ipynb cell 4) on `sample` particles with all host threads."""
+    from gpmdm_b200 import synthetic
+    from oracle import gpmdm_oracle as orc
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    C, d = spec.n_classes, spec.d
+    T = synthetic.markov_matrix(C)
+    parts = orc.divide_into_n_parts(sample, C)
+    g = torch.Generator().manual_seed(1)
+    init_idx = [torch.randint(0, hi - lo, (parts[c],), generator=g) for c, (lo, hi) in enumerate(spec.class_row_ranges())]
+    o = orc.FilterOracle(spec, T, sample, init_idx, factors)
+    trial = wl.test_trials[0][1]
+    times = []
+    with torch.no_grad():
+        for t in range(warmup + steps):
+            E, eps, u = synthetic.raw_draws(sample, C, d, 100 + t)
+            t0 = time.perf_counter()
+            o.update(trial[t % trial.shape[0]], E, eps, u, loop_ll=True)  # the reference's per-particle loop
+            o.get_most_likely_class()
+            dt = time.perf_counter() - t0
+            if t >= warmup:
+                times.append(dt)
+    return sample * len(times) / sum(times), 1e3 * sum(times) / len(times), torch.get_num_threads()
+
+
+# ---- main ---------------------------------------------------------------------------------------------------
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    wl, X0, hp = synthetic_inputs(a)
+    spec = oracle_spec(a, wl, X0, hp)
+    dev = "cuda" if torch.cuda.is_available() else "cpu"
+    f = oracle_factors(spec, dev)
+    warm = min(a.warmup, 1)
+    val, ms, cores = time_oracle(a, wl, spec, f, a.cpu_sample, a.steps, warm)
+    sample = f"{a.cpu_sample} of {a.particles} particles per step, {a.steps} steps (+{warm} warm-up), N_train={spec.N}"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+        "warmup": warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(a), "note": "CPU oracle port of the reference's torch-CPU filter "
+                   "(the Python reference does not travel to the GPU box); per-particle cost is independent of P"},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+def run_ours(a):
+    import torch.distributed as dist
+
+    from gpmdm_b200 import GPMDM_PF, _cabi, synthetic
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    lib = _cabi.lib()
+
+    wl, X0, hp = synthetic_inputs(a)
+    model = build_product_model(a, wl, X0, hp)
+    N = X0.shape[0]
+    C, d, D, P = a.classes, a.latent, a.obs_dim, a.particles
+    T = synthetic.markov_matrix(C)
+    pf = GPMDM_PF(model, T, P, seed=1234, tri=not a.dense, cdf_order="blocked")
+    trial = wl.test_trials[0][1]
+    z_dev = [torch.tensor(trial[t], dtype=torch.float64, device="cuda") for t in range(trial.shape[0])]
+    z_pinned = [torch.tensor(trial[t]).pin_memory() for t in range(trial.shape[0])]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident(t):
+        pf._update(z_dev[t % len(z_dev)])
+        pf._summaries()
+
+    def step_e2e(t):
+        pf.update(z_pinned[t % len(z_pinned)])          # H2D of the observation inside update()
+        return pf.class_probabilities().cpu()           # D2H of the class posterior
+
+    for t in range(a.warmup):
+        step_resident(t)
+    barrier()
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    pf._profile_events = []
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for t in range(a.steps):
+        step_resident(a.warmup + t)
+    ev1.record()
+    barrier()
+    elapsed_ms = ev0.elapsed_time(ev1)
+    obs_ms = [s.elapsed_time(e) for s, e in pf._profile_events]
+    pf._profile_events = None
+    clk = clocks.stop() if rank == 0 else None
+
+    # end-to-end leg (host buffers in, host result out)
+    ke = max(1, min(a.steps, 2))
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for t in range(ke):
+        probs = step_e2e(t)
+    e1.record()
+    barrier()
+    e2e_ms = e0.elapsed_time(e1)
+
+    if world > 1:
+        tt = torch.tensor([elapsed_ms, e2e_ms, sum(obs_ms) / max(len(obs_ms), 1)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        elapsed_ms, e2e_ms, obs_avg_ms = tt.tolist()
+    else:
+        obs_avg_ms = sum(obs_ms) / max(len(obs_ms), 1)
+
+    if rank == 0:
+        value = P * a.steps / (elapsed_ms * 1e-3)
+        e2e_val = P * ke / (e2e_ms * 1e-3)
+        # roofline of the dominant kernel: observation-GP contraction, one launch per step per rank
+        Pl = P // world
+        flops_alg = Pl * (2.0 * N * N + 2.0 * N * D)           # obs var + obs mean terms
+        n_pad = (N + 127) // 128 * 128
+        flops_exec = Pl * (2.0 * n_pad * 128) * ((n_pad // 128) * (n_pad // 128 + 1) / 2 + n_pad / 128) \
+            if not a.dense else Pl * (2.0 * n_pad * n_pad + 2.0 * n_pad * 128)
+        tf = ctypes_probe(lib)
+        achieved = flops_alg / (obs_avg_ms * 1e-3) / 1e12
+        roofline = {
+            "bound": "tensor", "achieved": achieved, "peak": tf, "unit": "TFLOP/s", "frac": achieved / tf,
+            "traffic": None, "kernel": "gp_predict_kernel<0,3> (gpmdm_pf_observe_f64)", "launch_ms": obs_avg_ms,
+            "peak_source": "fp64 mma.sync m8n8k4 issue-rate probe measured in this run (MEASURED_PEAKS.json holds "
+                           "no fp64 figure)",
+            "executed_tflops": flops_exec / (obs_avg_ms * 1e-3) / 1e12,
+            "executed_frac": flops_exec / (obs_avg_ms * 1e-3) / 1e12 / tf,
+            "note": "achieved counts ALGORITHMIC flops 2N^2+2ND per particle; the kernel executes ~half of them "
+                    "because k^T K^-1 k is evaluated on the triangular packing of the symmetric K^-1" if not a.dense
+                    else "dense K^-1",
+        }
+        cpu = None
+        if not a.no_cpu_baseline and world == 1:
+            spec = oracle_spec(a, wl, X0, hp)
+            f = oracle_factors(spec, "cuda")
+            v, ms, cores = time_oracle(a, wl, spec, f, a.cpu_sample, 2, 1)
+            cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                   "sample": f"{a.cpu_sample} of {P} particles, 2 steps (+1 warm-up), N_train={N}; per-particle cost "
+                             f"is independent of P"}
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": elapsed_ms / a.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(a), "l2": "inputs larger than L2 (K^-1 is %.1f GB)" % (8e-9 * N * N),
+                       "resampling": "multinomial", "draws": "device Philox4x32-10", "tri": not a.dense,
+                       "parallelism": f"particles sharded over {world} rank(s), factors replicated"},
+            "roofline": roofline, "cpu_baseline": cpu,
+            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(z_pinned[0].numel() * z_pinned[0].element_size()),
+                    "d2h_bytes_per_step": int(probs.numel() * probs.element_size()), "steps": ke},
+            "gpu_launches": int(pf.launches_per_step * a.steps), "clocks": clk,
+        }
+        print(json.dumps(out))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def ctypes_probe(lib):
+    import ctypes
+
+    tf = ctypes.c_double(0.0)
+    rc = lib.gpmdm_probe_dmma_tflops(20000, ctypes.byref(tf))
+    if rc != 0:
+        raise RuntimeError("gpmdm_probe_dmma_tflops failed")
+    return tf.value
+
+
+def main():
+    a = parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+        return
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (the product has no CPU path); use --impl reference for the CPU arm")
+    run_ours(a)
+
+
+if __name__ == "__main__":
+    main()

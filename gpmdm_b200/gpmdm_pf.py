@@ -169,8 +169,15 @@ class GPMDM_PF:
         check(lib.gpmdm_pf_propagate_f64(ctypes.byref(self._packed["dyn"]), ptr(x_prev), ptr(self._perm), ptr(self._tiles),
                                          ptr(self._n_tiles), Pl, ptr(eps), ptr(x_new_l), None, None, ptr(self._counter),
                                          st), "gpmdm_pf_propagate_f64")
+        prof = getattr(self, "_profile_events", None)
+        if prof is not None:  # bench.py: CUDA events around the dominant kernel, on the launching stream
+            ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            ev[0].record()
         check(lib.gpmdm_pf_observe_f64(ctypes.byref(self._packed["obs"]), ptr(x_new_l), Pl, ptr(z), self._ll_const,
                                        ptr(ll_l), None, None, ptr(self._counter), st), "gpmdm_pf_observe_f64")
+        if prof is not None:
+            ev[1].record()
+            prof.append(ev)
         # -- the one exchange step: every rank gets every particle's (x', c', ll)
         if self._world > 1:
             import torch.distributed as dist
@@ -191,6 +198,13 @@ class GPMDM_PF:
         self._log_likelihoods = ll_new.clone()
         self._log_weights, self._weights = lw_new, w_new
         self._step += 1
+
+    @property
+    def launches_per_step(self) -> int:
+        """Kernels of libgpmdm_sm100a.so launched by one update() + one query (device-draw mode)."""
+        draws, transition, bucket, propagate, observe, normalize, resample, summaries = 2, 1, 3, 1, 1, 5, 1, 4
+        cdf = 2 if self._cdf_mode == 0 else 3
+        return draws + transition + bucket + propagate + observe + normalize + cdf + resample + summaries
 
     def _log_weights_buf(self):
         return torch.empty(self._num_particles, dtype=self.dtype, device=self.device)
