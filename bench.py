@@ -295,7 +295,8 @@ def run_ours(a):
         Pl = P // world
         flops_alg = Pl * (2.0 * N * N + 2.0 * N * D)           # obs var + obs mean terms
         n_pad = (N + 127) // 128 * 128
-        flops_exec = Pl * (2.0 * n_pad * 128) * ((n_pad // 128) * (n_pad // 128 + 1) / 2 + n_pad / 128) \
+        nq = n_pad // 128  # executed per particle: [128 k-rows x 128 columns] blocks of the lower triangle incl. diagonal + mean tile
+        flops_exec = Pl * (2.0 * 128 ** 2) * (nq * (nq + 1) / 2 + nq) \
             if not a.dense else Pl * (2.0 * n_pad * n_pad + 2.0 * n_pad * 128)
         tf = ctypes_probe(lib)
         achieved = flops_alg / (obs_avg_ms * 1e-3) / 1e12

@@ -12,15 +12,20 @@
 // With tri = 1, L is the lower-triangular packing of K^-1 (k^T K^-1 k == k^T L k), so column tile J
 // only needs k >= 128 J: half the flops and half the bytes of the dense form.
 //
-// Kernel organisation (one persistent CTA per SM, 256 threads = 8 warps as 4 (rows) x 2 (columns)):
-//   * B tiles [16 x 128] and the 16 training-coordinate records of the k-chunk arrive through TMA 1-D
-//     bulk copies (cp.async.bulk, SASS UBLKCP) into a 4-stage shared-memory ring, completion counted
-//     on one mbarrier per stage;
-//   * the A operand (K* chunk, [16 x 128]) is generated by all 256 threads from the particle records
-//     held in shared memory (exp of an FMA chain; + the linear kernel for the dynamics GP) into a
-//     double-buffered shared tile -- the "GEMM prologue from latent coordinates";
-//   * fp64 tensor-core MMAs (mma.sync m8n8k4, the fastest DMMA shape on sm_100a, see
-//     profiles/microbench) accumulate a 32 x 64 warp tile = 64 accumulators per lane;
+// Kernel organisation (one persistent CTA per SM, 384 threads = 3 warpgroups, warp-specialised because
+// on sm_100a the fp64 MMA runs on the tensor pipe while exp()/DFMA run on the separate fp64 pipe --
+// ncu: sm__pipe_tensor_subpipe_dmma vs sm__pipe_fp64 -- so the K* prologue can overlap the MMAs):
+//   * warpgroup 0 (4 warps, one per SM sub-partition) is the PRODUCER: it generates the A operand
+//     (K* chunk [16 x 128], exp of an FMA chain over the particle/training records, + the linear kernel
+//     for the dynamics GP) into a 3-deep shared ring -- the "GEMM prologue from latent coordinates" --
+//     and its warp 0 also feeds the B ring: B tiles [16 x 128] of L / alpha arrive through TMA 1-D bulk
+//     copies (cp.async.bulk, SASS UBLKCP) into a 6-stage ring, completion counted on mbarriers;
+//   * warpgroups 1-2 (8 warps as 4 (rows) x 2 (columns)) are the CONSUMERS: fp64 tensor-core MMAs
+//     (mma.sync m8n8k4, the fastest DMMA shape on sm_100a, see profiles/microbench) accumulate a
+//     32 x 64 warp tile = 64 accumulators per lane, then run the fused epilogues;
+//   * producers hand registers to the consumers with setmaxnreg (56 vs 224 per thread);
+//   * rings are synchronised only by mbarriers (full/empty); the CTA-wide barrier is used once per
+//     128-particle tile;
 //   * shared tiles use a +4 double row padding, which makes both fragment loads bank-conflict free
 //     for the m8n8k4 lane layout (address = (lane&3)*132 + lane>>2 (+const) covers 16 distinct 8-byte
 //     banks per half warp);
@@ -29,16 +34,22 @@
 #include <math.h>
 
 #include "common.cuh"
+#include "fast_exp.cuh"
 
 namespace gpmdm {
 
 constexpr int TM = GPMDM_TILE;  // particles per tile
 constexpr int TN = GPMDM_TILE;  // columns per column tile
 constexpr int KC = 16;          // k rows per chunk
-constexpr int STAGES = 4;
+constexpr int BSTAGES = 6;      // B ring depth (TMA)
+constexpr int ASTAGES = 3;      // A ring depth (generated K*)
+constexpr int BAHEAD = BSTAGES - ASTAGES;  // B chunks in flight ahead of the producer's A chunk
 constexpr int LDB = TN + 4;
 constexpr int LDA = TM + 4;
-constexpr int NTHREADS = 256;
+constexpr int NPROD = 128;                 // producer threads (warpgroup 0)
+constexpr int NCONS = 256;                 // consumer threads (warpgroups 1-2)
+constexpr int NTHREADS = NPROD + NCONS;
+constexpr int PROD_REGS = 72, CONS_REGS = 216;  // 128*72 + 256*216 == 384*168
 constexpr int MAXD = GPMDM_MAX_LATENT;
 constexpr int REC_MAX = 2 * MAXD + 1;
 
@@ -68,282 +79,376 @@ struct PredictParams {
 };
 
 struct __align__(128) Smem {
-    double B[STAGES][KC][LDB];
-    double R[STAGES][KC * REC_MAX];
-    double A[2][KC][LDA];
+    double B[BSTAGES][KC][LDB];
+    double A[ASTAGES][KC][LDA];
     double Pb[MAXD + 1][TM];  // b_k = x_k / l_k ; row d holds -|b|^2
     double Px[MAXD][TM];      // raw x (linear kernel)
     double prior[TM];
     double vrow[TM];
     double red[2][TM];
-    uint64_t full[STAGES];
+    uint64_t b_full[BSTAGES], b_empty[BSTAGES], a_full[ASTAGES], a_empty[ASTAGES];
     int pidx[TM];
     int tile;
 };
 
 template <int KIND, int DL>
-__device__ __forceinline__ double kstar_from_records(const double* __restrict__ rec, const double (&pb)[MAXD + 1],
-                                                     const double (&px)[MAXD], int d, double c2last) {
+__device__ __forceinline__ double kstar_from_records(const double (&rec)[REC_MAX], const double (&pb)[MAXD + 1],
+                                                     const double (&px)[MAXD], double c2last) {
+    constexpr int d = DL;
     double arg = rec[d] + pb[d];
 #pragma unroll
-    for (int j = 0; j < MAXD; j++)
-        if (j < d) arg = fma(rec[j], pb[j], arg);
-    double val = exp(arg);
+    for (int j = 0; j < d; j++) arg = fma(rec[j], pb[j], arg);
+    double val = fast_exp(arg);
     if (KIND == 1) {
         double lin = c2last;
 #pragma unroll
-        for (int j = 0; j < MAXD; j++)
-            if (j < d) lin = fma(rec[d + 1 + j], px[j], lin);
+        for (int j = 0; j < d; j++) lin = fma(rec[d + 1 + j], px[j], lin);
         val += lin;
     }
     return val;
 }
 
 template <int KIND, int DL>
+__device__ __forceinline__ void load_record(const double* __restrict__ src, double (&rec)[REC_MAX]) {
+    constexpr int REC = KIND == 1 ? 2 * DL + 1 : DL + 1;
+    if (REC % 2 == 0) {  // 16-byte aligned records: vector loads
+#pragma unroll
+        for (int q = 0; q < REC; q += 2) {
+            const double2 v = __ldg(reinterpret_cast<const double2*>(src + q));
+            rec[q] = v.x;
+            rec[q + 1] = v.y;
+        }
+    } else {
+#pragma unroll
+        for (int q = 0; q < REC; q++) rec[q] = __ldg(src + q);
+    }
+}
+
+// K* for NB consecutive training rows and one particle, evaluated stage by stage across the batch so that the
+// NB exponentials form independent instruction chains (one producer warp per SM sub-partition has to hide the
+// fp64 pipe latency by itself).
+template <int KIND, int DL, int NB>
+__device__ __forceinline__ void kstar_batch(const double* __restrict__ rbase, const double (&pb)[MAXD + 1],
+                                            const double (&px)[MAXD], double c2last, double (&out)[NB]) {
+    constexpr int d = DL;
+    constexpr int REC = KIND == 1 ? 2 * d + 1 : d + 1;
+    double r[NB], lin[NB];
+    int n[NB];
+#pragma unroll
+    for (int b = 0; b < NB; b++) {
+        double rec[REC_MAX];
+        load_record<KIND, DL>(rbase + b * REC, rec);
+        double arg = rec[d] + pb[d];
+#pragma unroll
+        for (int j = 0; j < d; j++) arg = fma(rec[j], pb[j], arg);
+        if (KIND == 1) {
+            double l = c2last;
+#pragma unroll
+            for (int j = 0; j < d; j++) l = fma(rec[d + 1 + j], px[j], l);
+            lin[b] = l;
+        }
+        r[b] = exp_reduce(arg, n[b]);
+    }
+    constexpr double C[14] = {1.0, 1.0, 0.5, 1.0 / 6.0, 1.0 / 24.0, 1.0 / 120.0, 1.0 / 720.0, 1.0 / 5040.0,
+                              1.0 / 40320.0, 1.0 / 362880.0, 1.0 / 3628800.0, 1.0 / 39916800.0,
+                              1.0 / 479001600.0, 1.0 / 6227020800.0};
+    double p[NB];
+#pragma unroll
+    for (int b = 0; b < NB; b++) p[b] = C[13];
+#pragma unroll
+    for (int k = 12; k >= 0; k--)
+#pragma unroll
+        for (int b = 0; b < NB; b++) p[b] = fma(p[b], r[b], C[k]);
+#pragma unroll
+    for (int b = 0; b < NB; b++) {
+        const double v = exp_scale(p[b], n[b]);
+        out[b] = KIND == 1 ? v + lin[b] : v;
+    }
+}
+
+// Chunk schedule of one particle tile: column tile ct covers k-chunks [kbeg(ct), nkc).
+struct ChunkCursor {
+    int ct, k, nq, nct, nkc, tri;
+    __device__ __forceinline__ int kbeg(int t) const { return (tri && t < nq) ? t * (TN / KC) : 0; }
+    __device__ __forceinline__ void init(int nq_, int nct_, int nkc_, int tri_) {
+        nq = nq_, nct = nct_, nkc = nkc_, tri = tri_, ct = 0, k = 0;
+    }
+    __device__ __forceinline__ bool done() const { return ct >= nct; }
+    __device__ __forceinline__ void next() {
+        if (++k == nkc) {
+            ct++;
+            k = kbeg(ct);
+        }
+    }
+};
+
+template <int KIND, int DL>
 __global__ void __launch_bounds__(NTHREADS, 1) gp_predict_kernel(const PredictParams prm) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     Smem& s = *reinterpret_cast<Smem*>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int wm = warp & 3, wn = warp >> 2;
-    const int r = lane >> 2, c = lane & 3;
-    const int d = DL > 0 ? DL : prm.d;
-    const int REC = KIND == 1 ? 2 * d + 1 : d + 1;
+    constexpr int d = DL;
+    constexpr int REC = KIND == 1 ? 2 * d + 1 : d + 1;
     const double c2last = KIND == 1 ? prm.lin_c2[d] : 0.0;
+    const bool is_producer = warp < NPROD / 32;
 
     if (tid == 0) {
-        for (int i = 0; i < STAGES; i++) mbar_init(&s.full[i], 1);
+        for (int i = 0; i < BSTAGES; i++) {
+            mbar_init(&s.b_full[i], 1);           // one arrive.expect_tx + TMA bytes
+            mbar_init(&s.b_empty[i], NCONS / 32);  // one arrival per consumer warp
+        }
+        for (int i = 0; i < ASTAGES; i++) {
+            mbar_init(&s.a_full[i], NPROD);        // every producer thread
+            mbar_init(&s.a_empty[i], NCONS / 32);
+        }
         mbar_fence_init();
     }
     __syncthreads();
 
     const int total_tiles = prm.tiles ? *prm.n_tiles : (int)((prm.P + TM - 1) / TM);
-    uint32_t g = 0;  // chunks consumed by this CTA so far (selects ring stage and mbarrier parity)
+    uint32_t g = 0;   // chunks processed by this role so far (ring positions and mbarrier parities)
 
-    for (;;) {
-        if (tid == 0) s.tile = atomicAdd(prm.counter, 1);
-        __syncthreads();
-        const int t = s.tile;
-        if (t >= total_tiles) break;
-        int blk = 0, first = t * TM, count;
-        if (prm.tiles) {
-            blk = prm.tiles[4 * t + 0];
-            first = prm.tiles[4 * t + 1];
-            count = prm.tiles[4 * t + 2];
-        } else {
-            long long rem = prm.P - (long long)first;
-            count = rem < TM ? (int)rem : TM;
-        }
-        const gpmdm_gp_block gb = prm.blocks[blk];
-        const int n_pad = (int)gb.n_pad;
-        const int nkc = n_pad / KC;
-        const int nq = n_pad / TN;           // column tiles of L
-        const int nct = nq + prm.alpha_ld / TN;  // + column tiles of alpha
+    // Per-tile geometry, recomputed identically by both roles from s.tile.
+#define GPMDM_TILE_GEOMETRY()                                                   \
+    const int t = s.tile;                                                       \
+    if (t >= total_tiles) break;                                                \
+    int blk = 0, first = t * TM, count;                                         \
+    if (prm.tiles) {                                                            \
+        blk = prm.tiles[4 * t + 0];                                             \
+        first = prm.tiles[4 * t + 1];                                           \
+        count = prm.tiles[4 * t + 2];                                           \
+    } else {                                                                    \
+        long long rem = prm.P - (long long)first;                               \
+        count = rem < TM ? (int)rem : TM;                                       \
+    }                                                                           \
+    const gpmdm_gp_block gbk = prm.blocks[blk];                                 \
+    const int n_pad = (int)gbk.n_pad;                                           \
+    const int nkc = n_pad / KC;                                                 \
+    const int nq = n_pad / TN;              /* column tiles of L */             \
+    const int nct = nq + prm.alpha_ld / TN; /* + column tiles of alpha */       \
+    (void)first; (void)count;                                                   \
+    ChunkCursor cur;                                                            \
+    cur.init(nq, nct, nkc, prm.tri)
 
-        // ---- particle records -------------------------------------------------------------------
-        if (tid < TM) {
-            const int m = tid < count ? tid : count - 1;
-            const int p = prm.perm ? prm.perm[first + m] : first + m;
-            s.pidx[tid] = tid < count ? p : -1;
-            double nb = 0.0, prior = 1.0;
-            for (int j = 0; j < d; j++) {
-                const double xj = prm.x[(long long)p * d + j];
-                const double bj = xj / prm.ls[j];
-                s.Pb[j][tid] = bj;
-                nb = fma(bj, bj, nb);
-                if (KIND == 1) {
-                    s.Px[j][tid] = xj;
-                    prior = fma(prm.lin_c2[j] * xj, xj, prior);
+    // The two roles never re-converge after setmaxnreg (ptxas allocates registers per role only then).
+    if (is_producer) {
+        setmaxnreg_dec<PROD_REGS>();
+        uint32_t gb = 0;  // warp 0: B chunks issued so far
+        for (;;) {
+            if (tid == 0) s.tile = atomicAdd(prm.counter, 1);
+            named_bar_sync(2, NPROD);
+            GPMDM_TILE_GEOMETRY();
+            // ---- particle records ------------------------------------------------------------------
+            {
+                const int m = tid < count ? tid : count - 1;
+                const int p = prm.perm ? prm.perm[first + m] : first + m;
+                s.pidx[tid] = tid < count ? p : -1;
+                double nb = 0.0, prior = 1.0;
+#pragma unroll
+                for (int j = 0; j < d; j++) {
+                    const double xj = prm.x[(long long)p * d + j];
+                    const double bj = xj / prm.ls[j];
+                    s.Pb[j][tid] = bj;
+                    nb = fma(bj, bj, nb);
+                    if (KIND == 1) {
+                        s.Px[j][tid] = xj;
+                        prior = fma(prm.lin_c2[j] * xj, xj, prior);
+                    }
                 }
+                s.Pb[d][tid] = -nb;
+                if (KIND == 1) prior += c2last;
+                s.prior[tid] = prior;
             }
-            s.Pb[d][tid] = -nb;
-            if (KIND == 1) prior += c2last;
-            s.prior[tid] = prior;
-        }
-        __syncthreads();
+            named_bar_sync(0, NTHREADS);  // tile + records visible to the consumers
 
-        // ---- chunk schedule: column tile ct covers k chunks [kbeg(ct), nkc) -------------------------
-        int total_chunks = 0;
-        for (int ct = 0; ct < nct; ct++) total_chunks += nkc - ((prm.tri && ct < nq) ? ct * (TN / KC) : 0);
-        int issued = 0, pct = 0, pk = 0;  // producer cursor (warp 0)
 
-#define GPMDM_ISSUE_CHUNK(chunk_global_index)                                                          \
-    do {                                                                                               \
-        const int st_ = (int)((chunk_global_index) % STAGES);                                          \
-        const double* src_;                                                                            \
-        int ld_;                                                                                       \
-        if (pct < nq) {                                                                                \
-            src_ = gb.L + (long long)pct * TN;                                                         \
-            ld_ = n_pad;                                                                               \
-        } else {                                                                                       \
-            src_ = gb.alpha + (long long)(pct - nq) * TN;                                              \
-            ld_ = prm.alpha_ld;                                                                        \
-        }                                                                                              \
-        if (lane == 0) mbar_expect_tx(&s.full[st_], (uint32_t)(KC * TN * 8 + KC * REC * 8));           \
-        __syncwarp();                                                                                  \
-        if (lane < KC)                                                                                 \
-            bulk_g2s(&s.B[st_][lane][0], src_ + (long long)(pk * KC + lane) * ld_, TN * 8, &s.full[st_]); \
-        else if (lane == KC)                                                                           \
-            bulk_g2s(&s.R[st_][0], gb.coords + (long long)pk * KC * REC, (uint32_t)(KC * REC * 8),     \
-                     &s.full[st_]);                                                                    \
-        pk++;                                                                                          \
-        if (pk == nkc) {                                                                               \
-            pct++;                                                                                     \
-            pk = (prm.tri && pct < nq) ? pct * (TN / KC) : 0;                                          \
-        }                                                                                              \
-        issued++;                                                                                      \
-    } while (0)
-
-        if (warp == 0) {
-            for (int i = 0; i < STAGES - 1 && issued < total_chunks; i++) GPMDM_ISSUE_CHUNK(g + (uint32_t)i);
-        }
-
-        double qacc[4] = {0.0, 0.0, 0.0, 0.0};
-        double sacc[4] = {0.0, 0.0, 0.0, 0.0};
-        int local = 0;  // chunks consumed in this tile
-
-        for (int ct = 0; ct < nct; ct++) {
-            double acc[4][8][2];
-#pragma unroll
-            for (int i = 0; i < 4; i++)
-#pragma unroll
-                for (int j = 0; j < 8; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
-
-            const int kbeg = (prm.tri && ct < nq) ? ct * (TN / KC) : 0;
-            for (int k = kbeg; k < nkc; k++, g++, local++) {
-                const int stage = (int)(g % STAGES);
-                const int buf = (int)(g & 1);
-                mbar_wait(&s.full[stage], (g / STAGES) & 1);
-
-                // -- prologue: K* chunk [KC x TM] from the records -----------------------------------
-                {
-                    const int p = tid & (TM - 1), half = tid >> 7;
-                    double pb[MAXD + 1], px[MAXD];
-#pragma unroll
-                    for (int j = 0; j < MAXD; j++) {
-                        pb[j] = j < d ? s.Pb[j][p] : 0.0;
-                        px[j] = (KIND == 1 && j < d) ? s.Px[j][p] : 0.0;
-                    }
-                    pb[d] = s.Pb[d][p];
-                    // (for DL == 0 pb[d] above is a dynamic index: fall back to local memory is avoided
-                    //  because every supported d is a template instantiation)
-                    const double* R = &s.R[stage][0];
-#pragma unroll
-                    for (int kk = 0; kk < KC / 2; kk++) {
-                        const int kr = half * (KC / 2) + kk;
-                        s.A[buf][kr][p] = kstar_from_records<KIND, DL>(R + kr * REC, pb, px, d, c2last);
-                    }
+            // ======================= PRODUCER: B ring (warp 0, TMA) + A ring (K* generation) =================
+            ChunkCursor bcur = cur;  // B cursor runs BAHEAD chunks ahead of the A cursor
+            auto issue_b = [&]() {
+                const int st = (int)(gb % BSTAGES);
+                mbar_wait(&s.b_empty[st], ((gb / BSTAGES) & 1) ^ 1);  // first pass: passes immediately
+                const double* src;
+                int ld;
+                if (bcur.ct < nq) {
+                    src = gbk.L + (long long)bcur.ct * TN;
+                    ld = n_pad;
+                } else {
+                    src = gbk.alpha + (long long)(bcur.ct - nq) * TN;
+                    ld = prm.alpha_ld;
                 }
-                __syncthreads();
-                // every warp is past the MMAs of chunk g-1: its ring stage is free again
-                if (warp == 0 && issued < total_chunks) GPMDM_ISSUE_CHUNK(g + (uint32_t)(STAGES - 1));
+                if (lane == 0) mbar_expect_tx(&s.b_full[st], (uint32_t)(KC * TN * 8));
+                __syncwarp();
+                if (lane < KC)
+                    bulk_g2s(&s.B[st][lane][0], src + (long long)(bcur.k * KC + lane) * ld, TN * 8, &s.b_full[st]);
+                bcur.next();
+                gb++;
+            };
+            if (warp == 0)
+                for (int i = 0; i < BAHEAD && !bcur.done(); i++) issue_b();
 
-                // -- fp64 tensor-core MMAs -------------------------------------------------------------
+            const int p = tid;  // this thread's particle row
+            double pb[MAXD + 1], px[MAXD];
 #pragma unroll
-                for (int k4 = 0; k4 < KC / 4; k4++) {
-                    double a[4], b[8];
-#pragma unroll
-                    for (int i = 0; i < 4; i++) a[i] = s.A[buf][k4 * 4 + c][wm * 32 + i * 8 + r];
-#pragma unroll
-                    for (int j = 0; j < 8; j++) b[j] = s.B[stage][k4 * 4 + c][wn * 64 + j * 8 + r];
-#pragma unroll
-                    for (int i = 0; i < 4; i++)
-#pragma unroll
-                        for (int j = 0; j < 8; j++) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
-                }
+            for (int j = 0; j < MAXD; j++) {
+                pb[j] = j < d ? s.Pb[j][p] : 0.0;
+                px[j] = (KIND == 1 && j < d) ? s.Px[j][p] : 0.0;
             }
+            pb[d] = s.Pb[d][p];
 
-            // ---- epilogues ---------------------------------------------------------------------------
-            if (ct < nq) {
-                // q[p] += sum_n C[p,n] * K*[p,n] over this tile's columns (K* regenerated per element)
+            for (; !cur.done(); cur.next(), g++) {
+                if (warp == 0 && !bcur.done()) issue_b();
+                const int buf = (int)(g % ASTAGES);
+                mbar_wait(&s.a_empty[buf], ((g / ASTAGES) & 1) ^ 1);
+                const double* rbase = gbk.coords + (long long)cur.k * KC * REC;
+                constexpr int NB = 8;
+#pragma unroll 1
+                for (int k0 = 0; k0 < KC; k0 += NB) {
+                    double kv[NB];
+                    kstar_batch<KIND, DL, NB>(rbase + k0 * REC, pb, px, c2last, kv);
 #pragma unroll
-                for (int j = 0; j < 8; j++) {  // fully unrolled: acc[][][] must stay in registers
+                    for (int b = 0; b < NB; b++) s.A[buf][k0 + b][p] = kv[b];
+                }
+                mbar_arrive(&s.a_full[buf]);
+            }
+            named_bar_sync(0, NTHREADS);  // consumers are done with s.Pb / s.pidx / s.tile
+        }
+        // the "no more tiles" value of s.tile must reach the consumers too
+        named_bar_sync(0, NTHREADS);
+    } else {
+        setmaxnreg_inc<CONS_REGS>();
+        for (;;) {
+            named_bar_sync(0, NTHREADS);
+            GPMDM_TILE_GEOMETRY();
+            // ======================= CONSUMERS: DMMA main loop + fused epilogues ==============================
+            const int cw = warp - NPROD / 32;
+            const int wm = cw & 3, wn = cw >> 2;
+            const int r = lane >> 2, c = lane & 3;
+            const int ctid = tid - NPROD;
+            double qacc[4] = {0.0, 0.0, 0.0, 0.0};
+            double sacc[4] = {0.0, 0.0, 0.0, 0.0};
+
+            for (int ct = 0; ct < nct; ct++) {
+                double acc[4][8][2];
 #pragma unroll
-                    for (int e = 0; e < 2; e++) {
-                        const int n = ct * TN + wn * 64 + j * 8 + c * 2 + e;
-                        const double* rec = gb.coords + (long long)n * REC;
-                        double rr[REC_MAX];
+                for (int i = 0; i < 4; i++)
 #pragma unroll
-                        for (int q = 0; q < REC_MAX; q++) rr[q] = q < REC ? __ldg(rec + q) : 0.0;
+                    for (int j = 0; j < 8; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+                const int kbeg = cur.kbeg(ct);
+                for (int k = kbeg; k < nkc; k++, g++) {
+                    const int bst = (int)(g % BSTAGES), ast = (int)(g % ASTAGES);
+                    mbar_wait(&s.a_full[ast], (g / ASTAGES) & 1);
+                    mbar_wait(&s.b_full[bst], (g / BSTAGES) & 1);
 #pragma unroll
-                        for (int i = 0; i < 4; i++) {
-                            const int m = wm * 32 + i * 8 + r;
-                            double pb[MAXD + 1], px[MAXD];
+                    for (int k4 = 0; k4 < KC / 4; k4++) {
+                        double a[4], b[8];
 #pragma unroll
-                            for (int q = 0; q < MAXD; q++) {
-                                pb[q] = q < d ? s.Pb[q][m] : 0.0;
-                                px[q] = (KIND == 1 && q < d) ? s.Px[q][m] : 0.0;
-                            }
-                            pb[d] = s.Pb[d][m];
-                            const double kv = kstar_from_records<KIND, DL>(rr, pb, px, d, c2last);
-                            qacc[i] = fma(acc[i][j][e], kv, qacc[i]);
-                        }
+                        for (int i = 0; i < 4; i++) a[i] = s.A[ast][k4 * 4 + c][wm * 32 + i * 8 + r];
+#pragma unroll
+                        for (int j = 0; j < 8; j++) b[j] = s.B[bst][k4 * 4 + c][wn * 64 + j * 8 + r];
+#pragma unroll
+                        for (int i = 0; i < 4; i++)
+#pragma unroll
+                            for (int j = 0; j < 8; j++) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+                    }
+                    __syncwarp();
+                    if (lane == 0) {  // this warp is done reading both ring slots
+                        mbar_arrive(&s.a_empty[ast]);
+                        mbar_arrive(&s.b_empty[bst]);
                     }
                 }
-                if (ct == nq - 1) {
-                    // quadratic form complete: v[p] = prior[p] - q[p]
+
+                // ---- epilogues ---------------------------------------------------------------------------
+                if (ct < nq) {
+                    // q[p] += sum_n C[p,n] * K*[p,n] over this tile's columns (K* regenerated per element)
 #pragma unroll
-                    for (int i = 0; i < 4; i++) {
-                        double v = qacc[i];
-                        v += __shfl_xor_sync(0xffffffffu, v, 1);
-                        v += __shfl_xor_sync(0xffffffffu, v, 2);
-                        if (c == 0) s.red[wn][wm * 32 + i * 8 + r] = v;
-                    }
-                    __syncthreads();
-                    if (tid < TM) s.vrow[tid] = s.prior[tid] - (s.red[0][tid] + s.red[1][tid]);
-                    __syncthreads();
-                }
-            } else {
-                const int cbase = (ct - nq) * TN + wn * 64;
-#pragma unroll
-                for (int i = 0; i < 4; i++) {
-                    const int m = wm * 32 + i * 8 + r;
-                    const int p = s.pidx[m];
-#pragma unroll
-                    for (int j = 0; j < 8; j++) {
+                    for (int j = 0; j < 8; j++) {  // fully unrolled: acc[][][] must stay in registers
 #pragma unroll
                         for (int e = 0; e < 2; e++) {
-                            const int col = cbase + j * 8 + c * 2 + e;
-                            if (col >= prm.dout) continue;
-                            const double mu = acc[i][j][e];
-                            if (KIND == 0) {
-                                if (prm.z) {
-                                    const double dz = __ldg(prm.z + col) - mu;
-                                    sacc[i] = fma(__ldg(prm.scale + col) * dz, dz, sacc[i]);
+                            const int n = ct * TN + wn * 64 + j * 8 + c * 2 + e;
+                            double rec[REC_MAX];
+                            load_record<KIND, DL>(gbk.coords + (long long)n * REC, rec);
+#pragma unroll
+                            for (int i = 0; i < 4; i++) {
+                                const int m = wm * 32 + i * 8 + r;
+                                double pb[MAXD + 1], px[MAXD];
+#pragma unroll
+                                for (int q = 0; q < MAXD; q++) {
+                                    pb[q] = q < d ? s.Pb[q][m] : 0.0;
+                                    px[q] = (KIND == 1 && q < d) ? s.Px[q][m] : 0.0;
                                 }
-                                if (prm.mu_out && p >= 0) prm.mu_out[(long long)p * prm.dout + col] = mu;
-                            } else if (p >= 0) {
-                                const double var = s.vrow[m] * __ldg(prm.scale + col);
-                                const long long o = (long long)p * prm.dout + col;
-                                if (prm.x_new)  // torch.normal: randn * std + mean, two roundings (no FMA)
-                                    prm.x_new[o] = __dadd_rn(__dmul_rn(__ldg(prm.eps + o), sqrt(var)), mu);
-                                if (prm.mean_out) prm.mean_out[o] = mu;
-                                if (prm.var_out) prm.var_out[o] = var;
+                                pb[d] = s.Pb[d][m];
+                                const double kv = kstar_from_records<KIND, DL>(rec, pb, px, c2last);
+                                qacc[i] = fma(acc[i][j][e], kv, qacc[i]);
                             }
                         }
                     }
-                }
-                if (KIND == 0 && ct == nct - 1) {
+                    if (ct == nq - 1) {
+                        // quadratic form complete: v[p] = prior[p] - q[p]
+#pragma unroll
+                        for (int i = 0; i < 4; i++) {
+                            double v = qacc[i];
+                            v += __shfl_xor_sync(0xffffffffu, v, 1);
+                            v += __shfl_xor_sync(0xffffffffu, v, 2);
+                            if (c == 0) s.red[wn][wm * 32 + i * 8 + r] = v;
+                        }
+                        named_bar_sync(1, NCONS);
+                        if (ctid < TM) s.vrow[ctid] = s.prior[ctid] - (s.red[0][ctid] + s.red[1][ctid]);
+                        named_bar_sync(1, NCONS);
+                    }
+                } else {
+                    const int cbase = (ct - nq) * TN + wn * 64;
 #pragma unroll
                     for (int i = 0; i < 4; i++) {
-                        double v = sacc[i];
-                        v += __shfl_xor_sync(0xffffffffu, v, 1);
-                        v += __shfl_xor_sync(0xffffffffu, v, 2);
-                        if (c == 0) s.red[wn][wm * 32 + i * 8 + r] = v;
+                        const int m = wm * 32 + i * 8 + r;
+                        const int p = s.pidx[m];
+#pragma unroll
+                        for (int j = 0; j < 8; j++) {
+#pragma unroll
+                            for (int e = 0; e < 2; e++) {
+                                const int col = cbase + j * 8 + c * 2 + e;
+                                if (col >= prm.dout) continue;
+                                const double mu = acc[i][j][e];
+                                if (KIND == 0) {
+                                    if (prm.z) {
+                                        const double dz = __ldg(prm.z + col) - mu;
+                                        sacc[i] = fma(__ldg(prm.scale + col) * dz, dz, sacc[i]);
+                                    }
+                                    if (prm.mu_out && p >= 0) prm.mu_out[(long long)p * prm.dout + col] = mu;
+                                } else if (p >= 0) {
+                                    const double var = s.vrow[m] * __ldg(prm.scale + col);
+                                    const long long o = (long long)p * prm.dout + col;
+                                    if (prm.x_new)  // torch.normal: randn * std + mean, two roundings (no FMA)
+                                        prm.x_new[o] = __dadd_rn(__dmul_rn(__ldg(prm.eps + o), sqrt(var)), mu);
+                                    if (prm.mean_out) prm.mean_out[o] = mu;
+                                    if (prm.var_out) prm.var_out[o] = var;
+                                }
+                            }
+                        }
                     }
-                    __syncthreads();
-                    if (tid < TM && s.pidx[tid] >= 0) {
-                        const double S = s.red[0][tid] + s.red[1][tid];
-                        const double v = s.vrow[tid];
-                        const int p = s.pidx[tid];
-                        if (prm.ll) prm.ll[p] = -0.5 * S / v - (double)prm.dout * log(v) + prm.ll_const;
-                        if (prm.v_out) prm.v_out[p] = v;
+                    if (KIND == 0 && ct == nct - 1) {
+#pragma unroll
+                        for (int i = 0; i < 4; i++) {
+                            double v = sacc[i];
+                            v += __shfl_xor_sync(0xffffffffu, v, 1);
+                            v += __shfl_xor_sync(0xffffffffu, v, 2);
+                            if (c == 0) s.red[wn][wm * 32 + i * 8 + r] = v;
+                        }
+                        named_bar_sync(1, NCONS);
+                        if (ctid < TM && s.pidx[ctid] >= 0) {
+                            const double S = s.red[0][ctid] + s.red[1][ctid];
+                            const double v = s.vrow[ctid];
+                            const int p = s.pidx[ctid];
+                            if (prm.ll) prm.ll[p] = -0.5 * S / v - (double)prm.dout * log(v) + prm.ll_const;
+                            if (prm.v_out) prm.v_out[p] = v;
+                        }
                     }
                 }
             }
+            named_bar_sync(0, NTHREADS);  // s.tile, s.pidx, s.Pb ... are rewritten by the next tile
         }
-        __syncthreads();  // s.tile, s.pidx, s.Pb ... are rewritten by the next tile
     }
-#undef GPMDM_ISSUE_CHUNK
+#undef GPMDM_TILE_GEOMETRY
 }
 
 // ---- host side -------------------------------------------------------------------------------------

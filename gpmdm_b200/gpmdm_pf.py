@@ -71,7 +71,7 @@ class GPMDM_PF:
             raise ValueError("cdf_order must be 'sequential' or 'blocked'")
         if gpmdm.dyn_back_step != 1:
             raise ValueError("the particle filter uses the dynamics GP output as the next state: dyn_back_step must be 1")
-        self._seed, self._step = int(seed), 0
+        self._seed, self._step, self._resets = int(seed), 0, 0
         self._systematic = resampling == "systematic"
         self._cdf_mode = 0 if cdf_order == "sequential" else 1
         self._tri = bool(tri)
@@ -114,7 +114,10 @@ class GPMDM_PF:
     def _init_particles(self, init_indices=None):
         P, C = self._num_particles, self.num_classes
         n_per_class = self._divide_into_n_parts(P, C)
-        parts, classes = [], []
+        parts = []
+        # seeded so that every rank of a multi-GPU run draws the same (replicated) initial cloud
+        gen = torch.Generator(device=self.device)
+        gen.manual_seed(self._seed + 0x5EED * (self._resets + 1))
         for i in range(C):
             class_data = self._gpmdm.get_X_for_class(i)
             if init_indices is not None:
@@ -122,11 +125,13 @@ class GPMDM_PF:
                 if idx.numel() != n_per_class[i]:
                     raise ValueError("init_indices[%d] must hold %d indices" % (i, n_per_class[i]))
             else:
-                idx = torch.randint(0, class_data.size(0), (n_per_class[i],), device=self.device)
+                idx = torch.randint(0, class_data.size(0), (n_per_class[i],), device=self.device, generator=gen)
             parts.append(class_data[idx].detach().clone())
-            classes += [i] * n_per_class[i]
+        self._resets += 1
         self._particle_states = torch.cat(parts, dim=0).contiguous()
-        self._particle_classes = torch.tensor(classes, dtype=torch.int64, device=self.device)
+        self._particle_classes = torch.repeat_interleave(
+            torch.arange(C, dtype=torch.int64, device=self.device),
+            torch.tensor(n_per_class, dtype=torch.int64, device=self.device))
         self._log_likelihoods = torch.zeros(P, dtype=self.dtype, device=self.device)
         self._log_weights = torch.zeros(P, dtype=self.dtype, device=self.device)
         self._weights = torch.ones(P, dtype=self.dtype, device=self.device) / P
