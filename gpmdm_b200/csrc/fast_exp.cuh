@@ -50,6 +50,21 @@ __host__ __device__ __forceinline__ double exp_poly(double r) {
     return p;
 }
 
+// Two polynomials side by side (independent chains for the instruction scheduler).
+__host__ __device__ __forceinline__ void exp_poly2(double r0, double r1, double& e0, double& e1) {
+    constexpr double C[14] = {1.0, 1.0, 0.5, 1.0 / 6.0, 1.0 / 24.0, 1.0 / 120.0, 1.0 / 720.0, 1.0 / 5040.0,
+                              1.0 / 40320.0, 1.0 / 362880.0, 1.0 / 3628800.0, 1.0 / 39916800.0,
+                              1.0 / 479001600.0, 1.0 / 6227020800.0};
+    double p0 = C[13], p1 = C[13];
+#pragma unroll
+    for (int k = 12; k >= 0; k--) {
+        p0 = fma(p0, r0, C[k]);
+        p1 = fma(p1, r1, C[k]);
+    }
+    e0 = p0;
+    e1 = p1;
+}
+
 // Stage 3: p * 2^n
 __host__ __device__ __forceinline__ double exp_scale(double p, int n) {
     if (n < -1021) return 0.0;

@@ -12,23 +12,26 @@
 // With tri = 1, L is the lower-triangular packing of K^-1 (k^T K^-1 k == k^T L k), so column tile J
 // only needs k >= 128 J: half the flops and half the bytes of the dense form.
 //
-// Kernel organisation (one persistent CTA per SM, 384 threads = 3 warpgroups, warp-specialised because
-// on sm_100a the fp64 MMA runs on the tensor pipe while exp()/DFMA run on the separate fp64 pipe --
-// ncu: sm__pipe_tensor_subpipe_dmma vs sm__pipe_fp64 -- so the K* prologue can overlap the MMAs):
-//   * warpgroup 0 (4 warps, one per SM sub-partition) is the PRODUCER: it generates the A operand
-//     (K* chunk [16 x 128], exp of an FMA chain over the particle/training records, + the linear kernel
-//     for the dynamics GP) into a 3-deep shared ring -- the "GEMM prologue from latent coordinates" --
-//     and its warp 0 also feeds the B ring: B tiles [16 x 128] of L / alpha arrive through TMA 1-D bulk
-//     copies (cp.async.bulk, SASS UBLKCP) into a 6-stage ring, completion counted on mbarriers;
-//   * warpgroups 1-2 (8 warps as 4 (rows) x 2 (columns)) are the CONSUMERS: fp64 tensor-core MMAs
-//     (mma.sync m8n8k4, the fastest DMMA shape on sm_100a, see profiles/microbench) accumulate a
-//     32 x 64 warp tile = 64 accumulators per lane, then run the fused epilogues;
-//   * producers hand registers to the consumers with setmaxnreg (56 vs 224 per thread);
-//   * rings are synchronised only by mbarriers (full/empty); the CTA-wide barrier is used once per
-//     128-particle tile;
-//   * shared tiles use a +4 double row padding, which makes both fragment loads bank-conflict free
-//     for the m8n8k4 lane layout (address = (lane&3)*132 + lane>>2 (+const) covers 16 distinct 8-byte
-//     banks per half warp);
+// Kernel organisation (one persistent CTA per SM, 256 threads = 8 warps; measured facts that shaped it, see
+// profiles/: on sm_100a DMMA (sm__pipe_tensor_subpipe_dmma) and DFMA/exp (sm__pipe_fp64) contend for ONE
+// fp64 math datapath of 64 FMA/clk/SM -- a warp-specialised producer/consumer split only moved the K*
+// prologue into `stall_math` behind the consumers' DMMAs -- so the goal is zero idle time on that datapath
+// and as few non-MMA fp64 instructions as possible):
+//   * each warp owns 16 particle rows x all 128 columns of the column tile (64 accumulators per lane), so
+//     every lane GENERATES EXACTLY ITS OWN A FRAGMENTS: the K* values it feeds to mma.sync (rows r, r+8;
+//     k = 4 k4 + c) are computed in registers from the particle record (registers) and the training
+//     records of the chunk (shared memory) -- the "GEMM prologue from latent coordinates" -- with no A tile
+//     in shared memory, no redundancy between warps and no block-wide barrier in the main loop;
+//   * the exponentials for chunk g+1 are software-pipelined into the DMMA stream of chunk g (custom
+//     fast_exp, csrc/fast_exp.cuh), so the datapath always has an instruction to run;
+//   * B tiles [16 x 128] of L / alpha and the 16 training records of the chunk arrive through TMA 1-D bulk
+//     copies (cp.async.bulk, SASS UBLKCP) into an 8-stage shared ring; full/empty mbarriers are the only
+//     synchronisation between warps (the issuing duty rotates over the warps, 4 chunks ahead);
+//   * fp64 tensor-core MMAs are mma.sync m8n8k4, the fastest DMMA shape on sm_100a (profiles/microbench);
+//   * the +4 double row padding of the B ring makes the fragment loads bank-conflict free for the m8n8k4
+//     lane layout (address = (lane&3)*132 + lane>>2 (+const) covers 16 distinct 8-byte banks per half warp);
+//   * epilogues (Hadamard row-sum for the quadratic form, log-likelihood / Gaussian draw) are per warp:
+//     a row's 128 columns live in the 4 lanes of a quad, reductions are two shuffles;
 //   * tiles are handed out through an atomic counter, so class-sorted dynamics tiles of different
 //     block sizes balance across SMs.  Row results do not depend on tile assignment.
 #include <math.h>
@@ -41,17 +44,15 @@ namespace gpmdm {
 constexpr int TM = GPMDM_TILE;  // particles per tile
 constexpr int TN = GPMDM_TILE;  // columns per column tile
 constexpr int KC = 16;          // k rows per chunk
-constexpr int BSTAGES = 6;      // B ring depth (TMA)
-constexpr int ASTAGES = 3;      // A ring depth (generated K*)
-constexpr int BAHEAD = BSTAGES - ASTAGES;  // B chunks in flight ahead of the producer's A chunk
+constexpr int STAGES = 8;       // B / record ring depth (TMA)
+constexpr int AHEAD = 4;        // chunks in flight ahead of the consumers
 constexpr int LDB = TN + 4;
-constexpr int LDA = TM + 4;
-constexpr int NPROD = 128;                 // producer threads (warpgroup 0)
-constexpr int NCONS = 256;                 // consumer threads (warpgroups 1-2)
-constexpr int NTHREADS = NPROD + NCONS;
-constexpr int PROD_REGS = 72, CONS_REGS = 216;  // 128*72 + 256*216 == 384*168
+constexpr int NTHREADS = 256;
+constexpr int NWARPS = NTHREADS / 32;
 constexpr int MAXD = GPMDM_MAX_LATENT;
-constexpr int REC_MAX = 2 * MAXD + 1;
+constexpr int REC_MAX = 2 * MAXD;
+// training record width: a_i[0..d) (+ c_k^2 x_i[k] for the dynamics GP), padded to an even number of doubles
+__host__ __device__ constexpr int rec_width(int kind, int d) { return ((kind == 1 ? 2 * d : d) + 1) & ~1; }
 
 struct PredictParams {
     const gpmdm_gp_block* blocks;
@@ -79,90 +80,65 @@ struct PredictParams {
 };
 
 struct __align__(128) Smem {
-    double B[BSTAGES][KC][LDB];
-    double A[ASTAGES][KC][LDA];
-    double Pb[MAXD + 1][TM];  // b_k = x_k / l_k ; row d holds -|b|^2
-    double Px[MAXD][TM];      // raw x (linear kernel)
-    double prior[TM];
-    double vrow[TM];
-    double red[2][TM];
-    uint64_t b_full[BSTAGES], b_empty[BSTAGES], a_full[ASTAGES], a_empty[ASTAGES];
-    int pidx[TM];
+    double B[STAGES][KC][LDB];
+    double R[STAGES][KC * REC_MAX];
+    uint64_t full[STAGES], empty[STAGES];
     int tile;
 };
 
+// Per-lane particle record: b_k = x_k / l_k, and raw x for the linear kernel.
 template <int KIND, int DL>
-__device__ __forceinline__ double kstar_from_records(const double (&rec)[REC_MAX], const double (&pb)[MAXD + 1],
-                                                     const double (&px)[MAXD], double c2last) {
-    constexpr int d = DL;
-    double arg = rec[d] + pb[d];
-#pragma unroll
-    for (int j = 0; j < d; j++) arg = fma(rec[j], pb[j], arg);
-    double val = fast_exp(arg);
-    if (KIND == 1) {
-        double lin = c2last;
-#pragma unroll
-        for (int j = 0; j < d; j++) lin = fma(rec[d + 1 + j], px[j], lin);
-        val += lin;
-    }
-    return val;
-}
+struct ParticleRec {
+    double b[DL];
+    double x[KIND == 1 ? DL : 1];
+};
 
 template <int KIND, int DL>
 __device__ __forceinline__ void load_record(const double* __restrict__ src, double (&rec)[REC_MAX]) {
-    constexpr int REC = KIND == 1 ? 2 * DL + 1 : DL + 1;
-    if (REC % 2 == 0) {  // 16-byte aligned records: vector loads
+    constexpr int REC = rec_width(KIND, DL);  // even: 16-byte vector loads (shared or global)
 #pragma unroll
-        for (int q = 0; q < REC; q += 2) {
-            const double2 v = __ldg(reinterpret_cast<const double2*>(src + q));
-            rec[q] = v.x;
-            rec[q + 1] = v.y;
-        }
-    } else {
-#pragma unroll
-        for (int q = 0; q < REC; q++) rec[q] = __ldg(src + q);
+    for (int q = 0; q < REC; q += 2) {
+        const double2 v = *reinterpret_cast<const double2*>(src + q);
+        rec[q] = v.x;
+        rec[q + 1] = v.y;
     }
 }
 
-// K* for NB consecutive training rows and one particle, evaluated stage by stage across the batch so that the
-// NB exponentials form independent instruction chains (one producer warp per SM sub-partition has to hide the
-// fp64 pipe latency by itself).
-template <int KIND, int DL, int NB>
-__device__ __forceinline__ void kstar_batch(const double* __restrict__ rbase, const double (&pb)[MAXD + 1],
-                                            const double (&px)[MAXD], double c2last, double (&out)[NB]) {
+// K* of one training record against two particle rows, evaluated stage by stage so that the two
+// exponentials are independent chains the scheduler can weave into the surrounding DMMAs.
+template <int KIND, int DL>
+__device__ __forceinline__ void kstar_pair(const double (&rec)[REC_MAX], const ParticleRec<KIND, DL>& p0,
+                                           const ParticleRec<KIND, DL>& p1, double c2last, double& k0, double& k1) {
     constexpr int d = DL;
-    constexpr int REC = KIND == 1 ? 2 * d + 1 : d + 1;
-    double r[NB], lin[NB];
-    int n[NB];
-#pragma unroll
-    for (int b = 0; b < NB; b++) {
-        double rec[REC_MAX];
-        load_record<KIND, DL>(rbase + b * REC, rec);
-        double arg = rec[d] + pb[d];
-#pragma unroll
-        for (int j = 0; j < d; j++) arg = fma(rec[j], pb[j], arg);
-        if (KIND == 1) {
-            double l = c2last;
-#pragma unroll
-            for (int j = 0; j < d; j++) l = fma(rec[d + 1 + j], px[j], l);
-            lin[b] = l;
-        }
-        r[b] = exp_reduce(arg, n[b]);
+    // -|a - b|^2 in difference form: the expansion |a|^2 + |b|^2 - 2ab of gpmdm.py:515 loses ~|a|^2 ulps, which the
+    // ill-conditioned K^-1 amplifies; the difference form keeps K* at ~1 ulp (2 more fp64 ops per entry)
+    double a0, a1;
+    {
+        const double t0 = rec[0] - p0.b[0], t1 = rec[0] - p1.b[0];
+        a0 = -t0 * t0;
+        a1 = -t1 * t1;
     }
-    constexpr double C[14] = {1.0, 1.0, 0.5, 1.0 / 6.0, 1.0 / 24.0, 1.0 / 120.0, 1.0 / 720.0, 1.0 / 5040.0,
-                              1.0 / 40320.0, 1.0 / 362880.0, 1.0 / 3628800.0, 1.0 / 39916800.0,
-                              1.0 / 479001600.0, 1.0 / 6227020800.0};
-    double p[NB];
 #pragma unroll
-    for (int b = 0; b < NB; b++) p[b] = C[13];
+    for (int j = 1; j < d; j++) {
+        const double t0 = rec[j] - p0.b[j], t1 = rec[j] - p1.b[j];
+        a0 = fma(-t0, t0, a0);
+        a1 = fma(-t1, t1, a1);
+    }
+    int n0, n1;
+    const double r0 = exp_reduce(a0, n0), r1 = exp_reduce(a1, n1);
+    double e0, e1;
+    exp_poly2(r0, r1, e0, e1);
+    k0 = exp_scale(e0, n0);
+    k1 = exp_scale(e1, n1);
+    if (KIND == 1) {
+        double l0 = c2last, l1 = c2last;
 #pragma unroll
-    for (int k = 12; k >= 0; k--)
-#pragma unroll
-        for (int b = 0; b < NB; b++) p[b] = fma(p[b], r[b], C[k]);
-#pragma unroll
-    for (int b = 0; b < NB; b++) {
-        const double v = exp_scale(p[b], n[b]);
-        out[b] = KIND == 1 ? v + lin[b] : v;
+        for (int j = 0; j < d; j++) {
+            l0 = fma(rec[d + j], p0.x[j], l0);
+            l1 = fma(rec[d + j], p1.x[j], l1);
+        }
+        k0 += l0;
+        k1 += l1;
     }
 }
 
@@ -187,268 +163,225 @@ __global__ void __launch_bounds__(NTHREADS, 1) gp_predict_kernel(const PredictPa
     extern __shared__ __align__(128) unsigned char smem_raw[];
     Smem& s = *reinterpret_cast<Smem*>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int r = lane >> 2, c = lane & 3;
     constexpr int d = DL;
-    constexpr int REC = KIND == 1 ? 2 * d + 1 : d + 1;
+    constexpr int REC = rec_width(KIND, d);
     const double c2last = KIND == 1 ? prm.lin_c2[d] : 0.0;
-    const bool is_producer = warp < NPROD / 32;
 
     if (tid == 0) {
-        for (int i = 0; i < BSTAGES; i++) {
-            mbar_init(&s.b_full[i], 1);           // one arrive.expect_tx + TMA bytes
-            mbar_init(&s.b_empty[i], NCONS / 32);  // one arrival per consumer warp
-        }
-        for (int i = 0; i < ASTAGES; i++) {
-            mbar_init(&s.a_full[i], NPROD);        // every producer thread
-            mbar_init(&s.a_empty[i], NCONS / 32);
+        for (int i = 0; i < STAGES; i++) {
+            mbar_init(&s.full[i], 1);        // one arrive.expect_tx + TMA bytes
+            mbar_init(&s.empty[i], NWARPS);  // one arrival per warp
         }
         mbar_fence_init();
     }
     __syncthreads();
 
     const int total_tiles = prm.tiles ? *prm.n_tiles : (int)((prm.P + TM - 1) / TM);
-    uint32_t g = 0;   // chunks processed by this role so far (ring positions and mbarrier parities)
+    uint32_t g = 0;  // chunks consumed so far by this CTA (ring position and mbarrier parity)
 
-    // Per-tile geometry, recomputed identically by both roles from s.tile.
-#define GPMDM_TILE_GEOMETRY()                                                   \
-    const int t = s.tile;                                                       \
-    if (t >= total_tiles) break;                                                \
-    int blk = 0, first = t * TM, count;                                         \
-    if (prm.tiles) {                                                            \
-        blk = prm.tiles[4 * t + 0];                                             \
-        first = prm.tiles[4 * t + 1];                                           \
-        count = prm.tiles[4 * t + 2];                                           \
-    } else {                                                                    \
-        long long rem = prm.P - (long long)first;                               \
-        count = rem < TM ? (int)rem : TM;                                       \
-    }                                                                           \
-    const gpmdm_gp_block gbk = prm.blocks[blk];                                 \
-    const int n_pad = (int)gbk.n_pad;                                           \
-    const int nkc = n_pad / KC;                                                 \
-    const int nq = n_pad / TN;              /* column tiles of L */             \
-    const int nct = nq + prm.alpha_ld / TN; /* + column tiles of alpha */       \
-    (void)first; (void)count;                                                   \
-    ChunkCursor cur;                                                            \
-    cur.init(nq, nct, nkc, prm.tri)
-
-    // The two roles never re-converge after setmaxnreg (ptxas allocates registers per role only then).
-    if (is_producer) {
-        setmaxnreg_dec<PROD_REGS>();
-        uint32_t gb = 0;  // warp 0: B chunks issued so far
-        for (;;) {
-            if (tid == 0) s.tile = atomicAdd(prm.counter, 1);
-            named_bar_sync(2, NPROD);
-            GPMDM_TILE_GEOMETRY();
-            // ---- particle records ------------------------------------------------------------------
-            {
-                const int m = tid < count ? tid : count - 1;
-                const int p = prm.perm ? prm.perm[first + m] : first + m;
-                s.pidx[tid] = tid < count ? p : -1;
-                double nb = 0.0, prior = 1.0;
-#pragma unroll
-                for (int j = 0; j < d; j++) {
-                    const double xj = prm.x[(long long)p * d + j];
-                    const double bj = xj / prm.ls[j];
-                    s.Pb[j][tid] = bj;
-                    nb = fma(bj, bj, nb);
-                    if (KIND == 1) {
-                        s.Px[j][tid] = xj;
-                        prior = fma(prm.lin_c2[j] * xj, xj, prior);
-                    }
-                }
-                s.Pb[d][tid] = -nb;
-                if (KIND == 1) prior += c2last;
-                s.prior[tid] = prior;
-            }
-            named_bar_sync(0, NTHREADS);  // tile + records visible to the consumers
-
-
-            // ======================= PRODUCER: B ring (warp 0, TMA) + A ring (K* generation) =================
-            ChunkCursor bcur = cur;  // B cursor runs BAHEAD chunks ahead of the A cursor
-            auto issue_b = [&]() {
-                const int st = (int)(gb % BSTAGES);
-                mbar_wait(&s.b_empty[st], ((gb / BSTAGES) & 1) ^ 1);  // first pass: passes immediately
-                const double* src;
-                int ld;
-                if (bcur.ct < nq) {
-                    src = gbk.L + (long long)bcur.ct * TN;
-                    ld = n_pad;
-                } else {
-                    src = gbk.alpha + (long long)(bcur.ct - nq) * TN;
-                    ld = prm.alpha_ld;
-                }
-                if (lane == 0) mbar_expect_tx(&s.b_full[st], (uint32_t)(KC * TN * 8));
-                __syncwarp();
-                if (lane < KC)
-                    bulk_g2s(&s.B[st][lane][0], src + (long long)(bcur.k * KC + lane) * ld, TN * 8, &s.b_full[st]);
-                bcur.next();
-                gb++;
-            };
-            if (warp == 0)
-                for (int i = 0; i < BAHEAD && !bcur.done(); i++) issue_b();
-
-            const int p = tid;  // this thread's particle row
-            double pb[MAXD + 1], px[MAXD];
-#pragma unroll
-            for (int j = 0; j < MAXD; j++) {
-                pb[j] = j < d ? s.Pb[j][p] : 0.0;
-                px[j] = (KIND == 1 && j < d) ? s.Px[j][p] : 0.0;
-            }
-            pb[d] = s.Pb[d][p];
-
-            for (; !cur.done(); cur.next(), g++) {
-                if (warp == 0 && !bcur.done()) issue_b();
-                const int buf = (int)(g % ASTAGES);
-                mbar_wait(&s.a_empty[buf], ((g / ASTAGES) & 1) ^ 1);
-                const double* rbase = gbk.coords + (long long)cur.k * KC * REC;
-                constexpr int NB = 8;
-#pragma unroll 1
-                for (int k0 = 0; k0 < KC; k0 += NB) {
-                    double kv[NB];
-                    kstar_batch<KIND, DL, NB>(rbase + k0 * REC, pb, px, c2last, kv);
-#pragma unroll
-                    for (int b = 0; b < NB; b++) s.A[buf][k0 + b][p] = kv[b];
-                }
-                mbar_arrive(&s.a_full[buf]);
-            }
-            named_bar_sync(0, NTHREADS);  // consumers are done with s.Pb / s.pidx / s.tile
+    for (;;) {
+        if (tid == 0) s.tile = atomicAdd(prm.counter, 1);
+        __syncthreads();
+        const int t = s.tile;
+        __syncthreads();
+        if (t >= total_tiles) break;
+        int blk = 0, first = t * TM, count;
+        if (prm.tiles) {
+            blk = prm.tiles[4 * t + 0];
+            first = prm.tiles[4 * t + 1];
+            count = prm.tiles[4 * t + 2];
+        } else {
+            long long rem = prm.P - (long long)first;
+            count = rem < TM ? (int)rem : TM;
         }
-        // the "no more tiles" value of s.tile must reach the consumers too
-        named_bar_sync(0, NTHREADS);
-    } else {
-        setmaxnreg_inc<CONS_REGS>();
-        for (;;) {
-            named_bar_sync(0, NTHREADS);
-            GPMDM_TILE_GEOMETRY();
-            // ======================= CONSUMERS: DMMA main loop + fused epilogues ==============================
-            const int cw = warp - NPROD / 32;
-            const int wm = cw & 3, wn = cw >> 2;
-            const int r = lane >> 2, c = lane & 3;
-            const int ctid = tid - NPROD;
-            double qacc[4] = {0.0, 0.0, 0.0, 0.0};
-            double sacc[4] = {0.0, 0.0, 0.0, 0.0};
+        const gpmdm_gp_block gbk = prm.blocks[blk];
+        const int n_pad = (int)gbk.n_pad;
+        const int nkc = n_pad / KC;
+        const int nq = n_pad / TN;               // column tiles of L
+        const int nct = nq + prm.alpha_ld / TN;  // + column tiles of alpha
 
-            for (int ct = 0; ct < nct; ct++) {
-                double acc[4][8][2];
+        // ---- this lane's two particle rows ------------------------------------------------------------
+        ParticleRec<KIND, DL> pr[2];
+        int pidx[2];
+        double prior[2];
 #pragma unroll
-                for (int i = 0; i < 4; i++)
+        for (int i = 0; i < 2; i++) {
+            const int row = warp * 16 + i * 8 + r;
+            const int m = row < count ? row : count - 1;
+            const int p = prm.perm ? prm.perm[first + m] : first + m;
+            pidx[i] = row < count ? p : -1;
+            double pri = 1.0;
 #pragma unroll
-                    for (int j = 0; j < 8; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+            for (int j = 0; j < d; j++) {
+                const double xj = prm.x[(long long)p * d + j];
+                pr[i].b[j] = xj / prm.ls[j];
+                if (KIND == 1) {
+                    pr[i].x[j] = xj;
+                    pri = fma(prm.lin_c2[j] * xj, xj, pri);
+                }
+            }
+            if (KIND == 1) pri += c2last;
+            prior[i] = pri;
+        }
 
-                const int kbeg = cur.kbeg(ct);
-                for (int k = kbeg; k < nkc; k++, g++) {
-                    const int bst = (int)(g % BSTAGES), ast = (int)(g % ASTAGES);
-                    mbar_wait(&s.a_full[ast], (g / ASTAGES) & 1);
-                    mbar_wait(&s.b_full[bst], (g / BSTAGES) & 1);
+        // ---- TMA issue: all warps advance the same cursor, the duty warp issues ------------------------------
+        ChunkCursor bcur;
+        bcur.init(nq, nct, nkc, prm.tri);
+        uint32_t gb = g;  // ring position of the next chunk to issue
+        auto issue_b = [&]() {
+            const int st = (int)(gb % STAGES);
+            mbar_wait(&s.empty[st], ((gb / STAGES) & 1) ^ 1);  // first fill of a stage passes immediately
+            const double* src;
+            int ld;
+            if (bcur.ct < nq) {
+                src = gbk.L + (long long)bcur.ct * TN;
+                ld = n_pad;
+            } else {
+                src = gbk.alpha + (long long)(bcur.ct - nq) * TN;
+                ld = prm.alpha_ld;
+            }
+            if (lane == 0) mbar_expect_tx(&s.full[st], (uint32_t)(KC * TN * 8 + KC * REC * 8));
+            __syncwarp();
+            if (lane < KC)
+                bulk_g2s(&s.B[st][lane][0], src + (long long)(bcur.k * KC + lane) * ld, TN * 8, &s.full[st]);
+            else if (lane == KC)
+                bulk_g2s(&s.R[st][0], gbk.coords + (long long)bcur.k * KC * REC, (uint32_t)(KC * REC * 8), &s.full[st]);
+        };
+        for (int i = 0; i < AHEAD && !bcur.done(); i++) {
+            if (warp == 0) issue_b();
+            bcur.next();
+            gb++;
+        }
+
+        // ---- A fragments of the first chunk -------------------------------------------------------------
+        double a[KC / 4][2];  // a[k4][i] = K*[row 16 w + 8 i + r][k = 4 k4 + c] of the current chunk
+        mbar_wait(&s.full[g % STAGES], (g / STAGES) & 1);
 #pragma unroll
-                    for (int k4 = 0; k4 < KC / 4; k4++) {
-                        double a[4], b[8];
+        for (int k4 = 0; k4 < KC / 4; k4++) {
+            double rec[REC_MAX];
+            load_record<KIND, DL>(&s.R[g % STAGES][(k4 * 4 + c) * REC], rec);
+            kstar_pair<KIND, DL>(rec, pr[0], pr[1], c2last, a[k4][0], a[k4][1]);
+        }
+
+        ChunkCursor cur;
+        cur.init(nq, nct, nkc, prm.tri);
+        double qacc[2] = {0.0, 0.0};
+        double sacc[2] = {0.0, 0.0};
+        double vrow[2] = {0.0, 0.0};
+
+        for (int ct = 0; ct < nct; ct++) {
+            double acc[2][16][2];
 #pragma unroll
-                        for (int i = 0; i < 4; i++) a[i] = s.A[ast][k4 * 4 + c][wm * 32 + i * 8 + r];
+            for (int i = 0; i < 2; i++)
 #pragma unroll
-                        for (int j = 0; j < 8; j++) b[j] = s.B[bst][k4 * 4 + c][wn * 64 + j * 8 + r];
+                for (int j = 0; j < 16; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+            const int kbeg = cur.kbeg(ct);
+            for (int k = kbeg; k < nkc; k++, g++) {
+                const int st = (int)(g % STAGES);
+                // keep the ring AHEAD chunks full; the duty rotates so that no warp is always the one waiting
+                if (!bcur.done()) {
+                    if (warp == (int)(g % NWARPS)) issue_b();
+                    bcur.next();
+                    gb++;
+                }
+                // the next chunk (of this particle tile) provides the records for the next A fragments
+                const bool has_next = !(ct == nct - 1 && k == nkc - 1);
+                const int stn = (int)((g + 1) % STAGES);
+                if (has_next) mbar_wait(&s.full[stn], ((g + 1) / STAGES) & 1);
 #pragma unroll
-                        for (int i = 0; i < 4; i++)
+                for (int k4 = 0; k4 < KC / 4; k4++) {
+                    double b[16];
 #pragma unroll
-                            for (int j = 0; j < 8; j++) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+                    for (int j = 0; j < 16; j++) b[j] = s.B[st][k4 * 4 + c][j * 8 + r];
+                    const double a0 = a[k4][0], a1 = a[k4][1];
+                    if (has_next) {  // next chunk's A fragments for this k4, woven into the MMAs below
+                        double rec[REC_MAX];
+                        load_record<KIND, DL>(&s.R[stn][(k4 * 4 + c) * REC], rec);
+                        kstar_pair<KIND, DL>(rec, pr[0], pr[1], c2last, a[k4][0], a[k4][1]);
                     }
-                    __syncwarp();
-                    if (lane == 0) {  // this warp is done reading both ring slots
-                        mbar_arrive(&s.a_empty[ast]);
-                        mbar_arrive(&s.b_empty[bst]);
+#pragma unroll
+                    for (int j = 0; j < 16; j++) {
+                        dmma_m8n8k4(acc[0][j][0], acc[0][j][1], a0, b[j]);
+                        dmma_m8n8k4(acc[1][j][0], acc[1][j][1], a1, b[j]);
                     }
                 }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&s.empty[st]);  // this warp is done with the ring slot
+            }
 
-                // ---- epilogues ---------------------------------------------------------------------------
-                if (ct < nq) {
-                    // q[p] += sum_n C[p,n] * K*[p,n] over this tile's columns (K* regenerated per element)
+            // ---- epilogues (per warp; a row's columns live in the 4 lanes of a quad) -------------------------
+            if (ct < nq) {
+                // q[p] += sum_n C[p,n] * K*[p,n] over this tile's columns (K* regenerated per element)
 #pragma unroll
-                    for (int j = 0; j < 8; j++) {  // fully unrolled: acc[][][] must stay in registers
+                for (int j = 0; j < 16; j++) {  // fully unrolled: acc[][][] must stay in registers
+#pragma unroll
+                    for (int e = 0; e < 2; e++) {
+                        const int n = ct * TN + j * 8 + c * 2 + e;
+                        double rec[REC_MAX];
+                        load_record<KIND, DL>(gbk.coords + (long long)n * REC, rec);
+                        double k0, k1;
+                        kstar_pair<KIND, DL>(rec, pr[0], pr[1], c2last, k0, k1);
+                        qacc[0] = fma(acc[0][j][e], k0, qacc[0]);
+                        qacc[1] = fma(acc[1][j][e], k1, qacc[1]);
+                    }
+                }
+                if (ct == nq - 1) {
+                    // quadratic form complete: v[p] = prior[p] - q[p]
+#pragma unroll
+                    for (int i = 0; i < 2; i++) {
+                        double v = qacc[i];
+                        v += __shfl_xor_sync(0xffffffffu, v, 1);
+                        v += __shfl_xor_sync(0xffffffffu, v, 2);
+                        vrow[i] = prior[i] - v;
+                    }
+                }
+            } else {
+                const int cbase = (ct - nq) * TN;
+#pragma unroll
+                for (int i = 0; i < 2; i++) {
+                    const int p = pidx[i];
+#pragma unroll
+                    for (int j = 0; j < 16; j++) {
 #pragma unroll
                         for (int e = 0; e < 2; e++) {
-                            const int n = ct * TN + wn * 64 + j * 8 + c * 2 + e;
-                            double rec[REC_MAX];
-                            load_record<KIND, DL>(gbk.coords + (long long)n * REC, rec);
-#pragma unroll
-                            for (int i = 0; i < 4; i++) {
-                                const int m = wm * 32 + i * 8 + r;
-                                double pb[MAXD + 1], px[MAXD];
-#pragma unroll
-                                for (int q = 0; q < MAXD; q++) {
-                                    pb[q] = q < d ? s.Pb[q][m] : 0.0;
-                                    px[q] = (KIND == 1 && q < d) ? s.Px[q][m] : 0.0;
+                            const int col = cbase + j * 8 + c * 2 + e;
+                            if (col >= prm.dout) continue;
+                            const double mu = acc[i][j][e];
+                            if (KIND == 0) {
+                                if (prm.z) {
+                                    const double dz = __ldg(prm.z + col) - mu;
+                                    sacc[i] = fma(__ldg(prm.scale + col) * dz, dz, sacc[i]);
                                 }
-                                pb[d] = s.Pb[d][m];
-                                const double kv = kstar_from_records<KIND, DL>(rec, pb, px, c2last);
-                                qacc[i] = fma(acc[i][j][e], kv, qacc[i]);
+                                if (prm.mu_out && p >= 0) prm.mu_out[(long long)p * prm.dout + col] = mu;
+                            } else if (p >= 0) {
+                                const double var = vrow[i] * __ldg(prm.scale + col);
+                                const long long o = (long long)p * prm.dout + col;
+                                if (prm.x_new)  // torch.normal: randn * std + mean, two roundings (no FMA)
+                                    prm.x_new[o] = __dadd_rn(__dmul_rn(__ldg(prm.eps + o), sqrt(var)), mu);
+                                if (prm.mean_out) prm.mean_out[o] = mu;
+                                if (prm.var_out) prm.var_out[o] = var;
                             }
                         }
                     }
-                    if (ct == nq - 1) {
-                        // quadratic form complete: v[p] = prior[p] - q[p]
+                }
+                if (KIND == 0 && ct == nct - 1) {
 #pragma unroll
-                        for (int i = 0; i < 4; i++) {
-                            double v = qacc[i];
-                            v += __shfl_xor_sync(0xffffffffu, v, 1);
-                            v += __shfl_xor_sync(0xffffffffu, v, 2);
-                            if (c == 0) s.red[wn][wm * 32 + i * 8 + r] = v;
-                        }
-                        named_bar_sync(1, NCONS);
-                        if (ctid < TM) s.vrow[ctid] = s.prior[ctid] - (s.red[0][ctid] + s.red[1][ctid]);
-                        named_bar_sync(1, NCONS);
-                    }
-                } else {
-                    const int cbase = (ct - nq) * TN + wn * 64;
-#pragma unroll
-                    for (int i = 0; i < 4; i++) {
-                        const int m = wm * 32 + i * 8 + r;
-                        const int p = s.pidx[m];
-#pragma unroll
-                        for (int j = 0; j < 8; j++) {
-#pragma unroll
-                            for (int e = 0; e < 2; e++) {
-                                const int col = cbase + j * 8 + c * 2 + e;
-                                if (col >= prm.dout) continue;
-                                const double mu = acc[i][j][e];
-                                if (KIND == 0) {
-                                    if (prm.z) {
-                                        const double dz = __ldg(prm.z + col) - mu;
-                                        sacc[i] = fma(__ldg(prm.scale + col) * dz, dz, sacc[i]);
-                                    }
-                                    if (prm.mu_out && p >= 0) prm.mu_out[(long long)p * prm.dout + col] = mu;
-                                } else if (p >= 0) {
-                                    const double var = s.vrow[m] * __ldg(prm.scale + col);
-                                    const long long o = (long long)p * prm.dout + col;
-                                    if (prm.x_new)  // torch.normal: randn * std + mean, two roundings (no FMA)
-                                        prm.x_new[o] = __dadd_rn(__dmul_rn(__ldg(prm.eps + o), sqrt(var)), mu);
-                                    if (prm.mean_out) prm.mean_out[o] = mu;
-                                    if (prm.var_out) prm.var_out[o] = var;
-                                }
-                            }
-                        }
-                    }
-                    if (KIND == 0 && ct == nct - 1) {
-#pragma unroll
-                        for (int i = 0; i < 4; i++) {
-                            double v = sacc[i];
-                            v += __shfl_xor_sync(0xffffffffu, v, 1);
-                            v += __shfl_xor_sync(0xffffffffu, v, 2);
-                            if (c == 0) s.red[wn][wm * 32 + i * 8 + r] = v;
-                        }
-                        named_bar_sync(1, NCONS);
-                        if (ctid < TM && s.pidx[ctid] >= 0) {
-                            const double S = s.red[0][ctid] + s.red[1][ctid];
-                            const double v = s.vrow[ctid];
-                            const int p = s.pidx[ctid];
-                            if (prm.ll) prm.ll[p] = -0.5 * S / v - (double)prm.dout * log(v) + prm.ll_const;
-                            if (prm.v_out) prm.v_out[p] = v;
+                    for (int i = 0; i < 2; i++) {
+                        double S = sacc[i];
+                        S += __shfl_xor_sync(0xffffffffu, S, 1);
+                        S += __shfl_xor_sync(0xffffffffu, S, 2);
+                        if (c == 0 && pidx[i] >= 0) {
+                            const double v = vrow[i];
+                            if (prm.ll) prm.ll[pidx[i]] = -0.5 * S / v - (double)prm.dout * log(v) + prm.ll_const;
+                            if (prm.v_out) prm.v_out[pidx[i]] = v;
                         }
                     }
                 }
             }
-            named_bar_sync(0, NTHREADS);  // s.tile, s.pidx, s.Pb ... are rewritten by the next tile
         }
     }
-#undef GPMDM_TILE_GEOMETRY
 }
 
 // ---- host side -------------------------------------------------------------------------------------

@@ -429,13 +429,13 @@ class GPMDM(torch.nn.Module):
         lib = _cabi.lib()
         n, d = Xtrain.shape
         n_pad = _round_up(n, TILE)
-        a = Xtrain / torch.exp(log_ls)
-        cols = [2.0 * a, -torch.sum(a * a, dim=1, keepdim=True)]
+        cols = [Xtrain / torch.exp(log_ls)]
         if lin_c2 is not None:
             cols.append(Xtrain * lin_c2[:d])
         rec = torch.cat(cols, 1)
-        coords = torch.zeros(n_pad, rec.shape[1], dtype=self.dtype, device=self.device)
-        coords[:n] = rec
+        width = (rec.shape[1] + 1) & ~1  # records are padded to an even number of doubles (16-byte loads)
+        coords = torch.zeros(n_pad, width, dtype=self.dtype, device=self.device)
+        coords[:n, :rec.shape[1]] = rec
         L = torch.empty(n_pad, n_pad, dtype=self.dtype, device=self.device)
         Kinv = Kinv.contiguous()
         check(lib.gpmdm_pack_quadform_f64(ptr(Kinv), n, n_pad, int(tri), ptr(L), stream()), "gpmdm_pack_quadform_f64")

@@ -40,8 +40,9 @@ extern "C" {
  * has one block per class over that class' N_c (x_t -> x_t+1) pairs -- the block-diagonal structure
  * the reference expresses with dense 0/1 masks (gpmdm.py:311-378, 1299-1305).
  *
- *   coords [n_pad, rec]  per training row i:  2*a_i[0..d) , -|a_i|^2 , (dynamics only) c_k^2 * x_i[k]
- *                        with a_i = x_i / lengthscale  (gpmdm.py:508-517, 545-548); zero rows pad.
+ *   coords [n_pad, rec]  per training row i:  a_i[0..d) , (dynamics only) c_k^2 * x_i[k] for k in [0, d), then
+ *                        zero padding to an even width: rec = (d + 1) & ~1 (kind 0), (2d + 1) & ~1 (kind 1);
+ *                        a_i = x_i / lengthscale  (gpmdm.py:508-517, 545-548); zero rows pad.
  *   L      [n_pad, n_pad] quadratic-form matrix such that  k^T K^-1 k == k^T L k :
  *                        tri = 1:  L[i][j] = Kinv[i][j] + Kinv[j][i] (i > j), Kinv[i][i], 0 (i < j)
  *                        tri = 0:  L = Kinv.   Zero padded.  (written by gpmdm_pack_quadform_f64)

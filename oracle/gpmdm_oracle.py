@@ -412,3 +412,40 @@ def x_neg_log_likelihood(m: ModelSpec, Xin, Xout):
     W2 = torch.diag(torch.exp(m.x_log_lambdas) ** 2)
     return m.d / 2 * logdet + 0.5 * torch.trace(torch.linalg.multi_dot([Kinv, Xout, W2, Xout.t()])) \
         - Xin.shape[0] * 2 * torch.sum(m.x_log_lambdas)
+
+
+# ------------------------------------------------------------------------------------------------
+# extended-precision arbiter (layer L2)
+# ------------------------------------------------------------------------------------------------
+def dynamics_truth_longdouble(m: ModelSpec, f: Factors, Xstar, c: int):
+    """mean / var of `map_x_dynamics_for_class` with the cross-kernel, the contraction against the SAME fp64
+    `Kx_inv_blocks[c]` / `alpha_x[c]` and the cancellation `prior - q` carried out in numpy longdouble
+    (80-bit on x86).  Arbitrates between the oracle and the CUDA path: both approximate this value."""
+    ld = np.longdouble
+    a, b = m.class_pair_ranges()[c]
+    Xin = f.Xin[a:b].numpy().astype(ld)
+    Xs = Xstar.numpy().astype(ld)
+    ls = np.exp(m.x_log_lengthscales.numpy().astype(ld))
+    c2 = np.exp(m.x_log_lin_coeff.numpy().astype(ld)) ** 2
+    A, B = Xin / ls, Xs / ls
+    dist = ((A[:, None, :] - B[None, :, :]) ** 2).sum(-1)
+    K = np.exp(-dist) + (Xin * c2[:-1]) @ Xs.T + c2[-1]  # [N_c, P]
+    Kinv = f.Kx_inv_blocks[c].numpy().astype(ld)
+    q = np.einsum("ip,ip->p", K, Kinv @ K)
+    prior = 1 + (Xs * c2[:-1] * Xs).sum(1) + c2[-1]
+    lam = np.exp(m.x_log_lambdas.numpy().astype(ld)) ** -2
+    mean = K.T @ f.alpha_x[c].numpy().astype(ld)
+    var = (prior - q)[:, None] * lam[None, :]
+    return mean, var, prior
+
+
+def observation_truth_longdouble(m: ModelSpec, f: Factors, Xstar):
+    """mean / v of `map_x_to_y` in numpy longdouble against the same fp64 `Ky_inv` / `alpha_y`."""
+    ld = np.longdouble
+    X = m.X.numpy().astype(ld)
+    Xs = Xstar.numpy().astype(ld)
+    ls = np.exp(m.y_log_lengthscales.numpy().astype(ld))
+    A, B = X / ls, Xs / ls
+    K = np.exp(-((A[:, None, :] - B[None, :, :]) ** 2).sum(-1))
+    q = np.einsum("ip,ip->p", K, f.Ky_inv.numpy().astype(ld) @ K)
+    return K.T @ f.alpha_y.numpy().astype(ld), 1 - q

@@ -54,6 +54,33 @@ def test_dynamics_gp_vs_oracle(cfg1, P):
         assert scaled_err(var.cpu(), var_o, prior.unsqueeze(1) * lam_x.unsqueeze(0)) < TOL
 
 
+def test_variance_error_vs_extended_precision_arbiter(cfg1):
+    """The 1 - k^T K^-1 k cancellation limits how well ANY fp64 evaluation reproduces another.
+    Against an 80-bit evaluation on the same fp64 factors: the CUDA path's variance error stays below 1e-9 of
+    the prior variance and is not worse than a small multiple of the torch-CPU oracle's own error."""
+    spec, wl, f, model = cfg1
+    xs = particles_near_data(spec, 48, 11)
+    lam_x = (torch.exp(spec.x_log_lambdas) ** -2).numpy()
+    for c in range(spec.n_classes):
+        mean_t, var_t, prior_t = orc.dynamics_truth_longdouble(spec, f, xs, c)
+        mean_g, var_g = model.map_x_dynamics_for_class(xs.cuda(), c)
+        mean_o, var_o, _, _ = orc.map_x_dynamics_for_class(spec, f, xs, c)
+        scale = (prior_t[:, None] * lam_x[None, :]).astype(np.float64)
+        err_g = np.max(np.abs(var_g.cpu().numpy() - var_t.astype(np.float64)) / scale)
+        err_o = np.max(np.abs(var_o.numpy() - var_t.astype(np.float64)) / scale)
+        assert err_g < TOL, (err_g, err_o)
+        assert err_g < 4 * err_o + 1e-12, (err_g, err_o)
+        mscale = np.maximum(np.abs(mean_t.astype(np.float64)).max(1, keepdims=True), 1e-3)
+        assert np.max(np.abs(mean_g.cpu().numpy() - mean_t.astype(np.float64)) / mscale) < TOL
+    mu_t, v_t = orc.observation_truth_longdouble(spec, f, xs)
+    mu_g, var_g = model.map_x_to_y(xs.cuda())
+    _, _, v_o = orc.map_x_to_y(spec, f, xs)
+    lam_y = float(torch.exp(spec.y_log_lambdas[0]) ** -2)
+    err_g = np.max(np.abs(var_g.cpu().numpy()[:, 0] / lam_y - v_t.astype(np.float64)))
+    err_o = np.max(np.abs(v_o.numpy() - v_t.astype(np.float64)))
+    assert err_g < TOL and err_g < 4 * err_o + 1e-13, (err_g, err_o)
+
+
 def test_tri_and_dense_packings_agree(cfg1):
     spec, wl, f, model = cfg1
     xs = particles_near_data(spec, 300, 7).cuda()
@@ -97,9 +124,18 @@ def test_filter_trial_vs_oracle(cfg1, P):
         # dynamics draw: |dx'| <= |eps| * (1e-9 prior) / (2 std) + 1e-9 (1 + |x'|)
         x_o, mean_o, var_o = orc.dynamics_draw(spec, f, x_prev, c_new, eps)
         prior = orc.x_diag_kernel(spec, x_prev).unsqueeze(1) * lam_x.unsqueeze(0)
-        bound = torch.abs(eps) * (TOL * prior) / (2 * torch.sqrt(var_o)) + TOL * (1 + torch.abs(x_o))
+        # variance tolerance here is 4e-9 of the prior: two fp64 evaluations of prior - k^T K^-1 k (the oracle's and
+        # ours) each carry ~1e-9-of-prior cancellation noise at this conditioning; the error against an 80-bit
+        # arbiter is bounded at 1e-9 in test_variance_error_vs_extended_precision_arbiter
+        bound = torch.abs(eps) * (4 * TOL * prior) / (2 * torch.sqrt(var_o)) + TOL * (1 + torch.abs(x_o))
         x_gpu = pf.last_pre_resample_states.cpu()
-        assert bool(torch.all(torch.abs(x_gpu - x_o) <= bound))
+        ratio = torch.abs(x_gpu - x_o) / bound
+        worst = int(torch.argmax(ratio))
+        wp, wk = divmod(worst, d)
+        assert float(ratio.max()) <= 1.0, (
+            f"step {t} particle {wp} dim {wk}: |dx|={float(torch.abs(x_gpu - x_o)[wp, wk]):.3e} bound={float(bound[wp, wk]):.3e} "
+            f"var_o={float(var_o[wp, wk]):.3e} prior={float(prior[wp, wk]):.3e} eps={float(eps[wp, wk]):.3f} "
+            f"mean_o={float(mean_o[wp, wk]):.6f} class={int(c_new[wp])}")
         # observation likelihood on the CUDA path's own x'
         mu_o, _, v_o = orc.map_x_to_y(spec, f, x_gpu)
         ll_o = orc.log_likelihoods_fused(mu_o, v_o, z, spec.y_log_lambdas)
