@@ -294,10 +294,11 @@ def run_ours(a):
         # roofline of the dominant kernel: observation-GP contraction, one launch per step per rank
         Pl = P // world
         flops_alg = Pl * (2.0 * N * N + 2.0 * N * D)           # obs var + obs mean terms
-        n_pad = (N + 127) // 128 * 128
-        nq = n_pad // 128  # executed per particle: [128 k-rows x 128 columns] blocks of the lower triangle incl. diagonal + mean tile
-        flops_exec = Pl * (2.0 * 128 ** 2) * (nq * (nq + 1) / 2 + nq) \
-            if not a.dense else Pl * (2.0 * n_pad * n_pad + 2.0 * n_pad * 128)
+        TN = 256                                                # column-tile width of the predict kernel
+        n_pad = (N + TN - 1) // TN * TN
+        nq = n_pad // TN  # executed per particle: [TN k-rows x TN columns] blocks of the lower triangle + mean tile
+        flops_exec = Pl * (2.0 * TN ** 2) * (nq * (nq + 1) / 2 + nq) \
+            if not a.dense else Pl * (2.0 * n_pad * n_pad + 2.0 * n_pad * TN)
         tf = ctypes_probe(lib)
         achieved = flops_alg / (obs_avg_ms * 1e-3) / 1e12
         roofline = {

@@ -14,7 +14,8 @@ from . import build as _build
 
 _i32, _i64, _u64, _f64, _ptr = ctypes.c_int32, ctypes.c_int64, ctypes.c_uint64, ctypes.c_double, ctypes.c_void_p
 
-TILE = 128
+TILE_P = 64    # GPMDM_TILE_P: particles per predict tile
+TILE_N = 256   # GPMDM_TILE_N: row padding of factors / alpha_ld granularity
 MAX_LATENT = 8
 
 

@@ -81,8 +81,8 @@ extern "C" const char* gpmdm_last_error(void) { return g_err; }
 extern "C" int gpmdm_pack_quadform_f64(const double* Kinv, int64_t n, int64_t n_pad, int tri, double* L,
                                        void* stream) {
     GPMDM_REQUIRE(Kinv && L, GPMDM_E_INVALID, "null argument");
-    GPMDM_REQUIRE(n > 0 && n_pad >= n && n_pad % GPMDM_TILE == 0, GPMDM_E_INVALID,
-                  "n_pad %lld must be a multiple of %d and >= n %lld", (long long)n_pad, GPMDM_TILE, (long long)n);
+    GPMDM_REQUIRE(n > 0 && n_pad >= n && n_pad % GPMDM_TILE_N == 0, GPMDM_E_INVALID,
+                  "n_pad %lld must be a multiple of %d and >= n %lld", (long long)n_pad, GPMDM_TILE_N, (long long)n);
     dim3 grid((unsigned)(n_pad / 32), (unsigned)(n_pad / 32)), block(32, 8);
     pack_quadform_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(Kinv, n, n_pad, tri, L);
     return check_launch("pack_quadform_kernel");

@@ -5,33 +5,34 @@
 // (map_x_dynamics_for_class), and the per-particle Python loop of gpmdm/gpmdm_pf.py:188-192 plus
 // the draw of :167-168, which are fused here as epilogues.
 //
-// Shape of the computation, for one 128-particle tile (rows p) of one GP block (N_pad training rows):
+// Shape of the computation, for one 64-particle tile (rows p) of one GP block (N_pad training rows):
 //     C[p, n]  = sum_k  K*[p, k] * B[k, n]          B = [ L | alpha ],  K* generated on the fly
 //     q[p]     = sum_n  C[p, n] * K*[p, n]           (columns of L;   Hadamard + row-sum epilogue)
 //     mean[p,:] = C[p, N_pad:]                        (columns of alpha)
 // With tri = 1, L is the lower-triangular packing of K^-1 (k^T K^-1 k == k^T L k), so column tile J
-// only needs k >= 128 J: half the flops and half the bytes of the dense form.
+// only needs k >= 256 J: half the flops and half the bytes of the dense form.
 //
 // Kernel organisation (one persistent CTA per SM, 256 threads = 8 warps; measured facts that shaped it, see
 // profiles/: on sm_100a DMMA (sm__pipe_tensor_subpipe_dmma) and DFMA/exp (sm__pipe_fp64) contend for ONE
 // fp64 math datapath of 64 FMA/clk/SM -- a warp-specialised producer/consumer split only moved the K*
 // prologue into `stall_math` behind the consumers' DMMAs -- so the goal is zero idle time on that datapath
 // and as few non-MMA fp64 instructions as possible):
-//   * each warp owns 16 particle rows x all 128 columns of the column tile (64 accumulators per lane), so
-//     every lane GENERATES EXACTLY ITS OWN A FRAGMENTS: the K* values it feeds to mma.sync (rows r, r+8;
-//     k = 4 k4 + c) are computed in registers from the particle record (registers) and the training
+//   * the CTA tile is 64 particles x 256 columns; each warp owns 8 particle rows x all 256 columns of the
+//     column tile (64 accumulators per lane) -- a wide tile, because every generated K* entry then feeds 256
+//     column MMAs -- and every lane GENERATES EXACTLY ITS OWN A FRAGMENTS: the K* values it feeds to mma.sync
+//     (row r; k = 4 k4 + c) are computed in registers from the particle record (registers) and the training
 //     records of the chunk (shared memory) -- the "GEMM prologue from latent coordinates" -- with no A tile
 //     in shared memory, no redundancy between warps and no block-wide barrier in the main loop;
 //   * the exponentials for chunk g+1 are software-pipelined into the DMMA stream of chunk g (custom
 //     fast_exp, csrc/fast_exp.cuh), so the datapath always has an instruction to run;
-//   * B tiles [16 x 128] of L / alpha and the 16 training records of the chunk arrive through TMA 1-D bulk
-//     copies (cp.async.bulk, SASS UBLKCP) into an 8-stage shared ring; full/empty mbarriers are the only
-//     synchronisation between warps (the issuing duty rotates over the warps, 4 chunks ahead);
+//   * B tiles [16 x 256] of L / alpha and the 16 training records of the chunk arrive through TMA 1-D bulk
+//     copies (cp.async.bulk, SASS UBLKCP) into a 6-stage shared ring; full/empty mbarriers are the only
+//     synchronisation between warps (the issuing duty rotates over the warps, 3 chunks ahead);
 //   * fp64 tensor-core MMAs are mma.sync m8n8k4, the fastest DMMA shape on sm_100a (profiles/microbench);
 //   * the +4 double row padding of the B ring makes the fragment loads bank-conflict free for the m8n8k4
-//     lane layout (address = (lane&3)*132 + lane>>2 (+const) covers 16 distinct 8-byte banks per half warp);
+//     lane layout (address = (lane&3)*260 + lane>>2 (+const) covers 16 distinct 8-byte banks per half warp);
 //   * epilogues (Hadamard row-sum for the quadratic form, log-likelihood / Gaussian draw) are per warp:
-//     a row's 128 columns live in the 4 lanes of a quad, reductions are two shuffles;
+//     a row's 256 columns live in the 4 lanes of a quad, reductions are two shuffles;
 //   * tiles are handed out through an atomic counter, so class-sorted dynamics tiles of different
 //     block sizes balance across SMs.  Row results do not depend on tile assignment.
 #include <math.h>
@@ -41,11 +42,11 @@
 
 namespace gpmdm {
 
-constexpr int TM = GPMDM_TILE;  // particles per tile
-constexpr int TN = GPMDM_TILE;  // columns per column tile
-constexpr int KC = 16;          // k rows per chunk
-constexpr int STAGES = 8;       // B / record ring depth (TMA)
-constexpr int AHEAD = 4;        // chunks in flight ahead of the consumers
+constexpr int TM = GPMDM_TILE_P;  // particles per tile (8 warps x 8 rows)
+constexpr int TN = GPMDM_TILE_N;  // columns per column tile
+constexpr int KC = 16;            // k rows per chunk
+constexpr int STAGES = 6;         // B / record ring depth (TMA)
+constexpr int AHEAD = 3;          // chunks in flight ahead of the consumers
 constexpr int LDB = TN + 4;
 constexpr int NTHREADS = 256;
 constexpr int NWARPS = NTHREADS / 32;
@@ -82,9 +83,12 @@ struct PredictParams {
 struct __align__(128) Smem {
     double B[STAGES][KC][LDB];
     double R[STAGES][KC * REC_MAX];
+    double exptab[64];
     uint64_t full[STAGES], empty[STAGES];
     int tile;
 };
+
+__constant__ double c_exp_table[64] = {GPMDM_EXP_TABLE_VALUES};
 
 // Per-lane particle record: b_k = x_k / l_k, and raw x for the linear kernel.
 template <int KIND, int DL>
@@ -104,38 +108,44 @@ __device__ __forceinline__ void load_record(const double* __restrict__ src, doub
     }
 }
 
-// K* of one training record against two particle rows, evaluated stage by stage so that the two
-// exponentials are independent chains the scheduler can weave into the surrounding DMMAs.
+// K* of two training records against one particle row, evaluated stage by stage so that the two
+// exponentials are independent instruction chains.
+//   -|a - b|^2 in difference form: the expansion |a|^2 + |b|^2 - 2ab of gpmdm.py:515 loses ~|a|^2 ulps, which
+//   the ill-conditioned K^-1 amplifies; the difference form keeps K* at ~2 ulp.
 template <int KIND, int DL>
-__device__ __forceinline__ void kstar_pair(const double (&rec)[REC_MAX], const ParticleRec<KIND, DL>& p0,
-                                           const ParticleRec<KIND, DL>& p1, double c2last, double& k0, double& k1) {
+__device__ __forceinline__ void kstar_pair(const double (&rec0)[REC_MAX], const double (&rec1)[REC_MAX],
+                                           const ParticleRec<KIND, DL>& p, double c2last,
+                                           const double* __restrict__ exptab, double& k0, double& k1) {
     constexpr int d = DL;
-    // -|a - b|^2 in difference form: the expansion |a|^2 + |b|^2 - 2ab of gpmdm.py:515 loses ~|a|^2 ulps, which the
-    // ill-conditioned K^-1 amplifies; the difference form keeps K* at ~1 ulp (2 more fp64 ops per entry)
     double a0, a1;
     {
-        const double t0 = rec[0] - p0.b[0], t1 = rec[0] - p1.b[0];
+        const double t0 = rec0[0] - p.b[0], t1 = rec1[0] - p.b[0];
         a0 = -t0 * t0;
         a1 = -t1 * t1;
     }
 #pragma unroll
     for (int j = 1; j < d; j++) {
-        const double t0 = rec[j] - p0.b[j], t1 = rec[j] - p1.b[j];
+        const double t0 = rec0[j] - p.b[j], t1 = rec1[j] - p.b[j];
         a0 = fma(-t0, t0, a0);
         a1 = fma(-t1, t1, a1);
     }
     int n0, n1;
     const double r0 = exp_reduce(a0, n0), r1 = exp_reduce(a1, n1);
-    double e0, e1;
-    exp_poly2(r0, r1, e0, e1);
-    k0 = exp_scale(e0, n0);
-    k1 = exp_scale(e1, n1);
+    double e0 = 1.0 / 720.0, e1 = 1.0 / 720.0;
+    constexpr double C[6] = {1.0, 1.0, 0.5, 1.0 / 6.0, 1.0 / 24.0, 1.0 / 120.0};
+#pragma unroll
+    for (int k = 5; k >= 0; k--) {
+        e0 = fma(e0, r0, C[k]);
+        e1 = fma(e1, r1, C[k]);
+    }
+    k0 = exp_scale(e0, n0, exptab);
+    k1 = exp_scale(e1, n1, exptab);
     if (KIND == 1) {
         double l0 = c2last, l1 = c2last;
 #pragma unroll
         for (int j = 0; j < d; j++) {
-            l0 = fma(rec[d + j], p0.x[j], l0);
-            l1 = fma(rec[d + j], p1.x[j], l1);
+            l0 = fma(rec0[d + j], p.x[j], l0);
+            l1 = fma(rec1[d + j], p.x[j], l1);
         }
         k0 += l0;
         k1 += l1;
@@ -166,6 +176,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gp_predict_kernel(const PredictPa
     const int r = lane >> 2, c = lane & 3;
     constexpr int d = DL;
     constexpr int REC = rec_width(KIND, d);
+    constexpr int NJ = TN / 8;  // 8-column blocks per column tile
     const double c2last = KIND == 1 ? prm.lin_c2[d] : 0.0;
 
     if (tid == 0) {
@@ -175,7 +186,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) gp_predict_kernel(const PredictPa
         }
         mbar_fence_init();
     }
+    if (tid < 64) s.exptab[tid] = c_exp_table[tid];
     __syncthreads();
+    const double* exptab = s.exptab;
 
     const int total_tiles = prm.tiles ? *prm.n_tiles : (int)((prm.P + TM - 1) / TM);
     uint32_t g = 0;  // chunks consumed so far by this CTA (ring position and mbarrier parity)
@@ -201,28 +214,25 @@ __global__ void __launch_bounds__(NTHREADS, 1) gp_predict_kernel(const PredictPa
         const int nq = n_pad / TN;               // column tiles of L
         const int nct = nq + prm.alpha_ld / TN;  // + column tiles of alpha
 
-        // ---- this lane's two particle rows ------------------------------------------------------------
-        ParticleRec<KIND, DL> pr[2];
-        int pidx[2];
-        double prior[2];
-#pragma unroll
-        for (int i = 0; i < 2; i++) {
-            const int row = warp * 16 + i * 8 + r;
+        // ---- this lane's particle row --------------------------------------------------------------------
+        ParticleRec<KIND, DL> pr;
+        int pidx;
+        double prior = 1.0;
+        {
+            const int row = warp * 8 + r;
             const int m = row < count ? row : count - 1;
             const int p = prm.perm ? prm.perm[first + m] : first + m;
-            pidx[i] = row < count ? p : -1;
-            double pri = 1.0;
+            pidx = row < count ? p : -1;
 #pragma unroll
             for (int j = 0; j < d; j++) {
                 const double xj = prm.x[(long long)p * d + j];
-                pr[i].b[j] = xj / prm.ls[j];
+                pr.b[j] = xj / prm.ls[j];
                 if (KIND == 1) {
-                    pr[i].x[j] = xj;
-                    pri = fma(prm.lin_c2[j] * xj, xj, pri);
+                    pr.x[j] = xj;
+                    prior = fma(prm.lin_c2[j] * xj, xj, prior);
                 }
             }
-            if (KIND == 1) pri += c2last;
-            prior[i] = pri;
+            if (KIND == 1) prior += c2last;
         }
 
         // ---- TMA issue: all warps advance the same cursor, the duty warp issues ------------------------------
@@ -254,28 +264,25 @@ __global__ void __launch_bounds__(NTHREADS, 1) gp_predict_kernel(const PredictPa
             gb++;
         }
 
-        // ---- A fragments of the first chunk -------------------------------------------------------------
-        double a[KC / 4][2];  // a[k4][i] = K*[row 16 w + 8 i + r][k = 4 k4 + c] of the current chunk
+        // ---- A fragments of the first chunk: a[k4] = K*[row 8 w + r][k = 4 k4 + c] -----------------------------
+        double a[KC / 4];
         mbar_wait(&s.full[g % STAGES], (g / STAGES) & 1);
 #pragma unroll
-        for (int k4 = 0; k4 < KC / 4; k4++) {
-            double rec[REC_MAX];
-            load_record<KIND, DL>(&s.R[g % STAGES][(k4 * 4 + c) * REC], rec);
-            kstar_pair<KIND, DL>(rec, pr[0], pr[1], c2last, a[k4][0], a[k4][1]);
+        for (int k4 = 0; k4 < KC / 4; k4 += 2) {
+            double rec0[REC_MAX], rec1[REC_MAX];
+            load_record<KIND, DL>(&s.R[g % STAGES][(k4 * 4 + c) * REC], rec0);
+            load_record<KIND, DL>(&s.R[g % STAGES][(k4 * 4 + 4 + c) * REC], rec1);
+            kstar_pair<KIND, DL>(rec0, rec1, pr, c2last, exptab, a[k4], a[k4 + 1]);
         }
 
         ChunkCursor cur;
         cur.init(nq, nct, nkc, prm.tri);
-        double qacc[2] = {0.0, 0.0};
-        double sacc[2] = {0.0, 0.0};
-        double vrow[2] = {0.0, 0.0};
+        double qacc = 0.0, sacc = 0.0, vrow = 0.0;
 
         for (int ct = 0; ct < nct; ct++) {
-            double acc[2][16][2];
+            double acc[NJ][2];
 #pragma unroll
-            for (int i = 0; i < 2; i++)
-#pragma unroll
-                for (int j = 0; j < 16; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+            for (int j = 0; j < NJ; j++) acc[j][0] = acc[j][1] = 0.0;
 
             const int kbeg = cur.kbeg(ct);
             for (int k = kbeg; k < nkc; k++, g++) {
@@ -286,27 +293,32 @@ __global__ void __launch_bounds__(NTHREADS, 1) gp_predict_kernel(const PredictPa
                     bcur.next();
                     gb++;
                 }
-                // the next chunk (of this particle tile) provides the records for the next A fragments
+                // The next chunk provides the records for the next A fragments.  After the last chunk of the
+                // particle tile the fragments are recomputed from the current stage (values unused).
                 const bool has_next = !(ct == nct - 1 && k == nkc - 1);
-                const int stn = (int)((g + 1) % STAGES);
+                const int stn = has_next ? (int)((g + 1) % STAGES) : st;
                 if (has_next) mbar_wait(&s.full[stn], ((g + 1) / STAGES) & 1);
+                double an[KC / 4];
 #pragma unroll
                 for (int k4 = 0; k4 < KC / 4; k4++) {
-                    double b[16];
-#pragma unroll
-                    for (int j = 0; j < 16; j++) b[j] = s.B[st][k4 * 4 + c][j * 8 + r];
-                    const double a0 = a[k4][0], a1 = a[k4][1];
-                    if (has_next) {  // next chunk's A fragments for this k4, woven into the MMAs below
-                        double rec[REC_MAX];
-                        load_record<KIND, DL>(&s.R[stn][(k4 * 4 + c) * REC], rec);
-                        kstar_pair<KIND, DL>(rec, pr[0], pr[1], c2last, a[k4][0], a[k4][1]);
+                    if ((k4 & 1) == 0) {  // two of the next chunk's A fragments, woven into this block's MMAs
+                        double rec0[REC_MAX], rec1[REC_MAX];
+                        load_record<KIND, DL>(&s.R[stn][(k4 * 4 + c) * REC], rec0);
+                        load_record<KIND, DL>(&s.R[stn][(k4 * 4 + 4 + c) * REC], rec1);
+                        kstar_pair<KIND, DL>(rec0, rec1, pr, c2last, exptab, an[k4], an[k4 + 1]);
                     }
+                    const double ak = a[k4];
 #pragma unroll
-                    for (int j = 0; j < 16; j++) {
-                        dmma_m8n8k4(acc[0][j][0], acc[0][j][1], a0, b[j]);
-                        dmma_m8n8k4(acc[1][j][0], acc[1][j][1], a1, b[j]);
+                    for (int jg = 0; jg < NJ; jg += 8) {
+                        double b[8];
+#pragma unroll
+                        for (int j = 0; j < 8; j++) b[j] = s.B[st][k4 * 4 + c][(jg + j) * 8 + r];
+#pragma unroll
+                        for (int j = 0; j < 8; j++) dmma_m8n8k4(acc[jg + j][0], acc[jg + j][1], ak, b[j]);
                     }
                 }
+#pragma unroll
+                for (int k4 = 0; k4 < KC / 4; k4++) a[k4] = an[k4];
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&s.empty[st]);  // this warp is done with the ring slot
             }
@@ -315,68 +327,55 @@ __global__ void __launch_bounds__(NTHREADS, 1) gp_predict_kernel(const PredictPa
             if (ct < nq) {
                 // q[p] += sum_n C[p,n] * K*[p,n] over this tile's columns (K* regenerated per element)
 #pragma unroll
-                for (int j = 0; j < 16; j++) {  // fully unrolled: acc[][][] must stay in registers
-#pragma unroll
-                    for (int e = 0; e < 2; e++) {
-                        const int n = ct * TN + j * 8 + c * 2 + e;
-                        double rec[REC_MAX];
-                        load_record<KIND, DL>(gbk.coords + (long long)n * REC, rec);
-                        double k0, k1;
-                        kstar_pair<KIND, DL>(rec, pr[0], pr[1], c2last, k0, k1);
-                        qacc[0] = fma(acc[0][j][e], k0, qacc[0]);
-                        qacc[1] = fma(acc[1][j][e], k1, qacc[1]);
-                    }
+                for (int j = 0; j < NJ; j++) {  // fully unrolled: acc[][] must stay in registers
+                    const int n = ct * TN + j * 8 + c * 2;
+                    double rec0[REC_MAX], rec1[REC_MAX];
+                    load_record<KIND, DL>(gbk.coords + (long long)n * REC, rec0);
+                    load_record<KIND, DL>(gbk.coords + (long long)(n + 1) * REC, rec1);
+                    double k0, k1;
+                    kstar_pair<KIND, DL>(rec0, rec1, pr, c2last, exptab, k0, k1);
+                    qacc = fma(acc[j][0], k0, qacc);
+                    qacc = fma(acc[j][1], k1, qacc);
                 }
                 if (ct == nq - 1) {
                     // quadratic form complete: v[p] = prior[p] - q[p]
-#pragma unroll
-                    for (int i = 0; i < 2; i++) {
-                        double v = qacc[i];
-                        v += __shfl_xor_sync(0xffffffffu, v, 1);
-                        v += __shfl_xor_sync(0xffffffffu, v, 2);
-                        vrow[i] = prior[i] - v;
-                    }
+                    double v = qacc;
+                    v += __shfl_xor_sync(0xffffffffu, v, 1);
+                    v += __shfl_xor_sync(0xffffffffu, v, 2);
+                    vrow = prior - v;
                 }
             } else {
                 const int cbase = (ct - nq) * TN;
 #pragma unroll
-                for (int i = 0; i < 2; i++) {
-                    const int p = pidx[i];
+                for (int j = 0; j < NJ; j++) {
 #pragma unroll
-                    for (int j = 0; j < 16; j++) {
-#pragma unroll
-                        for (int e = 0; e < 2; e++) {
-                            const int col = cbase + j * 8 + c * 2 + e;
-                            if (col >= prm.dout) continue;
-                            const double mu = acc[i][j][e];
-                            if (KIND == 0) {
-                                if (prm.z) {
-                                    const double dz = __ldg(prm.z + col) - mu;
-                                    sacc[i] = fma(__ldg(prm.scale + col) * dz, dz, sacc[i]);
-                                }
-                                if (prm.mu_out && p >= 0) prm.mu_out[(long long)p * prm.dout + col] = mu;
-                            } else if (p >= 0) {
-                                const double var = vrow[i] * __ldg(prm.scale + col);
-                                const long long o = (long long)p * prm.dout + col;
-                                if (prm.x_new)  // torch.normal: randn * std + mean, two roundings (no FMA)
-                                    prm.x_new[o] = __dadd_rn(__dmul_rn(__ldg(prm.eps + o), sqrt(var)), mu);
-                                if (prm.mean_out) prm.mean_out[o] = mu;
-                                if (prm.var_out) prm.var_out[o] = var;
+                    for (int e = 0; e < 2; e++) {
+                        const int col = cbase + j * 8 + c * 2 + e;
+                        if (col >= prm.dout) continue;
+                        const double mu = acc[j][e];
+                        if (KIND == 0) {
+                            if (prm.z) {
+                                const double dz = __ldg(prm.z + col) - mu;
+                                sacc = fma(__ldg(prm.scale + col) * dz, dz, sacc);
                             }
+                            if (prm.mu_out && pidx >= 0) prm.mu_out[(long long)pidx * prm.dout + col] = mu;
+                        } else if (pidx >= 0) {
+                            const double var = vrow * __ldg(prm.scale + col);
+                            const long long o = (long long)pidx * prm.dout + col;
+                            if (prm.x_new)  // torch.normal: randn * std + mean, two roundings (no FMA)
+                                prm.x_new[o] = __dadd_rn(__dmul_rn(__ldg(prm.eps + o), sqrt(var)), mu);
+                            if (prm.mean_out) prm.mean_out[o] = mu;
+                            if (prm.var_out) prm.var_out[o] = var;
                         }
                     }
                 }
                 if (KIND == 0 && ct == nct - 1) {
-#pragma unroll
-                    for (int i = 0; i < 2; i++) {
-                        double S = sacc[i];
-                        S += __shfl_xor_sync(0xffffffffu, S, 1);
-                        S += __shfl_xor_sync(0xffffffffu, S, 2);
-                        if (c == 0 && pidx[i] >= 0) {
-                            const double v = vrow[i];
-                            if (prm.ll) prm.ll[pidx[i]] = -0.5 * S / v - (double)prm.dout * log(v) + prm.ll_const;
-                            if (prm.v_out) prm.v_out[pidx[i]] = v;
-                        }
+                    double S = sacc;
+                    S += __shfl_xor_sync(0xffffffffu, S, 1);
+                    S += __shfl_xor_sync(0xffffffffu, S, 2);
+                    if (c == 0 && pidx >= 0) {
+                        if (prm.ll) prm.ll[pidx] = -0.5 * S / vrow - (double)prm.dout * log(vrow) + prm.ll_const;
+                        if (prm.v_out) prm.v_out[pidx] = vrow;
                     }
                 }
             }

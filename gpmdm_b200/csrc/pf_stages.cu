@@ -132,7 +132,7 @@ __global__ void __launch_bounds__(1024) bucket_scan_kernel(int32_t* __restrict__
         int t = 0;
         for (int c = 0; c < C; c++) {
             tile_start[c] = t;
-            t += (cls_start[c + 1] - cls_start[c] + GPMDM_TILE - 1) / GPMDM_TILE;
+            t += (cls_start[c + 1] - cls_start[c] + GPMDM_TILE_P - 1) / GPMDM_TILE_P;
         }
         tile_start[C] = t;
         n_tiles[0] = t;
@@ -144,8 +144,8 @@ __global__ void __launch_bounds__(1024) bucket_scan_kernel(int32_t* __restrict__
         for (int t = threadIdx.x; t < nt; t += blockDim.x) {
             int32_t* d = tiles + 4ll * (tile_start[c] + t);
             d[0] = c;
-            d[1] = cls_start[c] + t * GPMDM_TILE;
-            d[2] = min(GPMDM_TILE, cnt - t * GPMDM_TILE);
+            d[1] = cls_start[c] + t * GPMDM_TILE_P;
+            d[2] = min(GPMDM_TILE_P, cnt - t * GPMDM_TILE_P);
             d[3] = 0;
         }
     }

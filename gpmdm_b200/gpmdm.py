@@ -29,7 +29,7 @@ import numpy as np
 import torch
 
 from . import _cabi
-from ._cabi import TILE, GpModel, check, ptr, stream
+from ._cabi import TILE_N, TILE_P, GpModel, check, ptr, stream
 
 
 def to_tensor(input_array, dtype, device):
@@ -428,7 +428,7 @@ class GPMDM(torch.nn.Module):
     def _pack_block(self, Xtrain, log_ls, Kinv, targets, alpha_ld, lin_c2, tri):
         lib = _cabi.lib()
         n, d = Xtrain.shape
-        n_pad = _round_up(n, TILE)
+        n_pad = _round_up(n, TILE_N)
         cols = [Xtrain / torch.exp(log_ls)]
         if lin_c2 is not None:
             cols.append(Xtrain * lin_c2[:d])
@@ -461,7 +461,7 @@ class GPMDM(torch.nn.Module):
                            lambdas=lam.data_ptr())
 
         # observation GP: one block over all frames
-        ald_y = _round_up(self.D, TILE)
+        ald_y = _round_up(self.D, TILE_N)
         oblk = self._pack_block(X, self.y_log_lengthscales.detach(), self.Ky_inv, self._Y_device(), ald_y, None, tri)
         ls_y = torch.exp(self.y_log_lengthscales.detach()).contiguous()
         lam2_y = (torch.exp(self.y_log_lambdas.detach()) ** 2).contiguous()
@@ -474,8 +474,8 @@ class GPMDM(torch.nn.Module):
             lam_x = (torch.exp(self.x_log_lambdas.detach()) ** -2).contiguous()
             offs = self.class_pair_offsets()
             dblks = [self._pack_block(Xin[offs[c]:offs[c + 1]], self.x_log_lengthscales.detach(), self.Kx_inv_class[c],
-                                      Xout[offs[c]:offs[c + 1]], TILE, c2, tri) for c in range(self.n_classes)]
-            dyn = model(dblks, self.d, self.d, TILE, 1, ls_x, c2, lam_x)
+                                      Xout[offs[c]:offs[c + 1]], TILE_N, c2, tri) for c in range(self.n_classes)]
+            dyn = model(dblks, self.d, self.d, TILE_N, 1, ls_x, c2, lam_x)
         else:
             dyn = None
         self._packed = dict(tri=tri, obs=obs, dyn=dyn, keep=keep,
@@ -516,9 +516,9 @@ class GPMDM(torch.nn.Module):
         if P == 0:
             return mean, var
         perm = torch.arange(P, dtype=torch.int32, device=self.device)
-        nt = (P + TILE - 1) // TILE
+        nt = (P + TILE_P - 1) // TILE_P
         t = torch.arange(nt, dtype=torch.int32, device=self.device)
-        tiles = torch.stack([torch.full_like(t, class_index), t * TILE, torch.clamp(P - t * TILE, max=TILE),
+        tiles = torch.stack([torch.full_like(t, class_index), t * TILE_P, torch.clamp(P - t * TILE_P, max=TILE_P),
                              torch.zeros_like(t)], 1).contiguous()
         n_tiles = torch.tensor([nt], dtype=torch.int32, device=self.device)
         check(lib.gpmdm_pf_propagate_f64(ctypes.byref(pk["dyn"]), ptr(Xs), ptr(perm), ptr(tiles), ptr(n_tiles), P, None,

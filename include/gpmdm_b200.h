@@ -33,7 +33,8 @@ extern "C" {
 #define GPMDM_E_UNSUPPORTED (-2) /* valid request outside this build's limits (d > 8, ...)      */
 #define GPMDM_E_NODEVICE (-3)    /* no sm_100 device                                            */
 
-#define GPMDM_TILE 128     /* particle-tile height, column-tile width and row padding of factors */
+#define GPMDM_TILE_P 64    /* particles per tile of the predict kernels                        */
+#define GPMDM_TILE_N 256   /* column-tile width: row padding of factors, granularity of alpha_ld */
 #define GPMDM_MAX_LATENT 8 /* latent dimension limit of the kernels                             */
 
 /* One GP "block": the observation GP is a single block over all N training frames; the dynamics GP
@@ -47,14 +48,14 @@ extern "C" {
  *                        tri = 1:  L[i][j] = Kinv[i][j] + Kinv[j][i] (i > j), Kinv[i][i], 0 (i < j)
  *                        tri = 0:  L = Kinv.   Zero padded.  (written by gpmdm_pack_quadform_f64)
  *   alpha  [n_pad, alpha_ld] = Kinv^T * targets (Y for the observation GP, Xout_c for dynamics),
- *                        zero padded to alpha_ld = multiple of GPMDM_TILE columns.
+ *                        zero padded to alpha_ld = multiple of GPMDM_TILE_N columns.
  */
 typedef struct gpmdm_gp_block {
     const double* coords;
     const double* L;
     const double* alpha;
     int64_t n;     /* real training rows of the block            */
-    int64_t n_pad; /* rows padded to a multiple of GPMDM_TILE    */
+    int64_t n_pad; /* rows padded to a multiple of GPMDM_TILE_N   */
 } gpmdm_gp_block;
 
 /* A GP model as consumed by the predict kernels.  `blocks` is a DEVICE array of n_blocks structs. */
@@ -63,7 +64,7 @@ typedef struct gpmdm_gp_model {
     int32_t n_blocks;
     int32_t d;        /* latent dimension (<= GPMDM_MAX_LATENT)                                   */
     int32_t dout;     /* D for the observation GP, d for the dynamics GP                          */
-    int32_t alpha_ld; /* columns of alpha (multiple of GPMDM_TILE, >= dout)                       */
+    int32_t alpha_ld; /* columns of alpha (multiple of GPMDM_TILE_N, >= dout)                       */
     int32_t kind;     /* 0 = RBF (gpmdm.py:381 get_y_kernel), 1 = RBF + linear (:408 get_x_kernel) */
     int32_t tri;      /* layout of L, see above                                                   */
     const double* lengthscales; /* device [d]   exp(log_lengthscales)                             */
@@ -88,10 +89,10 @@ int gpmdm_pack_quadform_f64(const double* Kinv, int64_t n, int64_t n_pad, int tr
 int gpmdm_pf_transition_f64(const int64_t* c_prev, const double* T, const double* E, int64_t P, int32_t C,
                             int64_t* c_new, void* stream);
 
-/* Groups particles by class so that every 128-particle tile of the dynamics kernel is class
+/* Groups particles by class so that every GPMDM_TILE_P-particle tile of the dynamics kernel is class
  * homogeneous (the reference's boolean-mask gather, gpmdm_pf.py:161).  Stable counting sort.
  *   perm  [P]            particle indices ordered by (class, index)
- *   tiles [P/128 + C, 4] {block, first position in perm, count, 0} per tile, int32
+ *   tiles [P/64 + C, 4]  {block, first position in perm, count, 0} per tile, int32
  *   n_tiles [1]          int32
  * workspace: gpmdm_workspace_bytes(P, C). */
 int gpmdm_pf_bucket_by_class(const int64_t* classes, int64_t P, int32_t C, int32_t* perm, int32_t* tiles,

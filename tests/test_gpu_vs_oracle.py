@@ -29,7 +29,7 @@ def particles_near_data(spec, P, seed):
     return spec.X[idx] + 0.05 * torch.randn(P, spec.d, dtype=torch.float64, generator=g)
 
 
-@pytest.mark.parametrize("P", [1, 100, 129, 3000])
+@pytest.mark.parametrize("P", [1, 64, 65, 100, 3000])
 def test_observation_gp_vs_oracle(cfg1, P):
     spec, wl, f, model = cfg1
     xs = particles_near_data(spec, P, 5)
@@ -169,7 +169,7 @@ def test_bucket_by_class_is_a_stable_partition():
             cls[cls == 1] = 0  # an empty class
         cls_d = cls.cuda()
         perm = torch.empty(P, dtype=torch.int32, device="cuda")
-        tiles = torch.zeros(P // 128 + C + 1, 4, dtype=torch.int32, device="cuda")
+        tiles = torch.zeros(P // 64 + C + 1, 4, dtype=torch.int32, device="cuda")
         nt = torch.zeros(1, dtype=torch.int32, device="cuda")
         ws = torch.empty(int(lib.gpmdm_workspace_bytes(P, C)) // 8 + 1, dtype=torch.float64, device="cuda")
         _cabi.check(lib.gpmdm_pf_bucket_by_class(cls_d.data_ptr(), P, C, perm.data_ptr(), tiles.data_ptr(),
@@ -180,7 +180,7 @@ def test_bucket_by_class_is_a_stable_partition():
         tl = tiles.cpu()[:n]
         covered = 0
         for blk, first, count, _ in tl.tolist():
-            assert 1 <= count <= 128 and first == covered
+            assert 1 <= count <= 64 and first == covered
             assert bool((cls[expect[first:first + count].long()] == blk).all())
             covered += count
         assert covered == P
