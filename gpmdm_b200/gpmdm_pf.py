@@ -35,7 +35,7 @@ from typing import Optional, Sequence
 import numpy as np
 import torch
 
-from . import _cabi
+from . import _cabi, sharding
 from ._cabi import check, ptr, stream
 from .gpmdm import GPMDM
 
@@ -76,16 +76,10 @@ class GPMDM_PF:
         self._cdf_mode = 0 if cdf_order == "sequential" else 1
         self._tri = bool(tri)
 
-        # one process per GPU; contiguous particle ranges
-        import torch.distributed as dist
-        use_dist = dist.is_available() and dist.is_initialized() if distributed is None else distributed
+        # one process per GPU; contiguous particle ranges (gpmdm_b200/sharding.py)
         self._pg = process_group
-        self._world = dist.get_world_size(process_group) if use_dist else 1
-        self._rank = dist.get_rank(process_group) if use_dist else 0
-        P, G = self._num_particles, self._world
-        if P % G != 0:
-            raise ValueError(f"num_particles ({P}) must be divisible by the number of ranks ({G})")
-        self._lo, self._hi = self._rank * (P // G), (self._rank + 1) * (P // G)
+        self._world, self._rank = sharding.world(process_group, distributed)
+        self._lo, self._hi = sharding.particle_range(self._num_particles, self._world, self._rank)
 
         self._packed = gpmdm.packed_models(self._tri)
         c32 = float(0.5 * self._gpmdm.D * _LOG_2PI)  # fp32 product, as gpmdm_pf.py:191
@@ -185,10 +179,7 @@ class GPMDM_PF:
             prof.append(ev)
         # -- the one exchange step: every rank gets every particle's (x', c', ll)
         if self._world > 1:
-            import torch.distributed as dist
-            dist.all_gather_into_tensor(self._ll_all, ll_l.clone(), group=self._pg)
-            dist.all_gather_into_tensor(self._x_new, x_new_l.clone(), group=self._pg)
-            dist.all_gather_into_tensor(self._c_new, c_new_l.clone(), group=self._pg)
+            sharding.all_gather_particles(self._x_new, self._c_new, self._ll_all, lo, hi, self._pg)
         # -- weights, cdf, resampling over all P particles (fixed order => identical on every rank)
         ll_new, lw_new, w_new = self._ll_all, self._log_weights_buf(), self._weights_buf()
         check(lib.gpmdm_pf_normalize_f64(ptr(ll_new), P, ptr(lw_new), ptr(w_new), ptr(self._stats), ptr(self._ws), st),

@@ -1,0 +1,134 @@
+"""GPU: training-side kernels (BASELINE config 5 shapes at oracle-checkable sizes): the kernel-matrix build with
+class-block masking and the hand-written NLL-gradient terms, against the oracle's torch-CPU expressions and
+torch autograd through them; and the GPMDM training surface (loss value, train_adam, save/load)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import gpmdm_oracle as orc
+from tests.helpers import product_model_from_spec, rel_err, synthetic_spec, t64
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def small():
+    spec, wl = synthetic_spec(3, 3, 20, 3, 40, sigma_n=1e-1, seed=4)  # N = 360, ragged vs 32-tiles
+    return spec, wl, product_model_from_spec(spec)
+
+
+def test_y_kernel_build_matches_reference_expression(small):
+    spec, wl, model = small
+    K = model.get_y_kernel(model.X, model.X).cpu()
+    K_o = orc.y_kernel(spec, spec.X, spec.X)
+    assert float(torch.max(torch.abs(K - K_o))) < 1e-12
+    K2 = model.get_y_kernel(model.X, model.X, flg_noise=False).cpu()
+    assert float(torch.max(torch.abs(K2 - orc.y_kernel(spec, spec.X, spec.X, False)))) < 1e-12
+
+
+def test_masked_x_kernel_build_matches_dense_mask(small):
+    spec, wl, model = small
+    Xin_o, Xout_o = orc.xin_xout(spec)
+    Xin, Xout, _ = model.get_Xin_Xout_matrices()
+    assert torch.equal(Xin.cpu(), Xin_o) and torch.equal(Xout.cpu(), Xout_o)
+    K = model.get_masked_x_kernel(Xin).cpu()
+    K_o = orc.x_kernel(spec, Xin_o, Xin_o) * orc.class_mask(spec)  # gpmdm.py:616
+    assert float(torch.max(torch.abs(K - K_o) / (1 + torch.abs(K_o)))) < 1e-13
+    assert torch.equal(K == 0, K_o == 0)  # exact zeros off the class blocks
+    assert torch.equal(model.get_M().cpu(), orc.class_mask(spec))
+
+
+@pytest.mark.parametrize("masked", [False, True])
+def test_kernel_gradient_terms_match_autograd(small, masked):
+    """G = dL/dK random (non-symmetric); our closed-form backward vs torch autograd through the oracle's
+    expression of the same kernel."""
+    spec, wl, model = small
+    g = torch.Generator().manual_seed(3)
+    if masked:
+        Xin_o, _ = orc.xin_xout(spec)
+        n = Xin_o.shape[0]
+        G = torch.randn(n, n, dtype=torch.float64, generator=g)
+        X = Xin_o.clone().requires_grad_(True)
+        pars = {k: getattr(spec, k).clone().requires_grad_(True) for k in ("x_log_lengthscales", "x_log_sigma_n", "x_log_lin_coeff")}
+        s2 = orc.ModelSpec(**{**spec.__dict__, **pars})
+        K_o = orc.x_kernel(s2, X, X) * orc.class_mask(spec)
+        (G * K_o).sum().backward()
+        Xd = Xin_o.cuda().requires_grad_(True)
+        for k in pars:
+            getattr(model, k).requires_grad_(True)
+            getattr(model, k).grad = None
+        K = model.get_masked_x_kernel(Xd)
+        (G.cuda() * K).sum().backward()
+        assert rel_err(Xd.grad.cpu(), X.grad) < 1e-9 or float(torch.max(torch.abs(Xd.grad.cpu() - X.grad))) < 1e-9
+        for k in pars:
+            a, b = getattr(model, k).grad.cpu(), pars[k].grad
+            assert float(torch.max(torch.abs(a - b) / (1e-9 + torch.abs(b)))) < 1e-9, k
+    else:
+        n = spec.N
+        G = torch.randn(n, n, dtype=torch.float64, generator=g)
+        X = spec.X.clone().requires_grad_(True)
+        pars = {k: getattr(spec, k).clone().requires_grad_(True) for k in ("y_log_lengthscales", "y_log_sigma_n")}
+        s2 = orc.ModelSpec(**{**spec.__dict__, **pars})
+        (G * orc.y_kernel(s2, X, X)).sum().backward()
+        Xd = spec.X.cuda().requires_grad_(True)
+        for k in pars:
+            getattr(model, k).requires_grad_(True)
+            getattr(model, k).grad = None
+        (G.cuda() * model.get_y_kernel(Xd, Xd)).sum().backward()
+        assert float(torch.max(torch.abs(Xd.grad.cpu() - X.grad) / (1e-9 + torch.abs(X.grad)))) < 1e-8
+        for k in pars:
+            a, b = getattr(model, k).grad.cpu(), pars[k].grad
+            assert float(torch.max(torch.abs(a - b) / (1e-9 + torch.abs(b)))) < 1e-9, k
+    model.set_evaluation_mode()
+
+
+def test_nll_value_and_gradient_match_reference_formula(small):
+    """gpdm_loss (gpmdm.py:721-760) and its gradient w.r.t. X and all seven hyper-parameters against autograd
+    through the oracle's restatement of get_y_neg_log_likelihood / get_x_neg_log_likelihood (:550-628)."""
+    spec, wl, model = small
+    names = ("y_log_lengthscales", "y_log_lambdas", "y_log_sigma_n", "x_log_lengthscales", "x_log_lambdas",
+             "x_log_sigma_n", "x_log_lin_coeff")
+    pars = {k: getattr(spec, k).clone().requires_grad_(True) for k in names}
+    X = spec.X.clone().requires_grad_(True)
+    s2 = orc.ModelSpec(**{**spec.__dict__, **pars, "X": X})
+    Xin_o, Xout_o = orc.xin_xout(s2)
+    loss_o = orc.y_neg_log_likelihood(s2) + orc.x_neg_log_likelihood(s2, Xin_o, Xout_o)
+    loss_o.backward()
+    model.set_training_mode("all")
+    model.X.requires_grad_(True)
+    for p in model.parameters():
+        p.grad = None
+    loss = model.gpdm_loss(model._Y_device(), spec.N)
+    loss.backward()
+    assert abs(float(loss) - float(loss_o)) < 1e-9 * abs(float(loss_o))
+    assert float(torch.max(torch.abs(model.X.grad.cpu() - X.grad) / (1e-6 + torch.abs(X.grad)))) < 1e-6
+    for k in names:
+        a, b = getattr(model, k).grad.cpu(), pars[k].grad
+        assert float(torch.max(torch.abs(a - b) / (1e-6 + torch.abs(b)))) < 1e-6, k
+    model.X.requires_grad_(False)
+    model.set_evaluation_mode()
+
+
+def test_train_adam_save_load_roundtrip(tmp_path):
+    from gpmdm_b200 import GPMDM, GPMDM_PF, synthetic
+
+    wl = synthetic.make_sequences(2, 12, 2, 30, seed=8, n_test_trials=1, test_frames=6)
+    hp = synthetic.notebook_hyperparameters(12, 3, 1e-1)
+    m = GPMDM(D=12, d=3, n_classes=2, dyn_target="full", dyn_back_step=1, **hp)
+    for c in range(2):
+        for s in wl.sequences[c]:
+            m.add_data(s, c)
+    m.init_X()
+    losses = m.train_adam(6, 0, lr=0.01)
+    assert len(losses) == 6 and losses[-1] < losses[0] and all(np.isfinite(losses))
+    path = os.path.join(tmp_path, "model.pth")
+    m.save(path)
+    m2 = GPMDM.load(path)
+    for (k, a), (_, b) in zip(m.state_dict().items(), m2.state_dict().items()):
+        assert torch.equal(a, b), k
+    assert float(torch.max(torch.abs(m.Ky_inv - m2.Ky_inv))) <= 1e-9 * float(torch.max(torch.abs(m.Ky_inv)))
+    pf = GPMDM_PF(m2, synthetic.markov_matrix(2), 64, seed=3)
+    pf.update(wl.test_trials[0][1][0])
+    assert abs(float(pf.class_probabilities().sum()) - 1.0) < 1e-12
