@@ -47,6 +47,7 @@ constexpr int TN = GPMDM_TILE_N;  // columns per column tile
 constexpr int KC = 16;            // k rows per chunk
 constexpr int STAGES = 6;         // B / record ring depth (TMA)
 constexpr int AHEAD = 3;          // chunks in flight ahead of the consumers
+constexpr unsigned SKEW_NS = 1300;  // start-up skew between the two warps of a sub-partition (~0.5 chunk)
 constexpr int LDB = TN + 4;
 constexpr int NTHREADS = 256;
 constexpr int NWARPS = NTHREADS / 32;
@@ -278,6 +279,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) gp_predict_kernel(const PredictPa
         ChunkCursor cur;
         cur.init(nq, nct, nkc, prm.tri);
         double qacc = 0.0, sacc = 0.0, vrow = 0.0;
+        // The two warps of an SM sub-partition (w, w + 4) share one fp64 datapath.  Started together they run in
+        // lockstep and stall it together at every chunk boundary / exponential block; a one-off skew of about
+        // half a chunk lets each warp's non-MMA phases hide under the other's DMMAs (ncu: idle 13% -> see profiles/).
+        if (warp >= NWARPS / 2) __nanosleep(SKEW_NS);
 
         for (int ct = 0; ct < nct; ct++) {
             double acc[NJ][2];

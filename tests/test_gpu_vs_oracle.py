@@ -240,3 +240,77 @@ def test_constructor_errors_match_reference():
         GPMDM_PF(model, synthetic.markov_matrix(3), 10)  # gpmdm_pf.py:74-75
     with pytest.raises(ValueError):
         model.add_data(np.zeros((5, 11), dtype=np.float32), 0)  # gpmdm.py:295-296
+
+
+def test_cfg2_100k_particles_sample_vs_oracle(cfg1):
+    """BASELINE config 2: 2-class model, N = 2000, P = 100 000 on one B200, fp64 exact path.  The oracle is
+    evaluated on a 1500-particle sample; batch-size independence makes that a statement about all rows."""
+    spec, wl, f, model = cfg1
+    P = 100_000
+    xs = particles_near_data(spec, P, 12)
+    xs_d = xs.cuda()
+    mu, var = model.map_x_to_y(xs_d)
+    sample = torch.randperm(P, generator=torch.Generator().manual_seed(1))[:1500]
+    mu_s, var_s = model.map_x_to_y(xs_d[sample.cuda()].contiguous())
+    assert torch.equal(mu[sample.cuda()], mu_s) and torch.equal(var[sample.cuda()], var_s)  # row results are batch independent
+    mu_o, var_o, v_o = orc.map_x_to_y(spec, f, xs[sample])
+    scale = torch.clamp(torch.abs(mu_o).max(dim=1, keepdim=True).values, min=1e-3)
+    assert scaled_err(mu_s.cpu(), mu_o, scale) < TOL
+    lam = (torch.exp(spec.y_log_lambdas) ** -2).unsqueeze(0).expand(var_o.shape)
+    assert scaled_err(var_s.cpu(), var_o, lam) < TOL
+    v = var[:, 0] / lam[0, 0].item()
+    assert bool(torch.all(v > 0)) and bool(torch.all(v <= 1 + 1e-12))
+    # a full filter step at P = 100k with injected draws: transition / ancestors exact w.r.t. the oracle stages
+    from gpmdm_b200 import GPMDM_PF
+    C, d = spec.n_classes, spec.d
+    T = synthetic.markov_matrix(C)
+    pf = GPMDM_PF(model, T, P, seed=3, cdf_order="sequential")
+    E, eps, u = synthetic.raw_draws(P, C, d, 77)
+    c_prev = pf._particle_classes.cpu().clone()
+    pf.update(wl.test_trials[0][1][0], draws=(E, eps, u))
+    assert torch.equal(pf.last_pre_resample_classes.cpu(), orc.transition(c_prev, T.to(torch.float64), E))
+    lw_o, w_o = orc.normalize(pf._log_likelihoods.cpu())
+    assert torch.equal(pf._log_weights.cpu(), lw_o)
+    assert torch.equal(pf.last_ancestors.cpu(), orc.resample(pf._weights.cpu(), u))
+    assert abs(float(pf._weights.sum()) - 1.0) < 1e-12
+
+
+def test_cfg3_scale_properties():
+    """BASELINE config 3 factor sizes (C = 8, N = 20 000, D = 62), where the oracle's dense objects are out of
+    reach: size-independent properties -- the triangular and dense packings are two independent evaluations of
+    k^T K^-1 k and must agree; variances lie in (0, prior]; a particle sitting on a training point predicts that
+    frame; weights sum to one; systematic-resampling ancestors are sorted; the step is reproducible."""
+    from gpmdm_b200 import GPMDM_PF
+
+    spec, wl = synthetic_spec(8, 3, 62, 25, 100, sigma_n=1e-1, seed=0)
+    model = product_model_from_spec(spec)
+    g = torch.Generator().manual_seed(2)
+    idx = torch.randint(0, spec.N, (1024,), generator=g)
+    xs = (spec.X[idx] + 0.02 * torch.randn(1024, 3, dtype=torch.float64, generator=g)).cuda()
+    model._packed = None
+    model.packed_models(True)
+    mu_t, var_t = model.map_x_to_y(xs)
+    m_t, v_t = model.map_x_dynamics_for_class(xs, 3)
+    model._packed = None
+    model.packed_models(False)
+    mu_d, var_d = model.map_x_to_y(xs)
+    m_d, v_d = model.map_x_dynamics_for_class(xs, 3)
+    model._packed = None
+    assert float(torch.max(torch.abs(mu_t - mu_d))) == 0.0 and float(torch.max(torch.abs(m_t - m_d))) == 0.0
+    assert float(torch.max(torch.abs(var_t - var_d))) < 1e-9
+    prior = 1 + (xs ** 2).sum(1) + 1  # all-ones linear coefficients
+    assert float(torch.max(torch.abs(v_t - v_d) / prior.unsqueeze(1))) < 1e-9
+    assert bool(torch.all(var_t > 0)) and bool(torch.all(var_t <= 1 + 1e-9))
+    # on a training point the GP mean reproduces the (noisy) training frame to within the noise level
+    mu_x, var_x = model.map_x_to_y(spec.X[idx[:64]].cuda())
+    assert float(torch.max(torch.abs(mu_x.cpu() - spec.Y[idx[:64]]))) < 0.5
+    T = synthetic.markov_matrix(8)
+    outs = []
+    for rep in range(2):
+        pf = GPMDM_PF(model, T, 4096, seed=11, resampling="systematic", cdf_order="blocked")
+        pf.update(wl.test_trials[0][1][0])
+        outs.append((pf._particle_states.clone(), pf.last_ancestors.clone(), pf.class_probabilities()))
+        assert abs(float(pf._weights.sum()) - 1.0) < 1e-12
+        anc = pf.last_ancestors
+        assert bool(torch.all(anc[1:] >= anc[:-1]))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
