@@ -25,6 +25,12 @@ class GpModel(ctypes.Structure):
                 ("kind", _i32), ("tri", _i32), ("lengthscales", _ptr), ("lin_c2", _ptr), ("lambdas", _ptr)]
 
 
+class GpModelTf32(ctypes.Structure):
+    """struct gpmdm_gp_model_tf32"""
+    _fields_ = [("coords", _ptr), ("wtiles", _ptr), ("atiles", _ptr), ("n", _i64), ("n_pad", _i64), ("d", _i32),
+                ("dout", _i32), ("lengthscales", _ptr), ("lambdas", _ptr)]
+
+
 _SIGNATURES = {
     "gpmdm_abi_version": (ctypes.c_int, []),
     "gpmdm_last_error": (ctypes.c_char_p, []),
@@ -42,6 +48,12 @@ _SIGNATURES = {
     "gpmdm_pf_draws_philox": (ctypes.c_int, [_u64, _u64, _i64, _i64, _i64, _i32, _i32, _i32, _ptr, _ptr, _ptr,
                                              _ptr]),
     "gpmdm_workspace_bytes": (_i64, [_i64, _i32]),
+    "gpmdm_tf32_wtiles_bytes": (_i64, [_i64]),
+    "gpmdm_tf32_atiles_bytes": (_i64, [_i64]),
+    "gpmdm_pack_whitened_tf32": (ctypes.c_int, [_ptr, _i64, _i64, _ptr, _ptr]),
+    "gpmdm_pack_alpha_tf32": (ctypes.c_int, [_ptr, _i64, _i64, _i32, _ptr, _ptr]),
+    "gpmdm_pf_observe_tf32": (ctypes.c_int, [ctypes.POINTER(GpModelTf32), _ptr, _i64, _ptr, _f64, _ptr, _ptr, _ptr,
+                                             _ptr]),
     "gpmdm_kernel_build_f64": (ctypes.c_int, [_ptr, _i64, _i32, _i32, _ptr, _ptr, _f64, _ptr, _i32, _ptr, _ptr]),
     "gpmdm_kernel_grad_f64": (ctypes.c_int, [_ptr, _ptr, _i64, _i32, _i32, _ptr, _ptr, _f64, _ptr, _i32, _ptr, _ptr,
                                              _ptr, _ptr, _ptr, _ptr]),

@@ -1,0 +1,463 @@
+// tf32 variant of the observation-GP kernel (BASELINE config 4): tcgen05 tensor cores, TMEM accumulators.
+//
+// Replaces the same reference lines as the fp64 kernel (gpmdm/gpmdm.py:923-963 + gpmdm_pf.py:188-192) for
+// callers that accept ~1e-4 relative accuracy.  It is NOT the fp64 kernel with narrower types:
+//   * the explicit-inverse form 1 - k^T K^-1 k is unusable in fp32 (K^-1 entries reach 1/sigma_n^2, rounding
+//     exceeds the variance), so the variance uses the whitened form  v = 1 - |W k|^2,  W = U^-T from the
+//     reference's upper Cholesky factor K = U^T U (gpmdm.py:1287-1288) -- positive terms bounded by the prior;
+//   * plain tf32 inputs (10-bit mantissa) would cap accuracy at ~5e-4, so every product is error-compensated
+//     ("3xTF32"):  a b ~ a_hi b_hi + a_lo b_hi + a_hi b_lo  with a_hi = tf32(a), a_lo = tf32(a - a_hi): three
+//     tcgen05.mma per k-step into one fp32 TMEM accumulator, ~2^-21 relative per product.
+//
+// Shape: per 128-particle tile and 256-column tile J of W (lower triangular: k < 256 (J+1)),
+//     U[p, n] = sum_k K*[p, k] W[n, k]      (tcgen05.mma M=128, N=256, K=8, kind::tf32, A and B from shared memory)
+//     q[p]   += sum_n U[p, n]^2             (epilogue: tcgen05.ld, one particle row per thread)
+// then one more tile with B = alpha^T for the mean and the fused log-likelihood.
+//
+// Warp roles (512 threads, one CTA per SM):
+//   warp 0       TMA producer: one cp.async.bulk (32 KB) per k-chunk of pre-packed W tiles -> B ring (3 stages)
+//   warp 1       MMA issuer (one elected lane): 6 tcgen05.mma per chunk, tcgen05.commit -> mbarriers; owns TMEM
+//   warps 4-11   K* generators: exp2-based RBF in fp32 from latent coordinates, hi/lo split, written straight into
+//                the UMMA canonical (core-matrix, no-swizzle, K-major) layout of the A ring (4 stages)
+//   warps 12-15  epilogue: TMEM -> registers, sum of squares / mean / log-likelihood; double-buffered accumulator
+// The operand tiles are packed on the host side once (gpmdm_pack_whitened_tf32) in exactly the byte order the
+// tensor core reads, so a 1-D bulk copy lands them ready to use (no tensor maps, no swizzle).
+#include <math.h>
+
+#include "common.cuh"
+
+namespace gpmdm {
+namespace tf32 {
+
+constexpr int TM = 128;      // particles per CTA tile (UMMA M)
+constexpr int TN = 256;      // columns per column tile (UMMA N)
+constexpr int KC = 16;       // k per chunk = 2 UMMA k-steps of 8
+constexpr int ASTAGES = 4;
+constexpr int BSTAGES = 3;
+constexpr int A_HALF = TM * KC;          // floats in the hi (or lo) part of an A stage
+constexpr int B_HALF = TN * KC;          // floats in the hi (or lo) part of a B stage / packed tile
+constexpr int NGEN = 256;                // generator threads
+constexpr int NEPI = 128;                // epilogue threads
+constexpr int NTHREADS = 512;
+constexpr int GEN_WARP0 = 4, EPI_WARP0 = 12;
+constexpr uint32_t LBO = 128, SBO = (KC / 4) * 128;  // core-matrix strides (bytes) along K and along M/N
+constexpr int CREC = 8;                  // floats per training record (a_i padded to 8)
+
+struct __align__(1024) Smem {
+    float A[ASTAGES][2][A_HALF];   // [stage][hi|lo] 8 KB each
+    float B[BSTAGES][2][B_HALF];   // [stage][hi|lo] 16 KB each
+    uint64_t a_full[ASTAGES], a_empty[ASTAGES], b_full[BSTAGES], b_empty[BSTAGES], t_full[2], t_empty[2];
+    uint32_t tmem_base;
+};
+
+struct Params {
+    const float* coords;   // [n_pad, CREC]
+    const float* wtiles;   // packed W tiles
+    const float* atiles;   // packed alpha tiles
+    int n_pad, d, dout;
+    const double* ls;      // [d]
+    const double* lam2;    // [dout]
+    const double* x;       // [P, d]
+    long long P;
+    const double* z;
+    double ll_const;
+    double* ll;
+    double* mu_out;
+    double* v_out;
+};
+
+// element (row, k) of a [rows x KC] operand tile in the canonical no-swizzle K-major layout, in floats
+__host__ __device__ __forceinline__ int tile_index(int row, int k) {
+    return (row >> 3) * (SBO / 4) + (k >> 2) * (LBO / 4) + (row & 7) * 4 + (k & 3);
+}
+
+__device__ __forceinline__ uint64_t smem_desc(const void* p) {
+    // SM100 shared-memory matrix descriptor: start address, leading (K) / stride (M,N) byte offsets in 16-byte
+    // units, version 1, no swizzle
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_u32(p) >> 4) & 0x3fff);
+    d |= (uint64_t)((LBO >> 4) & 0x3fff) << 16;
+    d |= (uint64_t)((SBO >> 4) & 0x3fff) << 32;
+    d |= (uint64_t)1 << 46;
+    return d;
+}
+// instruction descriptor: D = f32, A = B = tf32, both K-major, N = 256, M = 128
+constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(IDESC), "r"(accumulate), "r"(0u)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+    uint32_t* u = reinterpret_cast<uint32_t*>(v);
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+        : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]), "=r"(u[8]),
+          "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15]), "=r"(u[16]),
+          "=r"(u[17]), "=r"(u[18]), "=r"(u[19]), "=r"(u[20]), "=r"(u[21]), "=r"(u[22]), "=r"(u[23]), "=r"(u[24]),
+          "=r"(u[25]), "=r"(u[26]), "=r"(u[27]), "=r"(u[28]), "=r"(u[29]), "=r"(u[30]), "=r"(u[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ float to_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+
+// number of W tiles before column tile J, and in total
+__host__ __device__ __forceinline__ long long wtile_offset(int J) { return (long long)(TN / KC) * J * (J + 1) / 2; }
+
+template <int DL>
+__global__ void __launch_bounds__(NTHREADS, 1) observe_tf32_kernel(const Params prm) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    Smem& s = *reinterpret_cast<Smem*>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nq = prm.n_pad / TN, nkc = prm.n_pad / KC;
+    const int nct = nq + 1;  // + one alpha tile (dout <= 256)
+    const int n_tiles = (int)((prm.P + TM - 1) / TM);
+
+    if (tid == 0) {
+        for (int i = 0; i < ASTAGES; i++) {
+            mbar_init(&s.a_full[i], NGEN);
+            mbar_init(&s.a_empty[i], 1);
+        }
+        for (int i = 0; i < BSTAGES; i++) {
+            mbar_init(&s.b_full[i], 1);
+            mbar_init(&s.b_empty[i], 1);
+        }
+        for (int i = 0; i < 2; i++) {
+            mbar_init(&s.t_full[i], 1);
+            mbar_init(&s.t_empty[i], NEPI);
+        }
+        mbar_fence_init();
+    }
+    if (warp == 1) {  // TMEM: all 512 columns (two 256-column fp32 accumulators)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s.tmem_base)),
+                     "r"(512u)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = s.tmem_base;
+
+    // chunk count of column tile ct: W tiles are lower triangular (k < 256 (J+1)); the alpha tile needs all k
+    auto chunks_of = [&](int ct) { return ct < nq ? (ct + 1) * (TN / KC) : nkc; };
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            uint32_t g = 0;
+            for (int t = blockIdx.x; t < n_tiles; t += gridDim.x)
+                for (int ct = 0; ct < nct; ct++) {
+                    const float* base = ct < nq ? prm.wtiles + wtile_offset(ct) * (2 * B_HALF) : prm.atiles;
+                    const int nch = chunks_of(ct);
+                    for (int kc = 0; kc < nch; kc++, g++) {
+                        const int st = g % BSTAGES;
+                        mbar_wait(&s.b_empty[st], ((g / BSTAGES) & 1) ^ 1);
+                        mbar_expect_tx(&s.b_full[st], 2 * B_HALF * 4);
+                        bulk_g2s(&s.B[st][0][0], base + (long long)kc * (2 * B_HALF), 2 * B_HALF * 4, &s.b_full[st]);
+                    }
+                }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            uint32_t g = 0, tcount = 0;
+            for (int t = blockIdx.x; t < n_tiles; t += gridDim.x)
+                for (int ct = 0; ct < nct; ct++, tcount++) {
+                    const int acc = tcount & 1;
+                    mbar_wait(&s.t_empty[acc], ((tcount >> 1) & 1) ^ 1);  // epilogue drained this accumulator
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem + (uint32_t)acc * TN;
+                    const int nch = chunks_of(ct);
+                    for (int kc = 0; kc < nch; kc++, g++) {
+                        const int sa = g % ASTAGES, sb = g % BSTAGES;
+                        mbar_wait(&s.a_full[sa], (g / ASTAGES) & 1);
+                        mbar_wait(&s.b_full[sb], (g / BSTAGES) & 1);
+                        tc_fence_after();
+#pragma unroll
+                        for (int k8 = 0; k8 < KC / 8; k8++) {
+                            const uint32_t koff = k8 * 2 * LBO;  // two core matrices (8 tf32) along K per MMA
+                            const uint64_t a_hi = smem_desc(reinterpret_cast<const char*>(&s.A[sa][0][0]) + koff);
+                            const uint64_t a_lo = smem_desc(reinterpret_cast<const char*>(&s.A[sa][1][0]) + koff);
+                            const uint64_t b_hi = smem_desc(reinterpret_cast<const char*>(&s.B[sb][0][0]) + koff);
+                            const uint64_t b_lo = smem_desc(reinterpret_cast<const char*>(&s.B[sb][1][0]) + koff);
+                            umma_tf32(d_tmem, a_hi, b_hi, (kc | k8) != 0);
+                            umma_tf32(d_tmem, a_lo, b_hi, 1);
+                            umma_tf32(d_tmem, a_hi, b_lo, 1);
+                        }
+                        umma_commit(&s.a_empty[sa]);  // arrives when the MMAs above have read the operands
+                        umma_commit(&s.b_empty[sb]);
+                    }
+                    umma_commit(&s.t_full[acc]);  // accumulator complete
+                }
+        }
+    } else if (warp >= GEN_WARP0 && warp < EPI_WARP0) {
+        // ===================== K* generators =====================
+        const int gt = tid - GEN_WARP0 * 32;
+        const int row = gt & (TM - 1), khalf = gt >> 7;  // 8 consecutive k per thread
+        constexpr float LOG2E = 1.4426950408889634f;
+        uint32_t g = 0;
+        for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+            long long p = (long long)t * TM + row;
+            if (p >= prm.P) p = prm.P - 1;
+            float b[DL];
+#pragma unroll
+            for (int j = 0; j < DL; j++) b[j] = (float)(prm.x[p * DL + j] / prm.ls[j]);
+            for (int ct = 0; ct < nct; ct++) {
+                const int nch = chunks_of(ct);
+                for (int kc = 0; kc < nch; kc++, g++) {
+                    const int sa = g % ASTAGES;
+                    float hi[8], lo[8];
+                    const float* rec = prm.coords + (long long)(kc * KC + khalf * 8) * CREC;
+#pragma unroll
+                    for (int kk = 0; kk < 8; kk++) {
+                        float a[CREC];
+                        const float4 r0 = __ldg(reinterpret_cast<const float4*>(rec + kk * CREC));
+                        a[0] = r0.x, a[1] = r0.y, a[2] = r0.z, a[3] = r0.w;
+                        if (DL > 4) {
+                            const float4 r1 = __ldg(reinterpret_cast<const float4*>(rec + kk * CREC + 4));
+                            a[4] = r1.x, a[5] = r1.y, a[6] = r1.z, a[7] = r1.w;
+                        }
+                        float dist = 0.f;
+#pragma unroll
+                        for (int j = 0; j < DL; j++) {
+                            const float tdiff = a[j] - b[j];
+                            dist = fmaf(tdiff, tdiff, dist);
+                        }
+                        const float kv = exp2f(-LOG2E * dist);
+                        hi[kk] = to_tf32(kv);
+                        lo[kk] = to_tf32(kv - hi[kk]);
+                    }
+                    mbar_wait(&s.a_empty[sa], ((g / ASTAGES) & 1) ^ 1);
+                    float* ah = &s.A[sa][0][0];
+                    float* al = &s.A[sa][1][0];
+#pragma unroll
+                    for (int q = 0; q < 2; q++) {
+                        const int idx = tile_index(row, khalf * 8 + q * 4);
+                        *reinterpret_cast<float4*>(ah + idx) = make_float4(hi[q * 4], hi[q * 4 + 1], hi[q * 4 + 2], hi[q * 4 + 3]);
+                        *reinterpret_cast<float4*>(al + idx) = make_float4(lo[q * 4], lo[q * 4 + 1], lo[q * 4 + 2], lo[q * 4 + 3]);
+                    }
+                    fence_async_smem();  // generic-proxy stores -> visible to the tensor core's async proxy
+                    mbar_arrive(&s.a_full[sa]);
+                }
+            }
+        }
+    } else if (warp >= EPI_WARP0) {
+        // ===================== epilogue =====================
+        const int et = tid - EPI_WARP0 * 32;  // particle row; this warp owns TMEM lanes 32 (warp % 4) ..
+        const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+        uint32_t tcount = 0;
+        for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+            const long long p = (long long)t * TM + et;
+            const bool valid = p < prm.P;
+            float q = 0.f;
+            double S = 0.0;
+            for (int ct = 0; ct < nct; ct++, tcount++) {
+                const int acc = tcount & 1;
+                mbar_wait(&s.t_full[acc], (tcount >> 1) & 1);
+                tc_fence_after();
+                const uint32_t taddr = tmem + lane_base + (uint32_t)acc * TN;
+                if (ct < nq) {
+#pragma unroll 1
+                    for (int cb = 0; cb < TN; cb += 32) {
+                        float v[32];
+                        tmem_ld32(taddr + cb, v);
+                        float part = 0.f;
+#pragma unroll
+                        for (int i = 0; i < 32; i++) part = fmaf(v[i], v[i], part);
+                        q += part;
+                    }
+                } else {
+#pragma unroll 1
+                    for (int cb = 0; cb < TN && cb < prm.dout; cb += 32) {
+                        float v[32];
+                        tmem_ld32(taddr + cb, v);
+#pragma unroll
+                        for (int i = 0; i < 32; i++) {
+                            const int col = cb + i;
+                            if (col < prm.dout) {
+                                if (prm.z) {
+                                    const double dz = prm.z[col] - (double)v[i];
+                                    S = fma(prm.lam2[col] * dz, dz, S);
+                                }
+                                if (prm.mu_out && valid) prm.mu_out[p * prm.dout + col] = (double)v[i];
+                            }
+                        }
+                    }
+                }
+                tc_fence_before();
+                mbar_arrive(&s.t_empty[acc]);
+            }
+            if (valid) {
+                const double v = 1.0 - (double)q;
+                if (prm.ll) prm.ll[p] = -0.5 * S / v - (double)prm.dout * log(v) + prm.ll_const;
+                if (prm.v_out) prm.v_out[p] = v;
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+    }
+}
+
+// ---- packing ------------------------------------------------------------------------------------------------
+// W [n, n] (fp64, lower triangular, W = U^-T) -> tf32 hi/lo tiles in the UMMA canonical layout.
+//   tile (J, kc), kc < 16 (J+1):  B[row = n - 256 J][k - 16 kc] = W[n][k]
+__global__ void pack_whitened_kernel(const double* __restrict__ W, long long n, int n_pad, float* __restrict__ out) {
+    const int nq = n_pad / TN;
+    const long long total_tiles = wtile_offset(nq);
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total_tiles * B_HALF) return;
+    const long long tile = i / B_HALF;
+    const int e = (int)(i % B_HALF);
+    // invert wtile_offset: largest J with offset(J) <= tile
+    int J = (int)((sqrt(1.0 + 8.0 * (double)tile / (TN / KC)) - 1.0) * 0.5);
+    while (wtile_offset(J + 1) <= tile) J++;
+    while (wtile_offset(J) > tile) J--;
+    const int kc = (int)(tile - wtile_offset(J));
+    const int row = e / KC, k = e % KC;
+    const long long nn = (long long)J * TN + row, kk = (long long)kc * KC + k;
+    const double w = (nn < n && kk < n && kk <= nn) ? W[nn * n + kk] : 0.0;
+    const float hi = __uint_as_float(__float_as_uint((float)w) & 0xffffe000u);  // exact tf32 (truncation)
+    const float lo = (float)(w - (double)hi);
+    float* dst = out + tile * (2 * B_HALF);
+    const int idx = tile_index(row, k);
+    dst[idx] = hi;
+    dst[B_HALF + idx] = lo;
+}
+
+// alpha [n, dout] (fp64) -> tiles (kc):  B[row = output column j][k - 16 kc] = alpha[k][j]
+__global__ void pack_alpha_kernel(const double* __restrict__ alpha, long long n, int n_pad, int dout,
+                                  float* __restrict__ out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long total = (long long)(n_pad / KC) * B_HALF;
+    if (i >= total) return;
+    const long long kc = i / B_HALF;
+    const int e = (int)(i % B_HALF);
+    const int row = e / KC, k = e % KC;
+    const long long kk = kc * KC + k;
+    const double a = (row < dout && kk < n) ? alpha[kk * dout + row] : 0.0;
+    const float hi = __uint_as_float(__float_as_uint((float)a) & 0xffffe000u);
+    const float lo = (float)(a - (double)hi);
+    float* dst = out + kc * (2 * B_HALF);
+    const int idx = tile_index(row, k);
+    dst[idx] = hi;
+    dst[B_HALF + idx] = lo;
+}
+
+template <int DL>
+static int launch(const Params& prm, int grid, cudaStream_t st) {
+    static bool configured = false;
+    auto kern = observe_tf32_kernel<DL>;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
+        if (e != cudaSuccess) {
+            set_error("cudaFuncSetAttribute(observe_tf32): %s", cudaGetErrorString(e));
+            return (int)e;
+        }
+        configured = true;
+    }
+    kern<<<grid, NTHREADS, sizeof(Smem), st>>>(prm);
+    return check_launch("observe_tf32_kernel");
+}
+
+}  // namespace tf32
+}  // namespace gpmdm
+
+using namespace gpmdm;
+
+extern "C" int64_t gpmdm_tf32_wtiles_bytes(int64_t n_pad) {
+    return tf32::wtile_offset((int)(n_pad / tf32::TN)) * (2 * tf32::B_HALF) * 4;
+}
+extern "C" int64_t gpmdm_tf32_atiles_bytes(int64_t n_pad) { return (n_pad / tf32::KC) * (2 * tf32::B_HALF) * 4; }
+
+extern "C" int gpmdm_pack_whitened_tf32(const double* W, int64_t n, int64_t n_pad, float* wtiles, void* stream) {
+    GPMDM_REQUIRE(W && wtiles, GPMDM_E_INVALID, "null argument");
+    GPMDM_REQUIRE(n > 0 && n_pad >= n && n_pad % GPMDM_TILE_N == 0, GPMDM_E_INVALID, "bad sizes");
+    const long long total = tf32::wtile_offset((int)(n_pad / tf32::TN)) * tf32::B_HALF;
+    tf32::pack_whitened_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(W, n, (int)n_pad, wtiles);
+    return check_launch("pack_whitened_kernel");
+}
+
+extern "C" int gpmdm_pack_alpha_tf32(const double* alpha, int64_t n, int64_t n_pad, int32_t dout, float* atiles,
+                                     void* stream) {
+    GPMDM_REQUIRE(alpha && atiles, GPMDM_E_INVALID, "null argument");
+    GPMDM_REQUIRE(n > 0 && n_pad >= n && n_pad % GPMDM_TILE_N == 0 && dout >= 1 && dout <= tf32::TN, GPMDM_E_INVALID,
+                  "bad sizes (dout must be <= %d)", tf32::TN);
+    const long long total = (n_pad / tf32::KC) * tf32::B_HALF;
+    tf32::pack_alpha_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(alpha, n, (int)n_pad, dout,
+                                                                                              atiles);
+    return check_launch("pack_alpha_kernel");
+}
+
+extern "C" int gpmdm_pf_observe_tf32(const gpmdm_gp_model_tf32* m, const double* x, int64_t P, const double* z,
+                                     double ll_const, double* ll, double* mu_out, double* v_out, void* stream) {
+    GPMDM_REQUIRE(m && m->coords && m->wtiles && m->atiles && m->lengthscales && m->lambdas, GPMDM_E_INVALID,
+                  "null model field");
+    GPMDM_REQUIRE(m->d >= 1 && m->d <= GPMDM_MAX_LATENT, GPMDM_E_UNSUPPORTED, "latent dimension %d outside [1, %d]", m->d,
+                  GPMDM_MAX_LATENT);
+    GPMDM_REQUIRE(m->dout >= 1 && m->dout <= tf32::TN, GPMDM_E_UNSUPPORTED, "dout %d outside [1, %d]", m->dout, tf32::TN);
+    GPMDM_REQUIRE(m->n_pad > 0 && m->n_pad % GPMDM_TILE_N == 0, GPMDM_E_INVALID, "n_pad must be a multiple of %d",
+                  GPMDM_TILE_N);
+    GPMDM_REQUIRE(P >= 0 && P < (1ll << 31), GPMDM_E_INVALID, "P out of range");
+    if (P == 0) return 0;
+    GPMDM_REQUIRE(x, GPMDM_E_INVALID, "null argument");
+    GPMDM_REQUIRE(ll == nullptr || z != nullptr, GPMDM_E_INVALID, "ll requested without z");
+    tf32::Params prm{};
+    prm.coords = m->coords;
+    prm.wtiles = m->wtiles;
+    prm.atiles = m->atiles;
+    prm.n_pad = (int)m->n_pad;
+    prm.d = m->d;
+    prm.dout = m->dout;
+    prm.ls = m->lengthscales;
+    prm.lam2 = m->lambdas;
+    prm.x = x;
+    prm.P = P;
+    prm.z = z;
+    prm.ll_const = ll_const;
+    prm.ll = ll;
+    prm.mu_out = mu_out;
+    prm.v_out = v_out;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const long long tiles = (P + tf32::TM - 1) / tf32::TM;
+    const int grid = (int)(tiles < sms ? tiles : sms);
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (m->d) {
+        case 1: return tf32::launch<1>(prm, grid, st);
+        case 2: return tf32::launch<2>(prm, grid, st);
+        case 3: return tf32::launch<3>(prm, grid, st);
+        case 4: return tf32::launch<4>(prm, grid, st);
+        case 5: return tf32::launch<5>(prm, grid, st);
+        case 6: return tf32::launch<6>(prm, grid, st);
+        case 7: return tf32::launch<7>(prm, grid, st);
+        case 8: return tf32::launch<8>(prm, grid, st);
+    }
+    return GPMDM_E_UNSUPPORTED;
+}

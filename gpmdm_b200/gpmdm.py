@@ -29,7 +29,7 @@ import numpy as np
 import torch
 
 from . import _cabi
-from ._cabi import TILE_N, TILE_P, GpModel, check, ptr, stream
+from ._cabi import TILE_N, TILE_P, GpModel, GpModelTf32, check, ptr, stream
 
 
 def to_tensor(input_array, dtype, device):
@@ -406,6 +406,7 @@ class GPMDM(torch.nn.Module):
         self._Kx_inv_full = None
         self._factors_version += 1
         self._packed = None
+        self._packed_tf32 = None
 
     @property
     def Kx_inv(self):
@@ -423,6 +424,7 @@ class GPMDM(torch.nn.Module):
             self.Kx_inv_class = [to_tensor(b, self.dtype, self.device).contiguous() for b in Kx_inv_blocks]
         self._factors_version += 1
         self._packed = None
+        self._packed_tf32 = None
 
     # ---- packing for the fused predict kernels ---------------------------------------------------------------
     def _pack_block(self, Xtrain, log_ls, Kinv, targets, alpha_ld, lin_c2, tri):
@@ -482,6 +484,35 @@ class GPMDM(torch.nn.Module):
                             ll_const_terms=(2.0 * torch.sum(self.y_log_lambdas.detach())).item())
         return self._packed
 
+    @torch.no_grad()
+    def packed_model_tf32(self):
+        """Operands of the tf32 observation kernel (include/gpmdm_b200.h: gpmdm_gp_model_tf32): the whitening factor
+        W = U^-T of K_y = U^T U and alpha_y, split into tf32 hi/lo tiles in tensor-core operand order."""
+        if getattr(self, "_packed_tf32", None) is not None and self._packed_tf32["version"] == self._factors_version:
+            return self._packed_tf32
+        lib = _cabi.lib()
+        X = self.X.detach()
+        n, d = X.shape
+        n_pad = _round_up(n, TILE_N)
+        U, _info = torch.linalg.cholesky_ex(self.get_y_kernel(X, X), upper=True)
+        eye = torch.eye(n, dtype=self.dtype, device=self.device)
+        W = torch.linalg.solve_triangular(U, eye, upper=True).t().contiguous()  # U^-T, lower triangular
+        del U, eye
+        alpha = torch.matmul(self.Ky_inv.t(), self._Y_device()).contiguous()
+        wt = torch.empty(int(lib.gpmdm_tf32_wtiles_bytes(n_pad)) // 4, dtype=torch.float32, device=self.device)
+        at = torch.empty(int(lib.gpmdm_tf32_atiles_bytes(n_pad)) // 4, dtype=torch.float32, device=self.device)
+        check(lib.gpmdm_pack_whitened_tf32(ptr(W), n, n_pad, ptr(wt), stream()), "gpmdm_pack_whitened_tf32")
+        check(lib.gpmdm_pack_alpha_tf32(ptr(alpha), n, n_pad, self.D, ptr(at), stream()), "gpmdm_pack_alpha_tf32")
+        coords = torch.zeros(n_pad, 8, dtype=torch.float32, device=self.device)
+        coords[:n, :d] = (X / torch.exp(self.y_log_lengthscales.detach())).to(torch.float32)
+        ls = torch.exp(self.y_log_lengthscales.detach()).contiguous()
+        lam2 = (torch.exp(self.y_log_lambdas.detach()) ** 2).contiguous()
+        model = GpModelTf32(coords=coords.data_ptr(), wtiles=wt.data_ptr(), atiles=at.data_ptr(), n=n, n_pad=n_pad, d=d,
+                            dout=self.D, lengthscales=ls.data_ptr(), lambdas=lam2.data_ptr())
+        self._packed_tf32 = dict(version=self._factors_version, model=model, keep=(coords, wt, at, ls, lam2),
+                                 ll_const_terms=(2.0 * torch.sum(self.y_log_lambdas.detach())).item())
+        return self._packed_tf32
+
     # ---- prediction (gpmdm.py:923-963, 1032-1068) ----------------------------------------------------------
     def _scratch_counter(self):
         if getattr(self, "_counter", None) is None:
@@ -489,15 +520,23 @@ class GPMDM(torch.nn.Module):
         return self._counter
 
     @torch.no_grad()
-    def map_x_to_y(self, Xstar, flg_noise=False):
+    def map_x_to_y(self, Xstar, flg_noise=False, precision="fp64"):
+        """precision: 'fp64' (exact path, DMMA) or 'tf32' (tcgen05 variant, ~1e-4 relative; an addition)."""
         lib = _cabi.lib()
-        pk = self.packed_models()
         Xs = to_tensor(Xstar, self.dtype, self.device).contiguous()
         P = Xs.shape[0]
         mu = torch.empty(P, self.D, dtype=self.dtype, device=self.device)
         v = torch.empty(P, dtype=self.dtype, device=self.device)
-        check(lib.gpmdm_pf_observe_f64(ctypes.byref(pk["obs"]), ptr(Xs), P, None, 0.0, None, ptr(mu), ptr(v),
-                                       ptr(self._scratch_counter()), stream()), "gpmdm_pf_observe_f64")
+        if precision == "tf32":
+            pk = self.packed_model_tf32()
+            check(lib.gpmdm_pf_observe_tf32(ctypes.byref(pk["model"]), ptr(Xs), P, None, 0.0, None, ptr(mu), ptr(v),
+                                            stream()), "gpmdm_pf_observe_tf32")
+        elif precision == "fp64":
+            pk = self.packed_models()
+            check(lib.gpmdm_pf_observe_f64(ctypes.byref(pk["obs"]), ptr(Xs), P, None, 0.0, None, ptr(mu), ptr(v),
+                                           ptr(self._scratch_counter()), stream()), "gpmdm_pf_observe_f64")
+        else:
+            raise ValueError("precision must be 'fp64' or 'tf32'")
         if flg_noise:
             v = v + torch.exp(self.y_log_sigma_n) ** 2 + self.sigma_n_num_Y ** 2
         var = v.unsqueeze(1) * (torch.exp(self.y_log_lambdas) ** -2).unsqueeze(0)

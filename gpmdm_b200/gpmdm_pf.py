@@ -47,7 +47,7 @@ class GPMDM_PF:
 
     def __init__(self, gpmdm: GPMDM, markov_switching_model, num_particles: int, *,
                  seed: int = 0, resampling: str = "multinomial", cdf_order: str = "sequential",
-                 tri: bool = True, init_indices: Optional[Sequence] = None, process_group=None,
+                 tri: bool = True, precision: str = "fp64", init_indices: Optional[Sequence] = None, process_group=None,
                  distributed: Optional[bool] = None):
         """
         gpmdm, markov_switching_model [C, C], num_particles: as the reference (:47-50).
@@ -56,6 +56,8 @@ class GPMDM_PF:
         cdf_order       'sequential' = the reference's running sum, bit-identical cdf; 'blocked' = parallel
                         scan in fixed 1024-element blocks
         tri             use the triangular packing of K^-1 (half the flops of the dense quadratic form)
+        precision       'fp64' (exact path) or 'tf32': observation GP on tcgen05 tensor cores with error-compensated
+                        tf32 products and the whitened variance (~1e-4 relative); dynamics / resampling stay fp64
         init_indices    optional per-class index tensors replacing torch.randint in _init_particles (:113)
         """
         self._lib = _cabi.lib()
@@ -75,6 +77,9 @@ class GPMDM_PF:
         self._systematic = resampling == "systematic"
         self._cdf_mode = 0 if cdf_order == "sequential" else 1
         self._tri = bool(tri)
+        if precision not in ("fp64", "tf32"):
+            raise ValueError("precision must be 'fp64' or 'tf32'")
+        self._precision = precision
 
         # one process per GPU; contiguous particle ranges (gpmdm_b200/sharding.py)
         self._pg = process_group
@@ -82,6 +87,7 @@ class GPMDM_PF:
         self._lo, self._hi = sharding.particle_range(self._num_particles, self._world, self._rank)
 
         self._packed = gpmdm.packed_models(self._tri)
+        self._packed_tf32 = gpmdm.packed_model_tf32() if precision == "tf32" else None
         c32 = float(0.5 * self._gpmdm.D * _LOG_2PI)  # fp32 product, as gpmdm_pf.py:191
         self._ll_const = self._packed["ll_const_terms"] - c32
         self._alloc()
@@ -172,8 +178,12 @@ class GPMDM_PF:
         if prof is not None:  # bench.py: CUDA events around the dominant kernel, on the launching stream
             ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
             ev[0].record()
-        check(lib.gpmdm_pf_observe_f64(ctypes.byref(self._packed["obs"]), ptr(x_new_l), Pl, ptr(z), self._ll_const,
-                                       ptr(ll_l), None, None, ptr(self._counter), st), "gpmdm_pf_observe_f64")
+        if self._precision == "tf32":
+            check(lib.gpmdm_pf_observe_tf32(ctypes.byref(self._packed_tf32["model"]), ptr(x_new_l), Pl, ptr(z),
+                                            self._ll_const, ptr(ll_l), None, None, st), "gpmdm_pf_observe_tf32")
+        else:
+            check(lib.gpmdm_pf_observe_f64(ctypes.byref(self._packed["obs"]), ptr(x_new_l), Pl, ptr(z), self._ll_const,
+                                           ptr(ll_l), None, None, ptr(self._counter), st), "gpmdm_pf_observe_f64")
         if prof is not None:
             ev[1].record()
             prof.append(ev)

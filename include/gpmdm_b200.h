@@ -156,6 +156,36 @@ int gpmdm_pf_draws_philox(uint64_t seed, uint64_t step, int64_t first, int64_t n
 
 int64_t gpmdm_workspace_bytes(int64_t P, int32_t C);
 
+/* ---- tf32 variant of the observation GP (BASELINE config 4; ~1e-4 relative accuracy) ---------------------------
+ * tcgen05 tensor cores with TMEM accumulators, error-compensated tf32 products (3 MMAs per k-step), and the
+ * WHITENED variance  v = 1 - |W k|^2,  W = U^-T  with K = U^T U the reference's upper Cholesky factor
+ * (gpmdm.py:1287-1288): the explicit-inverse form of gpmdm.py:958-959 is not usable below fp64.
+ * The dynamics GP, the draws and the resampling stay on the fp64 path.
+ *   coords [n_pad, 8]  fp32  a_i = x_i / lengthscale, zero padded
+ *   wtiles             tf32 hi/lo tiles of W in tensor-core operand order (gpmdm_pack_whitened_tf32)
+ *   atiles             tf32 hi/lo tiles of alpha = K^-T Y                 (gpmdm_pack_alpha_tf32)            */
+typedef struct gpmdm_gp_model_tf32 {
+    const float* coords;
+    const float* wtiles;
+    const float* atiles;
+    int64_t n;
+    int64_t n_pad;              /* multiple of GPMDM_TILE_N                                        */
+    int32_t d;
+    int32_t dout;               /* <= 256                                                          */
+    const double* lengthscales; /* device [d]                                                      */
+    const double* lambdas;      /* device [dout] exp(y_log_lambdas)^2                              */
+} gpmdm_gp_model_tf32;
+
+int64_t gpmdm_tf32_wtiles_bytes(int64_t n_pad);
+int64_t gpmdm_tf32_atiles_bytes(int64_t n_pad);
+/* W [n, n] fp64 row-major, lower triangular (W = U^-T). */
+int gpmdm_pack_whitened_tf32(const double* W, int64_t n, int64_t n_pad, float* wtiles, void* stream);
+/* alpha [n, dout] fp64 row-major. */
+int gpmdm_pack_alpha_tf32(const double* alpha, int64_t n, int64_t n_pad, int32_t dout, float* atiles, void* stream);
+/* Same contract as gpmdm_pf_observe_f64 (x, z, ll, mu_out, v_out are fp64 arrays). */
+int gpmdm_pf_observe_tf32(const gpmdm_gp_model_tf32* obs, const double* x, int64_t P, const double* z, double ll_const,
+                          double* ll, double* mu_out, double* v_out, void* stream);
+
 /* ---- training-side kernel matrices (gpmdm.py:381-548, 311-340, 550-628) ------------------------
  * K = exp(-|(x_i-x_j)/l|^2) [+ [x_i,1]diag(c^2)[x_j,1]^T if kind 1] [+ noise2 on the diagonal],
  * multiplied by the class-block mask given as row offsets (class_offsets [n_classes+1], device int64;
