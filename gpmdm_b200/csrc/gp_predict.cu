@@ -74,6 +74,7 @@ struct PredictParams {
     double* mean_out;
     double* var_out;
     // observation epilogue
+    const double* v_in;  // mean-only mode: variances supplied (tf32 variant), skip the quadratic form
     const double* z;
     double ll_const;  // 2 sum_j log lambda_j - c32
     double* ll;
@@ -157,8 +158,8 @@ __device__ __forceinline__ void kstar_pair(const double (&rec0)[REC_MAX], const 
 struct ChunkCursor {
     int ct, k, nq, nct, nkc, tri;
     __device__ __forceinline__ int kbeg(int t) const { return (tri && t < nq) ? t * (TN / KC) : 0; }
-    __device__ __forceinline__ void init(int nq_, int nct_, int nkc_, int tri_) {
-        nq = nq_, nct = nct_, nkc = nkc_, tri = tri_, ct = 0, k = 0;
+    __device__ __forceinline__ void init(int nq_, int nct_, int nkc_, int tri_, int ct0) {
+        nq = nq_, nct = nct_, nkc = nkc_, tri = tri_, ct = ct0, k = kbeg(ct0);
     }
     __device__ __forceinline__ bool done() const { return ct >= nct; }
     __device__ __forceinline__ void next() {
@@ -214,6 +215,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gp_predict_kernel(const PredictPa
         const int nkc = n_pad / KC;
         const int nq = n_pad / TN;               // column tiles of L
         const int nct = nq + prm.alpha_ld / TN;  // + column tiles of alpha
+        const int ct0 = (KIND == 0 && prm.v_in) ? nq : 0;  // mean-only mode starts at the alpha tiles
 
         // ---- this lane's particle row --------------------------------------------------------------------
         ParticleRec<KIND, DL> pr;
@@ -238,7 +240,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gp_predict_kernel(const PredictPa
 
         // ---- TMA issue: all warps advance the same cursor, the duty warp issues ------------------------------
         ChunkCursor bcur;
-        bcur.init(nq, nct, nkc, prm.tri);
+        bcur.init(nq, nct, nkc, prm.tri, ct0);
         uint32_t gb = g;  // ring position of the next chunk to issue
         auto issue_b = [&]() {
             const int st = (int)(gb % STAGES);
@@ -277,56 +279,69 @@ __global__ void __launch_bounds__(NTHREADS, 1) gp_predict_kernel(const PredictPa
         }
 
         ChunkCursor cur;
-        cur.init(nq, nct, nkc, prm.tri);
+        cur.init(nq, nct, nkc, prm.tri, ct0);
         double qacc = 0.0, sacc = 0.0, vrow = 0.0;
+        if (KIND == 0 && prm.v_in) vrow = pidx >= 0 ? prm.v_in[pidx] : 1.0;
         // The two warps of an SM sub-partition (w, w + 4) share one fp64 datapath.  Started together they run in
         // lockstep and stall it together at every chunk boundary / exponential block; a one-off skew of about
         // half a chunk lets each warp's non-MMA phases hide under the other's DMMAs (ncu: idle 13% -> see profiles/).
         if (warp >= NWARPS / 2) __nanosleep(SKEW_NS);
 
-        for (int ct = 0; ct < nct; ct++) {
+        for (int ct = ct0; ct < nct; ct++) {
             double acc[NJ][2];
 #pragma unroll
             for (int j = 0; j < NJ; j++) acc[j][0] = acc[j][1] = 0.0;
 
             const int kbeg = cur.kbeg(ct);
-            for (int k = kbeg; k < nkc; k++, g++) {
-                const int st = (int)(g % STAGES);
-                // keep the ring AHEAD chunks full; the duty rotates so that no warp is always the one waiting
-                if (!bcur.done()) {
-                    if (warp == (int)(g % NWARPS)) issue_b();
-                    bcur.next();
-                    gb++;
-                }
-                // The next chunk provides the records for the next A fragments.  After the last chunk of the
-                // particle tile the fragments are recomputed from the current stage (values unused).
-                const bool has_next = !(ct == nct - 1 && k == nkc - 1);
-                const int stn = has_next ? (int)((g + 1) % STAGES) : st;
-                if (has_next) mbar_wait(&s.full[stn], ((g + 1) / STAGES) & 1);
-                double an[KC / 4];
-#pragma unroll
-                for (int k4 = 0; k4 < KC / 4; k4++) {
-                    if ((k4 & 1) == 0) {  // two of the next chunk's A fragments, woven into this block's MMAs
-                        double rec0[REC_MAX], rec1[REC_MAX];
-                        load_record<KIND, DL>(&s.R[stn][(k4 * 4 + c) * REC], rec0);
-                        load_record<KIND, DL>(&s.R[stn][(k4 * 4 + 4 + c) * REC], rec1);
-                        kstar_pair<KIND, DL>(rec0, rec1, pr, c2last, exptab, an[k4], an[k4 + 1]);
-                    }
-                    const double ak = a[k4];
-#pragma unroll
-                    for (int jg = 0; jg < NJ; jg += 8) {
-                        double b[8];
-#pragma unroll
-                        for (int j = 0; j < 8; j++) b[j] = s.B[st][k4 * 4 + c][(jg + j) * 8 + r];
-#pragma unroll
-                        for (int j = 0; j < 8; j++) dmma_m8n8k4(acc[jg + j][0], acc[jg + j][1], ak, b[j]);
-                    }
-                }
-#pragma unroll
-                for (int k4 = 0; k4 < KC / 4; k4++) a[k4] = an[k4];
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&s.empty[st]);  // this warp is done with the ring slot
+            // The k loop of one column tile.  GROUP_ON(jg) says whether the 8 column blocks starting at jg are
+            // needed: always for tiles of L; for alpha tiles only the blocks that hold real output columns.
+#define GPMDM_K_LOOP(GROUP_ON)                                                                                  \
+    for (int k = kbeg; k < nkc; k++, g++) {                                                                      \
+        const int st = (int)(g % STAGES);                                                                        \
+        /* keep the ring AHEAD chunks full; the duty rotates so that no warp is always the one waiting */        \
+        if (!bcur.done()) {                                                                                      \
+            if (warp == (int)(g % NWARPS)) issue_b();                                                            \
+            bcur.next();                                                                                         \
+            gb++;                                                                                                \
+        }                                                                                                        \
+        /* The next chunk provides the records for the next A fragments.  After the last chunk of the          \
+           particle tile the fragments are recomputed from the current stage (values unused). */                 \
+        const bool has_next = !(ct == nct - 1 && k == nkc - 1);                                                  \
+        const int stn = has_next ? (int)((g + 1) % STAGES) : st;                                                 \
+        if (has_next) mbar_wait(&s.full[stn], ((g + 1) / STAGES) & 1);                                           \
+        double an[KC / 4];                                                                                       \
+        _Pragma("unroll") for (int k4 = 0; k4 < KC / 4; k4++) {                                                  \
+            if ((k4 & 1) == 0) { /* two of the next chunk's A fragments, woven into this block's MMAs */         \
+                double rec0[REC_MAX], rec1[REC_MAX];                                                             \
+                load_record<KIND, DL>(&s.R[stn][(k4 * 4 + c) * REC], rec0);                                      \
+                load_record<KIND, DL>(&s.R[stn][(k4 * 4 + 4 + c) * REC], rec1);                                  \
+                kstar_pair<KIND, DL>(rec0, rec1, pr, c2last, exptab, an[k4], an[k4 + 1]);                        \
+            }                                                                                                    \
+            const double ak = a[k4];                                                                             \
+            _Pragma("unroll") for (int jg = 0; jg < NJ; jg += 8) {                                               \
+                if (GROUP_ON(jg)) {                                                                              \
+                    double b[8];                                                                                 \
+                    _Pragma("unroll") for (int j = 0; j < 8; j++) b[j] = s.B[st][k4 * 4 + c][(jg + j) * 8 + r];  \
+                    _Pragma("unroll") for (int j = 0; j < 8; j++)                                                \
+                        dmma_m8n8k4(acc[jg + j][0], acc[jg + j][1], ak, b[j]);                                   \
+                }                                                                                                \
+            }                                                                                                    \
+        }                                                                                                        \
+        _Pragma("unroll") for (int k4 = 0; k4 < KC / 4; k4++) a[k4] = an[k4];                                    \
+        __syncwarp();                                                                                            \
+        if (lane == 0) mbar_arrive(&s.empty[st]); /* this warp is done with the ring slot */                     \
+    }
+#define GPMDM_ALL_GROUPS(jg) true
+#define GPMDM_SOME_GROUPS(jg) ((jg) < jlim)
+            const int jlim = ct < nq ? NJ : (min(TN, prm.dout - (ct - nq) * TN) + 7) / 8;  // 8-column blocks in use
+            if (jlim > NJ - 8) {
+                GPMDM_K_LOOP(GPMDM_ALL_GROUPS)
+            } else {
+                GPMDM_K_LOOP(GPMDM_SOME_GROUPS)
             }
+#undef GPMDM_K_LOOP
+#undef GPMDM_ALL_GROUPS
+#undef GPMDM_SOME_GROUPS
 
             // ---- epilogues (per warp; a row's columns live in the 4 lanes of a quad) -------------------------
             if (ct < nq) {
@@ -490,9 +505,26 @@ extern "C" int gpmdm_pf_propagate_f64(const gpmdm_gp_model* dyn, const double* x
     return dispatch_d<1>(prm, grid, st);
 }
 
+static int observe_impl(const gpmdm_gp_model* obs, const double* x, int64_t P, const double* z, double ll_const,
+                        const double* v_in, double* ll, double* mu_out, double* v_out, int32_t* tile_counter,
+                        void* stream);
+
 extern "C" int gpmdm_pf_observe_f64(const gpmdm_gp_model* obs, const double* x, int64_t P, const double* z,
                                     double ll_const, double* ll, double* mu_out, double* v_out, int32_t* tile_counter,
                                     void* stream) {
+    return observe_impl(obs, x, P, z, ll_const, nullptr, ll, mu_out, v_out, tile_counter, stream);
+}
+
+extern "C" int gpmdm_pf_loglik_f64(const gpmdm_gp_model* obs, const double* x, int64_t P, const double* z,
+                                   double ll_const, const double* v_in, double* ll, double* mu_out,
+                                   int32_t* tile_counter, void* stream) {
+    GPMDM_REQUIRE(v_in != nullptr, GPMDM_E_INVALID, "v_in is required");
+    return observe_impl(obs, x, P, z, ll_const, v_in, ll, mu_out, nullptr, tile_counter, stream);
+}
+
+static int observe_impl(const gpmdm_gp_model* obs, const double* x, int64_t P, const double* z, double ll_const,
+                        const double* v_in, double* ll, double* mu_out, double* v_out, int32_t* tile_counter,
+                        void* stream) {
     if (int rc = validate_model(obs, 0)) return rc;
     GPMDM_REQUIRE(P >= 0 && P < (1ll << 31), GPMDM_E_INVALID, "P = %lld out of range", (long long)P);
     if (P == 0) return 0;
@@ -506,6 +538,7 @@ extern "C" int gpmdm_pf_observe_f64(const gpmdm_gp_model* obs, const double* x, 
     prm.P = P;
     prm.counter = tile_counter;
     prm.z = z;
+    prm.v_in = v_in;
     prm.ll_const = ll_const;
     prm.ll = ll;
     prm.mu_out = mu_out;

@@ -131,7 +131,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) observe_tf32_kernel(const Params 
     Smem& s = *reinterpret_cast<Smem*>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nq = prm.n_pad / TN, nkc = prm.n_pad / KC;
-    const int nct = nq + 1;  // + one alpha tile (dout <= 256)
+    const int nct = nq + ((prm.ll || prm.mu_out) ? 1 : 0);  // + one alpha tile (dout <= 256) when a mean is wanted
     const int n_tiles = (int)((prm.P + TM - 1) / TM);
 
     if (tid == 0) {

@@ -427,7 +427,7 @@ class GPMDM(torch.nn.Module):
         self._packed_tf32 = None
 
     # ---- packing for the fused predict kernels ---------------------------------------------------------------
-    def _pack_block(self, Xtrain, log_ls, Kinv, targets, alpha_ld, lin_c2, tri):
+    def _pack_block(self, Xtrain, log_ls, Kinv, targets, alpha_ld, lin_c2, tri, with_L=True):
         lib = _cabi.lib()
         n, d = Xtrain.shape
         n_pad = _round_up(n, TILE_N)
@@ -438,24 +438,30 @@ class GPMDM(torch.nn.Module):
         width = (rec.shape[1] + 1) & ~1  # records are padded to an even number of doubles (16-byte loads)
         coords = torch.zeros(n_pad, width, dtype=self.dtype, device=self.device)
         coords[:n, :rec.shape[1]] = rec
-        L = torch.empty(n_pad, n_pad, dtype=self.dtype, device=self.device)
         Kinv = Kinv.contiguous()
-        check(lib.gpmdm_pack_quadform_f64(ptr(Kinv), n, n_pad, int(tri), ptr(L), stream()), "gpmdm_pack_quadform_f64")
+        L = None
+        if with_L:
+            L = torch.empty(n_pad, n_pad, dtype=self.dtype, device=self.device)
+            check(lib.gpmdm_pack_quadform_f64(ptr(Kinv), n, n_pad, int(tri), ptr(L), stream()), "gpmdm_pack_quadform_f64")
         alpha = torch.zeros(n_pad, alpha_ld, dtype=self.dtype, device=self.device)
         alpha[:n, :targets.shape[1]] = torch.matmul(Kinv.t(), targets)
         return dict(coords=coords, L=L, alpha=alpha, n=n, n_pad=n_pad)
 
     @torch.no_grad()
-    def packed_models(self, tri: bool = True):
-        """Device-resident operands of the fused kernels (include/gpmdm_b200.h: gpmdm_gp_model)."""
-        if getattr(self, "_packed", None) is not None and self._packed["tri"] == tri:
+    def packed_models(self, tri: bool = True, with_obs_L: bool = True):
+        """Device-resident operands of the fused kernels (include/gpmdm_b200.h: gpmdm_gp_model).
+        with_obs_L=False leaves out the fp64 quadratic-form matrix of the observation block (8 N^2 bytes): enough for
+        gpmdm_pf_loglik_f64 when the tf32 variant supplies the variances."""
+        if getattr(self, "_packed", None) is not None and self._packed["tri"] == tri \
+                and (self._packed["obs_has_L"] or not with_obs_L):
             return self._packed
         X = self.X.detach()
         dev = self.device
         keep = []  # tensors that must outlive the C structs
 
         def model(blocks, d, dout, alpha_ld, kind, ls, c2, lam):
-            table = torch.tensor([[b["coords"].data_ptr(), b["L"].data_ptr(), b["alpha"].data_ptr(), b["n"], b["n_pad"]]
+            table = torch.tensor([[b["coords"].data_ptr(), b["L"].data_ptr() if b["L"] is not None else 0,
+                                   b["alpha"].data_ptr(), b["n"], b["n_pad"]]
                                   for b in blocks], dtype=torch.int64, device=dev)
             keep.extend([table, ls, c2, lam, blocks])
             return GpModel(blocks=table.data_ptr(), n_blocks=len(blocks), d=d, dout=dout, alpha_ld=alpha_ld, kind=kind,
@@ -464,7 +470,8 @@ class GPMDM(torch.nn.Module):
 
         # observation GP: one block over all frames
         ald_y = _round_up(self.D, TILE_N)
-        oblk = self._pack_block(X, self.y_log_lengthscales.detach(), self.Ky_inv, self._Y_device(), ald_y, None, tri)
+        oblk = self._pack_block(X, self.y_log_lengthscales.detach(), self.Ky_inv, self._Y_device(), ald_y, None, tri,
+                                with_L=with_obs_L)
         ls_y = torch.exp(self.y_log_lengthscales.detach()).contiguous()
         lam2_y = (torch.exp(self.y_log_lambdas.detach()) ** 2).contiguous()
         obs = model([oblk], self.d, self.D, ald_y, 0, ls_y, None, lam2_y)
@@ -480,7 +487,7 @@ class GPMDM(torch.nn.Module):
             dyn = model(dblks, self.d, self.d, TILE_N, 1, ls_x, c2, lam_x)
         else:
             dyn = None
-        self._packed = dict(tri=tri, obs=obs, dyn=dyn, keep=keep,
+        self._packed = dict(tri=tri, obs=obs, obs_has_L=with_obs_L, dyn=dyn, keep=keep,
                             ll_const_terms=(2.0 * torch.sum(self.y_log_lambdas.detach())).item())
         return self._packed
 
@@ -527,9 +534,15 @@ class GPMDM(torch.nn.Module):
         P = Xs.shape[0]
         mu = torch.empty(P, self.D, dtype=self.dtype, device=self.device)
         v = torch.empty(P, dtype=self.dtype, device=self.device)
-        if precision == "tf32":
-            pk = self.packed_model_tf32()
-            check(lib.gpmdm_pf_observe_tf32(ctypes.byref(pk["model"]), ptr(Xs), P, None, 0.0, None, ptr(mu), ptr(v),
+        if precision == "tf32":  # variances on tcgen05 (tf32 x3, whitened); means stay fp64 (DMMA, alpha tile only)
+            pk32, pk = self.packed_model_tf32(), self.packed_models(with_obs_L=False)
+            check(lib.gpmdm_pf_observe_tf32(ctypes.byref(pk32["model"]), ptr(Xs), P, None, 0.0, None, None, ptr(v),
+                                            stream()), "gpmdm_pf_observe_tf32")
+            check(lib.gpmdm_pf_loglik_f64(ctypes.byref(pk["obs"]), ptr(Xs), P, None, 0.0, ptr(v), None, ptr(mu),
+                                          ptr(self._scratch_counter()), stream()), "gpmdm_pf_loglik_f64")
+        elif precision == "tf32-pure":  # mean on the tensor cores as well (error ~1e-4..1e-3 of the row scale)
+            pk32 = self.packed_model_tf32()
+            check(lib.gpmdm_pf_observe_tf32(ctypes.byref(pk32["model"]), ptr(Xs), P, None, 0.0, None, ptr(mu), ptr(v),
                                             stream()), "gpmdm_pf_observe_tf32")
         elif precision == "fp64":
             pk = self.packed_models()

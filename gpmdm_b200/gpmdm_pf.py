@@ -86,7 +86,7 @@ class GPMDM_PF:
         self._world, self._rank = sharding.world(process_group, distributed)
         self._lo, self._hi = sharding.particle_range(self._num_particles, self._world, self._rank)
 
-        self._packed = gpmdm.packed_models(self._tri)
+        self._packed = gpmdm.packed_models(self._tri, with_obs_L=(precision == "fp64"))
         self._packed_tf32 = gpmdm.packed_model_tf32() if precision == "tf32" else None
         c32 = float(0.5 * self._gpmdm.D * _LOG_2PI)  # fp32 product, as gpmdm_pf.py:191
         self._ll_const = self._packed["ll_const_terms"] - c32
@@ -105,6 +105,7 @@ class GPMDM_PF:
         self._n_tiles, self._counter = e(1, dt=torch.int32), torch.zeros(1, dtype=torch.int32, device=dev)
         self._E, self._eps, self._u = e(Pl, C), e(Pl, d), e(P)
         self._stats = e(2)
+        self._v_buf = e(Pl)
         self._summary = e(C + d + 1)
         self._summary_step = -1
         ws = int(self._lib.gpmdm_workspace_bytes(P, C))
@@ -179,8 +180,12 @@ class GPMDM_PF:
             ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
             ev[0].record()
         if self._precision == "tf32":
-            check(lib.gpmdm_pf_observe_tf32(ctypes.byref(self._packed_tf32["model"]), ptr(x_new_l), Pl, ptr(z),
-                                            self._ll_const, ptr(ll_l), None, None, st), "gpmdm_pf_observe_tf32")
+            # variances: tcgen05 (3 x tf32, whitened form); means + log-likelihood: fp64 on the alpha tile only
+            check(lib.gpmdm_pf_observe_tf32(ctypes.byref(self._packed_tf32["model"]), ptr(x_new_l), Pl, None, 0.0, None,
+                                            None, ptr(self._v_buf), st), "gpmdm_pf_observe_tf32")
+            check(lib.gpmdm_pf_loglik_f64(ctypes.byref(self._packed["obs"]), ptr(x_new_l), Pl, ptr(z), self._ll_const,
+                                          ptr(self._v_buf), ptr(ll_l), None, ptr(self._counter), st),
+                  "gpmdm_pf_loglik_f64")
         else:
             check(lib.gpmdm_pf_observe_f64(ctypes.byref(self._packed["obs"]), ptr(x_new_l), Pl, ptr(z), self._ll_const,
                                            ptr(ll_l), None, None, ptr(self._counter), st), "gpmdm_pf_observe_f64")
@@ -208,7 +213,8 @@ class GPMDM_PF:
     @property
     def launches_per_step(self) -> int:
         """Kernels of libgpmdm_sm100a.so launched by one update() + one query (device-draw mode)."""
-        draws, transition, bucket, propagate, observe, normalize, resample, summaries = 2, 1, 3, 1, 1, 5, 1, 4
+        draws, transition, bucket, propagate, normalize, resample, summaries = 2, 1, 3, 1, 5, 1, 4
+        observe = 2 if self._precision == "tf32" else 1
         cdf = 2 if self._cdf_mode == 0 else 3
         return draws + transition + bucket + propagate + observe + normalize + cdf + resample + summaries
 

@@ -121,6 +121,12 @@ int gpmdm_pf_propagate_f64(const gpmdm_gp_model* dyn, const double* x_prev, cons
 int gpmdm_pf_observe_f64(const gpmdm_gp_model* obs, const double* x, int64_t P, const double* z, double ll_const,
                          double* ll, double* mu_out, double* v_out, int32_t* tile_counter, void* stream);
 
+/* Mean and log-likelihood only, with the predictive variances v_in [P] supplied by the caller (the tf32 variant
+ * computes them on tcgen05 tensor cores): the N x D mean contraction stays in fp64 because alpha = K^-1 Y cancels
+ * heavily; it is 2ND of the 2N^2 + 2ND flops.  The blocks of `obs` may have L == NULL for this call. */
+int gpmdm_pf_loglik_f64(const gpmdm_gp_model* obs, const double* x, int64_t P, const double* z, double ll_const,
+                        const double* v_in, double* ll, double* mu_out, int32_t* tile_counter, void* stream);
+
 /* GPMDM_PF._update_weights (second half, gpmdm_pf.py:200-204): lw = ll - max(ll); w = exp(lw)/sum.
  * Reductions run in a fixed blocked order independent of the GPU count.  stats_out [2] = {max, sum}. */
 int gpmdm_pf_normalize_f64(const double* ll, int64_t P, double* lw, double* w, double* stats_out,

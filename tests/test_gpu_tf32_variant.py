@@ -32,14 +32,18 @@ def test_tf32_observation_gp_matches_fp64(setup, P):
     xs = particles(spec, P, 3, 0.3).cuda()
     mu64, var64 = model.map_x_to_y(xs)
     mu32, var32 = model.map_x_to_y(xs, precision="tf32")
-    scale = torch.clamp(mu64.abs().max(dim=1, keepdim=True).values, min=1e-2)
-    assert float(torch.max(torch.abs(mu32 - mu64) / scale)) < TOL32
-    lam = (torch.exp(model.y_log_lambdas) ** -2).unsqueeze(0)
+    assert torch.equal(mu32, mu64)  # the hybrid variant keeps the mean contraction in fp64 (same kernel, alpha tile only)
+    lam = (torch.exp(model.y_log_lambdas.detach()) ** -2).unsqueeze(0)
     v64, v32 = var64 / lam, var32 / lam
     assert float(torch.max(torch.abs(v32 - v64))) < TOL32          # 1e-4 of the prior variance (= 1)
     ok = v64[:, 0] > 0.05
     if bool(ok.any()):
-        assert float(torch.max(torch.abs(v32[ok] - v64[ok]) / v64[ok])) < 2e-3
+        assert float(torch.max(torch.abs(v32[ok] - v64[ok]) / v64[ok])) < 1e-3
+    # the all-tensor-core mode: means from tf32 x3 products too (alpha = K^-1 Y cancels, so only ~1e-3 of the row scale)
+    mup, varp = model.map_x_to_y(xs, precision="tf32-pure")
+    scale = torch.clamp(mu64.abs().max(dim=1, keepdim=True).values, min=1e-2)
+    assert float(torch.max(torch.abs(mup - mu64) / scale)) < 2e-3
+    assert torch.equal(varp, var32)
 
 
 def test_tf32_filter_step_log_weights(setup):
@@ -62,5 +66,7 @@ def test_tf32_filter_step_log_weights(setup):
     ok = v > 0.05
     ll64, ll32 = pf64._log_likelihoods, pf32._log_likelihoods
     assert bool(torch.isfinite(ll32).all())
-    assert float(torch.max(torch.abs(ll32[ok] - ll64[ok]) / torch.abs(ll64[ok]))) < 2e-3
+    rel = torch.abs(ll32[ok] - ll64[ok]) / torch.abs(ll64[ok])
+    assert float(rel.max()) < 1e-3, float(rel.max())
+    assert float(rel.median()) < TOL32, float(rel.median())
     assert pf64.get_most_likely_class() == pf32.get_most_likely_class()
