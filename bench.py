@@ -61,8 +61,10 @@ def parse_args():
 
 def workload_name(a):
     n = a.classes * a.seqs_per_class * a.frames
-    return (f"BASELINE configs[2]: {a.classes}-class GPMDM, N_train={n}, D={a.obs_dim}, d={a.latent}, "
-            f"P={a.particles} particles, fp64")
+    which = "configs[3] (tf32 variant)" if getattr(a, "precision", "fp64") == "tf32" and a.classes == 64 else "configs[2]"
+    prec = "fp64" if getattr(a, "precision", "fp64") == "fp64" else "tf32x3 variances + fp64 means/dynamics"
+    return (f"BASELINE {which}: {a.classes}-class GPMDM, N_train={n}, D={a.obs_dim}, d={a.latent}, "
+            f"P={a.particles} particles, {prec}")
 
 
 # ---- synthetic model ------------------------------------------------------------------------------------
@@ -306,7 +308,7 @@ def run_ours(a):
             achieved = flops_alg / (obs_avg_ms * 1e-3) / 1e12
             roofline = {
                 "bound": "tensor", "achieved": achieved, "peak": tf, "unit": "TFLOP/s", "frac": achieved / tf,
-                "traffic": None, "kernel": "gp_predict_kernel<0,3> (gpmdm_pf_observe_f64)", "launch_ms": obs_avg_ms,
+                "traffic": None, "kernel": f"gp_predict_kernel<0,{d}> (gpmdm_pf_observe_f64)", "launch_ms": obs_avg_ms,
                 "peak_source": "fp64 mma.sync m8n8k4 issue-rate probe measured in this run (MEASURED_PEAKS.json holds "
                                "no fp64 figure)",
                 "executed_tflops": flops_exec / (obs_avg_ms * 1e-3) / 1e12,
@@ -323,7 +325,7 @@ def run_ours(a):
             achieved = flops_mma / (obs_avg_ms * 1e-3) / 1e12
             roofline = {
                 "bound": "tensor", "achieved": achieved, "peak": 1100.0, "unit": "TFLOP/s", "frac": achieved / 1100.0,
-                "traffic": None, "kernel": "observe_tf32_kernel<3> (gpmdm_pf_observe_tf32)", "launch_ms": obs_avg_ms,
+                "traffic": None, "kernel": f"observe_tf32_kernel<{d}> (gpmdm_pf_observe_tf32) + fp64 mean tile (gpmdm_pf_loglik_f64)", "launch_ms": obs_avg_ms,
                 "peak_source": "nominal dense tf32 (1.1 PFLOP/s); achieved counts the tf32 MMA flops issued (3 per product)",
                 "algorithmic_tflops": flops_alg32 / (obs_avg_ms * 1e-3) / 1e12,
             }
