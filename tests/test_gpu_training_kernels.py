@@ -132,3 +132,26 @@ def test_train_adam_save_load_roundtrip(tmp_path):
     pf = GPMDM_PF(m2, synthetic.markov_matrix(2), 64, seed=3)
     pf.update(wl.test_trials[0][1][0])
     assert abs(float(pf.class_probabilities().sum()) - 1.0) < 1e-12
+
+
+def test_load_a_model_file_written_by_the_reference():
+    """`GPMDM.load` on a .pth saved by the UNMODIFIED reference's `GPMDM.save` (tests/golden/ref_saved_model.pth,
+    written by oracle/make_saved_model.py): parameters identical, predictions equal to the reference's."""
+    from gpmdm_b200 import GPMDM
+
+    here = os.path.dirname(os.path.abspath(__file__))
+    model = GPMDM.load(os.path.join(here, "golden", "ref_saved_model.pth"))
+    exp = np.load(os.path.join(here, "golden", "ref_saved_model_expect.npz"), allow_pickle=True)
+    state = exp["state"].item()
+    for k, v in model.state_dict().items():
+        assert np.array_equal(v.cpu().numpy(), state[k]), k
+    xs = torch.as_tensor(exp["xs"]).cuda()
+    mu, var = model.map_x_to_y(xs)
+    scale = np.maximum(np.abs(exp["mu"]).max(1, keepdims=True), 1e-3)
+    assert np.max(np.abs(mu.cpu().numpy() - exp["mu"]) / scale) < 1e-7   # own inverses (not injected): factor-level noise
+    lam = (torch.exp(model.y_log_lambdas.detach()) ** -2).cpu().numpy()[None, :]
+    assert np.max(np.abs(var.cpu().numpy() - exp["var"]) / lam) < 1e-7
+    dm, dv = model.map_x_dynamics_for_class(xs, 1)
+    assert np.max(np.abs(dm.cpu().numpy() - exp["dyn_mean"])) < 1e-6
+    prior = (1 + (exp["xs"] ** 2 * np.exp(state["x_log_lin_coeff"][:3]) ** 2).sum(1) + np.exp(state["x_log_lin_coeff"][3]) ** 2)
+    assert np.max(np.abs(dv.cpu().numpy() - exp["dyn_var"]) / prior[:, None]) < 1e-6

@@ -1,0 +1,97 @@
+"""BASELINE config 5: training kernel build (block-masked dynamics + observation kernel matrices) and the NLL gradient
+terms at N_train = 20 000, feeding torch.linalg Cholesky.  Times each CUDA kernel with CUDA events and reports achieved
+HBM GB/s against the measured copy peak (MEASURED_PEAKS.json: 6453 GB/s), plus one full `gpdm_loss` forward+backward.
+
+    python tools/cfg5_train_bench.py [--n-classes 8 --seqs-per-class 25 --frames 100]
+Algorithmic bytes: build = 8 N^2 written; gradient = 16 N^2 read (G row-wise and column-wise) + 8 N d written."""
+import argparse
+import json
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+
+import bench
+
+HBM_PEAK = 6453.1
+
+
+def timed(fn, reps=5):
+    fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    best = 1e30
+    for _ in range(reps):
+        e0.record(); fn(); e1.record(); torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    return best
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--classes", type=int, default=8)
+    ap.add_argument("--seqs-per-class", type=int, default=25)
+    ap.add_argument("--frames", type=int, default=100)
+    o = ap.parse_args()
+    a = argparse.Namespace(classes=o.classes, seqs_per_class=o.seqs_per_class, frames=o.frames, latent=3, obs_dim=62)
+    from gpmdm_b200 import GPMDM
+    from gpmdm_b200.gpmdm import _KernelBuild
+
+    wl, X0, hp = bench.synthetic_inputs(a)
+    m = GPMDM(D=62, d=3, n_classes=o.classes, dyn_target="full", dyn_back_step=1, **hp)
+    for c in range(o.classes):
+        for s in wl.sequences[c]:
+            m.add_data(s, c)
+    m._precompute_class_matrices()
+    m.X = torch.nn.Parameter(torch.tensor(X0, dtype=torch.float64, device=m.device))
+    N = X0.shape[0]
+    Xin, Xout, _ = m.get_Xin_Xout_matrices()
+    Xin = Xin.detach().contiguous()
+    Nx = Xin.shape[0]
+    offs = m._pair_offsets_dev()
+    out = {"N": N, "Nx": Nx, "hbm_peak_gbs": HBM_PEAK}
+    with torch.no_grad():
+        t = timed(lambda: m.get_y_kernel(m.X.detach(), m.X.detach()))
+        out["build_Ky_ms"], out["build_Ky_gbs"] = t, 8.0 * N * N / (t * 1e-3) / 1e9
+        t = timed(lambda: m.get_masked_x_kernel(Xin))
+        out["build_Kx_masked_ms"], out["build_Kx_masked_gbs"] = t, 8.0 * Nx * Nx / (t * 1e-3) / 1e9
+    # gradient kernels: G = dL/dK random
+    G = torch.randn(N, N, dtype=torch.float64, device=m.device)
+    Xd = m.X.detach().clone().requires_grad_(True)
+    for p in m.parameters():
+        p.requires_grad_(True)
+    K = m.get_y_kernel(Xd, Xd)
+    t = timed(lambda: torch.autograd.grad(K, [Xd, m.y_log_lengthscales, m.y_log_sigma_n], G, retain_graph=True))
+    out["grad_Ky_ms"], out["grad_Ky_gbs"] = t, 16.0 * N * N / (t * 1e-3) / 1e9
+    del K, G
+    Gx = torch.randn(Nx, Nx, dtype=torch.float64, device=m.device)
+    Xi = Xin.clone().requires_grad_(True)
+    Kx = m.get_masked_x_kernel(Xi)
+    t = timed(lambda: torch.autograd.grad(Kx, [Xi, m.x_log_lengthscales, m.x_log_sigma_n, m.x_log_lin_coeff], Gx, retain_graph=True))
+    # class-masked: only the diagonal blocks of G are read (16 * sum N_c^2 bytes)
+    blocks = float(sum((int(offs[i + 1]) - int(offs[i])) ** 2 for i in range(o.classes)))
+    out["grad_Kx_masked_ms"], out["grad_Kx_masked_gbs"] = t, 16.0 * blocks / (t * 1e-3) / 1e9
+    del Kx, Gx
+    # one full loss forward + backward (kernel builds + torch.linalg Cholesky / triangular solves + our gradient kernels)
+    Y = m._Y_device()
+
+    def step():
+        for p in m.parameters():
+            p.grad = None
+        loss = m.gpdm_loss(Y, N)
+        loss.backward()
+        return loss
+
+    t = timed(step, reps=2)
+    out["gpdm_loss_fwd_bwd_ms"] = t
+    out["loss"] = float(step())
+    for k in list(out):
+        if k.endswith("_gbs"):
+            out[k.replace("_gbs", "_frac_of_hbm_peak")] = out[k] / HBM_PEAK
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()
