@@ -8,6 +8,7 @@
 #include <math.h>
 
 #include "common.cuh"
+#include "fast_exp.cuh"
 
 namespace gpmdm {
 
@@ -19,73 +20,101 @@ __device__ __forceinline__ int class_of_row(long long i, const int64_t* __restri
     return c;
 }
 
-// One 32 x 32 tile per block (32 x 8 threads); masked-out tiles are written as zeros without any math.
+__constant__ double c_exp_table_train[64] = {GPMDM_EXP_TABLE_VALUES};
+
+// K is symmetric: one block computes a 64 x 64 tile (I <= J) once and writes it twice -- rows of tile (I, J) directly and
+// tile (J, I) through a shared-memory transpose -- so every exponential is evaluated once and both writes are coalesced.
+// Off-class tiles are zero-filled without any math.  256 threads, 16 elements each.
+constexpr int BT = 64;
 __global__ void __launch_bounds__(256) kernel_build_kernel(const double* __restrict__ X, long long n, int d, int kind,
                                                            const double* __restrict__ ls,
                                                            const double* __restrict__ lin_c2, double noise2,
                                                            const int64_t* __restrict__ offs, int n_classes,
                                                            double* __restrict__ K) {
-    __shared__ double ai[32][MAXD_T + 1], aj[32][MAXD_T + 1];  // x / l and |x/l|^2
-    __shared__ double xi[32][MAXD_T], xj[32][MAXD_T];
-    __shared__ int ci[32], cj[32];
-    const long long i0 = (long long)blockIdx.y * 32, j0 = (long long)blockIdx.x * 32;
-    const int tx = threadIdx.x, ty = threadIdx.y, t = ty * 32 + tx;
-    if (t < 64) {
-        const bool is_i = t < 32;
-        const int r = t & 31;
+    const int I = blockIdx.y, J = blockIdx.x;
+    if (J < I) return;
+    __shared__ double ai[BT][MAXD_T + 1], aj[BT][MAXD_T + 1];  // x / l and |x/l|^2
+    __shared__ double xi[BT][MAXD_T];  // c_k^2 x_ik
+    __shared__ int ci[BT], cj[BT];
+    __shared__ double tile[BT][BT + 1];
+    __shared__ double exptab[64];
+    const long long i0 = (long long)I * BT, j0 = (long long)J * BT;
+    const int t = threadIdx.x;
+    if (t < 64) exptab[t] = c_exp_table_train[t];
+    if (t < 2 * BT) {
+        const bool is_i = t < BT;
+        const int r = t & (BT - 1);
         const long long row = (is_i ? i0 : j0) + r;
         double n2 = 0.0;
         for (int k = 0; k < d; k++) {
             const double x = row < n ? X[row * d + k] : 0.0;
             const double a = x / ls[k];
             (is_i ? ai : aj)[r][k] = a;
-            (is_i ? xi : xj)[r][k] = x;
+            if (is_i) xi[r][k] = (kind == 1) ? lin_c2[k] * x : 0.0;
             n2 = fma(a, a, n2);
         }
         (is_i ? ai : aj)[r][d] = n2;
         (is_i ? ci : cj)[r] = (offs && row < n) ? class_of_row(row, offs, n_classes) : 0;
     }
     __syncthreads();
-    const long long j = j0 + tx;
-    for (int r = ty; r < 32; r += 8) {
-        const long long i = i0 + r;
-        if (i >= n || j >= n) continue;
+    const int tx = t & 63, ty = t >> 6;  // column within the tile, 4 row groups
+    const double c2last = kind == 1 ? lin_c2[d] : 0.0;
+    double xraw[MAXD_T];
+    if (kind == 1)
+        for (int k = 0; k < d; k++) xraw[k] = (j0 + tx < n) ? X[(j0 + tx) * d + k] : 0.0;
+    for (int r = ty; r < BT; r += 4) {
+        const long long i = i0 + r, j = j0 + tx;
         double v = 0.0;
-        if (!offs || ci[r] == cj[tx]) {
+        if (i < n && j < n && (!offs || ci[r] == cj[tx])) {
             double dot = 0.0;
             for (int k = 0; k < d; k++) dot = fma(ai[r][k], aj[tx][k], dot);
-            v = exp(-(ai[r][d] + aj[tx][d] - 2.0 * dot));  // gpmdm.py:515-517 expansion form
+            v = fast_exp(-(ai[r][d] + aj[tx][d] - 2.0 * dot), exptab);  // gpmdm.py:515-517 expansion form
             if (i == j) v += noise2;
             if (kind == 1) {
-                double lin = lin_c2[d];
-                for (int k = 0; k < d; k++) lin = fma(lin_c2[k] * xi[r][k], xj[tx][k], lin);
+                double lin = c2last;
+                for (int k = 0; k < d; k++) lin = fma(xi[r][k], xraw[k], lin);
                 v += lin;
             }
         }
-        K[i * n + j] = v;
+        tile[r][tx] = v;
+        if (i < n && j < n) K[i * n + j] = v;
+    }
+    if (I == J) return;
+    __syncthreads();
+    for (int r = ty; r < BT; r += 4) {  // transposed copy: row (j0 + r), columns i0 + tx
+        const long long jj = j0 + r, ii = i0 + tx;
+        if (jj < n && ii < n) K[jj * n + ii] = tile[tx][r];
     }
 }
 
-// Gradient terms.  Block b owns rows [32 b, 32 b + 32) and walks all column tiles.
-//   part [nblk][2 d + 2] : per-block partials of g_log_ls[d], tr(G^), g_log_c[d+1]
+// Gradient terms.  Block (b, s) owns rows [32 b, 32 b + 32) and walks column split s of the (class-restricted) column
+// range.   partX [NS][n][d]: per-split row sums;  part [nblk * NS][2 d + 2]: per-block partials of g_log_ls[d],
+// tr(G^), g_log_c[d+1].  A second kernel adds the splits / blocks in a fixed order.
+template <int DL>
 __global__ void __launch_bounds__(256) kernel_grad_kernel(const double* __restrict__ X, const double* __restrict__ G,
-                                                          long long n, int d, int kind, const double* __restrict__ ls,
+                                                          long long n, int kind, const double* __restrict__ ls,
                                                           const double* __restrict__ lin_c2,
                                                           const int64_t* __restrict__ offs, int n_classes,
-                                                          double* __restrict__ gX, double* __restrict__ part) {
-    __shared__ double ai[32][MAXD_T], aj[32][MAXD_T];
-    __shared__ double xi[32][MAXD_T], xj[32][MAXD_T];
+                                                          double* __restrict__ partX, double* __restrict__ part) {
+    __shared__ double ai[32][MAXD_T], xi[32][MAXD_T];  // row side: read as broadcasts
+    __shared__ double aj[MAXD_T][32], xj[MAXD_T][32];  // column side: k-major, lane = column (conflict-free)
     __shared__ double GT[32][33];
     __shared__ int ci[32], cj[32];
     __shared__ double red[8][2 * MAXD_T + 2];
+    __shared__ double exptab[64];
+    __shared__ double inv_ls[MAXD_T];
+    constexpr int d = DL;  // compile-time latent dimension: the per-thread accumulators below stay in registers
     const long long i0 = (long long)blockIdx.x * 32;
+    const int NS = gridDim.y, split = blockIdx.y;
     const int tx = threadIdx.x, ty = threadIdx.y, t = ty * 32 + tx;
+    if (t < 64) exptab[t] = c_exp_table_train[t];
+    if (t < d) inv_ls[t] = 1.0 / ls[t];
     if (t < 32) {
         const long long row = i0 + t;
         for (int k = 0; k < d; k++) {
             const double x = row < n ? X[row * d + k] : 0.0;
             xi[t][k] = x;
-            ai[t][k] = x / ls[k];
+            ai[t][k] = x * (1.0 / ls[k]);
         }
         ci[t] = (offs && row < n) ? class_of_row(row, offs, n_classes) : 0;
     }
@@ -109,56 +138,91 @@ __global__ void __launch_bounds__(256) kernel_grad_kernel(const double* __restri
         jend = offs[class_of_row(last, offs, n_classes) + 1];
         jbeg = jbeg / 32 * 32;
     }
+    {
+        const long long ntile = (jend - jbeg + 31) / 32, per = (ntile + NS - 1) / NS;
+        const long long a0 = jbeg + split * per * 32;
+        const long long a1 = a0 + per * 32;
+        jbeg = a0;
+        jend = a1 < jend ? a1 : jend;
+    }
+    // G values of the current tile live in registers; the next tile's are prefetched while this one is computed, so
+    // the HBM latency of the two 8 KB tile reads (G[i][j] row-wise, G[j][i] as 256-byte column segments) is hidden.
+    double gcur[4], gtc[4];
+    auto fetch = [&](long long j0, double (&gv)[4], double (&gt)[4]) {
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const int r = ty + 8 * q;
+            const long long i = i0 + r, j = j0 + tx;
+            gv[q] = (j0 < jend && i < n && j < n) ? G[i * n + j] : 0.0;
+            const long long jj = j0 + r, ii = i0 + tx;
+            gt[q] = (j0 < jend && jj < n && ii < n) ? G[jj * n + ii] : 0.0;
+        }
+    };
+    fetch(jbeg, gcur, gtc);
     for (long long j0 = jbeg; j0 < jend; j0 += 32) {
         __syncthreads();
         if (t < 32) {
             const long long row = j0 + t;
             for (int k = 0; k < d; k++) {
                 const double x = row < n ? X[row * d + k] : 0.0;
-                xj[t][k] = x;
-                aj[t][k] = x / ls[k];
+                xj[k][t] = x;
+                aj[k][t] = x * inv_ls[k];
             }
             cj[t] = (offs && row < n) ? class_of_row(row, offs, n_classes) : 0;
         }
-        // transposed tile: GT[r][c] = G[j0 + r][i0 + c]  (32 rows of 256 contiguous bytes)
-        for (int r = ty; r < 32; r += 8) {
-            const long long jj = j0 + r, ii = i0 + tx;
-            GT[r][tx] = (jj < n && ii < n) ? G[jj * n + ii] : 0.0;
-        }
+        // transposed tile: GT[r][c] = G[j0 + r][i0 + c]
+#pragma unroll
+        for (int q = 0; q < 4; q++) GT[ty + 8 * q][tx] = gtc[q];
         __syncthreads();
+        double gnext[4], gtn[4];
+        fetch(j0 + 32, gnext, gtn);
         const long long j = j0 + tx;
+        double ajr[MAXD_T], xjr[MAXD_T];  // this lane's column, shared by its four rows
+#pragma unroll
+        for (int k = 0; k < MAXD_T; k++) {
+            ajr[k] = k < d ? aj[k][tx] : 0.0;
+            xjr[k] = (kind == 1 && k < d) ? xj[k][tx] : 0.0;
+        }
 #pragma unroll
         for (int q = 0; q < 4; q++) {
             const int r = ty + 8 * q;
             const long long i = i0 + r;
             if (i >= n || j >= n) continue;
             if (offs && ci[r] != cj[tx]) continue;
-            const double g = G[i * n + j];  // G^_ij
+            const double g = gcur[q];        // G^_ij
             const double s = g + GT[tx][r];  // S_ij = G^_ij + G^_ji
             double dist = 0.0;
             double dk[MAXD_T];
 #pragma unroll
             for (int k = 0; k < MAXD_T; k++)
                 if (k < d) {
-                    dk[k] = ai[r][k] - aj[tx][k];
+                    dk[k] = ai[r][k] - ajr[k];
                     dist = fma(dk[k], dk[k], dist);
                 }
-            const double kr = exp(-dist);
+            const double kr = fast_exp(-dist, exptab);
+            const double gkr = g * kr, skr = s * kr;
 #pragma unroll
             for (int k = 0; k < MAXD_T; k++)
                 if (k < d) {
                     // d k_rbf / d x_ik = k_rbf * (-2 (x_ik - x_jk) / l_k^2)
-                    double term = kr * (-2.0 * dk[k] / ls[k]);
-                    if (kind == 1) term = fma(lin_c2[k], xj[tx][k], term);
-                    gx[q][k] = fma(s, term, gx[q][k]);
-                    gl[k] = fma(g * kr, 2.0 * dk[k] * dk[k], gl[k]);
-                    if (kind == 1) gc[k] = fma(g, xi[r][k] * xj[tx][k], gc[k]);
+                    gx[q][k] = fma(skr, -2.0 * dk[k] * inv_ls[k], gx[q][k]);
+                    gl[k] = fma(gkr, 2.0 * dk[k] * dk[k], gl[k]);
+                    if (kind == 1) {
+                        gx[q][k] = fma(s * lin_c2[k], xjr[k], gx[q][k]);
+                        gc[k] = fma(g, xi[r][k] * xjr[k], gc[k]);
+                    }
                 }
             if (kind == 1) gc[d] += g;
             if (i == j) tr += g;
         }
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            gcur[q] = gnext[q];
+            gtc[q] = gtn[q];
+        }
     }
     // row sums: lanes of a warp share ty, i.e. the same four rows
+    double* px = partX + (long long)split * n * d;
 #pragma unroll
     for (int q = 0; q < 4; q++) {
         const long long i = i0 + ty + 8 * q;
@@ -166,7 +230,7 @@ __global__ void __launch_bounds__(256) kernel_grad_kernel(const double* __restri
         for (int k = 0; k < MAXD_T; k++)
             if (k < d) {
                 const double v = warp_sum(gx[q][k]);
-                if (tx == 0 && i < n) gX[i * d + k] = v;
+                if (tx == 0 && i < n) px[i * d + k] = v;
             }
     }
     // scalar partials: warp tree, then serial over the 8 warps
@@ -187,8 +251,18 @@ __global__ void __launch_bounds__(256) kernel_grad_kernel(const double* __restri
     if (t < ncol) {
         double v = 0.0;
         for (int w = 0; w < 8; w++) v += red[w][t];
-        part[(long long)blockIdx.x * ncol + t] = v;
+        part[((long long)blockIdx.x * NS + split) * ncol + t] = v;
     }
+}
+
+// fixed-order reductions of the partials: gX[i][k] = sum_s partX[s][i][k]; scalars = sum over blocks
+__global__ void kernel_grad_reduce_x_kernel(const double* __restrict__ partX, long long nd, int NS,
+                                            double* __restrict__ gX) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nd) return;
+    double v = 0.0;
+    for (int s = 0; s < NS; s++) v += partX[(long long)s * nd + i];
+    gX[i] = v;
 }
 
 __global__ void kernel_grad_final_kernel(const double* __restrict__ part, long long nblk, int d, int kind,
@@ -209,6 +283,8 @@ __global__ void kernel_grad_final_kernel(const double* __restrict__ part, long l
     }
 }
 
+constexpr int GRAD_SPLITS = 8;
+
 }  // namespace gpmdm
 
 using namespace gpmdm;
@@ -220,14 +296,14 @@ extern "C" int gpmdm_kernel_build_f64(const double* X, int64_t n, int32_t d, int
     GPMDM_REQUIRE(n > 0 && d >= 1 && d <= MAXD_T, GPMDM_E_INVALID, "bad sizes n=%lld d=%d", (long long)n, d);
     GPMDM_REQUIRE(kind == 0 || (kind == 1 && lin_c2), GPMDM_E_INVALID, "kind 1 needs lin_c2");
     GPMDM_REQUIRE(class_offsets == nullptr || n_classes >= 1, GPMDM_E_INVALID, "bad class offsets");
-    const unsigned g = (unsigned)((n + 31) / 32);
-    kernel_build_kernel<<<dim3(g, g), dim3(32, 8), 0, (cudaStream_t)stream>>>(X, n, d, kind, lengthscales, lin_c2,
-                                                                             noise2, class_offsets, n_classes, K);
+    const unsigned g = (unsigned)((n + BT - 1) / BT);
+    kernel_build_kernel<<<dim3(g, g), 256, 0, (cudaStream_t)stream>>>(X, n, d, kind, lengthscales, lin_c2, noise2,
+                                                                      class_offsets, n_classes, K);
     return check_launch("kernel_build_kernel");
 }
 
 extern "C" int64_t gpmdm_kernel_grad_workspace_bytes(int64_t n, int32_t d) {
-    return ((n + 31) / 32) * (int64_t)(2 * d + 2) * 8;
+    return ((n + 31) / 32) * GRAD_SPLITS * (int64_t)(2 * d + 2) * 8 + (int64_t)GRAD_SPLITS * n * d * 8;
 }
 
 extern "C" int gpmdm_kernel_grad_f64(const double* X, const double* G, int64_t n, int32_t d, int32_t kind,
@@ -240,8 +316,20 @@ extern "C" int gpmdm_kernel_grad_f64(const double* X, const double* G, int64_t n
     cudaStream_t st = (cudaStream_t)stream;
     const long long nblk = (n + 31) / 32;
     double* part = static_cast<double*>(workspace);
-    kernel_grad_kernel<<<(unsigned)nblk, dim3(32, 8), 0, st>>>(X, G, n, d, kind, lengthscales, lin_c2, class_offsets,
-                                                                n_classes, gX, part);
-    kernel_grad_final_kernel<<<1, 32, 0, st>>>(part, nblk, d, kind, lin_c2, sigma2, g_log_ls, g_log_sigma, g_log_c);
+    double* partX = part + nblk * GRAD_SPLITS * (2 * d + 2);
+    const dim3 grid((unsigned)nblk, GRAD_SPLITS), block(32, 8);
+#define GPMDM_GRAD_CASE(DL)                                                                                        \
+    case DL:                                                                                                       \
+        kernel_grad_kernel<DL><<<grid, block, 0, st>>>(X, G, n, kind, lengthscales, lin_c2, class_offsets, n_classes, \
+                                                       partX, part);                                               \
+        break;
+    switch (d) {
+        GPMDM_GRAD_CASE(1) GPMDM_GRAD_CASE(2) GPMDM_GRAD_CASE(3) GPMDM_GRAD_CASE(4)
+        GPMDM_GRAD_CASE(5) GPMDM_GRAD_CASE(6) GPMDM_GRAD_CASE(7) GPMDM_GRAD_CASE(8)
+    }
+#undef GPMDM_GRAD_CASE
+    kernel_grad_reduce_x_kernel<<<(unsigned)((n * d + 255) / 256), 256, 0, st>>>(partX, n * d, GRAD_SPLITS, gX);
+    kernel_grad_final_kernel<<<1, 32, 0, st>>>(part, nblk * GRAD_SPLITS, d, kind, lin_c2, sigma2, g_log_ls, g_log_sigma,
+                                               g_log_c);
     return check_launch("kernel_grad_kernel");
 }

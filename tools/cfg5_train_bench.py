@@ -52,28 +52,36 @@ def main():
     Nx = Xin.shape[0]
     offs = m._pair_offsets_dev()
     out = {"N": N, "Nx": Nx, "hbm_peak_gbs": HBM_PEAK}
-    with torch.no_grad():
-        t = timed(lambda: m.get_y_kernel(m.X.detach(), m.X.detach()))
-        out["build_Ky_ms"], out["build_Ky_gbs"] = t, 8.0 * N * N / (t * 1e-3) / 1e9
-        t = timed(lambda: m.get_masked_x_kernel(Xin))
-        out["build_Kx_masked_ms"], out["build_Kx_masked_gbs"] = t, 8.0 * Nx * Nx / (t * 1e-3) / 1e9
-    # gradient kernels: G = dL/dK random
-    G = torch.randn(N, N, dtype=torch.float64, device=m.device)
-    Xd = m.X.detach().clone().requires_grad_(True)
+    # ---- the CUDA kernels themselves, through the C ABI (no autograd / allocator overhead in the timed region)
+    from gpmdm_b200 import _cabi
+    from gpmdm_b200._cabi import check, ptr, stream
+    lib = _cabi.lib()
+    dev = m.device
+    X = m.X.detach().contiguous()
+    ls_y = torch.exp(m.y_log_lengthscales.detach()).contiguous()
+    ls_x = torch.exp(m.x_log_lengthscales.detach()).contiguous()
+    c2 = (torch.exp(m.x_log_lin_coeff.detach()) ** 2).contiguous()
+    s2y = float(torch.exp(m.y_log_sigma_n.detach()) ** 2)
+    s2x = float(torch.exp(m.x_log_sigma_n.detach()) ** 2)
+    K = torch.empty(N, N, dtype=torch.float64, device=dev)
+    t = timed(lambda: check(lib.gpmdm_kernel_build_f64(ptr(X), N, 3, 0, ptr(ls_y), None, s2y, None, 0, ptr(K), stream()), "build"))
+    out["build_Ky_ms"], out["build_Ky_gbs"] = t, 8.0 * N * N / (t * 1e-3) / 1e9
+    Kx = K[:Nx * Nx // N].reshape(-1)[:Nx * Nx].view(Nx, Nx) if Nx * Nx <= N * N else torch.empty(Nx, Nx, dtype=torch.float64, device=dev)
+    t = timed(lambda: check(lib.gpmdm_kernel_build_f64(ptr(Xin), Nx, 3, 1, ptr(ls_x), ptr(c2), s2x, ptr(offs), o.classes, ptr(Kx), stream()), "build"))
+    out["build_Kx_masked_ms"], out["build_Kx_masked_gbs"] = t, 8.0 * Nx * Nx / (t * 1e-3) / 1e9
+    G = torch.randn(N, N, dtype=torch.float64, device=dev)
+    gX = torch.empty(N, 3, dtype=torch.float64, device=dev)
+    gl, gs, gc = (torch.empty(k, dtype=torch.float64, device=dev) for k in (3, 1, 4))
+    ws = torch.empty(int(lib.gpmdm_kernel_grad_workspace_bytes(N, 3)) // 8 + 1, dtype=torch.float64, device=dev)
+    t = timed(lambda: check(lib.gpmdm_kernel_grad_f64(ptr(X), ptr(G), N, 3, 0, ptr(ls_y), None, s2y, None, 0, ptr(gX), ptr(gl), ptr(gs), None, ptr(ws), stream()), "grad"))
+    out["grad_Ky_ms"], out["grad_Ky_gbs"] = t, 16.0 * N * N / (t * 1e-3) / 1e9
+    Gx = G.reshape(-1)[:Nx * Nx].view(Nx, Nx)
+    t = timed(lambda: check(lib.gpmdm_kernel_grad_f64(ptr(Xin), ptr(Gx), Nx, 3, 1, ptr(ls_x), ptr(c2), s2x, ptr(offs), o.classes, ptr(gX), ptr(gl), ptr(gs), ptr(gc), ptr(ws), stream()), "grad"))
+    blocks = float(sum((int(offs[i + 1]) - int(offs[i])) ** 2 for i in range(o.classes)))  # only class blocks of G are read
+    out["grad_Kx_masked_ms"], out["grad_Kx_masked_gbs"] = t, 16.0 * blocks / (t * 1e-3) / 1e9
+    del K, G, Kx, Gx
     for p in m.parameters():
         p.requires_grad_(True)
-    K = m.get_y_kernel(Xd, Xd)
-    t = timed(lambda: torch.autograd.grad(K, [Xd, m.y_log_lengthscales, m.y_log_sigma_n], G, retain_graph=True))
-    out["grad_Ky_ms"], out["grad_Ky_gbs"] = t, 16.0 * N * N / (t * 1e-3) / 1e9
-    del K, G
-    Gx = torch.randn(Nx, Nx, dtype=torch.float64, device=m.device)
-    Xi = Xin.clone().requires_grad_(True)
-    Kx = m.get_masked_x_kernel(Xi)
-    t = timed(lambda: torch.autograd.grad(Kx, [Xi, m.x_log_lengthscales, m.x_log_sigma_n, m.x_log_lin_coeff], Gx, retain_graph=True))
-    # class-masked: only the diagonal blocks of G are read (16 * sum N_c^2 bytes)
-    blocks = float(sum((int(offs[i + 1]) - int(offs[i])) ** 2 for i in range(o.classes)))
-    out["grad_Kx_masked_ms"], out["grad_Kx_masked_gbs"] = t, 16.0 * blocks / (t * 1e-3) / 1e9
-    del Kx, Gx
     # one full loss forward + backward (kernel builds + torch.linalg Cholesky / triangular solves + our gradient kernels)
     Y = m._Y_device()
 
