@@ -256,9 +256,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) gp_predict_kernel(const PredictPa
             }
             if (lane == 0) mbar_expect_tx(&s.full[st], (uint32_t)(KC * TN * 8 + KC * REC * 8));
             __syncwarp();
-            if (lane < KC)
-                bulk_g2s(&s.B[st][lane][0], src + (long long)(bcur.k * KC + lane) * ld, TN * 8, &s.full[st]);
-            else if (lane == KC)
+            for (int row = lane; row < KC; row += 32)
+                bulk_g2s(&s.B[st][row][0], src + (long long)(bcur.k * KC + row) * ld, TN * 8, &s.full[st]);
+            if (lane == 0)
                 bulk_g2s(&s.R[st][0], gbk.coords + (long long)bcur.k * KC * REC, (uint32_t)(KC * REC * 8), &s.full[st]);
         };
         for (int i = 0; i < AHEAD && !bcur.done(); i++) {
