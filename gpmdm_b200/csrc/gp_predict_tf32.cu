@@ -51,7 +51,7 @@ struct __align__(1024) Smem {
 };
 
 struct Params {
-    const float* coords;   // [n_pad, CREC]
+    const float* coords;   // [n_pad / 2, CREC, 2]: pairs of training rows interleaved per coordinate
     const float* wtiles;   // packed W tiles
     const float* atiles;   // packed alpha tiles
     int n_pad, d, dout;
@@ -221,33 +221,41 @@ __global__ void __launch_bounds__(NTHREADS, 1) observe_tf32_kernel(const Params 
         for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
             long long p = (long long)t * TM + row;
             if (p >= prm.P) p = prm.P - 1;
-            float b[DL];
+            // particle coordinates, negated and duplicated into both halves of a packed f32x2 register
+            float2 nb[DL];
 #pragma unroll
-            for (int j = 0; j < DL; j++) b[j] = (float)(prm.x[p * DL + j] / prm.ls[j]);
+            for (int j = 0; j < DL; j++) {
+                const float bj = (float)(prm.x[p * DL + j] / prm.ls[j]);
+                nb[j] = make_float2(-bj, -bj);
+            }
             for (int ct = 0; ct < nct; ct++) {
                 const int nch = chunks_of(ct);
                 for (int kc = 0; kc < nch; kc++, g++) {
                     const int sa = g % ASTAGES;
                     float hi[8], lo[8];
-                    const float* rec = prm.coords + (long long)(kc * KC + khalf * 8) * CREC;
+                    // coords are stored per PAIR of training rows as [j][2] (a_k[j], a_k+1[j]): one 64-bit element feeds
+                    // the packed fp32x2 pipe (sm_100 FADD2 / FFMA2), two K* entries per instruction
+                    const float2* rec = reinterpret_cast<const float2*>(prm.coords) + (long long)(kc * KC + khalf * 8) / 2 * CREC;
 #pragma unroll
-                    for (int kk = 0; kk < 8; kk++) {
-                        float a[CREC];
-                        const float4 r0 = __ldg(reinterpret_cast<const float4*>(rec + kk * CREC));
-                        a[0] = r0.x, a[1] = r0.y, a[2] = r0.z, a[3] = r0.w;
-                        if (DL > 4) {
-                            const float4 r1 = __ldg(reinterpret_cast<const float4*>(rec + kk * CREC + 4));
-                            a[4] = r1.x, a[5] = r1.y, a[6] = r1.z, a[7] = r1.w;
+                    for (int kk = 0; kk < 8; kk += 2) {
+                        float2 a[CREC];
+#pragma unroll
+                        for (int q = 0; q < (DL + 1) / 2; q++) {
+                            const float4 r4 = __ldg(reinterpret_cast<const float4*>(rec + (kk / 2) * CREC + 2 * q));
+                            a[2 * q] = make_float2(r4.x, r4.y);
+                            a[2 * q + 1] = make_float2(r4.z, r4.w);
                         }
-                        float dist = 0.f;
+                        float2 dist = make_float2(0.f, 0.f);
 #pragma unroll
                         for (int j = 0; j < DL; j++) {
-                            const float tdiff = a[j] - b[j];
-                            dist = fmaf(tdiff, tdiff, dist);
+                            const float2 tdiff = __fadd2_rn(a[j], nb[j]);
+                            dist = __ffma2_rn(tdiff, tdiff, dist);
                         }
-                        const float kv = exp2f(-LOG2E * dist);
-                        hi[kk] = to_tf32(kv);
-                        lo[kk] = to_tf32(kv - hi[kk]);
+                        const float k0 = exp2f(-LOG2E * dist.x), k1 = exp2f(-LOG2E * dist.y);
+                        hi[kk] = to_tf32(k0);
+                        lo[kk] = to_tf32(k0 - hi[kk]);
+                        hi[kk + 1] = to_tf32(k1);
+                        lo[kk + 1] = to_tf32(k1 - hi[kk + 1]);
                     }
                     mbar_wait(&s.a_empty[sa], ((g / ASTAGES) & 1) ^ 1);
                     float* ah = &s.A[sa][0][0];

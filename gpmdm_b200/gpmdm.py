@@ -512,6 +512,7 @@ class GPMDM(torch.nn.Module):
         check(lib.gpmdm_pack_alpha_tf32(ptr(alpha), n, n_pad, self.D, ptr(at), stream()), "gpmdm_pack_alpha_tf32")
         coords = torch.zeros(n_pad, 8, dtype=torch.float32, device=self.device)
         coords[:n, :d] = (X / torch.exp(self.y_log_lengthscales.detach())).to(torch.float32)
+        coords = coords.view(n_pad // 2, 2, 8).transpose(1, 2).contiguous()  # [pair][coordinate][row in pair]
         ls = torch.exp(self.y_log_lengthscales.detach()).contiguous()
         lam2 = (torch.exp(self.y_log_lambdas.detach()) ** 2).contiguous()
         model = GpModelTf32(coords=coords.data_ptr(), wtiles=wt.data_ptr(), atiles=at.data_ptr(), n=n, n_pad=n_pad, d=d,
@@ -580,6 +581,101 @@ class GPMDM(torch.nn.Module):
             var = var + (torch.exp(self.x_log_sigma_n) ** 2 + self.sigma_n_num_X ** 2) \
                 * (torch.exp(self.x_log_lambdas) ** -2).unsqueeze(0)
         return mean, var
+
+    # ---- class-agnostic dynamics map and the notebook helpers (gpmdm.py:993-1030, 1103-1273) -----------------------
+    # Not on the filter path; kept so that the reference's notebooks run unchanged.  The masked
+    # K_x o M is block diagonal, so k*^T (K_x o M)^-1 (.) is the SUM over classes of the per-class fused prediction
+    # with the un-jittered block inverses -- the same kernel as the filter, no dense Nx x Nx product.
+    @torch.no_grad()
+    def _agnostic_dyn_model(self):
+        if getattr(self, "_packed_agn", None) is not None and self._packed_agn["version"] == self._factors_version:
+            return self._packed_agn
+        offs = self.class_pair_offsets()
+        c2 = (torch.exp(self.x_log_lin_coeff.detach()) ** 2).contiguous()
+        ls_x = torch.exp(self.x_log_lengthscales.detach()).contiguous()
+        lam_x = (torch.exp(self.x_log_lambdas.detach()) ** -2).contiguous()
+        blocks = []
+        for c in range(self.n_classes):
+            Xc = self._Xin[offs[c]:offs[c + 1]].contiguous()
+            Kc = _KernelBuild.apply(Xc, self.x_log_lengthscales, self.x_log_sigma_n, self.x_log_lin_coeff,
+                                    self.sigma_n_num_X, None, True)  # block of K_x o M: no 1e-6 jitter (gpmdm.py:1292)
+            blocks.append(self._pack_block(Xc, self.x_log_lengthscales.detach(), self._inverse_via_upper_cholesky(Kc),
+                                           self._Xout[offs[c]:offs[c + 1]], TILE_N, c2, True))
+        table = torch.tensor([[b["coords"].data_ptr(), b["L"].data_ptr(), b["alpha"].data_ptr(), b["n"], b["n_pad"]]
+                              for b in blocks], dtype=torch.int64, device=self.device)
+        model = GpModel(blocks=table.data_ptr(), n_blocks=len(blocks), d=self.d, dout=self.d, alpha_ld=TILE_N, kind=1,
+                        tri=1, lengthscales=ls_x.data_ptr(), lin_c2=c2.data_ptr(), lambdas=lam_x.data_ptr())
+        self._packed_agn = dict(version=self._factors_version, model=model, keep=(blocks, table, c2, ls_x, lam_x))
+        return self._packed_agn
+
+    @torch.no_grad()
+    def map_x_dynamics(self, Xstar, flg_noise=False):
+        """gpmdm.py:993-1030: GP prediction of the dynamics map with the class-masked (block-diagonal) K_x."""
+        if self.dyn_back_step != 1:
+            raise ValueError("fused dynamics prediction supports dyn_back_step == 1 only")
+        lib = _cabi.lib()
+        pk = self._agnostic_dyn_model()
+        Xs = to_tensor(Xstar, self.dtype, self.device).contiguous()
+        P = Xs.shape[0]
+        lam = torch.exp(self.x_log_lambdas.detach()) ** -2
+        prior = self.get_x_diag_kernel(Xs, flg_noise)
+        mean = torch.zeros(P, self.d, dtype=self.dtype, device=self.device)
+        q = torch.zeros(P, dtype=self.dtype, device=self.device)
+        if P == 0:
+            return mean, prior.unsqueeze(1) * lam.unsqueeze(0)
+        perm = torch.arange(P, dtype=torch.int32, device=self.device)
+        nt = (P + TILE_P - 1) // TILE_P
+        t = torch.arange(nt, dtype=torch.int32, device=self.device)
+        n_tiles = torch.tensor([nt], dtype=torch.int32, device=self.device)
+        m_c = torch.empty(P, self.d, dtype=self.dtype, device=self.device)
+        v_c = torch.empty(P, self.d, dtype=self.dtype, device=self.device)
+        prior0 = self.get_x_diag_kernel(Xs, False)
+        for c in range(self.n_classes):
+            tiles = torch.stack([torch.full_like(t, c), t * TILE_P, torch.clamp(P - t * TILE_P, max=TILE_P),
+                                 torch.zeros_like(t)], 1).contiguous()
+            check(lib.gpmdm_pf_propagate_f64(ctypes.byref(pk["model"]), ptr(Xs), ptr(perm), ptr(tiles), ptr(n_tiles), P,
+                                             None, None, ptr(m_c), ptr(v_c), ptr(self._scratch_counter()), stream()),
+                  "gpmdm_pf_propagate_f64")
+            mean += m_c
+            q += prior0 - v_c[:, 0] / lam[0]  # the kernel returns (prior - q_c) * lambda^-2
+        return mean, (prior - q).unsqueeze(1) * lam.unsqueeze(0)
+
+    def get_next_x(self, gp_mean_out, gp_out_var, Xold, flg_sample=False):
+        """gpmdm.py:1103-1145."""
+        from torch.distributions.normal import Normal
+
+        distribution = Normal(gp_mean_out, torch.sqrt(gp_out_var))
+        step = distribution.rsample() if flg_sample else gp_mean_out
+        if self.dyn_target == 'full':
+            return step
+        if self.dyn_target == 'delta':
+            return Xold + step
+
+    def get_dynamics_map_performance_for_class(self, class_index, flg_noise=False):
+        """gpmdm.py:1147-1194 (including its floor-division `//` in the NMSE, reproduced as is)."""
+        with torch.no_grad():
+            Xin, Xout, _ = self.get_Xin_Xout_matrices()
+            mean, var = self.map_x_dynamics_for_class(Xin, class_index, flg_noise=flg_noise)
+            mean, var = mean.cpu().numpy(), var.cpu().numpy()
+            Xout, Xin = Xout.detach().cpu().numpy(), Xin.detach().cpu().numpy()
+            NMSE = np.mean((Xout - mean) ** 2 // var)
+        return mean, var, Xout, Xin, NMSE
+
+    def get_latent_map_performance(self, flg_noise=False):
+        """gpmdm.py:1196-1237."""
+        with torch.no_grad():
+            mean, var = self.map_x_to_y(self.X, flg_noise=flg_noise)
+            mean, var = mean.cpu().numpy(), var.cpu().numpy()
+            Y = self.get_Y() + self.meanY
+            return mean, var, Y, np.mean((Y - mean) ** 2 // var)
+
+    def get_latent_map_performance_for_class(self, class_index, flg_noise=False):
+        """gpmdm.py:1239-1273."""
+        with torch.no_grad():
+            mean, var = self.map_x_to_y(self.get_X_for_class(class_index), flg_noise=flg_noise)
+            mean, var = mean.cpu().numpy(), var.cpu().numpy()
+            Y = self.get_Y_for_class(class_index) + self.meanY
+            return mean, var, Y, np.mean((Y - mean) ** 2 // var)
 
     # ---- save / load (gpmdm.py:1307-1414); same on-disk format ---------------------------------------------------
     def save(self, file_path):

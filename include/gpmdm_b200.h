@@ -167,7 +167,8 @@ int64_t gpmdm_workspace_bytes(int64_t P, int32_t C);
  * WHITENED variance  v = 1 - |W k|^2,  W = U^-T  with K = U^T U the reference's upper Cholesky factor
  * (gpmdm.py:1287-1288): the explicit-inverse form of gpmdm.py:958-959 is not usable below fp64.
  * The dynamics GP, the draws and the resampling stay on the fp64 path.
- *   coords [n_pad, 8]  fp32  a_i = x_i / lengthscale, zero padded
+ *   coords [n_pad/2, 8, 2] fp32  a_i = x_i / lengthscale, zero padded to 8 coordinates, rows interleaved in pairs:
+ *                      element [i/2][j][i%2] = a_i[j]  (one 64-bit load feeds the packed fp32x2 pipe)
  *   wtiles             tf32 hi/lo tiles of W in tensor-core operand order (gpmdm_pack_whitened_tf32)
  *   atiles             tf32 hi/lo tiles of alpha = K^-T Y                 (gpmdm_pack_alpha_tf32)            */
 typedef struct gpmdm_gp_model_tf32 {

@@ -315,3 +315,30 @@ def test_cfg3_scale_properties():
         anc = pf.last_ancestors
         assert bool(torch.all(anc[1:] >= anc[:-1]))
     assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+
+
+def test_class_agnostic_dynamics_map_and_helpers():
+    """`map_x_dynamics` (gpmdm.py:993-1030, not on the filter path): the sum of per-class fused predictions equals the
+    reference's dense expression with K_x o M; plus the notebook helper methods."""
+    spec, wl = synthetic_spec(3, 3, 10, 2, 30, sigma_n=1e-1, seed=7)
+    model = product_model_from_spec(spec)
+    xs = particles_near_data(spec, 70, 4)
+    mean, var = model.map_x_dynamics(xs.cuda())
+    Xin, Xout = orc.xin_xout(spec)
+    Kinv = orc.inverse_via_upper_cholesky(orc.x_kernel(spec, Xin, Xin) * orc.class_mask(spec))  # gpmdm.py:1292-1295
+    Ks = orc.x_kernel(spec, Xin, xs, False)
+    mean_o = torch.linalg.multi_dot([Xout.t(), Kinv, Ks]).t()
+    prior = orc.x_diag_kernel(spec, xs)
+    common = prior - torch.sum(torch.matmul(Ks.t(), Kinv) * Ks.t(), dim=1)
+    lam = torch.exp(spec.x_log_lambdas) ** -2
+    var_o = common.unsqueeze(1) * lam.unsqueeze(0)
+    scale = torch.clamp(mean_o.abs().max(dim=1, keepdim=True).values, min=1e-3)
+    assert scaled_err(mean.cpu(), mean_o, scale) < 1e-7
+    assert scaled_err(var.cpu(), var_o, (prior.unsqueeze(1) * lam.unsqueeze(0))) < 1e-7
+    # (the masked-kernel formula can go negative away from a class' data, in the reference as well: clamp for Normal)
+    nxt = model.get_next_x(mean, torch.clamp(var, min=1e-12), xs.cuda())
+    assert torch.equal(nxt, mean)
+    m1, v1, Xo, Xi, nmse = model.get_dynamics_map_performance_for_class(1)
+    assert m1.shape == Xo.shape and np.isfinite(nmse)
+    mu, vy, Y, nmse_y = model.get_latent_map_performance()
+    assert mu.shape == Y.shape and np.isfinite(nmse_y)
