@@ -342,3 +342,75 @@ def test_class_agnostic_dynamics_map_and_helpers():
     assert m1.shape == Xo.shape and np.isfinite(nmse)
     mu, vy, Y, nmse_y = model.get_latent_map_performance()
     assert mu.shape == Y.shape and np.isfinite(nmse_y)
+
+
+@pytest.mark.parametrize("C,d,D", [(2, 8, 35), (2, 1, 5), (3, 2, 300), (2, 5, 257)])
+def test_other_latent_and_observation_dimensions_vs_oracle(C, d, D):
+    """Template instances beyond d = 3/4 (d = 1, 2, 5, 8) and observation widths that need more than one 256-column
+    alpha tile (D = 257, 300): GP predictions and one injected-draw filter step against the oracle."""
+    from gpmdm_b200 import GPMDM_PF
+
+    spec, wl = synthetic_spec(C, d, D, 3, 40, sigma_n=1e-1, seed=13)
+    f = orc.precompute_factors(spec)
+    model = product_model_from_spec(spec, Ky_inv=f.Ky_inv, Kx_inv_blocks=f.Kx_inv_blocks)
+    xs = particles_near_data(spec, 200, 3)
+    mu, var = model.map_x_to_y(xs.cuda())
+    mu_o, var_o, v_o = orc.map_x_to_y(spec, f, xs)
+    scale = torch.clamp(torch.abs(mu_o).max(dim=1, keepdim=True).values, min=1e-3)
+    assert scaled_err(mu.cpu(), mu_o, scale) < TOL
+    lam = (torch.exp(spec.y_log_lambdas) ** -2).unsqueeze(0).expand(var_o.shape)
+    assert scaled_err(var.cpu(), var_o, lam) < TOL
+    lam_x = torch.exp(spec.x_log_lambdas) ** -2
+    for c in range(C):
+        mean, dvar = model.map_x_dynamics_for_class(xs.cuda(), c)
+        mean_o, dvar_o, q, prior = orc.map_x_dynamics_for_class(spec, f, xs, c)
+        sc = torch.clamp(torch.abs(mean_o).max(dim=1, keepdim=True).values, min=1e-3)
+        assert scaled_err(mean.cpu(), mean_o, sc) < TOL
+        assert scaled_err(dvar.cpu(), dvar_o, prior.unsqueeze(1) * lam_x.unsqueeze(0)) < 4 * TOL
+    P = 130
+    T = synthetic.markov_matrix(C)
+    pf = GPMDM_PF(model, T, P, seed=2, cdf_order="sequential")
+    E, eps, u = synthetic.raw_draws(P, C, d, 5)
+    x_prev, c_prev = pf._particle_states.cpu().clone(), pf._particle_classes.cpu().clone()
+    z = wl.test_trials[0][1][0]
+    pf.update(z, draws=(E, eps, u))
+    c_new = orc.transition(c_prev, T.to(torch.float64), E)
+    assert torch.equal(pf.last_pre_resample_classes.cpu(), c_new)
+    x_gpu = pf.last_pre_resample_states.cpu()
+    mu_o, _, v_o = orc.map_x_to_y(spec, f, x_gpu)
+    ll_o = orc.log_likelihoods_fused(mu_o, v_o, t64(z), spec.y_log_lambdas)
+    ok = v_o > 1e-3
+    assert rel_err(pf._log_likelihoods.cpu()[ok], ll_o[ok]) < 1e-6
+    assert torch.equal(pf.last_ancestors.cpu(), orc.resample(pf._weights.cpu(), u))
+
+
+def test_cfg1_readme_trial_150_frames(cfg1):
+    """BASELINE config 1 exactly: 2-class model, d = 3, D = 62, N = 2000, 100 particles, a 150-frame trial with
+    injected draws; every frame checked stage-wise against the oracle (classes / ancestors bit-exact, argmax class
+    identical), the filter itself running free on the CUDA path."""
+    from gpmdm_b200 import GPMDM_PF
+
+    spec, wl, f, model = cfg1
+    C, d, P = spec.n_classes, spec.d, 100
+    trial = synthetic.make_sequences(C, spec.D, 1, 150, seed=77).sequences[1][0]
+    T = synthetic.markov_matrix(C)
+    T64 = T.to(torch.float64)
+    parts = orc.divide_into_n_parts(P, C)
+    g = torch.Generator().manual_seed(10)
+    init_idx = [torch.randint(0, b - a, (parts[c],), generator=g) for c, (a, b) in enumerate(spec.class_row_ranges())]
+    pf = GPMDM_PF(model, T, P, init_indices=init_idx, cdf_order="sequential")
+    for t in range(150):
+        E, eps, u = synthetic.raw_draws(P, C, d, 9000 + t)
+        c_prev = pf._particle_classes.cpu().clone()
+        pf.update(trial[t], draws=(E, eps, u))
+        c_new = orc.transition(c_prev, T64, E)
+        assert torch.equal(pf.last_pre_resample_classes.cpu(), c_new), t
+        x_gpu = pf.last_pre_resample_states.cpu()
+        mu_o, _, v_o = orc.map_x_to_y(spec, f, x_gpu)
+        ll_o = orc.log_likelihoods_fused(mu_o, v_o, t64(trial[t]), spec.y_log_lambdas)
+        assert rel_err(pf._log_likelihoods.cpu(), ll_o) < 1e-6, t
+        lw_o, w_o = orc.normalize(pf._log_likelihoods.cpu())
+        anc_o = orc.resample(pf._weights.cpu(), u)
+        assert torch.equal(pf.last_ancestors.cpu(), anc_o), t
+        cp_o = orc.class_probabilities(pf._log_likelihoods.cpu(), lw_o, c_new[anc_o], C)
+        assert pf.get_most_likely_class() == int(torch.argmax(cp_o)), t
