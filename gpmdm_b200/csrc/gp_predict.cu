@@ -47,7 +47,6 @@ constexpr int TN = GPMDM_TILE_N;  // columns per column tile
 constexpr int KC = 16;            // k rows per chunk
 constexpr int STAGES = 6;         // B / record ring depth (TMA)
 constexpr int AHEAD = 3;          // chunks in flight ahead of the consumers
-constexpr unsigned SKEW_NS = 1300;  // start-up skew between the two warps of a sub-partition (~0.5 chunk)
 constexpr int LDB = TN + 4;
 constexpr int NTHREADS = 256;
 constexpr int NWARPS = NTHREADS / 32;
@@ -282,10 +281,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) gp_predict_kernel(const PredictPa
         cur.init(nq, nct, nkc, prm.tri, ct0);
         double qacc = 0.0, sacc = 0.0, vrow = 0.0;
         if (KIND == 0 && prm.v_in) vrow = pidx >= 0 ? prm.v_in[pidx] : 1.0;
-        // The two warps of an SM sub-partition (w, w + 4) share one fp64 datapath.  Started together they run in
-        // lockstep and stall it together at every chunk boundary / exponential block; a one-off skew of about
-        // half a chunk lets each warp's non-MMA phases hide under the other's DMMAs (ncu: idle 13% -> see profiles/).
-        if (warp >= NWARPS / 2) __nanosleep(SKEW_NS);
 
         for (int ct = ct0; ct < nct; ct++) {
             double acc[NJ][2];

@@ -51,6 +51,30 @@ __device__ __forceinline__ double block_max(double v, double* sh) {
     return out;
 }
 
+// 4 consecutive doubles per thread as two 16-byte accesses (arrays come from the caller 16-byte aligned and `base`
+// is a multiple of 4); the ragged tail of the array falls back to scalar accesses.
+__device__ __forceinline__ void load4(const double* __restrict__ p, long long base, long long n, double (&v)[4],
+                                      double fill) {
+    if (base + 4 <= n) {
+        const double2 a = __ldg(reinterpret_cast<const double2*>(p + base));
+        const double2 b = __ldg(reinterpret_cast<const double2*>(p + base + 2));
+        v[0] = a.x, v[1] = a.y, v[2] = b.x, v[3] = b.y;
+    } else {
+#pragma unroll
+        for (int k = 0; k < 4; k++) v[k] = base + k < n ? p[base + k] : fill;
+    }
+}
+__device__ __forceinline__ void store4(double* __restrict__ p, long long base, long long n, const double (&v)[4]) {
+    if (base + 4 <= n) {
+        *reinterpret_cast<double2*>(p + base) = make_double2(v[0], v[1]);
+        *reinterpret_cast<double2*>(p + base + 2) = make_double2(v[2], v[3]);
+    } else {
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+            if (base + k < n) p[base + k] = v[k];
+    }
+}
+
 // serial, fixed-order combination of per-block partials by one block (n_part <= a few thousand)
 template <bool IS_MAX>
 __global__ void __launch_bounds__(RT) combine_partials_kernel(const double* __restrict__ part, long long n_part,
@@ -91,7 +115,9 @@ __global__ void __launch_bounds__(RB) bucket_count_kernel(const int64_t* __restr
     for (int i = threadIdx.x; i < C; i += blockDim.x) sh_cnt[i] = 0;
     __syncthreads();
     const long long p = (long long)blockIdx.x * RB + threadIdx.x;
-    if (p < P) atomicAdd(&sh_cnt[(int)cls[p]], 1);
+    const int c = p < P ? (int)cls[p] : -1;
+    const unsigned peers = __match_any_sync(0xffffffffu, c);  // one shared-memory atomic per class per warp
+    if (c >= 0 && (peers & ((1u << (threadIdx.x & 31)) - 1u)) == 0) atomicAdd(&sh_cnt[c], __popc(peers));
     __syncthreads();
     for (int i = threadIdx.x; i < C; i += blockDim.x) counts[(long long)i * nb + blockIdx.x] = sh_cnt[i];
 }
@@ -99,32 +125,44 @@ __global__ void __launch_bounds__(RB) bucket_count_kernel(const int64_t* __restr
 __global__ void __launch_bounds__(1024) bucket_scan_kernel(int32_t* __restrict__ counts /*in: counts, out: offsets*/,
                                                            int C, int nb, int32_t* __restrict__ tiles,
                                                            int32_t* __restrict__ n_tiles) {
-    // exclusive scan over the class-major [C][nb] array, chunk by chunk (1024 entries per pass)
-    __shared__ int sh[1024];
+    // exclusive scan over the class-major [C][nb] array, 1024 entries per pass: shuffle scan inside each warp, the 32
+    // warp totals scanned by warp 0, running carry across passes
+    __shared__ int wtot[32];
     __shared__ int carry;
     extern __shared__ int cls_start[];  // [C + 1] class start offsets, then [C + 1] tile starts
     int* tile_start = cls_start + (C + 1);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (threadIdx.x == 0) carry = 0;
     __syncthreads();
     const long long total = (long long)C * nb;
     for (long long base = 0; base < total; base += 1024) {
         const long long i = base + threadIdx.x;
         const int v = i < total ? counts[i] : 0;
-        sh[threadIdx.x] = v;
-        __syncthreads();
-        for (int o = 1; o < 1024; o <<= 1) {
-            const int add = threadIdx.x >= o ? sh[threadIdx.x - o] : 0;
-            __syncthreads();
-            sh[threadIdx.x] += add;
-            __syncthreads();
+        int incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
         }
-        const int excl = carry + sh[threadIdx.x] - v;
+        if (lane == 31) wtot[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            int w = wtot[lane], wi = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, wi, o);
+                if (lane >= o) wi += t;
+            }
+            wtot[lane] = wi - w;  // exclusive prefix of the warp totals
+        }
+        __syncthreads();
+        const int excl = carry + wtot[warp] + incl - v;
         if (i < total) {
             counts[i] = excl;
             if (i % nb == 0) cls_start[i / nb] = excl;
         }
         __syncthreads();
-        if (threadIdx.x == 1023) carry += sh[1023];
+        if (threadIdx.x == 1023) carry = excl + v;
         __syncthreads();
     }
     if (threadIdx.x == 0) {
@@ -182,10 +220,12 @@ __global__ void __launch_bounds__(RT) block_max_kernel(const double* __restrict_
                                                        long long n, double* __restrict__ part) {
     __shared__ double sh[RT / 32 + 1];
     const long long base = (long long)blockIdx.x * RB + threadIdx.x * 4;
+    double va[4], vb[4] = {0.0, 0.0, 0.0, 0.0};
+    load4(a, base, n, va, -INFINITY);
+    if (b) load4(b, base, n, vb, 0.0);
     double v = -INFINITY;
 #pragma unroll
-    for (int k = 0; k < 4; k++)
-        if (base + k < n) v = fmax(v, b ? a[base + k] + b[base + k] : a[base + k]);
+    for (int k = 0; k < 4; k++) v = fmax(v, b ? va[k] + vb[k] : va[k]);
     v = block_max(v, sh);
     if (threadIdx.x == 0) part[blockIdx.x] = v;
 }
@@ -197,22 +237,29 @@ __global__ void __launch_bounds__(RT) exp_sum_kernel(const double* __restrict__ 
     const long long base = (long long)blockIdx.x * RB + threadIdx.x * 4;
     const double m = mx[0];
     double acc = 0.0;
+    double vl[4], l[4], e[4];
+    load4(ll, base, n, vl, -INFINITY);
 #pragma unroll
-    for (int k = 0; k < 4; k++)
-        if (base + k < n) {
-            const double l = ll[base + k] - m;
-            const double e = exp(l);
-            lw[base + k] = l;
-            w[base + k] = e;
-            acc += e;
-        }
+    for (int k = 0; k < 4; k++) {
+        l[k] = vl[k] - m;
+        e[k] = base + k < n ? exp(l[k]) : 0.0;
+        acc += e[k];
+    }
+    store4(lw, base, n, l);
+    store4(w, base, n, e);
     acc = block_sum_fixed(acc, sh);
     if (threadIdx.x == 0) part[blockIdx.x] = acc;
 }
 
 __global__ void divide_kernel(double* __restrict__ w, long long n, const double* __restrict__ total) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) w[i] = w[i] / total[0];
+    const long long base = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (base >= n) return;
+    const double t = total[0];
+    double v[4];
+    load4(w, base, n, v, 0.0);
+#pragma unroll
+    for (int k = 0; k < 4; k++) v[k] = v[k] / t;  // IEEE division, as the reference
+    store4(w, base, n, v);
 }
 
 // ---- cdf ---------------------------------------------------------------------------------------------------
@@ -246,8 +293,7 @@ __global__ void __launch_bounds__(RT) cdf_block_scan_kernel(const double* __rest
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const long long base = (long long)blockIdx.x * RB + threadIdx.x * 4;
     double v[4];
-#pragma unroll
-    for (int k = 0; k < 4; k++) v[k] = base + k < n ? w[base + k] : 0.0;
+    load4(w, base, n, v, 0.0);
     v[1] += v[0];
     v[2] += v[1];
     v[3] += v[2];
@@ -261,30 +307,65 @@ __global__ void __launch_bounds__(RT) cdf_block_scan_kernel(const double* __rest
     __syncthreads();
     double off = incl - v[3];  // exclusive prefix inside the warp
     for (int k = 0; k < warp; k++) off += wsum[k];
+    double o[4];
 #pragma unroll
-    for (int k = 0; k < 4; k++)
-        if (base + k < n) cdf[base + k] = off + v[k];
+    for (int k = 0; k < 4; k++) o[k] = off + v[k];
+    store4(cdf, base, n, o);
     if (threadIdx.x == RT - 1) part[blockIdx.x] = off + v[3];
 }
-// Pass B: serial exclusive scan of block totals (one thread; <= P/1024 entries).
-__global__ void cdf_scan_partials_kernel(double* __restrict__ part, long long nb, double* __restrict__ total) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    double run = 0.0;
-    for (long long i = 0; i < nb; i++) {
-        const double v = part[i];
-        part[i] = run;
-        run += v;
+// Pass B: exclusive scan of the block totals by one block, 1024 entries per pass, in a fixed order (shuffle scan inside
+// each warp, the warp totals scanned by warp 0, running carry) that depends only on the number of blocks.
+__global__ void __launch_bounds__(1024) cdf_scan_partials_kernel(double* __restrict__ part, long long nb,
+                                                                 double* __restrict__ total) {
+    __shared__ double wtot[32];
+    __shared__ double carry;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) carry = 0.0;
+    __syncthreads();
+    for (long long base = 0; base < nb; base += 1024) {
+        const long long i = base + threadIdx.x;
+        const double v = i < nb ? part[i] : 0.0;
+        double incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const double t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) wtot[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            const double w = wtot[lane];
+            double wi = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const double t = __shfl_up_sync(0xffffffffu, wi, o);
+                if (lane >= o) wi += t;
+            }
+            wtot[lane] = wi - w;
+        }
+        __syncthreads();
+        const double excl = carry + (wtot[warp] + (incl - v));
+        if (i < nb) part[i] = excl;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = excl + v;
+        __syncthreads();
     }
-    total[0] = run;
+    if (threadIdx.x == 0) total[0] = carry;
 }
 // Pass C: add the block prefix, divide by the total, force the last entry to 1.
 __global__ void cdf_finish_kernel(double* __restrict__ cdf, long long n, const double* __restrict__ part,
                                   const double* __restrict__ total) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    double v = cdf[i];
-    if (part) v = part[i / RB] + v;
-    cdf[i] = (i == n - 1) ? 1.0 : v / total[0];
+    const long long base = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;  // 4 | RB: one block prefix
+    if (base >= n) return;
+    const double t = total[0], pre = part ? part[base / RB] : 0.0;
+    double v[4];
+    load4(cdf, base, n, v, 0.0);
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const double x = part ? pre + v[k] : v[k];
+        v[k] = (base + k == n - 1) ? 1.0 : x / t;
+    }
+    store4(cdf, base, n, v);
 }
 
 // ---- resampling search + gather -----------------------------------------------------------------------------
@@ -295,10 +376,22 @@ __global__ void resample_kernel(const double* __restrict__ cdf, long long P, con
     const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n_out) return;
     const double us = u[s];
-    long long left = 0, right = P;  // ATen MultinomialKernel.cpp binary search: first j with cdf[j] >= u
+    // first j with cdf[j] >= u -- the answer of ATen's binary search (MultinomialKernel.cpp) for a monotone cdf.
+    // Two levels so that most probes hit cache: the last entry of every 1024-element block (a strided, L2-resident
+    // subset), then inside one 8 KB block.
+    const long long nblk = (P + RB - 1) / RB;
+    long long lo = 0, hi = nblk;  // first block whose last entry is >= u
+    while (hi - lo > 0) {
+        const long long mid = lo + (hi - lo) / 2;
+        const long long e = (mid + 1) * RB - 1;
+        if (__ldg(cdf + (e < P ? e : P - 1)) < us) lo = mid + 1;
+        else hi = mid;
+    }
+    long long left = lo * RB, right = (lo + 1) * RB < P ? (lo + 1) * RB : P;
+    if (lo >= nblk) left = right = P;
     while (right - left > 0) {
         const long long mid = left + (right - left) / 2;
-        if (cdf[mid] < us) left = mid + 1;
+        if (__ldg(cdf + mid) < us) left = mid + 1;
         else right = mid;
     }
     if (left >= P) left = P - 1;
@@ -320,13 +413,15 @@ __global__ void __launch_bounds__(RT) summaries_block_kernel(const double* __res
     __shared__ double sh[RT / 32 + 1];
     const long long base = (long long)blockIdx.x * RB + threadIdx.x * 4;
     const double m = gmax[0];
-    double e[4], ww[4];
+    double e[4], ww[4], vll[4], vlw[4];
     int cc[4];
+    load4(ll, base, n, vll, 0.0);
+    load4(lw, base, n, vlw, 0.0);
+    load4(w, base, n, ww, 0.0);
 #pragma unroll
     for (int k = 0; k < 4; k++) {
         const bool ok = base + k < n;
-        e[k] = ok ? exp((ll[base + k] + lw[base + k]) - m) : 0.0;
-        ww[k] = ok ? w[base + k] : 0.0;
+        e[k] = ok ? exp((vll[k] + vlw[k]) - m) : 0.0;
         cc[k] = ok ? (int)c_post[base + k] : -1;
     }
     double* out = part + (long long)blockIdx.x * (C + d + 1);
@@ -485,7 +580,7 @@ extern "C" int gpmdm_pf_normalize_f64(const double* ll, int64_t P, double* lw, d
     combine_partials_kernel<true><<<1, RT, 0, st>>>(part, nb, scal);
     exp_sum_kernel<<<nb, RT, 0, st>>>(ll, P, scal, lw, w, part);
     combine_partials_kernel<false><<<1, RT, 0, st>>>(part, nb, scal + 1);
-    divide_kernel<<<nblocks(P, 256), 256, 0, st>>>(w, P, scal + 1);
+    divide_kernel<<<nblocks(P, 1024), 256, 0, st>>>(w, P, scal + 1);
     if (stats_out) {
         cudaError_t e = cudaMemcpyAsync(stats_out, scal, 16, cudaMemcpyDeviceToDevice, st);
         GPMDM_REQUIRE(e == cudaSuccess, (int)e, "cudaMemcpyAsync: %s", cudaGetErrorString(e));
@@ -503,12 +598,12 @@ extern "C" int gpmdm_pf_cdf_f64(const double* w, int64_t P, int32_t mode, double
     double* part = reinterpret_cast<double*>(static_cast<char*>(workspace) + 256);
     if (mode == 0) {
         cdf_sequential_kernel<<<1, 32, 0, st>>>(w, P, cdf, scal);
-        cdf_finish_kernel<<<nblocks(P, 256), 256, 0, st>>>(cdf, P, nullptr, scal);
+        cdf_finish_kernel<<<nblocks(P, 1024), 256, 0, st>>>(cdf, P, nullptr, scal);
     } else {
         const int nb = nblocks(P, RB);
         cdf_block_scan_kernel<<<nb, RT, 0, st>>>(w, P, cdf, part);
-        cdf_scan_partials_kernel<<<1, 32, 0, st>>>(part, nb, scal);
-        cdf_finish_kernel<<<nblocks(P, 256), 256, 0, st>>>(cdf, P, part, scal);
+        cdf_scan_partials_kernel<<<1, 1024, 0, st>>>(part, nb, scal);
+        cdf_finish_kernel<<<nblocks(P, 1024), 256, 0, st>>>(cdf, P, part, scal);
     }
     return check_launch("cdf");
 }
