@@ -43,6 +43,11 @@ _SIGNATURES = {
                                             _ptr, _ptr]),
     "gpmdm_pf_loglik_f64": (ctypes.c_int, [ctypes.POINTER(GpModel), _ptr, _i64, _ptr, _f64, _ptr, _ptr, _ptr, _ptr,
                                            _ptr]),
+    "gpmdm_predict_lowlat_workspace_bytes": (_i64, [_i64, _i64, _i32]),
+    "gpmdm_pf_observe_lowlat_f64": (ctypes.c_int, [ctypes.POINTER(GpModel), _ptr, _i64, _ptr, _f64, _ptr, _ptr, _ptr,
+                                                   _ptr, _i64, _ptr, _ptr, _ptr]),
+    "gpmdm_pf_propagate_lowlat_f64": (ctypes.c_int, [ctypes.POINTER(GpModel), _ptr, _ptr, _ptr, _ptr, _i64, _ptr, _ptr,
+                                                     _ptr, _ptr, _i64, _ptr, _ptr, _ptr]),
     "gpmdm_pf_normalize_f64": (ctypes.c_int, [_ptr, _i64, _ptr, _ptr, _ptr, _ptr, _ptr]),
     "gpmdm_pf_cdf_f64": (ctypes.c_int, [_ptr, _i64, _i32, _ptr, _ptr, _ptr]),
     "gpmdm_pf_resample_f64": (ctypes.c_int, [_ptr, _i64, _ptr, _i64, _ptr, _ptr, _i32, _ptr, _ptr, _ptr, _ptr]),

@@ -67,6 +67,10 @@ struct PredictParams {
     const int32_t* n_tiles;
     long long P;
     int32_t* counter;
+    // low-latency (split) mode: one work item per (particle tile, column tile); partial results go to the workspace
+    int split, max_nct;
+    double* qpart;  // [max_nct][P] per-column-tile contributions to k^T L k
+    double* mu_ws;  // [P][dout] means
     // dynamics epilogue
     const double* eps;
     double* x_new;
@@ -194,12 +198,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) gp_predict_kernel(const PredictPa
     const int total_tiles = prm.tiles ? *prm.n_tiles : (int)((prm.P + TM - 1) / TM);
     uint32_t g = 0;  // chunks consumed so far by this CTA (ring position and mbarrier parity)
 
+    const int total_items = prm.split ? total_tiles * prm.max_nct : total_tiles;
     for (;;) {
         if (tid == 0) s.tile = atomicAdd(prm.counter, 1);
         __syncthreads();
-        const int t = s.tile;
+        const int item = s.tile;
         __syncthreads();
-        if (t >= total_tiles) break;
+        if (item >= total_items) break;
+        // split mode: items are ordered column tile first, so the longest (ct = 0 of every particle tile) start first
+        const int t = prm.split ? item % total_tiles : item;
+        const int item_ct = prm.split ? item / total_tiles : -1;
         int blk = 0, first = t * TM, count;
         if (prm.tiles) {
             blk = prm.tiles[4 * t + 0];
@@ -215,6 +223,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) gp_predict_kernel(const PredictPa
         const int nq = n_pad / TN;               // column tiles of L
         const int nct = nq + prm.alpha_ld / TN;  // + column tiles of alpha
         const int ct0 = (KIND == 0 && prm.v_in) ? nq : 0;  // mean-only mode starts at the alpha tiles
+        int ct_begin = ct0, ct_end = nct;
+        if (prm.split) {
+            if (item_ct < ct0 || item_ct >= nct) continue;  // this block has fewer column tiles (uniform for the CTA)
+            ct_begin = item_ct;
+            ct_end = item_ct + 1;
+        }
 
         // ---- this lane's particle row --------------------------------------------------------------------
         ParticleRec<KIND, DL> pr;
@@ -239,7 +253,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gp_predict_kernel(const PredictPa
 
         // ---- TMA issue: all warps advance the same cursor, the duty warp issues ------------------------------
         ChunkCursor bcur;
-        bcur.init(nq, nct, nkc, prm.tri, ct0);
+        bcur.init(nq, ct_end, nkc, prm.tri, ct_begin);
         uint32_t gb = g;  // ring position of the next chunk to issue
         auto issue_b = [&]() {
             const int st = (int)(gb % STAGES);
@@ -278,11 +292,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) gp_predict_kernel(const PredictPa
         }
 
         ChunkCursor cur;
-        cur.init(nq, nct, nkc, prm.tri, ct0);
+        cur.init(nq, ct_end, nkc, prm.tri, ct_begin);
         double qacc = 0.0, sacc = 0.0, vrow = 0.0;
         if (KIND == 0 && prm.v_in) vrow = pidx >= 0 ? prm.v_in[pidx] : 1.0;
 
-        for (int ct = ct0; ct < nct; ct++) {
+        for (int ct = ct_begin; ct < ct_end; ct++) {
             double acc[NJ][2];
 #pragma unroll
             for (int j = 0; j < NJ; j++) acc[j][0] = acc[j][1] = 0.0;
@@ -301,7 +315,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gp_predict_kernel(const PredictPa
         }                                                                                                        \
         /* The next chunk provides the records for the next A fragments.  After the last chunk of the          \
            particle tile the fragments are recomputed from the current stage (values unused). */                 \
-        const bool has_next = !(ct == nct - 1 && k == nkc - 1);                                                  \
+        const bool has_next = !(ct == ct_end - 1 && k == nkc - 1);                                               \
         const int stn = has_next ? (int)((g + 1) % STAGES) : st;                                                 \
         if (has_next) mbar_wait(&s.full[stn], ((g + 1) / STAGES) & 1);                                           \
         double an[KC / 4];                                                                                       \
@@ -352,7 +366,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) gp_predict_kernel(const PredictPa
                     qacc = fma(acc[j][0], k0, qacc);
                     qacc = fma(acc[j][1], k1, qacc);
                 }
-                if (ct == nq - 1) {
+                if (prm.split) {
+                    double v = qacc;
+                    v += __shfl_xor_sync(0xffffffffu, v, 1);
+                    v += __shfl_xor_sync(0xffffffffu, v, 2);
+                    if (c == 0 && pidx >= 0) prm.qpart[(long long)ct * prm.P + pidx] = v;
+                } else if (ct == nq - 1) {
                     // quadratic form complete: v[p] = prior[p] - q[p]
                     double v = qacc;
                     v += __shfl_xor_sync(0xffffffffu, v, 1);
@@ -368,7 +387,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) gp_predict_kernel(const PredictPa
                         const int col = cbase + j * 8 + c * 2 + e;
                         if (col >= prm.dout) continue;
                         const double mu = acc[j][e];
-                        if (KIND == 0) {
+                        if (prm.split) {  // finished by predict_finalize_kernel
+                            if (pidx >= 0) prm.mu_ws[(long long)pidx * prm.dout + col] = mu;
+                        } else if (KIND == 0) {
                             if (prm.z) {
                                 const double dz = __ldg(prm.z + col) - mu;
                                 sacc = fma(__ldg(prm.scale + col) * dz, dz, sacc);
@@ -384,7 +405,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gp_predict_kernel(const PredictPa
                         }
                     }
                 }
-                if (KIND == 0 && ct == nct - 1) {
+                if (KIND == 0 && !prm.split && ct == nct - 1) {
                     double S = sacc;
                     S += __shfl_xor_sync(0xffffffffu, S, 1);
                     S += __shfl_xor_sync(0xffffffffu, S, 2);
@@ -394,6 +415,46 @@ __global__ void __launch_bounds__(NTHREADS, 1) gp_predict_kernel(const PredictPa
                     }
                 }
             }
+        }
+    }
+}
+
+// Low-latency mode, second kernel: one thread per particle adds the per-column-tile contributions in a fixed order and
+// runs the epilogue the fused kernel would have run (log-likelihood, or the Gaussian draw).
+template <int KIND>
+__global__ void predict_finalize_kernel(const PredictParams prm, int max_nq) {
+    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= prm.P) return;
+    const int d = prm.d;
+    double q = 0.0;
+    for (int ct = 0; ct < max_nq; ct++) q += prm.qpart[(long long)ct * prm.P + p];
+    const double* mu = prm.mu_ws + p * prm.dout;
+    if (KIND == 0) {
+        const double v = prm.v_in ? prm.v_in[p] : 1.0 - q;
+        double S = 0.0;
+        for (int j = 0; j < prm.dout; j++) {
+            if (prm.z) {
+                const double dz = prm.z[j] - mu[j];
+                S = fma(prm.scale[j] * dz, dz, S);
+            }
+            if (prm.mu_out) prm.mu_out[p * prm.dout + j] = mu[j];
+        }
+        if (prm.ll) prm.ll[p] = -0.5 * S / v - (double)prm.dout * log(v) + prm.ll_const;
+        if (prm.v_out) prm.v_out[p] = v;
+    } else {
+        double prior = 1.0;
+        for (int j = 0; j < d; j++) {
+            const double xj = prm.x[p * d + j];
+            prior = fma(prm.lin_c2[j] * xj, xj, prior);
+        }
+        prior += prm.lin_c2[d];
+        const double v = prior - q;
+        for (int k = 0; k < prm.dout; k++) {
+            const double var = v * prm.scale[k];
+            const long long o = p * prm.dout + k;
+            if (prm.x_new) prm.x_new[o] = __dadd_rn(__dmul_rn(prm.eps[o], sqrt(var)), mu[k]);
+            if (prm.mean_out) prm.mean_out[o] = mu[k];
+            if (prm.var_out) prm.var_out[o] = var;
         }
     }
 }
@@ -543,4 +604,78 @@ static int observe_impl(const gpmdm_gp_model* obs, const double* x, int64_t P, c
     const long long n_tiles = (P + TM - 1) / TM;
     const int grid = (int)(n_tiles < num_sms() ? n_tiles : num_sms());
     return dispatch_d<0>(prm, grid, st);
+}
+
+// ---- low-latency variants: when there are fewer particle tiles than SMs, split every tile's column tiles over CTAs ----
+extern "C" int64_t gpmdm_predict_lowlat_workspace_bytes(int64_t P, int64_t max_n_pad, int32_t dout) {
+    return (max_n_pad / TN) * P * 8 + P * (int64_t)dout * 8;
+}
+
+template <int KIND>
+static int run_split(PredictParams& prm, int64_t max_n_pad, void* workspace, cudaStream_t st) {
+    GPMDM_REQUIRE(workspace != nullptr && max_n_pad > 0 && max_n_pad % TN == 0, GPMDM_E_INVALID,
+                  "low-latency mode needs a workspace and max_n_pad (multiple of %d)", TN);
+    const int max_nq = (int)(max_n_pad / TN);
+    prm.split = 1;
+    prm.max_nct = max_nq + prm.alpha_ld / TN;
+    prm.qpart = static_cast<double*>(workspace);
+    prm.mu_ws = prm.qpart + (long long)max_nq * prm.P;
+    cudaError_t e = cudaMemsetAsync(prm.qpart, 0, (size_t)max_nq * prm.P * 8, st);
+    GPMDM_REQUIRE(e == cudaSuccess, (int)e, "cudaMemsetAsync: %s", cudaGetErrorString(e));
+    e = cudaMemsetAsync(prm.counter, 0, sizeof(int32_t), st);
+    GPMDM_REQUIRE(e == cudaSuccess, (int)e, "cudaMemsetAsync: %s", cudaGetErrorString(e));
+    const long long items = ((prm.P + TM - 1) / TM + prm.n_blocks) * prm.max_nct;
+    const int grid = (int)(items < num_sms() ? items : num_sms());
+    if (int rc = dispatch_d<KIND>(prm, grid, st)) return rc;
+    predict_finalize_kernel<KIND><<<(unsigned)((prm.P + 127) / 128), 128, 0, st>>>(prm, max_nq);
+    return check_launch("predict_finalize_kernel");
+}
+
+extern "C" int gpmdm_pf_observe_lowlat_f64(const gpmdm_gp_model* obs, const double* x, int64_t P, const double* z,
+                                           double ll_const, const double* v_in, double* ll, double* mu_out,
+                                           double* v_out, int64_t max_n_pad, int32_t* tile_counter, void* workspace,
+                                           void* stream) {
+    if (int rc = validate_model(obs, 0)) return rc;
+    GPMDM_REQUIRE(P >= 0 && P < (1ll << 31), GPMDM_E_INVALID, "P = %lld out of range", (long long)P);
+    if (P == 0) return 0;
+    GPMDM_REQUIRE(x && tile_counter, GPMDM_E_INVALID, "null argument");
+    GPMDM_REQUIRE(ll == nullptr || z != nullptr, GPMDM_E_INVALID, "ll requested without z");
+    GPMDM_REQUIRE(obs->n_blocks == 1, GPMDM_E_INVALID, "observation GP has exactly one block");
+    PredictParams prm;
+    fill_common(prm, obs);
+    prm.x = x;
+    prm.P = P;
+    prm.counter = tile_counter;
+    prm.z = z;
+    prm.v_in = v_in;
+    prm.ll_const = ll_const;
+    prm.ll = ll;
+    prm.mu_out = mu_out;
+    prm.v_out = v_out;
+    return run_split<0>(prm, max_n_pad, workspace, (cudaStream_t)stream);
+}
+
+extern "C" int gpmdm_pf_propagate_lowlat_f64(const gpmdm_gp_model* dyn, const double* x_prev, const int32_t* perm,
+                                             const int32_t* tiles, const int32_t* n_tiles, int64_t P, const double* eps,
+                                             double* x_new, double* mean_out, double* var_out, int64_t max_n_pad,
+                                             int32_t* tile_counter, void* workspace, void* stream) {
+    if (int rc = validate_model(dyn, 1)) return rc;
+    GPMDM_REQUIRE(P >= 0 && P < (1ll << 31), GPMDM_E_INVALID, "P = %lld out of range", (long long)P);
+    if (P == 0) return 0;
+    GPMDM_REQUIRE(x_prev && perm && tiles && n_tiles && tile_counter, GPMDM_E_INVALID, "null argument");
+    GPMDM_REQUIRE(x_new == nullptr || eps != nullptr, GPMDM_E_INVALID, "x_new requested without eps");
+    GPMDM_REQUIRE(dyn->dout == dyn->d, GPMDM_E_INVALID, "dynamics GP must have dout == d");
+    PredictParams prm;
+    fill_common(prm, dyn);
+    prm.x = x_prev;
+    prm.perm = perm;
+    prm.tiles = tiles;
+    prm.n_tiles = n_tiles;
+    prm.P = P;
+    prm.counter = tile_counter;
+    prm.eps = eps;
+    prm.x_new = x_new;
+    prm.mean_out = mean_out;
+    prm.var_out = var_out;
+    return run_split<1>(prm, max_n_pad, workspace, (cudaStream_t)stream);
 }

@@ -487,7 +487,8 @@ class GPMDM(torch.nn.Module):
             dyn = model(dblks, self.d, self.d, TILE_N, 1, ls_x, c2, lam_x)
         else:
             dyn = None
-        self._packed = dict(tri=tri, obs=obs, obs_has_L=with_obs_L, dyn=dyn, keep=keep,
+        self._packed = dict(tri=tri, obs=obs, obs_has_L=with_obs_L, dyn=dyn, keep=keep, obs_n_pad=oblk["n_pad"],
+                            dyn_max_n_pad=max(b["n_pad"] for b in dblks) if dyn is not None else 0,
                             ll_const_terms=(2.0 * torch.sum(self.y_log_lambdas.detach())).item())
         return self._packed
 
@@ -521,6 +522,19 @@ class GPMDM(torch.nn.Module):
                                  ll_const_terms=(2.0 * torch.sum(self.y_log_lambdas.detach())).item())
         return self._packed_tf32
 
+    LOWLAT_MAX_TILES = 110  # below this many 64-particle tiles (of 148 SMs) the column tiles are split over CTAs
+
+    def _use_lowlat(self, P, low_latency):
+        return ((P + TILE_P - 1) // TILE_P <= self.LOWLAT_MAX_TILES) if low_latency is None else bool(low_latency)
+
+    def _lowlat_workspace(self, P, max_n_pad, dout):
+        lib = _cabi.lib()
+        need = int(lib.gpmdm_predict_lowlat_workspace_bytes(P, max_n_pad, dout)) // 8 + 1
+        ws = getattr(self, "_lowlat_ws", None)
+        if ws is None or ws.numel() < need:
+            self._lowlat_ws = ws = torch.empty(need, dtype=torch.float64, device=self.device)
+        return ws
+
     # ---- prediction (gpmdm.py:923-963, 1032-1068) ----------------------------------------------------------
     def _scratch_counter(self):
         if getattr(self, "_counter", None) is None:
@@ -528,8 +542,9 @@ class GPMDM(torch.nn.Module):
         return self._counter
 
     @torch.no_grad()
-    def map_x_to_y(self, Xstar, flg_noise=False, precision="fp64"):
-        """precision: 'fp64' (exact path, DMMA) or 'tf32' (tcgen05 variant, ~1e-4 relative; an addition)."""
+    def map_x_to_y(self, Xstar, flg_noise=False, precision="fp64", low_latency=None):
+        """precision: 'fp64' (exact path, DMMA) or 'tf32' (tcgen05 variant, ~1e-4 relative; an addition).
+        low_latency: None = automatic (few particles: split the column tiles over the SMs), True / False to force."""
         lib = _cabi.lib()
         Xs = to_tensor(Xstar, self.dtype, self.device).contiguous()
         P = Xs.shape[0]
@@ -547,8 +562,14 @@ class GPMDM(torch.nn.Module):
                                             stream()), "gpmdm_pf_observe_tf32")
         elif precision == "fp64":
             pk = self.packed_models()
-            check(lib.gpmdm_pf_observe_f64(ctypes.byref(pk["obs"]), ptr(Xs), P, None, 0.0, None, ptr(mu), ptr(v),
-                                           ptr(self._scratch_counter()), stream()), "gpmdm_pf_observe_f64")
+            if P > 0 and self._use_lowlat(P, low_latency):
+                ws = self._lowlat_workspace(P, pk["obs_n_pad"], self.D)
+                check(lib.gpmdm_pf_observe_lowlat_f64(ctypes.byref(pk["obs"]), ptr(Xs), P, None, 0.0, None, None, ptr(mu),
+                                                      ptr(v), pk["obs_n_pad"], ptr(self._scratch_counter()), ptr(ws),
+                                                      stream()), "gpmdm_pf_observe_lowlat_f64")
+            else:
+                check(lib.gpmdm_pf_observe_f64(ctypes.byref(pk["obs"]), ptr(Xs), P, None, 0.0, None, ptr(mu), ptr(v),
+                                               ptr(self._scratch_counter()), stream()), "gpmdm_pf_observe_f64")
         else:
             raise ValueError("precision must be 'fp64' or 'tf32'")
         if flg_noise:
@@ -557,7 +578,7 @@ class GPMDM(torch.nn.Module):
         return mu + torch.tensor(self.meanY, dtype=self.dtype, device=self.device), var
 
     @torch.no_grad()
-    def map_x_dynamics_for_class(self, Xstar, class_index: int, flg_noise=False):
+    def map_x_dynamics_for_class(self, Xstar, class_index: int, flg_noise=False, low_latency=None):
         lib = _cabi.lib()
         pk = self.packed_models()
         if pk["dyn"] is None:
@@ -574,9 +595,16 @@ class GPMDM(torch.nn.Module):
         tiles = torch.stack([torch.full_like(t, class_index), t * TILE_P, torch.clamp(P - t * TILE_P, max=TILE_P),
                              torch.zeros_like(t)], 1).contiguous()
         n_tiles = torch.tensor([nt], dtype=torch.int32, device=self.device)
-        check(lib.gpmdm_pf_propagate_f64(ctypes.byref(pk["dyn"]), ptr(Xs), ptr(perm), ptr(tiles), ptr(n_tiles), P, None,
-                                         None, ptr(mean), ptr(var), ptr(self._scratch_counter()), stream()),
-              "gpmdm_pf_propagate_f64")
+        if self._use_lowlat(P, low_latency):
+            ws = self._lowlat_workspace(P, pk["dyn_max_n_pad"], self.d)
+            check(lib.gpmdm_pf_propagate_lowlat_f64(ctypes.byref(pk["dyn"]), ptr(Xs), ptr(perm), ptr(tiles), ptr(n_tiles),
+                                                    P, None, None, ptr(mean), ptr(var), pk["dyn_max_n_pad"],
+                                                    ptr(self._scratch_counter()), ptr(ws), stream()),
+                  "gpmdm_pf_propagate_lowlat_f64")
+        else:
+            check(lib.gpmdm_pf_propagate_f64(ctypes.byref(pk["dyn"]), ptr(Xs), ptr(perm), ptr(tiles), ptr(n_tiles), P,
+                                             None, None, ptr(mean), ptr(var), ptr(self._scratch_counter()), stream()),
+                  "gpmdm_pf_propagate_f64")
         if flg_noise:
             var = var + (torch.exp(self.x_log_sigma_n) ** 2 + self.sigma_n_num_X ** 2) \
                 * (torch.exp(self.x_log_lambdas) ** -2).unsqueeze(0)

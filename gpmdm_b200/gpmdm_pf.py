@@ -47,7 +47,8 @@ class GPMDM_PF:
 
     def __init__(self, gpmdm: GPMDM, markov_switching_model, num_particles: int, *,
                  seed: int = 0, resampling: str = "multinomial", cdf_order: str = "sequential",
-                 tri: bool = True, precision: str = "fp64", init_indices: Optional[Sequence] = None, process_group=None,
+                 tri: bool = True, precision: str = "fp64", low_latency: Optional[bool] = None,
+                 init_indices: Optional[Sequence] = None, process_group=None,
                  distributed: Optional[bool] = None):
         """
         gpmdm, markov_switching_model [C, C], num_particles: as the reference (:47-50).
@@ -58,6 +59,8 @@ class GPMDM_PF:
         tri             use the triangular packing of K^-1 (half the flops of the dense quadratic form)
         precision       'fp64' (exact path) or 'tf32': observation GP on tcgen05 tensor cores with error-compensated
                         tf32 products and the whitened variance (~1e-4 relative); dynamics / resampling stay fp64
+        low_latency     None = automatic: with fewer 64-particle tiles than SMs the column tiles of each particle tile are
+                        split over the SMs (two kernels per GP stage instead of one); True / False to force
         init_indices    optional per-class index tensors replacing torch.randint in _init_particles (:113)
         """
         self._lib = _cabi.lib()
@@ -90,6 +93,7 @@ class GPMDM_PF:
         self._packed_tf32 = gpmdm.packed_model_tf32() if precision == "tf32" else None
         c32 = float(0.5 * self._gpmdm.D * _LOG_2PI)  # fp32 product, as gpmdm_pf.py:191
         self._ll_const = self._packed["ll_const_terms"] - c32
+        self._lowlat = gpmdm._use_lowlat(self._hi - self._lo, low_latency)
         self._alloc()
         self._init_particles(init_indices)
 
@@ -110,6 +114,10 @@ class GPMDM_PF:
         self._summary_step = -1
         ws = int(self._lib.gpmdm_workspace_bytes(P, C))
         self._ws = torch.empty(ws // 8 + 1, dtype=torch.float64, device=dev)
+        if self._lowlat:
+            need = max(int(self._lib.gpmdm_predict_lowlat_workspace_bytes(Pl, self._packed["obs_n_pad"], self.observation_dim)),
+                       int(self._lib.gpmdm_predict_lowlat_workspace_bytes(Pl, self._packed["dyn_max_n_pad"], d)))
+            self._ws_lowlat = torch.empty(need // 8 + 1, dtype=torch.float64, device=dev)
 
     # ---- initialisation (gpmdm_pf.py:87-115) -------------------------------------------------------------------
     def _init_particles(self, init_indices=None):
@@ -172,9 +180,15 @@ class GPMDM_PF:
               "gpmdm_pf_transition_f64")
         check(lib.gpmdm_pf_bucket_by_class(ptr(c_new_l), Pl, C, ptr(self._perm), ptr(self._tiles), ptr(self._n_tiles),
                                            ptr(self._ws), st), "gpmdm_pf_bucket_by_class")
-        check(lib.gpmdm_pf_propagate_f64(ctypes.byref(self._packed["dyn"]), ptr(x_prev), ptr(self._perm), ptr(self._tiles),
-                                         ptr(self._n_tiles), Pl, ptr(eps), ptr(x_new_l), None, None, ptr(self._counter),
-                                         st), "gpmdm_pf_propagate_f64")
+        if self._lowlat:
+            check(lib.gpmdm_pf_propagate_lowlat_f64(ctypes.byref(self._packed["dyn"]), ptr(x_prev), ptr(self._perm),
+                                                    ptr(self._tiles), ptr(self._n_tiles), Pl, ptr(eps), ptr(x_new_l), None,
+                                                    None, self._packed["dyn_max_n_pad"], ptr(self._counter),
+                                                    ptr(self._ws_lowlat), st), "gpmdm_pf_propagate_lowlat_f64")
+        else:
+            check(lib.gpmdm_pf_propagate_f64(ctypes.byref(self._packed["dyn"]), ptr(x_prev), ptr(self._perm),
+                                             ptr(self._tiles), ptr(self._n_tiles), Pl, ptr(eps), ptr(x_new_l), None, None,
+                                             ptr(self._counter), st), "gpmdm_pf_propagate_f64")
         prof = getattr(self, "_profile_events", None)
         if prof is not None:  # bench.py: CUDA events around the dominant kernel, on the launching stream
             ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
@@ -186,6 +200,11 @@ class GPMDM_PF:
             check(lib.gpmdm_pf_loglik_f64(ctypes.byref(self._packed["obs"]), ptr(x_new_l), Pl, ptr(z), self._ll_const,
                                           ptr(self._v_buf), ptr(ll_l), None, ptr(self._counter), st),
                   "gpmdm_pf_loglik_f64")
+        elif self._lowlat:
+            check(lib.gpmdm_pf_observe_lowlat_f64(ctypes.byref(self._packed["obs"]), ptr(x_new_l), Pl, ptr(z),
+                                                  self._ll_const, None, ptr(ll_l), None, None, self._packed["obs_n_pad"],
+                                                  ptr(self._counter), ptr(self._ws_lowlat), st),
+                  "gpmdm_pf_observe_lowlat_f64")
         else:
             check(lib.gpmdm_pf_observe_f64(ctypes.byref(self._packed["obs"]), ptr(x_new_l), Pl, ptr(z), self._ll_const,
                                            ptr(ll_l), None, None, ptr(self._counter), st), "gpmdm_pf_observe_f64")
@@ -214,7 +233,8 @@ class GPMDM_PF:
     def launches_per_step(self) -> int:
         """Kernels of libgpmdm_sm100a.so launched by one update() + one query (device-draw mode)."""
         draws, transition, bucket, propagate, normalize, resample, summaries = 2, 1, 3, 1, 5, 1, 4
-        observe = 2 if self._precision == "tf32" else 1
+        observe = 2 if (self._precision == "tf32" or self._lowlat) else 1
+        propagate = 2 if self._lowlat else 1
         cdf = 2 if self._cdf_mode == 0 else 3
         return draws + transition + bucket + propagate + observe + normalize + cdf + resample + summaries
 

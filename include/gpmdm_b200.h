@@ -127,6 +127,20 @@ int gpmdm_pf_observe_f64(const gpmdm_gp_model* obs, const double* x, int64_t P, 
 int gpmdm_pf_loglik_f64(const gpmdm_gp_model* obs, const double* x, int64_t P, const double* z, double ll_const,
                         const double* v_in, double* ll, double* mu_out, int32_t* tile_counter, void* stream);
 
+/* Low-latency variants for small particle counts (fewer 64-particle tiles than SMs, e.g. the reference's README setup
+ * with 100 particles): every (particle tile, 256-column tile) pair is a separate work item, the per-column-tile
+ * contributions to k^T L k are added in a fixed order by a second kernel that also runs the epilogue.  Same results
+ * contract as the fused calls; the summation order of the quadratic form differs (still deterministic).
+ * max_n_pad: largest n_pad over the model's blocks.  workspace: gpmdm_predict_lowlat_workspace_bytes(P, max_n_pad, dout). */
+int64_t gpmdm_predict_lowlat_workspace_bytes(int64_t P, int64_t max_n_pad, int32_t dout);
+int gpmdm_pf_observe_lowlat_f64(const gpmdm_gp_model* obs, const double* x, int64_t P, const double* z, double ll_const,
+                                const double* v_in, double* ll, double* mu_out, double* v_out, int64_t max_n_pad,
+                                int32_t* tile_counter, void* workspace, void* stream);
+int gpmdm_pf_propagate_lowlat_f64(const gpmdm_gp_model* dyn, const double* x_prev, const int32_t* perm,
+                                  const int32_t* tiles, const int32_t* n_tiles, int64_t P, const double* eps,
+                                  double* x_new, double* mean_out, double* var_out, int64_t max_n_pad,
+                                  int32_t* tile_counter, void* workspace, void* stream);
+
 /* GPMDM_PF._update_weights (second half, gpmdm_pf.py:200-204): lw = ll - max(ll); w = exp(lw)/sum.
  * Reductions run in a fixed blocked order independent of the GPU count.  stats_out [2] = {max, sum}. */
 int gpmdm_pf_normalize_f64(const double* ll, int64_t P, double* lw, double* w, double* stats_out,

@@ -26,14 +26,15 @@ def dev(a, dtype=torch.float64):
     return torch.as_tensor(np.asarray(a)).to("cuda", dtype).contiguous()
 
 
+@pytest.mark.parametrize("low_latency", [False, True])
 @pytest.mark.parametrize("tri", [True, False])
-def test_map_x_to_y_matches_reference(case, tri):
+def test_map_x_to_y_matches_reference(case, tri, low_latency):
     g, model = case
     model._packed = None
     model.packed_models(tri)
     s = g.step(0)
     x_ref = t64(s["eps"]) * t64(s["dyn_std"]) + t64(s["dyn_mean"])
-    mu, var = model.map_x_to_y(x_ref.cuda())
+    mu, var = model.map_x_to_y(x_ref.cuda(), low_latency=low_latency)
     scale = torch.clamp(torch.abs(t64(s["mu"])).max(dim=1, keepdim=True).values, min=1e-3)
     assert scaled_err(mu.cpu(), s["mu"], scale) < TOL
     lam = (torch.exp(g.spec.y_log_lambdas) ** -2).unsqueeze(0).expand(var.shape)
@@ -60,13 +61,14 @@ def test_map_x_dynamics_for_class_matches_reference(case):
         assert scaled_err(var.cpu(), ref_var, prior) < TOL
 
 
-def test_filter_stagewise_against_reference(case):
+@pytest.mark.parametrize("low_latency", [False, True])
+def test_filter_stagewise_against_reference(case, low_latency):
     """Drive the product filter with the reference's draws; before every step force its state to the
     reference's state, so each step is a stage-wise comparison."""
     from gpmdm_b200 import GPMDM_PF
 
     g, model = case
-    pf = GPMDM_PF(model, g.T, g.P, init_indices=g.init_idx, cdf_order="sequential")
+    pf = GPMDM_PF(model, g.T, g.P, init_indices=g.init_idx, cdf_order="sequential", low_latency=low_latency)
     assert torch.equal(pf._particle_classes.cpu(), torch.as_tensor(g.z["init_classes"]))
     assert torch.equal(pf._particle_states.cpu(), t64(g.z["init_states"]))
     lam_y = torch.exp(g.spec.y_log_lambdas) ** -2

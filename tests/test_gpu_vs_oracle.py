@@ -29,11 +29,12 @@ def particles_near_data(spec, P, seed):
     return spec.X[idx] + 0.05 * torch.randn(P, spec.d, dtype=torch.float64, generator=g)
 
 
+@pytest.mark.parametrize("low_latency", [False, True])
 @pytest.mark.parametrize("P", [1, 64, 65, 100, 3000])
-def test_observation_gp_vs_oracle(cfg1, P):
+def test_observation_gp_vs_oracle(cfg1, P, low_latency):
     spec, wl, f, model = cfg1
     xs = particles_near_data(spec, P, 5)
-    mu, var = model.map_x_to_y(xs.cuda())
+    mu, var = model.map_x_to_y(xs.cuda(), low_latency=low_latency)
     mu_o, var_o, v_o = orc.map_x_to_y(spec, f, xs)
     scale = torch.clamp(torch.abs(mu_o).max(dim=1, keepdim=True).values, min=1e-3)
     assert scaled_err(mu.cpu(), mu_o, scale) < TOL
@@ -41,13 +42,14 @@ def test_observation_gp_vs_oracle(cfg1, P):
     assert scaled_err(var.cpu(), var_o, lam) < TOL
 
 
+@pytest.mark.parametrize("low_latency", [False, True])
 @pytest.mark.parametrize("P", [1, 100, 1000])
-def test_dynamics_gp_vs_oracle(cfg1, P):
+def test_dynamics_gp_vs_oracle(cfg1, P, low_latency):
     spec, wl, f, model = cfg1
     xs = particles_near_data(spec, P, 6)
     lam_x = torch.exp(spec.x_log_lambdas) ** -2
     for c in range(spec.n_classes):
-        mean, var = model.map_x_dynamics_for_class(xs.cuda(), c)
+        mean, var = model.map_x_dynamics_for_class(xs.cuda(), c, low_latency=low_latency)
         mean_o, var_o, q, prior = orc.map_x_dynamics_for_class(spec, f, xs, c)
         scale = torch.clamp(torch.abs(mean_o).max(dim=1, keepdim=True).values, min=1e-3)
         assert scaled_err(mean.cpu(), mean_o, scale) < TOL
@@ -95,8 +97,9 @@ def test_tri_and_dense_packings_agree(cfg1):
     assert float(torch.max(torch.abs(var_t - var_d))) < 1e-10
 
 
+@pytest.mark.parametrize("low_latency", [False, True])
 @pytest.mark.parametrize("P", [100, 2500])
-def test_filter_trial_vs_oracle(cfg1, P):
+def test_filter_trial_vs_oracle(cfg1, P, low_latency):
     """8-frame trial with injected draws (BASELINE config 1 uses P = 100 over 150 frames; the oracle's cost
     bounds the frame count).  Every stage of every step is checked against the oracle evaluated on the CUDA
     path's own inputs to that stage, so rounding-level differences (the dynamics variance tolerance, amplified
@@ -109,7 +112,7 @@ def test_filter_trial_vs_oracle(cfg1, P):
     parts = orc.divide_into_n_parts(P, C)
     g = torch.Generator().manual_seed(9)
     init_idx = [torch.randint(0, b - a, (parts[c],), generator=g) for c, (a, b) in enumerate(spec.class_row_ranges())]
-    pf = GPMDM_PF(model, T, P, init_indices=init_idx, cdf_order="sequential")
+    pf = GPMDM_PF(model, T, P, init_indices=init_idx, cdf_order="sequential", low_latency=low_latency)
     cls_true, trial = wl.test_trials[0]
     lam_x = torch.exp(spec.x_log_lambdas) ** -2
     T64 = T.to(torch.float64)
@@ -251,8 +254,10 @@ def test_cfg2_100k_particles_sample_vs_oracle(cfg1):
     xs_d = xs.cuda()
     mu, var = model.map_x_to_y(xs_d)
     sample = torch.randperm(P, generator=torch.Generator().manual_seed(1))[:1500]
-    mu_s, var_s = model.map_x_to_y(xs_d[sample.cuda()].contiguous())
+    mu_s, var_s = model.map_x_to_y(xs_d[sample.cuda()].contiguous(), low_latency=False)
     assert torch.equal(mu[sample.cuda()], mu_s) and torch.equal(var[sample.cuda()], var_s)  # row results are batch independent
+    mu_l, var_l = model.map_x_to_y(xs_d[sample.cuda()].contiguous(), low_latency=True)  # other summation order of k^T L k
+    assert torch.equal(mu_l, mu_s) and float(torch.max(torch.abs(var_l - var_s))) < 1e-12
     mu_o, var_o, v_o = orc.map_x_to_y(spec, f, xs[sample])
     scale = torch.clamp(torch.abs(mu_o).max(dim=1, keepdim=True).values, min=1e-3)
     assert scaled_err(mu_s.cpu(), mu_o, scale) < TOL
