@@ -66,7 +66,8 @@ struct PredictParams {
     const int32_t* tiles;
     const int32_t* n_tiles;
     long long P;
-    int32_t* counter;
+    int32_t* counter;  // [0] tile hand-out, [1] round synchronisation
+    int round_sync;    // re-align the CTAs after every particle tile (uniform tiles, several rounds)
     // low-latency (split) mode: one work item per (particle tile, column tile); partial results go to the workspace
     int split, max_nct;
     double* qpart;  // [max_nct][P] per-column-tile contributions to k^T L k
@@ -199,12 +200,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) gp_predict_kernel(const PredictPa
     uint32_t g = 0;  // chunks consumed so far by this CTA (ring position and mbarrier parity)
 
     const int total_items = prm.split ? total_tiles * prm.max_nct : total_tiles;
+    int rounds_done = 0;
     for (;;) {
         if (tid == 0) s.tile = atomicAdd(prm.counter, 1);
         __syncthreads();
         const int item = s.tile;
         __syncthreads();
-        if (item >= total_items) break;
+        if (item >= total_items) {
+            // leaving: satisfy every later round so that nobody waits for this CTA
+            if (prm.round_sync && tid == 0) atomicAdd(prm.counter + 1, 1 << 20);  // > any target (n_tiles < 2^20)
+            break;
+        }
         // split mode: items are ordered column tile first, so the longest (ct = 0 of every particle tile) start first
         const int t = prm.split ? item % total_tiles : item;
         const int item_ct = prm.split ? item / total_tiles : -1;
@@ -416,6 +422,22 @@ __global__ void __launch_bounds__(NTHREADS, 1) gp_predict_kernel(const PredictPa
                 }
             }
         }
+        // Round synchronisation (observation kernel, several uniform tiles per CTA): every CTA waits, with a bounded
+        // number of polls, until all CTAs have finished the same number of tiles.  Within one round the CTAs walk L in
+        // lockstep and it is read from HBM once (L2 hit 97 %); without re-alignment they drift beyond the reach of
+        // the 126 MB L2 over the rounds and L is re-streamed ~9x (profiles/launches_r01.txt).
+        if (prm.round_sync) {
+            rounds_done++;
+            if (tid == 0) {
+                atomicAdd(prm.counter + 1, 1);
+                const int target = rounds_done * (int)gridDim.x;
+                for (int spin = 0; spin < 200000; spin++) {  // bounded: a missing CTA costs time, never a hang
+                    if (*reinterpret_cast<volatile int*>(prm.counter + 1) >= target) break;
+                    __nanosleep(100);
+                }
+            }
+            __syncthreads();
+        }
     }
 }
 
@@ -554,7 +576,7 @@ extern "C" int gpmdm_pf_propagate_f64(const gpmdm_gp_model* dyn, const double* x
     prm.x_new = x_new;
     prm.mean_out = mean_out;
     prm.var_out = var_out;
-    cudaError_t e = cudaMemsetAsync(tile_counter, 0, sizeof(int32_t), st);
+    cudaError_t e = cudaMemsetAsync(tile_counter, 0, 2 * sizeof(int32_t), st);
     GPMDM_REQUIRE(e == cudaSuccess, (int)e, "cudaMemsetAsync: %s", cudaGetErrorString(e));
     const long long max_tiles = (P + TM - 1) / TM + dyn->n_blocks;
     const int grid = (int)(max_tiles < num_sms() ? max_tiles : num_sms());
@@ -599,10 +621,11 @@ static int observe_impl(const gpmdm_gp_model* obs, const double* x, int64_t P, c
     prm.ll = ll;
     prm.mu_out = mu_out;
     prm.v_out = v_out;
-    cudaError_t e = cudaMemsetAsync(tile_counter, 0, sizeof(int32_t), st);
+    cudaError_t e = cudaMemsetAsync(tile_counter, 0, 2 * sizeof(int32_t), st);
     GPMDM_REQUIRE(e == cudaSuccess, (int)e, "cudaMemsetAsync: %s", cudaGetErrorString(e));
     const long long n_tiles = (P + TM - 1) / TM;
     const int grid = (int)(n_tiles < num_sms() ? n_tiles : num_sms());
+    prm.round_sync = (n_tiles >= 2ll * grid && n_tiles < (1ll << 20)) ? 1 : 0;
     return dispatch_d<0>(prm, grid, st);
 }
 
@@ -622,7 +645,7 @@ static int run_split(PredictParams& prm, int64_t max_n_pad, void* workspace, cud
     prm.mu_ws = prm.qpart + (long long)max_nq * prm.P;
     cudaError_t e = cudaMemsetAsync(prm.qpart, 0, (size_t)max_nq * prm.P * 8, st);
     GPMDM_REQUIRE(e == cudaSuccess, (int)e, "cudaMemsetAsync: %s", cudaGetErrorString(e));
-    e = cudaMemsetAsync(prm.counter, 0, sizeof(int32_t), st);
+    e = cudaMemsetAsync(prm.counter, 0, 2 * sizeof(int32_t), st);
     GPMDM_REQUIRE(e == cudaSuccess, (int)e, "cudaMemsetAsync: %s", cudaGetErrorString(e));
     const long long items = ((prm.P + TM - 1) / TM + prm.n_blocks) * prm.max_nct;
     const int grid = (int)(items < num_sms() ? items : num_sms());

@@ -538,7 +538,7 @@ class GPMDM(torch.nn.Module):
     # ---- prediction (gpmdm.py:923-963, 1032-1068) ----------------------------------------------------------
     def _scratch_counter(self):
         if getattr(self, "_counter", None) is None:
-            self._counter = torch.zeros(1, dtype=torch.int32, device=self.device)
+            self._counter = torch.zeros(4, dtype=torch.int32, device=self.device)
         return self._counter
 
     @torch.no_grad()

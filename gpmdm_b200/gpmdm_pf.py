@@ -106,7 +106,7 @@ class GPMDM_PF:
         self._cdf, self._anc = e(P), e(P, dt=torch.int64)
         self._states_alt, self._classes_alt = e(P, d), e(P, dt=torch.int64)
         self._perm, self._tiles = e(Pl, dt=torch.int32), e(Pl // _cabi.TILE_P + C + 1, 4, dt=torch.int32)
-        self._n_tiles, self._counter = e(1, dt=torch.int32), torch.zeros(1, dtype=torch.int32, device=dev)
+        self._n_tiles, self._counter = e(1, dt=torch.int32), torch.zeros(4, dtype=torch.int32, device=dev)
         self._E, self._eps, self._u = e(Pl, C), e(Pl, d), e(P)
         self._stats = e(2)
         self._v_buf = e(Pl)

@@ -105,7 +105,8 @@ int gpmdm_pf_bucket_by_class(const int64_t* classes, int64_t P, int32_t C, int32
  *     x_new = eps * sqrt(var) + mean                                   (mul, then add -- :168)
  * perm/tiles/n_tiles from gpmdm_pf_bucket_by_class.  eps [P, d] is indexed by particle.
  * mean_out / var_out ([P, d], may be NULL) expose the GP prediction (map_x_dynamics_for_class).
- * x_new may be NULL when only the prediction is wanted.  tile_counter: device int32 scratch [1]. */
+ * x_new may be NULL when only the prediction is wanted.  tile_counter: device int32 scratch [4] (tile hand-out
+ * counter and the round-synchronisation counter of the predict kernels; zeroed by the call). */
 int gpmdm_pf_propagate_f64(const gpmdm_gp_model* dyn, const double* x_prev, const int32_t* perm,
                            const int32_t* tiles, const int32_t* n_tiles, int64_t P, const double* eps,
                            double* x_new, double* mean_out, double* var_out, int32_t* tile_counter,

@@ -118,7 +118,7 @@ def test_observe_loglik_on_reference_states(case):
     ll = torch.empty(P, dtype=torch.float64, device="cuda")
     mu = torch.empty(P, g.spec.D, dtype=torch.float64, device="cuda")
     v = torch.empty(P, dtype=torch.float64, device="cuda")
-    counter = torch.zeros(1, dtype=torch.int32, device="cuda")
+    counter = torch.zeros(4, dtype=torch.int32, device="cuda")
     ll_const = float(2.0 * torch.sum(g.spec.y_log_lambdas)) - orc.c32_constant(g.spec.D)
     _cabi.check(lib.gpmdm_pf_observe_f64(ctypes.byref(pk["obs"]), x_ref.data_ptr(), P, z.data_ptr(), ll_const,
                                          ll.data_ptr(), mu.data_ptr(), v.data_ptr(), counter.data_ptr(),
