@@ -309,9 +309,8 @@ def run_ours(a):
             roofline = {
                 "bound": "tensor", "achieved": achieved, "peak": tf, "unit": "TFLOP/s", "frac": achieved / tf,
                 "traffic": None,
-                "traffic_note": "ncu (profiles/launches_r01.txt, profiles/ncu_observe_kernel_r01.txt): 1.77 GB per launch with "
-                                "one tile per SM (L read once, L2 hit 97.6%); 210 GB per launch at P=131072 (CTAs drift "
-                                "beyond L2 reach) = 116 GB/s = 1.8% of HBM peak; the kernel is tensor-bound",
+                "traffic_note": "not measurable live; ncu (profiles/launches_r01.txt): 1.74 GB of DRAM reads per round of 148 "
+                                "particle tiles (L + alpha read once per round; the rounds are kept in L2 lockstep)",
                 "kernel": f"gp_predict_kernel<0,{d}> (gpmdm_pf_observe_f64)", "launch_ms": obs_avg_ms,
                 "peak_source": "fp64 mma.sync m8n8k4 issue-rate probe measured in this run (MEASURED_PEAKS.json holds "
                                "no fp64 figure)",

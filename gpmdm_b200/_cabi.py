@@ -60,7 +60,7 @@ _SIGNATURES = {
     "gpmdm_pack_whitened_tf32": (ctypes.c_int, [_ptr, _i64, _i64, _ptr, _ptr]),
     "gpmdm_pack_alpha_tf32": (ctypes.c_int, [_ptr, _i64, _i64, _i32, _ptr, _ptr]),
     "gpmdm_pf_observe_tf32": (ctypes.c_int, [ctypes.POINTER(GpModelTf32), _ptr, _i64, _ptr, _f64, _ptr, _ptr, _ptr,
-                                             _ptr]),
+                                             _ptr, _ptr]),
     "gpmdm_kernel_build_f64": (ctypes.c_int, [_ptr, _i64, _i32, _i32, _ptr, _ptr, _f64, _ptr, _i32, _ptr, _ptr]),
     "gpmdm_kernel_grad_f64": (ctypes.c_int, [_ptr, _ptr, _i64, _i32, _i32, _ptr, _ptr, _f64, _ptr, _i32, _ptr, _ptr,
                                              _ptr, _ptr, _ptr, _ptr]),

@@ -64,6 +64,7 @@ struct Params {
     double* ll;
     double* mu_out;
     double* v_out;
+    int32_t* round_counter;  // device scratch (zeroed by the call), NULL = no round synchronisation
 };
 
 // element (row, k) of a [rows x KC] operand tile in the canonical no-swizzle K-major layout, in floats
@@ -167,7 +168,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) observe_tf32_kernel(const Params 
         // ===================== TMA producer =====================
         if (lane == 0) {
             uint32_t g = 0;
-            for (int t = blockIdx.x; t < n_tiles; t += gridDim.x)
+            int rounds = 0;
+            for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
                 for (int ct = 0; ct < nct; ct++) {
                     const float* base = ct < nq ? prm.wtiles + wtile_offset(ct) * (2 * B_HALF) : prm.atiles;
                     const int nch = chunks_of(ct);
@@ -178,6 +180,22 @@ __global__ void __launch_bounds__(NTHREADS, 1) observe_tf32_kernel(const Params 
                         bulk_g2s(&s.B[st][0][0], base + (long long)kc * (2 * B_HALF), 2 * B_HALF * 4, &s.b_full[st]);
                     }
                 }
+                // Round synchronisation of the producers (bounded polling, never a hang): the 148 CTAs stream the same
+                // W tiles; aligned, one HBM read serves all of them out of L2, adrift they would each pull 32 KB per
+                // chunk from HBM (148 x 32 KB per ~0.4 us is beyond HBM bandwidth).
+                if (prm.round_counter) {
+                    rounds++;
+                    atomicAdd(prm.round_counter, 1);
+                    const int full_rounds = n_tiles / (int)gridDim.x;  // rounds in which every CTA has a tile
+                    if (rounds <= full_rounds) {
+                        const int target = rounds * (int)gridDim.x;
+                        for (int spin = 0; spin < 200000; spin++) {
+                            if (*reinterpret_cast<volatile int*>(prm.round_counter) >= target) break;
+                            __nanosleep(100);
+                        }
+                    }
+                }
+            }
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
@@ -423,7 +441,8 @@ extern "C" int gpmdm_pack_alpha_tf32(const double* alpha, int64_t n, int64_t n_p
 }
 
 extern "C" int gpmdm_pf_observe_tf32(const gpmdm_gp_model_tf32* m, const double* x, int64_t P, const double* z,
-                                     double ll_const, double* ll, double* mu_out, double* v_out, void* stream) {
+                                     double ll_const, double* ll, double* mu_out, double* v_out, int32_t* tile_counter,
+                                     void* stream) {
     GPMDM_REQUIRE(m && m->coords && m->wtiles && m->atiles && m->lengthscales && m->lambdas, GPMDM_E_INVALID,
                   "null model field");
     GPMDM_REQUIRE(m->d >= 1 && m->d <= GPMDM_MAX_LATENT, GPMDM_E_UNSUPPORTED, "latent dimension %d outside [1, %d]", m->d,
@@ -457,6 +476,11 @@ extern "C" int gpmdm_pf_observe_tf32(const gpmdm_gp_model_tf32* m, const double*
     const long long tiles = (P + tf32::TM - 1) / tf32::TM;
     const int grid = (int)(tiles < sms ? tiles : sms);
     cudaStream_t st = (cudaStream_t)stream;
+    if (tile_counter && tiles >= 2ll * grid) {
+        cudaError_t e = cudaMemsetAsync(tile_counter, 0, sizeof(int32_t), st);
+        GPMDM_REQUIRE(e == cudaSuccess, (int)e, "cudaMemsetAsync: %s", cudaGetErrorString(e));
+        prm.round_counter = tile_counter;
+    }
     switch (m->d) {
         case 1: return tf32::launch<1>(prm, grid, st);
         case 2: return tf32::launch<2>(prm, grid, st);

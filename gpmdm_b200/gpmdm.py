@@ -553,13 +553,13 @@ class GPMDM(torch.nn.Module):
         if precision == "tf32":  # variances on tcgen05 (tf32 x3, whitened); means stay fp64 (DMMA, alpha tile only)
             pk32, pk = self.packed_model_tf32(), self.packed_models(with_obs_L=False)
             check(lib.gpmdm_pf_observe_tf32(ctypes.byref(pk32["model"]), ptr(Xs), P, None, 0.0, None, None, ptr(v),
-                                            stream()), "gpmdm_pf_observe_tf32")
+                                            ptr(self._scratch_counter()), stream()), "gpmdm_pf_observe_tf32")
             check(lib.gpmdm_pf_loglik_f64(ctypes.byref(pk["obs"]), ptr(Xs), P, None, 0.0, ptr(v), None, ptr(mu),
                                           ptr(self._scratch_counter()), stream()), "gpmdm_pf_loglik_f64")
         elif precision == "tf32-pure":  # mean on the tensor cores as well (error ~1e-4..1e-3 of the row scale)
             pk32 = self.packed_model_tf32()
             check(lib.gpmdm_pf_observe_tf32(ctypes.byref(pk32["model"]), ptr(Xs), P, None, 0.0, None, ptr(mu), ptr(v),
-                                            stream()), "gpmdm_pf_observe_tf32")
+                                            ptr(self._scratch_counter()), stream()), "gpmdm_pf_observe_tf32")
         elif precision == "fp64":
             pk = self.packed_models()
             if P > 0 and self._use_lowlat(P, low_latency):

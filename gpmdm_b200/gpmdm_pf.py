@@ -196,7 +196,7 @@ class GPMDM_PF:
         if self._precision == "tf32":
             # variances: tcgen05 (3 x tf32, whitened form); means + log-likelihood: fp64 on the alpha tile only
             check(lib.gpmdm_pf_observe_tf32(ctypes.byref(self._packed_tf32["model"]), ptr(x_new_l), Pl, None, 0.0, None,
-                                            None, ptr(self._v_buf), st), "gpmdm_pf_observe_tf32")
+                                            None, ptr(self._v_buf), ptr(self._counter), st), "gpmdm_pf_observe_tf32")
             check(lib.gpmdm_pf_loglik_f64(ctypes.byref(self._packed["obs"]), ptr(x_new_l), Pl, ptr(z), self._ll_const,
                                           ptr(self._v_buf), ptr(ll_l), None, ptr(self._counter), st),
                   "gpmdm_pf_loglik_f64")

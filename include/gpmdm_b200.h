@@ -204,9 +204,10 @@ int64_t gpmdm_tf32_atiles_bytes(int64_t n_pad);
 int gpmdm_pack_whitened_tf32(const double* W, int64_t n, int64_t n_pad, float* wtiles, void* stream);
 /* alpha [n, dout] fp64 row-major. */
 int gpmdm_pack_alpha_tf32(const double* alpha, int64_t n, int64_t n_pad, int32_t dout, float* atiles, void* stream);
-/* Same contract as gpmdm_pf_observe_f64 (x, z, ll, mu_out, v_out are fp64 arrays). */
+/* Same contract as gpmdm_pf_observe_f64 (x, z, ll, mu_out, v_out are fp64 arrays; tile_counter: int32 scratch [4],
+ * may be NULL). */
 int gpmdm_pf_observe_tf32(const gpmdm_gp_model_tf32* obs, const double* x, int64_t P, const double* z, double ll_const,
-                          double* ll, double* mu_out, double* v_out, void* stream);
+                          double* ll, double* mu_out, double* v_out, int32_t* tile_counter, void* stream);
 
 /* ---- training-side kernel matrices (gpmdm.py:381-548, 311-340, 550-628) ------------------------
  * K = exp(-|(x_i-x_j)/l|^2) [+ [x_i,1]diag(c^2)[x_j,1]^T if kind 1] [+ noise2 on the diagonal],
