@@ -230,6 +230,8 @@ def run_ours(a):
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local_rank)
     if world > 1:
+        # keep stdout to the one JSON line: NCCL's banner ("NCCL version ...") goes to stdout at the default debug level
+        os.environ["NCCL_DEBUG"] = os.environ.get("GPMDM_NCCL_DEBUG", "WARN")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     lib = _cabi.lib()
 
