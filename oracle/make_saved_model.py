@@ -23,8 +23,9 @@ def main():
         for s in wl.sequences[c]:
             m.add_data(s, c)
     m.init_X()
+    X0 = m.X.detach().numpy().copy()
     torch.manual_seed(0)
-    m.train_adam(5, 0, lr=0.01)
+    losses = m.train_adam(5, 0, lr=0.01)
     out = os.path.join(ROOT, "tests", "golden", "ref_saved_model.pth")
     m.save(out)
     with torch.no_grad():
@@ -34,7 +35,7 @@ def main():
         mu, var = m.map_x_to_y(xs)
         dm, dv = m.map_x_dynamics_for_class(xs, 1)
     np.savez_compressed(os.path.join(ROOT, "tests", "golden", "ref_saved_model_expect.npz"), xs=xs.numpy(), mu=mu.numpy(),
-                        var=var.numpy(), dyn_mean=dm.numpy(), dyn_var=dv.numpy(),
+                        var=var.numpy(), dyn_mean=dm.numpy(), dyn_var=dv.numpy(), losses=np.array(losses), X0=X0,
                         state={k: v.numpy() for k, v in m.state_dict().items()})
     print("wrote", out, os.path.getsize(out), "bytes")
 

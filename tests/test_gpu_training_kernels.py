@@ -155,3 +155,26 @@ def test_load_a_model_file_written_by_the_reference():
     assert np.max(np.abs(dm.cpu().numpy() - exp["dyn_mean"])) < 1e-6
     prior = (1 + (exp["xs"] ** 2 * np.exp(state["x_log_lin_coeff"][:3]) ** 2).sum(1) + np.exp(state["x_log_lin_coeff"][3]) ** 2)
     assert np.max(np.abs(dv.cpu().numpy() - exp["dyn_var"]) / prior[:, None]) < 1e-6
+
+
+def test_train_adam_trajectory_matches_the_reference():
+    """Five Adam steps from the same PCA initialisation on the same data: loss trajectory and trained parameters against
+    the UNMODIFIED reference's `train_adam` (recorded by oracle/make_saved_model.py in tests/golden/)."""
+    from gpmdm_b200 import GPMDM, synthetic
+
+    here = os.path.dirname(os.path.abspath(__file__))
+    exp = np.load(os.path.join(here, "golden", "ref_saved_model_expect.npz"), allow_pickle=True)
+    wl = synthetic.make_sequences(2, 12, 2, 30, seed=31, n_test_trials=1, test_frames=4)
+    hp = synthetic.notebook_hyperparameters(12, 3, 1e-1)
+    m = GPMDM(D=12, d=3, n_classes=2, dyn_target="full", dyn_back_step=1, **hp)
+    for c in range(2):
+        for s in wl.sequences[c]:
+            m.add_data(s, c)
+    m.init_X()
+    assert np.max(np.abs(m.X.detach().cpu().numpy() - exp["X0"])) < 1e-10  # same sklearn PCA initialisation
+    losses = m.train_adam(5, 0, lr=0.01)
+    ref_losses = exp["losses"]
+    assert np.max(np.abs(np.array(losses) - ref_losses) / np.abs(ref_losses)) < 1e-8
+    state = exp["state"].item()
+    for k, v in m.state_dict().items():
+        assert np.max(np.abs(v.cpu().numpy() - state[k])) < 1e-7, k
