@@ -230,9 +230,18 @@ def run_ours(a):
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local_rank)
     if world > 1:
-        # keep stdout to the one JSON line: NCCL's banner ("NCCL version ...") goes to stdout at the default debug level
-        os.environ["NCCL_DEBUG"] = os.environ.get("GPMDM_NCCL_DEBUG", "WARN")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # keep stdout to the one JSON line: NCCL prints its banner ("NCCL version ...") to fd 1 when the communicator
+        # is created, so fd 1 points at stderr while that happens
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            os.dup2(saved, 1)
+            os.close(saved)
     lib = _cabi.lib()
 
     wl, X0, hp = synthetic_inputs(a)
