@@ -158,6 +158,50 @@ __device__ __forceinline__ void kstar_pair(const double (&rec0)[REC_MAX], const 
     }
 }
 
+// K* of NB training records against one particle row: NB independent chains, evaluated stage by stage.
+template <int KIND, int DL, int NB>
+__device__ __forceinline__ void kstar_multi(const double* __restrict__ recs, int rec_stride,
+                                            const ParticleRec<KIND, DL>& p, double c2last,
+                                            const double* __restrict__ exptab, double (&out)[NB]) {
+    constexpr int d = DL;
+    double a[NB], lin[NB];
+    int n[NB];
+#pragma unroll
+    for (int b = 0; b < NB; b++) {
+        double rec[REC_MAX];
+        load_record<KIND, DL>(recs + b * rec_stride, rec);
+        const double t0 = rec[0] - p.b[0];
+        double acc = -t0 * t0;
+#pragma unroll
+        for (int j = 1; j < d; j++) {
+            const double t = rec[j] - p.b[j];
+            acc = fma(-t, t, acc);
+        }
+        a[b] = acc;
+        if (KIND == 1) {
+            double l = c2last;
+#pragma unroll
+            for (int j = 0; j < d; j++) l = fma(rec[d + j], p.x[j], l);
+            lin[b] = l;
+        }
+    }
+    double r[NB], e[NB];
+#pragma unroll
+    for (int b = 0; b < NB; b++) r[b] = exp_reduce(a[b], n[b]);
+    constexpr double C[6] = {1.0, 1.0, 0.5, 1.0 / 6.0, 1.0 / 24.0, 1.0 / 120.0};
+#pragma unroll
+    for (int b = 0; b < NB; b++) e[b] = 1.0 / 720.0;
+#pragma unroll
+    for (int k = 5; k >= 0; k--)
+#pragma unroll
+        for (int b = 0; b < NB; b++) e[b] = fma(e[b], r[b], C[k]);
+#pragma unroll
+    for (int b = 0; b < NB; b++) {
+        const double v = exp_scale(e[b], n[b], exptab);
+        out[b] = KIND == 1 ? v + lin[b] : v;
+    }
+}
+
 // Chunk schedule of one particle tile: column tile ct covers k-chunks [kbeg(ct), nkc).
 struct ChunkCursor {
     int ct, k, nq, nct, nkc, tri;
@@ -289,13 +333,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gp_predict_kernel(const PredictPa
         // ---- A fragments of the first chunk: a[k4] = K*[row 8 w + r][k = 4 k4 + c] -----------------------------
         double a[KC / 4];
         mbar_wait(&s.full[g % STAGES], (g / STAGES) & 1);
-#pragma unroll
-        for (int k4 = 0; k4 < KC / 4; k4 += 2) {
-            double rec0[REC_MAX], rec1[REC_MAX];
-            load_record<KIND, DL>(&s.R[g % STAGES][(k4 * 4 + c) * REC], rec0);
-            load_record<KIND, DL>(&s.R[g % STAGES][(k4 * 4 + 4 + c) * REC], rec1);
-            kstar_pair<KIND, DL>(rec0, rec1, pr, c2last, exptab, a[k4], a[k4 + 1]);
-        }
+        kstar_multi<KIND, DL, KC / 4>(&s.R[g % STAGES][c * REC], 4 * REC, pr, c2last, exptab, a);
 
         ChunkCursor cur;
         cur.init(nq, ct_end, nkc, prm.tri, ct_begin);
@@ -323,14 +361,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) gp_predict_kernel(const PredictPa
            particle tile the fragments are recomputed from the current stage (values unused). */                 \
         const bool has_next = !(ct == ct_end - 1 && k == nkc - 1);                                               \
         const int stn = has_next ? (int)((g + 1) % STAGES) : st;                                                 \
-        if (has_next) mbar_wait(&s.full[stn], ((g + 1) / STAGES) & 1);                                           \
+        /* probe the next chunk's barrier now, look at the answer one MMA block later (hides the probe latency) */ \
+        const uint32_t ready = has_next ? mbar_test(&s.full[stn], ((g + 1) / STAGES) & 1) : 1u;                  \
         double an[KC / 4];                                                                                       \
         _Pragma("unroll") for (int k4 = 0; k4 < KC / 4; k4++) {                                                  \
-            if ((k4 & 1) == 0) { /* two of the next chunk's A fragments, woven into this block's MMAs */         \
-                double rec0[REC_MAX], rec1[REC_MAX];                                                             \
-                load_record<KIND, DL>(&s.R[stn][(k4 * 4 + c) * REC], rec0);                                      \
-                load_record<KIND, DL>(&s.R[stn][(k4 * 4 + 4 + c) * REC], rec1);                                  \
-                kstar_pair<KIND, DL>(rec0, rec1, pr, c2last, exptab, an[k4], an[k4 + 1]);                        \
+            if (k4 == 1) { /* the next chunk's four A fragments: four independent exp chains in one block */     \
+                if (!ready) mbar_wait(&s.full[stn], ((g + 1) / STAGES) & 1);                                     \
+                kstar_multi<KIND, DL, KC / 4>(&s.R[stn][c * REC], 4 * REC, pr, c2last, exptab, an);              \
             }                                                                                                    \
             const double ak = a[k4];                                                                             \
             _Pragma("unroll") for (int jg = 0; jg < NJ; jg += 8) {                                               \
