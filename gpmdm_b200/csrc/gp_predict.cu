@@ -348,6 +348,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) gp_predict_kernel(const PredictPa
             const int kbeg = cur.kbeg(ct);
             // The k loop of one column tile.  GROUP_ON(jg) says whether the 8 column blocks starting at jg are
             // needed: always for tiles of L; for alpha tiles only the blocks that hold real output columns.
+#define constexpr_next_group(jg, k4)                                                                           \
+    {                                                                                                            \
+        const int njg = (jg) + 8 < jlim8 ? (jg) + 8 : 0;                                                         \
+        const int nk4 = (jg) + 8 < jlim8 ? (k4) : (k4) + 1;                                                      \
+        if (nk4 < KC / 4) {                                                                                      \
+            _Pragma("unroll") for (int j = 0; j < 8; j++) bq[j] = s.B[st][nk4 * 4 + c][(njg + j) * 8 + r];       \
+        }                                                                                                        \
+    }
 #define GPMDM_K_LOOP(GROUP_ON)                                                                                  \
     for (int k = kbeg; k < nkc; k++, g++) {                                                                      \
         const int st = (int)(g % STAGES);                                                                        \
@@ -361,25 +369,29 @@ __global__ void __launch_bounds__(NTHREADS, 1) gp_predict_kernel(const PredictPa
            particle tile the fragments are recomputed from the current stage (values unused). */                 \
         const bool has_next = !(ct == ct_end - 1 && k == nkc - 1);                                               \
         const int stn = has_next ? (int)((g + 1) % STAGES) : st;                                                 \
-        /* probe the next chunk's barrier now, look at the answer one MMA block later (hides the probe latency) */ \
+        /* probe the next chunk's barrier now, look at the answer after the MMA blocks (hides the probe latency) */ \
         const uint32_t ready = has_next ? mbar_test(&s.full[stn], ((g + 1) / STAGES) & 1) : 1u;                  \
-        double an[KC / 4];                                                                                       \
+        /* B fragments are software-pipelined one group of 8 column blocks ahead of the MMAs that use them */      \
+        double bq[8];                                                                                            \
+        if (GROUP_ON(0)) {                                                                                       \
+            _Pragma("unroll") for (int j = 0; j < 8; j++) bq[j] = s.B[st][c][j * 8 + r];                         \
+        }                                                                                                        \
         _Pragma("unroll") for (int k4 = 0; k4 < KC / 4; k4++) {                                                  \
-            if (k4 == 1) { /* the next chunk's four A fragments: four independent exp chains in one block */     \
-                if (!ready) mbar_wait(&s.full[stn], ((g + 1) / STAGES) & 1);                                     \
-                kstar_multi<KIND, DL, KC / 4>(&s.R[stn][c * REC], 4 * REC, pr, c2last, exptab, an);              \
-            }                                                                                                    \
             const double ak = a[k4];                                                                             \
             _Pragma("unroll") for (int jg = 0; jg < NJ; jg += 8) {                                               \
                 if (GROUP_ON(jg)) {                                                                              \
                     double b[8];                                                                                 \
-                    _Pragma("unroll") for (int j = 0; j < 8; j++) b[j] = s.B[st][k4 * 4 + c][(jg + j) * 8 + r];  \
+                    _Pragma("unroll") for (int j = 0; j < 8; j++) b[j] = bq[j];                                  \
+                    /* next group: same k4 block, or the first group of the next block */                        \
+                    constexpr_next_group(jg, k4);                                                                \
                     _Pragma("unroll") for (int j = 0; j < 8; j++)                                                \
                         dmma_m8n8k4(acc[jg + j][0], acc[jg + j][1], ak, b[j]);                                   \
                 }                                                                                                \
             }                                                                                                    \
         }                                                                                                        \
-        _Pragma("unroll") for (int k4 = 0; k4 < KC / 4; k4++) a[k4] = an[k4];                                    \
+        /* the next chunk's four A fragments: four independent exp chains in one block */                        \
+        if (!ready) mbar_wait(&s.full[stn], ((g + 1) / STAGES) & 1);                                             \
+        kstar_multi<KIND, DL, KC / 4>(&s.R[stn][c * REC], 4 * REC, pr, c2last, exptab, a);                       \
         __syncwarp();                                                                                            \
         if (lane == 0) mbar_arrive(&s.empty[st]); /* this warp is done with the ring slot */                     \
     }
@@ -387,11 +399,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) gp_predict_kernel(const PredictPa
 #define GPMDM_SOME_GROUPS(jg) ((jg) < jlim)
             const int jlim = ct < nq ? NJ : (min(TN, prm.dout - (ct - nq) * TN) + 7) / 8;  // 8-column blocks in use
             if (jlim > NJ - 8) {
+                constexpr int jlim8 = NJ;
                 GPMDM_K_LOOP(GPMDM_ALL_GROUPS)
             } else {
+                const int jlim8 = (jlim + 7) & ~7;
                 GPMDM_K_LOOP(GPMDM_SOME_GROUPS)
             }
 #undef GPMDM_K_LOOP
+#undef constexpr_next_group
 #undef GPMDM_ALL_GROUPS
 #undef GPMDM_SOME_GROUPS
 
