@@ -241,7 +241,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) gp_predict_kernel(const PredictPa
     const double* exptab = s.exptab;
 
     const int total_tiles = prm.tiles ? *prm.n_tiles : (int)((prm.P + TM - 1) / TM);
-    uint32_t g = 0;  // chunks consumed so far by this CTA (ring position and mbarrier parity)
+    // ring positions as (stage, parity) pairs advanced incrementally (STAGES is not a power of two)
+    int cst = 0, cph = 0;   // consumer: stage / parity of the chunk being consumed
+    int duty = 0;           // warp whose turn it is to issue the next TMA chunk
 
     const int total_items = prm.split ? total_tiles * prm.max_nct : total_tiles;
     int rounds_done = 0;
@@ -304,10 +306,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) gp_predict_kernel(const PredictPa
         // ---- TMA issue: all warps advance the same cursor, the duty warp issues ------------------------------
         ChunkCursor bcur;
         bcur.init(nq, ct_end, nkc, prm.tri, ct_begin);
-        uint32_t gb = g;  // ring position of the next chunk to issue
+        int pst = cst, pph = cph;  // producer: stage / parity of the next chunk to issue
         auto issue_b = [&]() {
-            const int st = (int)(gb % STAGES);
-            mbar_wait(&s.empty[st], ((gb / STAGES) & 1) ^ 1);  // first fill of a stage passes immediately
+            const int st = pst;
+            mbar_wait(&s.empty[st], pph ^ 1);  // first fill of a stage passes immediately
             const double* src;
             int ld;
             if (bcur.ct < nq) {
@@ -324,16 +326,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) gp_predict_kernel(const PredictPa
             if (lane == 0)
                 bulk_g2s(&s.R[st][0], gbk.coords + (long long)bcur.k * KC * REC, (uint32_t)(KC * REC * 8), &s.full[st]);
         };
+#define GPMDM_ADVANCE(st_, ph_)   \
+    if (++(st_) == STAGES) {      \
+        (st_) = 0;                \
+        (ph_) ^= 1;               \
+    }
         for (int i = 0; i < AHEAD && !bcur.done(); i++) {
             if (warp == 0) issue_b();
             bcur.next();
-            gb++;
+            GPMDM_ADVANCE(pst, pph)
         }
 
         // ---- A fragments of the first chunk: a[k4] = K*[row 8 w + r][k = 4 k4 + c] -----------------------------
         double a[KC / 4];
-        mbar_wait(&s.full[g % STAGES], (g / STAGES) & 1);
-        kstar_multi<KIND, DL, KC / 4>(&s.R[g % STAGES][c * REC], 4 * REC, pr, c2last, exptab, a);
+        mbar_wait(&s.full[cst], cph);
+        kstar_multi<KIND, DL, KC / 4>(&s.R[cst][c * REC], 4 * REC, pr, c2last, exptab, a);
 
         ChunkCursor cur;
         cur.init(nq, ct_end, nkc, prm.tri, ct_begin);
@@ -357,20 +364,22 @@ __global__ void __launch_bounds__(NTHREADS, 1) gp_predict_kernel(const PredictPa
         }                                                                                                        \
     }
 #define GPMDM_K_LOOP(GROUP_ON)                                                                                  \
-    for (int k = kbeg; k < nkc; k++, g++) {                                                                      \
-        const int st = (int)(g % STAGES);                                                                        \
+    for (int k = kbeg; k < nkc; k++) {                                                                           \
+        const int st = cst;                                                                                      \
         /* keep the ring AHEAD chunks full; the duty rotates so that no warp is always the one waiting */        \
         if (!bcur.done()) {                                                                                      \
-            if (warp == (int)(g % NWARPS)) issue_b();                                                            \
+            if (warp == duty) issue_b();                                                                         \
+            duty = (duty + 1) & (NWARPS - 1);                                                                    \
             bcur.next();                                                                                         \
-            gb++;                                                                                                \
+            GPMDM_ADVANCE(pst, pph)                                                                              \
         }                                                                                                        \
         /* The next chunk provides the records for the next A fragments.  After the last chunk of the          \
            particle tile the fragments are recomputed from the current stage (values unused). */                 \
         const bool has_next = !(ct == ct_end - 1 && k == nkc - 1);                                               \
-        const int stn = has_next ? (int)((g + 1) % STAGES) : st;                                                 \
+        int stn = cst, phn = cph;                                                                                \
+        if (has_next) { GPMDM_ADVANCE(stn, phn) }                                                                \
         /* probe the next chunk's barrier now, look at the answer after the MMA blocks (hides the probe latency) */ \
-        const uint32_t ready = has_next ? mbar_test(&s.full[stn], ((g + 1) / STAGES) & 1) : 1u;                  \
+        const uint32_t ready = has_next ? mbar_test(&s.full[stn], phn) : 1u;                                     \
         /* B fragments are software-pipelined one group of 8 column blocks ahead of the MMAs that use them */      \
         double bq[8];                                                                                            \
         if (GROUP_ON(0)) {                                                                                       \
@@ -390,10 +399,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) gp_predict_kernel(const PredictPa
             }                                                                                                    \
         }                                                                                                        \
         /* the next chunk's four A fragments: four independent exp chains in one block */                        \
-        if (!ready) mbar_wait(&s.full[stn], ((g + 1) / STAGES) & 1);                                             \
+        if (!ready) mbar_wait(&s.full[stn], phn);                                                                \
         kstar_multi<KIND, DL, KC / 4>(&s.R[stn][c * REC], 4 * REC, pr, c2last, exptab, a);                       \
         __syncwarp();                                                                                            \
         if (lane == 0) mbar_arrive(&s.empty[st]); /* this warp is done with the ring slot */                     \
+        GPMDM_ADVANCE(cst, cph)                                                                                  \
     }
 #define GPMDM_ALL_GROUPS(jg) true
 #define GPMDM_SOME_GROUPS(jg) ((jg) < jlim)
