@@ -355,6 +355,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) gp_predict_kernel(const PredictPa
             const int kbeg = cur.kbeg(ct);
             // The k loop of one column tile.  GROUP_ON(jg) says whether the 8 column blocks starting at jg are
             // needed: always for tiles of L; for alpha tiles only the blocks that hold real output columns.
+#ifdef GPMDM_DIAG_NO_EXP  /* timing diagnostic only: results are wrong */
+#define GPMDM_MAIN_LOOP_KSTAR a[0] += 1e-300; a[1] += 1e-300; a[2] += 1e-300; a[3] += 1e-300;
+#else
+#define GPMDM_MAIN_LOOP_KSTAR kstar_multi<KIND, DL, KC / 4>(&s.R[stn][c * REC], 4 * REC, pr, c2last, exptab, a);
+#endif
 #define constexpr_next_group(jg, k4)                                                                           \
     {                                                                                                            \
         const int njg = (jg) + 8 < jlim8 ? (jg) + 8 : 0;                                                         \
@@ -400,7 +405,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gp_predict_kernel(const PredictPa
         }                                                                                                        \
         /* the next chunk's four A fragments: four independent exp chains in one block */                        \
         if (!ready) mbar_wait(&s.full[stn], phn);                                                                \
-        kstar_multi<KIND, DL, KC / 4>(&s.R[stn][c * REC], 4 * REC, pr, c2last, exptab, a);                       \
+        GPMDM_MAIN_LOOP_KSTAR                                                                                    \
         __syncwarp();                                                                                            \
         if (lane == 0) mbar_arrive(&s.empty[st]); /* this warp is done with the ring slot */                     \
         GPMDM_ADVANCE(cst, cph)                                                                                  \
