@@ -51,7 +51,7 @@ def parse_args():
     ap.add_argument("--frames", type=int, default=100)
     ap.add_argument("--latent", type=int, default=3)
     ap.add_argument("--obs-dim", type=int, default=62)
-    ap.add_argument("--cpu-sample", type=int, default=2048, help="particles of the CPU-baseline sample")
+    ap.add_argument("--cpu-sample", type=int, default=4096, help="particles of the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--dense", action="store_true", help="dense K^-1 instead of the triangular packing")
     ap.add_argument("--precision", default="fp64", choices=["fp64", "tf32"],
