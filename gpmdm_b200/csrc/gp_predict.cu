@@ -72,6 +72,9 @@ struct PredictParams {
     int split, max_nct;
     double* qpart;  // [max_nct][P] per-column-tile contributions to k^T L k
     double* mu_ws;  // [P][dout] means
+    // K* cache (CACHE instantiation): per-CTA scratch of n_pad x 64 doubles in A-fragment order
+    double* kcache;
+    long long kcache_stride;  // doubles per CTA
     // dynamics epilogue
     const double* eps;
     double* x_new;
@@ -218,7 +221,13 @@ struct ChunkCursor {
     }
 };
 
-template <int KIND, int DL>
+// CACHE: the A fragments (K* of this lane's particle row against every training row) are generated ONCE per particle
+// tile into a per-CTA global scratch, in exactly the order the lane consumes them, and the k loop re-reads them (four
+// 8-byte loads per lane and chunk, issued one chunk ahead) instead of re-evaluating the exponentials for every column
+// tile: with the triangular packing a K* entry is used by nq/2 column tiles on average, so the fp64 datapath the
+// DMMAs run on is relieved of ~97 % of the exp work.  Each lane reads back only what it wrote itself: no barrier,
+// no fence.  Values are bit-identical to the on-the-fly instantiation (same function, same inputs).
+template <int KIND, int DL, bool CACHE>
 __global__ void __launch_bounds__(NTHREADS, 1) gp_predict_kernel(const PredictParams prm) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     Smem& s = *reinterpret_cast<Smem*>(smem_raw);
@@ -337,10 +346,30 @@ __global__ void __launch_bounds__(NTHREADS, 1) gp_predict_kernel(const PredictPa
             GPMDM_ADVANCE(pst, pph)
         }
 
+        // ---- K* cache: this lane's fragments for every chunk of the block, written in consumption order ----------
+        double* kc = nullptr;
+        constexpr int KCHUNK = TM * KC;  // doubles per chunk in the cache: [warp][k4][lane]
+        if (CACHE) {
+            if ((long long)n_pad * TM > prm.kcache_stride) __trap();  // workspace sized for a smaller block
+            kc = prm.kcache + (long long)blockIdx.x * prm.kcache_stride + warp * (KC / 4 * 32) + lane;
+            for (int k = 0; k < nkc; k++) {
+                double g[KC / 4];
+                kstar_multi<KIND, DL, KC / 4>(gbk.coords + (long long)(k * KC + c) * REC, 4 * REC, pr, c2last, exptab, g);
+#pragma unroll
+                for (int i = 0; i < KC / 4; i++) __stcg(kc + (long long)k * KCHUNK + i * 32, g[i]);
+            }
+        }
+
         // ---- A fragments of the first chunk: a[k4] = K*[row 8 w + r][k = 4 k4 + c] -----------------------------
         double a[KC / 4];
         mbar_wait(&s.full[cst], cph);
-        kstar_multi<KIND, DL, KC / 4>(&s.R[cst][c * REC], 4 * REC, pr, c2last, exptab, a);
+        if (CACHE) {
+            const int k0 = (prm.tri && ct_begin < nq) ? ct_begin * (TN / KC) : 0;
+#pragma unroll
+            for (int i = 0; i < KC / 4; i++) a[i] = __ldcg(kc + (long long)k0 * KCHUNK + i * 32);
+        } else {
+            kstar_multi<KIND, DL, KC / 4>(&s.R[cst][c * REC], 4 * REC, pr, c2last, exptab, a);
+        }
 
         ChunkCursor cur;
         cur.init(nq, ct_end, nkc, prm.tri, ct_begin);
@@ -358,7 +387,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) gp_predict_kernel(const PredictPa
 #ifdef GPMDM_DIAG_NO_EXP  /* timing diagnostic only: results are wrong */
 #define GPMDM_MAIN_LOOP_KSTAR a[0] += 1e-300; a[1] += 1e-300; a[2] += 1e-300; a[3] += 1e-300;
 #else
-#define GPMDM_MAIN_LOOP_KSTAR kstar_multi<KIND, DL, KC / 4>(&s.R[stn][c * REC], 4 * REC, pr, c2last, exptab, a);
+#define GPMDM_MAIN_LOOP_KSTAR                                                                        \
+    if (CACHE) {                                                                                     \
+        _Pragma("unroll") for (int i = 0; i < KC / 4; i++) a[i] = an[i];                             \
+    } else {                                                                                         \
+        kstar_multi<KIND, DL, KC / 4>(&s.R[stn][c * REC], 4 * REC, pr, c2last, exptab, a);           \
+    }
 #endif
 #define constexpr_next_group(jg, k4)                                                                           \
     {                                                                                                            \
@@ -383,6 +417,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) gp_predict_kernel(const PredictPa
         const bool has_next = !(ct == ct_end - 1 && k == nkc - 1);                                               \
         int stn = cst, phn = cph;                                                                                \
         if (has_next) { GPMDM_ADVANCE(stn, phn) }                                                                \
+        /* K* cache: the next chunk's fragments are requested now and consumed after the MMA blocks */           \
+        double an[KC / 4];                                                                                       \
+        if (CACHE) {                                                                                             \
+            const int kn = !has_next ? k : (k + 1 < nkc ? k + 1 : cur.kbeg(ct + 1));                             \
+            _Pragma("unroll") for (int i = 0; i < KC / 4; i++) an[i] = __ldcg(kc + (long long)kn * KCHUNK + i * 32); \
+        }                                                                                                        \
         /* probe the next chunk's barrier now, look at the answer after the MMA blocks (hides the probe latency) */ \
         const uint32_t ready = has_next ? mbar_test(&s.full[stn], phn) : 1u;                                     \
         /* B fragments are software-pipelined one group of 8 column blocks ahead of the MMAs that use them */      \
@@ -549,10 +589,10 @@ __global__ void predict_finalize_kernel(const PredictParams prm, int max_nq) {
 }
 
 // ---- host side -------------------------------------------------------------------------------------
-template <int KIND, int DL>
+template <int KIND, int DL, bool CACHE = false>
 static int launch_instance(const PredictParams& prm, int grid, cudaStream_t st) {
     static bool configured = false;  // per instantiation
-    auto kern = gp_predict_kernel<KIND, DL>;
+    auto kern = gp_predict_kernel<KIND, DL, CACHE>;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
         if (e != cudaSuccess) {
@@ -563,6 +603,21 @@ static int launch_instance(const PredictParams& prm, int grid, cudaStream_t st) 
     }
     kern<<<grid, NTHREADS, sizeof(Smem), st>>>(prm);
     return check_launch("gp_predict_kernel");
+}
+
+static int dispatch_d_cached(const PredictParams& prm, int grid, cudaStream_t st) {
+    switch (prm.d) {
+        case 1: return launch_instance<0, 1, true>(prm, grid, st);
+        case 2: return launch_instance<0, 2, true>(prm, grid, st);
+        case 3: return launch_instance<0, 3, true>(prm, grid, st);
+        case 4: return launch_instance<0, 4, true>(prm, grid, st);
+        case 5: return launch_instance<0, 5, true>(prm, grid, st);
+        case 6: return launch_instance<0, 6, true>(prm, grid, st);
+        case 7: return launch_instance<0, 7, true>(prm, grid, st);
+        case 8: return launch_instance<0, 8, true>(prm, grid, st);
+    }
+    set_error("latent dimension %d outside [1, %d]", prm.d, MAXD);
+    return GPMDM_E_UNSUPPORTED;
 }
 
 template <int KIND>
@@ -652,12 +707,27 @@ extern "C" int gpmdm_pf_propagate_f64(const gpmdm_gp_model* dyn, const double* x
 
 static int observe_impl(const gpmdm_gp_model* obs, const double* x, int64_t P, const double* z, double ll_const,
                         const double* v_in, double* ll, double* mu_out, double* v_out, int32_t* tile_counter,
-                        void* stream);
+                        void* stream, void* kstar_ws = nullptr, int64_t kstar_ws_bytes = 0, int64_t n_pad = 0);
 
 extern "C" int gpmdm_pf_observe_f64(const gpmdm_gp_model* obs, const double* x, int64_t P, const double* z,
                                     double ll_const, double* ll, double* mu_out, double* v_out, int32_t* tile_counter,
                                     void* stream) {
     return observe_impl(obs, x, P, z, ll_const, nullptr, ll, mu_out, v_out, tile_counter, stream);
+}
+
+// Same call with a scratch for the K* cache (see gp_predict_kernel<.., CACHE>): one slice of n_pad x 64 doubles per CTA.
+extern "C" int64_t gpmdm_pf_observe_kstar_workspace_bytes(int64_t n_pad) {
+    return (int64_t)num_sms() * n_pad * TM * 8;
+}
+
+extern "C" int gpmdm_pf_observe_cached_f64(const gpmdm_gp_model* obs, const double* x, int64_t P, const double* z,
+                                           double ll_const, double* ll, double* mu_out, double* v_out,
+                                           int64_t n_pad, int32_t* tile_counter, void* kstar_ws,
+                                           int64_t kstar_ws_bytes, void* stream) {
+    GPMDM_REQUIRE(kstar_ws != nullptr && kstar_ws_bytes > 0, GPMDM_E_INVALID, "K* workspace is required");
+    GPMDM_REQUIRE(n_pad > 0 && n_pad % TN == 0, GPMDM_E_INVALID, "n_pad must be the block's padded size (multiple of %d)", TN);
+    return observe_impl(obs, x, P, z, ll_const, nullptr, ll, mu_out, v_out, tile_counter, stream, kstar_ws,
+                        kstar_ws_bytes, n_pad);
 }
 
 extern "C" int gpmdm_pf_loglik_f64(const gpmdm_gp_model* obs, const double* x, int64_t P, const double* z,
@@ -669,7 +739,7 @@ extern "C" int gpmdm_pf_loglik_f64(const gpmdm_gp_model* obs, const double* x, i
 
 static int observe_impl(const gpmdm_gp_model* obs, const double* x, int64_t P, const double* z, double ll_const,
                         const double* v_in, double* ll, double* mu_out, double* v_out, int32_t* tile_counter,
-                        void* stream) {
+                        void* stream, void* kstar_ws, int64_t kstar_ws_bytes, int64_t ws_n_pad) {
     if (int rc = validate_model(obs, 0)) return rc;
     GPMDM_REQUIRE(P >= 0 && P < (1ll << 31), GPMDM_E_INVALID, "P = %lld out of range", (long long)P);
     if (P == 0) return 0;
@@ -693,6 +763,14 @@ static int observe_impl(const gpmdm_gp_model* obs, const double* x, int64_t P, c
     const long long n_tiles = (P + TM - 1) / TM;
     const int grid = (int)(n_tiles < num_sms() ? n_tiles : num_sms());
     prm.round_sync = (n_tiles >= 2ll * grid && n_tiles < (1ll << 20)) ? 1 : 0;
+    if (kstar_ws) {
+        prm.kcache = static_cast<double*>(kstar_ws);
+        prm.kcache_stride = (long long)ws_n_pad * TM;  // the kernel traps if the block on the device is larger
+        GPMDM_REQUIRE((int64_t)grid * prm.kcache_stride * 8 <= kstar_ws_bytes, GPMDM_E_INVALID,
+                      "K* workspace too small: %lld bytes for %d CTAs x n_pad %lld", (long long)kstar_ws_bytes, grid,
+                      (long long)ws_n_pad);
+        return dispatch_d_cached(prm, grid, st);
+    }
     return dispatch_d<0>(prm, grid, st);
 }
 

@@ -21,6 +21,7 @@ What differs by design (B200-first):
 from __future__ import annotations
 
 import ctypes
+import os
 import time
 from pathlib import Path
 from typing import List, Optional
@@ -632,15 +633,32 @@ class GPMDM(torch.nn.Module):
         return ws
 
     # ---- prediction (gpmdm.py:923-963, 1032-1068) ----------------------------------------------------------
+    KSTAR_CACHE_MIN_TILES = 4  # column tiles of L from which caching K* pays (a K* entry is reused nq/2 times)
+
+    def _use_kstar_cache(self, n_pad, kstar_cache):
+        env = os.environ.get("GPMDM_KSTAR_CACHE")
+        if kstar_cache is None and env is not None:
+            kstar_cache = env not in ("0", "")
+        return (n_pad // TILE_N >= self.KSTAR_CACHE_MIN_TILES) if kstar_cache is None else bool(kstar_cache)
+
+    def _kstar_workspace(self, n_pad):
+        need = int(_cabi.lib().gpmdm_pf_observe_kstar_workspace_bytes(n_pad)) // 8
+        ws = getattr(self, "_ws_kstar", None)
+        if ws is None or ws.numel() < need:
+            self._ws_kstar = ws = torch.empty(need, dtype=self.dtype, device=self.device)
+        return ws
+
     def _scratch_counter(self):
         if getattr(self, "_counter", None) is None:
             self._counter = torch.zeros(4, dtype=torch.int32, device=self.device)
         return self._counter
 
     @torch.no_grad()
-    def map_x_to_y(self, Xstar, flg_noise=False, precision="fp64", low_latency=None):
+    def map_x_to_y(self, Xstar, flg_noise=False, precision="fp64", low_latency=None, kstar_cache=None):
         """precision: 'fp64' (exact path, DMMA) or 'tf32' (tcgen05 variant, ~1e-4 relative; an addition).
-        low_latency: None = automatic (few particles: split the column tiles over the SMs), True / False to force."""
+        low_latency: None = automatic (few particles: split the column tiles over the SMs), True / False to force.
+        kstar_cache: None = automatic (fused mode, N_pad >= 1024: K* of a particle tile is evaluated once into a per-SM
+        scratch); True / False to force.  Bit-identical results either way."""
         lib = _cabi.lib()
         Xs = to_tensor(Xstar, self.dtype, self.device).contiguous()
         P = Xs.shape[0]
@@ -663,6 +681,11 @@ class GPMDM(torch.nn.Module):
                 check(lib.gpmdm_pf_observe_lowlat_f64(ctypes.byref(pk["obs"]), ptr(Xs), P, None, 0.0, None, None, ptr(mu),
                                                       ptr(v), pk["obs_n_pad"], ptr(self._scratch_counter()), ptr(ws),
                                                       stream()), "gpmdm_pf_observe_lowlat_f64")
+            elif P > 0 and self._use_kstar_cache(pk["obs_n_pad"], kstar_cache):
+                ws = self._kstar_workspace(pk["obs_n_pad"])
+                check(lib.gpmdm_pf_observe_cached_f64(ctypes.byref(pk["obs"]), ptr(Xs), P, None, 0.0, None, ptr(mu),
+                                                      ptr(v), pk["obs_n_pad"], ptr(self._scratch_counter()), ptr(ws),
+                                                      ws.numel() * 8, stream()), "gpmdm_pf_observe_cached_f64")
             else:
                 check(lib.gpmdm_pf_observe_f64(ctypes.byref(pk["obs"]), ptr(Xs), P, None, 0.0, None, ptr(mu), ptr(v),
                                                ptr(self._scratch_counter()), stream()), "gpmdm_pf_observe_f64")

@@ -48,7 +48,7 @@ class GPMDM_PF:
     def __init__(self, gpmdm: GPMDM, markov_switching_model, num_particles: int, *,
                  seed: int = 0, resampling: str = "multinomial", cdf_order: str = "sequential",
                  tri: bool = True, precision: str = "fp64", low_latency: Optional[bool] = None,
-                 init_indices: Optional[Sequence] = None, process_group=None,
+                 kstar_cache: Optional[bool] = None, init_indices: Optional[Sequence] = None, process_group=None,
                  distributed: Optional[bool] = None):
         """
         gpmdm, markov_switching_model [C, C], num_particles: as the reference (:47-50).
@@ -61,6 +61,9 @@ class GPMDM_PF:
                         tf32 products and the whitened variance (~1e-4 relative); dynamics / resampling stay fp64
         low_latency     None = automatic: with fewer 64-particle tiles than SMs the column tiles of each particle tile are
                         split over the SMs (two kernels per GP stage instead of one); True / False to force
+        kstar_cache     None = automatic: the fused fp64 observation kernel keeps each particle tile's cross-kernel K* in a
+                        per-SM scratch (#SMs x N_pad x 64 doubles) instead of re-evaluating it for every column tile;
+                        bit-identical results; True / False to force
         init_indices    optional per-class index tensors replacing torch.randint in _init_particles (:113)
         """
         self._lib = _cabi.lib()
@@ -94,6 +97,8 @@ class GPMDM_PF:
         c32 = float(0.5 * self._gpmdm.D * _LOG_2PI)  # fp32 product, as gpmdm_pf.py:191
         self._ll_const = self._packed["ll_const_terms"] - c32
         self._lowlat = gpmdm._use_lowlat(self._hi - self._lo, low_latency)
+        self._kstar_cache = (precision == "fp64" and not self._lowlat
+                             and gpmdm._use_kstar_cache(self._packed["obs_n_pad"], kstar_cache))
         self._alloc()
         self._init_particles(init_indices)
 
@@ -118,6 +123,7 @@ class GPMDM_PF:
             need = max(int(self._lib.gpmdm_predict_lowlat_workspace_bytes(Pl, self._packed["obs_n_pad"], self.observation_dim)),
                        int(self._lib.gpmdm_predict_lowlat_workspace_bytes(Pl, self._packed["dyn_max_n_pad"], d)))
             self._ws_lowlat = torch.empty(need // 8 + 1, dtype=torch.float64, device=dev)
+        self._ws_kstar = self._gpmdm._kstar_workspace(self._packed["obs_n_pad"]) if self._kstar_cache else None
 
     # ---- initialisation (gpmdm_pf.py:87-115) -------------------------------------------------------------------
     def _init_particles(self, init_indices=None):
@@ -205,6 +211,11 @@ class GPMDM_PF:
                                                   self._ll_const, None, ptr(ll_l), None, None, self._packed["obs_n_pad"],
                                                   ptr(self._counter), ptr(self._ws_lowlat), st),
                   "gpmdm_pf_observe_lowlat_f64")
+        elif self._kstar_cache:
+            check(lib.gpmdm_pf_observe_cached_f64(ctypes.byref(self._packed["obs"]), ptr(x_new_l), Pl, ptr(z),
+                                                  self._ll_const, ptr(ll_l), None, None, self._packed["obs_n_pad"],
+                                                  ptr(self._counter), ptr(self._ws_kstar), self._ws_kstar.numel() * 8, st),
+                  "gpmdm_pf_observe_cached_f64")
         else:
             check(lib.gpmdm_pf_observe_f64(ctypes.byref(self._packed["obs"]), ptr(x_new_l), Pl, ptr(z), self._ll_const,
                                            ptr(ll_l), None, None, ptr(self._counter), st), "gpmdm_pf_observe_f64")

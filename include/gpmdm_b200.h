@@ -122,6 +122,17 @@ int gpmdm_pf_propagate_f64(const gpmdm_gp_model* dyn, const double* x_prev, cons
 int gpmdm_pf_observe_f64(const gpmdm_gp_model* obs, const double* x, int64_t P, const double* z, double ll_const,
                          double* ll, double* mu_out, double* v_out, int32_t* tile_counter, void* stream);
 
+/* The same call with a K* cache: each CTA evaluates the cross-kernel of its 64-particle tile against all n_pad training
+ * rows once (the N x P_tile slice of get_y_kernel(X, X*), gpmdm.py:955) into its slice of `kstar_ws`, already in
+ * tensor-core fragment order, and the contraction re-reads it for every column tile instead of re-evaluating the
+ * exponentials.  Results are bit-identical to gpmdm_pf_observe_f64.  n_pad: padded size of the observation block;
+ * kstar_ws: device scratch of gpmdm_pf_observe_kstar_workspace_bytes(n_pad) bytes (#SMs x n_pad x 64 doubles),
+ * contents undefined before and after. */
+int64_t gpmdm_pf_observe_kstar_workspace_bytes(int64_t n_pad);
+int gpmdm_pf_observe_cached_f64(const gpmdm_gp_model* obs, const double* x, int64_t P, const double* z,
+                                double ll_const, double* ll, double* mu_out, double* v_out, int64_t n_pad,
+                                int32_t* tile_counter, void* kstar_ws, int64_t kstar_ws_bytes, void* stream);
+
 /* Mean and log-likelihood only, with the predictive variances v_in [P] supplied by the caller (the tf32 variant
  * computes them on tcgen05 tensor cores): the N x D mean contraction stays in fp64 because alpha = K^-1 Y cancels
  * heavily; it is 2ND of the 2N^2 + 2ND flops.  The blocks of `obs` may have L == NULL for this call. */

@@ -42,6 +42,30 @@ def test_observation_gp_vs_oracle(cfg1, P, low_latency):
     assert scaled_err(var.cpu(), var_o, lam) < TOL
 
 
+@pytest.mark.parametrize("P", [1, 65, 3000, 25000])
+def test_kstar_cache_is_bit_identical_to_on_the_fly_evaluation(cfg1, P):
+    """The cached instantiation of the observation kernel (K* of a particle tile evaluated once into the per-SM scratch)
+    against the one that re-evaluates K* per column tile: same values, bit for bit -- also over several rounds of
+    particle tiles per CTA (P = 25 000: 391 tiles on 148 SMs), where every scratch slice is overwritten and re-read."""
+    from gpmdm_b200 import GPMDM_PF
+
+    spec, wl, f, model = cfg1
+    xs = particles_near_data(spec, P, 9).cuda()
+    mu_c, var_c = model.map_x_to_y(xs, low_latency=False, kstar_cache=True)
+    mu_f, var_f = model.map_x_to_y(xs, low_latency=False, kstar_cache=False)
+    assert torch.equal(mu_c, mu_f) and torch.equal(var_c, var_f)
+    if P >= 3000:
+        T = synthetic.markov_matrix(spec.n_classes)
+        lls = []
+        for cache in (True, False):
+            pf = GPMDM_PF(model, T, P, seed=4, low_latency=False, kstar_cache=cache)
+            assert pf._kstar_cache == cache
+            for z in wl.test_trials[0][1][:2]:
+                pf.update(z)
+            lls.append((pf._log_likelihoods.clone(), pf._particle_states.clone(), pf.last_ancestors.clone()))
+        assert all(torch.equal(a, b) for a, b in zip(*lls))
+
+
 @pytest.mark.parametrize("low_latency", [False, True])
 @pytest.mark.parametrize("P", [1, 100, 1000])
 def test_dynamics_gp_vs_oracle(cfg1, P, low_latency):
