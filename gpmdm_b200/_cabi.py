@@ -34,7 +34,10 @@ class GpModelTf32(ctypes.Structure):
 _SIGNATURES = {
     "gpmdm_abi_version": (ctypes.c_int, []),
     "gpmdm_last_error": (ctypes.c_char_p, []),
+    "gpmdm_quadform_bytes": (_i64, [_i64, ctypes.c_int]),
     "gpmdm_pack_quadform_f64": (ctypes.c_int, [_ptr, _i64, _i64, ctypes.c_int, _ptr, _ptr]),
+    "gpmdm_alpha_bytes": (_i64, [_i64, _i32]),
+    "gpmdm_pack_alpha_f64": (ctypes.c_int, [_ptr, _i64, _i64, _i32, _i32, _ptr, _ptr]),
     "gpmdm_pf_transition_f64": (ctypes.c_int, [_ptr, _ptr, _ptr, _i64, _i32, _ptr, _ptr]),
     "gpmdm_pf_bucket_by_class": (ctypes.c_int, [_ptr, _i64, _i32, _ptr, _ptr, _ptr, _ptr, _ptr]),
     "gpmdm_pf_propagate_f64": (ctypes.c_int, [ctypes.POINTER(GpModel), _ptr, _ptr, _ptr, _ptr, _i64, _ptr, _ptr,
@@ -92,7 +95,7 @@ def lib() -> ctypes.CDLL:
         for name, (res, args) in _SIGNATURES.items():
             fn = getattr(handle, name)  # AttributeError if the build is stale
             fn.restype, fn.argtypes = res, args
-        if handle.gpmdm_abi_version() != 1:
+        if handle.gpmdm_abi_version() != 2:
             raise RuntimeError("libgpmdm_sm100a.so ABI version mismatch; rebuild")
         _lib = handle
     return _lib

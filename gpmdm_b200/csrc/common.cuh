@@ -106,6 +106,12 @@ __device__ __forceinline__ double warp_max(double v) {
     return v;
 }
 
+// first stored row of column panel t of L, and the row offset of that panel in the packed array (gpmdm_gp_block)
+__host__ __device__ __forceinline__ long long panel_first_row(int t, int tri) { return tri ? (long long)t * GPMDM_TILE_N : 0; }
+__host__ __device__ __forceinline__ long long panel_row_offset(long long t, long long n_pad, int tri) {
+    return tri ? t * n_pad - (GPMDM_TILE_N / 2) * t * (t - 1) : t * n_pad;
+}
+
 inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 
 }  // namespace gpmdm

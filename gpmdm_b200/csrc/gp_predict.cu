@@ -47,7 +47,8 @@ constexpr int TN = GPMDM_TILE_N;  // columns per column tile
 constexpr int KC = 16;            // k rows per chunk
 constexpr int STAGES = 6;         // B / record ring depth (TMA)
 constexpr int AHEAD = 3;          // chunks in flight ahead of the consumers
-constexpr int LDB = TN + 4;
+constexpr int LDB = GPMDM_PANEL_LD;  // = TN + 4
+static_assert(LDB == TN + 4, "panel pitch");
 constexpr int NTHREADS = 256;
 constexpr int NWARPS = NTHREADS / 32;
 constexpr int MAXD = GPMDM_MAX_LATENT;
@@ -319,21 +320,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) gp_predict_kernel(const PredictPa
         auto issue_b = [&]() {
             const int st = pst;
             mbar_wait(&s.empty[st], pph ^ 1);  // first fill of a stage passes immediately
-            const double* src;
-            int ld;
-            if (bcur.ct < nq) {
-                src = gbk.L + (long long)bcur.ct * TN;
-                ld = n_pad;
-            } else {
-                src = gbk.alpha + (long long)(bcur.ct - nq) * TN;
-                ld = prm.alpha_ld;
+            // 16 consecutive rows of a column panel are contiguous in the packed factors: ONE bulk copy per chunk
+            const long long row0 = (long long)bcur.k * KC;
+            const double* src =
+                bcur.ct < nq ? gbk.L + (panel_row_offset(bcur.ct, n_pad, prm.tri) + row0 - panel_first_row(bcur.ct, prm.tri)) * LDB
+                             : gbk.alpha + ((long long)(bcur.ct - nq) * n_pad + row0) * LDB;
+            if (lane == 0) {
+                // the training records feed the on-the-fly K* prologue only: not needed with the K* cache
+                mbar_expect_tx(&s.full[st], (uint32_t)(KC * LDB * 8 + (CACHE ? 0 : KC * REC * 8)));
+                bulk_g2s(&s.B[st][0][0], src, KC * LDB * 8, &s.full[st]);
+                if (!CACHE)
+                    bulk_g2s(&s.R[st][0], gbk.coords + (long long)bcur.k * KC * REC, (uint32_t)(KC * REC * 8), &s.full[st]);
             }
-            if (lane == 0) mbar_expect_tx(&s.full[st], (uint32_t)(KC * TN * 8 + KC * REC * 8));
-            __syncwarp();
-            for (int row = lane; row < KC; row += 32)
-                bulk_g2s(&s.B[st][row][0], src + (long long)(bcur.k * KC + row) * ld, TN * 8, &s.full[st]);
-            if (lane == 0)
-                bulk_g2s(&s.R[st][0], gbk.coords + (long long)bcur.k * KC * REC, (uint32_t)(KC * REC * 8), &s.full[st]);
         };
 #define GPMDM_ADVANCE(st_, ph_)   \
     if (++(st_) == STAGES) {      \

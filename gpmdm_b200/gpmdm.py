@@ -537,11 +537,12 @@ class GPMDM(torch.nn.Module):
         coords[:n, :rec.shape[1]] = rec
         Kinv = Kinv.contiguous()
         L = None
-        if with_L:
-            L = torch.empty(n_pad, n_pad, dtype=self.dtype, device=self.device)
+        if with_L:  # column panels of the quadratic-form matrix (include/gpmdm_b200.h: gpmdm_gp_block)
+            L = torch.empty(int(lib.gpmdm_quadform_bytes(n_pad, int(tri))) // 8, dtype=self.dtype, device=self.device)
             check(lib.gpmdm_pack_quadform_f64(ptr(Kinv), n, n_pad, int(tri), ptr(L), stream()), "gpmdm_pack_quadform_f64")
-        alpha = torch.zeros(n_pad, alpha_ld, dtype=self.dtype, device=self.device)
-        alpha[:n, :targets.shape[1]] = torch.matmul(Kinv.t(), targets)
+        A = torch.matmul(Kinv.t(), targets).contiguous()
+        alpha = torch.empty(int(lib.gpmdm_alpha_bytes(n_pad, alpha_ld)) // 8, dtype=self.dtype, device=self.device)
+        check(lib.gpmdm_pack_alpha_f64(ptr(A), n, n_pad, A.shape[1], alpha_ld, ptr(alpha), stream()), "gpmdm_pack_alpha_f64")
         return dict(coords=coords, L=L, alpha=alpha, n=n, n_pad=n_pad)
 
     @torch.no_grad()

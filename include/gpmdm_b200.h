@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define GPMDM_ABI_VERSION 1
+#define GPMDM_ABI_VERSION 2
 
 #define GPMDM_E_INVALID (-1)     /* bad size / null pointer / unsupported dimension            */
 #define GPMDM_E_UNSUPPORTED (-2) /* valid request outside this build's limits (d > 8, ...)      */
@@ -35,6 +35,7 @@ extern "C" {
 
 #define GPMDM_TILE_P 64    /* particles per tile of the predict kernels                        */
 #define GPMDM_TILE_N 256   /* column-tile width: row padding of factors, granularity of alpha_ld */
+#define GPMDM_PANEL_LD 260 /* row pitch (doubles) of the L / alpha column panels = shared-memory pitch  */
 #define GPMDM_MAX_LATENT 8 /* latent dimension limit of the kernels                             */
 
 /* One GP "block": the observation GP is a single block over all N training frames; the dynamics GP
@@ -44,11 +45,21 @@ extern "C" {
  *   coords [n_pad, rec]  per training row i:  a_i[0..d) , (dynamics only) c_k^2 * x_i[k] for k in [0, d), then
  *                        zero padding to an even width: rec = (d + 1) & ~1 (kind 0), (2d + 1) & ~1 (kind 1);
  *                        a_i = x_i / lengthscale  (gpmdm.py:508-517, 545-548); zero rows pad.
- *   L      [n_pad, n_pad] quadratic-form matrix such that  k^T K^-1 k == k^T L k :
- *                        tri = 1:  L[i][j] = Kinv[i][j] + Kinv[j][i] (i > j), Kinv[i][i], 0 (i < j)
- *                        tri = 0:  L = Kinv.   Zero padded.  (written by gpmdm_pack_quadform_f64)
- *   alpha  [n_pad, alpha_ld] = Kinv^T * targets (Y for the observation GP, Xout_c for dynamics),
- *                        zero padded to alpha_ld = multiple of GPMDM_TILE_N columns.
+ *   L      quadratic-form matrix Q such that  k^T K^-1 k == k^T Q k :
+ *                        tri = 1:  Q[i][j] = Kinv[i][j] + Kinv[j][i] (i > j), Kinv[i][i], 0 (i < j)
+ *                        tri = 0:  Q = Kinv.   Zero padded to n_pad.
+ *                        Stored as COLUMN PANELS in the order the kernel streams them: panel t holds columns
+ *                        [256 t, 256 t + 256) of the rows k >= kb(t) (kb = 256 t for tri = 1 -- the rows above are
+ *                        zero and are neither stored nor read -- and 0 for tri = 0), each row padded to
+ *                        GPMDM_PANEL_LD = 260 doubles (the shared-memory row pitch that makes the tensor-core
+ *                        fragment loads bank-conflict free), panels back to back.  Any 16 consecutive rows of a
+ *                        panel are one contiguous 33 280-byte block = one TMA bulk copy.  tri = 1 takes
+ *                        ~half the memory of the dense matrix (1.68 GB instead of 3.27 GB at N = 20 000).
+ *                        Size: gpmdm_quadform_bytes(n_pad, tri); written by gpmdm_pack_quadform_f64.
+ *   alpha  = Kinv^T * targets (Y for the observation GP, Xout_c for dynamics), zero padded to n_pad rows and
+ *                        alpha_ld = multiple of GPMDM_TILE_N columns, in the same panel layout:
+ *                        [alpha_ld / 256][n_pad][260].  Size: gpmdm_alpha_bytes(n_pad, alpha_ld); written by
+ *                        gpmdm_pack_alpha_f64.
  */
 typedef struct gpmdm_gp_block {
     const double* coords;
@@ -78,8 +89,13 @@ const char* gpmdm_last_error(void);
 
 /* ---- factor packing ------------------------------------------------------------------------------
  * Kinv [n, n] (e.g. the reference's Ky_inv, or a diagonal block of Kx_inv_class[c],
- * gpmdm.py:1289,1305) -> L [n_pad, n_pad] as described on gpmdm_gp_block. */
+ * gpmdm.py:1289,1305) -> the column panels of L described on gpmdm_gp_block. */
+int64_t gpmdm_quadform_bytes(int64_t n_pad, int tri);
 int gpmdm_pack_quadform_f64(const double* Kinv, int64_t n, int64_t n_pad, int tri, double* L, void* stream);
+/* A [n, dout] row-major (= Kinv^T * targets: K_y^-1 Y of gpmdm.py:957, K_c^-1 Xout of :1064) -> alpha panels. */
+int64_t gpmdm_alpha_bytes(int64_t n_pad, int32_t alpha_ld);
+int gpmdm_pack_alpha_f64(const double* A, int64_t n, int64_t n_pad, int32_t dout, int32_t alpha_ld, double* alpha,
+                         void* stream);
 
 /* ---- filter step ------------------------------------------------------------------------------ */
 
