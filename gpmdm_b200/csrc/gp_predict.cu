@@ -206,18 +206,28 @@ __device__ __forceinline__ void kstar_multi(const double* __restrict__ recs, int
     }
 }
 
-// Chunk schedule of one particle tile: column tile ct covers k-chunks [kbeg(ct), nkc).
+// Chunk schedule of one particle tile: column tile ct covers k-chunks [kbeg(ct), nkc).  `src` follows the chunk through
+// the packed column panels incrementally (one add per chunk; the panel base is recomputed only when the tile changes).
 struct ChunkCursor {
     int ct, k, nq, nct, nkc, tri;
+    const double *L, *alpha, *src;
+    long long n_pad;
     __device__ __forceinline__ int kbeg(int t) const { return (tri && t < nq) ? t * (TN / KC) : 0; }
-    __device__ __forceinline__ void init(int nq_, int nct_, int nkc_, int tri_, int ct0) {
+    __device__ __forceinline__ const double* base(int t) const {
+        return t < nq ? L + panel_row_offset(t, n_pad, tri) * LDB : alpha + (long long)(t - nq) * n_pad * LDB;
+    }
+    __device__ __forceinline__ void init(int nq_, int nct_, int nkc_, int tri_, int ct0, const gpmdm_gp_block& b) {
         nq = nq_, nct = nct_, nkc = nkc_, tri = tri_, ct = ct0, k = kbeg(ct0);
+        L = b.L, alpha = b.alpha, n_pad = b.n_pad;
+        src = ct < nct ? base(ct) : nullptr;
     }
     __device__ __forceinline__ bool done() const { return ct >= nct; }
     __device__ __forceinline__ void next() {
+        src += KC * LDB;
         if (++k == nkc) {
             ct++;
             k = kbeg(ct);
+            if (ct < nct) src = base(ct);
         }
     }
 };
@@ -315,16 +325,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) gp_predict_kernel(const PredictPa
 
         // ---- TMA issue: all warps advance the same cursor, the duty warp issues ------------------------------
         ChunkCursor bcur;
-        bcur.init(nq, ct_end, nkc, prm.tri, ct_begin);
+        bcur.init(nq, ct_end, nkc, prm.tri, ct_begin, gbk);
         int pst = cst, pph = cph;  // producer: stage / parity of the next chunk to issue
         auto issue_b = [&]() {
             const int st = pst;
             mbar_wait(&s.empty[st], pph ^ 1);  // first fill of a stage passes immediately
             // 16 consecutive rows of a column panel are contiguous in the packed factors: ONE bulk copy per chunk
-            const long long row0 = (long long)bcur.k * KC;
-            const double* src =
-                bcur.ct < nq ? gbk.L + (panel_row_offset(bcur.ct, n_pad, prm.tri) + row0 - panel_first_row(bcur.ct, prm.tri)) * LDB
-                             : gbk.alpha + ((long long)(bcur.ct - nq) * n_pad + row0) * LDB;
+            const double* src = bcur.src;
             if (lane == 0) {
                 // the training records feed the on-the-fly K* prologue only: not needed with the K* cache
                 mbar_expect_tx(&s.full[st], (uint32_t)(KC * LDB * 8 + (CACHE ? 0 : KC * REC * 8)));
@@ -370,7 +377,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gp_predict_kernel(const PredictPa
         }
 
         ChunkCursor cur;
-        cur.init(nq, ct_end, nkc, prm.tri, ct_begin);
+        cur.init(nq, ct_end, nkc, prm.tri, ct_begin, gbk);
         double qacc = 0.0, sacc = 0.0, vrow = 0.0;
         if (KIND == 0 && prm.v_in) vrow = pidx >= 0 ? prm.v_in[pidx] : 1.0;
 
