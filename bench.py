@@ -317,12 +317,24 @@ def run_ours(a):
         if a.precision == "fp64":
             tf = ctypes_probe(lib)
             achieved = flops_alg / (obs_avg_ms * 1e-3) / 1e12
+            cached = bool(getattr(pf, "_kstar_cache", False))
+            tiles = (Pl + 63) // 64
+            # DRAM bytes per 64-particle tile from the ncu launch list of this command at P = 131072
+            # (profiles/launches_r01.txt): (4454.3 + 106.6) GB over 5 launches of 2048 tiles.  With the K* cache the
+            # kernel trades the exp re-evaluation for re-reading the tile's K* slice (n_pad x 64 doubles) once per column tile.
+            per_tile = (4454.346e9 + 106.627e9) / 5 / 2048 if cached and N == 20000 and not a.dense else None
             roofline = {
                 "bound": "tensor", "achieved": achieved, "peak": tf, "unit": "TFLOP/s", "frac": achieved / tf,
-                "traffic": None,
-                "traffic_note": "not measurable live; ncu (profiles/launches_r01.txt): 1.74 GB of DRAM reads per round of 148 "
-                                "particle tiles (L + alpha read once per round; the rounds are kept in L2 lockstep)",
-                "kernel": f"gp_predict_kernel<0,{d}> (gpmdm_pf_observe_f64)", "launch_ms": obs_avg_ms,
+                "traffic": per_tile * tiles if per_tile else None,
+                "traffic_note": "DRAM bytes per launch = ncu-measured bytes per 64-particle tile (launch list of this command at "
+                                "P=131072, profiles/launches_r01.txt: 445 MB per tile, of which 12 MB are L + alpha -- read "
+                                "once per round of 148 tiles, the rounds are kept in L2 lockstep -- and the rest is the per-SM "
+                                "K* cache being re-read once per column tile: 557 GB/s = 8.6 % of the HBM peak, traded for "
+                                "the exp work on the fp64 datapath) x the tiles of this launch"
+                                if per_tile else "not measured for this configuration",
+                "kernel": f"gp_predict_kernel<0,{d},{'true' if cached else 'false'}> "
+                          f"({'gpmdm_pf_observe_cached_f64' if cached else 'gpmdm_pf_observe_f64'})",
+                "launch_ms": obs_avg_ms,
                 "peak_source": "fp64 mma.sync m8n8k4 issue-rate probe measured in this run (MEASURED_PEAKS.json holds "
                                "no fp64 figure)",
                 "executed_tflops": flops_exec / (obs_avg_ms * 1e-3) / 1e12,

@@ -185,6 +185,41 @@ def test_filter_trial_vs_oracle(cfg1, P, low_latency):
         assert abs(pf.log_likelihood() - float(orc.weighted_log_sum(ll_gpu, lw_o))) < 1e-12 * abs(pf.log_likelihood())
 
 
+@pytest.mark.parametrize("tri", [0, 1])
+def test_factor_panels_hold_the_quadratic_form_matrix(tri):
+    """gpmdm_pack_quadform_f64 / gpmdm_pack_alpha_f64 against a numpy construction of the column-panel layout
+    (include/gpmdm_b200.h: gpmdm_gp_block): panel t = columns [256 t, 256 t + 256) of rows >= 256 t (tri) / all rows,
+    row pitch 260, zero padded."""
+    from gpmdm_b200 import _cabi
+    from gpmdm_b200._cabi import check, ptr, stream
+
+    lib = _cabi.lib()
+    n, n_pad, dout, ald = 600, 768, 300, 512
+    g = torch.Generator().manual_seed(1)
+    Kinv = torch.randn(n, n, dtype=torch.float64, generator=g)
+    Q = Kinv.clone() if not tri else torch.tril(Kinv, -1) + torch.tril(Kinv.t(), -1) + torch.diag(torch.diagonal(Kinv))
+    Qp = torch.zeros(n_pad, n_pad, dtype=torch.float64)
+    Qp[:n, :n] = Q
+    want = []
+    for t in range(n_pad // 256):
+        rows = Qp[(256 * t if tri else 0):, 256 * t:256 * t + 256]
+        want.append(torch.cat([rows, torch.zeros(rows.shape[0], 4, dtype=torch.float64)], 1))
+    want = torch.cat(want, 0).reshape(-1)
+    assert int(lib.gpmdm_quadform_bytes(n_pad, tri)) == want.numel() * 8
+    L = torch.full((want.numel(),), float("nan"), dtype=torch.float64, device="cuda")
+    check(lib.gpmdm_pack_quadform_f64(ptr(Kinv.cuda()), n, n_pad, tri, ptr(L), stream()), "pack")
+    assert torch.equal(L.cpu(), want)
+    A = torch.randn(n, dout, dtype=torch.float64, generator=g)
+    Ap = torch.zeros(ald // 256, n_pad, 260, dtype=torch.float64)
+    for t in range(ald // 256):
+        w = min(256, dout - 256 * t)
+        Ap[t, :n, :w] = A[:, 256 * t:256 * t + w]
+    assert int(lib.gpmdm_alpha_bytes(n_pad, ald)) == Ap.numel() * 8
+    out = torch.full((Ap.numel(),), float("nan"), dtype=torch.float64, device="cuda")
+    check(lib.gpmdm_pack_alpha_f64(ptr(A.cuda()), n, n_pad, dout, ald, ptr(out), stream()), "pack alpha")
+    assert torch.equal(out.cpu(), Ap.reshape(-1))
+
+
 def test_bucket_by_class_is_a_stable_partition():
     from gpmdm_b200 import _cabi
 
@@ -389,6 +424,11 @@ def test_other_latent_and_observation_dimensions_vs_oracle(C, d, D):
     assert scaled_err(mu.cpu(), mu_o, scale) < TOL
     lam = (torch.exp(spec.y_log_lambdas) ** -2).unsqueeze(0).expand(var_o.shape)
     assert scaled_err(var.cpu(), var_o, lam) < TOL
+    # fused mode, with and without the K* cache (these template instances are otherwise only reached in low-latency mode)
+    mu_c, var_c = model.map_x_to_y(xs.cuda(), low_latency=False, kstar_cache=True)
+    mu_f, var_f = model.map_x_to_y(xs.cuda(), low_latency=False, kstar_cache=False)
+    assert torch.equal(mu_c, mu_f) and torch.equal(var_c, var_f)
+    assert scaled_err(mu_c.cpu(), mu_o, scale) < TOL and scaled_err(var_c.cpu(), var_o, lam) < TOL
     lam_x = torch.exp(spec.x_log_lambdas) ** -2
     for c in range(C):
         mean, dvar = model.map_x_dynamics_for_class(xs.cuda(), c)
