@@ -90,20 +90,43 @@ __global__ void __launch_bounds__(RT) combine_partials_kernel(const double* __re
 }
 
 // ---- class transition ----------------------------------------------------------------------------------
-__global__ void transition_kernel(const int64_t* __restrict__ c_prev, const double* __restrict__ T,
-                                  const double* __restrict__ E, long long P, int C, int64_t* __restrict__ c_new) {
+// The Exp(1) draws are the bulk of the traffic (8 C bytes per particle): each thread streams its row with 16-byte
+// loads issued ahead of the (sequential, first-maximum-wins) comparison chain; T lives in shared memory.
+__global__ void __launch_bounds__(256) transition_kernel(const int64_t* __restrict__ c_prev,
+                                                         const double* __restrict__ T, const double* __restrict__ E,
+                                                         long long P, int C, int64_t* __restrict__ c_new) {
+    extern __shared__ double sT[];  // [C][C]
+    for (int i = threadIdx.x; i < C * C; i += blockDim.x) sT[i] = T[i];
+    __syncthreads();
     const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= P) return;
-    const double* row = T + c_prev[p] * C;
+    const double* row = sT + c_prev[p] * C;
     const double* e = E + p * C;
-    double best = row[0] / e[0];
+    double best = -INFINITY;
     int arg = 0;
-    for (int j = 1; j < C; j++) {
-        const double q = row[j] / e[j];  // IEEE division, as torch's `dist / q`
-        if (q > best) {                  // first maximum wins, as torch.argmax
-            best = q;
-            arg = j;
+    int j = 0;
+    if ((C & 1) == 0) {  // rows are 16-byte aligned
+        for (; j + 8 <= C; j += 8) {
+            double2 v[4];
+#pragma unroll
+            for (int q = 0; q < 4; q++) v[q] = __ldcs(reinterpret_cast<const double2*>(e + j) + q);
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const double q0 = row[j + 2 * q] / v[q].x, q1 = row[j + 2 * q + 1] / v[q].y;  // IEEE division, as torch's `dist / q`
+                if (q0 > best || (j + 2 * q == 0)) best = q0, arg = j + 2 * q;  // first maximum wins, as torch.argmax
+                if (q1 > best) best = q1, arg = j + 2 * q + 1;
+            }
         }
+        for (; j + 2 <= C; j += 2) {
+            const double2 v = __ldcs(reinterpret_cast<const double2*>(e + j));
+            const double q0 = row[j] / v.x, q1 = row[j + 1] / v.y;
+            if (q0 > best || j == 0) best = q0, arg = j;
+            if (q1 > best) best = q1, arg = j + 1;
+        }
+    }
+    for (; j < C; j++) {
+        const double q = row[j] / __ldcs(e + j);
+        if (q > best || j == 0) best = q, arg = j;
     }
     c_new[p] = arg;
 }
@@ -547,10 +570,10 @@ extern "C" int64_t gpmdm_workspace_bytes(int64_t P, int32_t C) {
 
 extern "C" int gpmdm_pf_transition_f64(const int64_t* c_prev, const double* T, const double* E, int64_t P, int32_t C,
                                        int64_t* c_new, void* stream) {
-    GPMDM_REQUIRE(P >= 0 && C >= 1, GPMDM_E_INVALID, "bad sizes P=%lld C=%d", (long long)P, C);
+    GPMDM_REQUIRE(P >= 0 && C >= 1 && C <= 64, GPMDM_E_INVALID, "bad sizes P=%lld C=%d (1 <= C <= 64)", (long long)P, C);
     if (P == 0) return 0;
     GPMDM_REQUIRE(c_prev && T && E && c_new, GPMDM_E_INVALID, "null argument");
-    transition_kernel<<<nblocks(P, 256), 256, 0, (cudaStream_t)stream>>>(c_prev, T, E, P, C, c_new);
+    transition_kernel<<<nblocks(P, 256), 256, (size_t)C * C * sizeof(double), (cudaStream_t)stream>>>(c_prev, T, E, P, C, c_new);
     return check_launch("transition_kernel");
 }
 

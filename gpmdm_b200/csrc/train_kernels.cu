@@ -24,17 +24,22 @@ __constant__ double c_exp_table_train[64] = {GPMDM_EXP_TABLE_VALUES};
 
 // K is symmetric: one block computes a 64 x 64 tile (I <= J) once and writes it twice -- rows of tile (I, J) directly and
 // tile (J, I) through a shared-memory transpose -- so every exponential is evaluated once and both writes are coalesced.
-// Off-class tiles are zero-filled without any math.  256 threads, 16 elements each.
+// Off-class tiles are zero-filled without any math.  256 threads, 16 elements each.  The latent dimension and the kernel
+// kind are compile-time (ncu on the run-time-d version: 85 % issue-slot utilisation, i.e. instruction bound, not HBM
+// bound): the thread's column record stays in registers and the d-loops unroll.
 constexpr int BT = 64;
-__global__ void __launch_bounds__(256) kernel_build_kernel(const double* __restrict__ X, long long n, int d, int kind,
+template <int DL, int KIND>
+__global__ void __launch_bounds__(256) kernel_build_kernel(const double* __restrict__ X, long long n,
                                                            const double* __restrict__ ls,
                                                            const double* __restrict__ lin_c2, double noise2,
                                                            const int64_t* __restrict__ offs, int n_classes,
                                                            double* __restrict__ K) {
+    constexpr int d = DL;
+    constexpr int AW = (DL + 2) & ~1;  // a_i[0..d), |a_i|^2, padded to an even width (16-byte shared loads)
     const int I = blockIdx.y, J = blockIdx.x;
     if (J < I) return;
-    __shared__ double ai[BT][MAXD_T + 1], aj[BT][MAXD_T + 1];  // x / l and |x/l|^2
-    __shared__ double xi[BT][MAXD_T];  // c_k^2 x_ik
+    __shared__ __align__(16) double ai[BT][AW], aj[BT][AW];  // x / l and |x/l|^2
+    __shared__ __align__(16) double xi[BT][KIND == 1 ? ((DL + 1) & ~1) : 2];  // c_k^2 x_ik
     __shared__ int ci[BT], cj[BT];
     __shared__ double tile[BT][BT + 1];
     __shared__ double exptab[64];
@@ -46,11 +51,12 @@ __global__ void __launch_bounds__(256) kernel_build_kernel(const double* __restr
         const int r = t & (BT - 1);
         const long long row = (is_i ? i0 : j0) + r;
         double n2 = 0.0;
+#pragma unroll
         for (int k = 0; k < d; k++) {
             const double x = row < n ? X[row * d + k] : 0.0;
             const double a = x / ls[k];
             (is_i ? ai : aj)[r][k] = a;
-            if (is_i) xi[r][k] = (kind == 1) ? lin_c2[k] * x : 0.0;
+            if (KIND == 1 && is_i) xi[r][k] = lin_c2[k] * x;
             n2 = fma(a, a, n2);
         }
         (is_i ? ai : aj)[r][d] = n2;
@@ -58,31 +64,49 @@ __global__ void __launch_bounds__(256) kernel_build_kernel(const double* __restr
     }
     __syncthreads();
     const int tx = t & 63, ty = t >> 6;  // column within the tile, 4 row groups
-    const double c2last = kind == 1 ? lin_c2[d] : 0.0;
-    double xraw[MAXD_T];
-    if (kind == 1)
-        for (int k = 0; k < d; k++) xraw[k] = (j0 + tx < n) ? X[(j0 + tx) * d + k] : 0.0;
+    const double c2last = KIND == 1 ? lin_c2[d] : 0.0;
+    const long long j = j0 + tx;
+    double ajr[DL + 1], xraw[KIND == 1 ? DL : 1];
+#pragma unroll
+    for (int k = 0; k <= d; k++) ajr[k] = aj[tx][k];
+    if (KIND == 1) {
+#pragma unroll
+        for (int k = 0; k < d; k++) xraw[k] = j < n ? X[j * d + k] : 0.0;
+    }
+    const int cjx = cj[tx];
+    double* const kcol = K + j;
+#pragma unroll 4
     for (int r = ty; r < BT; r += 4) {
-        const long long i = i0 + r, j = j0 + tx;
+        const long long i = i0 + r;
         double v = 0.0;
-        if (i < n && j < n && (!offs || ci[r] == cj[tx])) {
+        if (i < n && j < n && (!offs || ci[r] == cjx)) {
+            double air[AW];
+#pragma unroll
+            for (int q = 0; q < AW; q += 2) {
+                const double2 w = *reinterpret_cast<const double2*>(&ai[r][q]);
+                air[q] = w.x, air[q + 1] = w.y;
+            }
             double dot = 0.0;
-            for (int k = 0; k < d; k++) dot = fma(ai[r][k], aj[tx][k], dot);
-            v = fast_exp(-(ai[r][d] + aj[tx][d] - 2.0 * dot), exptab);  // gpmdm.py:515-517 expansion form
+#pragma unroll
+            for (int k = 0; k < d; k++) dot = fma(air[k], ajr[k], dot);
+            v = fast_exp(-(air[d] + ajr[d] - 2.0 * dot), exptab);  // gpmdm.py:515-517 expansion form
             if (i == j) v += noise2;
-            if (kind == 1) {
+            if (KIND == 1) {
                 double lin = c2last;
+#pragma unroll
                 for (int k = 0; k < d; k++) lin = fma(xi[r][k], xraw[k], lin);
                 v += lin;
             }
         }
         tile[r][tx] = v;
-        if (i < n && j < n) K[i * n + j] = v;
+        if (i < n && j < n) kcol[i * n] = v;
     }
     if (I == J) return;
     __syncthreads();
+    const long long ii = i0 + tx;
+#pragma unroll 4
     for (int r = ty; r < BT; r += 4) {  // transposed copy: row (j0 + r), columns i0 + tx
-        const long long jj = j0 + r, ii = i0 + tx;
+        const long long jj = j0 + r;
         if (jj < n && ii < n) K[jj * n + ii] = tile[tx][r];
     }
 }
@@ -297,8 +321,20 @@ extern "C" int gpmdm_kernel_build_f64(const double* X, int64_t n, int32_t d, int
     GPMDM_REQUIRE(kind == 0 || (kind == 1 && lin_c2), GPMDM_E_INVALID, "kind 1 needs lin_c2");
     GPMDM_REQUIRE(class_offsets == nullptr || n_classes >= 1, GPMDM_E_INVALID, "bad class offsets");
     const unsigned g = (unsigned)((n + BT - 1) / BT);
-    kernel_build_kernel<<<dim3(g, g), 256, 0, (cudaStream_t)stream>>>(X, n, d, kind, lengthscales, lin_c2, noise2,
-                                                                      class_offsets, n_classes, K);
+    const dim3 grid(g, g);
+    cudaStream_t st = (cudaStream_t)stream;
+#define GPMDM_BUILD_CASE(DL)                                                                                          \
+    case DL:                                                                                                          \
+        if (kind == 1)                                                                                                \
+            kernel_build_kernel<DL, 1><<<grid, 256, 0, st>>>(X, n, lengthscales, lin_c2, noise2, class_offsets, n_classes, K); \
+        else                                                                                                          \
+            kernel_build_kernel<DL, 0><<<grid, 256, 0, st>>>(X, n, lengthscales, lin_c2, noise2, class_offsets, n_classes, K); \
+        break;
+    switch (d) {
+        GPMDM_BUILD_CASE(1) GPMDM_BUILD_CASE(2) GPMDM_BUILD_CASE(3) GPMDM_BUILD_CASE(4)
+        GPMDM_BUILD_CASE(5) GPMDM_BUILD_CASE(6) GPMDM_BUILD_CASE(7) GPMDM_BUILD_CASE(8)
+    }
+#undef GPMDM_BUILD_CASE
     return check_launch("kernel_build_kernel");
 }
 
