@@ -70,9 +70,11 @@ struct PredictParams {
     int32_t* counter;  // [0] tile hand-out, [1] round synchronisation
     int round_sync;    // re-align the CTAs after every particle tile (uniform tiles, several rounds)
     // low-latency (split) mode: one work item per (particle tile, column tile); partial results go to the workspace
-    int split, max_nct;
-    double* qpart;  // [max_nct][P] per-column-tile contributions to k^T L k
-    double* mu_ws;  // [P][dout] means
+    // The k range of every column tile is cut further into `nseg` segments of `seg_chunks` chunks, so that a handful of
+    // particle tiles still yields several work items per SM.
+    int split, max_nct, nseg, seg_chunks;
+    double* qpart;  // [max_nq * nseg][P] per-(column tile, segment) contributions to k^T L k
+    double* mu_ws;  // [nseg][P][dout] per-segment contributions to the means
     // K* cache (CACHE instantiation): per-CTA scratch of n_pad x 64 doubles in A-fragment order
     double* kcache;
     long long kcache_stride;  // doubles per CTA
@@ -216,10 +218,13 @@ struct ChunkCursor {
     __device__ __forceinline__ const double* base(int t) const {
         return t < nq ? L + panel_row_offset(t, n_pad, tri) * LDB : alpha + (long long)(t - nq) * n_pad * LDB;
     }
-    __device__ __forceinline__ void init(int nq_, int nct_, int nkc_, int tri_, int ct0, const gpmdm_gp_block& b) {
-        nq = nq_, nct = nct_, nkc = nkc_, tri = tri_, ct = ct0, k = kbeg(ct0);
+    // kstart / kend >= 0 restrict the (single) column tile to the k-chunks [kstart, kend) (low-latency mode)
+    __device__ __forceinline__ void init(int nq_, int nct_, int nkc_, int tri_, int ct0, const gpmdm_gp_block& b,
+                                         int kstart = -1, int kend = -1) {
+        nq = nq_, nct = nct_, nkc = kend >= 0 ? kend : nkc_, tri = tri_, ct = ct0;
+        k = kstart >= 0 ? kstart : kbeg(ct0);
         L = b.L, alpha = b.alpha, n_pad = b.n_pad;
-        src = ct < nct ? base(ct) : nullptr;
+        src = ct < nct ? base(ct) + (long long)(k - kbeg(ct)) * (KC * LDB) : nullptr;
     }
     __device__ __forceinline__ bool done() const { return ct >= nct; }
     __device__ __forceinline__ void next() {
@@ -265,7 +270,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gp_predict_kernel(const PredictPa
     int cst = 0, cph = 0;   // consumer: stage / parity of the chunk being consumed
     int duty = 0;           // warp whose turn it is to issue the next TMA chunk
 
-    const int total_items = prm.split ? total_tiles * prm.max_nct : total_tiles;
+    const int total_items = prm.split ? total_tiles * prm.max_nct * prm.nseg : total_tiles;
     int rounds_done = 0;
     for (;;) {
         if (tid == 0) s.tile = atomicAdd(prm.counter, 1);
@@ -279,7 +284,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) gp_predict_kernel(const PredictPa
         }
         // split mode: items are ordered column tile first, so the longest (ct = 0 of every particle tile) start first
         const int t = prm.split ? item % total_tiles : item;
-        const int item_ct = prm.split ? item / total_tiles : -1;
+        int item_ct = -1, item_s = 0;
+        if (prm.split) {
+            const int rest = item / total_tiles;
+            item_ct = rest / prm.nseg;
+            item_s = rest - item_ct * prm.nseg;
+        }
         int blk = 0, first = t * TM, count;
         if (prm.tiles) {
             blk = prm.tiles[4 * t + 0];
@@ -296,10 +306,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) gp_predict_kernel(const PredictPa
         const int nct = nq + prm.alpha_ld / TN;  // + column tiles of alpha
         const int ct0 = (KIND == 0 && prm.v_in) ? nq : 0;  // mean-only mode starts at the alpha tiles
         int ct_begin = ct0, ct_end = nct;
+        int kfirst = -1, kend = nkc;  // k-chunk range of the work item (split mode: one segment of one column tile)
         if (prm.split) {
             if (item_ct < ct0 || item_ct >= nct) continue;  // this block has fewer column tiles (uniform for the CTA)
             ct_begin = item_ct;
             ct_end = item_ct + 1;
+            kfirst = ((prm.tri && item_ct < nq) ? item_ct * (TN / KC) : 0) + item_s * prm.seg_chunks;
+            if (kfirst >= nkc) continue;  // ... or fewer segments
+            kend = min(kfirst + prm.seg_chunks, nkc);
         }
 
         // ---- this lane's particle row --------------------------------------------------------------------
@@ -325,7 +339,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gp_predict_kernel(const PredictPa
 
         // ---- TMA issue: all warps advance the same cursor, the duty warp issues ------------------------------
         ChunkCursor bcur;
-        bcur.init(nq, ct_end, nkc, prm.tri, ct_begin, gbk);
+        bcur.init(nq, ct_end, nkc, prm.tri, ct_begin, gbk, kfirst, prm.split ? kend : -1);
         int pst = cst, pph = cph;  // producer: stage / parity of the next chunk to issue
         auto issue_b = [&]() {
             const int st = pst;
@@ -377,7 +391,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gp_predict_kernel(const PredictPa
         }
 
         ChunkCursor cur;
-        cur.init(nq, ct_end, nkc, prm.tri, ct_begin, gbk);
+        cur.init(nq, ct_end, nkc, prm.tri, ct_begin, gbk, kfirst, prm.split ? kend : -1);
         double qacc = 0.0, sacc = 0.0, vrow = 0.0;
         if (KIND == 0 && prm.v_in) vrow = pidx >= 0 ? prm.v_in[pidx] : 1.0;
 
@@ -386,7 +400,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gp_predict_kernel(const PredictPa
 #pragma unroll
             for (int j = 0; j < NJ; j++) acc[j][0] = acc[j][1] = 0.0;
 
-            const int kbeg = cur.kbeg(ct);
+            const int kbeg = kfirst >= 0 ? kfirst : cur.kbeg(ct);
             // The k loop of one column tile.  GROUP_ON(jg) says whether the 8 column blocks starting at jg are
             // needed: always for tiles of L; for alpha tiles only the blocks that hold real output columns.
 #ifdef GPMDM_DIAG_NO_EXP  /* timing diagnostic only: results are wrong */
@@ -408,7 +422,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gp_predict_kernel(const PredictPa
         }                                                                                                        \
     }
 #define GPMDM_K_LOOP(GROUP_ON)                                                                                  \
-    for (int k = kbeg; k < nkc; k++) {                                                                           \
+    for (int k = kbeg; k < kend; k++) {                                                                          \
         const int st = cst;                                                                                      \
         /* keep the ring AHEAD chunks full; the duty rotates so that no warp is always the one waiting */        \
         if (!bcur.done()) {                                                                                      \
@@ -419,13 +433,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) gp_predict_kernel(const PredictPa
         }                                                                                                        \
         /* The next chunk provides the records for the next A fragments.  After the last chunk of the          \
            particle tile the fragments are recomputed from the current stage (values unused). */                 \
-        const bool has_next = !(ct == ct_end - 1 && k == nkc - 1);                                               \
+        const bool has_next = !(ct == ct_end - 1 && k == kend - 1);                                              \
         int stn = cst, phn = cph;                                                                                \
         if (has_next) { GPMDM_ADVANCE(stn, phn) }                                                                \
         /* K* cache: the next chunk's fragments are requested now and consumed after the MMA blocks */           \
         double an[KC / 4];                                                                                       \
         if (CACHE) {                                                                                             \
-            const int kn = !has_next ? k : (k + 1 < nkc ? k + 1 : cur.kbeg(ct + 1));                             \
+            const int kn = !has_next ? k : (k + 1 < kend ? k + 1 : cur.kbeg(ct + 1));                            \
             _Pragma("unroll") for (int i = 0; i < KC / 4; i++) an[i] = __ldcg(kc + (long long)kn * KCHUNK + i * 32); \
         }                                                                                                        \
         /* probe the next chunk's barrier now, look at the answer after the MMA blocks (hides the probe latency) */ \
@@ -488,7 +502,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gp_predict_kernel(const PredictPa
                     double v = qacc;
                     v += __shfl_xor_sync(0xffffffffu, v, 1);
                     v += __shfl_xor_sync(0xffffffffu, v, 2);
-                    if (c == 0 && pidx >= 0) prm.qpart[(long long)ct * prm.P + pidx] = v;
+                    if (c == 0 && pidx >= 0) prm.qpart[((long long)ct * prm.nseg + item_s) * prm.P + pidx] = v;
                 } else if (ct == nq - 1) {
                     // quadratic form complete: v[p] = prior[p] - q[p]
                     double v = qacc;
@@ -506,7 +520,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gp_predict_kernel(const PredictPa
                         if (col >= prm.dout) continue;
                         const double mu = acc[j][e];
                         if (prm.split) {  // finished by predict_finalize_kernel
-                            if (pidx >= 0) prm.mu_ws[(long long)pidx * prm.dout + col] = mu;
+                            if (pidx >= 0) prm.mu_ws[((long long)item_s * prm.P + pidx) * prm.dout + col] = mu;
                         } else if (KIND == 0) {
                             if (prm.z) {
                                 const double dz = __ldg(prm.z + col) - mu;
@@ -561,17 +575,22 @@ __global__ void predict_finalize_kernel(const PredictParams prm, int max_nq) {
     if (p >= prm.P) return;
     const int d = prm.d;
     double q = 0.0;
-    for (int ct = 0; ct < max_nq; ct++) q += prm.qpart[(long long)ct * prm.P + p];
-    const double* mu = prm.mu_ws + p * prm.dout;
+    for (int i = 0; i < max_nq * prm.nseg; i++) q += prm.qpart[(long long)i * prm.P + p];
+    auto mean = [&](int j) {
+        double m = 0.0;
+        for (int sg = 0; sg < prm.nseg; sg++) m += prm.mu_ws[((long long)sg * prm.P + p) * prm.dout + j];
+        return m;
+    };
     if (KIND == 0) {
         const double v = prm.v_in ? prm.v_in[p] : 1.0 - q;
         double S = 0.0;
         for (int j = 0; j < prm.dout; j++) {
+            const double mu = mean(j);
             if (prm.z) {
-                const double dz = prm.z[j] - mu[j];
+                const double dz = prm.z[j] - mu;
                 S = fma(prm.scale[j] * dz, dz, S);
             }
-            if (prm.mu_out) prm.mu_out[p * prm.dout + j] = mu[j];
+            if (prm.mu_out) prm.mu_out[p * prm.dout + j] = mu;
         }
         if (prm.ll) prm.ll[p] = -0.5 * S / v - (double)prm.dout * log(v) + prm.ll_const;
         if (prm.v_out) prm.v_out[p] = v;
@@ -584,10 +603,10 @@ __global__ void predict_finalize_kernel(const PredictParams prm, int max_nq) {
         prior += prm.lin_c2[d];
         const double v = prior - q;
         for (int k = 0; k < prm.dout; k++) {
-            const double var = v * prm.scale[k];
+            const double var = v * prm.scale[k], mu = mean(k);
             const long long o = p * prm.dout + k;
-            if (prm.x_new) prm.x_new[o] = __dadd_rn(__dmul_rn(prm.eps[o], sqrt(var)), mu[k]);
-            if (prm.mean_out) prm.mean_out[o] = mu[k];
+            if (prm.x_new) prm.x_new[o] = __dadd_rn(__dmul_rn(prm.eps[o], sqrt(var)), mu);
+            if (prm.mean_out) prm.mean_out[o] = mu;
             if (prm.var_out) prm.var_out[o] = var;
         }
     }
@@ -780,8 +799,21 @@ static int observe_impl(const gpmdm_gp_model* obs, const double* x, int64_t P, c
 }
 
 // ---- low-latency variants: when there are fewer particle tiles than SMs, split every tile's column tiles over CTAs ----
+// k-segment length (in chunks) of the low-latency work items: about 8 items per SM, at least 16 chunks each
+static void choose_segments(int64_t P, int64_t max_n_pad, int& seg, int& nseg) {
+    const long long tiles = (P + TM - 1) / TM, nkc = max_n_pad / KC, nq = max_n_pad / TN;
+    const long long total = tiles * ((TN / KC) * nq * (nq + 1) / 2 + nkc);  // chunks of all tiles (triangular packing)
+    long long sg = (total + 8ll * num_sms() - 1) / (8ll * num_sms());
+    sg = sg < 16 ? 16 : sg;
+    sg = sg > nkc ? nkc : sg;
+    seg = (int)sg;
+    nseg = (int)((nkc + sg - 1) / sg);
+}
+
 extern "C" int64_t gpmdm_predict_lowlat_workspace_bytes(int64_t P, int64_t max_n_pad, int32_t dout) {
-    return (max_n_pad / TN) * P * 8 + P * (int64_t)dout * 8;
+    int seg, nseg;
+    choose_segments(P, max_n_pad, seg, nseg);
+    return ((max_n_pad / TN) * P + P * (int64_t)dout) * nseg * 8;
 }
 
 template <int KIND>
@@ -791,13 +823,15 @@ static int run_split(PredictParams& prm, int64_t max_n_pad, void* workspace, cud
     const int max_nq = (int)(max_n_pad / TN);
     prm.split = 1;
     prm.max_nct = max_nq + prm.alpha_ld / TN;
+    choose_segments(prm.P, max_n_pad, prm.seg_chunks, prm.nseg);
     prm.qpart = static_cast<double*>(workspace);
-    prm.mu_ws = prm.qpart + (long long)max_nq * prm.P;
-    cudaError_t e = cudaMemsetAsync(prm.qpart, 0, (size_t)max_nq * prm.P * 8, st);
+    prm.mu_ws = prm.qpart + (long long)max_nq * prm.nseg * prm.P;
+    // segments a (smaller) block does not have contribute zeros
+    cudaError_t e = cudaMemsetAsync(prm.qpart, 0, ((size_t)max_nq * prm.P + (size_t)prm.P * prm.dout) * prm.nseg * 8, st);
     GPMDM_REQUIRE(e == cudaSuccess, (int)e, "cudaMemsetAsync: %s", cudaGetErrorString(e));
     e = cudaMemsetAsync(prm.counter, 0, 2 * sizeof(int32_t), st);
     GPMDM_REQUIRE(e == cudaSuccess, (int)e, "cudaMemsetAsync: %s", cudaGetErrorString(e));
-    const long long items = ((prm.P + TM - 1) / TM + prm.n_blocks) * prm.max_nct;
+    const long long items = ((prm.P + TM - 1) / TM + prm.n_blocks) * prm.max_nct * prm.nseg;
     const int grid = (int)(items < num_sms() ? items : num_sms());
     if (int rc = dispatch_d<KIND>(prm, grid, st)) return rc;
     predict_finalize_kernel<KIND><<<(unsigned)((prm.P + 127) / 128), 128, 0, st>>>(prm, max_nq);

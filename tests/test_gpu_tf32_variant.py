@@ -32,7 +32,11 @@ def test_tf32_observation_gp_matches_fp64(setup, P):
     xs = particles(spec, P, 3, 0.3).cuda()
     mu64, var64 = model.map_x_to_y(xs)
     mu32, var32 = model.map_x_to_y(xs, precision="tf32")
-    assert torch.equal(mu32, mu64)  # the hybrid variant keeps the mean contraction in fp64 (same kernel, alpha tile only)
+    # the hybrid variant keeps the mean contraction in fp64 (same kernel, alpha tile only); the fp64 call above runs in
+    # low-latency mode at these sizes (k range split over the SMs), so only the summation order over k differs
+    assert float(torch.max(torch.abs(mu32 - mu64) / torch.clamp(mu64.abs().max(dim=1, keepdim=True).values, min=1e-2))) < 1e-12
+    mu64f, _ = model.map_x_to_y(xs, low_latency=False)
+    assert torch.equal(mu32, mu64f)
     lam = (torch.exp(model.y_log_lambdas.detach()) ** -2).unsqueeze(0)
     v64, v32 = var64 / lam, var32 / lam
     assert float(torch.max(torch.abs(v32 - v64))) < TOL32          # 1e-4 of the prior variance (= 1)
