@@ -31,6 +31,21 @@ class GpModelTf32(ctypes.Structure):
                 ("dout", _i32), ("lengthscales", _ptr), ("lambdas", _ptr)]
 
 
+class PfStepArgs(ctypes.Structure):
+    """struct gpmdm_pf_step_args"""
+    _fields_ = [("dyn", ctypes.POINTER(GpModel)), ("obs", ctypes.POINTER(GpModel)),
+                ("P", _i64), ("lo", _i64), ("n_local", _i64), ("C", _i32), ("d", _i32),
+                ("generate_draws", _i32), ("systematic", _i32), ("cdf_mode", _i32), ("predict_mode", _i32),
+                ("seed", _u64), ("step", _u64), ("T", _ptr), ("z", _ptr), ("ll_const", _f64),
+                ("x_prev", _ptr), ("c_prev", _ptr), ("E", _ptr), ("eps", _ptr), ("u", _ptr),
+                ("x_new", _ptr), ("c_new", _ptr), ("ll", _ptr),
+                ("perm", _ptr), ("tiles", _ptr), ("n_tiles", _ptr), ("tile_counter", _ptr),
+                ("workspace", _ptr), ("lowlat_workspace", _ptr), ("obs_n_pad", _i64), ("dyn_max_n_pad", _i64),
+                ("kstar_workspace", _ptr), ("kstar_workspace_bytes", _i64),
+                ("lw", _ptr), ("w", _ptr), ("stats", _ptr), ("cdf", _ptr), ("anc", _ptr), ("x_out", _ptr),
+                ("c_out", _ptr)]
+
+
 _SIGNATURES = {
     "gpmdm_abi_version": (ctypes.c_int, []),
     "gpmdm_last_error": (ctypes.c_char_p, []),
@@ -54,6 +69,8 @@ _SIGNATURES = {
                                                    _ptr, _i64, _ptr, _ptr, _ptr]),
     "gpmdm_pf_propagate_lowlat_f64": (ctypes.c_int, [ctypes.POINTER(GpModel), _ptr, _ptr, _ptr, _ptr, _i64, _ptr, _ptr,
                                                      _ptr, _ptr, _i64, _ptr, _ptr, _ptr]),
+    "gpmdm_pf_step_local_f64": (ctypes.c_int, [ctypes.POINTER(PfStepArgs), _ptr]),
+    "gpmdm_pf_step_global_f64": (ctypes.c_int, [ctypes.POINTER(PfStepArgs), _ptr]),
     "gpmdm_pf_normalize_f64": (ctypes.c_int, [_ptr, _i64, _ptr, _ptr, _ptr, _ptr, _ptr]),
     "gpmdm_pf_cdf_f64": (ctypes.c_int, [_ptr, _i64, _i32, _ptr, _ptr, _ptr]),
     "gpmdm_pf_resample_f64": (ctypes.c_int, [_ptr, _i64, _ptr, _i64, _ptr, _ptr, _i32, _ptr, _ptr, _ptr, _ptr]),

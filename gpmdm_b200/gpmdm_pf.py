@@ -48,7 +48,7 @@ class GPMDM_PF:
     def __init__(self, gpmdm: GPMDM, markov_switching_model, num_particles: int, *,
                  seed: int = 0, resampling: str = "multinomial", cdf_order: str = "sequential",
                  tri: bool = True, precision: str = "fp64", low_latency: Optional[bool] = None,
-                 kstar_cache: Optional[bool] = None, init_indices: Optional[Sequence] = None, process_group=None,
+                 kstar_cache: Optional[bool] = None, native_step: bool = True, init_indices: Optional[Sequence] = None, process_group=None,
                  distributed: Optional[bool] = None):
         """
         gpmdm, markov_switching_model [C, C], num_particles: as the reference (:47-50).
@@ -64,6 +64,8 @@ class GPMDM_PF:
         kstar_cache     None = automatic: the fused fp64 observation kernel keeps each particle tile's cross-kernel K* in a
                         per-SM scratch (#SMs x N_pad x 64 doubles) instead of re-evaluating it for every column tile;
                         bit-identical results; True / False to force
+        native_step     issue the stage launches of a step from native code (two C-ABI calls per step instead of twelve;
+                        matters when a step is launch-latency bound, i.e. with few particles); same kernels, same results
         init_indices    optional per-class index tensors replacing torch.randint in _init_particles (:113)
         """
         self._lib = _cabi.lib()
@@ -99,6 +101,7 @@ class GPMDM_PF:
         self._lowlat = gpmdm._use_lowlat(self._hi - self._lo, low_latency)
         self._kstar_cache = (precision == "fp64" and not self._lowlat
                              and gpmdm._use_kstar_cache(self._packed["obs_n_pad"], kstar_cache))
+        self._native_step = bool(native_step) and precision == "fp64"
         self._alloc()
         self._init_particles(init_indices)
 
@@ -124,6 +127,21 @@ class GPMDM_PF:
                        int(self._lib.gpmdm_predict_lowlat_workspace_bytes(Pl, self._packed["dyn_max_n_pad"], d)))
             self._ws_lowlat = torch.empty(need // 8 + 1, dtype=torch.float64, device=dev)
         self._ws_kstar = self._gpmdm._kstar_workspace(self._packed["obs_n_pad"]) if self._kstar_cache else None
+        if self._native_step:  # struct gpmdm_pf_step_args: the per-trial constants; per-step fields are set in _update
+            a = self._step_args = _cabi.PfStepArgs()
+            a.dyn, a.obs = ctypes.pointer(self._packed["dyn"]), ctypes.pointer(self._packed["obs"])
+            a.P, a.lo, a.n_local, a.C, a.d = P, self._lo, Pl, C, d
+            a.systematic, a.cdf_mode = int(self._systematic), self._cdf_mode
+            a.predict_mode = 2 if self._lowlat else (1 if self._kstar_cache else 0)
+            a.seed, a.T, a.ll_const = self._seed, ptr(self._markov_switching_model), self._ll_const
+            a.u, a.x_new, a.c_new, a.ll = ptr(self._u), ptr(self._x_new), ptr(self._c_new), ptr(self._ll_all)
+            a.perm, a.tiles, a.n_tiles, a.tile_counter = ptr(self._perm), ptr(self._tiles), ptr(self._n_tiles), ptr(self._counter)
+            a.workspace = ptr(self._ws)
+            a.lowlat_workspace = ptr(self._ws_lowlat) if self._lowlat else None
+            a.obs_n_pad, a.dyn_max_n_pad = self._packed["obs_n_pad"], self._packed["dyn_max_n_pad"]
+            a.kstar_workspace = ptr(self._ws_kstar) if self._kstar_cache else None
+            a.kstar_workspace_bytes = self._ws_kstar.numel() * 8 if self._kstar_cache else 0
+            a.stats, a.cdf, a.anc = ptr(self._stats), ptr(self._cdf), ptr(self._anc)
 
     # ---- initialisation (gpmdm_pf.py:87-115) -------------------------------------------------------------------
     def _init_particles(self, init_indices=None):
@@ -166,12 +184,16 @@ class GPMDM_PF:
         Pl = hi - lo
         if z.numel() != self.observation_dim:
             raise ValueError("z must have D = %d entries" % self.observation_dim)
+        # the stage-by-stage sequence below is also what csrc/pf_step.cu issues natively (bench.py uses the stages to put
+        # CUDA events around the dominant kernel)
+        native = self._native_step and getattr(self, "_profile_events", None) is None
         # -- raw draws
         if draws is None:
-            check(lib.gpmdm_pf_draws_philox(self._seed, self._step, lo, Pl, P, C, d, 0, ptr(self._E), ptr(self._eps),
-                                            None, st), "gpmdm_pf_draws_philox")
-            check(lib.gpmdm_pf_draws_philox(self._seed, self._step, 0, P, P, C, d, int(self._systematic), None, None,
-                                            ptr(self._u), st), "gpmdm_pf_draws_philox")
+            if not native:
+                check(lib.gpmdm_pf_draws_philox(self._seed, self._step, lo, Pl, P, C, d, 0, ptr(self._E), ptr(self._eps),
+                                                None, st), "gpmdm_pf_draws_philox")
+                check(lib.gpmdm_pf_draws_philox(self._seed, self._step, 0, P, P, C, d, int(self._systematic), None, None,
+                                                ptr(self._u), st), "gpmdm_pf_draws_philox")
             E, eps, u = self._E, self._eps, self._u
         else:
             E, eps, u = (torch.as_tensor(a).to(device=self.device, dtype=self.dtype) for a in draws)
@@ -181,6 +203,8 @@ class GPMDM_PF:
         x_prev = self._particle_states[lo:hi]
         c_prev = self._particle_classes[lo:hi]
         x_new_l, c_new_l, ll_l = self._x_new[lo:hi], self._c_new[lo:hi], self._ll_all[lo:hi]
+        if native:
+            return self._update_native(z, draws is None, E, eps, u, x_prev, c_prev)
         # -- class transition, bucketing, dynamics draw, observation likelihood (local particles)
         check(lib.gpmdm_pf_transition_f64(ptr(c_prev), ptr(self._markov_switching_model), ptr(E), Pl, C, ptr(c_new_l), st),
               "gpmdm_pf_transition_f64")
@@ -237,6 +261,23 @@ class GPMDM_PF:
         self._particle_states, self._states_alt = self._states_alt, self._particle_states
         self._particle_classes, self._classes_alt = self._classes_alt, self._particle_classes
         self._log_likelihoods = ll_new.clone()
+        self._log_weights, self._weights = lw_new, w_new
+        self._step += 1
+
+    def _update_native(self, z, generate, E, eps, u, x_prev, c_prev):
+        """The same step through gpmdm_pf_step_local_f64 / gpmdm_pf_step_global_f64 (csrc/pf_step.cu)."""
+        lib, st, a = self._lib, stream(), self._step_args
+        lw_new, w_new = self._log_weights_buf(), self._weights_buf()
+        a.generate_draws, a.step, a.z = int(generate), self._step, ptr(z)
+        a.x_prev, a.c_prev, a.E, a.eps, a.u = ptr(x_prev), ptr(c_prev), ptr(E), ptr(eps), ptr(u)
+        a.lw, a.w, a.x_out, a.c_out = ptr(lw_new), ptr(w_new), ptr(self._states_alt), ptr(self._classes_alt)
+        check(lib.gpmdm_pf_step_local_f64(ctypes.byref(a), st), "gpmdm_pf_step_local_f64")
+        if self._world > 1:
+            sharding.all_gather_particles(self._x_new, self._c_new, self._ll_all, self._lo, self._hi, self._pg)
+        check(lib.gpmdm_pf_step_global_f64(ctypes.byref(a), st), "gpmdm_pf_step_global_f64")
+        self._particle_states, self._states_alt = self._states_alt, self._particle_states
+        self._particle_classes, self._classes_alt = self._classes_alt, self._particle_classes
+        self._log_likelihoods = self._ll_all.clone()
         self._log_weights, self._weights = lw_new, w_new
         self._step += 1
 

@@ -236,6 +236,54 @@ int gpmdm_pack_alpha_tf32(const double* alpha, int64_t n, int64_t n_pad, int32_t
 int gpmdm_pf_observe_tf32(const gpmdm_gp_model_tf32* obs, const double* x, int64_t P, const double* z, double ll_const,
                           double* ll, double* mu_out, double* v_out, int32_t* tile_counter, void* stream);
 
+/* ---- one filter step as two calls (GPMDM_PF._update, gpmdm_pf.py:126-135) ----------------------------------
+ * The host-side sequence of the stage entry points above, issued from native code so that a step costs two FFI calls
+ * instead of ~twelve (with 100 particles the step is launch-latency bound).  `local` = draws, transition, bucketing,
+ * dynamics draw, observation log-likelihood for this rank's particles [lo, lo + n_local); then -- multi-GPU only --
+ * the caller all-gathers (x_new, c_new, ll); `global` = normalise, cdf, resample over all P particles.
+ * All pointers are device pointers except the struct itself; nothing is retained after the call. */
+typedef struct gpmdm_pf_step_args {
+    const gpmdm_gp_model* dyn;  /* host structs (device block tables inside)                              */
+    const gpmdm_gp_model* obs;
+    int64_t P, lo, n_local;     /* all particles; this rank's range                                         */
+    int32_t C, d;
+    int32_t generate_draws;     /* 1: Philox draws into E/eps/u (seed, step); 0: E/eps/u hold injected draws */
+    int32_t systematic;         /* resampling comb instead of P independent uniforms                        */
+    int32_t cdf_mode;           /* gpmdm_pf_cdf_f64 mode                                                    */
+    int32_t predict_mode;       /* 0 fused, 1 fused with K* cache, 2 low latency                            */
+    uint64_t seed, step;
+    const double* T;            /* [C, C]                                                                   */
+    const double* z;            /* [D]                                                                      */
+    double ll_const;
+    const double* x_prev;       /* [n_local, d] this rank's slice of the particle states                    */
+    const int64_t* c_prev;      /* [n_local]                                                                */
+    double* E;                  /* [n_local, C]                                                             */
+    double* eps;                /* [n_local, d]                                                             */
+    double* u;                  /* [P]                                                                      */
+    double* x_new;              /* [P, d]  pre-resample states; local rows written by `local`               */
+    int64_t* c_new;             /* [P]                                                                      */
+    double* ll;                 /* [P]                                                                      */
+    int32_t* perm;              /* bucketing scratch, see gpmdm_pf_bucket_by_class                          */
+    int32_t* tiles;
+    int32_t* n_tiles;
+    int32_t* tile_counter;
+    void* workspace;            /* gpmdm_workspace_bytes(P, C)                                              */
+    void* lowlat_workspace;     /* predict_mode 2                                                           */
+    int64_t obs_n_pad, dyn_max_n_pad;
+    void* kstar_workspace;      /* predict_mode 1                                                           */
+    int64_t kstar_workspace_bytes;
+    double* lw;                 /* [P] outputs of `global`                                                  */
+    double* w;
+    double* stats;              /* [2] {max ll, sum exp}                                                    */
+    double* cdf;
+    int64_t* anc;
+    double* x_out;              /* [P, d] resampled states                                                  */
+    int64_t* c_out;             /* [P]                                                                      */
+} gpmdm_pf_step_args;
+
+int gpmdm_pf_step_local_f64(const gpmdm_pf_step_args* a, void* stream);
+int gpmdm_pf_step_global_f64(const gpmdm_pf_step_args* a, void* stream);
+
 /* ---- training-side kernel matrices (gpmdm.py:381-548, 311-340, 550-628) ------------------------
  * K = exp(-|(x_i-x_j)/l|^2) [+ [x_i,1]diag(c^2)[x_j,1]^T if kind 1] [+ noise2 on the diagonal],
  * multiplied by the class-block mask given as row offsets (class_offsets [n_classes+1], device int64;

@@ -222,6 +222,28 @@ def test_factor_panels_hold_the_quadratic_form_matrix(tri):
     assert torch.equal(out.cpu(), Ap.reshape(-1))
 
 
+@pytest.mark.parametrize("P,kw", [(100, {}), (3000, {}), (20000, {}), (300, dict(resampling="systematic", cdf_order="blocked"))])
+def test_native_step_equals_the_stage_by_stage_sequence(cfg1, P, kw):
+    """gpmdm_pf_step_local_f64 / _global_f64 (csrc/pf_step.cu) against the same launches issued stage by stage from
+    Python, in low-latency, fused and cached modes, with device draws and with injected draws: identical state."""
+    from gpmdm_b200 import GPMDM_PF
+
+    spec, wl, f, model = cfg1
+    T = synthetic.markov_matrix(spec.n_classes)
+    g = torch.Generator().manual_seed(21)
+    inj = (-torch.log1p(-torch.rand(P, spec.n_classes, dtype=torch.float64, generator=g)),
+           torch.randn(P, spec.d, dtype=torch.float64, generator=g), torch.rand(P, dtype=torch.float64, generator=g))
+    outs = []
+    for native in (True, False):
+        pf = GPMDM_PF(model, T, P, seed=8, native_step=native, **kw)
+        assert pf._native_step == native
+        for t, z in enumerate(wl.test_trials[0][1][:3]):
+            pf.update(z, draws=inj if t == 1 else None)
+        outs.append((pf._particle_states.clone(), pf._particle_classes.clone(), pf._log_likelihoods.clone(),
+                     pf._log_weights.clone(), pf._weights.clone(), pf.last_ancestors.clone(), pf.class_probabilities()))
+    assert all(torch.equal(a, b) for a, b in zip(*outs))
+
+
 def test_bucket_by_class_is_a_stable_partition():
     from gpmdm_b200 import _cabi
 
