@@ -401,6 +401,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) gp_predict_kernel(const PredictPa
             for (int j = 0; j < NJ; j++) acc[j][0] = acc[j][1] = 0.0;
 
             const int kbeg = kfirst >= 0 ? kfirst : cur.kbeg(ct);
+            // The Hadamard epilogue of a tile of L re-reads the tile's 256 training records from global memory, 64
+            // dependent iterations per lane: request them into L1 now (it is otherwise idle: B arrives by TMA, K* by
+            // ld.cg), so that the epilogue does not pay 64 L2 round trips (~30 us per column tile).
+            if (ct < nq) {
+                const char* recs = reinterpret_cast<const char*>(gbk.coords + (long long)ct * TN * REC);
+                for (int off = tid * 128; off < TN * REC * 8; off += NTHREADS * 128)
+                    asm volatile("prefetch.global.L1 [%0];" ::"l"(recs + off));
+            }
             // The k loop of one column tile.  GROUP_ON(jg) says whether the 8 column blocks starting at jg are
             // needed: always for tiles of L; for alpha tiles only the blocks that hold real output columns.
 #ifdef GPMDM_DIAG_NO_EXP  /* timing diagnostic only: results are wrong */
@@ -569,13 +577,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) gp_predict_kernel(const PredictPa
 
 // Low-latency mode, second kernel: one thread per particle adds the per-column-tile contributions in a fixed order and
 // runs the epilogue the fused kernel would have run (log-likelihood, or the Gaussian draw).
+// One warp per particle: lanes stride over the (column tile, segment) partials and over the output columns.
 template <int KIND>
-__global__ void predict_finalize_kernel(const PredictParams prm, int max_nq) {
-    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(128) predict_finalize_kernel(const PredictParams prm, int max_nq) {
+    const long long p = (long long)blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
     if (p >= prm.P) return;
     const int d = prm.d;
+    // fixed order: lane l adds entries l, l + 32, ...; then a shuffle tree
     double q = 0.0;
-    for (int i = 0; i < max_nq * prm.nseg; i++) q += prm.qpart[(long long)i * prm.P + p];
+    for (int i = lane; i < max_nq * prm.nseg; i += 32) q += prm.qpart[(long long)i * prm.P + p];
+    q = warp_sum(q);
     auto mean = [&](int j) {
         double m = 0.0;
         for (int sg = 0; sg < prm.nseg; sg++) m += prm.mu_ws[((long long)sg * prm.P + p) * prm.dout + j];
@@ -584,7 +596,7 @@ __global__ void predict_finalize_kernel(const PredictParams prm, int max_nq) {
     if (KIND == 0) {
         const double v = prm.v_in ? prm.v_in[p] : 1.0 - q;
         double S = 0.0;
-        for (int j = 0; j < prm.dout; j++) {
+        for (int j = lane; j < prm.dout; j += 32) {
             const double mu = mean(j);
             if (prm.z) {
                 const double dz = prm.z[j] - mu;
@@ -592,8 +604,11 @@ __global__ void predict_finalize_kernel(const PredictParams prm, int max_nq) {
             }
             if (prm.mu_out) prm.mu_out[p * prm.dout + j] = mu;
         }
-        if (prm.ll) prm.ll[p] = -0.5 * S / v - (double)prm.dout * log(v) + prm.ll_const;
-        if (prm.v_out) prm.v_out[p] = v;
+        S = warp_sum(S);
+        if (lane == 0) {
+            if (prm.ll) prm.ll[p] = -0.5 * S / v - (double)prm.dout * log(v) + prm.ll_const;
+            if (prm.v_out) prm.v_out[p] = v;
+        }
     } else {
         double prior = 1.0;
         for (int j = 0; j < d; j++) {
@@ -602,7 +617,7 @@ __global__ void predict_finalize_kernel(const PredictParams prm, int max_nq) {
         }
         prior += prm.lin_c2[d];
         const double v = prior - q;
-        for (int k = 0; k < prm.dout; k++) {
+        for (int k = lane; k < prm.dout; k += 32) {
             const double var = v * prm.scale[k], mu = mean(k);
             const long long o = p * prm.dout + k;
             if (prm.x_new) prm.x_new[o] = __dadd_rn(__dmul_rn(prm.eps[o], sqrt(var)), mu);
@@ -834,7 +849,7 @@ static int run_split(PredictParams& prm, int64_t max_n_pad, void* workspace, cud
     const long long items = ((prm.P + TM - 1) / TM + prm.n_blocks) * prm.max_nct * prm.nseg;
     const int grid = (int)(items < num_sms() ? items : num_sms());
     if (int rc = dispatch_d<KIND>(prm, grid, st)) return rc;
-    predict_finalize_kernel<KIND><<<(unsigned)((prm.P + 127) / 128), 128, 0, st>>>(prm, max_nq);
+    predict_finalize_kernel<KIND><<<(unsigned)((prm.P + 3) / 4), 128, 0, st>>>(prm, max_nq);
     return check_launch("predict_finalize_kernel");
 }
 
