@@ -384,6 +384,14 @@ def test_cfg3_scale_properties():
     mu_d, var_d = model.map_x_to_y(xs)
     m_d, v_d = model.map_x_dynamics_for_class(xs, 3)
     model._packed = None
+    # the kernel instance bench.py measures (fused, K* cache, 79 column panels) against the on-the-fly instance and the
+    # low-latency decomposition at this size
+    model.packed_models(True)
+    mu_c, var_c = model.map_x_to_y(xs[:300], low_latency=False, kstar_cache=True)
+    mu_f, var_f = model.map_x_to_y(xs[:300], low_latency=False, kstar_cache=False)
+    assert torch.equal(mu_c, mu_f) and torch.equal(var_c, var_f)
+    assert float(torch.max(torch.abs(mu_c - mu_t[:300]))) < 1e-10 and float(torch.max(torch.abs(var_c - var_t[:300]))) < 1e-10
+    model._packed = None
     assert float(torch.max(torch.abs(mu_t - mu_d))) == 0.0 and float(torch.max(torch.abs(m_t - m_d))) == 0.0
     assert float(torch.max(torch.abs(var_t - var_d))) < 1e-9
     prior = 1 + (xs ** 2).sum(1) + 1  # all-ones linear coefficients
