@@ -156,9 +156,10 @@ int gpmdm_pf_loglik_f64(const gpmdm_gp_model* obs, const double* x, int64_t P, c
                         const double* v_in, double* ll, double* mu_out, int32_t* tile_counter, void* stream);
 
 /* Low-latency variants for small particle counts (fewer 64-particle tiles than SMs, e.g. the reference's README setup
- * with 100 particles): every (particle tile, 256-column tile) pair is a separate work item, the per-column-tile
- * contributions to k^T L k are added in a fixed order by a second kernel that also runs the epilogue.  Same results
- * contract as the fused calls; the summation order of the quadratic form differs (still deterministic).
+ * with 100 particles): every (particle tile, 256-column tile, k segment) triple is a separate work item -- the k range
+ * of a column tile is cut so that there are about 8 items per SM -- and the per-item contributions to k^T L k and to
+ * the means are added in a fixed order by a second kernel that also runs the epilogue.  Same results contract as the
+ * fused calls; only the summation order over k differs (deterministic for a given P and model).
  * max_n_pad: largest n_pad over the model's blocks.  workspace: gpmdm_predict_lowlat_workspace_bytes(P, max_n_pad, dout). */
 int64_t gpmdm_predict_lowlat_workspace_bytes(int64_t P, int64_t max_n_pad, int32_t dout);
 int gpmdm_pf_observe_lowlat_f64(const gpmdm_gp_model* obs, const double* x, int64_t P, const double* z, double ll_const,
