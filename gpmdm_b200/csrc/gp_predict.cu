@@ -814,11 +814,12 @@ static int observe_impl(const gpmdm_gp_model* obs, const double* x, int64_t P, c
 }
 
 // ---- low-latency variants: when there are fewer particle tiles than SMs, split every tile's column tiles over CTAs ----
-// k-segment length (in chunks) of the low-latency work items: about 8 items per SM, at least 16 chunks each
-static void choose_segments(int64_t P, int64_t max_n_pad, int& seg, int& nseg) {
-    const long long tiles = (P + TM - 1) / TM, nkc = max_n_pad / KC, nq = max_n_pad / TN;
-    const long long total = tiles * ((TN / KC) * nq * (nq + 1) / 2 + nkc);  // chunks of all tiles (triangular packing)
-    long long sg = (total + 8ll * num_sms() - 1) / (8ll * num_sms());
+// k-segment length (in chunks) of the low-latency work items: a sixteenth of the k range, at least 16 chunks -- with one
+// particle tile that is already ~4 items per SM at N = 20 k.  A function of the model size only (not of P or of the
+// device), so that results do not depend on how the particles are sharded.
+static void choose_segments(int64_t max_n_pad, int& seg, int& nseg) {
+    const long long nkc = max_n_pad / KC;
+    long long sg = (nkc + 15) / 16;
     sg = sg < 16 ? 16 : sg;
     sg = sg > nkc ? nkc : sg;
     seg = (int)sg;
@@ -827,7 +828,7 @@ static void choose_segments(int64_t P, int64_t max_n_pad, int& seg, int& nseg) {
 
 extern "C" int64_t gpmdm_predict_lowlat_workspace_bytes(int64_t P, int64_t max_n_pad, int32_t dout) {
     int seg, nseg;
-    choose_segments(P, max_n_pad, seg, nseg);
+    choose_segments(max_n_pad, seg, nseg);
     return ((max_n_pad / TN) * P + P * (int64_t)dout) * nseg * 8;
 }
 
@@ -838,7 +839,7 @@ static int run_split(PredictParams& prm, int64_t max_n_pad, void* workspace, cud
     const int max_nq = (int)(max_n_pad / TN);
     prm.split = 1;
     prm.max_nct = max_nq + prm.alpha_ld / TN;
-    choose_segments(prm.P, max_n_pad, prm.seg_chunks, prm.nseg);
+    choose_segments(max_n_pad, prm.seg_chunks, prm.nseg);
     prm.qpart = static_cast<double*>(workspace);
     prm.mu_ws = prm.qpart + (long long)max_nq * prm.nseg * prm.P;
     // segments a (smaller) block does not have contribute zeros

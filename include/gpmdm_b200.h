@@ -157,9 +157,9 @@ int gpmdm_pf_loglik_f64(const gpmdm_gp_model* obs, const double* x, int64_t P, c
 
 /* Low-latency variants for small particle counts (fewer 64-particle tiles than SMs, e.g. the reference's README setup
  * with 100 particles): every (particle tile, 256-column tile, k segment) triple is a separate work item -- the k range
- * of a column tile is cut so that there are about 8 items per SM -- and the per-item contributions to k^T L k and to
+ * of a column tile is cut into (up to) 16 segments, a function of n_pad only -- and the per-item contributions to k^T L k and to
  * the means are added in a fixed order by a second kernel that also runs the epilogue.  Same results contract as the
- * fused calls; only the summation order over k differs (deterministic for a given P and model).
+ * fused calls; only the summation order over k differs (deterministic; independent of P and of the sharding).
  * max_n_pad: largest n_pad over the model's blocks.  workspace: gpmdm_predict_lowlat_workspace_bytes(P, max_n_pad, dout). */
 int64_t gpmdm_predict_lowlat_workspace_bytes(int64_t P, int64_t max_n_pad, int32_t dout);
 int gpmdm_pf_observe_lowlat_f64(const gpmdm_gp_model* obs, const double* x, int64_t P, const double* z, double ll_const,

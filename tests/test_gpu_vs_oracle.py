@@ -67,6 +67,20 @@ def test_kstar_cache_is_bit_identical_to_on_the_fly_evaluation(cfg1, P):
 
 
 @pytest.mark.parametrize("low_latency", [False, True])
+def test_row_results_do_not_depend_on_the_batch(cfg1, low_latency):
+    """A particle's prediction is bit-identical whatever else is in the batch (tile hand-out, work-item decomposition
+    and k segmentation depend on the model size only) -- the property that makes a sharded run equal the 1-GPU run."""
+    spec, wl, f, model = cfg1
+    xs = particles_near_data(spec, 700, 17).cuda()
+    mu_a, var_a = model.map_x_to_y(xs, low_latency=low_latency)
+    mu_b, var_b = model.map_x_to_y(xs[130:235].contiguous(), low_latency=low_latency)
+    assert torch.equal(mu_a[130:235], mu_b) and torch.equal(var_a[130:235], var_b)
+    m_a, v_a = model.map_x_dynamics_for_class(xs, 1, low_latency=low_latency)
+    m_b, v_b = model.map_x_dynamics_for_class(xs[3:40].contiguous(), 1, low_latency=low_latency)
+    assert torch.equal(m_a[3:40], m_b) and torch.equal(v_a[3:40], v_b)
+
+
+@pytest.mark.parametrize("low_latency", [False, True])
 @pytest.mark.parametrize("P", [1, 100, 1000])
 def test_dynamics_gp_vs_oracle(cfg1, P, low_latency):
     spec, wl, f, model = cfg1
