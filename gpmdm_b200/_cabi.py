@@ -74,6 +74,7 @@ _SIGNATURES = {
     "gpmdm_pf_normalize_f64": (ctypes.c_int, [_ptr, _i64, _ptr, _ptr, _ptr, _ptr, _ptr]),
     "gpmdm_pf_cdf_f64": (ctypes.c_int, [_ptr, _i64, _i32, _ptr, _ptr, _ptr]),
     "gpmdm_pf_resample_f64": (ctypes.c_int, [_ptr, _i64, _ptr, _i64, _ptr, _ptr, _i32, _ptr, _ptr, _ptr, _ptr]),
+    "gpmdm_pf_resample_sorted_f64": (ctypes.c_int, [_ptr, _i64, _ptr, _i64, _ptr, _ptr, _i32, _ptr, _ptr, _ptr, _ptr]),
     "gpmdm_pf_summaries_f64": (ctypes.c_int, [_ptr, _ptr, _ptr, _ptr, _ptr, _i64, _i32, _i32, _ptr, _ptr, _ptr]),
     "gpmdm_pf_draws_philox": (ctypes.c_int, [_u64, _u64, _i64, _i64, _i64, _i32, _i32, _i32, _ptr, _ptr, _ptr,
                                              _ptr]),

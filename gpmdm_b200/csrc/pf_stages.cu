@@ -424,6 +424,79 @@ __global__ void resample_kernel(const double* __restrict__ cdf, long long P, con
     if (c_out) c_out[s] = c_in[left];
 }
 
+// Ascending u (the systematic comb): the 1024 outputs of a block fall into one contiguous window [j_lo, j_hi] of the
+// cdf, found by two global searches per block; the window is staged in shared memory with coalesced loads and every
+// output is a search in shared memory.  The answer is the same index as resample_kernel's (the cdf is monotone, so the
+// first j with cdf_j >= u lies inside the window).  Windows wider than the staging buffer (many consecutive particles of
+// ~zero weight) fall back to a global search inside the window.
+constexpr int RS_OUT = 1024;   // outputs per block
+constexpr int RS_CAP = 4096;   // cdf entries staged per block (32 KB)
+// first j in [0, P] with cdf[j] >= us (P if none), by a whole warp: 32 probes per step, log32(P) dependent steps
+__device__ __forceinline__ long long warp_lower_bound(const double* __restrict__ cdf, long long P, double us) {
+    const int lane = threadIdx.x & 31;
+    long long lo = 0, hi = P;  // the answer lies in [lo, hi]; entries below lo are < us
+    while (hi - lo > 0) {
+        const long long len = hi - lo, step = (len + 31) / 32;
+        long long probe = lo + (lane + 1) * step - 1;  // last entry of this lane's chunk
+        if (probe > hi - 1) probe = hi - 1;
+        const unsigned ge = __ballot_sync(0xffffffffu, __ldg(cdf + probe) >= us);
+        if (ge == 0) return hi;  // every entry of [lo, hi) is < us
+        const int first = __ffs(ge) - 1;
+        const long long nlo = lo + first * step;
+        long long nhi = lo + (first + 1) * step - 1;  // cdf[nhi] >= us: the answer is in [nlo, nhi]
+        if (nhi > hi - 1) nhi = hi - 1;
+        lo = nlo;
+        hi = nhi;
+    }
+    return lo;
+}
+
+__global__ void __launch_bounds__(256) resample_sorted_kernel(const double* __restrict__ cdf, long long P,
+                                                              const double* __restrict__ u, long long n_out,
+                                                              const double* __restrict__ x_in,
+                                                              const int64_t* __restrict__ c_in, int d,
+                                                              int64_t* __restrict__ anc, double* __restrict__ x_out,
+                                                              int64_t* __restrict__ c_out) {
+    __shared__ double win[RS_CAP];
+    __shared__ long long bounds[2];
+    const long long s0 = (long long)blockIdx.x * RS_OUT;
+    const long long s1 = s0 + RS_OUT < n_out ? s0 + RS_OUT : n_out;  // exclusive
+    if (threadIdx.x < 64) {  // warp 0: window start, warp 1: window end
+        const long long b = warp_lower_bound(cdf, P, u[threadIdx.x < 32 ? s0 : s1 - 1]);
+        if ((threadIdx.x & 31) == 0) bounds[threadIdx.x >> 5] = b;
+    }
+    __syncthreads();
+    const long long j_lo = bounds[0], j_hi = bounds[1] < P ? bounds[1] : P - 1;  // answers lie in [j_lo, j_hi]
+    const long long span = j_hi - j_lo + 1;
+    const bool staged = span <= RS_CAP;
+    if (staged)
+        for (long long i = threadIdx.x; i < span; i += blockDim.x) win[i] = cdf[j_lo + i];
+    __syncthreads();
+    for (long long s = s0 + threadIdx.x; s < s1; s += blockDim.x) {
+        const double us = u[s];
+        long long left = 0, right = span;  // first index in the window with cdf >= u (== span only if u > cdf[j_hi])
+        if (staged) {
+            while (right - left > 0) {
+                const long long mid = left + (right - left) / 2;
+                if (win[mid] < us) left = mid + 1;
+                else right = mid;
+            }
+        } else {
+            while (right - left > 0) {
+                const long long mid = left + (right - left) / 2;
+                if (__ldg(cdf + j_lo + mid) < us) left = mid + 1;
+                else right = mid;
+            }
+        }
+        long long a = j_lo + left;
+        if (a >= P) a = P - 1;
+        if (anc) anc[s] = a;
+        if (x_out)
+            for (int k = 0; k < d; k++) x_out[s * d + k] = x_in[a * d + k];
+        if (c_out) c_out[s] = c_in[a];
+    }
+}
+
 // ---- summaries --------------------------------------------------------------------------------------------
 // part [nb][C + d + 1]: per-block class sums of exp(g - max), state-mean partials, total.
 __global__ void __launch_bounds__(RT) summaries_block_kernel(const double* __restrict__ ll,
@@ -642,6 +715,19 @@ extern "C" int gpmdm_pf_resample_f64(const double* cdf, int64_t P, const double*
     resample_kernel<<<nblocks(n_out, 256), 256, 0, (cudaStream_t)stream>>>(cdf, P, u, n_out, x_in, c_in, d, anc,
                                                                            x_out, c_out);
     return check_launch("resample_kernel");
+}
+
+extern "C" int gpmdm_pf_resample_sorted_f64(const double* cdf, int64_t P, const double* u, int64_t n_out,
+                                            const double* x_in, const int64_t* c_in, int32_t d, int64_t* anc,
+                                            double* x_out, int64_t* c_out, void* stream) {
+    GPMDM_REQUIRE(P > 0 && n_out >= 0 && d >= 0, GPMDM_E_INVALID, "bad sizes");
+    if (n_out == 0) return 0;
+    GPMDM_REQUIRE(cdf && u, GPMDM_E_INVALID, "null argument");
+    GPMDM_REQUIRE((x_out == nullptr || x_in != nullptr) && (c_out == nullptr || c_in != nullptr), GPMDM_E_INVALID,
+                  "gather output without input");
+    resample_sorted_kernel<<<nblocks(n_out, RS_OUT), 256, 0, (cudaStream_t)stream>>>(cdf, P, u, n_out, x_in, c_in, d, anc,
+                                                                                    x_out, c_out);
+    return check_launch("resample_sorted_kernel");
 }
 
 extern "C" int gpmdm_pf_summaries_f64(const double* ll, const double* lw, const double* w, const int64_t* c_post,

@@ -52,6 +52,11 @@ extern "C" int gpmdm_pf_step_global_f64(const gpmdm_pf_step_args* a, void* strea
     const int64_t P = a->P;
     GPMDM_TRY(gpmdm_pf_normalize_f64(a->ll, P, a->lw, a->w, a->stats, a->workspace, stream));
     GPMDM_TRY(gpmdm_pf_cdf_f64(a->w, P, a->cdf_mode, a->cdf, a->workspace, stream));
-    GPMDM_TRY(gpmdm_pf_resample_f64(a->cdf, P, a->u, P, a->x_new, a->c_new, a->d, a->anc, a->x_out, a->c_out, stream));
+    // device-generated systematic draws are an ascending comb; injected draws may be in any order
+    if (a->systematic && a->generate_draws)
+        GPMDM_TRY(gpmdm_pf_resample_sorted_f64(a->cdf, P, a->u, P, a->x_new, a->c_new, a->d, a->anc, a->x_out, a->c_out,
+                                               stream));
+    else
+        GPMDM_TRY(gpmdm_pf_resample_f64(a->cdf, P, a->u, P, a->x_new, a->c_new, a->d, a->anc, a->x_out, a->c_out, stream));
     return 0;
 }

@@ -254,7 +254,9 @@ class GPMDM_PF:
         check(lib.gpmdm_pf_normalize_f64(ptr(ll_new), P, ptr(lw_new), ptr(w_new), ptr(self._stats), ptr(self._ws), st),
               "gpmdm_pf_normalize_f64")
         check(lib.gpmdm_pf_cdf_f64(ptr(w_new), P, self._cdf_mode, ptr(self._cdf), ptr(self._ws), st), "gpmdm_pf_cdf_f64")
-        check(lib.gpmdm_pf_resample_f64(ptr(self._cdf), P, ptr(u), P, ptr(self._x_new), ptr(self._c_new), d,
+        # device-generated systematic draws are an ascending comb: windowed search with coalesced accesses
+        resample = lib.gpmdm_pf_resample_sorted_f64 if (self._systematic and draws is None) else lib.gpmdm_pf_resample_f64
+        check(resample(ptr(self._cdf), P, ptr(u), P, ptr(self._x_new), ptr(self._c_new), d,
                                         ptr(self._anc), ptr(self._states_alt), ptr(self._classes_alt), st),
               "gpmdm_pf_resample_f64")
         # publish (swap buffers; no copies)

@@ -187,6 +187,13 @@ int gpmdm_pf_resample_f64(const double* cdf, int64_t P, const double* u, int64_t
                           const int64_t* c_in, int32_t d, int64_t* anc, double* x_out, int64_t* c_out,
                           void* stream);
 
+/* The same search for ASCENDING u (the systematic comb u[s] = (u0 + s) / P): one window of the cdf per 1024 outputs is
+ * staged in shared memory, all HBM accesses are coalesced.  Identical ancestors to gpmdm_pf_resample_f64 on the same
+ * inputs; undefined for u that is not ascending. */
+int gpmdm_pf_resample_sorted_f64(const double* cdf, int64_t P, const double* u, int64_t n_out, const double* x_in,
+                                 const int64_t* c_in, int32_t d, int64_t* anc, double* x_out, int64_t* c_out,
+                                 void* stream);
+
 /* GPMDM_PF.class_probabilities / current_state_mean / log_likelihood (gpmdm_pf.py:215-262), with the
  * reference's mix of post-resample classes/states and pre-resample weights:
  *   g = ll + lw - max(ll + lw);  class_prob[i] = sum_{c_post=i} exp(g) / sum exp(g)

@@ -258,6 +258,46 @@ def test_native_step_equals_the_stage_by_stage_sequence(cfg1, P, kw):
     assert all(torch.equal(a, b) for a, b in zip(*outs))
 
 
+@pytest.mark.parametrize("kind", ["uniform", "peaked", "sparse", "one_hot"])
+@pytest.mark.parametrize("P,n_out", [(5000, 5000), (70001, 70001), (3000, 9000)])
+def test_windowed_resample_for_ascending_u_equals_the_generic_search(kind, P, n_out):
+    """gpmdm_pf_resample_sorted_f64 (systematic comb: one staged cdf window per 1024 outputs) against
+    gpmdm_pf_resample_f64 and the oracle's definition, on weight profiles that make the windows tiny (a few heavy
+    particles), wide beyond the staging buffer (long runs of zero weight) or degenerate (one particle has it all)."""
+    from gpmdm_b200 import _cabi
+    from gpmdm_b200._cabi import check, ptr, stream
+
+    lib = _cabi.lib()
+    g = torch.Generator().manual_seed(P + len(kind))
+    w = torch.rand(P, dtype=torch.float64, generator=g)
+    if kind == "peaked":
+        w = w ** 40
+    elif kind == "sparse":
+        w = w * (torch.rand(P, generator=g) < 2e-4)  # runs of ~5000 zero weights
+        w[P // 2] += 1.0
+    elif kind == "one_hot":
+        w = torch.zeros(P, dtype=torch.float64)
+        w[P // 3] = 1.0
+    w = (w / w.sum()).cuda()
+    ws = torch.empty(int(lib.gpmdm_workspace_bytes(P, 4)) // 8 + 1, dtype=torch.float64, device="cuda")
+    cdf = torch.empty(P, dtype=torch.float64, device="cuda")
+    check(lib.gpmdm_pf_cdf_f64(ptr(w), P, 1, ptr(cdf), ptr(ws), stream()), "cdf")
+    u = ((0.37 + torch.arange(n_out, dtype=torch.float64)) / n_out).cuda()
+    x = torch.randn(P, 3, dtype=torch.float64, generator=g).cuda()
+    c = torch.randint(0, 4, (P,), generator=g).cuda()
+    out = []
+    for fn in (lib.gpmdm_pf_resample_sorted_f64, lib.gpmdm_pf_resample_f64):
+        anc = torch.full((n_out,), -1, dtype=torch.int64, device="cuda")
+        xo = torch.empty(n_out, 3, dtype=torch.float64, device="cuda")
+        co = torch.empty(n_out, dtype=torch.int64, device="cuda")
+        check(fn(ptr(cdf), P, ptr(u), n_out, ptr(x), ptr(c), 3, ptr(anc), ptr(xo), ptr(co), stream()), "resample")
+        out.append((anc, xo, co))
+    assert all(torch.equal(a, b) for a, b in zip(*out))
+    anc = out[0][0]
+    assert torch.equal(anc.cpu(), torch.clamp(torch.searchsorted(cdf.cpu(), u.cpu(), right=False), max=P - 1))
+    assert torch.equal(out[0][1], x[anc]) and torch.equal(out[0][2], c[anc])
+
+
 def test_bucket_by_class_is_a_stable_partition():
     from gpmdm_b200 import _cabi
 

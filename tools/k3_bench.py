@@ -64,7 +64,7 @@ def main():
         "cdf_blocked": (lambda: check(lib.gpmdm_pf_cdf_f64(ptr(w), P, 1, ptr(cdf), ptr(ws), st), "c"), 16, 16 + 16),
         "resample_multinomial": (lambda: check(lib.gpmdm_pf_resample_f64(ptr(cdf), P, ptr(u), P, ptr(x), ptr(c), d, ptr(anc), ptr(xo), ptr(co), st), "r"),
                                  8 + 8 + 2 * (8 * d + 8), 8 + 8 + 2 * (8 * d + 8)),
-        "resample_systematic": (lambda: check(lib.gpmdm_pf_resample_f64(ptr(cdf), P, ptr(us), P, ptr(x), ptr(c), d, ptr(anc), ptr(xo), ptr(co), st), "r"),
+        "resample_systematic": (lambda: check(lib.gpmdm_pf_resample_sorted_f64(ptr(cdf), P, ptr(us), P, ptr(x), ptr(c), d, ptr(anc), ptr(xo), ptr(co), st), "r"),
                                 8 + 8 + 2 * (8 * d + 8), 8 + 8 + 2 * (8 * d + 8)),
         "summaries": (lambda: check(lib.gpmdm_pf_summaries_f64(ptr(ll), ptr(lw), ptr(w), ptr(co), ptr(xo), P, C, d, ptr(out), ptr(ws), st), "s"),
                       24 + 8 + 8 * d, 16 + 24 + 8 + 8 * d),
