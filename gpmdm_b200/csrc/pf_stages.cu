@@ -506,7 +506,6 @@ __global__ void __launch_bounds__(RT) summaries_block_kernel(const double* __res
                                                              const double* __restrict__ x_post, long long n, int C,
                                                              int d, const double* __restrict__ gmax,
                                                              double* __restrict__ part) {
-    __shared__ double sh[RT / 32 + 1];
     const long long base = (long long)blockIdx.x * RB + threadIdx.x * 4;
     const double m = gmax[0];
     double e[4], ww[4], vll[4], vlw[4];
@@ -520,25 +519,34 @@ __global__ void __launch_bounds__(RT) summaries_block_kernel(const double* __res
         e[k] = ok ? exp((vll[k] + vlw[k]) - m) : 0.0;
         cc[k] = ok ? (int)c_post[base + k] : -1;
     }
-    double* out = part + (long long)blockIdx.x * (C + d + 1);
-    for (int c = 0; c < C; c++) {
+    // C + d + 1 block sums with two barriers in all: shuffle tree per value inside each warp, then one thread per
+    // value adds the 8 warp totals serially -- the same order as block_sum_fixed, value by value.
+    __shared__ double wtot[RT / 32][64 + GPMDM_MAX_LATENT + 1];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int ncol = C + d + 1;
+    for (int col = 0; col < ncol; col++) {
         double v = 0.0;
+        if (col < C) {
 #pragma unroll
-        for (int k = 0; k < 4; k++) v += cc[k] == c ? e[k] : 0.0;
-        v = block_sum_fixed(v, sh);
-        if (threadIdx.x == 0) out[c] = v;
-    }
-    for (int j = 0; j < d; j++) {
-        double v = 0.0;
+            for (int k = 0; k < 4; k++) v += cc[k] == col ? e[k] : 0.0;
+        } else if (col < C + d) {
+            const int j = col - C;
 #pragma unroll
-        for (int k = 0; k < 4; k++)
-            if (base + k < n) v += x_post[(base + k) * d + j] * ww[k];
-        v = block_sum_fixed(v, sh);
-        if (threadIdx.x == 0) out[C + j] = v;
+            for (int k = 0; k < 4; k++)
+                if (base + k < n) v += x_post[(base + k) * d + j] * ww[k];
+        } else {
+            v = (e[0] + e[1]) + (e[2] + e[3]);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+        if (lane == 0) wtot[warp][col] = v;
     }
-    double v = (e[0] + e[1]) + (e[2] + e[3]);
-    v = block_sum_fixed(v, sh);
-    if (threadIdx.x == 0) out[C + d] = v;
+    __syncthreads();
+    if (threadIdx.x < ncol) {
+        double t = 0.0;
+        for (int w = 0; w < RT / 32; w++) t += wtot[w][threadIdx.x];
+        part[(long long)blockIdx.x * ncol + threadIdx.x] = t;
+    }
 }
 
 __global__ void __launch_bounds__(RT) summaries_final_kernel(const double* __restrict__ part, long long nb, int C,
