@@ -132,15 +132,21 @@ __global__ void __launch_bounds__(256) transition_kernel(const int64_t* __restri
 }
 
 // ---- bucket by class (stable counting sort) ---------------------------------------------------------------
+// Each CTA handles BSUB consecutive 1024-particle sub-blocks, so that the single-CTA scan between the two passes has
+// 4x fewer entries to walk.
+constexpr int BSUB = 4;
 __global__ void __launch_bounds__(RB) bucket_count_kernel(const int64_t* __restrict__ cls, long long P, int C,
                                                           int nb, int32_t* __restrict__ counts /*[C][nb]*/) {
     extern __shared__ int sh_cnt[];
     for (int i = threadIdx.x; i < C; i += blockDim.x) sh_cnt[i] = 0;
     __syncthreads();
-    const long long p = (long long)blockIdx.x * RB + threadIdx.x;
-    const int c = p < P ? (int)cls[p] : -1;
-    const unsigned peers = __match_any_sync(0xffffffffu, c);  // one shared-memory atomic per class per warp
-    if (c >= 0 && (peers & ((1u << (threadIdx.x & 31)) - 1u)) == 0) atomicAdd(&sh_cnt[c], __popc(peers));
+#pragma unroll
+    for (int sub = 0; sub < BSUB; sub++) {
+        const long long p = ((long long)blockIdx.x * BSUB + sub) * RB + threadIdx.x;
+        const int c = p < P ? (int)cls[p] : -1;
+        const unsigned peers = __match_any_sync(0xffffffffu, c);  // one shared-memory atomic per class per warp
+        if (c >= 0 && (peers & ((1u << (threadIdx.x & 31)) - 1u)) == 0) atomicAdd(&sh_cnt[c], __popc(peers));
+    }
     __syncthreads();
     for (int i = threadIdx.x; i < C; i += blockDim.x) counts[(long long)i * nb + blockIdx.x] = sh_cnt[i];
 }
@@ -215,27 +221,33 @@ __global__ void __launch_bounds__(1024) bucket_scan_kernel(int32_t* __restrict__
 __global__ void __launch_bounds__(RB) bucket_scatter_kernel(const int64_t* __restrict__ cls, long long P, int C,
                                                             int nb, const int32_t* __restrict__ offsets,
                                                             int32_t* __restrict__ perm) {
-    extern __shared__ int wc[];  // [32 warps][C]
+    extern __shared__ int wc[];  // [32 warps][C], then [C] running base of the CTA's earlier sub-blocks
+    int* base = wc + 32 * C;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int i = threadIdx.x; i < 32 * C; i += blockDim.x) wc[i] = 0;
-    __syncthreads();
-    const long long p = (long long)blockIdx.x * RB + threadIdx.x;
-    const int c = p < P ? (int)cls[p] : -1;
-    const unsigned peers = __match_any_sync(0xffffffffu, c);
-    const int rank = __popc(peers & ((1u << lane) - 1u));
-    if (c >= 0 && rank == 0) wc[warp * C + c] = __popc(peers);
-    __syncthreads();
-    // exclusive scan over warps, one thread per class
-    for (int k = threadIdx.x; k < C; k += blockDim.x) {
-        int run = 0;
-        for (int w = 0; w < 32; w++) {
-            const int v = wc[w * C + k];
-            wc[w * C + k] = run;
-            run += v;
+    for (int i = threadIdx.x; i < C; i += blockDim.x) base[i] = 0;
+    for (int sub = 0; sub < BSUB; sub++) {
+        for (int i = threadIdx.x; i < 32 * C; i += blockDim.x) wc[i] = 0;
+        __syncthreads();
+        const long long p = ((long long)blockIdx.x * BSUB + sub) * RB + threadIdx.x;
+        const int c = p < P ? (int)cls[p] : -1;
+        const unsigned peers = __match_any_sync(0xffffffffu, c);
+        const int rank = __popc(peers & ((1u << lane) - 1u));
+        if (c >= 0 && rank == 0) wc[warp * C + c] = __popc(peers);
+        __syncthreads();
+        // exclusive scan over warps, one thread per class, continuing from the earlier sub-blocks
+        for (int k = threadIdx.x; k < C; k += blockDim.x) {
+            int run = base[k];
+            for (int w = 0; w < 32; w++) {
+                const int v = wc[w * C + k];
+                wc[w * C + k] = run;
+                run += v;
+            }
+            base[k] = run;
         }
+        __syncthreads();
+        if (c >= 0) perm[offsets[(long long)c * nb + blockIdx.x] + wc[warp * C + c] + rank] = (int32_t)p;
+        __syncthreads();
     }
-    __syncthreads();
-    if (c >= 0) perm[offsets[(long long)c * nb + blockIdx.x] + wc[warp * C + c] + rank] = (int32_t)p;
 }
 
 // ---- normalisation -------------------------------------------------------------------------------------
@@ -664,11 +676,11 @@ extern "C" int gpmdm_pf_bucket_by_class(const int64_t* classes, int64_t P, int32
                   (long long)P, C);
     GPMDM_REQUIRE(classes && perm && tiles && n_tiles && workspace, GPMDM_E_INVALID, "null argument");
     cudaStream_t st = (cudaStream_t)stream;
-    const int nb = nblocks(P, RB);
+    const int nb = nblocks(P, RB * BSUB);
     int32_t* counts = reinterpret_cast<int32_t*>(static_cast<char*>(workspace) + 256);
     bucket_count_kernel<<<nb, RB, C * sizeof(int), st>>>(classes, P, C, nb, counts);
     bucket_scan_kernel<<<1, 1024, 2 * (C + 1) * sizeof(int), st>>>(counts, C, nb, tiles, n_tiles);
-    bucket_scatter_kernel<<<nb, RB, 32 * C * sizeof(int), st>>>(classes, P, C, nb, counts, perm);
+    bucket_scatter_kernel<<<nb, RB, 33 * C * sizeof(int), st>>>(classes, P, C, nb, counts, perm);
     return check_launch("bucket_by_class");
 }
 
