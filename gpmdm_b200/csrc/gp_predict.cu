@@ -10,7 +10,7 @@
 //     q[p]     = sum_n  C[p, n] * K*[p, n]           (columns of L;   Hadamard + row-sum epilogue)
 //     mean[p,:] = C[p, N_pad:]                        (columns of alpha)
 // With tri = 1, L is the lower-triangular packing of K^-1 (k^T K^-1 k == k^T L k), so column tile J
-// only needs k >= 256 J: half the flops and half the bytes of the dense form.
+// only needs k >= 256 J: half the flops and half the bytes of the dense form (the rows above are not even stored).
 //
 // Kernel organisation (one persistent CTA per SM, 256 threads = 8 warps; measured facts that shaped it, see
 // profiles/: on sm_100a DMMA (sm__pipe_tensor_subpipe_dmma) and DFMA/exp (sm__pipe_fp64) contend for ONE
@@ -23,10 +23,13 @@
 //     (row r; k = 4 k4 + c) are computed in registers from the particle record (registers) and the training
 //     records of the chunk (shared memory) -- the "GEMM prologue from latent coordinates" -- with no A tile
 //     in shared memory, no redundancy between warps and no block-wide barrier in the main loop;
-//   * the exponentials for chunk g+1 are software-pipelined into the DMMA stream of chunk g (custom
-//     fast_exp, csrc/fast_exp.cuh), so the datapath always has an instruction to run;
-//   * B tiles [16 x 256] of L / alpha and the 16 training records of the chunk arrive through TMA 1-D bulk
-//     copies (cp.async.bulk, SASS UBLKCP) into a 6-stage shared ring; full/empty mbarriers are the only
+//   * CACHE instantiation (observation GP, fused mode): those fragments are evaluated once per particle tile into a
+//     per-CTA global scratch in consumption order and re-read per column tile (see the comment on the kernel); in the
+//     other instantiations the exponentials for chunk g+1 are software-pipelined into the DMMA stream of chunk g
+//     (custom fast_exp, csrc/fast_exp.cuh), so the datapath always has an instruction to run;
+//   * B tiles [16 x 256] of L / alpha arrive as ONE TMA 1-D bulk copy per chunk (cp.async.bulk, SASS UBLKCP; the
+//     factors are packed as padded column panels, include/gpmdm_b200.h) -- plus one for the chunk's 16 training
+//     records when K* is evaluated on the fly -- into a 6-stage shared ring; full/empty mbarriers are the only
 //     synchronisation between warps (the issuing duty rotates over the warps, 3 chunks ahead);
 //   * fp64 tensor-core MMAs are mma.sync m8n8k4, the fastest DMMA shape on sm_100a (profiles/microbench);
 //   * the +4 double row padding of the B ring makes the fragment loads bank-conflict free for the m8n8k4
