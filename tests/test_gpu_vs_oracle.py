@@ -569,3 +569,40 @@ def test_cfg1_readme_trial_150_frames(cfg1):
         assert torch.equal(pf.last_ancestors.cpu(), anc_o), t
         cp_o = orc.class_probabilities(pf._log_likelihoods.cpu(), lw_o, c_new[anc_o], C)
         assert pf.get_most_likely_class() == int(torch.argmax(cp_o)), t
+
+
+@pytest.mark.parametrize("C,P", [(1, 50), (3, 2), (3, 1), (2, 64), (2, 65)])
+def test_degenerate_particle_and_class_counts(C, P):
+    """One-class models, fewer particles than classes (some classes start empty), a single particle, and exactly one
+    tile / one tile plus one: two filter steps with injected draws against the oracle stages."""
+    from gpmdm_b200 import GPMDM_PF
+
+    spec, wl = synthetic_spec(C, 2, 7, 2, 30, sigma_n=1e-1, seed=5)
+    f = orc.precompute_factors(spec)
+    model = product_model_from_spec(spec, Ky_inv=f.Ky_inv, Kx_inv_blocks=f.Kx_inv_blocks)
+    T = torch.eye(1, dtype=torch.float32) if C == 1 else synthetic.markov_matrix(C)
+    pf = GPMDM_PF(model, T, P, seed=2, cdf_order="sequential")
+    assert pf._particle_states.shape == (P, 2) and pf._particle_classes.shape == (P,)
+    for t in range(2):
+        E, eps, u = synthetic.raw_draws(P, C, 2, 90 + t)
+        c_prev, x_prev = pf._particle_classes.cpu().clone(), pf._particle_states.cpu().clone()
+        z = wl.test_trials[0][1][t]
+        pf.update(z, draws=(E, eps, u))
+        c_new = orc.transition(c_prev, T.to(torch.float64), E)
+        assert torch.equal(pf.last_pre_resample_classes.cpu(), c_new)
+        x_new = pf.last_pre_resample_states.cpu()
+        for c in range(C):
+            m = c_new == c
+            if bool(m.any()):
+                mean_o, var_o, _, prior = orc.map_x_dynamics_for_class(spec, f, x_prev[m], c)
+                x_o = eps[m] * torch.sqrt(var_o) + mean_o
+                assert float(torch.max(torch.abs(x_new[m] - x_o))) < 1e-8
+        mu_o, _, v_o = orc.map_x_to_y(spec, f, x_new)
+        ll_o = orc.log_likelihoods_fused(mu_o, v_o, torch.as_tensor(z, dtype=torch.float64), spec.y_log_lambdas)
+        assert float(torch.max(torch.abs(pf._log_likelihoods.cpu() - ll_o) / torch.abs(ll_o))) < 1e-6
+        lw_o, w_o = orc.normalize(pf._log_likelihoods.cpu())
+        assert torch.equal(pf._log_weights.cpu(), lw_o)
+        assert torch.equal(pf.last_ancestors.cpu(), orc.resample(pf._weights.cpu(), u))
+        probs = pf.class_probabilities()
+        assert probs.shape == (C,) and abs(float(probs.sum()) - 1.0) < 1e-12
+        assert 0 <= pf.get_most_likely_class() < C
