@@ -367,7 +367,9 @@ def run_ours(a):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": elapsed_ms / a.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64" if a.precision == "fp64" else "tf32x3 (observation GP) + f64", "data": "synthetic",
-            "config": {"workload": workload_name(a), "l2": "inputs larger than L2 (K^-1 is %.1f GB)" % (8e-9 * N * N),
+            "config": {"workload": workload_name(a),
+                       "l2": "inputs larger than L2 (the packed K^-1 panels streamed by every particle tile are %.2f GB)"
+                             % (1e-9 * lib.gpmdm_quadform_bytes((N + 255) // 256 * 256, 0 if a.dense else 1)),
                        "resampling": "multinomial", "draws": "device Philox4x32-10", "tri": not a.dense,
                        "parallelism": f"particles sharded over {world} rank(s), factors replicated"},
             "roofline": roofline, "cpu_baseline": cpu,
