@@ -633,15 +633,19 @@ __global__ void __launch_bounds__(128) predict_finalize_kernel(const PredictPara
 // ---- host side -------------------------------------------------------------------------------------
 template <int KIND, int DL, bool CACHE = false>
 static int launch_instance(const PredictParams& prm, int grid, cudaStream_t st) {
-    static bool configured = false;  // per instantiation
+    // the opt-in to > 48 KB of dynamic shared memory is per function AND per device
+    static bool configured[64] = {};  // per instantiation
+    int dev = 0;
+    cudaGetDevice(&dev);
+    dev = (dev >= 0 && dev < 64) ? dev : 0;
     auto kern = gp_predict_kernel<KIND, DL, CACHE>;
-    if (!configured) {
+    if (!configured[dev]) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
         if (e != cudaSuccess) {
             set_error("cudaFuncSetAttribute(gp_predict): %s", cudaGetErrorString(e));
             return (int)e;
         }
-        configured = true;
+        configured[dev] = true;
     }
     kern<<<grid, NTHREADS, sizeof(Smem), st>>>(prm);
     return check_launch("gp_predict_kernel");

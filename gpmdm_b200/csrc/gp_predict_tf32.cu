@@ -397,15 +397,19 @@ __global__ void pack_alpha_kernel(const double* __restrict__ alpha, long long n,
 
 template <int DL>
 static int launch(const Params& prm, int grid, cudaStream_t st) {
-    static bool configured = false;
+    // the opt-in to > 48 KB of dynamic shared memory is per function AND per device
+    static bool configured[64] = {};  // per instantiation
+    int dev = 0;
+    cudaGetDevice(&dev);
+    dev = (dev >= 0 && dev < 64) ? dev : 0;
     auto kern = observe_tf32_kernel<DL>;
-    if (!configured) {
+    if (!configured[dev]) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
         if (e != cudaSuccess) {
             set_error("cudaFuncSetAttribute(observe_tf32): %s", cudaGetErrorString(e));
             return (int)e;
         }
-        configured = true;
+        configured[dev] = true;
     }
     kern<<<grid, NTHREADS, sizeof(Smem), st>>>(prm);
     return check_launch("observe_tf32_kernel");
