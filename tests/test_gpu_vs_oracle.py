@@ -606,3 +606,44 @@ def test_degenerate_particle_and_class_counts(C, P):
         probs = pf.class_probabilities()
         assert probs.shape == (C,) and abs(float(probs.sum()) - 1.0) < 1e-12
         assert 0 <= pf.get_most_likely_class() < C
+
+
+def test_unequal_class_blocks_low_latency_vs_fused():
+    """Dynamics blocks of very different sizes (N_c = 39, 299, 1295: 1, 2 and 6 column panels) in one model: the
+    low-latency decomposition (per-block column tiles and k segments inside a uniform item grid) against the fused
+    kernel, per class and through a filter step."""
+    from gpmdm_b200 import GPMDM, GPMDM_PF
+
+    D, d = 9, 2
+    wl = synthetic.make_sequences(3, D, 5, 300, seed=4, n_test_trials=1, test_frames=4)
+    hp = synthetic.notebook_hyperparameters(D, d, 1e-1)
+    m = GPMDM(D=D, d=d, n_classes=3, dyn_target="full", dyn_back_step=1, **hp)
+    m.add_data(wl.sequences[0][0][:40], 0)
+    m.add_data(wl.sequences[1][0], 1)
+    for s in wl.sequences[2]:
+        m.add_data(s[:260], 2)
+    m.init_X()
+    m.set_evaluation_mode()
+    g = torch.Generator().manual_seed(3)
+    X = m.X.detach().cpu()
+    xs = (X[torch.randint(0, X.shape[0], (333,), generator=g)] + 0.05 * torch.randn(333, d, dtype=torch.float64, generator=g)).cuda()
+    for c in range(3):
+        mf, vf = m.map_x_dynamics_for_class(xs, c, low_latency=False)
+        ml, vl = m.map_x_dynamics_for_class(xs, c, low_latency=True)
+        prior = (2.0 + (xs ** 2).sum(1)).unsqueeze(1)  # all-ones linear coefficients; the variance contract is 1e-9 of it
+        assert float(torch.max(torch.abs(mf - ml))) < 1e-10 and float(torch.max(torch.abs(vf - vl) / prior)) < 1e-9
+    mu_f, var_f = m.map_x_to_y(xs, low_latency=False)
+    mu_l, var_l = m.map_x_to_y(xs, low_latency=True)
+    assert float(torch.max(torch.abs(mu_f - mu_l))) < 1e-10 and float(torch.max(torch.abs(var_f - var_l))) < 1e-10
+    T = synthetic.markov_matrix(3)
+    outs = []
+    for low in (False, True):
+        pf = GPMDM_PF(m, T, 500, seed=6, low_latency=low)
+        pf.update(wl.test_trials[0][1][0])
+        outs.append((pf.last_pre_resample_classes.clone(), pf.last_pre_resample_states.clone(), pf._log_likelihoods.clone()))
+    assert torch.equal(outs[0][0], outs[1][0])
+    # x' = eps * sqrt(var) + mean: where the predictive variance is ~1e-6 of the prior, the 1e-9-of-the-prior agreement of
+    # two summation orders becomes ~1e-7 after the square root (the reference itself is no more reproducible there,
+    # SURVEY fact 8)
+    assert float(torch.max(torch.abs(outs[0][1] - outs[1][1]))) < 1e-5
+    assert float(torch.max(torch.abs(outs[0][2] - outs[1][2]) / torch.abs(outs[0][2]))) < 1e-5
