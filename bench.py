@@ -143,35 +143,17 @@ def oracle_spec(a, wl, X0, hp):
 
 
 def oracle_factors(spec, device):
-    """The oracle's factor recipe (oracle.precompute_factors) evaluated with plain torch on `device`
-    (setup only -- it is not part of any timed region), returned on the CPU."""
+    """The oracle's factor recipe with the O(N^3) part evaluated by plain torch on `device` (setup only -- it is not
+    part of any timed region), returned on the CPU."""
     from oracle import gpmdm_oracle as orc
 
-    def inv(K):
-        U, _ = torch.linalg.cholesky_ex(K, upper=True)
-        Ui = torch.linalg.solve_triangular(U, torch.eye(K.shape[0], dtype=K.dtype, device=K.device), upper=True)
-        return Ui @ Ui.t()
-
-    ls = torch.exp(spec.y_log_lengthscales).to(device)
-    X = spec.X.to(device)
-    A = X / ls
-    A2 = (A * A).sum(1, keepdim=True)
-    Ky = torch.exp(-(A2 + A2.t() - 2 * A @ A.t()))
-    Ky.diagonal().add_(float(torch.exp(spec.y_log_sigma_n) ** 2 + spec.sigma_n_num_Y ** 2))
-    Ky_inv = inv(Ky).cpu()
-    del Ky
-    Xin, Xout = orc.xin_xout(spec)
-    blocks = []
-    for a, b in spec.class_pair_ranges():
-        Kc = orc.x_kernel(spec, Xin[a:b], Xin[a:b]).to(device)
-        Kc.diagonal().add_(1e-6)
-        blocks.append(inv(Kc).cpu())
-    return orc.precompute_factors(spec, Ky_inv=Ky_inv, Kx_inv_blocks=blocks)
+    return orc.precompute_factors_on(spec, device)
 
 
-def time_oracle(a, wl, spec, factors, sample, steps, warmup):
+def time_oracle(a, wl, spec, factors, sample, steps, warmup, loop_ll=True):
     """Times `FilterOracle.update` + class query (the region the reference's notebook times,
-    test_gpmdm_pf.ipynb cell 4) on `sample` particles with all host threads."""
+    test_gpmdm_pf.ipynb cell 4) on `sample` particles with all host threads.  Also returns the oracle with the trace
+    of its last step and that step's inputs (the parity block compares the CUDA path on exactly those)."""
     from gpmdm_b200 import synthetic
     from oracle import gpmdm_oracle as orc
 
@@ -183,17 +165,107 @@ def time_oracle(a, wl, spec, factors, sample, steps, warmup):
     init_idx = [torch.randint(0, hi - lo, (parts[c],), generator=g) for c, (lo, hi) in enumerate(spec.class_row_ranges())]
     o = orc.FilterOracle(spec, T, sample, init_idx, factors)
     trial = wl.test_trials[0][1]
-    times = []
+    times, last = [], None
     with torch.no_grad():
         for t in range(warmup + steps):
             E, eps, u = synthetic.raw_draws(sample, C, d, 100 + t)
+            last = dict(x_prev=o.states.clone(), c_prev=o.classes.clone(), z=trial[t % trial.shape[0]], E=E, eps=eps, u=u)
             t0 = time.perf_counter()
-            o.update(trial[t % trial.shape[0]], E, eps, u, loop_ll=True)  # the reference's per-particle loop
+            o.update(last["z"], E, eps, u, loop_ll=loop_ll)  # loop_ll: the reference's per-particle loop
             o.get_most_likely_class()
             dt = time.perf_counter() - t0
             if t >= warmup:
                 times.append(dt)
-    return sample * len(times) / sum(times), 1e3 * sum(times) / len(times), torch.get_num_threads()
+    return sample * len(times) / sum(times), 1e3 * sum(times) / len(times), torch.get_num_threads(), o, last
+
+
+def parity_block(pf, model, o, last, T):
+    """The CUDA path (the kernel instances of the timed region: fused observation kernel with the K* cache, fused
+    dynamics kernel, filter stages) on the inputs of the oracle's last step, against the oracle's outputs for that step.
+    Runs outside every timed region.  Reference lines: gpmdm.py:923-963, :1032-1068, gpmdm_pf.py:137-213."""
+    import ctypes
+
+    from gpmdm_b200 import _cabi
+    from gpmdm_b200._cabi import check, ptr, stream
+
+    lib = _cabi.lib()
+    tr, spec = o.trace, o.m
+    n, C, d, D = o.P, spec.n_classes, spec.d, spec.D
+    dev = model.device
+    f64 = torch.float64
+    cu = lambda t: t.to(dev).contiguous()
+    # observation GP + fused log-likelihood on the oracle's pre-resample states
+    x = cu(tr["x_new"])
+    z = torch.as_tensor(np.asarray(last["z"]), dtype=f64, device=dev)
+    ll, mu, v = (torch.empty(n, dtype=f64, device=dev), torch.empty(n, D, dtype=f64, device=dev),
+                 torch.empty(n, dtype=f64, device=dev))
+    pk = pf._packed
+    counter = torch.zeros(4, dtype=torch.int32, device=dev)
+    if pf._kstar_cache:
+        check(lib.gpmdm_pf_observe_cached_f64(ctypes.byref(pk["obs"]), ptr(x), n, ptr(z), pf._ll_const, ptr(ll), ptr(mu),
+                                              ptr(v), pk["obs_n_pad"], ptr(counter), ptr(pf._ws_kstar),
+                                              pf._ws_kstar.numel() * 8, stream()), "gpmdm_pf_observe_cached_f64")
+        kern = "gpmdm_pf_observe_cached_f64"
+    else:
+        check(lib.gpmdm_pf_observe_f64(ctypes.byref(pk["obs"]), ptr(x), n, ptr(z), pf._ll_const, ptr(ll), ptr(mu), ptr(v),
+                                       ptr(counter), stream()), "gpmdm_pf_observe_f64")
+        kern = "gpmdm_pf_observe_f64"
+    mu, v, ll = mu.cpu(), v.cpu(), ll.cpu()
+    mscale = torch.clamp(tr["mu"].abs().max(dim=1, keepdim=True).values, min=1e-3)
+    ok = tr["v"] > 1e-3
+    ll_rel = (ll - tr["ll"]).abs() / tr["ll"].abs()
+    # dynamics GP (fused kernel) per class on the oracle's previous states
+    lam_x = torch.exp(spec.x_log_lambdas) ** -2
+    dm = dv = 0.0
+    for c in range(C):
+        rows = torch.nonzero(tr["c_new"] == c).squeeze(-1)
+        if rows.numel() == 0:
+            continue
+        xs = last["x_prev"][rows]
+        mean, var = model.map_x_dynamics_for_class(cu(xs), c, low_latency=False)
+        prior = (1.0 + (xs * xs * torch.exp(spec.x_log_lin_coeff[:-1]) ** 2).sum(1)
+                 + torch.exp(spec.x_log_lin_coeff[-1]) ** 2).unsqueeze(1) * lam_x.unsqueeze(0)
+        sc = torch.clamp(tr["dyn_mean"][rows].abs().max(dim=1, keepdim=True).values, min=1e-3)
+        dm = max(dm, float(((mean.cpu() - tr["dyn_mean"][rows]).abs() / sc).max()))
+        dv = max(dv, float(((var.cpu() - tr["dyn_var"][rows]).abs() / prior).max()))
+    # integer stages on the oracle's own inputs: class transition, normalise + sequential cdf + search
+    c_new = torch.empty(n, dtype=torch.int64, device=dev)
+    check(lib.gpmdm_pf_transition_f64(ptr(cu(last["c_prev"])), ptr(cu(T.to(f64))), ptr(cu(last["E"])), n, C, ptr(c_new),
+                                      stream()), "gpmdm_pf_transition_f64")
+    ws = torch.empty(int(lib.gpmdm_workspace_bytes(n, C)) // 8 + 1, dtype=f64, device=dev)
+    lw, w, cdf, st2 = (torch.empty(n, dtype=f64, device=dev) for _ in range(4))
+    anc = torch.empty(n, dtype=torch.int64, device=dev)
+    ll_o = cu(tr["ll"])
+    check(lib.gpmdm_pf_normalize_f64(ptr(ll_o), n, ptr(lw), ptr(w), ptr(st2), ptr(ws), stream()), "gpmdm_pf_normalize_f64")
+    check(lib.gpmdm_pf_cdf_f64(ptr(w), n, 0, ptr(cdf), ptr(ws), stream()), "gpmdm_pf_cdf_f64")
+    check(lib.gpmdm_pf_resample_f64(ptr(cdf), n, ptr(cu(last["u"])), n, None, None, d, ptr(anc), None, None, stream()),
+          "gpmdm_pf_resample_f64")
+    return {
+        "against": "CPU oracle (oracle/gpmdm_oracle.py, pinned to the unmodified reference by tests/golden), its last step",
+        "sample_particles": n, "observe_entry_point": kern,
+        "obs_mean_err_of_row_scale_max": float(((mu - tr["mu"]).abs() / mscale).max()),
+        "obs_var_err_of_prior_max": float((v - tr["v"]).abs().max()),
+        "ll_rel_err_max": float(ll_rel[ok].max()) if bool(ok.any()) else None,
+        "ll_rel_err_median": float(ll_rel[ok].median()) if bool(ok.any()) else None,
+        "ll_compared": int(ok.sum()), "v_min": float(tr["v"].min()),
+        "dyn_mean_err_of_row_scale_max": dm, "dyn_var_err_of_prior_max": dv,
+        "classes_equal": bool(torch.equal(c_new.cpu(), tr["c_new"])),
+        "log_weights_equal": bool(torch.equal(lw.cpu(), tr["lw"])),
+        "ancestors_equal": bool(torch.equal(anc.cpu(), tr["anc"])),
+        "tolerances": "north_star: integers bit-exact; means / variances 1e-9 (variances of the prior); ll 1e-6 where "
+                      "v > 1e-3 (cancellation in 1 - k^T K^-1 k, DESIGN.md section 2)",
+    }
+
+
+def state_digest(pf):
+    """sha256 over the replicated filter state after the last timed step: post-resample classes || ancestors || the
+    bits of the log-likelihoods.  Identical for every GPU count iff a G-GPU run equals the 1-GPU run bit for bit."""
+    import hashlib
+
+    h = hashlib.sha256()
+    for t in (pf._particle_classes, pf.last_ancestors, pf._log_likelihoods):
+        h.update(t.detach().cpu().contiguous().numpy().tobytes())
+    return h.hexdigest()
 
 
 # ---- main ---------------------------------------------------------------------------------------------------
@@ -206,7 +278,7 @@ def run_reference(a):
     dev = "cuda" if torch.cuda.is_available() else "cpu"
     f = oracle_factors(spec, dev)
     warm = min(a.warmup, 1)
-    val, ms, cores = time_oracle(a, wl, spec, f, a.cpu_sample, a.steps, warm)
+    val, ms, cores, _, _ = time_oracle(a, wl, spec, f, a.cpu_sample, a.steps, warm)
     sample = f"{a.cpu_sample} of {a.particles} particles per step, {a.steps} steps (+{warm} warm-up), N_train={spec.N}"
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
@@ -284,6 +356,7 @@ def run_ours(a):
     obs_ms = [s.elapsed_time(e) for s, e in pf._profile_events]
     pf._profile_events = None
     clk = clocks.stop() if rank == 0 else None
+    digest = state_digest(pf) if rank == 0 else None  # after the last timed step, outside the timed region
 
     # end-to-end leg (host buffers in, host result out)
     ke = max(1, min(a.steps, 2))
@@ -308,61 +381,74 @@ def run_ours(a):
         e2e_val = P * ke / (e2e_ms * 1e-3)
         # roofline of the dominant kernel: observation-GP contraction, one launch per step per rank
         Pl = P // world
-        flops_alg = Pl * (2.0 * N * N + 2.0 * N * D)           # obs var + obs mean terms
         TN = 256                                                # column-tile width of the predict kernel
         n_pad = (N + TN - 1) // TN * TN
-        nq = n_pad // TN  # executed per particle: [TN k-rows x TN columns] blocks of the lower triangle + mean tile
-        flops_exec = Pl * (2.0 * TN ** 2) * (nq * (nq + 1) / 2 + nq) \
-            if not a.dense else Pl * (2.0 * n_pad * n_pad + 2.0 * n_pad * TN)
+        nq = n_pad // TN
+        secs = obs_avg_ms * 1e-3
+        tiles = (Pl + 63) // 64
         if a.precision == "fp64":
             tf = ctypes_probe(lib)
-            achieved = flops_alg / (obs_avg_ms * 1e-3) / 1e12
+            # flops the algorithm in use needs per particle (un-padded): k^T Q k on the triangular packing of the
+            # symmetric K^-1 (N^2: N(N+1)/2 multiply-adds) + the mean K* alpha (2ND)
+            flops_need = Pl * (1.0 * N * N + 2.0 * N * D) if not a.dense else Pl * (2.0 * N * N + 2.0 * N * D)
+            # flops the kernel issues per 64-particle tile: [16 k x 256 col] DMMA chunks of the lower triangle of column
+            # panels, + for the alpha tile only the groups of 8 column blocks (64 columns) that hold real outputs
+            alpha_cols = min((D + 63) // 64 * 64, TN) + (max(D - TN, 0) + 63) // 64 * 64
+            flops_exec = tiles * 64 * (2.0 * TN * TN * (nq * (nq + 1) / 2 if not a.dense else nq * nq) + 2.0 * n_pad * alpha_cols)
+            flops_dense = Pl * (2.0 * N * N + 2.0 * N * D)       # the dense formulation's count
+            achieved = flops_need / secs / 1e12
             cached = bool(getattr(pf, "_kstar_cache", False))
-            tiles = (Pl + 63) // 64
-            # DRAM bytes per 64-particle tile from the ncu launch list of this command at P = 131072
-            # (profiles/launches_r01.txt): (4454.3 + 106.6) GB over 5 launches of 2048 tiles.  With the K* cache the
-            # kernel trades the exp re-evaluation for re-reading the tile's K* slice (n_pad x 64 doubles) once per column tile.
-            per_tile = (4454.346e9 + 106.627e9) / 5 / 2048 if cached and N == 20000 and not a.dense else None
+            traffic, traffic_note = measured_traffic(N, d, cached, not a.dense, tiles)
             roofline = {
                 "bound": "tensor", "achieved": achieved, "peak": tf, "unit": "TFLOP/s", "frac": achieved / tf,
-                "traffic": per_tile * tiles if per_tile else None,
-                "traffic_note": "DRAM bytes per launch = ncu-measured bytes per 64-particle tile (launch list of this command at "
-                                "P=131072, profiles/launches_r01.txt: 445 MB per tile, of which 12 MB are L + alpha -- read "
-                                "once per round of 148 tiles, the rounds are kept in L2 lockstep -- and the rest is the per-SM "
-                                "K* cache being re-read once per column tile: 557 GB/s = 8.6 % of the HBM peak, traded for "
-                                "the exp work on the fp64 datapath) x the tiles of this launch"
-                                if per_tile else "not measured for this configuration",
+                "traffic": traffic, "traffic_note": traffic_note,
                 "kernel": f"gp_predict_kernel<0,{d},{'true' if cached else 'false'}> "
                           f"({'gpmdm_pf_observe_cached_f64' if cached else 'gpmdm_pf_observe_f64'})",
-                "launch_ms": obs_avg_ms,
+                "launch_ms": obs_avg_ms, "launch_share_of_step": obs_avg_ms / (elapsed_ms / a.steps),
                 "peak_source": "fp64 mma.sync m8n8k4 issue-rate probe measured in this run (MEASURED_PEAKS.json holds "
-                               "no fp64 figure)",
-                "executed_tflops": flops_exec / (obs_avg_ms * 1e-3) / 1e12,
-                "executed_frac": flops_exec / (obs_avg_ms * 1e-3) / 1e12 / tf,
-                "note": "achieved counts ALGORITHMIC flops 2N^2+2ND per particle; the kernel executes ~half of them "
-                        "because k^T K^-1 k is evaluated on the triangular packing of the symmetric K^-1" if not a.dense
-                        else "dense K^-1",
+                               "no fp64 figure); = 148 SMs x 64 FMA/clk x 2 x SM clock",
+                "executed_tflops": flops_exec / secs / 1e12, "executed_frac": flops_exec / secs / 1e12 / tf,
+                "dense_equivalent_tflops": flops_dense / secs / 1e12,
+                "note": ("achieved = (N^2 + 2ND) flops per particle, the un-padded need of the algorithm in use (quadratic form "
+                         "on the triangular packing of the symmetric K^-1); executed = DMMA flops issued incl. padding of N to "
+                         "256 and of D to 64; dense_equivalent = SURVEY 8(d)'s 2N^2 + 2ND per particle over the same time "
+                         "(not a roofline fraction)") if not a.dense else "dense K^-1",
             }
         else:
             # tf32 variant: whitened form |W k|^2 on the lower-triangular W (N^2 + 2ND algorithmic flops per particle),
-            # executed as 3 tf32 MMAs per product; peak = nominal dense tf32 (no measured tf32 figure in MEASURED_PEAKS)
+            # executed as 3 tf32 MMAs per product; peak = tcgen05 kind::tf32 issue-rate probe of this run
+            tf = ctypes_probe(lib, "gpmdm_probe_tf32_tflops", 20000)
+            tiles128 = (Pl + 127) // 128
             flops_alg32 = Pl * (1.0 * N * N + 2.0 * N * D)
-            flops_mma = 3.0 * Pl * (2.0 * TN * TN) * (nq * (nq + 1) / 2 + nq)
-            achieved = flops_mma / (obs_avg_ms * 1e-3) / 1e12
+            flops_mma = 3.0 * tiles128 * 128 * (2.0 * TN * TN) * (nq * (nq + 1) / 2 + nq)
+            achieved = flops_mma / secs / 1e12
             roofline = {
-                "bound": "tensor", "achieved": achieved, "peak": 1100.0, "unit": "TFLOP/s", "frac": achieved / 1100.0,
-                "traffic": None, "kernel": f"observe_tf32_kernel<{d}> (gpmdm_pf_observe_tf32) + fp64 mean tile (gpmdm_pf_loglik_f64)", "launch_ms": obs_avg_ms,
-                "peak_source": "nominal dense tf32 (1.1 PFLOP/s); achieved counts the tf32 MMA flops issued (3 per product)",
-                "algorithmic_tflops": flops_alg32 / (obs_avg_ms * 1e-3) / 1e12,
+                "bound": "tensor", "achieved": achieved, "peak": tf, "unit": "TFLOP/s", "frac": achieved / tf,
+                "traffic": None, "kernel": f"observe_tf32_kernel<{d}> (gpmdm_pf_observe_tf32) + fp64 mean tile (gpmdm_pf_loglik_f64)",
+                "launch_ms": obs_avg_ms, "launch_share_of_step": obs_avg_ms / (elapsed_ms / a.steps),
+                "peak_source": "tcgen05.mma kind::tf32 M128 N256 K8 issue-rate probe (resident pseudo-random operands) measured "
+                               "in this run; nominal dense tf32 is 1100; achieved counts the tf32 MMA flops issued (3 per product)",
+                "algorithmic_tflops": flops_alg32 / secs / 1e12, "algorithmic_frac": flops_alg32 / secs / 1e12 / tf,
             }
-        cpu = None
-        if not a.no_cpu_baseline and world == 1:
+        cpu, parity = None, None
+        if not a.no_cpu_baseline:
             spec = oracle_spec(a, wl, X0, hp)
             f = oracle_factors(spec, "cuda")
-            v, ms, cores = time_oracle(a, wl, spec, f, a.cpu_sample, 2, 1)
-            cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                   "sample": f"{a.cpu_sample} of {P} particles, 2 steps (+1 warm-up), N_train={N}; per-particle cost "
-                             f"is independent of P"}
+            if world == 1:
+                v, ms, cores, orc_f, last = time_oracle(a, wl, spec, f, a.cpu_sample, 2, 1)
+                cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                       "sample": f"{a.cpu_sample} of {P} particles, 2 steps (+1 warm-up), N_train={N}; per-particle cost "
+                                 f"is independent of P"}
+            else:  # N > 1: no CPU timing (contract), a smaller untimed oracle step for the parity block only
+                _, _, _, orc_f, last = time_oracle(a, wl, spec, f, min(a.cpu_sample, 512), 1, 0, loop_ll=False)
+            parity = parity_block(pf, model, orc_f, last, T)
+            del f, orc_f
+        if parity is not None:
+            parity["digest"] = digest
+            parity["digest_of"] = (f"sha256(classes_post || ancestors || ll bits) after {a.warmup} warm-up + {a.steps} timed "
+                                   f"steps, seed 1234: equal across --gpus N iff the sharded run is bit-identical")
+        else:
+            parity = {"digest": digest}
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": elapsed_ms / a.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -372,7 +458,7 @@ def run_ours(a):
                              % (1e-9 * lib.gpmdm_quadform_bytes((N + 255) // 256 * 256, 0 if a.dense else 1)),
                        "resampling": "multinomial", "draws": "device Philox4x32-10", "tri": not a.dense,
                        "parallelism": f"particles sharded over {world} rank(s), factors replicated"},
-            "roofline": roofline, "cpu_baseline": cpu,
+            "roofline": roofline, "cpu_baseline": cpu, "parity": parity,
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(z_pinned[0].numel() * z_pinned[0].element_size()),
                     "d2h_bytes_per_step": int(probs.numel() * probs.element_size()), "steps": ke},
             "gpu_launches": int(pf.launches_per_step * a.steps), "clocks": clk,
@@ -383,14 +469,31 @@ def run_ours(a):
         dist.destroy_process_group()
 
 
-def ctypes_probe(lib):
+def ctypes_probe(lib, name="gpmdm_probe_dmma_tflops", iters=20000):
     import ctypes
 
     tf = ctypes.c_double(0.0)
-    rc = lib.gpmdm_probe_dmma_tflops(20000, ctypes.byref(tf))
+    rc = getattr(lib, name)(iters, ctypes.byref(tf))
     if rc != 0:
-        raise RuntimeError("gpmdm_probe_dmma_tflops failed")
+        raise RuntimeError(name + " failed")
     return tf.value
+
+
+def measured_traffic(N, d, cached, tri, tiles):
+    """DRAM bytes per launch of the observation kernel = bytes per 64-particle tile measured by ncu on the committed code
+    (profiles/traffic_obs_kernel.json, written by tools/ncu_traffic.py from an `ncu --set full` capture) x the tiles of
+    this launch.  None when no capture matches this configuration."""
+    path = os.path.join(ROOT, "profiles", "traffic_obs_kernel.json")
+    try:
+        rec = json.load(open(path))
+    except (OSError, ValueError):
+        return None, "no ncu capture committed (profiles/traffic_obs_kernel.json missing)"
+    for r in rec.get("captures", []):
+        if r["N"] == N and r["d"] == d and bool(r["kstar_cache"]) == cached and bool(r["tri"]) == tri:
+            return r["dram_bytes_per_tile"] * tiles, (
+                f"offline ncu measurement ({r['source']}): {r['dram_bytes_per_tile'] / 1e6:.1f} MB of DRAM traffic per "
+                f"64-particle tile x {tiles} tiles of this launch; {r.get('note', '')}")
+    return None, "no ncu capture for this configuration in profiles/traffic_obs_kernel.json"
 
 
 def main():

@@ -90,6 +90,7 @@ _SIGNATURES = {
                                              _ptr, _ptr, _ptr, _ptr]),
     "gpmdm_kernel_grad_workspace_bytes": (_i64, [_i64, _i32]),
     "gpmdm_probe_dmma_tflops": (ctypes.c_int, [_i32, ctypes.POINTER(_f64)]),
+    "gpmdm_probe_tf32_tflops": (ctypes.c_int, [_i32, ctypes.POINTER(_f64)]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
@@ -113,7 +114,7 @@ def lib() -> ctypes.CDLL:
         for name, (res, args) in _SIGNATURES.items():
             fn = getattr(handle, name)  # AttributeError if the build is stale
             fn.restype, fn.argtypes = res, args
-        if handle.gpmdm_abi_version() != 2:
+        if handle.gpmdm_abi_version() != 3:
             raise RuntimeError("libgpmdm_sm100a.so ABI version mismatch; rebuild")
         _lib = handle
     return _lib

@@ -71,6 +71,7 @@ struct PredictParams {
     const int32_t* n_tiles;
     long long P;
     int32_t* counter;  // [0] tile hand-out, [1] round synchronisation
+    int32_t* status;   // [0] dynamics, [1] observation: particles whose predictive variance was not a positive finite number
     int round_sync;    // re-align the CTAs after every particle tile (uniform tiles, several rounds)
     // low-latency (split) mode: one work item per (particle tile, column tile); partial results go to the workspace
     // The k range of every column tile is cut further into `nseg` segments of `seg_chunks` chunks, so that a handful of
@@ -520,6 +521,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) gp_predict_kernel(const PredictPa
                     v += __shfl_xor_sync(0xffffffffu, v, 1);
                     v += __shfl_xor_sync(0xffffffffu, v, 2);
                     vrow = prior - v;
+                    // the reference lets sqrt / log of such a variance produce NaN (gpmdm_pf.py:168, :189); so does this
+                    // kernel, but it also counts the particles it happened to
+                    if (c == 0 && pidx >= 0 && !(vrow > 0.0 && vrow < INFINITY)) atomicAdd(prm.status + (KIND == 0 ? 1 : 0), 1);
                 }
             } else {
                 const int cbase = (ct - nq) * TN;
@@ -598,6 +602,7 @@ __global__ void __launch_bounds__(128) predict_finalize_kernel(const PredictPara
     };
     if (KIND == 0) {
         const double v = prm.v_in ? prm.v_in[p] : 1.0 - q;
+        if (lane == 0 && !prm.v_in && !(v > 0.0 && v < INFINITY)) atomicAdd(prm.status + 1, 1);
         double S = 0.0;
         for (int j = lane; j < prm.dout; j += 32) {
             const double mu = mean(j);
@@ -620,6 +625,7 @@ __global__ void __launch_bounds__(128) predict_finalize_kernel(const PredictPara
         }
         prior += prm.lin_c2[d];
         const double v = prior - q;
+        if (lane == 0 && !(v > 0.0 && v < INFINITY)) atomicAdd(prm.status, 1);
         for (int k = lane; k < prm.dout; k += 32) {
             const double var = v * prm.scale[k], mu = mean(k);
             const long long o = p * prm.dout + k;
@@ -740,6 +746,7 @@ extern "C" int gpmdm_pf_propagate_f64(const gpmdm_gp_model* dyn, const double* x
     prm.n_tiles = n_tiles;
     prm.P = P;
     prm.counter = tile_counter;
+    prm.status = tile_counter + 2;
     prm.eps = eps;
     prm.x_new = x_new;
     prm.mean_out = mean_out;
@@ -798,6 +805,7 @@ static int observe_impl(const gpmdm_gp_model* obs, const double* x, int64_t P, c
     prm.x = x;
     prm.P = P;
     prm.counter = tile_counter;
+    prm.status = tile_counter + 2;
     prm.z = z;
     prm.v_in = v_in;
     prm.ll_const = ll_const;
@@ -876,6 +884,7 @@ extern "C" int gpmdm_pf_observe_lowlat_f64(const gpmdm_gp_model* obs, const doub
     prm.x = x;
     prm.P = P;
     prm.counter = tile_counter;
+    prm.status = tile_counter + 2;
     prm.z = z;
     prm.v_in = v_in;
     prm.ll_const = ll_const;
@@ -903,6 +912,7 @@ extern "C" int gpmdm_pf_propagate_lowlat_f64(const gpmdm_gp_model* dyn, const do
     prm.n_tiles = n_tiles;
     prm.P = P;
     prm.counter = tile_counter;
+    prm.status = tile_counter + 2;
     prm.eps = eps;
     prm.x_new = x_new;
     prm.mean_out = mean_out;

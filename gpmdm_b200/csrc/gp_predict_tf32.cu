@@ -65,6 +65,7 @@ struct Params {
     double* mu_out;
     double* v_out;
     int32_t* round_counter;  // device scratch (zeroed by the call), NULL = no round synchronisation
+    int32_t* status;         // particles whose variance was not a positive finite number (NULL = not counted)
 };
 
 // element (row, k) of a [rows x KC] operand tile in the canonical no-swizzle K-major layout, in floats
@@ -337,6 +338,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) observe_tf32_kernel(const Params 
             }
             if (valid) {
                 const double v = 1.0 - (double)q;
+                if (prm.status && !(v > 0.0 && v < INFINITY)) atomicAdd(prm.status, 1);
                 if (prm.ll) prm.ll[p] = -0.5 * S / v - (double)prm.dout * log(v) + prm.ll_const;
                 if (prm.v_out) prm.v_out[p] = v;
             }
@@ -415,6 +417,67 @@ static int launch(const Params& prm, int grid, cudaStream_t st) {
     return check_launch("observe_tf32_kernel");
 }
 
+// ---- tf32 tensor-core peak probe (the denominator of the tf32 roofline in bench.py) --------------------------------
+// One CTA per SM; one thread issues `iters` x 2 tcgen05.mma (M = 128, N = 256, K = 8, kind::tf32) back to back on a
+// resident pair of operand tiles holding pseudo-random values (realistic datapath toggling, i.e. realistic power),
+// alternating between the two TMEM accumulators exactly as observe_tf32_kernel does.  No loads, no epilogue: this is
+// the rate the tensor pipe sustains when nothing else limits it.
+struct ProbeSmem {
+    float A[A_HALF];
+    float B[B_HALF];
+    uint64_t done;
+    uint32_t tmem_base;
+};
+
+__global__ void __launch_bounds__(128, 1) tf32_probe_kernel(int iters, float* __restrict__ sink) {
+    __shared__ __align__(1024) ProbeSmem s;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    uint32_t h = 0x9E3779B9u * (uint32_t)(tid + 1);
+    for (int i = tid; i < A_HALF + B_HALF; i += 128) {
+        h = h * 1664525u + 1013904223u;
+        const float u = (float)(h >> 8) * (1.0f / 16777216.0f);  // [0, 1)
+        if (i < A_HALF) s.A[i] = to_tf32(u);
+        else s.B[i - A_HALF] = to_tf32((u - 0.5f) * 1e-3f);
+    }
+    if (tid == 0) {
+        mbar_init(&s.done, 1);
+        mbar_fence_init();
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s.tmem_base)),
+                     "r"(512u)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = s.tmem_base;
+    if (tid == 0) {
+        for (int it = 0; it < iters; it++) {
+            const uint32_t d_tmem = tmem + (uint32_t)(it & 1) * TN;
+#pragma unroll
+            for (int k8 = 0; k8 < KC / 8; k8++) {
+                const uint32_t koff = k8 * 2 * LBO;
+                umma_tf32(d_tmem, smem_desc(reinterpret_cast<const char*>(s.A) + koff),
+                          smem_desc(reinterpret_cast<const char*>(s.B) + koff), (it > 1) || k8);
+            }
+        }
+        umma_commit(&s.done);
+        mbar_wait(&s.done, 0);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (warp == 0) {
+        float v[32];
+        tmem_ld32(tmem, v);  // keep the accumulator observable
+        if (v[0] == 123.456f && sink) sink[0] = v[1];
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+    }
+}
+
 }  // namespace tf32
 }  // namespace gpmdm
 
@@ -480,6 +543,7 @@ extern "C" int gpmdm_pf_observe_tf32(const gpmdm_gp_model_tf32* m, const double*
     const long long tiles = (P + tf32::TM - 1) / tf32::TM;
     const int grid = (int)(tiles < sms ? tiles : sms);
     cudaStream_t st = (cudaStream_t)stream;
+    prm.status = tile_counter ? tile_counter + 3 : nullptr;
     if (tile_counter && tiles >= 2ll * grid) {
         cudaError_t e = cudaMemsetAsync(tile_counter, 0, sizeof(int32_t), st);
         GPMDM_REQUIRE(e == cudaSuccess, (int)e, "cudaMemsetAsync: %s", cudaGetErrorString(e));
@@ -496,4 +560,33 @@ extern "C" int gpmdm_pf_observe_tf32(const gpmdm_gp_model_tf32* m, const double*
         case 8: return tf32::launch<8>(prm, grid, st);
     }
     return GPMDM_E_UNSUPPORTED;
+}
+
+extern "C" int gpmdm_probe_tf32_tflops(int32_t iters, double* tflops_host) {
+    GPMDM_REQUIRE(tflops_host && iters > 0, GPMDM_E_INVALID, "bad argument");
+    int dev = 0, sms = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    GPMDM_REQUIRE(e == cudaSuccess, GPMDM_E_NODEVICE, "cudaGetDevice: %s", cudaGetErrorString(e));
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaEvent_t t0, t1;
+    cudaEventCreate(&t0);
+    cudaEventCreate(&t1);
+    tf32::tf32_probe_kernel<<<sms, 128>>>(iters / 4 + 1, nullptr);  // warm-up
+    float best = 1e30f;
+    for (int rep = 0; rep < 5; rep++) {
+        cudaEventRecord(t0);
+        tf32::tf32_probe_kernel<<<sms, 128>>>(iters, nullptr);
+        cudaEventRecord(t1);
+        cudaEventSynchronize(t1);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, t0, t1);
+        if (ms < best) best = ms;
+    }
+    cudaEventDestroy(t0);
+    cudaEventDestroy(t1);
+    int rc = check_launch("tf32_probe_kernel");
+    if (rc) return rc;
+    const double flops = 2.0 * tf32::TM * tf32::TN * tf32::KC * (double)iters * sms;
+    *tflops_host = flops / (best * 1e-3) / 1e12;
+    return 0;
 }

@@ -64,21 +64,21 @@ class _KernelBuild(torch.autograd.Function):
         kind = 0 if log_lin_coeff is None else 1
         ls = torch.exp(log_ls).contiguous()
         c2 = (torch.exp(log_lin_coeff) ** 2).contiguous() if kind else None
-        sigma2 = float(torch.exp(log_sigma_n) ** 2) if flg_noise else 0.0
+        sigma2 = float(torch.exp(log_sigma_n.detach()).reshape(-1)[0] ** 2) if flg_noise else 0.0
         noise2 = sigma2 + (float(sigma_n_num) ** 2 if flg_noise else 0.0)
         K = torch.empty(n, n, dtype=X.dtype, device=X.device)
         ncls = 0 if class_offsets is None else class_offsets.numel() - 1
         check(lib.gpmdm_kernel_build_f64(ptr(X), n, d, kind, ptr(ls), ptr(c2), noise2, ptr(class_offsets), ncls,
                                          ptr(K), stream()), "gpmdm_kernel_build_f64")
         ctx.save_for_backward(X, ls, c2 if kind else X.new_empty(0), class_offsets if ncls else X.new_empty(0))
-        ctx.meta = (kind, sigma2, ncls, log_sigma_n is not None)
+        ctx.meta = (kind, sigma2, ncls, tuple(log_sigma_n.shape))
         return K
 
     @staticmethod
     def backward(ctx, G):
         lib = _cabi.lib()
         X, ls, c2, offs = ctx.saved_tensors
-        kind, sigma2, ncls, _ = ctx.meta
+        kind, sigma2, ncls, sig_shape = ctx.meta
         n, d = X.shape
         G = G.contiguous()
         gX = torch.empty_like(X)
@@ -89,7 +89,7 @@ class _KernelBuild(torch.autograd.Function):
         check(lib.gpmdm_kernel_grad_f64(ptr(X), ptr(G), n, d, kind, ptr(ls), ptr(c2) if kind else None, sigma2,
                                         ptr(offs) if ncls else None, ncls, ptr(gX), ptr(g_ls), ptr(g_sig),
                                         ptr(g_c) if kind else None, ptr(ws), stream()), "gpmdm_kernel_grad_f64")
-        return gX, g_ls, g_sig, g_c, None, None, None
+        return gX, g_ls, g_sig.reshape(sig_shape), g_c, None, None, None
 
 
 # ------------------------------------------------------------------------------------------------
@@ -139,6 +139,89 @@ def spd_inverse_from_cholesky(L):
     _tril_inverse_into(L, Li)
     out = torch.empty_like(L)
     _gram_of_tril_into(Li, out)
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# Factor precompute without dense intermediates (replaces the recipe of gpmdm.py:1284-1305: upper Cholesky,
+# torch.inverse(U), U^-1 U^-T -- five live N x N arrays in a direct transcription).  Here:
+#     K  --cholesky_ex-->  L (lower; K is released)  --in place-->  L^-1  --GEMM per column panel-->  Q panels
+# with K^-1 = L^-T L^-1 never stored densely: column panel J of the quadratic-form matrix the predict kernels stream
+# (include/gpmdm_b200.h: gpmdm_gp_block) is one GEMM   L^-1[c0:, r0:]^T  L^-1[c0:, c0:c0+256]   written straight into
+# the padded panel.  Peak memory: 2 N^2 doubles (K and L during the factorisation), 1.5 N^2 afterwards.
+# Pure torch (cuSOLVER potrf + cuBLAS DGEMM on the device); device agnostic, so the CPU suite checks the algebra.
+# ------------------------------------------------------------------------------------------------
+_TRINV_LEAF = 1024
+PANEL_LD = 260  # GPMDM_PANEL_LD
+
+
+def tril_inverse_inplace(L):
+    """L <- L^-1 for a lower-triangular L whose strict upper part is zero (stays zero).
+    [[A, 0], [B, C]]^-1 = [[A^-1, 0], [-C^-1 B A^-1, C^-1]], recursively, with one temporary of a quarter of the
+    matrix at the top level (GEMM-shaped: DGEMM runs at ~36 TF/s on B200, TRSM / cuSOLVER's trtri well below)."""
+    n = L.shape[0]
+    if n <= _TRINV_LEAF:
+        L.copy_(torch.linalg.solve_triangular(L, torch.eye(n, dtype=L.dtype, device=L.device), upper=False))
+        return L
+    h = _split(n)
+    A, B, C = L[:h, :h], L[h:, :h], L[h:, h:]
+    tril_inverse_inplace(A)
+    tril_inverse_inplace(C)
+    T = torch.mm(B, A)
+    torch.mm(C, T, out=B)
+    del T
+    B.neg_()
+    return L
+
+
+def panel_row_offset(t: int, n_pad: int, tri: bool) -> int:
+    """First row of column panel t in the packed quadratic-form array (csrc/common.cuh: panel_row_offset)."""
+    return t * n_pad - (TILE_N // 2) * t * (t - 1) if tri else t * n_pad
+
+
+def quadform_panel_elems(n_pad: int, tri: bool) -> int:
+    return panel_row_offset(n_pad // TILE_N, n_pad, tri) * PANEL_LD
+
+
+def quadform_panels_from_tril_inverse(Linv, n_pad: int, tri: bool, out=None):
+    """Column panels of Q (k^T K^-1 k == k^T Q k; tri: Q = 2 K^-1 strictly below the diagonal, K^-1 on it, 0 above;
+    dense: Q = K^-1) for K^-1 = Linv^T Linv, one GEMM per 256-column panel, written in place into the layout the
+    predict kernels stream.  Linv [n, n] lower triangular with an explicit zero upper part."""
+    n = Linv.shape[0]
+    if out is None:
+        out = torch.empty(quadform_panel_elems(n_pad, tri), dtype=Linv.dtype, device=Linv.device)
+    out.zero_()
+    for J in range(n_pad // TILE_N):
+        c0 = J * TILE_N
+        if c0 >= n:
+            break
+        w = min(TILE_N, n - c0)
+        r0 = c0 if tri else 0
+        off = panel_row_offset(J, n_pad, tri) * PANEL_LD
+        dst = out[off:off + (n_pad - r0) * PANEL_LD].view(n_pad - r0, PANEL_LD)[:n - r0, :w]
+        # K^-1[i, j] = sum_{k >= max(i, j)} Linv[k, i] Linv[k, j];  j >= c0 here, so k runs over rows c0.. only
+        torch.mm(Linv[c0:, r0:].t(), Linv[c0:, c0:c0 + w], out=dst)
+        if tri:
+            dst[w:].mul_(2.0)
+            diag = dst[:w]
+            diag.copy_(2.0 * torch.tril(diag, -1) + torch.diag(torch.diagonal(diag)))
+    return out
+
+
+def dense_from_quadform_panels(panels, n: int, n_pad: int, tri: bool):
+    """The dense symmetric K^-1 [n, n] back from the packed panels (API parity: `Ky_inv`, `Kx_inv_class[c]`)."""
+    out = torch.zeros(n, n, dtype=panels.dtype, device=panels.device)
+    for J in range(n_pad // TILE_N):
+        c0 = J * TILE_N
+        if c0 >= n:
+            break
+        w = min(TILE_N, n - c0)
+        r0 = c0 if tri else 0
+        off = panel_row_offset(J, n_pad, tri) * PANEL_LD
+        out[r0:, c0:c0 + w] = panels[off:off + (n_pad - r0) * PANEL_LD].view(n_pad - r0, PANEL_LD)[:n - r0, :w]
+    if tri:  # halving is exact
+        low = torch.tril(out, -1) * 0.5
+        out = low + low.t() + torch.diag(torch.diagonal(out))
     return out
 
 
@@ -476,34 +559,113 @@ class GPMDM(torch.nn.Module):
 
     @staticmethod
     def _inverse_via_upper_cholesky(K):
-        """U = chol_upper(K); K^-1 = U^-1 U^-T (gpmdm.py:1287-1289), with a triangular solve for U^-1."""
+        """U = chol_upper(K); K^-1 = U^-1 U^-T (gpmdm.py:1287-1289) as a dense matrix -- only for the class-agnostic
+        `Kx_inv` (not on the filter path); the filter's factors never take this route (`_factor_block`)."""
         U, _info = torch.linalg.cholesky_ex(K, upper=True)
         eye = torch.eye(K.shape[0], dtype=K.dtype, device=K.device)
         U_inv = torch.linalg.solve_triangular(U, eye, upper=True)
         return torch.matmul(U_inv, U_inv.t())
 
+    # Factor precisions built by `_precompute_kernel_inverses`: "fp64" = the quadratic-form panels of the exact path,
+    # "tf32" = the whitening-factor tiles of the tf32 variant.  Whatever is missing is built on first use; a tf32-only
+    # deployment at N = 50 k sets ("tf32",) to never hold the 10 GB of fp64 panels.
+    default_factor_precisions = ("fp64",)
+
+    def _factor_block(self, make_K, targets, want_fp64=True, want_tf32=False, tri=True):
+        """Factors of one GP block from its kernel matrix K = make_K() (built here so that this frame holds the only
+        reference and K is released as soon as it is factored).  K = L L^T (the reference's U is L^T), L^-1 in place, then
+            alpha  = K^-1 targets = L^-T (L^-1 targets)                         (gpmdm.py:957, 1064)
+            panels = column panels of Q, K^-1 = L^-T L^-1 never stored densely  (gpmdm.py:1289, 1305)
+            wtiles = W = U^-T = L^-1 as tf32 hi/lo tensor-core tiles            (tf32 variant)
+        Peak memory 2 N^2 doubles (K + L inside cholesky_ex)."""
+        lib = _cabi.lib()
+        K = make_K()
+        n = K.shape[0]
+        n_pad = _round_up(n, TILE_N)
+        L, _info = torch.linalg.cholesky_ex(K, upper=False)  # gpmdm.py:1287: info is ignored by the reference as well
+        del K
+        Linv = tril_inverse_inplace(L)
+        del L
+        blk = dict(n=n, n_pad=n_pad, dense=None, panels={}, wtiles=None,
+                   A=torch.mm(Linv.t(), torch.mm(Linv, targets)).contiguous())
+        if want_fp64:
+            blk["panels"][bool(tri)] = quadform_panels_from_tril_inverse(Linv, n_pad, bool(tri))
+        if want_tf32:
+            wt = torch.empty(int(lib.gpmdm_tf32_wtiles_bytes(n_pad)) // 4, dtype=torch.float32, device=self.device)
+            check(lib.gpmdm_pack_whitened_tf32(ptr(Linv), n, n_pad, ptr(wt), stream()), "gpmdm_pack_whitened_tf32")
+            blk["wtiles"] = wt
+        return blk
+
+    def _obs_kernel_matrix(self):
+        X = self.X.detach()
+        return self.get_y_kernel(X, X)  # same object twice: the symmetric CUDA build (csrc/train_kernels.cu)
+
+    def _dyn_kernel_matrix(self, c, jitter=1e-6):
+        offs = self.class_pair_offsets()
+        Xc = self._Xin[offs[c]:offs[c + 1]].contiguous()
+        Kc = _KernelBuild.apply(Xc, self.x_log_lengthscales, self.x_log_sigma_n, self.x_log_lin_coeff,
+                                self.sigma_n_num_X, None, True)
+        if jitter:
+            Kc.diagonal().add_(jitter)  # gpmdm.py:1302
+        return Kc
+
     @torch.no_grad()
     def _precompute_kernel_inverses(self):
-        """Ky_inv, per-class Kx_inv_class[c] (N_c x N_c blocks) and the alpha vectors.  The reference's
-        dense `Kx_inv` (:1291-1295) is only used by the class-agnostic `map_x_dynamics`, which the filter
+        """The factors the filter consumes (gpmdm.py:1284-1305) -- per block the alpha matrix and the packed
+        quadratic-form panels, built without dense N x N intermediates (`_factor_block`).  `Ky_inv` and
+        `Kx_inv_class[c]` (N_c x N_c diagonal blocks) remain available as attributes, materialised on access.  The
+        reference's dense `Kx_inv` (:1291-1295) is only used by the class-agnostic `map_x_dynamics`, which the filter
         never calls; it is built lazily by `Kx_inv` below."""
         X = self.X.detach()
-        self.Ky_inv = self._inverse_via_upper_cholesky(self.get_y_kernel(X, X))
         Xin, Xout, _ = self.get_Xin_Xout_matrices(X)
         self._Xin, self._Xout = Xin.contiguous(), Xout.contiguous()
-        self.Kx_inv_class = []
+        want = self.default_factor_precisions
+        self._obs_blk = self._factor_block(self._obs_kernel_matrix, self._Y_device(), "fp64" in want, "tf32" in want)
         offs = self.class_pair_offsets()
-        for c in range(self.n_classes):
-            a, b = offs[c], offs[c + 1]
-            Xc = Xin[a:b].contiguous()
-            Kc = _KernelBuild.apply(Xc, self.x_log_lengthscales, self.x_log_sigma_n, self.x_log_lin_coeff,
-                                    self.sigma_n_num_X, None, True)
-            Kc = Kc + 1e-6 * torch.eye(b - a, dtype=self.dtype, device=self.device)  # gpmdm.py:1302
-            self.Kx_inv_class.append(self._inverse_via_upper_cholesky(Kc))
+        self._dyn_blks = [self._factor_block(lambda: self._dyn_kernel_matrix(c), self._Xout[offs[c]:offs[c + 1]].contiguous())
+                          for c in range(self.n_classes)]
         self._Kx_inv_full = None
         self._factors_version += 1
         self._packed = None
         self._packed_tf32 = None
+
+    def _block_panels(self, blk, tri):
+        """Quadratic-form panels of a block in the requested packing: as factored, or packed from a dense inverse
+        (injected by `set_inverses`, or materialised from the other packing)."""
+        tri = bool(tri)
+        if tri not in blk["panels"]:
+            lib = _cabi.lib()
+            if blk["dense"] is None and not blk["panels"]:  # factored without fp64 panels (tf32-only precompute)
+                return None
+            Kinv = self._block_dense(blk)
+            L = torch.empty(int(lib.gpmdm_quadform_bytes(blk["n_pad"], int(tri))) // 8, dtype=self.dtype, device=self.device)
+            check(lib.gpmdm_pack_quadform_f64(ptr(Kinv), blk["n"], blk["n_pad"], int(tri), ptr(L), stream()),
+                  "gpmdm_pack_quadform_f64")
+            blk["panels"][tri] = L
+        return blk["panels"][tri]
+
+    def _block_dense(self, blk):
+        if blk["dense"] is not None:
+            return blk["dense"]
+        tri = True if True in blk["panels"] else False
+        return dense_from_quadform_panels(blk["panels"][tri], blk["n"], blk["n_pad"], tri)
+
+    def _ensure_fp64_obs_panels(self, tri):
+        blk = self._obs_blk
+        if blk["dense"] is None and not blk["panels"]:
+            fresh = self._factor_block(self._obs_kernel_matrix, self._Y_device(), True, False, tri)
+            blk["panels"] = fresh["panels"]
+
+    @property
+    def Ky_inv(self):
+        """Dense K_y^-1 [N, N] (gpmdm.py:1289).  Not stored: materialised from the packed panels on access."""
+        self._ensure_fp64_obs_panels(True)
+        return self._block_dense(self._obs_blk)
+
+    @property
+    def Kx_inv_class(self):
+        """Per class, the N_c x N_c diagonal block of the reference's `Kx_inv_class[c]` (gpmdm.py:1305)."""
+        return [self._block_dense(b) for b in self._dyn_blks]
 
     @property
     def Kx_inv(self):
@@ -512,22 +674,30 @@ class GPMDM(torch.nn.Module):
                 self._Kx_inv_full = self._inverse_via_upper_cholesky(self.get_masked_x_kernel(self._Xin))
         return self._Kx_inv_full
 
+    @torch.no_grad()
     def set_inverses(self, Ky_inv=None, Kx_inv_blocks=None):
         """Inject precomputed inverses (e.g. the reference's own `Ky_inv` and the diagonal blocks of its
         `Kx_inv_class[c]`) -- used by the parity tests to compare kernels on identical factors."""
+        def injected(Kinv, targets):
+            Kinv = to_tensor(Kinv, self.dtype, self.device).contiguous()
+            n = Kinv.shape[0]
+            return dict(n=n, n_pad=_round_up(n, TILE_N), dense=Kinv, panels={}, wtiles=None,
+                        A=torch.matmul(Kinv.t(), targets).contiguous())
+
         if Ky_inv is not None:
-            self.Ky_inv = to_tensor(Ky_inv, self.dtype, self.device).contiguous()
+            self._obs_blk = injected(Ky_inv, self._Y_device())
         if Kx_inv_blocks is not None:
-            self.Kx_inv_class = [to_tensor(b, self.dtype, self.device).contiguous() for b in Kx_inv_blocks]
+            offs = self.class_pair_offsets()
+            self._dyn_blks = [injected(b, self._Xout[offs[c]:offs[c + 1]]) for c, b in enumerate(Kx_inv_blocks)]
         self._factors_version += 1
         self._packed = None
         self._packed_tf32 = None
 
     # ---- packing for the fused predict kernels ---------------------------------------------------------------
-    def _pack_block(self, Xtrain, log_ls, Kinv, targets, alpha_ld, lin_c2, tri, with_L=True):
+    def _pack_block(self, Xtrain, log_ls, blk, alpha_ld, lin_c2, tri, with_L=True):
         lib = _cabi.lib()
         n, d = Xtrain.shape
-        n_pad = _round_up(n, TILE_N)
+        n_pad = blk["n_pad"]
         cols = [Xtrain / torch.exp(log_ls)]
         if lin_c2 is not None:
             cols.append(Xtrain * lin_c2[:d])
@@ -535,12 +705,8 @@ class GPMDM(torch.nn.Module):
         width = (rec.shape[1] + 1) & ~1  # records are padded to an even number of doubles (16-byte loads)
         coords = torch.zeros(n_pad, width, dtype=self.dtype, device=self.device)
         coords[:n, :rec.shape[1]] = rec
-        Kinv = Kinv.contiguous()
-        L = None
-        if with_L:  # column panels of the quadratic-form matrix (include/gpmdm_b200.h: gpmdm_gp_block)
-            L = torch.empty(int(lib.gpmdm_quadform_bytes(n_pad, int(tri))) // 8, dtype=self.dtype, device=self.device)
-            check(lib.gpmdm_pack_quadform_f64(ptr(Kinv), n, n_pad, int(tri), ptr(L), stream()), "gpmdm_pack_quadform_f64")
-        A = torch.matmul(Kinv.t(), targets).contiguous()
+        L = self._block_panels(blk, tri) if with_L else None  # column panels (include/gpmdm_b200.h: gpmdm_gp_block)
+        A = blk["A"]
         alpha = torch.empty(int(lib.gpmdm_alpha_bytes(n_pad, alpha_ld)) // 8, dtype=self.dtype, device=self.device)
         check(lib.gpmdm_pack_alpha_f64(ptr(A), n, n_pad, A.shape[1], alpha_ld, ptr(alpha), stream()), "gpmdm_pack_alpha_f64")
         return dict(coords=coords, L=L, alpha=alpha, n=n, n_pad=n_pad)
@@ -568,20 +734,21 @@ class GPMDM(torch.nn.Module):
 
         # observation GP: one block over all frames
         ald_y = _round_up(self.D, TILE_N)
-        oblk = self._pack_block(X, self.y_log_lengthscales.detach(), self.Ky_inv, self._Y_device(), ald_y, None, tri,
-                                with_L=with_obs_L)
+        if with_obs_L:
+            self._ensure_fp64_obs_panels(tri)
+        oblk = self._pack_block(X, self.y_log_lengthscales.detach(), self._obs_blk, ald_y, None, tri, with_L=with_obs_L)
         ls_y = torch.exp(self.y_log_lengthscales.detach()).contiguous()
         lam2_y = (torch.exp(self.y_log_lambdas.detach()) ** 2).contiguous()
         obs = model([oblk], self.d, self.D, ald_y, 0, ls_y, None, lam2_y)
         # dynamics GP: one block per class ('full', back_step 1 -- the only mode the filter supports)
-        Xin, Xout = self._Xin, self._Xout
+        Xin = self._Xin
         if self.dyn_back_step == 1:
             c2 = (torch.exp(self.x_log_lin_coeff.detach()) ** 2).contiguous()
             ls_x = torch.exp(self.x_log_lengthscales.detach()).contiguous()
             lam_x = (torch.exp(self.x_log_lambdas.detach()) ** -2).contiguous()
             offs = self.class_pair_offsets()
-            dblks = [self._pack_block(Xin[offs[c]:offs[c + 1]], self.x_log_lengthscales.detach(), self.Kx_inv_class[c],
-                                      Xout[offs[c]:offs[c + 1]], TILE_N, c2, tri) for c in range(self.n_classes)]
+            dblks = [self._pack_block(Xin[offs[c]:offs[c + 1]], self.x_log_lengthscales.detach(), self._dyn_blks[c],
+                                      TILE_N, c2, tri) for c in range(self.n_classes)]
             dyn = model(dblks, self.d, self.d, TILE_N, 1, ls_x, c2, lam_x)
         else:
             dyn = None
@@ -593,21 +760,18 @@ class GPMDM(torch.nn.Module):
     @torch.no_grad()
     def packed_model_tf32(self):
         """Operands of the tf32 observation kernel (include/gpmdm_b200.h: gpmdm_gp_model_tf32): the whitening factor
-        W = U^-T of K_y = U^T U and alpha_y, split into tf32 hi/lo tiles in tensor-core operand order."""
+        W = U^-T = L^-1 of K_y = U^T U = L L^T and alpha_y, split into tf32 hi/lo tiles in tensor-core operand order."""
         if getattr(self, "_packed_tf32", None) is not None and self._packed_tf32["version"] == self._factors_version:
             return self._packed_tf32
         lib = _cabi.lib()
         X = self.X.detach()
         n, d = X.shape
         n_pad = _round_up(n, TILE_N)
-        U, _info = torch.linalg.cholesky_ex(self.get_y_kernel(X, X), upper=True)
-        eye = torch.eye(n, dtype=self.dtype, device=self.device)
-        W = torch.linalg.solve_triangular(U, eye, upper=True).t().contiguous()  # U^-T, lower triangular
-        del U, eye
-        alpha = torch.matmul(self.Ky_inv.t(), self._Y_device()).contiguous()
-        wt = torch.empty(int(lib.gpmdm_tf32_wtiles_bytes(n_pad)) // 4, dtype=torch.float32, device=self.device)
+        if self._obs_blk.get("wtiles") is None:  # not part of the precompute: factor K_y (again) for the W tiles only
+            self._obs_blk["wtiles"] = self._factor_block(self._obs_kernel_matrix, self._Y_device(), False, True)["wtiles"]
+        wt = self._obs_blk["wtiles"]
+        alpha = self._obs_blk["A"]
         at = torch.empty(int(lib.gpmdm_tf32_atiles_bytes(n_pad)) // 4, dtype=torch.float32, device=self.device)
-        check(lib.gpmdm_pack_whitened_tf32(ptr(W), n, n_pad, ptr(wt), stream()), "gpmdm_pack_whitened_tf32")
         check(lib.gpmdm_pack_alpha_tf32(ptr(alpha), n, n_pad, self.D, ptr(at), stream()), "gpmdm_pack_alpha_tf32")
         coords = torch.zeros(n_pad, 8, dtype=torch.float32, device=self.device)
         coords[:n, :d] = (X / torch.exp(self.y_log_lengthscales.detach())).to(torch.float32)
@@ -625,13 +789,19 @@ class GPMDM(torch.nn.Module):
     def _use_lowlat(self, P, low_latency):
         return ((P + TILE_P - 1) // TILE_P <= self.LOWLAT_MAX_TILES) if low_latency is None else bool(low_latency)
 
+    def _stream_scratch(self, name, need, dtype):
+        """Scratch of the `map_x_*` calls, one buffer per (purpose, CUDA stream): calls issued on different streams
+        never share a K* slice, a work-item counter or a partial-sum workspace.  (`GPMDM_PF` owns its own.)"""
+        pool = self.__dict__.setdefault("_scratch_pool", {})
+        key = (name, torch.cuda.current_stream().cuda_stream)
+        buf = pool.get(key)
+        if buf is None or buf.numel() < need:
+            buf = pool[key] = torch.zeros(need, dtype=dtype, device=self.device)
+        return buf
+
     def _lowlat_workspace(self, P, max_n_pad, dout):
-        lib = _cabi.lib()
-        need = int(lib.gpmdm_predict_lowlat_workspace_bytes(P, max_n_pad, dout)) // 8 + 1
-        ws = getattr(self, "_lowlat_ws", None)
-        if ws is None or ws.numel() < need:
-            self._lowlat_ws = ws = torch.empty(need, dtype=torch.float64, device=self.device)
-        return ws
+        need = int(_cabi.lib().gpmdm_predict_lowlat_workspace_bytes(P, max_n_pad, dout)) // 8 + 1
+        return self._stream_scratch("lowlat", need, torch.float64)
 
     # ---- prediction (gpmdm.py:923-963, 1032-1068) ----------------------------------------------------------
     KSTAR_CACHE_MIN_TILES = 4  # column tiles of L from which caching K* pays (a K* entry is reused nq/2 times)
@@ -644,15 +814,10 @@ class GPMDM(torch.nn.Module):
 
     def _kstar_workspace(self, n_pad):
         need = int(_cabi.lib().gpmdm_pf_observe_kstar_workspace_bytes(n_pad)) // 8
-        ws = getattr(self, "_ws_kstar", None)
-        if ws is None or ws.numel() < need:
-            self._ws_kstar = ws = torch.empty(need, dtype=self.dtype, device=self.device)
-        return ws
+        return self._stream_scratch("kstar", need, self.dtype)
 
     def _scratch_counter(self):
-        if getattr(self, "_counter", None) is None:
-            self._counter = torch.zeros(4, dtype=torch.int32, device=self.device)
-        return self._counter
+        return self._stream_scratch("counter", 4, torch.int32)
 
     @torch.no_grad()
     def map_x_to_y(self, Xstar, flg_noise=False, precision="fp64", low_latency=None, kstar_cache=None):
@@ -745,10 +910,9 @@ class GPMDM(torch.nn.Module):
         blocks = []
         for c in range(self.n_classes):
             Xc = self._Xin[offs[c]:offs[c + 1]].contiguous()
-            Kc = _KernelBuild.apply(Xc, self.x_log_lengthscales, self.x_log_sigma_n, self.x_log_lin_coeff,
-                                    self.sigma_n_num_X, None, True)  # block of K_x o M: no 1e-6 jitter (gpmdm.py:1292)
-            blocks.append(self._pack_block(Xc, self.x_log_lengthscales.detach(), self._inverse_via_upper_cholesky(Kc),
-                                           self._Xout[offs[c]:offs[c + 1]], TILE_N, c2, True))
+            # block of K_x o M: no 1e-6 jitter (gpmdm.py:1292)
+            blk = self._factor_block(lambda: self._dyn_kernel_matrix(c, jitter=0.0), self._Xout[offs[c]:offs[c + 1]].contiguous())
+            blocks.append(self._pack_block(Xc, self.x_log_lengthscales.detach(), blk, TILE_N, c2, True))
         table = torch.tensor([[b["coords"].data_ptr(), b["L"].data_ptr(), b["alpha"].data_ptr(), b["n"], b["n_pad"]]
                               for b in blocks], dtype=torch.int64, device=self.device)
         model = GpModel(blocks=table.data_ptr(), n_blocks=len(blocks), d=self.d, dout=self.d, alpha_ld=TILE_N, kind=1,

@@ -98,7 +98,9 @@ class GPMDM_PF:
         self._packed_tf32 = gpmdm.packed_model_tf32() if precision == "tf32" else None
         c32 = float(0.5 * self._gpmdm.D * _LOG_2PI)  # fp32 product, as gpmdm_pf.py:191
         self._ll_const = self._packed["ll_const_terms"] - c32
-        self._lowlat = gpmdm._use_lowlat(self._hi - self._lo, low_latency)
+        # the mode is chosen from the TOTAL particle count: the two decompositions sum over k in different orders, so a
+        # choice that depended on this rank's share would make a G-GPU run differ from the 1-GPU run
+        self._lowlat = gpmdm._use_lowlat(self._num_particles, low_latency)
         self._kstar_cache = (precision == "fp64" and not self._lowlat
                              and gpmdm._use_kstar_cache(self._packed["obs_n_pad"], kstar_cache))
         self._native_step = bool(native_step) and precision == "fp64"
@@ -126,7 +128,11 @@ class GPMDM_PF:
             need = max(int(self._lib.gpmdm_predict_lowlat_workspace_bytes(Pl, self._packed["obs_n_pad"], self.observation_dim)),
                        int(self._lib.gpmdm_predict_lowlat_workspace_bytes(Pl, self._packed["dyn_max_n_pad"], d)))
             self._ws_lowlat = torch.empty(need // 8 + 1, dtype=torch.float64, device=dev)
-        self._ws_kstar = self._gpmdm._kstar_workspace(self._packed["obs_n_pad"]) if self._kstar_cache else None
+        # scratch is owned by the filter instance (two filters on one model may run on different streams)
+        self._ws_kstar = None
+        if self._kstar_cache:
+            need = int(self._lib.gpmdm_pf_observe_kstar_workspace_bytes(self._packed["obs_n_pad"])) // 8
+            self._ws_kstar = torch.empty(need, dtype=f64, device=dev)
         if self._native_step:  # struct gpmdm_pf_step_args: the per-trial constants; per-step fields are set in _update
             a = self._step_args = _cabi.PfStepArgs()
             a.dyn, a.obs = ctypes.pointer(self._packed["dyn"]), ctypes.pointer(self._packed["obs"])
@@ -322,6 +328,15 @@ class GPMDM_PF:
 
     def reset(self):
         self._init_particles()
+        self._counter[2:].zero_()
+
+    def variance_faults(self):
+        """(dynamics, observation): particle updates since construction / reset() whose predictive variance was not a
+        positive finite number.  The reference silently produces NaN states / log-likelihoods for them (sqrt at
+        gpmdm_pf.py:168, log at :189) and so does this filter; the kernels' epilogues count them in a device word.
+        Synchronises the stream."""
+        dyn, obs = self._counter[2:4].tolist()
+        return int(dyn), int(obs)
 
     # ---- stage outputs of the last step (for tests / diagnostics) ------------------------------------------------
     @property

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define GPMDM_ABI_VERSION 2
+#define GPMDM_ABI_VERSION 3
 
 #define GPMDM_E_INVALID (-1)     /* bad size / null pointer / unsupported dimension            */
 #define GPMDM_E_UNSUPPORTED (-2) /* valid request outside this build's limits (d > 8, ...)      */
@@ -121,8 +121,12 @@ int gpmdm_pf_bucket_by_class(const int64_t* classes, int64_t P, int32_t C, int32
  *     x_new = eps * sqrt(var) + mean                                   (mul, then add -- :168)
  * perm/tiles/n_tiles from gpmdm_pf_bucket_by_class.  eps [P, d] is indexed by particle.
  * mean_out / var_out ([P, d], may be NULL) expose the GP prediction (map_x_dynamics_for_class).
- * x_new may be NULL when only the prediction is wanted.  tile_counter: device int32 scratch [4] (tile hand-out
- * counter and the round-synchronisation counter of the predict kernels; zeroed by the call). */
+ * x_new may be NULL when only the prediction is wanted.
+ * tile_counter: device int32 [4], shared by all predict entry points.  [0], [1]: tile hand-out and round-synchronisation
+ * counters, zeroed by every call.  [2], [3]: STATUS words, only ever incremented by the library (the caller zeroes them
+ * when it wants a fresh count): [2] += particles whose dynamics predictive variance was not a positive finite number,
+ * [3] += the same for the observation variance.  The results for such particles are what the reference produces --
+ * NaN from sqrt / log of the variance (gpmdm_pf.py:168, :189) -- the words make the event observable. */
 int gpmdm_pf_propagate_f64(const gpmdm_gp_model* dyn, const double* x_prev, const int32_t* perm,
                            const int32_t* tiles, const int32_t* n_tiles, int64_t P, const double* eps,
                            double* x_new, double* mean_out, double* var_out, int32_t* tile_counter,
@@ -312,6 +316,9 @@ int64_t gpmdm_kernel_grad_workspace_bytes(int64_t n, int32_t d);
 /* ---- measurement helper: sustained fp64 mma.sync (DMMA m8n8k4) rate of this device, TFLOP/s, the
  * denominator of the contraction roofline (bench.py).  Synchronous. */
 int gpmdm_probe_dmma_tflops(int32_t iters, double* tflops_host);
+/* The same for the tf32 variant: sustained tcgen05.mma kind::tf32 (M = 128, N = 256, K = 8, operands resident in shared
+ * memory, pseudo-random values) rate of this device, TFLOP/s.  Synchronous. */
+int gpmdm_probe_tf32_tflops(int32_t iters, double* tflops_host);
 
 #ifdef __cplusplus
 }

@@ -213,6 +213,31 @@ def precompute_factors(m: ModelSpec, Ky_inv: Optional[torch.Tensor] = None,
                    alpha_x=alpha_x, Xin=Xin, Xout=Xout)
 
 
+def precompute_factors_on(m: ModelSpec, device) -> Factors:
+    """`precompute_factors` with the O(N^3) linear algebra (the reference recipe gpmdm.py:1287-1289, 1301-1305:
+    upper Cholesky, triangular inverse, U^-1 U^-T) evaluated by plain torch on `device`, returned on the CPU.
+    For N = 20 000 the CPU recipe takes minutes; tests and bench.py use this to SET UP the oracle at the benchmark
+    sizes (never inside a timed region).  The cross-kernel and every prediction stay on the CPU."""
+    def inv(K):
+        U, _ = torch.linalg.cholesky_ex(K, upper=True)
+        Ui = torch.linalg.solve_triangular(U, torch.eye(K.shape[0], dtype=K.dtype, device=K.device), upper=True)
+        del U
+        return Ui @ Ui.t()
+
+    X = m.X.to(device)
+    Ky = torch.exp(-weighted_distances(X, X, m.y_log_lengthscales.to(device)))
+    Ky.diagonal().add_(float(torch.exp(m.y_log_sigma_n) ** 2 + m.sigma_n_num_Y ** 2))
+    Ky_inv = inv(Ky).cpu()
+    del Ky
+    Xin, _ = xin_xout(m)
+    blocks = []
+    for a, b in m.class_pair_ranges():
+        Kc = x_kernel(m, Xin[a:b], Xin[a:b]).to(device)
+        Kc.diagonal().add_(1e-6)
+        blocks.append(inv(Kc).cpu())
+    return precompute_factors(m, Ky_inv=Ky_inv, Kx_inv_blocks=blocks)
+
+
 # ------------------------------------------------------------------------------------------------
 # GP prediction (gpmdm.py:923-963, 1032-1068)
 # ------------------------------------------------------------------------------------------------

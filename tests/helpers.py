@@ -57,7 +57,7 @@ def scaled_err(a, b, scale):
 
 
 # ---- product-side helpers (GPU tests) -----------------------------------------------------------------
-def product_model_from_spec(spec, Ky_inv=None, Kx_inv_blocks=None):
+def product_model_from_spec(spec, Ky_inv=None, Kx_inv_blocks=None, own_factors=True):
     """Build the product `GPMDM` (CUDA) holding exactly the latents / hyper-parameters of an oracle
     ModelSpec, optionally with injected inverses (the reference's own, for stage-wise parity)."""
     from gpmdm_b200 import GPMDM
@@ -80,7 +80,12 @@ def product_model_from_spec(spec, Ky_inv=None, Kx_inv_blocks=None):
             getattr(m, k).data.copy_(getattr(spec, k).to(m.device))
     m._precompute_class_matrices()
     m.X = torch.nn.Parameter(spec.X.to(m.device).clone(), requires_grad=False)
-    m._precompute_kernel_inverses()
+    if own_factors:
+        m._precompute_kernel_inverses()
+    else:  # large N: skip the product's own factorisation, both inverses are injected
+        assert Ky_inv is not None and Kx_inv_blocks is not None
+        m._Xin, m._Xout, _ = m.get_Xin_Xout_matrices(m.X.detach())
+        m._Xin, m._Xout = m._Xin.contiguous(), m._Xout.contiguous()
     if Ky_inv is not None or Kx_inv_blocks is not None:
         m.set_inverses(Ky_inv, Kx_inv_blocks)
     return m

@@ -57,3 +57,60 @@ def test_spd_inverse_from_cholesky_block_recursion(n, monkeypatch):
     assert float((Kinv - ref).abs().max()) < 1e-13 * float(ref.abs().max())
     assert torch.equal(Kinv, Kinv.t())
     assert float((Kinv @ K - torch.eye(n, dtype=F64)).abs().max()) < 1e-10
+
+
+# ---- factor precompute without dense intermediates (gpmdm.py:1284-1305 -> GPMDM._factor_block) -------------------------
+@pytest.mark.parametrize("n", [1, 7, 256, 300, 700])
+def test_tril_inverse_in_place(n, monkeypatch):
+    monkeypatch.setattr(G, "_TRINV_LEAF", 64)
+    gen = torch.Generator().manual_seed(n)
+    L = torch.linalg.cholesky(spd(n, gen))
+    out = G.tril_inverse_inplace(L.clone())
+    ref = torch.linalg.solve_triangular(L, torch.eye(n, dtype=F64), upper=False)
+    assert float((out - ref).abs().max()) < 1e-13 * float(ref.abs().max())
+    assert float(torch.triu(out, 1).abs().max()) == 0.0 if n > 1 else True
+
+
+@pytest.mark.parametrize("tri", [True, False])
+@pytest.mark.parametrize("n", [5, 256, 300, 777])
+def test_quadform_panels_straight_from_the_triangular_inverse(n, tri, monkeypatch):
+    """Panels built by one GEMM per column panel from L^-1 hold exactly the layout gpmdm_pack_quadform_f64 writes from a
+    dense inverse (include/gpmdm_b200.h: gpmdm_gp_block), and k^T Q k == k^T K^-1 k."""
+    monkeypatch.setattr(G, "_TRINV_LEAF", 64)
+    gen = torch.Generator().manual_seed(n + 1)
+    K = spd(n, gen) / n
+    Kinv = torch.linalg.inv(K)
+    Linv = G.tril_inverse_inplace(torch.linalg.cholesky(K))
+    n_pad = (n + 255) // 256 * 256
+    panels = G.quadform_panels_from_tril_inverse(Linv, n_pad, tri)
+    assert panels.numel() == G.quadform_panel_elems(n_pad, tri)
+    # the layout, from a numpy-style construction of the same panels out of the dense inverse
+    Q = Kinv.clone() if not tri else 2 * torch.tril(Kinv, -1) + torch.diag(torch.diagonal(Kinv))
+    Qp = torch.zeros(n_pad, n_pad, dtype=F64)
+    Qp[:n, :n] = Q
+    want = torch.cat([torch.cat([Qp[(256 * t if tri else 0):, 256 * t:256 * t + 256],
+                                 torch.zeros(n_pad - (256 * t if tri else 0), 4, dtype=F64)], 1)
+                      for t in range(n_pad // 256)], 0).reshape(-1)
+    assert float((panels - want).abs().max()) < 1e-12 * float(Kinv.abs().max())
+    assert bool((panels[want == 0] == 0).all())  # padding, pitch columns and the upper part of diagonal blocks
+    back = G.dense_from_quadform_panels(panels, n, n_pad, tri)
+    assert float((back - Kinv).abs().max()) < 1e-12 * float(Kinv.abs().max())
+    k = torch.rand(n, dtype=F64, generator=gen)
+    assert abs(float(k @ Q @ k) - float(k @ Kinv @ k)) < 1e-10 * abs(float(k @ Kinv @ k))
+
+
+def test_factor_recipe_reproduces_the_reference_inverse_on_the_goldens():
+    """K_y^-1 from (lower Cholesky, in-place triangular inverse, panel GEMMs) against the `Ky_inv` the unmodified reference
+    computed for the golden models (gpmdm.py:1287-1289: upper Cholesky, torch.inverse, U^-1 U^-T): 1e-9 of max |K^-1|."""
+    from oracle import gpmdm_oracle as orc
+    from tests.helpers import GOLDEN_CASES, Golden, t64
+
+    for name in GOLDEN_CASES:
+        g = Golden(name)
+        K = orc.y_kernel(g.spec, g.spec.X, g.spec.X)
+        Linv = G.tril_inverse_inplace(torch.linalg.cholesky(K))
+        n = K.shape[0]
+        n_pad = (n + 255) // 256 * 256
+        own = G.dense_from_quadform_panels(G.quadform_panels_from_tril_inverse(Linv, n_pad, True), n, n_pad, True)
+        ref = t64(g.z["Ky_inv"])
+        assert float((own - ref).abs().max()) < 1e-9 * float(ref.abs().max()), name
