@@ -214,6 +214,14 @@ def parity_block(pf, model, o, last, T):
     mscale = torch.clamp(tr["mu"].abs().max(dim=1, keepdim=True).values, min=1e-3)
     ok = tr["v"] > 1e-3
     ll_rel = (ll - tr["ll"]).abs() / tr["ll"].abs()
+    # ll = -S/(2v) - D log v + const: an error dv in the variance moves it by (S/(2 v^2) + D/v) dv.  `ll_err_vs_bound` <= 1
+    # means every ll difference is explained by variances matched to 1e-9 of the prior plus 1e-9 of the terms' magnitude.
+    lam2 = torch.exp(spec.y_log_lambdas) ** 2
+    S = (lam2.unsqueeze(0) * (torch.as_tensor(np.asarray(last["z"]), dtype=f64).unsqueeze(0) - tr["mu"]) ** 2).sum(1)
+    vo = tr["v"]
+    terms = S / (2 * vo) + D * vo.log().abs() + abs(pf._ll_const)
+    ll_bound = (S / (2 * vo * vo) + D / vo) * 1e-9 + 1e-9 * terms
+    ll_vs_bound = (ll - tr["ll"]).abs() / ll_bound
     # dynamics GP (fused kernel) per class on the oracle's previous states
     lam_x = torch.exp(spec.x_log_lambdas) ** -2
     dm = dv = 0.0
@@ -245,9 +253,12 @@ def parity_block(pf, model, o, last, T):
         "sample_particles": n, "observe_entry_point": kern,
         "obs_mean_err_of_row_scale_max": float(((mu - tr["mu"]).abs() / mscale).max()),
         "obs_var_err_of_prior_max": float((v - tr["v"]).abs().max()),
-        "ll_rel_err_max": float(ll_rel[ok].max()) if bool(ok.any()) else None,
-        "ll_rel_err_median": float(ll_rel[ok].median()) if bool(ok.any()) else None,
-        "ll_compared": int(ok.sum()), "v_min": float(tr["v"].min()),
+        "ll_rel_err_max_where_v_gt_1e-3": float(ll_rel[ok].max()) if bool(ok.any()) else None,
+        "ll_rel_err_median": float(ll_rel.median()),
+        "ll_compared": int(ok.sum()), "v_min": float(tr["v"].min()), "v_median": float(tr["v"].median()),
+        "ll_err_vs_bound_max": float(ll_vs_bound.max()),
+        "ll_err_vs_bound": "|ll - ll_oracle| / ((S/(2v^2) + D/v) 1e-9 + 1e-9 (S/(2v) + D|log v| + |const|)) over ALL sample "
+                           "particles: <= 1 means the difference is what a variance matched to 1e-9 of the prior allows",
         "dyn_mean_err_of_row_scale_max": dm, "dyn_var_err_of_prior_max": dv,
         "classes_equal": bool(torch.equal(c_new.cpu(), tr["c_new"])),
         "log_weights_equal": bool(torch.equal(lw.cpu(), tr["lw"])),

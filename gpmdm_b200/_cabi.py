@@ -71,6 +71,8 @@ _SIGNATURES = {
                                                      _ptr, _ptr, _i64, _ptr, _ptr, _ptr]),
     "gpmdm_pf_step_local_f64": (ctypes.c_int, [ctypes.POINTER(PfStepArgs), _ptr]),
     "gpmdm_pf_step_global_f64": (ctypes.c_int, [ctypes.POINTER(PfStepArgs), _ptr]),
+    "gpmdm_pf_small_max_particles": (_i32, []),
+    "gpmdm_pf_step_small_f64": (ctypes.c_int, [ctypes.POINTER(PfStepArgs), _ptr, _ptr, _ptr]),
     "gpmdm_pf_normalize_f64": (ctypes.c_int, [_ptr, _i64, _ptr, _ptr, _ptr, _ptr, _ptr]),
     "gpmdm_pf_cdf_f64": (ctypes.c_int, [_ptr, _i64, _i32, _ptr, _ptr, _ptr]),
     "gpmdm_pf_resample_f64": (ctypes.c_int, [_ptr, _i64, _ptr, _i64, _ptr, _ptr, _i32, _ptr, _ptr, _ptr, _ptr]),

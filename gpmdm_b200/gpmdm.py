@@ -584,6 +584,8 @@ class GPMDM(torch.nn.Module):
         n_pad = _round_up(n, TILE_N)
         L, _info = torch.linalg.cholesky_ex(K, upper=False)  # gpmdm.py:1287: info is ignored by the reference as well
         del K
+        if not L.is_contiguous():  # torch.linalg hands back column-major storage; the packers read row-major
+            L = L.contiguous()
         Linv = tril_inverse_inplace(L)
         del L
         blk = dict(n=n, n_pad=n_pad, dense=None, panels={}, wtiles=None,

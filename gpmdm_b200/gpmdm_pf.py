@@ -49,7 +49,7 @@ class GPMDM_PF:
                  seed: int = 0, resampling: str = "multinomial", cdf_order: str = "sequential",
                  tri: bool = True, precision: str = "fp64", low_latency: Optional[bool] = None,
                  kstar_cache: Optional[bool] = None, native_step: bool = True, init_indices: Optional[Sequence] = None, process_group=None,
-                 distributed: Optional[bool] = None):
+                 distributed: Optional[bool] = None, cuda_graph: Optional[bool] = None):
         """
         gpmdm, markov_switching_model [C, C], num_particles: as the reference (:47-50).
         seed            Philox key for device-side draws (the reference has no seed argument)
@@ -67,6 +67,9 @@ class GPMDM_PF:
         native_step     issue the stage launches of a step from native code (two C-ABI calls per step instead of twelve;
                         matters when a step is launch-latency bound, i.e. with few particles); same kernels, same results
         init_indices    optional per-class index tensors replacing torch.randint in _init_particles (:113)
+        cuda_graph      small clouds (P <= 4096, one GPU, low-latency mode): the step is six kernels (csrc/pf_small.cu) with
+                        no per-step host parameter; None / True = capture them into a CUDA graph after two warm-up steps
+                        and replay it per frame, False = launch them directly.  Same results either way
         """
         self._lib = _cabi.lib()
         self._gpmdm = gpmdm
@@ -104,6 +107,10 @@ class GPMDM_PF:
         self._kstar_cache = (precision == "fp64" and not self._lowlat
                              and gpmdm._use_kstar_cache(self._packed["obs_n_pad"], kstar_cache))
         self._native_step = bool(native_step) and precision == "fp64"
+        # small-cloud step: draws+transition+bucketing and normalise+cdf+resample+summaries as two single-CTA kernels
+        self._small = (self._native_step and self._lowlat and self._world == 1
+                       and self._num_particles <= int(self._lib.gpmdm_pf_small_max_particles()))
+        self._use_graph = self._small and (cuda_graph is None or bool(cuda_graph))
         self._alloc()
         self._init_particles(init_indices)
 
@@ -122,6 +129,18 @@ class GPMDM_PF:
         self._v_buf = e(Pl)
         self._summary = e(C + d + 1)
         self._summary_step = -1
+        if self._small:
+            # ping-pong sets: the graph of parity p reads (states, classes)[p] and writes ll / lw / w [p] and
+            # (states, classes)[1 - p]; the arrays of the previous step stay intact for one more step
+            self._S, self._Cl = [e(P, d), e(P, d)], [e(P, dt=torch.int64), e(P, dt=torch.int64)]
+            self._LL, self._LW, self._W = [e(P), e(P)], [e(P), e(P)], [e(P), e(P)]
+            self._par, self._graphs, self._small_steps = 0, [None, None], 0
+            self._step_dev = torch.zeros(1, dtype=torch.int64, device=dev)
+            self._step_dev_host = 0
+            self._z_buf = e(self.observation_dim)
+            self._z_pin = [torch.empty(self.observation_dim, dtype=f64).pin_memory() for _ in range(4)]
+            self._z_ev = [None] * 4
+            self._z_slot = 0
         ws = int(self._lib.gpmdm_workspace_bytes(P, C))
         self._ws = torch.empty(ws // 8 + 1, dtype=torch.float64, device=dev)
         if self._lowlat:
@@ -180,8 +199,27 @@ class GPMDM_PF:
     def update(self, z, draws=None):
         """Update the particle filter with a new observation z [D] (numpy / sequence / tensor).
         draws: optional (E [P,C] Exp(1), eps [P,d] N(0,1), u [P] U(0,1)) raw draws for ALL particles."""
+        if self._small and not (isinstance(z, torch.Tensor) and z.is_cuda):
+            return self._update(self._stage_z(z), draws)
         z = torch.as_tensor(np.asarray(z) if not isinstance(z, torch.Tensor) else z).to(device=self.device, dtype=self.dtype)
         self._update(z.contiguous(), draws)
+
+    def _stage_z(self, z):
+        """Host observation -> the persistent device buffer the step reads, through a small ring of pinned buffers (a slot
+        is reused only after the copy that read it has completed)."""
+        i = self._z_slot
+        self._z_slot = (i + 1) % len(self._z_pin)
+        if self._z_ev[i] is not None:
+            self._z_ev[i].synchronize()
+        src = z if isinstance(z, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(z))
+        if src.numel() != self.observation_dim:
+            raise ValueError("z must have D = %d entries" % self.observation_dim)
+        self._z_pin[i].copy_(src.reshape(-1))
+        self._z_buf.copy_(self._z_pin[i], non_blocking=True)
+        if self._z_ev[i] is None:
+            self._z_ev[i] = torch.cuda.Event()
+        self._z_ev[i].record()
+        return self._z_buf
 
     def _update(self, z, draws=None):
         lib, st = self._lib, stream()
@@ -209,6 +247,8 @@ class GPMDM_PF:
         x_prev = self._particle_states[lo:hi]
         c_prev = self._particle_classes[lo:hi]
         x_new_l, c_new_l, ll_l = self._x_new[lo:hi], self._c_new[lo:hi], self._ll_all[lo:hi]
+        if native and self._small:
+            return self._update_small(z, draws is None, E, eps, u)
         if native:
             return self._update_native(z, draws is None, E, eps, u, x_prev, c_prev)
         # -- class transition, bucketing, dynamics draw, observation likelihood (local particles)
@@ -289,9 +329,50 @@ class GPMDM_PF:
         self._log_weights, self._weights = lw_new, w_new
         self._step += 1
 
+    # ---- small clouds: six kernels per step, replayed from a CUDA graph ------------------------------------------------
+    def _issue_small(self, par, generate, E, eps, u):
+        a = self._step_args
+        a.generate_draws, a.step, a.z = int(generate), self._step, ptr(self._z_buf)
+        a.x_prev, a.c_prev, a.E, a.eps, a.u = ptr(self._S[par]), ptr(self._Cl[par]), ptr(E), ptr(eps), ptr(u)
+        a.ll, a.lw, a.w = ptr(self._LL[par]), ptr(self._LW[par]), ptr(self._W[par])
+        a.x_out, a.c_out = ptr(self._S[1 - par]), ptr(self._Cl[1 - par])
+        check(self._lib.gpmdm_pf_step_small_f64(ctypes.byref(a), ptr(self._step_dev), ptr(self._summary), stream()),
+              "gpmdm_pf_step_small_f64")
+
+    def _update_small(self, z, generate, E, eps, u):
+        par = self._par
+        # the step reads the particle cloud from its own buffers: adopt a cloud that was rebound from outside
+        if self._particle_states.data_ptr() != self._S[par].data_ptr():
+            self._S[par].copy_(self._particle_states)
+        if self._particle_classes.data_ptr() != self._Cl[par].data_ptr():
+            self._Cl[par].copy_(self._particle_classes)
+        if z.data_ptr() != self._z_buf.data_ptr():
+            self._z_buf.copy_(z)
+        if self._step_dev_host != self._step:  # keeps the device step key equal to the host's (reset(), injected draws)
+            self._step_dev.fill_(self._step)
+        if generate and self._use_graph and self._small_steps >= 2:
+            if self._graphs[par] is None:  # every kernel has run at least once (function attributes are set): capture
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._issue_small(par, True, self._E, self._eps, self._u)
+                self._graphs[par] = g
+            self._graphs[par].replay()
+        else:
+            self._issue_small(par, generate, E, eps, u)
+        self._small_steps += 1
+        self._step += 1
+        self._step_dev_host = self._step
+        self._particle_states, self._particle_classes = self._S[1 - par], self._Cl[1 - par]
+        self._x_new_small = None
+        self._log_likelihoods, self._log_weights, self._weights = self._LL[par], self._LW[par], self._W[par]
+        self._summary_step = self._step  # the post kernel has already written the summaries of this state
+        self._par = 1 - par
+
     @property
     def launches_per_step(self) -> int:
         """Kernels of libgpmdm_sm100a.so launched by one update() + one query (device-draw mode)."""
+        if self._small:
+            return 6  # pre, propagate (items + finalise), observe (items + finalise), post -- the query is a read
         draws, transition, bucket, propagate, normalize, resample, summaries = 2, 1, 3, 1, 5, 1, 4
         observe = 2 if (self._precision == "tf32" or self._lowlat) else 1
         propagate = 2 if self._lowlat else 1
@@ -320,7 +401,8 @@ class GPMDM_PF:
         return self._summaries()[:self.num_classes].clone()
 
     def get_most_likely_class(self) -> int:
-        return torch.argmax(self.class_probabilities()).item()
+        # one device-to-host read of the class posteriors; argmax on the host (first maximum, as torch.argmax)
+        return int(torch.argmax(self._summaries()[:self.num_classes].cpu()))
 
     def current_state_mean(self):
         C = self.num_classes

@@ -296,6 +296,18 @@ typedef struct gpmdm_pf_step_args {
 int gpmdm_pf_step_local_f64(const gpmdm_pf_step_args* a, void* stream);
 int gpmdm_pf_step_global_f64(const gpmdm_pf_step_args* a, void* stream);
 
+/* The whole step for a SMALL cloud on one rank (1 <= P <= gpmdm_pf_small_max_particles() = 4096, lo = 0, n_local = P,
+ * predict_mode = 2) -- the reference's own operating point is 100 particles (notebooks/test_gpmdm_pf.ipynb cell 3), where a
+ * step is bound by launch latency: draws + transition + bucketing run as ONE single-CTA kernel, normalise + cdf +
+ * resampling + the class / state summaries as another, around the two low-latency predict calls: 6 kernels instead of ~28.
+ * Same device functions and the same fixed reduction order as the staged entry points: bit-identical results.
+ *   step_dev  device uint64 (may be NULL): when given, the Philox step key is read from it instead of a->step and it is
+ *             advanced by one at the end of the step, so the launch sequence has no per-step host parameter and can be
+ *             captured once into a CUDA graph and replayed per frame (gpmdm_b200/gpmdm_pf.py does).
+ *   summary   device [C + d + 1] (may be NULL): the outputs of gpmdm_pf_summaries_f64 for the post-step state. */
+int32_t gpmdm_pf_small_max_particles(void);
+int gpmdm_pf_step_small_f64(const gpmdm_pf_step_args* a, uint64_t* step_dev, double* summary, void* stream);
+
 /* ---- training-side kernel matrices (gpmdm.py:381-548, 311-340, 550-628) ------------------------
  * K = exp(-|(x_i-x_j)/l|^2) [+ [x_i,1]diag(c^2)[x_j,1]^T if kind 1] [+ noise2 on the diagonal],
  * multiplied by the class-block mask given as row offsets (class_offsets [n_classes+1], device int64;
