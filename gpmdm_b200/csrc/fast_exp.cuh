@@ -56,7 +56,9 @@ __host__ __device__ __forceinline__ double exp_from_bits(int64_t b) {
 __host__ __device__ __forceinline__ double exp_reduce(double x, int& n) {
     // clamp x >= -800 with integer compares: for negative doubles a larger high word means a smaller value
     const uint32_t hi = (uint32_t)(exp_bits(x) >> 32);
-    if (hi > 0xC0890000u) x = -800.0;
+    // (up to and including -inf = 0xFFF00000:00000000; NaNs lie above it and must propagate, as they do through the
+    // reference's torch.exp: a NaN particle state gives NaN predictions, gpmdm_pf.py:168 -> :189)
+    if (hi > 0xC0890000u && hi <= 0xFFF00000u) x = -800.0;
     const double tn = fma(x, ExpConst::INV, ExpConst::MAGIC);
     n = (int)(uint32_t)exp_bits(tn);
     const double nf = tn - ExpConst::MAGIC;

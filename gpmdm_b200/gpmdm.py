@@ -33,6 +33,9 @@ from . import _cabi
 from ._cabi import TILE_N, TILE_P, GpModel, GpModelTf32, check, ptr, stream
 
 
+F64 = torch.float64  # working precision of every kernel buffer and factor (the public dtype may be float32)
+
+
 def to_tensor(input_array, dtype, device):
     if isinstance(input_array, torch.Tensor):
         return input_array.to(dtype=dtype, device=device)
@@ -59,14 +62,16 @@ class _KernelBuild(torch.autograd.Function):
     @staticmethod
     def forward(ctx, X, log_ls, log_sigma_n, log_lin_coeff, sigma_n_num, class_offsets, flg_noise):
         lib = _cabi.lib()
-        X = X.contiguous()
+        # fp32 models: parameters are up-cast here, the kernel matrix and the loss are fp64, gradients go back as fp32
+        ctx.in_dtypes = (X.dtype, log_ls.dtype, log_sigma_n.dtype, None if log_lin_coeff is None else log_lin_coeff.dtype)
+        X = X.to(F64).contiguous()
         n, d = X.shape
         kind = 0 if log_lin_coeff is None else 1
-        ls = torch.exp(log_ls).contiguous()
-        c2 = (torch.exp(log_lin_coeff) ** 2).contiguous() if kind else None
-        sigma2 = float(torch.exp(log_sigma_n.detach()).reshape(-1)[0] ** 2) if flg_noise else 0.0
+        ls = torch.exp(log_ls.to(F64)).contiguous()
+        c2 = (torch.exp(log_lin_coeff.to(F64)) ** 2).contiguous() if kind else None
+        sigma2 = float(torch.exp(log_sigma_n.detach().to(F64)).reshape(-1)[0] ** 2) if flg_noise else 0.0
         noise2 = sigma2 + (float(sigma_n_num) ** 2 if flg_noise else 0.0)
-        K = torch.empty(n, n, dtype=X.dtype, device=X.device)
+        K = torch.empty(n, n, dtype=F64, device=X.device)
         ncls = 0 if class_offsets is None else class_offsets.numel() - 1
         check(lib.gpmdm_kernel_build_f64(ptr(X), n, d, kind, ptr(ls), ptr(c2), noise2, ptr(class_offsets), ncls,
                                          ptr(K), stream()), "gpmdm_kernel_build_f64")
@@ -82,14 +87,15 @@ class _KernelBuild(torch.autograd.Function):
         n, d = X.shape
         G = G.contiguous()
         gX = torch.empty_like(X)
-        g_ls = torch.empty(d, dtype=X.dtype, device=X.device)
-        g_sig = torch.empty((), dtype=X.dtype, device=X.device)
-        g_c = torch.empty(d + 1, dtype=X.dtype, device=X.device) if kind else None
+        g_ls = torch.empty(d, dtype=F64, device=X.device)
+        g_sig = torch.empty((), dtype=F64, device=X.device)
+        g_c = torch.empty(d + 1, dtype=F64, device=X.device) if kind else None
         ws = torch.empty(lib.gpmdm_kernel_grad_workspace_bytes(n, d) // 8 + 1, dtype=torch.float64, device=X.device)
         check(lib.gpmdm_kernel_grad_f64(ptr(X), ptr(G), n, d, kind, ptr(ls), ptr(c2) if kind else None, sigma2,
                                         ptr(offs) if ncls else None, ncls, ptr(gX), ptr(g_ls), ptr(g_sig),
                                         ptr(g_c) if kind else None, ptr(ws), stream()), "gpmdm_kernel_grad_f64")
-        return gX, g_ls, g_sig.reshape(sig_shape), g_c, None, None, None
+        tx, tl, ts, tc = ctx.in_dtypes
+        return (gX.to(tx), g_ls.to(tl), g_sig.reshape(sig_shape).to(ts), g_c.to(tc) if kind else None, None, None, None)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -286,8 +292,12 @@ class GPMDM(torch.nn.Module):
                  sigma_n_num_Y=0., sigma_n_num_X=0.,
                  dtype=torch.float64, device=None):
         super().__init__()
-        if dtype != torch.float64:
-            raise ValueError("this build implements the fp64 (exact) path only")
+        if dtype not in (torch.float64, torch.float32):
+            raise ValueError("dtype must be torch.float64 or torch.float32")
+        # `dtype` is the PUBLIC dtype, as in the reference: parameters, latents and returned predictions.  All kernel
+        # arithmetic and every factor is fp64 whatever it is (the fp32 reference inverts K in fp32; here fp32 parameters
+        # are up-cast first).  A float32 model makes the particle filter default to the tf32 tensor-core variant of the
+        # observation GP (precision="tf32": north_star's 1e-4 variant).
         self.dtype = dtype
         self.device = torch.device(device) if device is not None else _default_device()
         if self.device.type != "cuda":
@@ -296,7 +306,7 @@ class GPMDM(torch.nn.Module):
         self.dyn_target, self.dyn_back_step = dyn_target, dyn_back_step
 
         def par(init, flag):
-            return torch.nn.Parameter(torch.log(to_tensor(init, self.dtype, self.device)), requires_grad=flag)
+            return torch.nn.Parameter(torch.log(to_tensor(init, F64, self.device)).to(self.dtype), requires_grad=flag)
 
         self.y_log_lengthscales = par(y_lengthscales_init, flg_train_y_lengthscales)
         self.y_log_lambdas = par(y_lambdas_init, flg_train_y_lambdas)
@@ -311,6 +321,10 @@ class GPMDM(torch.nn.Module):
         self.meanY = 0
         self._Y_dev = None
         self._factors_version = 0
+
+    def _d(self, name):
+        """A parameter as the kernels see it: detached, fp64 (a no-op view for float64 models)."""
+        return getattr(self, name).detach().to(F64)
 
     # ---- modes (gpmdm.py:239-279) ------------------------------------------------------------------
     def set_evaluation_mode(self):
@@ -360,7 +374,7 @@ class GPMDM(torch.nn.Module):
 
     def _Y_device(self):
         if self._Y_dev is None:
-            self._Y_dev = torch.tensor(self.get_Y(), dtype=self.dtype, device=self.device)
+            self._Y_dev = torch.tensor(self.get_Y(), dtype=F64, device=self.device)
         return self._Y_dev
 
     # ---- class structure as offsets (replaces get_M / get_M_for_class, gpmdm.py:311-378) -------------
@@ -383,14 +397,14 @@ class GPMDM(torch.nn.Module):
     def get_M(self):
         """Dense class mask (gpmdm.py:311-340).  Provided for API parity / small N; unused internally."""
         offs = self.class_pair_offsets()
-        M = torch.zeros(offs[-1], offs[-1], dtype=self.dtype, device=self.device)
+        M = torch.zeros(offs[-1], offs[-1], dtype=F64, device=self.device)
         for a, b in zip(offs[:-1], offs[1:]):
             M[a:b, a:b] = 1
         return M
 
     def get_M_for_class(self, class_index: int):
         offs = self.class_pair_offsets()
-        M = torch.zeros(offs[-1], offs[-1], dtype=self.dtype, device=self.device)
+        M = torch.zeros(offs[-1], offs[-1], dtype=F64, device=self.device)
         a, b = offs[class_index], offs[class_index + 1]
         M[a:b, a:b] = 1
         return M
@@ -414,7 +428,7 @@ class GPMDM(torch.nn.Module):
         K = torch.exp(-self.get_weighted_distances(X1, X2, log_lengthscales_par))
         if flg_noise:
             N = X1.shape[0]
-            eye = torch.eye(N, dtype=self.dtype, device=self.device)
+            eye = torch.eye(N, dtype=F64, device=self.device)
             K = K + torch.exp(log_sigma_n_par) ** 2 * eye + sigma_n_num ** 2 * eye
         return K
 
@@ -428,8 +442,8 @@ class GPMDM(torch.nn.Module):
 
     def get_lin_kernel(self, X1, X2, log_lin_coeff_par):
         Sigma = torch.diag(torch.exp(log_lin_coeff_par) ** 2)
-        X1 = torch.cat([X1, torch.ones(X1.shape[0], 1, dtype=self.dtype, device=self.device)], 1)
-        X2 = torch.cat([X2, torch.ones(X2.shape[0], 1, dtype=self.dtype, device=self.device)], 1)
+        X1 = torch.cat([X1, torch.ones(X1.shape[0], 1, dtype=F64, device=self.device)], 1)
+        X2 = torch.cat([X2, torch.ones(X2.shape[0], 1, dtype=F64, device=self.device)], 1)
         return torch.matmul(X1, torch.matmul(Sigma, X2.transpose(0, 1)))
 
     def get_masked_x_kernel(self, Xin):
@@ -439,14 +453,14 @@ class GPMDM(torch.nn.Module):
 
     def get_x_diag_kernel(self, X, flg_noise=False):
         c2 = torch.exp(self.x_log_lin_coeff) ** 2
-        Xa = torch.cat([X, torch.ones(X.shape[0], 1, dtype=self.dtype, device=self.device)], 1)
-        out = torch.ones(X.shape[0], dtype=self.dtype, device=self.device) + torch.sum((Xa * c2) * Xa, dim=1)
+        Xa = torch.cat([X, torch.ones(X.shape[0], 1, dtype=F64, device=self.device)], 1)
+        out = torch.ones(X.shape[0], dtype=F64, device=self.device) + torch.sum((Xa * c2) * Xa, dim=1)
         if flg_noise:
             out = out + torch.exp(self.x_log_sigma_n) ** 2 + self.sigma_n_num_X ** 2
         return out
 
     def get_y_diag_kernel(self, X, flg_noise=False):
-        out = torch.ones(X.shape[0], dtype=self.dtype, device=self.device)
+        out = torch.ones(X.shape[0], dtype=F64, device=self.device)
         if flg_noise:
             out = out + torch.exp(self.y_log_sigma_n) ** 2 + self.sigma_n_num_Y ** 2
         return out
@@ -455,7 +469,7 @@ class GPMDM(torch.nn.Module):
     @staticmethod
     def _logdet_and_trace(K, T, offsets=None):
         """log det K and tr(K^-1 T T^T) (closed-form backward, block-wise factorisation: `_LogdetTrace`)."""
-        return _LogdetTrace.apply(K, T, offsets)
+        return _LogdetTrace.apply(K, T.to(K.dtype), offsets)
 
     def get_y_neg_log_likelihood(self, Y, X, N):
         K_y = self.get_y_kernel(X, X)
@@ -599,7 +613,7 @@ class GPMDM(torch.nn.Module):
         return blk
 
     def _obs_kernel_matrix(self):
-        X = self.X.detach()
+        X = self._d("X")
         return self.get_y_kernel(X, X)  # same object twice: the symmetric CUDA build (csrc/train_kernels.cu)
 
     def _dyn_kernel_matrix(self, c, jitter=1e-6):
@@ -618,7 +632,7 @@ class GPMDM(torch.nn.Module):
         `Kx_inv_class[c]` (N_c x N_c diagonal blocks) remain available as attributes, materialised on access.  The
         reference's dense `Kx_inv` (:1291-1295) is only used by the class-agnostic `map_x_dynamics`, which the filter
         never calls; it is built lazily by `Kx_inv` below."""
-        X = self.X.detach()
+        X = self._d("X")
         Xin, Xout, _ = self.get_Xin_Xout_matrices(X)
         self._Xin, self._Xout = Xin.contiguous(), Xout.contiguous()
         want = self.default_factor_precisions
@@ -640,7 +654,7 @@ class GPMDM(torch.nn.Module):
             if blk["dense"] is None and not blk["panels"]:  # factored without fp64 panels (tf32-only precompute)
                 return None
             Kinv = self._block_dense(blk)
-            L = torch.empty(int(lib.gpmdm_quadform_bytes(blk["n_pad"], int(tri))) // 8, dtype=self.dtype, device=self.device)
+            L = torch.empty(int(lib.gpmdm_quadform_bytes(blk["n_pad"], int(tri))) // 8, dtype=F64, device=self.device)
             check(lib.gpmdm_pack_quadform_f64(ptr(Kinv), blk["n"], blk["n_pad"], int(tri), ptr(L), stream()),
                   "gpmdm_pack_quadform_f64")
             blk["panels"][tri] = L
@@ -681,7 +695,7 @@ class GPMDM(torch.nn.Module):
         """Inject precomputed inverses (e.g. the reference's own `Ky_inv` and the diagonal blocks of its
         `Kx_inv_class[c]`) -- used by the parity tests to compare kernels on identical factors."""
         def injected(Kinv, targets):
-            Kinv = to_tensor(Kinv, self.dtype, self.device).contiguous()
+            Kinv = to_tensor(Kinv, F64, self.device).contiguous()
             n = Kinv.shape[0]
             return dict(n=n, n_pad=_round_up(n, TILE_N), dense=Kinv, panels={}, wtiles=None,
                         A=torch.matmul(Kinv.t(), targets).contiguous())
@@ -705,11 +719,11 @@ class GPMDM(torch.nn.Module):
             cols.append(Xtrain * lin_c2[:d])
         rec = torch.cat(cols, 1)
         width = (rec.shape[1] + 1) & ~1  # records are padded to an even number of doubles (16-byte loads)
-        coords = torch.zeros(n_pad, width, dtype=self.dtype, device=self.device)
+        coords = torch.zeros(n_pad, width, dtype=F64, device=self.device)
         coords[:n, :rec.shape[1]] = rec
         L = self._block_panels(blk, tri) if with_L else None  # column panels (include/gpmdm_b200.h: gpmdm_gp_block)
         A = blk["A"]
-        alpha = torch.empty(int(lib.gpmdm_alpha_bytes(n_pad, alpha_ld)) // 8, dtype=self.dtype, device=self.device)
+        alpha = torch.empty(int(lib.gpmdm_alpha_bytes(n_pad, alpha_ld)) // 8, dtype=F64, device=self.device)
         check(lib.gpmdm_pack_alpha_f64(ptr(A), n, n_pad, A.shape[1], alpha_ld, ptr(alpha), stream()), "gpmdm_pack_alpha_f64")
         return dict(coords=coords, L=L, alpha=alpha, n=n, n_pad=n_pad)
 
@@ -721,7 +735,7 @@ class GPMDM(torch.nn.Module):
         if getattr(self, "_packed", None) is not None and self._packed["tri"] == tri \
                 and (self._packed["obs_has_L"] or not with_obs_L):
             return self._packed
-        X = self.X.detach()
+        X = self._d("X")
         dev = self.device
         keep = []  # tensors that must outlive the C structs
 
@@ -738,25 +752,25 @@ class GPMDM(torch.nn.Module):
         ald_y = _round_up(self.D, TILE_N)
         if with_obs_L:
             self._ensure_fp64_obs_panels(tri)
-        oblk = self._pack_block(X, self.y_log_lengthscales.detach(), self._obs_blk, ald_y, None, tri, with_L=with_obs_L)
-        ls_y = torch.exp(self.y_log_lengthscales.detach()).contiguous()
-        lam2_y = (torch.exp(self.y_log_lambdas.detach()) ** 2).contiguous()
+        oblk = self._pack_block(X, self._d("y_log_lengthscales"), self._obs_blk, ald_y, None, tri, with_L=with_obs_L)
+        ls_y = torch.exp(self._d("y_log_lengthscales")).contiguous()
+        lam2_y = (torch.exp(self._d("y_log_lambdas")) ** 2).contiguous()
         obs = model([oblk], self.d, self.D, ald_y, 0, ls_y, None, lam2_y)
         # dynamics GP: one block per class ('full', back_step 1 -- the only mode the filter supports)
         Xin = self._Xin
         if self.dyn_back_step == 1:
-            c2 = (torch.exp(self.x_log_lin_coeff.detach()) ** 2).contiguous()
-            ls_x = torch.exp(self.x_log_lengthscales.detach()).contiguous()
-            lam_x = (torch.exp(self.x_log_lambdas.detach()) ** -2).contiguous()
+            c2 = (torch.exp(self._d("x_log_lin_coeff")) ** 2).contiguous()
+            ls_x = torch.exp(self._d("x_log_lengthscales")).contiguous()
+            lam_x = (torch.exp(self._d("x_log_lambdas")) ** -2).contiguous()
             offs = self.class_pair_offsets()
-            dblks = [self._pack_block(Xin[offs[c]:offs[c + 1]], self.x_log_lengthscales.detach(), self._dyn_blks[c],
+            dblks = [self._pack_block(Xin[offs[c]:offs[c + 1]], self._d("x_log_lengthscales"), self._dyn_blks[c],
                                       TILE_N, c2, tri) for c in range(self.n_classes)]
             dyn = model(dblks, self.d, self.d, TILE_N, 1, ls_x, c2, lam_x)
         else:
             dyn = None
         self._packed = dict(tri=tri, obs=obs, obs_has_L=with_obs_L, dyn=dyn, keep=keep, obs_n_pad=oblk["n_pad"],
                             dyn_max_n_pad=max(b["n_pad"] for b in dblks) if dyn is not None else 0,
-                            ll_const_terms=(2.0 * torch.sum(self.y_log_lambdas.detach())).item())
+                            ll_const_terms=(2.0 * torch.sum(self._d("y_log_lambdas"))).item())
         return self._packed
 
     @torch.no_grad()
@@ -766,7 +780,7 @@ class GPMDM(torch.nn.Module):
         if getattr(self, "_packed_tf32", None) is not None and self._packed_tf32["version"] == self._factors_version:
             return self._packed_tf32
         lib = _cabi.lib()
-        X = self.X.detach()
+        X = self._d("X")
         n, d = X.shape
         n_pad = _round_up(n, TILE_N)
         if self._obs_blk.get("wtiles") is None:  # not part of the precompute: factor K_y (again) for the W tiles only
@@ -776,14 +790,14 @@ class GPMDM(torch.nn.Module):
         at = torch.empty(int(lib.gpmdm_tf32_atiles_bytes(n_pad)) // 4, dtype=torch.float32, device=self.device)
         check(lib.gpmdm_pack_alpha_tf32(ptr(alpha), n, n_pad, self.D, ptr(at), stream()), "gpmdm_pack_alpha_tf32")
         coords = torch.zeros(n_pad, 8, dtype=torch.float32, device=self.device)
-        coords[:n, :d] = (X / torch.exp(self.y_log_lengthscales.detach())).to(torch.float32)
+        coords[:n, :d] = (X / torch.exp(self._d("y_log_lengthscales"))).to(torch.float32)
         coords = coords.view(n_pad // 2, 2, 8).transpose(1, 2).contiguous()  # [pair][coordinate][row in pair]
-        ls = torch.exp(self.y_log_lengthscales.detach()).contiguous()
-        lam2 = (torch.exp(self.y_log_lambdas.detach()) ** 2).contiguous()
+        ls = torch.exp(self._d("y_log_lengthscales")).contiguous()
+        lam2 = (torch.exp(self._d("y_log_lambdas")) ** 2).contiguous()
         model = GpModelTf32(coords=coords.data_ptr(), wtiles=wt.data_ptr(), atiles=at.data_ptr(), n=n, n_pad=n_pad, d=d,
                             dout=self.D, lengthscales=ls.data_ptr(), lambdas=lam2.data_ptr())
         self._packed_tf32 = dict(version=self._factors_version, model=model, keep=(coords, wt, at, ls, lam2),
-                                 ll_const_terms=(2.0 * torch.sum(self.y_log_lambdas.detach())).item())
+                                 ll_const_terms=(2.0 * torch.sum(self._d("y_log_lambdas"))).item())
         return self._packed_tf32
 
     LOWLAT_MAX_TILES = 110  # below this many 64-particle tiles (of 148 SMs) the column tiles are split over CTAs
@@ -816,7 +830,7 @@ class GPMDM(torch.nn.Module):
 
     def _kstar_workspace(self, n_pad):
         need = int(_cabi.lib().gpmdm_pf_observe_kstar_workspace_bytes(n_pad)) // 8
-        return self._stream_scratch("kstar", need, self.dtype)
+        return self._stream_scratch("kstar", need, F64)
 
     def _scratch_counter(self):
         return self._stream_scratch("counter", 4, torch.int32)
@@ -828,10 +842,10 @@ class GPMDM(torch.nn.Module):
         kstar_cache: None = automatic (fused mode, N_pad >= 1024: K* of a particle tile is evaluated once into a per-SM
         scratch); True / False to force.  Bit-identical results either way."""
         lib = _cabi.lib()
-        Xs = to_tensor(Xstar, self.dtype, self.device).contiguous()
+        Xs = to_tensor(Xstar, F64, self.device).contiguous()
         P = Xs.shape[0]
-        mu = torch.empty(P, self.D, dtype=self.dtype, device=self.device)
-        v = torch.empty(P, dtype=self.dtype, device=self.device)
+        mu = torch.empty(P, self.D, dtype=F64, device=self.device)
+        v = torch.empty(P, dtype=F64, device=self.device)
         if precision == "tf32":  # variances on tcgen05 (tf32 x3, whitened); means stay fp64 (DMMA, alpha tile only)
             pk32, pk = self.packed_model_tf32(), self.packed_models(with_obs_L=False)
             check(lib.gpmdm_pf_observe_tf32(ctypes.byref(pk32["model"]), ptr(Xs), P, None, 0.0, None, None, ptr(v),
@@ -860,9 +874,9 @@ class GPMDM(torch.nn.Module):
         else:
             raise ValueError("precision must be 'fp64' or 'tf32'")
         if flg_noise:
-            v = v + torch.exp(self.y_log_sigma_n) ** 2 + self.sigma_n_num_Y ** 2
-        var = v.unsqueeze(1) * (torch.exp(self.y_log_lambdas) ** -2).unsqueeze(0)
-        return mu + torch.tensor(self.meanY, dtype=self.dtype, device=self.device), var
+            v = v + torch.exp(self._d("y_log_sigma_n")) ** 2 + self.sigma_n_num_Y ** 2
+        var = v.unsqueeze(1) * (torch.exp(self._d("y_log_lambdas")) ** -2).unsqueeze(0)
+        return (mu + torch.tensor(self.meanY, dtype=F64, device=self.device)).to(self.dtype), var.to(self.dtype)
 
     @torch.no_grad()
     def map_x_dynamics_for_class(self, Xstar, class_index: int, flg_noise=False, low_latency=None):
@@ -870,10 +884,10 @@ class GPMDM(torch.nn.Module):
         pk = self.packed_models()
         if pk["dyn"] is None:
             raise ValueError("fused dynamics prediction supports dyn_back_step == 1 only")
-        Xs = to_tensor(Xstar, self.dtype, self.device).contiguous()
+        Xs = to_tensor(Xstar, F64, self.device).contiguous()
         P = Xs.shape[0]
-        mean = torch.empty(P, self.d, dtype=self.dtype, device=self.device)
-        var = torch.empty(P, self.d, dtype=self.dtype, device=self.device)
+        mean = torch.empty(P, self.d, dtype=F64, device=self.device)
+        var = torch.empty(P, self.d, dtype=F64, device=self.device)
         if P == 0:
             return mean, var
         perm = torch.arange(P, dtype=torch.int32, device=self.device)
@@ -893,9 +907,9 @@ class GPMDM(torch.nn.Module):
                                              None, None, ptr(mean), ptr(var), ptr(self._scratch_counter()), stream()),
                   "gpmdm_pf_propagate_f64")
         if flg_noise:
-            var = var + (torch.exp(self.x_log_sigma_n) ** 2 + self.sigma_n_num_X ** 2) \
-                * (torch.exp(self.x_log_lambdas) ** -2).unsqueeze(0)
-        return mean, var
+            var = var + (torch.exp(self._d("x_log_sigma_n")) ** 2 + self.sigma_n_num_X ** 2) \
+                * (torch.exp(self._d("x_log_lambdas")) ** -2).unsqueeze(0)
+        return mean.to(self.dtype), var.to(self.dtype)
 
     # ---- class-agnostic dynamics map and the notebook helpers (gpmdm.py:993-1030, 1103-1273) -----------------------
     # Not on the filter path; kept so that the reference's notebooks run unchanged.  The masked
@@ -906,15 +920,15 @@ class GPMDM(torch.nn.Module):
         if getattr(self, "_packed_agn", None) is not None and self._packed_agn["version"] == self._factors_version:
             return self._packed_agn
         offs = self.class_pair_offsets()
-        c2 = (torch.exp(self.x_log_lin_coeff.detach()) ** 2).contiguous()
-        ls_x = torch.exp(self.x_log_lengthscales.detach()).contiguous()
-        lam_x = (torch.exp(self.x_log_lambdas.detach()) ** -2).contiguous()
+        c2 = (torch.exp(self._d("x_log_lin_coeff")) ** 2).contiguous()
+        ls_x = torch.exp(self._d("x_log_lengthscales")).contiguous()
+        lam_x = (torch.exp(self._d("x_log_lambdas")) ** -2).contiguous()
         blocks = []
         for c in range(self.n_classes):
             Xc = self._Xin[offs[c]:offs[c + 1]].contiguous()
             # block of K_x o M: no 1e-6 jitter (gpmdm.py:1292)
             blk = self._factor_block(lambda: self._dyn_kernel_matrix(c, jitter=0.0), self._Xout[offs[c]:offs[c + 1]].contiguous())
-            blocks.append(self._pack_block(Xc, self.x_log_lengthscales.detach(), blk, TILE_N, c2, True))
+            blocks.append(self._pack_block(Xc, self._d("x_log_lengthscales"), blk, TILE_N, c2, True))
         table = torch.tensor([[b["coords"].data_ptr(), b["L"].data_ptr(), b["alpha"].data_ptr(), b["n"], b["n_pad"]]
                               for b in blocks], dtype=torch.int64, device=self.device)
         model = GpModel(blocks=table.data_ptr(), n_blocks=len(blocks), d=self.d, dout=self.d, alpha_ld=TILE_N, kind=1,
@@ -929,20 +943,20 @@ class GPMDM(torch.nn.Module):
             raise ValueError("fused dynamics prediction supports dyn_back_step == 1 only")
         lib = _cabi.lib()
         pk = self._agnostic_dyn_model()
-        Xs = to_tensor(Xstar, self.dtype, self.device).contiguous()
+        Xs = to_tensor(Xstar, F64, self.device).contiguous()
         P = Xs.shape[0]
-        lam = torch.exp(self.x_log_lambdas.detach()) ** -2
+        lam = torch.exp(self._d("x_log_lambdas")) ** -2
         prior = self.get_x_diag_kernel(Xs, flg_noise)
-        mean = torch.zeros(P, self.d, dtype=self.dtype, device=self.device)
-        q = torch.zeros(P, dtype=self.dtype, device=self.device)
+        mean = torch.zeros(P, self.d, dtype=F64, device=self.device)
+        q = torch.zeros(P, dtype=F64, device=self.device)
         if P == 0:
             return mean, prior.unsqueeze(1) * lam.unsqueeze(0)
         perm = torch.arange(P, dtype=torch.int32, device=self.device)
         nt = (P + TILE_P - 1) // TILE_P
         t = torch.arange(nt, dtype=torch.int32, device=self.device)
         n_tiles = torch.tensor([nt], dtype=torch.int32, device=self.device)
-        m_c = torch.empty(P, self.d, dtype=self.dtype, device=self.device)
-        v_c = torch.empty(P, self.d, dtype=self.dtype, device=self.device)
+        m_c = torch.empty(P, self.d, dtype=F64, device=self.device)
+        v_c = torch.empty(P, self.d, dtype=F64, device=self.device)
         prior0 = self.get_x_diag_kernel(Xs, False)
         for c in range(self.n_classes):
             tiles = torch.stack([torch.full_like(t, c), t * TILE_P, torch.clamp(P - t * TILE_P, max=TILE_P),

@@ -47,7 +47,7 @@ class GPMDM_PF:
 
     def __init__(self, gpmdm: GPMDM, markov_switching_model, num_particles: int, *,
                  seed: int = 0, resampling: str = "multinomial", cdf_order: str = "sequential",
-                 tri: bool = True, precision: str = "fp64", low_latency: Optional[bool] = None,
+                 tri: bool = True, precision: Optional[str] = None, low_latency: Optional[bool] = None,
                  kstar_cache: Optional[bool] = None, native_step: bool = True, init_indices: Optional[Sequence] = None, process_group=None,
                  distributed: Optional[bool] = None, cuda_graph: Optional[bool] = None):
         """
@@ -58,7 +58,8 @@ class GPMDM_PF:
                         scan in fixed 1024-element blocks
         tri             use the triangular packing of K^-1 (half the flops of the dense quadratic form)
         precision       'fp64' (exact path) or 'tf32': observation GP on tcgen05 tensor cores with error-compensated
-                        tf32 products and the whitened variance (~1e-4 relative); dynamics / resampling stay fp64
+                        tf32 products and the whitened variance (~1e-4 relative); dynamics / resampling stay fp64.
+                        None = 'fp64' for a float64 model, 'tf32' for a float32 model (reference ctor dtype, gpmdm.py:108)
         low_latency     None = automatic: with fewer 64-particle tiles than SMs the column tiles of each particle tile are
                         split over the SMs (two kernels per GP stage instead of one); True / False to force
         kstar_cache     None = automatic: the fused fp64 observation kernel keeps each particle tile's cross-kernel K* in a
@@ -74,7 +75,10 @@ class GPMDM_PF:
         self._lib = _cabi.lib()
         self._gpmdm = gpmdm
         self._gpmdm.set_evaluation_mode()
-        self._markov_switching_model = torch.as_tensor(markov_switching_model).type(self.dtype).to(self.device).contiguous()
+        # cast to the model dtype as gpmdm_pf.py:71 does (a float32 model sees float32 transition probabilities), then
+        # to the fp64 the kernels compute in
+        self._markov_switching_model = torch.as_tensor(markov_switching_model).type(self.dtype).to(
+            device=self.device, dtype=torch.float64).contiguous()
         self._num_particles = int(num_particles)
         if self._gpmdm.n_classes != self._markov_switching_model.size(0):
             raise ValueError("Number of classes in the GPMDM model and the Markov model do not match")
@@ -88,6 +92,8 @@ class GPMDM_PF:
         self._systematic = resampling == "systematic"
         self._cdf_mode = 0 if cdf_order == "sequential" else 1
         self._tri = bool(tri)
+        if precision is None:
+            precision = "tf32" if gpmdm.dtype == torch.float32 else "fp64"
         if precision not in ("fp64", "tf32"):
             raise ValueError("precision must be 'fp64' or 'tf32'")
         self._precision = precision
@@ -116,7 +122,7 @@ class GPMDM_PF:
 
     # ---- buffers ------------------------------------------------------------------------------------------
     def _alloc(self):
-        P, d, C, dev, f64 = self._num_particles, self.latent_dim, self.num_classes, self.device, self.dtype
+        P, d, C, dev, f64 = self._num_particles, self.latent_dim, self.num_classes, self.device, torch.float64
         Pl = self._hi - self._lo
         e = lambda *s, dt=f64: torch.empty(*s, dtype=dt, device=dev)
         self._x_new, self._c_new, self._ll_all = e(P, d), e(P, dt=torch.int64), e(P)
@@ -184,15 +190,16 @@ class GPMDM_PF:
                     raise ValueError("init_indices[%d] must hold %d indices" % (i, n_per_class[i]))
             else:
                 idx = torch.randint(0, class_data.size(0), (n_per_class[i],), device=self.device, generator=gen)
-            parts.append(class_data[idx].detach().clone())
+            parts.append(class_data[idx].detach().to(torch.float64))
         self._resets += 1
         self._particle_states = torch.cat(parts, dim=0).contiguous()
         self._particle_classes = torch.repeat_interleave(
             torch.arange(C, dtype=torch.int64, device=self.device),
             torch.tensor(n_per_class, dtype=torch.int64, device=self.device))
-        self._log_likelihoods = torch.zeros(P, dtype=self.dtype, device=self.device)
-        self._log_weights = torch.zeros(P, dtype=self.dtype, device=self.device)
-        self._weights = torch.ones(P, dtype=self.dtype, device=self.device) / P
+        # the particle cloud and its weights are held in fp64 whatever the model's public dtype
+        self._log_likelihoods = torch.zeros(P, dtype=torch.float64, device=self.device)
+        self._log_weights = torch.zeros(P, dtype=torch.float64, device=self.device)
+        self._weights = torch.ones(P, dtype=torch.float64, device=self.device) / P
         self._summary_step = -1
 
     # ---- the filter step (gpmdm_pf.py:117-135) -----------------------------------------------------------------
@@ -201,7 +208,7 @@ class GPMDM_PF:
         draws: optional (E [P,C] Exp(1), eps [P,d] N(0,1), u [P] U(0,1)) raw draws for ALL particles."""
         if self._small and not (isinstance(z, torch.Tensor) and z.is_cuda):
             return self._update(self._stage_z(z), draws)
-        z = torch.as_tensor(np.asarray(z) if not isinstance(z, torch.Tensor) else z).to(device=self.device, dtype=self.dtype)
+        z = torch.as_tensor(np.asarray(z) if not isinstance(z, torch.Tensor) else z).to(device=self.device, dtype=torch.float64)
         self._update(z.contiguous(), draws)
 
     def _stage_z(self, z):
@@ -240,7 +247,7 @@ class GPMDM_PF:
                                                 ptr(self._u), st), "gpmdm_pf_draws_philox")
             E, eps, u = self._E, self._eps, self._u
         else:
-            E, eps, u = (torch.as_tensor(a).to(device=self.device, dtype=self.dtype) for a in draws)
+            E, eps, u = (torch.as_tensor(a).to(device=self.device, dtype=torch.float64) for a in draws)
             if E.shape != (P, C) or eps.shape != (P, d) or u.shape != (P,):
                 raise ValueError("draws must be (E [P,C], eps [P,d], u [P])")
             E, eps, u = E[lo:hi].contiguous(), eps[lo:hi].contiguous(), u.contiguous()
@@ -380,7 +387,7 @@ class GPMDM_PF:
         return draws + transition + bucket + propagate + observe + normalize + cdf + resample + summaries
 
     def _log_weights_buf(self):
-        return torch.empty(self._num_particles, dtype=self.dtype, device=self.device)
+        return torch.empty(self._num_particles, dtype=torch.float64, device=self.device)
 
     _weights_buf = _log_weights_buf
 
@@ -406,7 +413,7 @@ class GPMDM_PF:
 
     def current_state_mean(self):
         C = self.num_classes
-        return self._summaries()[C:C + self.latent_dim].clone()
+        return self._summaries()[C:C + self.latent_dim].to(self.dtype, copy=True)
 
     def reset(self):
         self._init_particles()

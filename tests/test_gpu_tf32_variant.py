@@ -74,3 +74,58 @@ def test_tf32_filter_step_log_weights(setup):
     assert float(rel.max()) < 1e-3, float(rel.max())
     assert float(rel.median()) < TOL32, float(rel.median())
     assert pf64.get_most_likely_class() == pf32.get_most_likely_class()
+
+
+def test_float32_model_dtype_argument(tmp_path):
+    """The reference ctor's `dtype` argument (gpmdm.py:108-109): a float32 model keeps float32 parameters / latents and
+    returns float32 predictions; the filter defaults to the tf32 variant.  Against a float64 model holding the same
+    (up-cast) parameters: north_star's fp32 tolerance 1e-4 on means, variances (of the prior) and log-weights."""
+    from gpmdm_b200 import GPMDM, GPMDM_PF
+
+    C, d, D = 2, 3, 20
+    wl = synthetic.make_sequences(C, D, 4, 80, seed=3, n_test_trials=1, test_frames=6)
+    hp = synthetic.notebook_hyperparameters(D, d, 1e-1)
+    m32 = GPMDM(D=D, d=d, n_classes=C, dyn_target="full", dyn_back_step=1, dtype=torch.float32, **hp)
+    for c in range(C):
+        for s in wl.sequences[c]:
+            m32.add_data(s, c)
+    m32.init_X()
+    losses = m32.train_adam(3, 0, lr=0.01)
+    assert len(losses) == 3 and all(np.isfinite(losses))
+    assert m32.X.dtype == torch.float32 and m32.y_log_lambdas.dtype == torch.float32 and m32.X.grad.dtype == torch.float32
+    # the same model in float64
+    m64 = GPMDM(D=D, d=d, n_classes=C, dyn_target="full", dyn_back_step=1, **hp)
+    for c in range(C):
+        for s in wl.sequences[c]:
+            m64.add_data(s, c)
+    m64.init_X()
+    m64.load_state_dict({k: v.double() for k, v in m32.state_dict().items()})
+    m64._precompute_kernel_inverses()
+    m32.set_evaluation_mode()
+    xs = (m64.X.detach()[::3] + 0.2).contiguous()
+    mu32, var32 = m32.map_x_to_y(xs.float(), precision="tf32")
+    mu64, var64 = m64.map_x_to_y(xs)
+    assert mu32.dtype == torch.float32 and var32.dtype == torch.float32
+    scale = torch.clamp(mu64.abs().max(dim=1, keepdim=True).values, min=1e-2)
+    assert float(((mu32.double() - mu64).abs() / scale).max()) < TOL32
+    assert float((var32.double() - var64).abs().max()) < TOL32  # lambda = exp(trained) ~ 1: of the prior variance
+    dm32, dv32 = m32.map_x_dynamics_for_class(xs.float(), 1)
+    dm64, dv64 = m64.map_x_dynamics_for_class(xs, 1)
+    assert dm32.dtype == torch.float32 and float((dm32.double() - dm64).abs().max()) < TOL32 * (1 + float(dm64.abs().max()))
+    T = synthetic.markov_matrix(C)
+    pf32, pf64 = GPMDM_PF(m32, T, 512, seed=2), GPMDM_PF(m64, T, 512, seed=2, precision="tf32")
+    assert pf32._precision == "tf32" and pf32.dtype == torch.float32
+    z = wl.test_trials[0][1][0]
+    pf32.update(z)
+    pf64.update(z)
+    assert torch.equal(pf32.last_pre_resample_classes, pf64.last_pre_resample_classes)
+    ok = torch.isfinite(pf64._log_likelihoods)
+    rel = (pf32._log_likelihoods[ok] - pf64._log_likelihoods[ok]).abs() / pf64._log_likelihoods[ok].abs()
+    assert float(rel.median()) < TOL32
+    assert pf32.class_probabilities().dtype == torch.float64 and pf32.current_state_mean().dtype == torch.float32
+    path = str(tmp_path / "m32.pth")
+    m32.save(path)
+    back = GPMDM.load(path)
+    assert back.dtype == torch.float32 and back.X.dtype == torch.float32
+    mu_b, _ = back.map_x_to_y(xs.float())
+    assert float((mu_b - m32.map_x_to_y(xs.float())[0]).abs().max()) == 0.0

@@ -35,6 +35,8 @@ def main():
     ap.add_argument("--train-frames", type=int, default=100)
     ap.add_argument("--train-steps", type=int, default=0)
     ap.add_argument("--precision", default="fp64")
+    ap.add_argument("--no-graph", action="store_true", help="launch the small-cloud step directly instead of replaying a CUDA graph")
+    ap.add_argument("--staged", action="store_true", help="the stage-by-stage launch sequence (round-1 path)")
     a = ap.parse_args()
     from gpmdm_b200 import GPMDM, GPMDM_PF, synthetic
 
@@ -48,8 +50,11 @@ def main():
     if a.train_steps:
         model.train_adam(a.train_steps, 0, lr=0.01)
     T = synthetic.markov_matrix(C)
-    pf = GPMDM_PF(model, T, a.particles, seed=0, precision=a.precision)
-    pf.update(wl.test_trials[0][1][0]); pf.reset()  # warm-up (kernel attributes, allocator)
+    pf = GPMDM_PF(model, T, a.particles, seed=0, precision=a.precision, cuda_graph=not a.no_graph,
+                  native_step=not a.staged)
+    for z in wl.test_trials[0][1][:4]:  # warm-up (kernel attributes, allocator, graph capture)
+        pf.update(z)
+    pf.reset()
     frame_true, frame_pred, trial_true, trial_pred, secs, frames = [], [], [], [], 0.0, 0
     for cls, trial in wl.test_trials:
         pf.reset()
@@ -71,6 +76,9 @@ def main():
                     f"{a.trials} synthetic trials x {a.frames} frames, precision={a.precision}",
         "frame_accuracy": float(np.mean(ft == fp_)), "frame_f1": f1_macro(ft, fp_, C),
         "trial_accuracy": float(np.mean(tt == tp_)), "trial_f1": f1_macro(tt, tp_, C),
+        "step_path": ("small-cloud kernels, " + ("CUDA graph replay" if pf._use_graph else "direct launches")) if pf._small
+                     else ("native launch sequence" if pf._native_step else "staged launches"),
+        "launches_per_step": pf.launches_per_step,
         "seconds_per_frame": secs / frames, "fps": frames / secs, "particle_updates_per_sec": a.particles * frames / secs,
         "reference_published": {"fps": 12.78, "trial_accuracy": 0.974, "frame_accuracy": 0.921,
                                 "note": "laptop CPU, CMU mocap (not in tree), P=100 -- test_gpmdm_pf.ipynb"},
