@@ -54,15 +54,17 @@ def parse_args():
     ap.add_argument("--cpu-sample", type=int, default=4096, help="particles of the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--dense", action="store_true", help="dense K^-1 instead of the triangular packing")
-    ap.add_argument("--precision", default="fp64", choices=["fp64", "tf32"],
-                    help="fp64 = exact path (the headline); tf32 = tcgen05 variant of the observation GP (config 4)")
+    ap.add_argument("--precision", default="fp64", choices=["fp64", "tf32", "f16x2"],
+                    help="fp64 = exact path (the headline); tf32 / f16x2 = tcgen05 variants of the observation GP (config 4)")
     return ap.parse_args()
 
 
 def workload_name(a):
     n = a.classes * a.seqs_per_class * a.frames
-    which = "configs[3] (tf32 variant)" if getattr(a, "precision", "fp64") == "tf32" and a.classes == 64 else "configs[2]"
-    prec = "fp64" if getattr(a, "precision", "fp64") == "fp64" else "tf32x3 variances + fp64 means/dynamics"
+    pr = getattr(a, "precision", "fp64")
+    which = "configs[3] (fp32-accuracy variant)" if pr != "fp64" and a.classes == 64 else "configs[2]"
+    prec = {"fp64": "fp64", "tf32": "tf32x3 variances + fp64 means/dynamics",
+            "f16x2": "fp16-split (2 x fp16, 3 MMAs) variances + fp64 means/dynamics"}[pr]
     return (f"BASELINE {which}: {a.classes}-class GPMDM, N_train={n}, D={a.obs_dim}, d={a.latent}, "
             f"P={a.particles} particles, {prec}")
 
@@ -84,6 +86,8 @@ def synthetic_inputs(a):
 def build_product_model(a, wl, X0, hp):
     from gpmdm_b200 import GPMDM
 
+    if getattr(a, "precision", "fp64") != "fp64":  # tensor-core variants: never build (or hold) the fp64 panels
+        GPMDM.default_factor_precisions = (a.precision,)
     m = GPMDM(D=a.obs_dim, d=a.latent, n_classes=a.classes, dyn_target="full", dyn_back_step=1, **hp)
     for c in range(a.classes):
         for s in wl.sequences[c]:
@@ -426,19 +430,24 @@ def run_ours(a):
                          "(not a roofline fraction)") if not a.dense else "dense K^-1",
             }
         else:
-            # tf32 variant: whitened form |W k|^2 on the lower-triangular W (N^2 + 2ND algorithmic flops per particle),
-            # executed as 3 tf32 MMAs per product; peak = tcgen05 kind::tf32 issue-rate probe of this run
-            tf = ctypes_probe(lib, "gpmdm_probe_tf32_tflops", 20000)
+            # tensor-core variants: whitened form |W k|^2 on the lower-triangular W (N^2 + 2ND algorithmic flops per
+            # particle), executed as 3 MMAs per product (tf32 triple, or fp16 pair); peak = tcgen05 issue-rate probe of
+            # the same MMA kind measured in this run
+            f16 = a.precision == "f16x2"
+            tf = ctypes_probe(lib, "gpmdm_probe_f16_tflops" if f16 else "gpmdm_probe_tf32_tflops", 20000)
             tiles128 = (Pl + 127) // 128
             flops_alg32 = Pl * (1.0 * N * N + 2.0 * N * D)
-            flops_mma = 3.0 * tiles128 * 128 * (2.0 * TN * TN) * (nq * (nq + 1) / 2 + nq)
+            flops_mma = 3.0 * tiles128 * 128 * (2.0 * TN * TN) * (nq * (nq + 1) / 2 + (0 if f16 else nq))
             achieved = flops_mma / secs / 1e12
+            kname = "observe_tf32_kernel<%d,%s>" % (d, "MODE_F16X2" if f16 else "MODE_TF32X3")
             roofline = {
                 "bound": "tensor", "achieved": achieved, "peak": tf, "unit": "TFLOP/s", "frac": achieved / tf,
-                "traffic": None, "kernel": f"observe_tf32_kernel<{d}> (gpmdm_pf_observe_tf32) + fp64 mean tile (gpmdm_pf_loglik_f64)",
+                "traffic": None, "kernel": f"{kname} ({'gpmdm_pf_observe_f16x2' if f16 else 'gpmdm_pf_observe_tf32'}) + fp64 mean tile (gpmdm_pf_loglik_f64)",
                 "launch_ms": obs_avg_ms, "launch_share_of_step": obs_avg_ms / (elapsed_ms / a.steps),
-                "peak_source": "tcgen05.mma kind::tf32 M128 N256 K8 issue-rate probe (resident pseudo-random operands) measured "
-                               "in this run; nominal dense tf32 is 1100; achieved counts the tf32 MMA flops issued (3 per product)",
+                "peak_source": ("tcgen05.mma kind::%s M128 N256 K%d issue-rate probe (resident pseudo-random operands) measured in this "
+                                "run; achieved counts the MMA flops issued (3 per product); launch_ms covers both kernels of the "
+                                "observation stage" % (("f16", 16) if f16 else ("tf32", 8))),
+                "measured_peaks_bf16_tflops": measured_peak("bf16_tflops"),
                 "algorithmic_tflops": flops_alg32 / secs / 1e12, "algorithmic_frac": flops_alg32 / secs / 1e12 / tf,
             }
         cpu, parity = None, None
@@ -463,7 +472,8 @@ def run_ours(a):
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": elapsed_ms / a.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "f64" if a.precision == "fp64" else "tf32x3 (observation GP) + f64", "data": "synthetic",
+            "dtype": {"fp64": "f64", "tf32": "tf32x3 (observation GP) + f64", "f16x2": "f16x2 (observation GP) + f64"}[a.precision],
+            "data": "synthetic",
             "config": {"workload": workload_name(a),
                        "l2": "inputs larger than L2 (the packed K^-1 panels streamed by every particle tile are %.2f GB)"
                              % (1e-9 * lib.gpmdm_quadform_bytes((N + 255) // 256 * 256, 0 if a.dense else 1)),
@@ -488,6 +498,13 @@ def ctypes_probe(lib, name="gpmdm_probe_dmma_tflops", iters=20000):
     if rc != 0:
         raise RuntimeError(name + " failed")
     return tf.value
+
+
+def measured_peak(key):
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get(key)
+    except (OSError, ValueError):
+        return None
 
 
 def measured_traffic(N, d, cached, tri, tiles):

@@ -93,6 +93,10 @@ _SIGNATURES = {
     "gpmdm_kernel_grad_workspace_bytes": (_i64, [_i64, _i32]),
     "gpmdm_probe_dmma_tflops": (ctypes.c_int, [_i32, ctypes.POINTER(_f64)]),
     "gpmdm_probe_tf32_tflops": (ctypes.c_int, [_i32, ctypes.POINTER(_f64)]),
+    "gpmdm_probe_f16_tflops": (ctypes.c_int, [_i32, ctypes.POINTER(_f64)]),
+    "gpmdm_f16_wtiles_bytes": (_i64, [_i64]),
+    "gpmdm_pack_whitened_f16x2": (ctypes.c_int, [_ptr, _i64, _i64, _ptr, _ptr]),
+    "gpmdm_pf_observe_f16x2": (ctypes.c_int, [ctypes.POINTER(GpModelTf32), _ptr, _i64, _ptr, _ptr, _ptr]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

@@ -22,6 +22,16 @@
 //   warps 12-15  epilogue: TMEM -> registers, sum of squares / mean / log-likelihood; double-buffered accumulator
 // The operand tiles are packed on the host side once (gpmdm_pack_whitened_tf32) in exactly the byte order the
 // tensor core reads, so a 1-D bulk copy lands them ready to use (no tensor maps, no swizzle).
+//
+// MODE_F16X2 -- the same kernel with every operand split into TWO fp16 pieces instead of the error-compensated tf32
+// triple:  a = a_hi + 2^-11 a_lo,  a_hi = fp16(a),  a_lo = fp16((a - a_hi) 2^11)  (the scaling keeps the residual inside
+// fp16's narrow exponent range: K* lies in [0, 1], |W| <= 1/sigma_n),
+//     a b ~ a_hi b_hi + 2^-11 (a_lo b_hi + a_hi b_lo)          -- 22 significant bits, as 3xTF32
+// i.e. three kind::f16 MMAs per k-step of 16 (twice the k of a tf32 step, at the same cycle count): half the tensor-pipe
+// time, half the operand bytes per product.  The two terms go to separate fp32 TMEM accumulators (D1, D2 = 2 x 256
+// columns, so the accumulator is single-buffered) and are combined in the epilogue.  Variance only; means and the
+// log-likelihood stay with the fp64 mean tile (gpmdm_pf_loglik_f64), as in the hybrid tf32 variant.
+#include <cuda_fp16.h>
 #include <math.h>
 
 #include "common.cuh"
@@ -29,23 +39,33 @@
 namespace gpmdm {
 namespace tf32 {
 
+constexpr int MODE_TF32X3 = 0, MODE_F16X2 = 1;
 constexpr int TM = 128;      // particles per CTA tile (UMMA M)
 constexpr int TN = 256;      // columns per column tile (UMMA N)
-constexpr int KC = 16;       // k per chunk = 2 UMMA k-steps of 8
 constexpr int ASTAGES = 4;
 constexpr int BSTAGES = 3;
-constexpr int A_HALF = TM * KC;          // floats in the hi (or lo) part of an A stage
-constexpr int B_HALF = TN * KC;          // floats in the hi (or lo) part of a B stage / packed tile
+constexpr int A_HALF_BYTES = TM * 16 * 4;   // bytes in the hi (or lo) part of an A stage: 8 KB in both modes
+constexpr int B_HALF_BYTES = TN * 16 * 4;   // bytes in the hi (or lo) part of a B stage / packed tile: 16 KB
 constexpr int NGEN = 256;                // generator threads
 constexpr int NEPI = 128;                // epilogue threads
 constexpr int NTHREADS = 512;
 constexpr int GEN_WARP0 = 4, EPI_WARP0 = 12;
-constexpr uint32_t LBO = 128, SBO = (KC / 4) * 128;  // core-matrix strides (bytes) along K and along M/N
 constexpr int CREC = 8;                  // floats per training record (a_i padded to 8)
+// k per chunk: 16 tf32 (2 MMA k-steps of 8) or 32 fp16 (2 k-steps of 16) -- 64 operand bytes per row either way, i.e.
+// four 16-byte core-matrix rows along K, so stages, tiles and descriptors have the same byte geometry in both modes
+template <int MODE> struct Geo {
+    static constexpr int ESIZE = MODE == MODE_F16X2 ? 2 : 4;
+    static constexpr int KC = 64 / ESIZE;
+    static constexpr int KSTEP = 32 / ESIZE;   // k per MMA
+    static constexpr int CM = 16 / ESIZE;      // elements per core-matrix row
+};
+constexpr int KC = Geo<MODE_TF32X3>::KC;       // (tf32 names kept for the packers and the probe below)
+constexpr int A_HALF = A_HALF_BYTES / 4, B_HALF = B_HALF_BYTES / 4;
+constexpr uint32_t LBO = 128, SBO = 4 * 128;  // core-matrix strides (bytes) along K and along M/N
 
 struct __align__(1024) Smem {
-    float A[ASTAGES][2][A_HALF];   // [stage][hi|lo] 8 KB each
-    float B[BSTAGES][2][B_HALF];   // [stage][hi|lo] 16 KB each
+    unsigned char A[ASTAGES][2][A_HALF_BYTES];   // [stage][hi|lo]
+    unsigned char B[BSTAGES][2][B_HALF_BYTES];   // [stage][hi|lo]
     uint64_t a_full[ASTAGES], a_empty[ASTAGES], b_full[BSTAGES], b_empty[BSTAGES], t_full[2], t_empty[2];
     uint32_t tmem_base;
 };
@@ -68,9 +88,11 @@ struct Params {
     int32_t* status;         // particles whose variance was not a positive finite number (NULL = not counted)
 };
 
-// element (row, k) of a [rows x KC] operand tile in the canonical no-swizzle K-major layout, in floats
+// element (row, k) of a [rows x KC] operand tile in the canonical no-swizzle K-major layout, in elements
+template <int MODE = MODE_TF32X3>
 __host__ __device__ __forceinline__ int tile_index(int row, int k) {
-    return (row >> 3) * (SBO / 4) + (k >> 2) * (LBO / 4) + (row & 7) * 4 + (k & 3);
+    constexpr int CM = Geo<MODE>::CM, ES = Geo<MODE>::ESIZE;
+    return (row >> 3) * (SBO / ES) + (k / CM) * (LBO / ES) + (row & 7) * CM + (k % CM);
 }
 
 __device__ __forceinline__ uint64_t smem_desc(const void* p) {
@@ -83,8 +105,10 @@ __device__ __forceinline__ uint64_t smem_desc(const void* p) {
     d |= (uint64_t)1 << 46;
     return d;
 }
-// instruction descriptor: D = f32, A = B = tf32, both K-major, N = 256, M = 128
+// instruction descriptor: D = f32 (bits 4-5 = 1), A / B format (bits 7-9 / 10-12: tf32 = 2 for kind::tf32, f16 = 0 for
+// kind::f16), both K-major, N = 256 (bits 17-22 = N >> 3), M = 128 (bits 24-28 = M >> 4)
 constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+constexpr uint32_t IDESC_F16 = (1u << 4) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
 
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
     asm volatile(
@@ -94,6 +118,16 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t"
         "}\n" ::"r"(tmem_d),
         "l"(adesc), "l"(bdesc), "r"(IDESC), "r"(accumulate), "r"(0u)
+        : "memory");
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(IDESC_F16), "r"(accumulate), "r"(0u)
         : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
@@ -124,16 +158,41 @@ __device__ __forceinline__ float to_tf32(float x) {
     return __uint_as_float(r);
 }
 
-// number of W tiles before column tile J, and in total
-__host__ __device__ __forceinline__ long long wtile_offset(int J) { return (long long)(TN / KC) * J * (J + 1) / 2; }
+// number of W tiles before column tile J, and in total (KC = k per chunk / per packed tile)
+__host__ __device__ __forceinline__ long long wtile_offset_kc(int J, int kc) { return (long long)(TN / kc) * J * (J + 1) / 2; }
+__host__ __device__ __forceinline__ long long wtile_offset(int J) { return wtile_offset_kc(J, KC); }
 
-template <int DL>
+// bounded mbarrier wait for the MODE_F16X2 instance: a protocol bug traps (launch failure) instead of hanging the GPU.
+// try_wait suspends the thread for a hardware-defined interval per attempt, so waiting warps do not take issue slots.
+__device__ __forceinline__ void mbar_wait_b(uint64_t* bar, uint32_t parity) {
+    for (uint32_t spin = 0; spin < (1u << 24); spin++) {
+        uint32_t ok;
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+        if (ok) return;
+    }
+    __trap();
+}
+
+template <int DL, int MODE>
 __global__ void __launch_bounds__(NTHREADS, 1) observe_tf32_kernel(const Params prm) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     Smem& s = *reinterpret_cast<Smem*>(smem_raw);
+    using G = Geo<MODE>;
+    constexpr int KCm = G::KC;                               // k per chunk in this mode
+    constexpr bool F16 = MODE == MODE_F16X2;
+    // accumulator buffers: two in tf32 mode; one in F16X2 mode, where D1 | D2 fill all 512 TMEM columns
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int nq = prm.n_pad / TN, nkc = prm.n_pad / KC;
-    const int nct = nq + ((prm.ll || prm.mu_out) ? 1 : 0);  // + one alpha tile (dout <= 256) when a mean is wanted
+    const int nq = prm.n_pad / TN, nkc = prm.n_pad / KCm;
+    // + one alpha tile (dout <= 256) when a mean is wanted (tf32 mode only: the fp16 split is used for variances)
+    const int nct = nq + ((!F16 && (prm.ll || prm.mu_out)) ? 1 : 0);
     const int n_tiles = (int)((prm.P + TM - 1) / TM);
 
     if (tid == 0) {
@@ -161,24 +220,30 @@ __global__ void __launch_bounds__(NTHREADS, 1) observe_tf32_kernel(const Params 
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = s.tmem_base;
+    auto wait = [](uint64_t* bar, uint32_t parity) {
+        if (F16) mbar_wait_b(bar, parity);
+        else mbar_wait(bar, parity);
+    };
 
     // chunk count of column tile ct: W tiles are lower triangular (k < 256 (J+1)); the alpha tile needs all k
-    auto chunks_of = [&](int ct) { return ct < nq ? (ct + 1) * (TN / KC) : nkc; };
+    auto chunks_of = [&](int ct) { return ct < nq ? (ct + 1) * (TN / KCm) : nkc; };
 
     if (warp == 0) {
         // ===================== TMA producer =====================
         if (lane == 0) {
             uint32_t g = 0;
             int rounds = 0;
+            const unsigned char* wt = reinterpret_cast<const unsigned char*>(prm.wtiles);
+            const unsigned char* at = reinterpret_cast<const unsigned char*>(prm.atiles);
             for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
                 for (int ct = 0; ct < nct; ct++) {
-                    const float* base = ct < nq ? prm.wtiles + wtile_offset(ct) * (2 * B_HALF) : prm.atiles;
+                    const unsigned char* base = ct < nq ? wt + wtile_offset_kc(ct, KCm) * (2 * B_HALF_BYTES) : at;
                     const int nch = chunks_of(ct);
                     for (int kc = 0; kc < nch; kc++, g++) {
                         const int st = g % BSTAGES;
-                        mbar_wait(&s.b_empty[st], ((g / BSTAGES) & 1) ^ 1);
-                        mbar_expect_tx(&s.b_full[st], 2 * B_HALF * 4);
-                        bulk_g2s(&s.B[st][0][0], base + (long long)kc * (2 * B_HALF), 2 * B_HALF * 4, &s.b_full[st]);
+                        wait(&s.b_empty[st], ((g / BSTAGES) & 1) ^ 1);
+                        mbar_expect_tx(&s.b_full[st], 2 * B_HALF_BYTES);
+                        bulk_g2s(&s.B[st][0][0], base + (long long)kc * (2 * B_HALF_BYTES), 2 * B_HALF_BYTES, &s.b_full[st]);
                     }
                 }
                 // Round synchronisation of the producers (bounded polling, never a hang): the 148 CTAs stream the same
@@ -204,26 +269,33 @@ __global__ void __launch_bounds__(NTHREADS, 1) observe_tf32_kernel(const Params 
             uint32_t g = 0, tcount = 0;
             for (int t = blockIdx.x; t < n_tiles; t += gridDim.x)
                 for (int ct = 0; ct < nct; ct++, tcount++) {
-                    const int acc = tcount & 1;
-                    mbar_wait(&s.t_empty[acc], ((tcount >> 1) & 1) ^ 1);  // epilogue drained this accumulator
+                    const int acc = F16 ? 0 : (tcount & 1);
+                    const uint32_t use = F16 ? tcount : (tcount >> 1);     // how often this buffer has been used before
+                    wait(&s.t_empty[acc], (use & 1) ^ 1);  // epilogue drained this accumulator
                     tc_fence_after();
                     const uint32_t d_tmem = tmem + (uint32_t)acc * TN;
                     const int nch = chunks_of(ct);
                     for (int kc = 0; kc < nch; kc++, g++) {
                         const int sa = g % ASTAGES, sb = g % BSTAGES;
-                        mbar_wait(&s.a_full[sa], (g / ASTAGES) & 1);
-                        mbar_wait(&s.b_full[sb], (g / BSTAGES) & 1);
+                        wait(&s.a_full[sa], (g / ASTAGES) & 1);
+                        wait(&s.b_full[sb], (g / BSTAGES) & 1);
                         tc_fence_after();
 #pragma unroll
-                        for (int k8 = 0; k8 < KC / 8; k8++) {
-                            const uint32_t koff = k8 * 2 * LBO;  // two core matrices (8 tf32) along K per MMA
-                            const uint64_t a_hi = smem_desc(reinterpret_cast<const char*>(&s.A[sa][0][0]) + koff);
-                            const uint64_t a_lo = smem_desc(reinterpret_cast<const char*>(&s.A[sa][1][0]) + koff);
-                            const uint64_t b_hi = smem_desc(reinterpret_cast<const char*>(&s.B[sb][0][0]) + koff);
-                            const uint64_t b_lo = smem_desc(reinterpret_cast<const char*>(&s.B[sb][1][0]) + koff);
-                            umma_tf32(d_tmem, a_hi, b_hi, (kc | k8) != 0);
-                            umma_tf32(d_tmem, a_lo, b_hi, 1);
-                            umma_tf32(d_tmem, a_hi, b_lo, 1);
+                        for (int ks = 0; ks < 2; ks++) {  // two MMA k-steps per chunk (2 x 8 tf32 / 2 x 16 fp16)
+                            const uint32_t koff = ks * 2 * LBO;  // two core matrices (32 bytes of every row) along K per MMA
+                            const uint64_t a_hi = smem_desc(&s.A[sa][0][0] + koff);
+                            const uint64_t a_lo = smem_desc(&s.A[sa][1][0] + koff);
+                            const uint64_t b_hi = smem_desc(&s.B[sb][0][0] + koff);
+                            const uint64_t b_lo = smem_desc(&s.B[sb][1][0] + koff);
+                            if (F16) {  // D1 += a_hi b_hi ;  D2 += a_lo b_hi + a_hi b_lo  (scaled by 2^-11 in the epilogue)
+                                umma_f16(d_tmem, a_hi, b_hi, (kc | ks) != 0);
+                                umma_f16(d_tmem + TN, a_lo, b_hi, (kc | ks) != 0);
+                                umma_f16(d_tmem + TN, a_hi, b_lo, 1);
+                            } else {
+                                umma_tf32(d_tmem, a_hi, b_hi, (kc | ks) != 0);
+                                umma_tf32(d_tmem, a_lo, b_hi, 1);
+                                umma_tf32(d_tmem, a_hi, b_lo, 1);
+                            }
                         }
                         umma_commit(&s.a_empty[sa]);  // arrives when the MMAs above have read the operands
                         umma_commit(&s.b_empty[sb]);
@@ -234,8 +306,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) observe_tf32_kernel(const Params 
     } else if (warp >= GEN_WARP0 && warp < EPI_WARP0) {
         // ===================== K* generators =====================
         const int gt = tid - GEN_WARP0 * 32;
-        const int row = gt & (TM - 1), khalf = gt >> 7;  // 8 consecutive k per thread
+        const int row = gt & (TM - 1), khalf = gt >> 7;  // KCm / 2 consecutive k per thread
         constexpr float LOG2E = 1.4426950408889634f;
+        constexpr int KPT = KCm / 2;                     // k per thread and chunk: 8 (tf32) / 16 (fp16)
         uint32_t g = 0;
         for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
             long long p = (long long)t * TM + row;
@@ -251,12 +324,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) observe_tf32_kernel(const Params 
                 const int nch = chunks_of(ct);
                 for (int kc = 0; kc < nch; kc++, g++) {
                     const int sa = g % ASTAGES;
-                    float hi[8], lo[8];
+                    float kv[KPT];
                     // coords are stored per PAIR of training rows as [j][2] (a_k[j], a_k+1[j]): one 64-bit element feeds
                     // the packed fp32x2 pipe (sm_100 FADD2 / FFMA2), two K* entries per instruction
-                    const float2* rec = reinterpret_cast<const float2*>(prm.coords) + (long long)(kc * KC + khalf * 8) / 2 * CREC;
+                    const float2* rec = reinterpret_cast<const float2*>(prm.coords) + (long long)(kc * KCm + khalf * KPT) / 2 * CREC;
 #pragma unroll
-                    for (int kk = 0; kk < 8; kk += 2) {
+                    for (int kk = 0; kk < KPT; kk += 2) {
                         float2 a[CREC];
 #pragma unroll
                         for (int q = 0; q < (DL + 1) / 2; q++) {
@@ -270,20 +343,42 @@ __global__ void __launch_bounds__(NTHREADS, 1) observe_tf32_kernel(const Params 
                             const float2 tdiff = __fadd2_rn(a[j], nb[j]);
                             dist = __ffma2_rn(tdiff, tdiff, dist);
                         }
-                        const float k0 = exp2f(-LOG2E * dist.x), k1 = exp2f(-LOG2E * dist.y);
-                        hi[kk] = to_tf32(k0);
-                        lo[kk] = to_tf32(k0 - hi[kk]);
-                        hi[kk + 1] = to_tf32(k1);
-                        lo[kk + 1] = to_tf32(k1 - hi[kk + 1]);
+                        kv[kk] = exp2f(-LOG2E * dist.x);
+                        kv[kk + 1] = exp2f(-LOG2E * dist.y);
                     }
-                    mbar_wait(&s.a_empty[sa], ((g / ASTAGES) & 1) ^ 1);
-                    float* ah = &s.A[sa][0][0];
-                    float* al = &s.A[sa][1][0];
+                    wait(&s.a_empty[sa], ((g / ASTAGES) & 1) ^ 1);
+                    if (F16) {
+                        // a = hi + 2^-11 lo: 16 consecutive k of one row = two 16-byte core-matrix rows per piece
+                        __half* ah = reinterpret_cast<__half*>(&s.A[sa][0][0]);
+                        __half* al = reinterpret_cast<__half*>(&s.A[sa][1][0]);
 #pragma unroll
-                    for (int q = 0; q < 2; q++) {
-                        const int idx = tile_index(row, khalf * 8 + q * 4);
-                        *reinterpret_cast<float4*>(ah + idx) = make_float4(hi[q * 4], hi[q * 4 + 1], hi[q * 4 + 2], hi[q * 4 + 3]);
-                        *reinterpret_cast<float4*>(al + idx) = make_float4(lo[q * 4], lo[q * 4 + 1], lo[q * 4 + 2], lo[q * 4 + 3]);
+                        for (int q = 0; q < KPT / 8; q++) {
+                            __align__(16) __half hi[8], lo[8];
+#pragma unroll
+                            for (int i = 0; i < 8; i++) {
+                                const float kvi = kv[q * 8 + i];
+                                hi[i] = __float2half_rn(kvi);
+                                lo[i] = __float2half_rn((kvi - __half2float(hi[i])) * 2048.f);
+                            }
+                            const int idx = tile_index<MODE>(row, khalf * KPT + q * 8);
+                            *reinterpret_cast<uint4*>(ah + idx) = *reinterpret_cast<const uint4*>(hi);
+                            *reinterpret_cast<uint4*>(al + idx) = *reinterpret_cast<const uint4*>(lo);
+                        }
+                    } else {
+                        float* ah = reinterpret_cast<float*>(&s.A[sa][0][0]);
+                        float* al = reinterpret_cast<float*>(&s.A[sa][1][0]);
+#pragma unroll
+                        for (int q = 0; q < KPT / 4; q++) {
+                            float hi[4], lo[4];
+#pragma unroll
+                            for (int i = 0; i < 4; i++) {
+                                hi[i] = to_tf32(kv[q * 4 + i]);
+                                lo[i] = to_tf32(kv[q * 4 + i] - hi[i]);
+                            }
+                            const int idx = tile_index<MODE>(row, khalf * KPT + q * 4);
+                            *reinterpret_cast<float4*>(ah + idx) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+                            *reinterpret_cast<float4*>(al + idx) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+                        }
                     }
                     fence_async_smem();  // generic-proxy stores -> visible to the tensor core's async proxy
                     mbar_arrive(&s.a_full[sa]);
@@ -301,8 +396,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) observe_tf32_kernel(const Params 
             float q = 0.f;
             double S = 0.0;
             for (int ct = 0; ct < nct; ct++, tcount++) {
-                const int acc = tcount & 1;
-                mbar_wait(&s.t_full[acc], (tcount >> 1) & 1);
+                const int acc = F16 ? 0 : (tcount & 1);
+                const uint32_t use = F16 ? tcount : (tcount >> 1);
+                wait(&s.t_full[acc], use & 1);
                 tc_fence_after();
                 const uint32_t taddr = tmem + lane_base + (uint32_t)acc * TN;
                 if (ct < nq) {
@@ -311,8 +407,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) observe_tf32_kernel(const Params 
                         float v[32];
                         tmem_ld32(taddr + cb, v);
                         float part = 0.f;
+                        if (F16) {
+                            float w[32];
+                            tmem_ld32(taddr + TN + cb, w);
 #pragma unroll
-                        for (int i = 0; i < 32; i++) part = fmaf(v[i], v[i], part);
+                            for (int i = 0; i < 32; i++) {
+                                const float u = fmaf(w[i], 1.0f / 2048.f, v[i]);
+                                part = fmaf(u, u, part);
+                            }
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 32; i++) part = fmaf(v[i], v[i], part);
+                        }
                         q += part;
                     }
                 } else {
@@ -397,14 +503,40 @@ __global__ void pack_alpha_kernel(const double* __restrict__ alpha, long long n,
     dst[B_HALF + idx] = lo;
 }
 
-template <int DL>
+// W [n, n] (fp64, lower triangular) -> fp16 hi / scaled-lo tiles (MODE_F16X2): w = hi + 2^-11 lo.
+//   tile (J, kc), kc < 8 (J+1):  B[row = n - 256 J][k - 32 kc] = W[n][k]
+__global__ void pack_whitened_f16_kernel(const double* __restrict__ W, long long n, int n_pad, __half* __restrict__ out) {
+    constexpr int KCh = Geo<MODE_F16X2>::KC;
+    constexpr int TILE_ELEMS = B_HALF_BYTES / 2;  // halves in one piece of a packed tile: 256 x 32
+    const int nq = n_pad / TN;
+    const long long total_tiles = wtile_offset_kc(nq, KCh);
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total_tiles * TILE_ELEMS) return;
+    const long long tile = i / TILE_ELEMS;
+    const int e = (int)(i % TILE_ELEMS);
+    int J = (int)((sqrt(1.0 + 8.0 * (double)tile / (TN / KCh)) - 1.0) * 0.5);
+    while (wtile_offset_kc(J + 1, KCh) <= tile) J++;
+    while (wtile_offset_kc(J, KCh) > tile) J--;
+    const int kc = (int)(tile - wtile_offset_kc(J, KCh));
+    const int row = e / KCh, k = e % KCh;
+    const long long nn = (long long)J * TN + row, kk = (long long)kc * KCh + k;
+    const double w = (nn < n && kk < n && kk <= nn) ? W[nn * n + kk] : 0.0;
+    const __half hi = __double2half(w);
+    const __half lo = __double2half((w - (double)__half2float(hi)) * 2048.0);
+    __half* dst = out + tile * (2 * TILE_ELEMS);
+    const int idx = tile_index<MODE_F16X2>(row, k);
+    dst[idx] = hi;
+    dst[TILE_ELEMS + idx] = lo;
+}
+
+template <int DL, int MODE = MODE_TF32X3>
 static int launch(const Params& prm, int grid, cudaStream_t st) {
     // the opt-in to > 48 KB of dynamic shared memory is per function AND per device
     static bool configured[64] = {};  // per instantiation
     int dev = 0;
     cudaGetDevice(&dev);
     dev = (dev >= 0 && dev < 64) ? dev : 0;
-    auto kern = observe_tf32_kernel<DL>;
+    auto kern = observe_tf32_kernel<DL, MODE>;
     if (!configured[dev]) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
         if (e != cudaSuccess) {
@@ -429,6 +561,7 @@ struct ProbeSmem {
     uint32_t tmem_base;
 };
 
+template <bool F16>
 __global__ void __launch_bounds__(128, 1) tf32_probe_kernel(int iters, float* __restrict__ sink) {
     __shared__ __align__(1024) ProbeSmem s;
     const int tid = threadIdx.x, warp = tid >> 5;
@@ -436,8 +569,15 @@ __global__ void __launch_bounds__(128, 1) tf32_probe_kernel(int iters, float* __
     for (int i = tid; i < A_HALF + B_HALF; i += 128) {
         h = h * 1664525u + 1013904223u;
         const float u = (float)(h >> 8) * (1.0f / 16777216.0f);  // [0, 1)
-        if (i < A_HALF) s.A[i] = to_tf32(u);
-        else s.B[i - A_HALF] = to_tf32((u - 0.5f) * 1e-3f);
+        // the same bytes are read as 16 x tf32 or 32 x fp16 per row; for fp16 pack two modest values per word
+        const float a = i < A_HALF ? u : (u - 0.5f) * 1e-3f;
+        float word = to_tf32(a);
+        if (F16) {
+            const __half2 h2 = __floats2half2_rn(a, a * 0.75f);
+            word = *reinterpret_cast<const float*>(&h2);
+        }
+        if (i < A_HALF) s.A[i] = word;
+        else s.B[i - A_HALF] = word;
     }
     if (tid == 0) {
         mbar_init(&s.done, 1);
@@ -460,8 +600,12 @@ __global__ void __launch_bounds__(128, 1) tf32_probe_kernel(int iters, float* __
 #pragma unroll
             for (int k8 = 0; k8 < KC / 8; k8++) {
                 const uint32_t koff = k8 * 2 * LBO;
-                umma_tf32(d_tmem, smem_desc(reinterpret_cast<const char*>(s.A) + koff),
-                          smem_desc(reinterpret_cast<const char*>(s.B) + koff), (it > 1) || k8);
+                if (F16)
+                    umma_f16(d_tmem, smem_desc(reinterpret_cast<const char*>(s.A) + koff),
+                             smem_desc(reinterpret_cast<const char*>(s.B) + koff), (it > 1) || k8);
+                else
+                    umma_tf32(d_tmem, smem_desc(reinterpret_cast<const char*>(s.A) + koff),
+                              smem_desc(reinterpret_cast<const char*>(s.B) + koff), (it > 1) || k8);
             }
         }
         umma_commit(&s.done);
@@ -562,7 +706,8 @@ extern "C" int gpmdm_pf_observe_tf32(const gpmdm_gp_model_tf32* m, const double*
     return GPMDM_E_UNSUPPORTED;
 }
 
-extern "C" int gpmdm_probe_tf32_tflops(int32_t iters, double* tflops_host) {
+template <bool F16>
+static int probe_impl(int32_t iters, double* tflops_host) {
     GPMDM_REQUIRE(tflops_host && iters > 0, GPMDM_E_INVALID, "bad argument");
     int dev = 0, sms = 0;
     cudaError_t e = cudaGetDevice(&dev);
@@ -571,11 +716,11 @@ extern "C" int gpmdm_probe_tf32_tflops(int32_t iters, double* tflops_host) {
     cudaEvent_t t0, t1;
     cudaEventCreate(&t0);
     cudaEventCreate(&t1);
-    tf32::tf32_probe_kernel<<<sms, 128>>>(iters / 4 + 1, nullptr);  // warm-up
+    tf32::tf32_probe_kernel<F16><<<sms, 128>>>(iters / 4 + 1, nullptr);  // warm-up
     float best = 1e30f;
     for (int rep = 0; rep < 5; rep++) {
         cudaEventRecord(t0);
-        tf32::tf32_probe_kernel<<<sms, 128>>>(iters, nullptr);
+        tf32::tf32_probe_kernel<F16><<<sms, 128>>>(iters, nullptr);
         cudaEventRecord(t1);
         cudaEventSynchronize(t1);
         float ms = 0;
@@ -586,7 +731,70 @@ extern "C" int gpmdm_probe_tf32_tflops(int32_t iters, double* tflops_host) {
     cudaEventDestroy(t1);
     int rc = check_launch("tf32_probe_kernel");
     if (rc) return rc;
-    const double flops = 2.0 * tf32::TM * tf32::TN * tf32::KC * (double)iters * sms;
+    // per iteration: two MMAs of M = 128, N = 256 and K = 8 (tf32) / 16 (fp16)
+    const double flops = 2.0 * tf32::TM * tf32::TN * (F16 ? 32.0 : 16.0) * (double)iters * sms;
     *tflops_host = flops / (best * 1e-3) / 1e12;
     return 0;
+}
+
+extern "C" int gpmdm_probe_tf32_tflops(int32_t iters, double* tflops_host) { return probe_impl<false>(iters, tflops_host); }
+extern "C" int gpmdm_probe_f16_tflops(int32_t iters, double* tflops_host) { return probe_impl<true>(iters, tflops_host); }
+
+extern "C" int64_t gpmdm_f16_wtiles_bytes(int64_t n_pad) {
+    return tf32::wtile_offset_kc((int)(n_pad / tf32::TN), tf32::Geo<tf32::MODE_F16X2>::KC) * (2 * tf32::B_HALF_BYTES);
+}
+
+extern "C" int gpmdm_pack_whitened_f16x2(const double* W, int64_t n, int64_t n_pad, void* wtiles, void* stream) {
+    GPMDM_REQUIRE(W && wtiles, GPMDM_E_INVALID, "null argument");
+    GPMDM_REQUIRE(n > 0 && n_pad >= n && n_pad % GPMDM_TILE_N == 0, GPMDM_E_INVALID, "bad sizes");
+    const long long total = gpmdm_f16_wtiles_bytes(n_pad) / 4;  // one thread per (hi, lo) pair of halves
+    tf32::pack_whitened_f16_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        W, n, (int)n_pad, static_cast<__half*>(wtiles));
+    return check_launch("pack_whitened_f16_kernel");
+}
+
+extern "C" int gpmdm_pf_observe_f16x2(const gpmdm_gp_model_tf32* m, const double* x, int64_t P, double* v_out,
+                                      int32_t* tile_counter, void* stream) {
+    GPMDM_REQUIRE(m && m->coords && m->wtiles && m->lengthscales, GPMDM_E_INVALID, "null model field");
+    GPMDM_REQUIRE(m->d >= 1 && m->d <= GPMDM_MAX_LATENT, GPMDM_E_UNSUPPORTED, "latent dimension %d outside [1, %d]", m->d,
+                  GPMDM_MAX_LATENT);
+    GPMDM_REQUIRE(m->n_pad > 0 && m->n_pad % GPMDM_TILE_N == 0, GPMDM_E_INVALID, "n_pad must be a multiple of %d",
+                  GPMDM_TILE_N);
+    GPMDM_REQUIRE(P >= 0 && P < (1ll << 31), GPMDM_E_INVALID, "P out of range");
+    if (P == 0) return 0;
+    GPMDM_REQUIRE(x && v_out, GPMDM_E_INVALID, "null argument");
+    tf32::Params prm{};
+    prm.coords = m->coords;
+    prm.wtiles = m->wtiles;
+    prm.n_pad = (int)m->n_pad;
+    prm.d = m->d;
+    prm.dout = m->dout;
+    prm.ls = m->lengthscales;
+    prm.lam2 = m->lambdas;
+    prm.x = x;
+    prm.P = P;
+    prm.v_out = v_out;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const long long tiles = (P + tf32::TM - 1) / tf32::TM;
+    const int grid = (int)(tiles < sms ? tiles : sms);
+    cudaStream_t st = (cudaStream_t)stream;
+    prm.status = tile_counter ? tile_counter + 3 : nullptr;
+    if (tile_counter && tiles >= 2ll * grid) {
+        cudaError_t e = cudaMemsetAsync(tile_counter, 0, sizeof(int32_t), st);
+        GPMDM_REQUIRE(e == cudaSuccess, (int)e, "cudaMemsetAsync: %s", cudaGetErrorString(e));
+        prm.round_counter = tile_counter;
+    }
+    switch (m->d) {
+        case 1: return tf32::launch<1, tf32::MODE_F16X2>(prm, grid, st);
+        case 2: return tf32::launch<2, tf32::MODE_F16X2>(prm, grid, st);
+        case 3: return tf32::launch<3, tf32::MODE_F16X2>(prm, grid, st);
+        case 4: return tf32::launch<4, tf32::MODE_F16X2>(prm, grid, st);
+        case 5: return tf32::launch<5, tf32::MODE_F16X2>(prm, grid, st);
+        case 6: return tf32::launch<6, tf32::MODE_F16X2>(prm, grid, st);
+        case 7: return tf32::launch<7, tf32::MODE_F16X2>(prm, grid, st);
+        case 8: return tf32::launch<8, tf32::MODE_F16X2>(prm, grid, st);
+    }
+    return GPMDM_E_UNSUPPORTED;
 }

@@ -581,11 +581,11 @@ class GPMDM(torch.nn.Module):
         return torch.matmul(U_inv, U_inv.t())
 
     # Factor precisions built by `_precompute_kernel_inverses`: "fp64" = the quadratic-form panels of the exact path,
-    # "tf32" = the whitening-factor tiles of the tf32 variant.  Whatever is missing is built on first use; a tf32-only
+    # "tf32" / "f16x2" = the whitening-factor tiles of the tensor-core variants.  Whatever is missing is built on first use; a tf32-only
     # deployment at N = 50 k sets ("tf32",) to never hold the 10 GB of fp64 panels.
     default_factor_precisions = ("fp64",)
 
-    def _factor_block(self, make_K, targets, want_fp64=True, want_tf32=False, tri=True):
+    def _factor_block(self, make_K, targets, want=("fp64",), tri=True):
         """Factors of one GP block from its kernel matrix K = make_K() (built here so that this frame holds the only
         reference and K is released as soon as it is factored).  K = L L^T (the reference's U is L^T), L^-1 in place, then
             alpha  = K^-1 targets = L^-T (L^-1 targets)                         (gpmdm.py:957, 1064)
@@ -602,14 +602,21 @@ class GPMDM(torch.nn.Module):
             L = L.contiguous()
         Linv = tril_inverse_inplace(L)
         del L
-        blk = dict(n=n, n_pad=n_pad, dense=None, panels={}, wtiles=None,
+        blk = dict(n=n, n_pad=n_pad, dense=None, panels={}, wtiles=None, wtiles_f16=None,
                    A=torch.mm(Linv.t(), torch.mm(Linv, targets)).contiguous())
-        if want_fp64:
+        if "fp64" in want:
             blk["panels"][bool(tri)] = quadform_panels_from_tril_inverse(Linv, n_pad, bool(tri))
-        if want_tf32:
+        if "tf32" in want:
             wt = torch.empty(int(lib.gpmdm_tf32_wtiles_bytes(n_pad)) // 4, dtype=torch.float32, device=self.device)
             check(lib.gpmdm_pack_whitened_tf32(ptr(Linv), n, n_pad, ptr(wt), stream()), "gpmdm_pack_whitened_tf32")
             blk["wtiles"] = wt
+        if "f16x2" in want:
+            wmax = float(Linv.abs().max())
+            if not wmax < 3.0e4:  # fp16 overflows at 65504: |W| <= 1/sigma_n, so this only happens for noise std < ~3e-5
+                raise ValueError("precision 'f16x2' needs |W| = |L^-1| < 3e4 (max is %.3g): use 'tf32' or 'fp64'" % wmax)
+            wh = torch.empty(int(lib.gpmdm_f16_wtiles_bytes(n_pad)) // 2, dtype=torch.float16, device=self.device)
+            check(lib.gpmdm_pack_whitened_f16x2(ptr(Linv), n, n_pad, ptr(wh), stream()), "gpmdm_pack_whitened_f16x2")
+            blk["wtiles_f16"] = wh
         return blk
 
     def _obs_kernel_matrix(self):
@@ -636,7 +643,7 @@ class GPMDM(torch.nn.Module):
         Xin, Xout, _ = self.get_Xin_Xout_matrices(X)
         self._Xin, self._Xout = Xin.contiguous(), Xout.contiguous()
         want = self.default_factor_precisions
-        self._obs_blk = self._factor_block(self._obs_kernel_matrix, self._Y_device(), "fp64" in want, "tf32" in want)
+        self._obs_blk = self._factor_block(self._obs_kernel_matrix, self._Y_device(), want)
         offs = self.class_pair_offsets()
         self._dyn_blks = [self._factor_block(lambda: self._dyn_kernel_matrix(c), self._Xout[offs[c]:offs[c + 1]].contiguous())
                           for c in range(self.n_classes)]
@@ -669,7 +676,7 @@ class GPMDM(torch.nn.Module):
     def _ensure_fp64_obs_panels(self, tri):
         blk = self._obs_blk
         if blk["dense"] is None and not blk["panels"]:
-            fresh = self._factor_block(self._obs_kernel_matrix, self._Y_device(), True, False, tri)
+            fresh = self._factor_block(self._obs_kernel_matrix, self._Y_device(), ("fp64",), tri)
             blk["panels"] = fresh["panels"]
 
     @property
@@ -697,7 +704,7 @@ class GPMDM(torch.nn.Module):
         def injected(Kinv, targets):
             Kinv = to_tensor(Kinv, F64, self.device).contiguous()
             n = Kinv.shape[0]
-            return dict(n=n, n_pad=_round_up(n, TILE_N), dense=Kinv, panels={}, wtiles=None,
+            return dict(n=n, n_pad=_round_up(n, TILE_N), dense=Kinv, panels={}, wtiles=None, wtiles_f16=None,
                         A=torch.matmul(Kinv.t(), targets).contiguous())
 
         if Ky_inv is not None:
@@ -774,31 +781,35 @@ class GPMDM(torch.nn.Module):
         return self._packed
 
     @torch.no_grad()
-    def packed_model_tf32(self):
-        """Operands of the tf32 observation kernel (include/gpmdm_b200.h: gpmdm_gp_model_tf32): the whitening factor
-        W = U^-T = L^-1 of K_y = U^T U = L L^T and alpha_y, split into tf32 hi/lo tiles in tensor-core operand order."""
-        if getattr(self, "_packed_tf32", None) is not None and self._packed_tf32["version"] == self._factors_version:
-            return self._packed_tf32
+    def packed_model_tf32(self, kind="tf32"):
+        """Operands of the tensor-core observation kernels (include/gpmdm_b200.h: gpmdm_gp_model_tf32): the whitening
+        factor W = U^-T = L^-1 of K_y = U^T U = L L^T as tensor-core operand tiles -- tf32 hi/lo (kind "tf32", plus alpha_y
+        tiles) or fp16 hi / scaled lo (kind "f16x2")."""
+        cache = self.__dict__.setdefault("_packed_tc", {})
+        if kind in cache and cache[kind]["version"] == self._factors_version:
+            return cache[kind]
         lib = _cabi.lib()
         X = self._d("X")
         n, d = X.shape
         n_pad = _round_up(n, TILE_N)
-        if self._obs_blk.get("wtiles") is None:  # not part of the precompute: factor K_y (again) for the W tiles only
-            self._obs_blk["wtiles"] = self._factor_block(self._obs_kernel_matrix, self._Y_device(), False, True)["wtiles"]
-        wt = self._obs_blk["wtiles"]
-        alpha = self._obs_blk["A"]
-        at = torch.empty(int(lib.gpmdm_tf32_atiles_bytes(n_pad)) // 4, dtype=torch.float32, device=self.device)
-        check(lib.gpmdm_pack_alpha_tf32(ptr(alpha), n, n_pad, self.D, ptr(at), stream()), "gpmdm_pack_alpha_tf32")
+        key = "wtiles" if kind == "tf32" else "wtiles_f16"
+        if self._obs_blk.get(key) is None:  # not part of the precompute: factor K_y (again) for the W tiles only
+            self._obs_blk[key] = self._factor_block(self._obs_kernel_matrix, self._Y_device(), (kind,))[key]
+        wt = self._obs_blk[key]
+        at = None
+        if kind == "tf32":
+            at = torch.empty(int(lib.gpmdm_tf32_atiles_bytes(n_pad)) // 4, dtype=torch.float32, device=self.device)
+            check(lib.gpmdm_pack_alpha_tf32(ptr(self._obs_blk["A"]), n, n_pad, self.D, ptr(at), stream()), "gpmdm_pack_alpha_tf32")
         coords = torch.zeros(n_pad, 8, dtype=torch.float32, device=self.device)
         coords[:n, :d] = (X / torch.exp(self._d("y_log_lengthscales"))).to(torch.float32)
         coords = coords.view(n_pad // 2, 2, 8).transpose(1, 2).contiguous()  # [pair][coordinate][row in pair]
         ls = torch.exp(self._d("y_log_lengthscales")).contiguous()
         lam2 = (torch.exp(self._d("y_log_lambdas")) ** 2).contiguous()
-        model = GpModelTf32(coords=coords.data_ptr(), wtiles=wt.data_ptr(), atiles=at.data_ptr(), n=n, n_pad=n_pad, d=d,
-                            dout=self.D, lengthscales=ls.data_ptr(), lambdas=lam2.data_ptr())
-        self._packed_tf32 = dict(version=self._factors_version, model=model, keep=(coords, wt, at, ls, lam2),
-                                 ll_const_terms=(2.0 * torch.sum(self._d("y_log_lambdas"))).item())
-        return self._packed_tf32
+        model = GpModelTf32(coords=coords.data_ptr(), wtiles=wt.data_ptr(), atiles=at.data_ptr() if at is not None else None,
+                            n=n, n_pad=n_pad, d=d, dout=self.D, lengthscales=ls.data_ptr(), lambdas=lam2.data_ptr())
+        cache[kind] = dict(version=self._factors_version, model=model, keep=(coords, wt, at, ls, lam2),
+                           ll_const_terms=(2.0 * torch.sum(self._d("y_log_lambdas"))).item())
+        return cache[kind]
 
     LOWLAT_MAX_TILES = 110  # below this many 64-particle tiles (of 148 SMs) the column tiles are split over CTAs
 
@@ -852,6 +863,12 @@ class GPMDM(torch.nn.Module):
                                             ptr(self._scratch_counter()), stream()), "gpmdm_pf_observe_tf32")
             check(lib.gpmdm_pf_loglik_f64(ctypes.byref(pk["obs"]), ptr(Xs), P, None, 0.0, ptr(v), None, ptr(mu),
                                           ptr(self._scratch_counter()), stream()), "gpmdm_pf_loglik_f64")
+        elif precision == "f16x2":  # variances on tcgen05 with fp16-split operands; means fp64 as above
+            pk16, pk = self.packed_model_tf32("f16x2"), self.packed_models(with_obs_L=False)
+            check(lib.gpmdm_pf_observe_f16x2(ctypes.byref(pk16["model"]), ptr(Xs), P, ptr(v), ptr(self._scratch_counter()),
+                                             stream()), "gpmdm_pf_observe_f16x2")
+            check(lib.gpmdm_pf_loglik_f64(ctypes.byref(pk["obs"]), ptr(Xs), P, None, 0.0, ptr(v), None, ptr(mu),
+                                          ptr(self._scratch_counter()), stream()), "gpmdm_pf_loglik_f64")
         elif precision == "tf32-pure":  # mean on the tensor cores as well (error ~1e-4..1e-3 of the row scale)
             pk32 = self.packed_model_tf32()
             check(lib.gpmdm_pf_observe_tf32(ctypes.byref(pk32["model"]), ptr(Xs), P, None, 0.0, None, ptr(mu), ptr(v),
@@ -872,7 +889,7 @@ class GPMDM(torch.nn.Module):
                 check(lib.gpmdm_pf_observe_f64(ctypes.byref(pk["obs"]), ptr(Xs), P, None, 0.0, None, ptr(mu), ptr(v),
                                                ptr(self._scratch_counter()), stream()), "gpmdm_pf_observe_f64")
         else:
-            raise ValueError("precision must be 'fp64' or 'tf32'")
+            raise ValueError("precision must be 'fp64', 'tf32' or 'f16x2'")
         if flg_noise:
             v = v + torch.exp(self._d("y_log_sigma_n")) ** 2 + self.sigma_n_num_Y ** 2
         var = v.unsqueeze(1) * (torch.exp(self._d("y_log_lambdas")) ** -2).unsqueeze(0)

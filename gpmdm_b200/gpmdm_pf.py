@@ -57,8 +57,9 @@ class GPMDM_PF:
         cdf_order       'sequential' = the reference's running sum, bit-identical cdf; 'blocked' = parallel
                         scan in fixed 1024-element blocks
         tri             use the triangular packing of K^-1 (half the flops of the dense quadratic form)
-        precision       'fp64' (exact path) or 'tf32': observation GP on tcgen05 tensor cores with error-compensated
-                        tf32 products and the whitened variance (~1e-4 relative); dynamics / resampling stay fp64.
+        precision       'fp64' (exact path), or 'tf32' / 'f16x2': observation GP on tcgen05 tensor cores with error-compensated
+                        products (3 x tf32, or 2 x fp16 split at twice the rate) and the whitened variance (~1e-4 relative);
+                        dynamics / resampling stay fp64.
                         None = 'fp64' for a float64 model, 'tf32' for a float32 model (reference ctor dtype, gpmdm.py:108)
         low_latency     None = automatic: with fewer 64-particle tiles than SMs the column tiles of each particle tile are
                         split over the SMs (two kernels per GP stage instead of one); True / False to force
@@ -94,8 +95,8 @@ class GPMDM_PF:
         self._tri = bool(tri)
         if precision is None:
             precision = "tf32" if gpmdm.dtype == torch.float32 else "fp64"
-        if precision not in ("fp64", "tf32"):
-            raise ValueError("precision must be 'fp64' or 'tf32'")
+        if precision not in ("fp64", "tf32", "f16x2"):
+            raise ValueError("precision must be 'fp64', 'tf32' or 'f16x2'")
         self._precision = precision
 
         # one process per GPU; contiguous particle ranges (gpmdm_b200/sharding.py)
@@ -104,7 +105,7 @@ class GPMDM_PF:
         self._lo, self._hi = sharding.particle_range(self._num_particles, self._world, self._rank)
 
         self._packed = gpmdm.packed_models(self._tri, with_obs_L=(precision == "fp64"))
-        self._packed_tf32 = gpmdm.packed_model_tf32() if precision == "tf32" else None
+        self._packed_tf32 = gpmdm.packed_model_tf32(precision) if precision != "fp64" else None
         c32 = float(0.5 * self._gpmdm.D * _LOG_2PI)  # fp32 product, as gpmdm_pf.py:191
         self._ll_const = self._packed["ll_const_terms"] - c32
         # the mode is chosen from the TOTAL particle count: the two decompositions sum over k in different orders, so a
@@ -276,10 +277,14 @@ class GPMDM_PF:
         if prof is not None:  # bench.py: CUDA events around the dominant kernel, on the launching stream
             ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
             ev[0].record()
-        if self._precision == "tf32":
-            # variances: tcgen05 (3 x tf32, whitened form); means + log-likelihood: fp64 on the alpha tile only
-            check(lib.gpmdm_pf_observe_tf32(ctypes.byref(self._packed_tf32["model"]), ptr(x_new_l), Pl, None, 0.0, None,
-                                            None, ptr(self._v_buf), ptr(self._counter), st), "gpmdm_pf_observe_tf32")
+        if self._precision != "fp64":
+            # variances: tcgen05 (3 x tf32 or 2 x fp16 split, whitened form); means + log-likelihood: fp64 on the alpha tile only
+            if self._precision == "tf32":
+                check(lib.gpmdm_pf_observe_tf32(ctypes.byref(self._packed_tf32["model"]), ptr(x_new_l), Pl, None, 0.0, None,
+                                                None, ptr(self._v_buf), ptr(self._counter), st), "gpmdm_pf_observe_tf32")
+            else:
+                check(lib.gpmdm_pf_observe_f16x2(ctypes.byref(self._packed_tf32["model"]), ptr(x_new_l), Pl, ptr(self._v_buf),
+                                                 ptr(self._counter), st), "gpmdm_pf_observe_f16x2")
             check(lib.gpmdm_pf_loglik_f64(ctypes.byref(self._packed["obs"]), ptr(x_new_l), Pl, ptr(z), self._ll_const,
                                           ptr(self._v_buf), ptr(ll_l), None, ptr(self._counter), st),
                   "gpmdm_pf_loglik_f64")
@@ -381,7 +386,7 @@ class GPMDM_PF:
         if self._small:
             return 6  # pre, propagate (items + finalise), observe (items + finalise), post -- the query is a read
         draws, transition, bucket, propagate, normalize, resample, summaries = 2, 1, 3, 1, 5, 1, 4
-        observe = 2 if (self._precision == "tf32" or self._lowlat) else 1
+        observe = 2 if (self._precision != "fp64" or self._lowlat) else 1
         propagate = 2 if self._lowlat else 1
         cdf = 2 if self._cdf_mode == 0 else 3
         return draws + transition + bucket + propagate + observe + normalize + cdf + resample + summaries

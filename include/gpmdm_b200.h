@@ -248,6 +248,18 @@ int gpmdm_pack_alpha_tf32(const double* alpha, int64_t n, int64_t n_pad, int32_t
 int gpmdm_pf_observe_tf32(const gpmdm_gp_model_tf32* obs, const double* x, int64_t P, const double* z, double ll_const,
                           double* ll, double* mu_out, double* v_out, int32_t* tile_counter, void* stream);
 
+/* ---- fp16-split variant of the same kernel (precision "f16x2"): every operand as TWO fp16 pieces, a = hi + 2^-11 lo
+ * (the scaling keeps the residual inside fp16's exponent range; requires |W| < 6e4, i.e. noise std above ~2e-5), three
+ * kind::f16 MMAs per k-step of 16 into two fp32 TMEM accumulators combined in the epilogue: the same ~22 significant
+ * bits per product as the 3 x tf32 scheme at half the tensor-pipe time and half the operand bytes.  Variances only
+ * (v_out [P]); means and log-likelihoods come from gpmdm_pf_loglik_f64 as in the hybrid tf32 variant.
+ * `obs->wtiles` must point at tiles written by gpmdm_pack_whitened_f16x2 (gpmdm_f16_wtiles_bytes(n_pad) bytes);
+ * `obs->atiles` is not used. */
+int64_t gpmdm_f16_wtiles_bytes(int64_t n_pad);
+int gpmdm_pack_whitened_f16x2(const double* W, int64_t n, int64_t n_pad, void* wtiles, void* stream);
+int gpmdm_pf_observe_f16x2(const gpmdm_gp_model_tf32* obs, const double* x, int64_t P, double* v_out,
+                           int32_t* tile_counter, void* stream);
+
 /* ---- one filter step as two calls (GPMDM_PF._update, gpmdm_pf.py:126-135) ----------------------------------
  * The host-side sequence of the stage entry points above, issued from native code so that a step costs two FFI calls
  * instead of ~twelve (with 100 particles the step is launch-latency bound).  `local` = draws, transition, bucketing,
@@ -331,6 +343,8 @@ int gpmdm_probe_dmma_tflops(int32_t iters, double* tflops_host);
 /* The same for the tf32 variant: sustained tcgen05.mma kind::tf32 (M = 128, N = 256, K = 8, operands resident in shared
  * memory, pseudo-random values) rate of this device, TFLOP/s.  Synchronous. */
 int gpmdm_probe_tf32_tflops(int32_t iters, double* tflops_host);
+/* ... and for kind::f16 (M = 128, N = 256, K = 16). */
+int gpmdm_probe_f16_tflops(int32_t iters, double* tflops_host);
 
 #ifdef __cplusplus
 }

@@ -26,12 +26,14 @@ def particles(spec, P, seed, spread):
     return spec.X[idx] + spread * torch.randn(P, spec.d, dtype=torch.float64, generator=g)
 
 
-@pytest.mark.parametrize("P", [1, 128, 129, 1000])
-def test_tf32_observation_gp_matches_fp64(setup, P):
+@pytest.mark.parametrize("prec", ["tf32", "f16x2"])
+@pytest.mark.parametrize("P", [1, 128, 129, 1000, 40000])
+def test_tf32_observation_gp_matches_fp64(setup, P, prec):
+    """Both tensor-core variants: 3 x tf32 and the fp16 split (a = hi + 2^-11 lo, two accumulators)."""
     spec, wl, model = setup
     xs = particles(spec, P, 3, 0.3).cuda()
     mu64, var64 = model.map_x_to_y(xs)
-    mu32, var32 = model.map_x_to_y(xs, precision="tf32")
+    mu32, var32 = model.map_x_to_y(xs, precision=prec)
     # the hybrid variant keeps the mean contraction in fp64 (same kernel, alpha tile only); the fp64 call above runs in
     # low-latency mode at these sizes (k range split over the SMs), so only the summation order over k differs
     assert float(torch.max(torch.abs(mu32 - mu64) / torch.clamp(mu64.abs().max(dim=1, keepdim=True).values, min=1e-2))) < 1e-12
@@ -43,6 +45,8 @@ def test_tf32_observation_gp_matches_fp64(setup, P):
     ok = v64[:, 0] > 0.05
     if bool(ok.any()):
         assert float(torch.max(torch.abs(v32[ok] - v64[ok]) / v64[ok])) < 1e-3
+    if prec != "tf32":
+        return
     # the all-tensor-core mode: means from tf32 x3 products too (alpha = K^-1 Y cancels, so only ~1e-3 of the row scale)
     mup, varp = model.map_x_to_y(xs, precision="tf32-pure")
     scale = torch.clamp(mu64.abs().max(dim=1, keepdim=True).values, min=1e-2)
@@ -50,7 +54,8 @@ def test_tf32_observation_gp_matches_fp64(setup, P):
     assert torch.equal(varp, var32)
 
 
-def test_tf32_filter_step_log_weights(setup):
+@pytest.mark.parametrize("prec", ["tf32", "f16x2"])
+def test_tf32_filter_step_log_weights(setup, prec):
     from gpmdm_b200 import GPMDM_PF
 
     spec, wl, model = setup
@@ -58,7 +63,7 @@ def test_tf32_filter_step_log_weights(setup):
     T = synthetic.markov_matrix(C)
     P = 2048
     pf64 = GPMDM_PF(model, T, P, seed=5)
-    pf32 = GPMDM_PF(model, T, P, seed=5, precision="tf32")
+    pf32 = GPMDM_PF(model, T, P, seed=5, precision=prec)
     z = wl.test_trials[0][1][0]
     pf64.update(z)
     pf32.update(z)
