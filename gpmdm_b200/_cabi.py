@@ -41,6 +41,7 @@ class PfStepArgs(ctypes.Structure):
                 ("x_new", _ptr), ("c_new", _ptr), ("ll", _ptr),
                 ("perm", _ptr), ("tiles", _ptr), ("n_tiles", _ptr), ("tile_counter", _ptr),
                 ("workspace", _ptr), ("lowlat_workspace", _ptr), ("obs_n_pad", _i64), ("dyn_max_n_pad", _i64),
+                ("obs_seg_chunks", _i32), ("dyn_seg_chunks", _i32),
                 ("kstar_workspace", _ptr), ("kstar_workspace_bytes", _i64),
                 ("lw", _ptr), ("w", _ptr), ("stats", _ptr), ("cdf", _ptr), ("anc", _ptr), ("x_out", _ptr),
                 ("c_out", _ptr)]
@@ -64,11 +65,12 @@ _SIGNATURES = {
                                                    _i64, _ptr, _ptr, _i64, _ptr]),
     "gpmdm_pf_loglik_f64": (ctypes.c_int, [ctypes.POINTER(GpModel), _ptr, _i64, _ptr, _f64, _ptr, _ptr, _ptr, _ptr,
                                            _ptr]),
-    "gpmdm_predict_lowlat_workspace_bytes": (_i64, [_i64, _i64, _i32]),
+    "gpmdm_predict_lowlat_workspace_bytes": (_i64, [_i64, _i64, _i32, _i32]),
+    "gpmdm_predict_lowlat_pick_segment": (_i32, [_i64, _i64, _i32, _i32]),
     "gpmdm_pf_observe_lowlat_f64": (ctypes.c_int, [ctypes.POINTER(GpModel), _ptr, _i64, _ptr, _f64, _ptr, _ptr, _ptr,
-                                                   _ptr, _i64, _ptr, _ptr, _ptr]),
+                                                   _ptr, _i64, _i32, _ptr, _ptr, _ptr]),
     "gpmdm_pf_propagate_lowlat_f64": (ctypes.c_int, [ctypes.POINTER(GpModel), _ptr, _ptr, _ptr, _ptr, _i64, _ptr, _ptr,
-                                                     _ptr, _ptr, _i64, _ptr, _ptr, _ptr]),
+                                                     _ptr, _ptr, _i64, _i32, _ptr, _ptr, _ptr]),
     "gpmdm_pf_step_local_f64": (ctypes.c_int, [ctypes.POINTER(PfStepArgs), _ptr]),
     "gpmdm_pf_step_global_f64": (ctypes.c_int, [ctypes.POINTER(PfStepArgs), _ptr]),
     "gpmdm_pf_small_max_particles": (_i32, []),

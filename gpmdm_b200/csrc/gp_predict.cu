@@ -829,32 +829,61 @@ static int observe_impl(const gpmdm_gp_model* obs, const double* x, int64_t P, c
 }
 
 // ---- low-latency variants: when there are fewer particle tiles than SMs, split every tile's column tiles over CTAs ----
-// k-segment length (in chunks) of the low-latency work items: a sixteenth of the k range, at least 16 chunks -- with one
-// particle tile that is already ~4 items per SM at N = 20 k.  A function of the model size only (not of P or of the
-// device), so that results do not depend on how the particles are sharded.
-static void choose_segments(int64_t max_n_pad, int& seg, int& nseg) {
+// k-segment length (in chunks) of the low-latency work items.  Default rule: a sixteenth of the k range, at least 16 chunks
+// -- a function of the model size only (not of P or of the device), so that results do not depend on how the particles are
+// batched or sharded (GPMDM.map_x_* rely on that).  A caller that knows the whole cloud (the particle filter) may pass
+// an explicit length instead, e.g. from gpmdm_predict_lowlat_pick_segment: results then depend on that choice only through
+// the summation order over k.
+static void choose_segments(int64_t max_n_pad, int32_t seg_chunks, int& seg, int& nseg) {
     const long long nkc = max_n_pad / KC;
-    long long sg = (nkc + 15) / 16;
-    sg = sg < 16 ? 16 : sg;
+    long long sg = seg_chunks > 0 ? seg_chunks : (nkc + 15) / 16;
+    if (seg_chunks <= 0) sg = sg < 16 ? 16 : sg;
     sg = sg > nkc ? nkc : sg;
     seg = (int)sg;
     nseg = (int)((nkc + sg - 1) / sg);
 }
 
-extern "C" int64_t gpmdm_predict_lowlat_workspace_bytes(int64_t P, int64_t max_n_pad, int32_t dout) {
+extern "C" int64_t gpmdm_predict_lowlat_workspace_bytes(int64_t P, int64_t max_n_pad, int32_t dout, int32_t seg_chunks) {
     int seg, nseg;
-    choose_segments(max_n_pad, seg, nseg);
+    choose_segments(max_n_pad, seg_chunks, seg, nseg);
     return ((max_n_pad / TN) * P + P * (int64_t)dout) * nseg * 8;
 }
 
+// Segment length that minimises the modelled makespan of the item grid of ONE launch on this device: `n_tiles` particle
+// tiles against a block of n_pad rows (alpha_ld / 256 mean tiles) -- waves of #SMs items, each item costing its chunks
+// (~2.5 us per [16 x 256] chunk at the uncached DMMA rate) plus a fixed ~8 us (item fetch, first TMA round trip, Hadamard
+// epilogue, partial-sum writes).  With 100 particles and N = 2000 it turns 88 items of 16 chunks (148 SMs: 60 % busy, 57 us)
+// into 148 items of 10.
+extern "C" int32_t gpmdm_predict_lowlat_pick_segment(int64_t n_tiles, int64_t n_pad, int32_t alpha_ld, int32_t tri) {
+    if (n_tiles <= 0 || n_pad <= 0 || n_pad % TN != 0) return 0;
+    const long long nkc = n_pad / KC, nq = n_pad / TN, na = alpha_ld / TN;
+    int dflt, nseg_d;
+    choose_segments(n_pad, 0, dflt, nseg_d);
+    const double t_chunk = 2.5, t_item = 8.0;
+    double best = 1e300;
+    int best_seg = dflt;
+    for (long long sg = dflt; sg >= 4; sg--) {
+        long long items = na * ((nkc + sg - 1) / sg);
+        for (long long J = 0; J < nq; J++) {
+            const long long len = tri ? (nq - J) * (TN / KC) : nkc;
+            items += (len + sg - 1) / sg;
+        }
+        items *= n_tiles;
+        const long long waves = (items + num_sms() - 1) / num_sms();
+        const double t = waves * (sg * t_chunk + t_item);
+        if (t < best - 1e-9) best = t, best_seg = (int)sg;
+    }
+    return best_seg;
+}
+
 template <int KIND>
-static int run_split(PredictParams& prm, int64_t max_n_pad, void* workspace, cudaStream_t st) {
+static int run_split(PredictParams& prm, int64_t max_n_pad, int32_t seg_chunks, void* workspace, cudaStream_t st) {
     GPMDM_REQUIRE(workspace != nullptr && max_n_pad > 0 && max_n_pad % TN == 0, GPMDM_E_INVALID,
                   "low-latency mode needs a workspace and max_n_pad (multiple of %d)", TN);
     const int max_nq = (int)(max_n_pad / TN);
     prm.split = 1;
     prm.max_nct = max_nq + prm.alpha_ld / TN;
-    choose_segments(max_n_pad, prm.seg_chunks, prm.nseg);
+    choose_segments(max_n_pad, seg_chunks, prm.seg_chunks, prm.nseg);
     prm.qpart = static_cast<double*>(workspace);
     prm.mu_ws = prm.qpart + (long long)max_nq * prm.nseg * prm.P;
     // segments a (smaller) block does not have contribute zeros
@@ -871,8 +900,8 @@ static int run_split(PredictParams& prm, int64_t max_n_pad, void* workspace, cud
 
 extern "C" int gpmdm_pf_observe_lowlat_f64(const gpmdm_gp_model* obs, const double* x, int64_t P, const double* z,
                                            double ll_const, const double* v_in, double* ll, double* mu_out,
-                                           double* v_out, int64_t max_n_pad, int32_t* tile_counter, void* workspace,
-                                           void* stream) {
+                                           double* v_out, int64_t max_n_pad, int32_t seg_chunks, int32_t* tile_counter,
+                                           void* workspace, void* stream) {
     if (int rc = validate_model(obs, 0)) return rc;
     GPMDM_REQUIRE(P >= 0 && P < (1ll << 31), GPMDM_E_INVALID, "P = %lld out of range", (long long)P);
     if (P == 0) return 0;
@@ -891,13 +920,13 @@ extern "C" int gpmdm_pf_observe_lowlat_f64(const gpmdm_gp_model* obs, const doub
     prm.ll = ll;
     prm.mu_out = mu_out;
     prm.v_out = v_out;
-    return run_split<0>(prm, max_n_pad, workspace, (cudaStream_t)stream);
+    return run_split<0>(prm, max_n_pad, seg_chunks, workspace, (cudaStream_t)stream);
 }
 
 extern "C" int gpmdm_pf_propagate_lowlat_f64(const gpmdm_gp_model* dyn, const double* x_prev, const int32_t* perm,
                                              const int32_t* tiles, const int32_t* n_tiles, int64_t P, const double* eps,
                                              double* x_new, double* mean_out, double* var_out, int64_t max_n_pad,
-                                             int32_t* tile_counter, void* workspace, void* stream) {
+                                             int32_t seg_chunks, int32_t* tile_counter, void* workspace, void* stream) {
     if (int rc = validate_model(dyn, 1)) return rc;
     GPMDM_REQUIRE(P >= 0 && P < (1ll << 31), GPMDM_E_INVALID, "P = %lld out of range", (long long)P);
     if (P == 0) return 0;
@@ -917,5 +946,5 @@ extern "C" int gpmdm_pf_propagate_lowlat_f64(const gpmdm_gp_model* dyn, const do
     prm.x_new = x_new;
     prm.mean_out = mean_out;
     prm.var_out = var_out;
-    return run_split<1>(prm, max_n_pad, workspace, (cudaStream_t)stream);
+    return run_split<1>(prm, max_n_pad, seg_chunks, workspace, (cudaStream_t)stream);
 }

@@ -71,7 +71,7 @@ struct __align__(1024) Smem {
 };
 
 struct Params {
-    const float* coords;   // [n_pad / 2, CREC, 2]: pairs of training rows interleaved per coordinate
+    const float* coords;   // [n_pad / 2, CREC, 2]: pairs of training rows interleaved per coordinate, x sqrt(log2 e) / l
     const float* wtiles;   // packed W tiles
     const float* atiles;   // packed alpha tiles
     int n_pad, d, dout;
@@ -152,6 +152,12 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// 2^x, one MUFU.EX2 (results below 2^-126 flush to zero: a cross-kernel entry of 1e-38 is zero for every purpose here)
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 __device__ __forceinline__ float to_tf32(float x) {
     uint32_t r;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
@@ -307,7 +313,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) observe_tf32_kernel(const Params 
         // ===================== K* generators =====================
         const int gt = tid - GEN_WARP0 * 32;
         const int row = gt & (TM - 1), khalf = gt >> 7;  // KCm / 2 consecutive k per thread
-        constexpr float LOG2E = 1.4426950408889634f;
+        // exp(-|a - b|^2) = 2^(-|s a - s b|^2), s = sqrt(log2 e): the training coordinates arrive pre-scaled by s
+        // (GPMDM.packed_model_tf32) and the particle's are scaled here, so a K* entry is the distance + ONE ex2.approx
+        constexpr double SQRT_LOG2E = 1.2011224087864498;
         constexpr int KPT = KCm / 2;                     // k per thread and chunk: 8 (tf32) / 16 (fp16)
         uint32_t g = 0;
         for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
@@ -317,7 +325,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) observe_tf32_kernel(const Params 
             float2 nb[DL];
 #pragma unroll
             for (int j = 0; j < DL; j++) {
-                const float bj = (float)(prm.x[p * DL + j] / prm.ls[j]);
+                const float bj = (float)(prm.x[p * DL + j] / prm.ls[j] * SQRT_LOG2E);
                 nb[j] = make_float2(-bj, -bj);
             }
             for (int ct = 0; ct < nct; ct++) {
@@ -343,8 +351,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) observe_tf32_kernel(const Params 
                             const float2 tdiff = __fadd2_rn(a[j], nb[j]);
                             dist = __ffma2_rn(tdiff, tdiff, dist);
                         }
-                        kv[kk] = exp2f(-LOG2E * dist.x);
-                        kv[kk + 1] = exp2f(-LOG2E * dist.y);
+                        kv[kk] = ex2_approx(-dist.x);
+                        kv[kk + 1] = ex2_approx(-dist.y);
                     }
                     wait(&s.a_empty[sa], ((g / ASTAGES) & 1) ^ 1);
                     if (F16) {
@@ -353,16 +361,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) observe_tf32_kernel(const Params 
                         __half* al = reinterpret_cast<__half*>(&s.A[sa][1][0]);
 #pragma unroll
                         for (int q = 0; q < KPT / 8; q++) {
-                            __align__(16) __half hi[8], lo[8];
+                            // packed conversions (two values per F2FP): scalar fp32 <-> fp16 conversions run at a
+                            // fraction of the rate and would bound the kernel at this chunk rate
+                            __half2 hi[4], lo[4];
 #pragma unroll
-                            for (int i = 0; i < 8; i++) {
-                                const float kvi = kv[q * 8 + i];
-                                hi[i] = __float2half_rn(kvi);
-                                lo[i] = __float2half_rn((kvi - __half2float(hi[i])) * 2048.f);
+                            for (int i = 0; i < 4; i++) {
+                                const float k0 = kv[q * 8 + 2 * i], k1 = kv[q * 8 + 2 * i + 1];
+                                hi[i] = __floats2half2_rn(k0, k1);
+                                const float2 hb = __half22float2(hi[i]);
+                                lo[i] = __floats2half2_rn(fmaf(hb.x, -2048.f, k0 * 2048.f), fmaf(hb.y, -2048.f, k1 * 2048.f));
                             }
                             const int idx = tile_index<MODE>(row, khalf * KPT + q * 8);
-                            *reinterpret_cast<uint4*>(ah + idx) = *reinterpret_cast<const uint4*>(hi);
-                            *reinterpret_cast<uint4*>(al + idx) = *reinterpret_cast<const uint4*>(lo);
+                            *reinterpret_cast<uint4*>(ah + idx) = make_uint4(*reinterpret_cast<uint32_t*>(&hi[0]), *reinterpret_cast<uint32_t*>(&hi[1]),
+                                                                             *reinterpret_cast<uint32_t*>(&hi[2]), *reinterpret_cast<uint32_t*>(&hi[3]));
+                            *reinterpret_cast<uint4*>(al + idx) = make_uint4(*reinterpret_cast<uint32_t*>(&lo[0]), *reinterpret_cast<uint32_t*>(&lo[1]),
+                                                                             *reinterpret_cast<uint32_t*>(&lo[2]), *reinterpret_cast<uint32_t*>(&lo[3]));
                         }
                     } else {
                         float* ah = reinterpret_cast<float*>(&s.A[sa][0][0]);

@@ -134,6 +134,7 @@ __global__ void __launch_bounds__(RT, 1) small_post_kernel(const SmallPostArgs a
     __shared__ double carry;
     __shared__ double wtot[RT / 32][SUMM_COLS];
     __shared__ double cls[SUMM_COLS];
+    __shared__ double sbuf[SMALL_P_MAX + 1];
     const int tid = threadIdx.x;
     const long long P = a.P;
     const int nb = (int)((P + RB - 1) / RB);
@@ -161,17 +162,37 @@ __global__ void __launch_bounds__(RT, 1) small_post_kernel(const SmallPostArgs a
     __syncthreads();
     // ---- cdf (gpmdm_pf.py:211: the running sum of torch.multinomial's CPU kernel, or the blocked scan) ----
     if (a.cdf_mode == 0) {
+        // the reference's running sum is inherently serial: stage the weights in shared memory (coalesced), let one
+        // thread add them there (an L2 round trip per element otherwise: 40 us at P = 100), write back in parallel
+        for (long long i = tid; i < P; i += RT) sbuf[i] = __ldcg(a.w + i);
+        __syncthreads();
         if (tid == 0) {
             double run = 0.0;
-            for (long long i = 0; i < P; i++) {
-                run = __dadd_rn(run, __ldcg(a.w + i));
-                a.cdf[i] = run;
+            long long i = 0;
+            for (; i + 8 <= P; i += 8) {
+                double v[8];
+#pragma unroll
+                for (int k = 0; k < 8; k++) v[k] = sbuf[i + k];
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    run = __dadd_rn(run, v[k]);
+                    sbuf[i + k] = run;
+                }
+            }
+            for (; i < P; i++) {
+                run = __dadd_rn(run, sbuf[i]);
+                sbuf[i] = run;
             }
             scal[2] = run;
+            sbuf[SMALL_P_MAX] = run;
         }
         __syncthreads();
-        const double total = __ldcg(scal + 2);
-        for (long long base = tid * 4; base < P; base += RT * 4) cdf_finish_dev<false>(a.cdf, P, nullptr, total, base);
+        const double total = sbuf[SMALL_P_MAX];
+        for (long long i = tid; i < P; i += RT) {
+            const double c = (i == P - 1) ? 1.0 : sbuf[i] / total;  // as cdf_finish_dev
+            a.cdf[i] = c;
+            sbuf[i] = c;
+        }
     } else {
         for (int vb = 0; vb < nb; vb++) {
             const double t = cdf_block_scan_dev<false>(a.w, P, a.cdf, vb, wsum);
@@ -181,11 +202,20 @@ __global__ void __launch_bounds__(RT, 1) small_post_kernel(const SmallPostArgs a
         const double total = scan_partials_dev<RT, false>(part, nb, wtot32, &carry);
         __syncthreads();
         for (long long base = tid * 4; base < P; base += RT * 4) cdf_finish_dev<false>(a.cdf, P, part, total, base);
+        __syncthreads();
+        for (long long i = tid; i < P; i += RT) sbuf[i] = __ldcg(a.cdf + i);
     }
     __syncthreads();
-    // ---- ancestors + gathers (gpmdm_pf.py:206-213) ----
+    // ---- ancestors + gathers (gpmdm_pf.py:206-213): first j with cdf[j] >= u, searched in the shared-memory copy ----
     for (long long s = tid; s < P; s += RT) {
-        const long long j = cdf_search<false>(a.cdf, P, a.u[s]);
+        const double us = a.u[s];
+        long long lo = 0, hi = P;
+        while (hi - lo > 0) {
+            const long long mid = lo + (hi - lo) / 2;
+            if (sbuf[mid] < us) lo = mid + 1;
+            else hi = mid;
+        }
+        const long long j = lo >= P ? P - 1 : lo;
         a.anc[s] = j;
         for (int k = 0; k < a.d; k++) a.x_out[s * a.d + k] = a.x_new[j * a.d + k];
         a.c_out[s] = a.c_new[j];
@@ -240,9 +270,9 @@ extern "C" int gpmdm_pf_step_small_f64(const gpmdm_pf_step_args* a, uint64_t* st
     small_pre_kernel<<<1, PRE_T, (size_t)a->C * a->C * sizeof(double), st>>>(pre);
     GPMDM_TRY(check_launch("small_pre_kernel"));
     GPMDM_TRY(gpmdm_pf_propagate_lowlat_f64(a->dyn, a->x_prev, a->perm, a->tiles, a->n_tiles, P, a->eps, a->x_new, nullptr,
-                                            nullptr, a->dyn_max_n_pad, a->tile_counter, a->lowlat_workspace, stream));
+                                            nullptr, a->dyn_max_n_pad, a->dyn_seg_chunks, a->tile_counter, a->lowlat_workspace, stream));
     GPMDM_TRY(gpmdm_pf_observe_lowlat_f64(a->obs, a->x_new, P, a->z, a->ll_const, nullptr, a->ll, nullptr, nullptr,
-                                          a->obs_n_pad, a->tile_counter, a->lowlat_workspace, stream));
+                                          a->obs_n_pad, a->obs_seg_chunks, a->tile_counter, a->lowlat_workspace, stream));
     SmallPostArgs post{};
     post.P = P, post.C = a->C, post.d = a->d, post.cdf_mode = a->cdf_mode;
     post.ll = a->ll, post.u = a->u, post.x_new = a->x_new, post.c_new = a->c_new;

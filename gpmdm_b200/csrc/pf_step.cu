@@ -31,9 +31,9 @@ extern "C" int gpmdm_pf_step_local_f64(const gpmdm_pf_step_args* a, void* stream
     GPMDM_TRY(gpmdm_pf_bucket_by_class(c_new, n, C, a->perm, a->tiles, a->n_tiles, a->workspace, stream));
     if (a->predict_mode == 2) {
         GPMDM_TRY(gpmdm_pf_propagate_lowlat_f64(a->dyn, a->x_prev, a->perm, a->tiles, a->n_tiles, n, a->eps, x_new, nullptr,
-                                                nullptr, a->dyn_max_n_pad, a->tile_counter, a->lowlat_workspace, stream));
+                                                nullptr, a->dyn_max_n_pad, a->dyn_seg_chunks, a->tile_counter, a->lowlat_workspace, stream));
         GPMDM_TRY(gpmdm_pf_observe_lowlat_f64(a->obs, x_new, n, a->z, a->ll_const, nullptr, ll, nullptr, nullptr,
-                                              a->obs_n_pad, a->tile_counter, a->lowlat_workspace, stream));
+                                              a->obs_n_pad, a->obs_seg_chunks, a->tile_counter, a->lowlat_workspace, stream));
     } else {
         GPMDM_TRY(gpmdm_pf_propagate_f64(a->dyn, a->x_prev, a->perm, a->tiles, a->n_tiles, n, a->eps, x_new, nullptr, nullptr,
                                          a->tile_counter, stream));

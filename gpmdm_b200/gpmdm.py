@@ -801,7 +801,7 @@ class GPMDM(torch.nn.Module):
             at = torch.empty(int(lib.gpmdm_tf32_atiles_bytes(n_pad)) // 4, dtype=torch.float32, device=self.device)
             check(lib.gpmdm_pack_alpha_tf32(ptr(self._obs_blk["A"]), n, n_pad, self.D, ptr(at), stream()), "gpmdm_pack_alpha_tf32")
         coords = torch.zeros(n_pad, 8, dtype=torch.float32, device=self.device)
-        coords[:n, :d] = (X / torch.exp(self._d("y_log_lengthscales"))).to(torch.float32)
+        coords[:n, :d] = (X / torch.exp(self._d("y_log_lengthscales")) * 1.2011224087864498).to(torch.float32)  # sqrt(log2 e)
         coords = coords.view(n_pad // 2, 2, 8).transpose(1, 2).contiguous()  # [pair][coordinate][row in pair]
         ls = torch.exp(self._d("y_log_lengthscales")).contiguous()
         lam2 = (torch.exp(self._d("y_log_lambdas")) ** 2).contiguous()
@@ -827,7 +827,7 @@ class GPMDM(torch.nn.Module):
         return buf
 
     def _lowlat_workspace(self, P, max_n_pad, dout):
-        need = int(_cabi.lib().gpmdm_predict_lowlat_workspace_bytes(P, max_n_pad, dout)) // 8 + 1
+        need = int(_cabi.lib().gpmdm_predict_lowlat_workspace_bytes(P, max_n_pad, dout, 0)) // 8 + 1
         return self._stream_scratch("lowlat", need, torch.float64)
 
     # ---- prediction (gpmdm.py:923-963, 1032-1068) ----------------------------------------------------------
@@ -878,7 +878,7 @@ class GPMDM(torch.nn.Module):
             if P > 0 and self._use_lowlat(P, low_latency):
                 ws = self._lowlat_workspace(P, pk["obs_n_pad"], self.D)
                 check(lib.gpmdm_pf_observe_lowlat_f64(ctypes.byref(pk["obs"]), ptr(Xs), P, None, 0.0, None, None, ptr(mu),
-                                                      ptr(v), pk["obs_n_pad"], ptr(self._scratch_counter()), ptr(ws),
+                                                      ptr(v), pk["obs_n_pad"], 0, ptr(self._scratch_counter()), ptr(ws),
                                                       stream()), "gpmdm_pf_observe_lowlat_f64")
             elif P > 0 and self._use_kstar_cache(pk["obs_n_pad"], kstar_cache):
                 ws = self._kstar_workspace(pk["obs_n_pad"])
@@ -916,7 +916,7 @@ class GPMDM(torch.nn.Module):
         if self._use_lowlat(P, low_latency):
             ws = self._lowlat_workspace(P, pk["dyn_max_n_pad"], self.d)
             check(lib.gpmdm_pf_propagate_lowlat_f64(ctypes.byref(pk["dyn"]), ptr(Xs), ptr(perm), ptr(tiles), ptr(n_tiles),
-                                                    P, None, None, ptr(mean), ptr(var), pk["dyn_max_n_pad"],
+                                                    P, None, None, ptr(mean), ptr(var), pk["dyn_max_n_pad"], 0,
                                                     ptr(self._scratch_counter()), ptr(ws), stream()),
                   "gpmdm_pf_propagate_lowlat_f64")
         else:

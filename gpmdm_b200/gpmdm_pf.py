@@ -148,11 +148,26 @@ class GPMDM_PF:
             self._z_pin = [torch.empty(self.observation_dim, dtype=f64).pin_memory() for _ in range(4)]
             self._z_ev = [None] * 4
             self._z_slot = 0
+            # graph mode: the observation's host-to-device copy and the summaries' device-to-host copy are nodes of the
+            # graph (one pinned buffer each; `_graph_done` orders their reuse), so a frame is ONE launch from the host
+            self._z_graph_pin = torch.empty(self.observation_dim, dtype=f64).pin_memory()
+            self._summary_pin = torch.zeros(C + d + 1, dtype=f64).pin_memory()
+            self._graph_done = torch.cuda.Event()
+            self._summary_host_step = -1
         ws = int(self._lib.gpmdm_workspace_bytes(P, C))
         self._ws = torch.empty(ws // 8 + 1, dtype=torch.float64, device=dev)
+        self._seg_obs = self._seg_dyn = 0
         if self._lowlat:
-            need = max(int(self._lib.gpmdm_predict_lowlat_workspace_bytes(Pl, self._packed["obs_n_pad"], self.observation_dim)),
-                       int(self._lib.gpmdm_predict_lowlat_workspace_bytes(Pl, self._packed["dyn_max_n_pad"], d)))
+            # k-segment lengths of the low-latency work items, chosen ONCE from the whole cloud (all ranks agree) so that
+            # the item grid fills the SMs in whole waves; a fixed function of (P, C, model sizes)
+            tiles = (P + _cabi.TILE_P - 1) // _cabi.TILE_P
+            # (from the TOTAL particle count, never from this rank's share: the choice fixes the summation order over k)
+            self._seg_obs = int(self._lib.gpmdm_predict_lowlat_pick_segment(tiles, self._packed["obs_n_pad"], _cabi.TILE_N,
+                                                                            int(self._tri)))
+            self._seg_dyn = int(self._lib.gpmdm_predict_lowlat_pick_segment(max(tiles, min(C, P)), self._packed["dyn_max_n_pad"],
+                                                                            _cabi.TILE_N, int(self._tri)))
+            need = max(int(self._lib.gpmdm_predict_lowlat_workspace_bytes(Pl, self._packed["obs_n_pad"], self.observation_dim, self._seg_obs)),
+                       int(self._lib.gpmdm_predict_lowlat_workspace_bytes(Pl, self._packed["dyn_max_n_pad"], d, self._seg_dyn)))
             self._ws_lowlat = torch.empty(need // 8 + 1, dtype=torch.float64, device=dev)
         # scratch is owned by the filter instance (two filters on one model may run on different streams)
         self._ws_kstar = None
@@ -171,6 +186,7 @@ class GPMDM_PF:
             a.workspace = ptr(self._ws)
             a.lowlat_workspace = ptr(self._ws_lowlat) if self._lowlat else None
             a.obs_n_pad, a.dyn_max_n_pad = self._packed["obs_n_pad"], self._packed["dyn_max_n_pad"]
+            a.obs_seg_chunks, a.dyn_seg_chunks = self._seg_obs, self._seg_dyn
             a.kstar_workspace = ptr(self._ws_kstar) if self._kstar_cache else None
             a.kstar_workspace_bytes = self._ws_kstar.numel() * 8 if self._kstar_cache else 0
             a.stats, a.cdf, a.anc = ptr(self._stats), ptr(self._cdf), ptr(self._anc)
@@ -201,13 +217,15 @@ class GPMDM_PF:
         self._log_likelihoods = torch.zeros(P, dtype=torch.float64, device=self.device)
         self._log_weights = torch.zeros(P, dtype=torch.float64, device=self.device)
         self._weights = torch.ones(P, dtype=torch.float64, device=self.device) / P
-        self._summary_step = -1
+        self._summary_step = self._summary_host_step = -1
 
     # ---- the filter step (gpmdm_pf.py:117-135) -----------------------------------------------------------------
     def update(self, z, draws=None):
         """Update the particle filter with a new observation z [D] (numpy / sequence / tensor).
         draws: optional (E [P,C] Exp(1), eps [P,d] N(0,1), u [P] U(0,1)) raw draws for ALL particles."""
         if self._small and not (isinstance(z, torch.Tensor) and z.is_cuda):
+            if draws is None and self._use_graph and self._small_steps >= 2 and getattr(self, "_profile_events", None) is None:
+                return self._replay_small(z)
             return self._update(self._stage_z(z), draws)
         z = torch.as_tensor(np.asarray(z) if not isinstance(z, torch.Tensor) else z).to(device=self.device, dtype=torch.float64)
         self._update(z.contiguous(), draws)
@@ -267,7 +285,7 @@ class GPMDM_PF:
         if self._lowlat:
             check(lib.gpmdm_pf_propagate_lowlat_f64(ctypes.byref(self._packed["dyn"]), ptr(x_prev), ptr(self._perm),
                                                     ptr(self._tiles), ptr(self._n_tiles), Pl, ptr(eps), ptr(x_new_l), None,
-                                                    None, self._packed["dyn_max_n_pad"], ptr(self._counter),
+                                                    None, self._packed["dyn_max_n_pad"], self._seg_dyn, ptr(self._counter),
                                                     ptr(self._ws_lowlat), st), "gpmdm_pf_propagate_lowlat_f64")
         else:
             check(lib.gpmdm_pf_propagate_f64(ctypes.byref(self._packed["dyn"]), ptr(x_prev), ptr(self._perm),
@@ -291,7 +309,7 @@ class GPMDM_PF:
         elif self._lowlat:
             check(lib.gpmdm_pf_observe_lowlat_f64(ctypes.byref(self._packed["obs"]), ptr(x_new_l), Pl, ptr(z),
                                                   self._ll_const, None, ptr(ll_l), None, None, self._packed["obs_n_pad"],
-                                                  ptr(self._counter), ptr(self._ws_lowlat), st),
+                                                  self._seg_obs, ptr(self._counter), ptr(self._ws_lowlat), st),
                   "gpmdm_pf_observe_lowlat_f64")
         elif self._kstar_cache:
             check(lib.gpmdm_pf_observe_cached_f64(ctypes.byref(self._packed["obs"]), ptr(x_new_l), Pl, ptr(z),
@@ -362,23 +380,50 @@ class GPMDM_PF:
             self._z_buf.copy_(z)
         if self._step_dev_host != self._step:  # keeps the device step key equal to the host's (reset(), injected draws)
             self._step_dev.fill_(self._step)
-        if generate and self._use_graph and self._small_steps >= 2:
-            if self._graphs[par] is None:  # every kernel has run at least once (function attributes are set): capture
-                g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g):
-                    self._issue_small(par, True, self._E, self._eps, self._u)
-                self._graphs[par] = g
-            self._graphs[par].replay()
-        else:
-            self._issue_small(par, generate, E, eps, u)
+        self._issue_small(par, generate, E, eps, u)
+        self._finish_small(par)
+
+    def _replay_small(self, z):
+        """One frame = one graph launch: [H2D z] -> pre -> dynamics GP -> observation GP -> post -> [D2H summaries]."""
+        par = self._par
+        if self._particle_states.data_ptr() != self._S[par].data_ptr():
+            self._S[par].copy_(self._particle_states)
+        if self._particle_classes.data_ptr() != self._Cl[par].data_ptr():
+            self._Cl[par].copy_(self._particle_classes)
+        if self._step_dev_host != self._step:
+            self._step_dev.fill_(self._step)
+        src = z if isinstance(z, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(z))
+        if src.numel() != self.observation_dim:
+            raise ValueError("z must have D = %d entries" % self.observation_dim)
+        self._graph_done.synchronize()  # the previous replay has consumed / produced the pinned buffers
+        self._z_graph_pin.copy_(src.reshape(-1))
+        if self._graphs[par] is None:  # every kernel has run at least once (function attributes are set): capture
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._z_buf.copy_(self._z_graph_pin, non_blocking=True)
+                self._issue_small(par, True, self._E, self._eps, self._u)
+                self._summary_pin.copy_(self._summary, non_blocking=True)
+            self._graphs[par] = g
+        self._graphs[par].replay()
+        self._graph_done.record()
+        self._finish_small(par)
+        self._summary_host_step = self._step
+
+    def _finish_small(self, par):
         self._small_steps += 1
         self._step += 1
         self._step_dev_host = self._step
         self._particle_states, self._particle_classes = self._S[1 - par], self._Cl[1 - par]
-        self._x_new_small = None
         self._log_likelihoods, self._log_weights, self._weights = self._LL[par], self._LW[par], self._W[par]
         self._summary_step = self._step  # the post kernel has already written the summaries of this state
         self._par = 1 - par
+
+    def _summary_host(self):
+        """The summaries on the host: already there after a graph replay (pinned buffer written by the graph's last node)."""
+        if self._small and self._summary_host_step == self._step:
+            self._graph_done.synchronize()
+            return self._summary_pin
+        return self._summaries().cpu()
 
     @property
     def launches_per_step(self) -> int:
@@ -407,14 +452,14 @@ class GPMDM_PF:
         return self._summary
 
     def log_likelihood(self) -> float:
-        return self._summaries()[self.num_classes + self.latent_dim].item()
+        return float(self._summary_host()[self.num_classes + self.latent_dim])
 
     def class_probabilities(self):
         return self._summaries()[:self.num_classes].clone()
 
     def get_most_likely_class(self) -> int:
         # one device-to-host read of the class posteriors; argmax on the host (first maximum, as torch.argmax)
-        return int(torch.argmax(self._summaries()[:self.num_classes].cpu()))
+        return int(torch.argmax(self._summary_host()[:self.num_classes]))
 
     def current_state_mean(self):
         C = self.num_classes

@@ -164,15 +164,19 @@ int gpmdm_pf_loglik_f64(const gpmdm_gp_model* obs, const double* x, int64_t P, c
  * of a column tile is cut into (up to) 16 segments, a function of n_pad only -- and the per-item contributions to k^T L k and to
  * the means are added in a fixed order by a second kernel that also runs the epilogue.  Same results contract as the
  * fused calls; only the summation order over k differs (deterministic; independent of P and of the sharding).
- * max_n_pad: largest n_pad over the model's blocks.  workspace: gpmdm_predict_lowlat_workspace_bytes(P, max_n_pad, dout). */
-int64_t gpmdm_predict_lowlat_workspace_bytes(int64_t P, int64_t max_n_pad, int32_t dout);
+ * max_n_pad: largest n_pad over the model's blocks.  seg_chunks: k-segment length in 16-row chunks, 0 = the default rule
+ * (a function of max_n_pad only, so results do not depend on the batch); a caller that knows the whole cloud may pass
+ * gpmdm_predict_lowlat_pick_segment(...) to fill the SMs in whole waves (results depend on the value only through the
+ * summation order over k).  workspace: gpmdm_predict_lowlat_workspace_bytes(P, max_n_pad, dout, seg_chunks). */
+int64_t gpmdm_predict_lowlat_workspace_bytes(int64_t P, int64_t max_n_pad, int32_t dout, int32_t seg_chunks);
+int32_t gpmdm_predict_lowlat_pick_segment(int64_t n_tiles, int64_t n_pad, int32_t alpha_ld, int32_t tri);
 int gpmdm_pf_observe_lowlat_f64(const gpmdm_gp_model* obs, const double* x, int64_t P, const double* z, double ll_const,
                                 const double* v_in, double* ll, double* mu_out, double* v_out, int64_t max_n_pad,
-                                int32_t* tile_counter, void* workspace, void* stream);
+                                int32_t seg_chunks, int32_t* tile_counter, void* workspace, void* stream);
 int gpmdm_pf_propagate_lowlat_f64(const gpmdm_gp_model* dyn, const double* x_prev, const int32_t* perm,
                                   const int32_t* tiles, const int32_t* n_tiles, int64_t P, const double* eps,
                                   double* x_new, double* mean_out, double* var_out, int64_t max_n_pad,
-                                  int32_t* tile_counter, void* workspace, void* stream);
+                                  int32_t seg_chunks, int32_t* tile_counter, void* workspace, void* stream);
 
 /* GPMDM_PF._update_weights (second half, gpmdm_pf.py:200-204): lw = ll - max(ll); w = exp(lw)/sum.
  * Reductions run in a fixed blocked order independent of the GPU count.  stats_out [2] = {max, sum}. */
@@ -221,7 +225,8 @@ int64_t gpmdm_workspace_bytes(int64_t P, int32_t C);
  * WHITENED variance  v = 1 - |W k|^2,  W = U^-T  with K = U^T U the reference's upper Cholesky factor
  * (gpmdm.py:1287-1288): the explicit-inverse form of gpmdm.py:958-959 is not usable below fp64.
  * The dynamics GP, the draws and the resampling stay on the fp64 path.
- *   coords [n_pad/2, 8, 2] fp32  a_i = x_i / lengthscale, zero padded to 8 coordinates, rows interleaved in pairs:
+ *   coords [n_pad/2, 8, 2] fp32  a_i = sqrt(log2 e) * x_i / lengthscale (so that exp(-|a-b|^2) is one ex2 of the squared
+ *                      distance), zero padded to 8 coordinates, rows interleaved in pairs:
  *                      element [i/2][j][i%2] = a_i[j]  (one 64-bit load feeds the packed fp32x2 pipe)
  *   wtiles             tf32 hi/lo tiles of W in tensor-core operand order (gpmdm_pack_whitened_tf32)
  *   atiles             tf32 hi/lo tiles of alpha = K^-T Y                 (gpmdm_pack_alpha_tf32)            */
@@ -294,6 +299,7 @@ typedef struct gpmdm_pf_step_args {
     void* workspace;            /* gpmdm_workspace_bytes(P, C)                                              */
     void* lowlat_workspace;     /* predict_mode 2                                                           */
     int64_t obs_n_pad, dyn_max_n_pad;
+    int32_t obs_seg_chunks, dyn_seg_chunks; /* predict_mode 2: k-segment lengths (0 = default rule)                 */
     void* kstar_workspace;      /* predict_mode 1                                                           */
     int64_t kstar_workspace_bytes;
     double* lw;                 /* [P] outputs of `global`                                                  */

@@ -67,11 +67,12 @@ def test_guard_bands_survive_every_predict_mode(small, P):
     x_new, mean, var = G("x_new", P * d), G("dyn_mean", P * d), G("dyn_var", P * d)
     check(lib.gpmdm_pf_propagate_f64(ctypes.byref(pk["dyn"]), ptr(xs), ptr(perm), ptr(tiles), ptr(n_tiles), P, ptr(eps),
                                      ptr(x_new), ptr(mean), ptr(var), ptr(counter), stream()), "propagate")
-    ll_ws = G("lowlat_ws", max(int(lib.gpmdm_predict_lowlat_workspace_bytes(P, pk["dyn_max_n_pad"], d)),
-                               int(lib.gpmdm_predict_lowlat_workspace_bytes(P, pk["obs_n_pad"], D))) // 8)
+    seg = 0 if P % 2 else 5  # the default segmentation rule, and an explicit (short) segment length
+    ll_ws = G("lowlat_ws", max(int(lib.gpmdm_predict_lowlat_workspace_bytes(P, pk["dyn_max_n_pad"], d, seg)),
+                               int(lib.gpmdm_predict_lowlat_workspace_bytes(P, pk["obs_n_pad"], D, seg))) // 8)
     x_new2 = G("x_new_lowlat", P * d)
     check(lib.gpmdm_pf_propagate_lowlat_f64(ctypes.byref(pk["dyn"]), ptr(xs), ptr(perm), ptr(tiles), ptr(n_tiles), P,
-                                            ptr(eps), ptr(x_new2), None, None, pk["dyn_max_n_pad"], ptr(counter), ptr(ll_ws),
+                                            ptr(eps), ptr(x_new2), None, None, pk["dyn_max_n_pad"], seg, ptr(counter), ptr(ll_ws),
                                             stream()), "propagate lowlat")
     # observation: fused, cached, low latency
     outs = []
@@ -88,7 +89,7 @@ def test_guard_bands_survive_every_predict_mode(small, P):
                                                   pk["obs_n_pad"], ptr(counter), ptr(kws), kws.numel() * 8, stream()), mode)
         else:
             check(lib.gpmdm_pf_observe_lowlat_f64(ctypes.byref(pk["obs"]), ptr(xs), P, ptr(z), 0.5, None, ptr(ll), ptr(mu),
-                                                  ptr(v), pk["obs_n_pad"], ptr(counter), ptr(ll_ws), stream()), mode)
+                                                  ptr(v), pk["obs_n_pad"], seg, ptr(counter), ptr(ll_ws), stream()), mode)
         outs.append((ll.clone(), mu.clone(), v.clone()))
     # stages
     lw, w, cdf, stats = G("lw", P), G("w", P), G("cdf", P), G("stats", 2)
