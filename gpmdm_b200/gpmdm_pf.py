@@ -303,6 +303,9 @@ class GPMDM_PF:
             else:
                 check(lib.gpmdm_pf_observe_f16x2(ctypes.byref(self._packed_tf32["model"]), ptr(x_new_l), Pl, ptr(self._v_buf),
                                                  ptr(self._counter), st), "gpmdm_pf_observe_f16x2")
+            if prof is not None:  # the tensor-core kernel alone (the fp64 mean tile follows)
+                ev = ev + (torch.cuda.Event(enable_timing=True),)
+                ev[2].record()
             check(lib.gpmdm_pf_loglik_f64(ctypes.byref(self._packed["obs"]), ptr(x_new_l), Pl, ptr(z), self._ll_const,
                                           ptr(self._v_buf), ptr(ll_l), None, ptr(self._counter), st),
                   "gpmdm_pf_loglik_f64")
