@@ -49,11 +49,16 @@ def _worker(rank, world_size, port, P, steps, seed, out_path):
 
 
 @pytest.mark.timeout(600)
+@pytest.mark.parametrize("P", [4096, 8192, 20480])
 @pytest.mark.parametrize("world_size", [2])
-def test_sharded_filter_is_bitwise_equal_to_single_gpu(tmp_path, world_size):
+def test_sharded_filter_is_bitwise_equal_to_single_gpu(tmp_path, world_size, P):
+    """P = 4096: low-latency mode on both sides (and the single-GPU side takes the small-cloud kernels); P = 8192: 128
+    tiles in all, 64 per rank -- the mode is chosen from the TOTAL particle count, so both sides run the fused kernels
+    (a per-rank choice would have put the 2-GPU run in low-latency mode, with another summation order over k);
+    P = 20 480: several tiles per SM on one GPU, fewer than SMs per rank on two."""
     if torch.cuda.device_count() < world_size:
         pytest.skip(f"needs {world_size} GPUs")
-    P, steps, seed = 4096, 4, 21
+    steps, seed = 4, 21
     out = os.path.join(tmp_path, "multi.pt")
     mp.spawn(_worker, args=(world_size, _free_port(), P, steps, seed, out), nprocs=world_size, join=True)
     multi = torch.load(out)
