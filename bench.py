@@ -242,15 +242,17 @@ def parity_block(pf, model, o, last, T):
         dv = max(dv, float(((var.cpu() - tr["dyn_var"][rows]).abs() / prior).max()))
     # integer stages on the oracle's own inputs: class transition, normalise + sequential cdf + search
     c_new = torch.empty(n, dtype=torch.int64, device=dev)
-    check(lib.gpmdm_pf_transition_f64(ptr(cu(last["c_prev"])), ptr(cu(T.to(f64))), ptr(cu(last["E"])), n, C, ptr(c_new),
-                                      stream()), "gpmdm_pf_transition_f64")
+    # (device copies are bound to names: a temporary would be returned to the allocator -- and possibly handed to the next
+    # argument's copy -- before the asynchronous kernel has read it)
+    c_prev_d, T_d, E_d, u_d = cu(last["c_prev"]), cu(T.to(f64)), cu(last["E"]), cu(last["u"])
+    check(lib.gpmdm_pf_transition_f64(ptr(c_prev_d), ptr(T_d), ptr(E_d), n, C, ptr(c_new), stream()), "gpmdm_pf_transition_f64")
     ws = torch.empty(int(lib.gpmdm_workspace_bytes(n, C)) // 8 + 1, dtype=f64, device=dev)
     lw, w, cdf, st2 = (torch.empty(n, dtype=f64, device=dev) for _ in range(4))
     anc = torch.empty(n, dtype=torch.int64, device=dev)
     ll_o = cu(tr["ll"])
     check(lib.gpmdm_pf_normalize_f64(ptr(ll_o), n, ptr(lw), ptr(w), ptr(st2), ptr(ws), stream()), "gpmdm_pf_normalize_f64")
     check(lib.gpmdm_pf_cdf_f64(ptr(w), n, 0, ptr(cdf), ptr(ws), stream()), "gpmdm_pf_cdf_f64")
-    check(lib.gpmdm_pf_resample_f64(ptr(cdf), n, ptr(cu(last["u"])), n, None, None, d, ptr(anc), None, None, stream()),
+    check(lib.gpmdm_pf_resample_f64(ptr(cdf), n, ptr(u_d), n, None, None, d, ptr(anc), None, None, stream()),
           "gpmdm_pf_resample_f64")
     return {
         "against": "CPU oracle (oracle/gpmdm_oracle.py, pinned to the unmodified reference by tests/golden), its last step",

@@ -4,7 +4,8 @@
 // get_weighted_distances / get_lin_kernel), the dense 0/1 class masks of :311-378 (`* self.M`,
 // :616, :1292) and the autograd backward through those ops.  The O(N^3) factorisation stays with
 // torch.linalg (cuSOLVER); these kernels are HBM-bound: the build writes 8 N^2 bytes, the gradient
-// reads G twice (16 N^2 bytes: once row-wise, once as coalesced 256-byte column segments).
+// reads G once (8 N^2 bytes: each pair of mirror-image tiles is visited by one block, row-wise and as coalesced
+// 256-byte column segments).
 #include <math.h>
 
 #include "common.cuh"
@@ -111,28 +112,42 @@ __global__ void __launch_bounds__(256) kernel_build_kernel(const double* __restr
     }
 }
 
-// Gradient terms.  Block (b, s) owns rows [32 b, 32 b + 32) and walks column split s of the (class-restricted) column
-// range.   partX [NS][n][d]: per-split row sums;  part [nblk * NS][2 d + 2]: per-block partials of g_log_ls[d],
-// tr(G^), g_log_c[d+1].  A second kernel adds the splits / blocks in a fixed order.
+// Gradient terms.  With S = G^ + G^^T (G^ = G o M) every UNORDERED pair (i, j) contributes to row i and to row j:
+//     dL/dx_i += S_ij [ k_rbf (-2 D_ij / l^2) + c^2 x_j ]        dL/dx_j += S_ij [ k_rbf (+2 D_ij / l^2) + c^2 x_i ]
+//     dL/dlog l_k += S_ij k_rbf 2 D_ijk^2 / l_k^2                  dL/dlog c_k += 2 c_k^2 S_ij x~_ik x~_jk   (App. A.5)
+// so block (b, s) owns the 32-row strip b and walks only the column tiles J >= b of split s of its (class-restricted)
+// column range: every tile PAIR {(I, J), (J, I)} of G is read exactly once -- 8 N^2 bytes in all, where the row-wise
+// kernel this replaces read 16 N^2 -- and every exponential is evaluated once instead of twice.
+//   row side  -> registers over the walk -> partX [NS][n][d]      (per-split row sums)
+//   col side  -> per tile, reduced over the 8 warps in shared memory -> partC[I][j][d], j >= 32 I (each entry is written
+//                by exactly one block); the second kernel adds the strips I <= j/32 in a fixed order
+//   part [nblk * NS][2 d + 2]: per-block partials of g_log_ls[d], tr(G^), g_log_c[d+1].
+// offset (in rows of d doubles) of strip I in partC: rows j = 32 I .. 32 nblk - 1
+__host__ __device__ __forceinline__ long long partc_offset(long long I, long long nblk) {
+    return 32 * (I * nblk - I * (I - 1) / 2);
+}
+
 template <int DL>
 __global__ void __launch_bounds__(256) kernel_grad_kernel(const double* __restrict__ X, const double* __restrict__ G,
                                                           long long n, int kind, const double* __restrict__ ls,
                                                           const double* __restrict__ lin_c2,
                                                           const int64_t* __restrict__ offs, int n_classes,
-                                                          double* __restrict__ partX, double* __restrict__ part) {
+                                                          double* __restrict__ partX, double* __restrict__ partC,
+                                                          double* __restrict__ part) {
     __shared__ double ai[32][MAXD_T], xi[32][MAXD_T];  // row side: read as broadcasts
     __shared__ double aj[MAXD_T][32], xj[MAXD_T][32];  // column side: k-major, lane = column (conflict-free)
     __shared__ double GT[32][33];
+    __shared__ double colred[8][DL][32];               // column-side partial sums of the 8 warps
     __shared__ int ci[32], cj[32];
     __shared__ double red[8][2 * MAXD_T + 2];
     __shared__ double exptab[64];
-    __shared__ double inv_ls[MAXD_T];
+    __shared__ double w2[MAXD_T];                      // 2 / l_k
     constexpr int d = DL;  // compile-time latent dimension: the per-thread accumulators below stay in registers
-    const long long i0 = (long long)blockIdx.x * 32;
+    const long long I = blockIdx.x, i0 = I * 32, nblk = gridDim.x;
     const int NS = gridDim.y, split = blockIdx.y;
     const int tx = threadIdx.x, ty = threadIdx.y, t = ty * 32 + tx;
     if (t < 64) exptab[t] = c_exp_table_train[t];
-    if (t < d) inv_ls[t] = 1.0 / ls[t];
+    if (t < d) w2[t] = 2.0 / ls[t];
     if (t < 32) {
         const long long row = i0 + t;
         for (int k = 0; k < d; k++) {
@@ -142,25 +157,22 @@ __global__ void __launch_bounds__(256) kernel_grad_kernel(const double* __restri
         }
         ci[t] = (offs && row < n) ? class_of_row(row, offs, n_classes) : 0;
     }
-    double gx[4][MAXD_T];
-    double gl[MAXD_T], gc[MAXD_T + 1], tr = 0.0;
+    double gx[4][DL], gl[DL], gc[DL + 1], tr = 0.0;
 #pragma unroll
     for (int q = 0; q < 4; q++)
 #pragma unroll
-        for (int k = 0; k < MAXD_T; k++) gx[q][k] = 0.0;
+        for (int k = 0; k < d; k++) gx[q][k] = 0.0;
 #pragma unroll
-    for (int k = 0; k < MAXD_T; k++) gl[k] = gc[k] = 0.0;
-    gc[MAXD_T] = 0.0;
+    for (int k = 0; k < d; k++) gl[k] = gc[k] = 0.0;
+    gc[d] = 0.0;
 
-    // class-masked gradients vanish outside the class block: restrict the column walk to it
-    long long jbeg = 0, jend = n;
+    // the walk: column tiles from the strip's own diagonal tile to the end of its class range (class-masked gradients
+    // vanish outside the class block; rows of one strip may straddle classes: walk up to the last one's end)
+    long long jbeg = i0, jend = n;
     __syncthreads();
     if (offs) {
-        // rows of one block may straddle two classes; walk the union of their column ranges
         const long long last = (i0 + 31 < n ? i0 + 31 : n - 1);
-        jbeg = offs[class_of_row(i0, offs, n_classes)];
         jend = offs[class_of_row(last, offs, n_classes) + 1];
-        jbeg = jbeg / 32 * 32;
     }
     {
         const long long ntile = (jend - jbeg + 31) / 32, per = (ntile + NS - 1) / NS;
@@ -169,6 +181,7 @@ __global__ void __launch_bounds__(256) kernel_grad_kernel(const double* __restri
         jbeg = a0;
         jend = a1 < jend ? a1 : jend;
     }
+    double* pc = partC + partc_offset(I, nblk) * d - i0 * d;  // pc[j * d + k], j >= i0
     // G values of the current tile live in registers; the next tile's are prefetched while this one is computed, so
     // the HBM latency of the two 8 KB tile reads (G[i][j] row-wise, G[j][i] as 256-byte column segments) is hidden.
     double gcur[4], gtc[4];
@@ -190,7 +203,7 @@ __global__ void __launch_bounds__(256) kernel_grad_kernel(const double* __restri
             for (int k = 0; k < d; k++) {
                 const double x = row < n ? X[row * d + k] : 0.0;
                 xj[k][t] = x;
-                aj[k][t] = x * inv_ls[k];
+                aj[k][t] = x * (0.5 * w2[k]);
             }
             cj[t] = (offs && row < n) ? class_of_row(row, offs, n_classes) : 0;
         }
@@ -201,11 +214,13 @@ __global__ void __launch_bounds__(256) kernel_grad_kernel(const double* __restri
         double gnext[4], gtn[4];
         fetch(j0 + 32, gnext, gtn);
         const long long j = j0 + tx;
-        double ajr[MAXD_T], xjr[MAXD_T];  // this lane's column, shared by its four rows
+        const bool diag_tile = j0 == i0;
+        double ajr[DL], xjr[DL], gcol[DL];  // this lane's column, shared by its four rows
 #pragma unroll
-        for (int k = 0; k < MAXD_T; k++) {
-            ajr[k] = k < d ? aj[k][tx] : 0.0;
-            xjr[k] = (kind == 1 && k < d) ? xj[k][tx] : 0.0;
+        for (int k = 0; k < d; k++) {
+            ajr[k] = aj[k][tx];
+            xjr[k] = kind == 1 ? xj[k][tx] : 0.0;
+            gcol[k] = 0.0;
         }
 #pragma unroll
         for (int q = 0; q < 4; q++) {
@@ -213,31 +228,56 @@ __global__ void __launch_bounds__(256) kernel_grad_kernel(const double* __restri
             const long long i = i0 + r;
             if (i >= n || j >= n) continue;
             if (offs && ci[r] != cj[tx]) continue;
-            const double g = gcur[q];        // G^_ij
-            const double s = g + GT[tx][r];  // S_ij = G^_ij + G^_ji
-            double dist = 0.0;
-            double dk[MAXD_T];
-#pragma unroll
-            for (int k = 0; k < MAXD_T; k++)
-                if (k < d) {
-                    dk[k] = ai[r][k] - ajr[k];
-                    dist = fma(dk[k], dk[k], dist);
-                }
-            const double kr = fast_exp(-dist, exptab);
-            const double gkr = g * kr, skr = s * kr;
-#pragma unroll
-            for (int k = 0; k < MAXD_T; k++)
-                if (k < d) {
-                    // d k_rbf / d x_ik = k_rbf * (-2 (x_ik - x_jk) / l_k^2)
-                    gx[q][k] = fma(skr, -2.0 * dk[k] * inv_ls[k], gx[q][k]);
-                    gl[k] = fma(gkr, 2.0 * dk[k] * dk[k], gl[k]);
+            if (diag_tile && i >= j) {
+                if (i == j) {  // diagonal element: S_ii = 2 G_ii, k_rbf = 1, D = 0
+                    const double g = gcur[q];
+                    tr += g;
                     if (kind == 1) {
-                        gx[q][k] = fma(s * lin_c2[k], xjr[k], gx[q][k]);
-                        gc[k] = fma(g, xi[r][k] * xjr[k], gc[k]);
+#pragma unroll
+                        for (int k = 0; k < d; k++) {
+                            gx[q][k] = fma(2.0 * g * lin_c2[k], xjr[k], gx[q][k]);
+                            gc[k] = fma(g, xjr[k] * xjr[k], gc[k]);
+                        }
+                        gc[d] += g;
                     }
                 }
-            if (kind == 1) gc[d] += g;
-            if (i == j) tr += g;
+                continue;  // pairs below the diagonal are handled from their mirror image
+            }
+            const double s = gcur[q] + GT[tx][r];  // S_ij = G^_ij + G^_ji
+            double dist = 0.0;
+            double dk[DL];
+#pragma unroll
+            for (int k = 0; k < d; k++) {
+                dk[k] = ai[r][k] - ajr[k];
+                dist = fma(dk[k], dk[k], dist);
+            }
+            const double skr = s * fast_exp(-dist, exptab);
+#pragma unroll
+            for (int k = 0; k < d; k++) {
+                // d k_rbf / d x_ik = k_rbf * (-2 (x_ik - x_jk) / l_k^2) = -d k_rbf / d x_jk
+                const double u = skr * dk[k] * w2[k];
+                gx[q][k] -= u;
+                gcol[k] += u;
+                gl[k] = fma(skr * dk[k], 2.0 * dk[k], gl[k]);
+                if (kind == 1) {
+                    const double sc = s * lin_c2[k];
+                    gx[q][k] = fma(sc, xjr[k], gx[q][k]);
+                    gcol[k] = fma(sc, xi[r][k], gcol[k]);
+                    gc[k] = fma(s, xi[r][k] * xjr[k], gc[k]);
+                }
+            }
+            if (kind == 1) gc[d] += s;
+        }
+        // column sums of this tile: the 8 warps' partials added in warp order by one thread per (column, k)
+#pragma unroll
+        for (int k = 0; k < d; k++) colred[ty][k][tx] = gcol[k];
+        __syncthreads();
+        if (t < 32 * d) {
+            const int c = t & 31, k = t >> 5;
+            double v = 0.0;
+#pragma unroll
+            for (int w = 0; w < 8; w++) v += colred[w][k][c];
+            if (j0 + c < n) pc[(j0 + c) * d + k] = v;
         }
 #pragma unroll
         for (int q = 0; q < 4; q++) {
@@ -251,11 +291,10 @@ __global__ void __launch_bounds__(256) kernel_grad_kernel(const double* __restri
     for (int q = 0; q < 4; q++) {
         const long long i = i0 + ty + 8 * q;
 #pragma unroll
-        for (int k = 0; k < MAXD_T; k++)
-            if (k < d) {
-                const double v = warp_sum(gx[q][k]);
-                if (tx == 0 && i < n) px[i * d + k] = v;
-            }
+        for (int k = 0; k < d; k++) {
+            const double v = warp_sum(gx[q][k]);
+            if (tx == 0 && i < n) px[i * d + k] = v;
+        }
     }
     // scalar partials: warp tree, then serial over the 8 warps
     const int ncol = 2 * d + 2;
@@ -279,14 +318,20 @@ __global__ void __launch_bounds__(256) kernel_grad_kernel(const double* __restri
     }
 }
 
-// fixed-order reductions of the partials: gX[i][k] = sum_s partX[s][i][k]; scalars = sum over blocks
-__global__ void kernel_grad_reduce_x_kernel(const double* __restrict__ partX, long long nd, int NS,
+// fixed-order reductions of the partials:
+//   gX[i][k] = sum_s partX[s][i][k]  +  sum over the strips I that hold rows of i's class, I <= i / 32, of partC[I][i][k]
+__global__ void kernel_grad_reduce_x_kernel(const double* __restrict__ partX, const double* __restrict__ partC, long long n,
+                                            int d, int NS, long long nblk, const int64_t* __restrict__ offs, int n_classes,
                                             double* __restrict__ gX) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nd) return;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n * d) return;
+    const long long i = idx / d;
+    const int k = (int)(idx - i * d);
     double v = 0.0;
-    for (int s = 0; s < NS; s++) v += partX[(long long)s * nd + i];
-    gX[i] = v;
+    for (int s = 0; s < NS; s++) v += partX[(long long)s * n * d + idx];
+    const long long I_lo = offs ? offs[class_of_row(i, offs, n_classes)] / 32 : 0, I_hi = i / 32;
+    for (long long I = I_lo; I <= I_hi; I++) v += partC[(partc_offset(I, nblk) + (i - 32 * I)) * d + k];
+    gX[idx] = v;
 }
 
 __global__ void kernel_grad_final_kernel(const double* __restrict__ part, long long nblk, int d, int kind,
@@ -298,7 +343,7 @@ __global__ void kernel_grad_final_kernel(const double* __restrict__ part, long l
     double v = 0.0;
     for (long long b = 0; b < nblk; b++) v += part[b * ncol + col];
     if (col < d) {
-        if (g_log_ls) g_log_ls[col] = v;  // sum G^ k 2 dist_k  (dk already divided by l_k)
+        if (g_log_ls) g_log_ls[col] = v;  // sum S k 2 dist_k over unordered pairs (dk already divided by l_k)
     } else if (col == d) {
         if (g_log_sigma) g_log_sigma[0] = 2.0 * sigma2 * v;
     } else if (kind == 1 && g_log_c) {
@@ -339,7 +384,9 @@ extern "C" int gpmdm_kernel_build_f64(const double* X, int64_t n, int32_t d, int
 }
 
 extern "C" int64_t gpmdm_kernel_grad_workspace_bytes(int64_t n, int32_t d) {
-    return ((n + 31) / 32) * GRAD_SPLITS * (int64_t)(2 * d + 2) * 8 + (int64_t)GRAD_SPLITS * n * d * 8;
+    const int64_t nblk = (n + 31) / 32;
+    return nblk * GRAD_SPLITS * (int64_t)(2 * d + 2) * 8 + (int64_t)GRAD_SPLITS * n * d * 8 +
+           partc_offset(nblk, nblk) * d * 8;
 }
 
 extern "C" int gpmdm_kernel_grad_f64(const double* X, const double* G, int64_t n, int32_t d, int32_t kind,
@@ -353,18 +400,20 @@ extern "C" int gpmdm_kernel_grad_f64(const double* X, const double* G, int64_t n
     const long long nblk = (n + 31) / 32;
     double* part = static_cast<double*>(workspace);
     double* partX = part + nblk * GRAD_SPLITS * (2 * d + 2);
+    double* partC = partX + (long long)GRAD_SPLITS * n * d;
     const dim3 grid((unsigned)nblk, GRAD_SPLITS), block(32, 8);
 #define GPMDM_GRAD_CASE(DL)                                                                                        \
     case DL:                                                                                                       \
         kernel_grad_kernel<DL><<<grid, block, 0, st>>>(X, G, n, kind, lengthscales, lin_c2, class_offsets, n_classes, \
-                                                       partX, part);                                               \
+                                                       partX, partC, part);                                        \
         break;
     switch (d) {
         GPMDM_GRAD_CASE(1) GPMDM_GRAD_CASE(2) GPMDM_GRAD_CASE(3) GPMDM_GRAD_CASE(4)
         GPMDM_GRAD_CASE(5) GPMDM_GRAD_CASE(6) GPMDM_GRAD_CASE(7) GPMDM_GRAD_CASE(8)
     }
 #undef GPMDM_GRAD_CASE
-    kernel_grad_reduce_x_kernel<<<(unsigned)((n * d + 255) / 256), 256, 0, st>>>(partX, n * d, GRAD_SPLITS, gX);
+    kernel_grad_reduce_x_kernel<<<(unsigned)((n * d + 255) / 256), 256, 0, st>>>(partX, partC, n, d, GRAD_SPLITS, nblk,
+                                                                                class_offsets, n_classes, gX);
     kernel_grad_final_kernel<<<1, 32, 0, st>>>(part, nblk * GRAD_SPLITS, d, kind, lin_c2, sigma2, g_log_ls, g_log_sigma,
                                                g_log_c);
     return check_launch("kernel_grad_kernel");

@@ -3,7 +3,7 @@ terms at N_train = 20 000, feeding torch.linalg Cholesky.  Times each CUDA kerne
 HBM GB/s against the measured copy peak (MEASURED_PEAKS.json: 6453 GB/s), plus one full `gpdm_loss` forward+backward.
 
     python tools/cfg5_train_bench.py [--n-classes 8 --seqs-per-class 25 --frames 100]
-Algorithmic bytes: build = 8 N^2 written; gradient = 16 N^2 read (G row-wise and column-wise) + 8 N d written."""
+Algorithmic bytes: build = 8 N^2 written; gradient = 8 N^2 read (every mirror-image tile pair of G once) + 8 N d written."""
 import argparse
 import json
 import os
@@ -74,11 +74,11 @@ def main():
     gl, gs, gc = (torch.empty(k, dtype=torch.float64, device=dev) for k in (3, 1, 4))
     ws = torch.empty(int(lib.gpmdm_kernel_grad_workspace_bytes(N, 3)) // 8 + 1, dtype=torch.float64, device=dev)
     t = timed(lambda: check(lib.gpmdm_kernel_grad_f64(ptr(X), ptr(G), N, 3, 0, ptr(ls_y), None, s2y, None, 0, ptr(gX), ptr(gl), ptr(gs), None, ptr(ws), stream()), "grad"))
-    out["grad_Ky_ms"], out["grad_Ky_gbs"] = t, 16.0 * N * N / (t * 1e-3) / 1e9
+    out["grad_Ky_ms"], out["grad_Ky_gbs"] = t, 8.0 * N * N / (t * 1e-3) / 1e9
     Gx = G.reshape(-1)[:Nx * Nx].view(Nx, Nx)
     t = timed(lambda: check(lib.gpmdm_kernel_grad_f64(ptr(Xin), ptr(Gx), Nx, 3, 1, ptr(ls_x), ptr(c2), s2x, ptr(offs), o.classes, ptr(gX), ptr(gl), ptr(gs), ptr(gc), ptr(ws), stream()), "grad"))
     blocks = float(sum((int(offs[i + 1]) - int(offs[i])) ** 2 for i in range(o.classes)))  # only class blocks of G are read
-    out["grad_Kx_masked_ms"], out["grad_Kx_masked_gbs"] = t, 16.0 * blocks / (t * 1e-3) / 1e9
+    out["grad_Kx_masked_ms"], out["grad_Kx_masked_gbs"] = t, 8.0 * blocks / (t * 1e-3) / 1e9
     del K, G, Kx, Gx
     for p in m.parameters():
         p.requires_grad_(True)
