@@ -33,6 +33,7 @@
 // log-likelihood stay with the fp64 mean tile (gpmdm_pf_loglik_f64), as in the hybrid tf32 variant.
 #include <cuda_fp16.h>
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -63,12 +64,17 @@ constexpr int KC = Geo<MODE_TF32X3>::KC;       // (tf32 names kept for the packe
 constexpr int A_HALF = A_HALF_BYTES / 4, B_HALF = B_HALF_BYTES / 4;
 constexpr uint32_t LBO = 128, SBO = 4 * 128;  // core-matrix strides (bytes) along K and along M/N
 
-struct __align__(1024) Smem {
-    unsigned char A[ASTAGES][2][A_HALF_BYTES];   // [stage][hi|lo]
-    unsigned char B[BSTAGES][2][B_HALF_BYTES];   // [stage][hi|lo]
+// CG = CTAs per tensor-core tile group: 1, or 2 = a cluster of two CTAs (SM pair) issuing cta_group::2 MMAs -- each CTA
+// supplies its own 128 particles (A) and HALF of every W tile (B rows 0-127 / 128-255): half the B bytes per SM from L2 and
+// from shared memory, the two resources the single-CTA kernel runs out of (profiles/ncu_observe_f16x2_kernel_r02.txt).
+template <int CG>
+struct __align__(1024) SmemT {
+    unsigned char A[ASTAGES][2][A_HALF_BYTES];        // [stage][hi|lo]
+    unsigned char B[BSTAGES][2][B_HALF_BYTES / CG];   // [stage][hi|lo], this CTA's share of the 256 rows
     uint64_t a_full[ASTAGES], a_empty[ASTAGES], b_full[BSTAGES], b_empty[BSTAGES], t_full[2], t_empty[2];
     uint32_t tmem_base;
 };
+using Smem = SmemT<1>;
 
 struct Params {
     const float* coords;   // [n_pad / 2, CREC, 2]: pairs of training rows interleaved per coordinate, x sqrt(log2 e) / l
@@ -134,6 +140,57 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                  : "memory");
 }
+// ---- cta_group::2 (CTA pair) variants ---------------------------------------------------------------------------------
+constexpr uint32_t IDESC2 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)((2 * TM) >> 4) << 24);
+constexpr uint32_t IDESC2_F16 = (1u << 4) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)((2 * TM) >> 4) << 24);
+template <bool F16>
+__device__ __forceinline__ void umma_2cta(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+    if (F16)
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t"
+            "}\n" ::"r"(tmem_d),
+            "l"(adesc), "l"(bdesc), "r"(IDESC2_F16), "r"(accumulate), "r"(0u)
+            : "memory");
+    else
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t"
+            "}\n" ::"r"(tmem_d),
+            "l"(adesc), "l"(bdesc), "r"(IDESC2), "r"(accumulate), "r"(0u)
+            : "memory");
+}
+// arrives (once the MMAs issued so far have completed) on the barrier at this offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma_commit_2cta(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                     smem_u32(bar)),
+                 "h"((uint16_t)3)
+                 : "memory");
+}
+// arrive on the barrier at this offset in the shared memory of CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t rank) {
+    asm volatile(
+        "{\n"
+        ".reg .b32 ra;\n"
+        "mapa.shared::cluster.u32 ra, %0, %1;\n"
+        "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(rank)
+        : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -187,47 +244,62 @@ __device__ __forceinline__ void mbar_wait_b(uint64_t* bar, uint32_t parity) {
     __trap();
 }
 
-template <int DL, int MODE>
+template <int DL, int MODE, int CG>
 __global__ void __launch_bounds__(NTHREADS, 1) observe_tf32_kernel(const Params prm) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    Smem& s = *reinterpret_cast<Smem*>(smem_raw);
+    SmemT<CG>& s = *reinterpret_cast<SmemT<CG>*>(smem_raw);
     using G = Geo<MODE>;
     constexpr int KCm = G::KC;                               // k per chunk in this mode
     constexpr bool F16 = MODE == MODE_F16X2;
+    constexpr int BH = B_HALF_BYTES / CG;                    // bytes of one piece (hi or lo) of this CTA's share of a W tile
     // accumulator buffers: two in tf32 mode; one in F16X2 mode, where D1 | D2 fill all 512 TMEM columns
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nq = prm.n_pad / TN, nkc = prm.n_pad / KCm;
     // + one alpha tile (dout <= 256) when a mean is wanted (tf32 mode only: the fp16 split is used for variances)
     const int nct = nq + ((!F16 && (prm.ll || prm.mu_out)) ? 1 : 0);
     const int n_tiles = (int)((prm.P + TM - 1) / TM);
+    // work units: particle tiles (CG = 1), or PAIRS of particle tiles 2u, 2u+1 handled by the two CTAs of a cluster
+    const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;
+    const bool leader = rank == 0;
+    const int n_units = (n_tiles + CG - 1) / CG;
+    const int unit0 = (int)blockIdx.x / CG, unit_stride = (int)gridDim.x / CG;
+    auto tile_of = [&](int u) { return CG * u + (int)rank; };  // may be == n_tiles for the second CTA of the last pair
 
     if (tid == 0) {
         for (int i = 0; i < ASTAGES; i++) {
-            mbar_init(&s.a_full[i], NGEN);
+            mbar_init(&s.a_full[i], NGEN + ((CG == 2 && leader) ? 1 : 0));  // + the relay of the peer's generators
             mbar_init(&s.a_empty[i], 1);
         }
         for (int i = 0; i < BSTAGES; i++) {
-            mbar_init(&s.b_full[i], 1);
+            mbar_init(&s.b_full[i], (CG == 2 && leader) ? 2 : 1);           // own TMA + the relay of the peer's TMA
             mbar_init(&s.b_empty[i], 1);
         }
         for (int i = 0; i < 2; i++) {
             mbar_init(&s.t_full[i], 1);
-            mbar_init(&s.t_empty[i], NEPI);
+            mbar_init(&s.t_empty[i], NEPI * CG);                            // both CTAs' epilogue warps (leader's copy)
         }
         mbar_fence_init();
     }
     if (warp == 1) {  // TMEM: all 512 columns (two 256-column fp32 accumulators)
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s.tmem_base)),
-                     "r"(512u)
-                     : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if (CG == 2) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s.tmem_base)),
+                         "r"(512u)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s.tmem_base)),
+                         "r"(512u)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     tc_fence_before();
     __syncthreads();
+    if (CG == 2) cluster_sync();  // the peer's barriers exist before anything arrives on them remotely
     tc_fence_after();
     const uint32_t tmem = s.tmem_base;
     auto wait = [](uint64_t* bar, uint32_t parity) {
-        if (F16) mbar_wait_b(bar, parity);
+        if (F16 || CG == 2) mbar_wait_b(bar, parity);
         else mbar_wait(bar, parity);
     };
 
@@ -241,15 +313,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) observe_tf32_kernel(const Params 
             int rounds = 0;
             const unsigned char* wt = reinterpret_cast<const unsigned char*>(prm.wtiles);
             const unsigned char* at = reinterpret_cast<const unsigned char*>(prm.atiles);
-            for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+            for (int u = unit0; u < n_units; u += unit_stride) {
                 for (int ct = 0; ct < nct; ct++) {
                     const unsigned char* base = ct < nq ? wt + wtile_offset_kc(ct, KCm) * (2 * B_HALF_BYTES) : at;
                     const int nch = chunks_of(ct);
                     for (int kc = 0; kc < nch; kc++, g++) {
                         const int st = g % BSTAGES;
                         wait(&s.b_empty[st], ((g / BSTAGES) & 1) ^ 1);
-                        mbar_expect_tx(&s.b_full[st], 2 * B_HALF_BYTES);
-                        bulk_g2s(&s.B[st][0][0], base + (long long)kc * (2 * B_HALF_BYTES), 2 * B_HALF_BYTES, &s.b_full[st]);
+                        mbar_expect_tx(&s.b_full[st], 2 * BH);
+                        const unsigned char* src = base + (long long)kc * (2 * B_HALF_BYTES);
+                        if (CG == 1) {
+                            bulk_g2s(&s.B[st][0][0], src, 2 * B_HALF_BYTES, &s.b_full[st]);
+                        } else {  // this CTA's 128 of the 256 rows of the hi and of the lo piece: two contiguous ranges
+                            bulk_g2s(&s.B[st][0][0], src + rank * BH, BH, &s.b_full[st]);
+                            bulk_g2s(&s.B[st][1][0], src + B_HALF_BYTES + rank * BH, BH, &s.b_full[st]);
+                        }
                     }
                 }
                 // Round synchronisation of the producers (bounded polling, never a hang): the 148 CTAs stream the same
@@ -258,7 +336,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) observe_tf32_kernel(const Params 
                 if (prm.round_counter) {
                     rounds++;
                     atomicAdd(prm.round_counter, 1);
-                    const int full_rounds = n_tiles / (int)gridDim.x;  // rounds in which every CTA has a tile
+                    const int full_rounds = n_units / unit_stride;  // rounds in which every CTA has work
                     if (rounds <= full_rounds) {
                         const int target = rounds * (int)gridDim.x;
                         for (int spin = 0; spin < 200000; spin++) {
@@ -270,10 +348,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) observe_tf32_kernel(const Params 
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        if (lane == 0) {
+        // ===================== MMA issuer (the pair's leader CTA issues for both) =====================
+        if (lane == 0 && leader) {
             uint32_t g = 0, tcount = 0;
-            for (int t = blockIdx.x; t < n_tiles; t += gridDim.x)
+            for (int u = unit0; u < n_units; u += unit_stride)
                 for (int ct = 0; ct < nct; ct++, tcount++) {
                     const int acc = F16 ? 0 : (tcount & 1);
                     const uint32_t use = F16 ? tcount : (tcount >> 1);     // how often this buffer has been used before
@@ -293,20 +371,59 @@ __global__ void __launch_bounds__(NTHREADS, 1) observe_tf32_kernel(const Params 
                             const uint64_t a_lo = smem_desc(&s.A[sa][1][0] + koff);
                             const uint64_t b_hi = smem_desc(&s.B[sb][0][0] + koff);
                             const uint64_t b_lo = smem_desc(&s.B[sb][1][0] + koff);
-                            if (F16) {  // D1 += a_hi b_hi ;  D2 += a_lo b_hi + a_hi b_lo  (scaled by 2^-11 in the epilogue)
-                                umma_f16(d_tmem, a_hi, b_hi, (kc | ks) != 0);
-                                umma_f16(d_tmem + TN, a_lo, b_hi, (kc | ks) != 0);
+                            const uint32_t first = (kc | ks) != 0;
+                            if (CG == 2) {
+                                if (F16) {
+                                    umma_2cta<true>(d_tmem, a_hi, b_hi, first);
+                                    umma_2cta<true>(d_tmem + TN, a_lo, b_hi, first);
+                                    umma_2cta<true>(d_tmem + TN, a_hi, b_lo, 1);
+                                } else {
+                                    umma_2cta<false>(d_tmem, a_hi, b_hi, first);
+                                    umma_2cta<false>(d_tmem, a_lo, b_hi, 1);
+                                    umma_2cta<false>(d_tmem, a_hi, b_lo, 1);
+                                }
+                            } else if (F16) {  // D1 += a_hi b_hi ;  D2 += a_lo b_hi + a_hi b_lo  (scaled by 2^-11 in the epilogue)
+                                umma_f16(d_tmem, a_hi, b_hi, first);
+                                umma_f16(d_tmem + TN, a_lo, b_hi, first);
                                 umma_f16(d_tmem + TN, a_hi, b_lo, 1);
                             } else {
-                                umma_tf32(d_tmem, a_hi, b_hi, (kc | ks) != 0);
+                                umma_tf32(d_tmem, a_hi, b_hi, first);
                                 umma_tf32(d_tmem, a_lo, b_hi, 1);
                                 umma_tf32(d_tmem, a_hi, b_lo, 1);
                             }
                         }
-                        umma_commit(&s.a_empty[sa]);  // arrives when the MMAs above have read the operands
-                        umma_commit(&s.b_empty[sb]);
+                        if (CG == 2) {
+                            umma_commit_2cta(&s.a_empty[sa]);  // frees the stage in both CTAs
+                            umma_commit_2cta(&s.b_empty[sb]);
+                        } else {
+                            umma_commit(&s.a_empty[sa]);  // arrives when the MMAs above have read the operands
+                            umma_commit(&s.b_empty[sb]);
+                        }
                     }
-                    umma_commit(&s.t_full[acc]);  // accumulator complete
+                    if (CG == 2) umma_commit_2cta(&s.t_full[acc]);
+                    else umma_commit(&s.t_full[acc]);  // accumulator complete
+                }
+        }
+    } else if (CG == 2 && !leader && (warp == 2 || warp == 3)) {
+        // ===================== relays (second CTA of a pair): local "full" -> the leader's barrier =====================
+        // The leader's MMA thread waits on ITS a_full / b_full only; this CTA's generators and TMA complete on the local
+        // copies, and one thread per ring forwards each completion with a single remote arrive.
+        if (lane == 0) {
+            uint32_t g = 0;
+            for (int u = unit0; u < n_units; u += unit_stride)
+                for (int ct = 0; ct < nct; ct++) {
+                    const int nch = chunks_of(ct);
+                    for (int kc = 0; kc < nch; kc++, g++) {
+                        if (warp == 2) {
+                            const int sa = g % ASTAGES;
+                            wait(&s.a_full[sa], (g / ASTAGES) & 1);
+                            mbar_arrive_remote(&s.a_full[sa], 0);
+                        } else {
+                            const int sb = g % BSTAGES;
+                            wait(&s.b_full[sb], (g / BSTAGES) & 1);
+                            mbar_arrive_remote(&s.b_full[sb], 0);
+                        }
+                    }
                 }
         }
     } else if (warp >= GEN_WARP0 && warp < EPI_WARP0) {
@@ -318,8 +435,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) observe_tf32_kernel(const Params 
         constexpr double SQRT_LOG2E = 1.2011224087864498;
         constexpr int KPT = KCm / 2;                     // k per thread and chunk: 8 (tf32) / 16 (fp16)
         uint32_t g = 0;
-        for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-            long long p = (long long)t * TM + row;
+        for (int u = unit0; u < n_units; u += unit_stride) {
+            long long p = (long long)tile_of(u) * TM + row;
             if (p >= prm.P) p = prm.P - 1;
             // particle coordinates, negated and duplicated into both halves of a packed f32x2 register
             float2 nb[DL];
@@ -362,7 +479,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) observe_tf32_kernel(const Params 
 #pragma unroll
                         for (int q = 0; q < KPT / 8; q++) {
                             // packed conversions (two values per F2FP): scalar fp32 <-> fp16 conversions run at a
-                            // fraction of the rate and would bound the kernel at this chunk rate
+                            // fraction of the rate
                             __half2 hi[4], lo[4];
 #pragma unroll
                             for (int i = 0; i < 4; i++) {
@@ -403,8 +520,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) observe_tf32_kernel(const Params 
         const int et = tid - EPI_WARP0 * 32;  // particle row; this warp owns TMEM lanes 32 (warp % 4) ..
         const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
         uint32_t tcount = 0;
-        for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-            const long long p = (long long)t * TM + et;
+        for (int u = unit0; u < n_units; u += unit_stride) {
+            const long long p = (long long)tile_of(u) * TM + et;
             const bool valid = p < prm.P;
             float q = 0.f;
             double S = 0.0;
@@ -425,8 +542,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) observe_tf32_kernel(const Params 
                             tmem_ld32(taddr + TN + cb, w);
 #pragma unroll
                             for (int i = 0; i < 32; i++) {
-                                const float u = fmaf(w[i], 1.0f / 2048.f, v[i]);
-                                part = fmaf(u, u, part);
+                                const float uu = fmaf(w[i], 1.0f / 2048.f, v[i]);
+                                part = fmaf(uu, uu, part);
                             }
                         } else {
 #pragma unroll
@@ -453,7 +570,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) observe_tf32_kernel(const Params 
                     }
                 }
                 tc_fence_before();
-                mbar_arrive(&s.t_empty[acc]);
+                if (CG == 2 && !leader) mbar_arrive_remote(&s.t_empty[acc], 0);  // the leader's MMA thread owns the count
+                else mbar_arrive(&s.t_empty[acc]);
             }
             if (valid) {
                 const double v = 1.0 - (double)q;
@@ -465,9 +583,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) observe_tf32_kernel(const Params 
     }
     tc_fence_before();
     __syncthreads();
+    if (CG == 2) cluster_sync();  // neither CTA leaves (or frees TMEM) while the pair's MMAs may still read its shared memory
     if (warp == 1) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+        if (CG == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
     }
 }
 
@@ -542,24 +662,60 @@ __global__ void pack_whitened_f16_kernel(const double* __restrict__ W, long long
     dst[TILE_ELEMS + idx] = lo;
 }
 
-template <int DL, int MODE = MODE_TF32X3>
-static int launch(const Params& prm, int grid, cudaStream_t st) {
+// CTA pairs (cta_group::2) unless GPMDM_TC_CLUSTER=0 or there are too few particle tiles to pair up
+static bool use_cluster(long long tiles) {
+    const char* e = getenv("GPMDM_TC_CLUSTER");  // read per call: tests compare the two variants in one process
+    return !(e && e[0] == '0') && tiles >= 4;
+}
+
+template <int DL, int MODE, int CG>
+static int launch_cg(const Params& prm, int grid, cudaStream_t st) {
     // the opt-in to > 48 KB of dynamic shared memory is per function AND per device
     static bool configured[64] = {};  // per instantiation
     int dev = 0;
     cudaGetDevice(&dev);
     dev = (dev >= 0 && dev < 64) ? dev : 0;
-    auto kern = observe_tf32_kernel<DL, MODE>;
+    auto kern = observe_tf32_kernel<DL, MODE, CG>;
     if (!configured[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemT<CG>));
         if (e != cudaSuccess) {
             set_error("cudaFuncSetAttribute(observe_tf32): %s", cudaGetErrorString(e));
             return (int)e;
         }
         configured[dev] = true;
     }
-    kern<<<grid, NTHREADS, sizeof(Smem), st>>>(prm);
+    if (CG == 1) {
+        kern<<<grid, NTHREADS, sizeof(SmemT<CG>), st>>>(prm);
+    } else {
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3((unsigned)grid);
+        cfg.blockDim = dim3(NTHREADS);
+        cfg.dynamicSmemBytes = sizeof(SmemT<CG>);
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        cudaError_t e = cudaLaunchKernelEx(&cfg, kern, prm);
+        if (e != cudaSuccess) {
+            set_error("cudaLaunchKernelEx(observe_tf32, cluster 2): %s", cudaGetErrorString(e));
+            return (int)e;
+        }
+    }
     return check_launch("observe_tf32_kernel");
+}
+
+// grid: one CTA per 128-particle tile up to one per SM; in pairs when the cluster variant is used
+template <int DL, int MODE = MODE_TF32X3>
+static int launch(const Params& prm, long long tiles, int sms, cudaStream_t st) {
+    if (use_cluster(tiles)) {
+        const long long units = (tiles + 1) / 2, clusters = units < sms / 2 ? units : sms / 2;
+        return launch_cg<DL, MODE, 2>(prm, (int)(2 * clusters), st);
+    }
+    return launch_cg<DL, MODE, 1>(prm, (int)(tiles < sms ? tiles : sms), st);
 }
 
 // ---- tf32 tensor-core peak probe (the denominator of the tf32 roofline in bench.py) --------------------------------
@@ -698,23 +854,22 @@ extern "C" int gpmdm_pf_observe_tf32(const gpmdm_gp_model_tf32* m, const double*
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const long long tiles = (P + tf32::TM - 1) / tf32::TM;
-    const int grid = (int)(tiles < sms ? tiles : sms);
     cudaStream_t st = (cudaStream_t)stream;
     prm.status = tile_counter ? tile_counter + 3 : nullptr;
-    if (tile_counter && tiles >= 2ll * grid) {
+    if (tile_counter && tiles >= 2ll * sms) {
         cudaError_t e = cudaMemsetAsync(tile_counter, 0, sizeof(int32_t), st);
         GPMDM_REQUIRE(e == cudaSuccess, (int)e, "cudaMemsetAsync: %s", cudaGetErrorString(e));
         prm.round_counter = tile_counter;
     }
     switch (m->d) {
-        case 1: return tf32::launch<1>(prm, grid, st);
-        case 2: return tf32::launch<2>(prm, grid, st);
-        case 3: return tf32::launch<3>(prm, grid, st);
-        case 4: return tf32::launch<4>(prm, grid, st);
-        case 5: return tf32::launch<5>(prm, grid, st);
-        case 6: return tf32::launch<6>(prm, grid, st);
-        case 7: return tf32::launch<7>(prm, grid, st);
-        case 8: return tf32::launch<8>(prm, grid, st);
+        case 1: return tf32::launch<1>(prm, tiles, sms, st);
+        case 2: return tf32::launch<2>(prm, tiles, sms, st);
+        case 3: return tf32::launch<3>(prm, tiles, sms, st);
+        case 4: return tf32::launch<4>(prm, tiles, sms, st);
+        case 5: return tf32::launch<5>(prm, tiles, sms, st);
+        case 6: return tf32::launch<6>(prm, tiles, sms, st);
+        case 7: return tf32::launch<7>(prm, tiles, sms, st);
+        case 8: return tf32::launch<8>(prm, tiles, sms, st);
     }
     return GPMDM_E_UNSUPPORTED;
 }
@@ -791,23 +946,22 @@ extern "C" int gpmdm_pf_observe_f16x2(const gpmdm_gp_model_tf32* m, const double
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const long long tiles = (P + tf32::TM - 1) / tf32::TM;
-    const int grid = (int)(tiles < sms ? tiles : sms);
     cudaStream_t st = (cudaStream_t)stream;
     prm.status = tile_counter ? tile_counter + 3 : nullptr;
-    if (tile_counter && tiles >= 2ll * grid) {
+    if (tile_counter && tiles >= 2ll * sms) {
         cudaError_t e = cudaMemsetAsync(tile_counter, 0, sizeof(int32_t), st);
         GPMDM_REQUIRE(e == cudaSuccess, (int)e, "cudaMemsetAsync: %s", cudaGetErrorString(e));
         prm.round_counter = tile_counter;
     }
     switch (m->d) {
-        case 1: return tf32::launch<1, tf32::MODE_F16X2>(prm, grid, st);
-        case 2: return tf32::launch<2, tf32::MODE_F16X2>(prm, grid, st);
-        case 3: return tf32::launch<3, tf32::MODE_F16X2>(prm, grid, st);
-        case 4: return tf32::launch<4, tf32::MODE_F16X2>(prm, grid, st);
-        case 5: return tf32::launch<5, tf32::MODE_F16X2>(prm, grid, st);
-        case 6: return tf32::launch<6, tf32::MODE_F16X2>(prm, grid, st);
-        case 7: return tf32::launch<7, tf32::MODE_F16X2>(prm, grid, st);
-        case 8: return tf32::launch<8, tf32::MODE_F16X2>(prm, grid, st);
+        case 1: return tf32::launch<1, tf32::MODE_F16X2>(prm, tiles, sms, st);
+        case 2: return tf32::launch<2, tf32::MODE_F16X2>(prm, tiles, sms, st);
+        case 3: return tf32::launch<3, tf32::MODE_F16X2>(prm, tiles, sms, st);
+        case 4: return tf32::launch<4, tf32::MODE_F16X2>(prm, tiles, sms, st);
+        case 5: return tf32::launch<5, tf32::MODE_F16X2>(prm, tiles, sms, st);
+        case 6: return tf32::launch<6, tf32::MODE_F16X2>(prm, tiles, sms, st);
+        case 7: return tf32::launch<7, tf32::MODE_F16X2>(prm, tiles, sms, st);
+        case 8: return tf32::launch<8, tf32::MODE_F16X2>(prm, tiles, sms, st);
     }
     return GPMDM_E_UNSUPPORTED;
 }

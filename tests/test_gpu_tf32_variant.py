@@ -134,3 +134,17 @@ def test_float32_model_dtype_argument(tmp_path):
     assert back.dtype == torch.float32 and back.X.dtype == torch.float32
     mu_b, _ = back.map_x_to_y(xs.float())
     assert float((mu_b - m32.map_x_to_y(xs.float())[0]).abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("prec", ["tf32", "f16x2"])
+@pytest.mark.parametrize("P", [512, 513, 640, 40000])
+def test_cta_pair_variant_equals_single_cta_variant(setup, P, prec, monkeypatch):
+    """cta_group::2 (clusters of two CTAs sharing every W tile, odd tile counts leave the last pair half empty) against the
+    single-CTA kernel (GPMDM_TC_CLUSTER=0): the same products accumulated in the same order -> identical variances."""
+    spec, wl, model = setup
+    xs = particles(spec, P, 7, 0.3).cuda()
+    monkeypatch.setenv("GPMDM_TC_CLUSTER", "1")
+    _, var2 = model.map_x_to_y(xs, precision=prec)
+    monkeypatch.setenv("GPMDM_TC_CLUSTER", "0")
+    _, var1 = model.map_x_to_y(xs, precision=prec)
+    assert torch.equal(var1, var2)
