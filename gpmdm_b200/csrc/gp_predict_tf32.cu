@@ -67,11 +67,19 @@ constexpr uint32_t LBO = 128, SBO = 4 * 128;  // core-matrix strides (bytes) alo
 // CG = CTAs per tensor-core tile group: 1, or 2 = a cluster of two CTAs (SM pair) issuing cta_group::2 MMAs -- each CTA
 // supplies its own 128 particles (A) and HALF of every W tile (B rows 0-127 / 128-255): half the B bytes per SM from L2 and
 // from shared memory, the two resources the single-CTA kernel runs out of (profiles/ncu_observe_f16x2_kernel_r02.txt).
+// Ring depths: the pair variant's producer -> consumer path crosses the cluster (local barrier -> relay -> the leader's
+// barrier, and the multicast commit back), a round trip of several chunk times: with the single-CTA depths (4 / 3) the
+// pair ran 8-19 % SLOWER than the single CTAs; the half-size B stages leave room for 8 / 5.
+template <int CG>
+struct Ring {
+    static constexpr int A = CG == 2 ? 8 : ASTAGES;
+    static constexpr int B = CG == 2 ? 5 : BSTAGES;
+};
 template <int CG>
 struct __align__(1024) SmemT {
-    unsigned char A[ASTAGES][2][A_HALF_BYTES];        // [stage][hi|lo]
-    unsigned char B[BSTAGES][2][B_HALF_BYTES / CG];   // [stage][hi|lo], this CTA's share of the 256 rows
-    uint64_t a_full[ASTAGES], a_empty[ASTAGES], b_full[BSTAGES], b_empty[BSTAGES], t_full[2], t_empty[2];
+    unsigned char A[Ring<CG>::A][2][A_HALF_BYTES];        // [stage][hi|lo]
+    unsigned char B[Ring<CG>::B][2][B_HALF_BYTES / CG];   // [stage][hi|lo], this CTA's share of the 256 rows
+    uint64_t a_full[Ring<CG>::A], a_empty[Ring<CG>::A], b_full[Ring<CG>::B], b_empty[Ring<CG>::B], t_full[2], t_empty[2];
     uint32_t tmem_base;
 };
 using Smem = SmemT<1>;
@@ -251,6 +259,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) observe_tf32_kernel(const Params 
     using G = Geo<MODE>;
     constexpr int KCm = G::KC;                               // k per chunk in this mode
     constexpr bool F16 = MODE == MODE_F16X2;
+    constexpr int AST = Ring<CG>::A, BST = Ring<CG>::B;         // ring depths
     constexpr int BH = B_HALF_BYTES / CG;                    // bytes of one piece (hi or lo) of this CTA's share of a W tile
     // accumulator buffers: two in tf32 mode; one in F16X2 mode, where D1 | D2 fill all 512 TMEM columns
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -266,11 +275,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) observe_tf32_kernel(const Params 
     auto tile_of = [&](int u) { return CG * u + (int)rank; };  // may be == n_tiles for the second CTA of the last pair
 
     if (tid == 0) {
-        for (int i = 0; i < ASTAGES; i++) {
+        for (int i = 0; i < AST; i++) {
             mbar_init(&s.a_full[i], NGEN + ((CG == 2 && leader) ? 1 : 0));  // + the relay of the peer's generators
             mbar_init(&s.a_empty[i], 1);
         }
-        for (int i = 0; i < BSTAGES; i++) {
+        for (int i = 0; i < BST; i++) {
             mbar_init(&s.b_full[i], (CG == 2 && leader) ? 2 : 1);           // own TMA + the relay of the peer's TMA
             mbar_init(&s.b_empty[i], 1);
         }
@@ -318,8 +327,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) observe_tf32_kernel(const Params 
                     const unsigned char* base = ct < nq ? wt + wtile_offset_kc(ct, KCm) * (2 * B_HALF_BYTES) : at;
                     const int nch = chunks_of(ct);
                     for (int kc = 0; kc < nch; kc++, g++) {
-                        const int st = g % BSTAGES;
-                        wait(&s.b_empty[st], ((g / BSTAGES) & 1) ^ 1);
+                        const int st = g % BST;
+                        wait(&s.b_empty[st], ((g / BST) & 1) ^ 1);
                         mbar_expect_tx(&s.b_full[st], 2 * BH);
                         const unsigned char* src = base + (long long)kc * (2 * B_HALF_BYTES);
                         if (CG == 1) {
@@ -360,9 +369,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) observe_tf32_kernel(const Params 
                     const uint32_t d_tmem = tmem + (uint32_t)acc * TN;
                     const int nch = chunks_of(ct);
                     for (int kc = 0; kc < nch; kc++, g++) {
-                        const int sa = g % ASTAGES, sb = g % BSTAGES;
-                        wait(&s.a_full[sa], (g / ASTAGES) & 1);
-                        wait(&s.b_full[sb], (g / BSTAGES) & 1);
+                        const int sa = g % AST, sb = g % BST;
+                        wait(&s.a_full[sa], (g / AST) & 1);
+                        wait(&s.b_full[sb], (g / BST) & 1);
                         tc_fence_after();
 #pragma unroll
                         for (int ks = 0; ks < 2; ks++) {  // two MMA k-steps per chunk (2 x 8 tf32 / 2 x 16 fp16)
@@ -415,12 +424,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) observe_tf32_kernel(const Params 
                     const int nch = chunks_of(ct);
                     for (int kc = 0; kc < nch; kc++, g++) {
                         if (warp == 2) {
-                            const int sa = g % ASTAGES;
-                            wait(&s.a_full[sa], (g / ASTAGES) & 1);
+                            const int sa = g % AST;
+                            wait(&s.a_full[sa], (g / AST) & 1);
                             mbar_arrive_remote(&s.a_full[sa], 0);
                         } else {
-                            const int sb = g % BSTAGES;
-                            wait(&s.b_full[sb], (g / BSTAGES) & 1);
+                            const int sb = g % BST;
+                            wait(&s.b_full[sb], (g / BST) & 1);
                             mbar_arrive_remote(&s.b_full[sb], 0);
                         }
                     }
@@ -448,7 +457,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) observe_tf32_kernel(const Params 
             for (int ct = 0; ct < nct; ct++) {
                 const int nch = chunks_of(ct);
                 for (int kc = 0; kc < nch; kc++, g++) {
-                    const int sa = g % ASTAGES;
+                    const int sa = g % AST;
                     float kv[KPT];
                     // coords are stored per PAIR of training rows as [j][2] (a_k[j], a_k+1[j]): one 64-bit element feeds
                     // the packed fp32x2 pipe (sm_100 FADD2 / FFMA2), two K* entries per instruction
@@ -471,7 +480,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) observe_tf32_kernel(const Params 
                         kv[kk] = ex2_approx(-dist.x);
                         kv[kk + 1] = ex2_approx(-dist.y);
                     }
-                    wait(&s.a_empty[sa], ((g / ASTAGES) & 1) ^ 1);
+                    wait(&s.a_empty[sa], ((g / AST) & 1) ^ 1);
                     if (F16) {
                         // a = hi + 2^-11 lo: 16 consecutive k of one row = two 16-byte core-matrix rows per piece
                         __half* ah = reinterpret_cast<__half*>(&s.A[sa][0][0]);
