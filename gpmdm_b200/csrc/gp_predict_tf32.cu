@@ -79,6 +79,7 @@ template <int CG>
 struct __align__(1024) SmemT {
     unsigned char A[Ring<CG>::A][2][A_HALF_BYTES];        // [stage][hi|lo]
     unsigned char B[Ring<CG>::B][2][B_HALF_BYTES / CG];   // [stage][hi|lo], this CTA's share of the 256 rows
+    float coords[2][32 * CREC];                           // the generators' double buffer: one chunk of training records
     uint64_t a_full[Ring<CG>::A], a_empty[Ring<CG>::A], b_full[Ring<CG>::B], b_empty[Ring<CG>::B], t_full[2], t_empty[2];
     uint32_t tmem_base;
 };
@@ -443,7 +444,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) observe_tf32_kernel(const Params 
         // (GPMDM.packed_model_tf32) and the particle's are scaled here, so a K* entry is the distance + ONE ex2.approx
         constexpr double SQRT_LOG2E = 1.2011224087864498;
         constexpr int KPT = KCm / 2;                     // k per thread and chunk: 8 (tf32) / 16 (fp16)
+        // The chunk's KCm training records (KCm x 8 floats, contiguous) are staged in shared memory by the 256 generator
+        // threads themselves -- one coalesced 4-byte load per thread, issued a whole chunk ahead -- and read back as
+        // warp-wide broadcasts.  (Every thread used to pull its 8-16 records through L1 with 16-byte loads: at d = 8 the
+        // 12 % of them that missed L1 were the kernel's largest stall, profiles/ncu_observe_f16x2_kernel_r02.txt.)
+        constexpr int CHUNK_FLOATS = KCm * CREC;  // 256 (fp16) / 128 (tf32)
         uint32_t g = 0;
+        if (gt < CHUNK_FLOATS) s.coords[0][gt] = __ldg(prm.coords + gt);  // chunk 0 of the first column tile
+        named_bar_sync(1, NGEN);
         for (int u = unit0; u < n_units; u += unit_stride) {
             long long p = (long long)tile_of(u) * TM + row;
             if (p >= prm.P) p = prm.P - 1;
@@ -458,16 +466,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) observe_tf32_kernel(const Params 
                 const int nch = chunks_of(ct);
                 for (int kc = 0; kc < nch; kc++, g++) {
                     const int sa = g % AST;
+                    // the next chunk of this thread's walk (every column tile, and every unit, starts again at k = 0)
+                    const int kn = kc + 1 < nch ? kc + 1 : 0;
+                    float cnext = 0.f;
+                    if (gt < CHUNK_FLOATS) cnext = __ldg(prm.coords + (long long)kn * CHUNK_FLOATS + gt);
                     float kv[KPT];
-                    // coords are stored per PAIR of training rows as [j][2] (a_k[j], a_k+1[j]): one 64-bit element feeds
+                    // records are stored per PAIR of training rows as [j][2] (a_k[j], a_k+1[j]): one 64-bit element feeds
                     // the packed fp32x2 pipe (sm_100 FADD2 / FFMA2), two K* entries per instruction
-                    const float2* rec = reinterpret_cast<const float2*>(prm.coords) + (long long)(kc * KCm + khalf * KPT) / 2 * CREC;
+                    const float2* rec = reinterpret_cast<const float2*>(s.coords[g & 1]) + (khalf * KPT) / 2 * CREC;
 #pragma unroll
                     for (int kk = 0; kk < KPT; kk += 2) {
                         float2 a[CREC];
 #pragma unroll
                         for (int q = 0; q < (DL + 1) / 2; q++) {
-                            const float4 r4 = __ldg(reinterpret_cast<const float4*>(rec + (kk / 2) * CREC + 2 * q));
+                            const float4 r4 = *reinterpret_cast<const float4*>(rec + (kk / 2) * CREC + 2 * q);
                             a[2 * q] = make_float2(r4.x, r4.y);
                             a[2 * q + 1] = make_float2(r4.z, r4.w);
                         }
@@ -480,6 +492,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) observe_tf32_kernel(const Params 
                         kv[kk] = ex2_approx(-dist.x);
                         kv[kk + 1] = ex2_approx(-dist.y);
                     }
+                    if (gt < CHUNK_FLOATS) s.coords[(g + 1) & 1][gt] = cnext;
+                    named_bar_sync(1, NGEN);  // next chunk's records visible; nobody still reads the buffer written next time
                     wait(&s.a_empty[sa], ((g / AST) & 1) ^ 1);
                     if (F16) {
                         // a = hi + 2^-11 lo: 16 consecutive k of one row = two 16-byte core-matrix rows per piece
