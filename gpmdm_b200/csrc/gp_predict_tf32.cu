@@ -685,10 +685,13 @@ __global__ void pack_whitened_f16_kernel(const double* __restrict__ W, long long
     dst[TILE_ELEMS + idx] = lo;
 }
 
-// CTA pairs (cta_group::2) unless GPMDM_TC_CLUSTER=0 or there are too few particle tiles to pair up
+// CTA pairs (cta_group::2) only on request (GPMDM_TC_CLUSTER=1).  Measured on B200 (profiles/tensor_core_variants_r02.md):
+// bit-identical results, but never faster than independent CTAs -- 3 % slower (fp16 split) to 22 % slower (tf32) at
+// N = 20 k, level / 11 % slower at N = 50 k: what the pair saves in W-tile bytes it loses on the cross-CTA hand-offs
+// (generators -> relay -> leader barrier, multicast commits back), even with 8- / 5-deep rings.
 static bool use_cluster(long long tiles) {
     const char* e = getenv("GPMDM_TC_CLUSTER");  // read per call: tests compare the two variants in one process
-    return !(e && e[0] == '0') && tiles >= 4;
+    return e && e[0] == '1' && tiles >= 4;
 }
 
 template <int DL, int MODE, int CG>
