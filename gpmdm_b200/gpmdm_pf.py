@@ -152,6 +152,8 @@ class GPMDM_PF:
             # graph (one pinned buffer each; `_graph_done` orders their reuse), so a frame is ONE launch from the host
             self._z_graph_pin = torch.empty(self.observation_dim, dtype=f64).pin_memory()
             self._summary_pin = torch.zeros(C + d + 1, dtype=f64).pin_memory()
+            self._z_graph_np, self._summary_np = self._z_graph_pin.numpy(), self._summary_pin.numpy()  # views: no torch op per frame
+            self._probs = [e(C), e(C)]  # class posteriors of the last two steps on the device (no clone per query)
             self._graph_done = torch.cuda.Event()
             self._summary_host_step = -1
         ws = int(self._lib.gpmdm_workspace_bytes(P, C))
@@ -395,22 +397,23 @@ class GPMDM_PF:
             self._Cl[par].copy_(self._particle_classes)
         if self._step_dev_host != self._step:
             self._step_dev.fill_(self._step)
-        src = z if isinstance(z, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(z))
-        if src.numel() != self.observation_dim:
+        src = np.asarray(z.detach().cpu() if isinstance(z, torch.Tensor) else z).reshape(-1)
+        if src.size != self.observation_dim:
             raise ValueError("z must have D = %d entries" % self.observation_dim)
         self._graph_done.synchronize()  # the previous replay has consumed / produced the pinned buffers
-        self._z_graph_pin.copy_(src.reshape(-1))
+        np.copyto(self._z_graph_np, src, casting="same_kind")
         if self._graphs[par] is None:  # every kernel has run at least once (function attributes are set): capture
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
                 self._z_buf.copy_(self._z_graph_pin, non_blocking=True)
                 self._issue_small(par, True, self._E, self._eps, self._u)
                 self._summary_pin.copy_(self._summary, non_blocking=True)
+                self._probs[par].copy_(self._summary[:self.num_classes])
             self._graphs[par] = g
         self._graphs[par].replay()
         self._graph_done.record()
         self._finish_small(par)
-        self._summary_host_step = self._step
+        self._summary_host_step, self._probs_par = self._step, par
 
     def _finish_small(self, par):
         self._small_steps += 1
@@ -425,8 +428,8 @@ class GPMDM_PF:
         """The summaries on the host: already there after a graph replay (pinned buffer written by the graph's last node)."""
         if self._small and self._summary_host_step == self._step:
             self._graph_done.synchronize()
-            return self._summary_pin
-        return self._summaries().cpu()
+            return self._summary_np
+        return self._summaries().cpu().numpy()
 
     @property
     def launches_per_step(self) -> int:
@@ -458,11 +461,13 @@ class GPMDM_PF:
         return float(self._summary_host()[self.num_classes + self.latent_dim])
 
     def class_probabilities(self):
+        if self._small and self._summary_host_step == self._step:
+            return self._probs[self._probs_par]  # written by the graph; stays valid until the step after next
         return self._summaries()[:self.num_classes].clone()
 
     def get_most_likely_class(self) -> int:
         # one device-to-host read of the class posteriors; argmax on the host (first maximum, as torch.argmax)
-        return int(torch.argmax(self._summary_host()[:self.num_classes]))
+        return int(np.argmax(self._summary_host()[:self.num_classes]))
 
     def current_state_mean(self):
         C = self.num_classes
