@@ -40,8 +40,8 @@ __global__ void __launch_bounds__(256) transition_kernel(const int64_t* __restri
 
 // ---- bucket by class (stable counting sort) ---------------------------------------------------------------
 // Each CTA handles BSUB consecutive 1024-particle sub-blocks, so that the single-CTA scan between the two passes has
-// 4x fewer entries to walk.
-constexpr int BSUB = 4;
+// BSUB x fewer entries to walk.
+constexpr int BSUB = 8;
 __global__ void __launch_bounds__(RB) bucket_count_kernel(const int64_t* __restrict__ cls, long long P, int C,
                                                           int nb, int32_t* __restrict__ counts /*[C][nb]*/) {
     extern __shared__ int sh_cnt[];
@@ -141,15 +141,20 @@ __global__ void __launch_bounds__(RB) bucket_scatter_kernel(const int64_t* __res
         const int rank = __popc(peers & ((1u << lane) - 1u));
         if (c >= 0 && rank == 0) wc[warp * C + c] = __popc(peers);
         __syncthreads();
-        // exclusive scan over warps, one thread per class, continuing from the earlier sub-blocks
-        for (int k = threadIdx.x; k < C; k += blockDim.x) {
-            int run = base[k];
-            for (int w = 0; w < 32; w++) {
-                const int v = wc[w * C + k];
-                wc[w * C + k] = run;
-                run += v;
+        // exclusive scan over the 32 warps' counts, one WARP per class (lane = warp index, five shuffle steps; a single
+        // thread walking the 32 counts per class left 1000 threads idle for 32 dependent shared-memory updates),
+        // continuing from the earlier sub-blocks
+        for (int k = warp; k < C; k += RB / 32) {
+            const int v = wc[lane * C + k];
+            int incl = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t;
             }
-            base[k] = run;
+            const int b = base[k];
+            wc[lane * C + k] = b + incl - v;
+            if (lane == 31) base[k] = b + incl;
         }
         __syncthreads();
         if (c >= 0) perm[offsets[(long long)c * nb + blockIdx.x] + wc[warp * C + c] + rank] = (int32_t)p;

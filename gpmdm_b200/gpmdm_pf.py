@@ -232,6 +232,26 @@ class GPMDM_PF:
         z = torch.as_tensor(np.asarray(z) if not isinstance(z, torch.Tensor) else z).to(device=self.device, dtype=torch.float64)
         self._update(z.contiguous(), draws)
 
+    @torch.no_grad()
+    def update_many(self, Z):
+        """Batched multi-frame update -- the caller loop of the reference's notebooks/test_gpmdm_pf.ipynb cell 4
+        (`for z in trial: pf.update(z); pf.get_most_likely_class(); pf.class_probabilities()`) as ONE call: the T
+        observations are uploaded once, the T steps and their summaries are enqueued back to back with no host
+        synchronisation in between, and the per-frame class posteriors [T, C], argmax classes [T] and state means [T, d]
+        come back as device tensors.  Identical to T calls of update() + the three queries."""
+        Z = torch.as_tensor(np.asarray(Z) if not isinstance(Z, torch.Tensor) else Z).to(device=self.device, dtype=torch.float64)
+        if Z.dim() != 2 or Z.shape[1] != self.observation_dim:
+            raise ValueError("Z must be [T, D = %d]" % self.observation_dim)
+        Z = Z.contiguous()
+        T, C, d = Z.shape[0], self.num_classes, self.latent_dim
+        out = torch.empty(T, C + d + 1, dtype=torch.float64, device=self.device)
+        for t in range(T):
+            self._update(Z[t])
+            out[t].copy_(self._summaries())
+        self._summary_host_step = -1
+        probs = out[:, :C]
+        return probs, torch.argmax(probs, dim=1), out[:, C:C + d].to(self.dtype)
+
     def _stage_z(self, z):
         """Host observation -> the persistent device buffer the step reads, through a small ring of pinned buffers (a slot
         is reused only after the copy that read it has completed)."""

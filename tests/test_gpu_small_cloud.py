@@ -93,3 +93,20 @@ def test_clouds_above_the_limit_take_the_general_path(setup):
     assert not pf._small and pf._lowlat
     pf.update(wl.test_trials[0][1][0])
     assert abs(float(pf._weights.sum()) - 1.0) < 1e-12
+
+
+@pytest.mark.parametrize("P", [100, 6000])
+def test_update_many_equals_frame_by_frame_updates(setup, P):
+    """The batched multi-frame call (small-cloud kernels at P = 100, the general native step at P = 6000) against the
+    reference-style loop of update() + queries: same posteriors, classes, state means and final cloud, bit for bit."""
+    spec, wl, f, model = setup
+    T = synthetic.markov_matrix(spec.n_classes)
+    trial = np.concatenate([wl.test_trials[0][1], wl.test_trials[1][1]], 0)
+    a, b = GPMDM_PF(model, T, P, seed=4), GPMDM_PF(model, T, P, seed=4)
+    probs, cls, means = a.update_many(trial)
+    for t, z in enumerate(trial):
+        b.update(z)
+        assert torch.equal(b.class_probabilities(), probs[t]) and b.get_most_likely_class() == int(cls[t])
+        assert torch.equal(b.current_state_mean(), means[t])
+    assert torch.equal(a._particle_states, b._particle_states) and torch.equal(a._particle_classes, b._particle_classes)
+    assert torch.equal(a._log_likelihoods, b._log_likelihoods) and a.get_most_likely_class() == b.get_most_likely_class()

@@ -37,6 +37,7 @@ def main():
     ap.add_argument("--precision", default="fp64")
     ap.add_argument("--no-graph", action="store_true", help="launch the small-cloud step directly instead of replaying a CUDA graph")
     ap.add_argument("--staged", action="store_true", help="the stage-by-stage launch sequence (round-1 path)")
+    ap.add_argument("--batched", action="store_true", help="one update_many() call per trial instead of the per-frame loop")
     a = ap.parse_args()
     from gpmdm_b200 import GPMDM, GPMDM_PF, synthetic
 
@@ -59,6 +60,18 @@ def main():
     for cls, trial in wl.test_trials:
         pf.reset()
         votes = np.zeros(C)
+        if a.batched:
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            probs, preds, _ = pf.update_many(trial)
+            preds = preds.cpu().numpy()
+            torch.cuda.synchronize()
+            secs += time.perf_counter() - t0
+            frames += len(trial)
+            for pred in preds:
+                frame_true.append(cls); frame_pred.append(int(pred)); votes[int(pred)] += 1
+            trial_true.append(cls); trial_pred.append(int(np.argmax(votes)))
+            continue
         for z in trial:
             torch.cuda.synchronize()
             t0 = time.perf_counter()
@@ -76,6 +89,7 @@ def main():
                     f"{a.trials} synthetic trials x {a.frames} frames, precision={a.precision}",
         "frame_accuracy": float(np.mean(ft == fp_)), "frame_f1": f1_macro(ft, fp_, C),
         "trial_accuracy": float(np.mean(tt == tp_)), "trial_f1": f1_macro(tt, tp_, C),
+        "driver": "update_many(trial): one call per trial" if a.batched else "per-frame loop: update, get_most_likely_class, class_probabilities",
         "step_path": ("small-cloud kernels, " + ("CUDA graph replay" if pf._use_graph else "direct launches")) if pf._small
                      else ("native launch sequence" if pf._native_step else "staged launches"),
         "launches_per_step": pf.launches_per_step,
