@@ -456,7 +456,12 @@ def run_ours(a):
                 "peak_source": ("tcgen05.mma kind::%s M128 N256 K%d issue-rate probe (resident pseudo-random operands) measured in this "
                                 "run; achieved counts the MMA flops issued (3 per product) over the tensor-core kernel's own launch "
                                 "time (rank 0)" % (("f16", 16) if f16 else ("tf32", 8))),
+                # kind::f16 MMAs run on the pipe the driver's cuBLAS bf16 GEMM measures (MEASURED_PEAKS.json): burst, and
+                # sustained for seconds under the power cap -- the regime of this kernel inside a long step
                 "measured_peaks_bf16_tflops": measured_peak("bf16_tflops"),
+                "measured_peaks_bf16_tflops_sustained": measured_peak("bf16_tflops_sustained"),
+                "frac_of_measured_bf16_sustained": (achieved / measured_peak("bf16_tflops_sustained"))
+                if (f16 and measured_peak("bf16_tflops_sustained")) else None,
                 "algorithmic_tflops": flops_alg32 / secs / 1e12, "algorithmic_frac": flops_alg32 / secs / 1e12 / tf,
             }
         cpu, parity = None, None

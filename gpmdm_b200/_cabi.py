@@ -107,7 +107,8 @@ _lib = None
 
 
 def library_path() -> str:
-    return _build.LIB_PATH
+    # GPMDM_LIBRARY: another build of the same sources (tuning experiments); the default is the in-tree build
+    return os.environ.get("GPMDM_LIBRARY") or _build.LIB_PATH
 
 
 def lib() -> ctypes.CDLL:

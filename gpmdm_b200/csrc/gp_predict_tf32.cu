@@ -43,8 +43,14 @@ namespace tf32 {
 constexpr int MODE_TF32X3 = 0, MODE_F16X2 = 1;
 constexpr int TM = 128;      // particles per CTA tile (UMMA M)
 constexpr int TN = 256;      // columns per column tile (UMMA N)
-constexpr int ASTAGES = 4;
-constexpr int BSTAGES = 3;
+#ifndef GPMDM_TC_ASTAGES
+#define GPMDM_TC_ASTAGES 4
+#endif
+#ifndef GPMDM_TC_BSTAGES
+#define GPMDM_TC_BSTAGES 3
+#endif
+constexpr int ASTAGES = GPMDM_TC_ASTAGES;  // ring depths of the single-CTA variant (tuning experiments: -DGPMDM_TC_ASTAGES=..)
+constexpr int BSTAGES = GPMDM_TC_BSTAGES;
 constexpr int A_HALF_BYTES = TM * 16 * 4;   // bytes in the hi (or lo) part of an A stage: 8 KB in both modes
 constexpr int B_HALF_BYTES = TN * 16 * 4;   // bytes in the hi (or lo) part of a B stage / packed tile: 16 KB
 constexpr int NGEN = 256;                // generator threads
