@@ -63,6 +63,8 @@ _SIGNATURES = {
     "gpmdm_pf_observe_kstar_workspace_bytes": (_i64, [_i64]),
     "gpmdm_pf_observe_cached_f64": (ctypes.c_int, [ctypes.POINTER(GpModel), _ptr, _i64, _ptr, _f64, _ptr, _ptr, _ptr,
                                                    _i64, _ptr, _ptr, _i64, _ptr]),
+    "gpmdm_pf_propagate_cached_f64": (ctypes.c_int, [ctypes.POINTER(GpModel), _ptr, _ptr, _ptr, _ptr, _i64, _ptr, _ptr,
+                                                     _ptr, _ptr, _i64, _ptr, _ptr, _i64, _ptr]),
     "gpmdm_pf_loglik_f64": (ctypes.c_int, [ctypes.POINTER(GpModel), _ptr, _i64, _ptr, _f64, _ptr, _ptr, _ptr, _ptr,
                                            _ptr]),
     "gpmdm_predict_lowlat_workspace_bytes": (_i64, [_i64, _i64, _i32, _i32]),

@@ -660,16 +660,17 @@ static int launch_instance(const PredictParams& prm, int grid, cudaStream_t st) 
     return check_launch("gp_predict_kernel");
 }
 
+template <int KIND>
 static int dispatch_d_cached(const PredictParams& prm, int grid, cudaStream_t st) {
     switch (prm.d) {
-        case 1: return launch_instance<0, 1, true>(prm, grid, st);
-        case 2: return launch_instance<0, 2, true>(prm, grid, st);
-        case 3: return launch_instance<0, 3, true>(prm, grid, st);
-        case 4: return launch_instance<0, 4, true>(prm, grid, st);
-        case 5: return launch_instance<0, 5, true>(prm, grid, st);
-        case 6: return launch_instance<0, 6, true>(prm, grid, st);
-        case 7: return launch_instance<0, 7, true>(prm, grid, st);
-        case 8: return launch_instance<0, 8, true>(prm, grid, st);
+        case 1: return launch_instance<KIND, 1, true>(prm, grid, st);
+        case 2: return launch_instance<KIND, 2, true>(prm, grid, st);
+        case 3: return launch_instance<KIND, 3, true>(prm, grid, st);
+        case 4: return launch_instance<KIND, 4, true>(prm, grid, st);
+        case 5: return launch_instance<KIND, 5, true>(prm, grid, st);
+        case 6: return launch_instance<KIND, 6, true>(prm, grid, st);
+        case 7: return launch_instance<KIND, 7, true>(prm, grid, st);
+        case 8: return launch_instance<KIND, 8, true>(prm, grid, st);
     }
     set_error("latent dimension %d outside [1, %d]", prm.d, MAXD);
     return GPMDM_E_UNSUPPORTED;
@@ -730,10 +731,10 @@ static void fill_common(PredictParams& prm, const gpmdm_gp_model* m) {
 
 using namespace gpmdm;
 
-extern "C" int gpmdm_pf_propagate_f64(const gpmdm_gp_model* dyn, const double* x_prev, const int32_t* perm,
-                                      const int32_t* tiles, const int32_t* n_tiles, int64_t P, const double* eps,
-                                      double* x_new, double* mean_out, double* var_out, int32_t* tile_counter,
-                                      void* stream) {
+static int propagate_impl(const gpmdm_gp_model* dyn, const double* x_prev, const int32_t* perm, const int32_t* tiles,
+                          const int32_t* n_tiles, int64_t P, const double* eps, double* x_new, double* mean_out,
+                          double* var_out, int32_t* tile_counter, void* stream, void* kstar_ws, int64_t kstar_ws_bytes,
+                          int64_t max_n_pad) {
     if (int rc = validate_model(dyn, 1)) return rc;
     GPMDM_REQUIRE(P >= 0 && P < (1ll << 31), GPMDM_E_INVALID, "P = %lld out of range", (long long)P);
     if (P == 0) return 0;
@@ -758,7 +759,37 @@ extern "C" int gpmdm_pf_propagate_f64(const gpmdm_gp_model* dyn, const double* x
     GPMDM_REQUIRE(e == cudaSuccess, (int)e, "cudaMemsetAsync: %s", cudaGetErrorString(e));
     const long long max_tiles = (P + TM - 1) / TM + dyn->n_blocks;
     const int grid = (int)(max_tiles < num_sms() ? max_tiles : num_sms());
+    if (kstar_ws) {
+        prm.kcache = static_cast<double*>(kstar_ws);
+        prm.kcache_stride = (long long)max_n_pad * TM;  // the kernel traps if a block on the device is larger
+        GPMDM_REQUIRE((int64_t)grid * prm.kcache_stride * 8 <= kstar_ws_bytes, GPMDM_E_INVALID,
+                      "K* workspace too small: %lld bytes for %d CTAs x n_pad %lld", (long long)kstar_ws_bytes, grid,
+                      (long long)max_n_pad);
+        return dispatch_d_cached<1>(prm, grid, st);
+    }
     return dispatch_d<1>(prm, grid, st);
+}
+
+extern "C" int gpmdm_pf_propagate_f64(const gpmdm_gp_model* dyn, const double* x_prev, const int32_t* perm,
+                                      const int32_t* tiles, const int32_t* n_tiles, int64_t P, const double* eps,
+                                      double* x_new, double* mean_out, double* var_out, int32_t* tile_counter,
+                                      void* stream) {
+    return propagate_impl(dyn, x_prev, perm, tiles, n_tiles, P, eps, x_new, mean_out, var_out, tile_counter, stream, nullptr,
+                          0, 0);
+}
+
+// The same call with the per-CTA K* cache of gpmdm_pf_observe_cached_f64 (one slice of max_n_pad x 64 doubles per CTA; the
+// two calls of a step may share the scratch): each class block's cross-kernel is evaluated once per particle tile.
+// Bit-identical results; pays from ~4 column panels per block (N_c >= 1024).
+extern "C" int gpmdm_pf_propagate_cached_f64(const gpmdm_gp_model* dyn, const double* x_prev, const int32_t* perm,
+                                             const int32_t* tiles, const int32_t* n_tiles, int64_t P, const double* eps,
+                                             double* x_new, double* mean_out, double* var_out, int64_t max_n_pad,
+                                             int32_t* tile_counter, void* kstar_ws, int64_t kstar_ws_bytes, void* stream) {
+    GPMDM_REQUIRE(kstar_ws != nullptr && kstar_ws_bytes > 0, GPMDM_E_INVALID, "K* workspace is required");
+    GPMDM_REQUIRE(max_n_pad > 0 && max_n_pad % TN == 0, GPMDM_E_INVALID,
+                  "max_n_pad must be the largest padded block size (multiple of %d)", TN);
+    return propagate_impl(dyn, x_prev, perm, tiles, n_tiles, P, eps, x_new, mean_out, var_out, tile_counter, stream, kstar_ws,
+                          kstar_ws_bytes, max_n_pad);
 }
 
 static int observe_impl(const gpmdm_gp_model* obs, const double* x, int64_t P, const double* z, double ll_const,
@@ -826,7 +857,7 @@ static int observe_impl(const gpmdm_gp_model* obs, const double* x, int64_t P, c
         GPMDM_REQUIRE((int64_t)grid * prm.kcache_stride * 8 <= kstar_ws_bytes, GPMDM_E_INVALID,
                       "K* workspace too small: %lld bytes for %d CTAs x n_pad %lld", (long long)kstar_ws_bytes, grid,
                       (long long)ws_n_pad);
-        return dispatch_d_cached(prm, grid, st);
+        return dispatch_d_cached<0>(prm, grid, st);
     }
     return dispatch_d<0>(prm, grid, st);
 }

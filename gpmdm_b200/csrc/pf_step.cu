@@ -35,8 +35,15 @@ extern "C" int gpmdm_pf_step_local_f64(const gpmdm_pf_step_args* a, void* stream
         GPMDM_TRY(gpmdm_pf_observe_lowlat_f64(a->obs, x_new, n, a->z, a->ll_const, nullptr, ll, nullptr, nullptr,
                                               a->obs_n_pad, a->obs_seg_chunks, a->tile_counter, a->lowlat_workspace, stream));
     } else {
-        GPMDM_TRY(gpmdm_pf_propagate_f64(a->dyn, a->x_prev, a->perm, a->tiles, a->n_tiles, n, a->eps, x_new, nullptr, nullptr,
-                                         a->tile_counter, stream));
+        // the K* cache pays from ~4 column panels per class block; its scratch is shared with the observation call
+        if (a->predict_mode == 1 && a->dyn_max_n_pad >= 4 * GPMDM_TILE_N &&
+            (int64_t)a->dyn_max_n_pad <= a->obs_n_pad)
+            GPMDM_TRY(gpmdm_pf_propagate_cached_f64(a->dyn, a->x_prev, a->perm, a->tiles, a->n_tiles, n, a->eps, x_new, nullptr,
+                                                    nullptr, a->dyn_max_n_pad, a->tile_counter, a->kstar_workspace,
+                                                    a->kstar_workspace_bytes, stream));
+        else
+            GPMDM_TRY(gpmdm_pf_propagate_f64(a->dyn, a->x_prev, a->perm, a->tiles, a->n_tiles, n, a->eps, x_new, nullptr, nullptr,
+                                             a->tile_counter, stream));
         if (a->predict_mode == 1)
             GPMDM_TRY(gpmdm_pf_observe_cached_f64(a->obs, x_new, n, a->z, a->ll_const, ll, nullptr, nullptr, a->obs_n_pad,
                                                   a->tile_counter, a->kstar_workspace, a->kstar_workspace_bytes, stream));

@@ -896,7 +896,7 @@ class GPMDM(torch.nn.Module):
         return (mu + torch.tensor(self.meanY, dtype=F64, device=self.device)).to(self.dtype), var.to(self.dtype)
 
     @torch.no_grad()
-    def map_x_dynamics_for_class(self, Xstar, class_index: int, flg_noise=False, low_latency=None):
+    def map_x_dynamics_for_class(self, Xstar, class_index: int, flg_noise=False, low_latency=None, kstar_cache=None):
         lib = _cabi.lib()
         pk = self.packed_models()
         if pk["dyn"] is None:
@@ -919,6 +919,12 @@ class GPMDM(torch.nn.Module):
                                                     P, None, None, ptr(mean), ptr(var), pk["dyn_max_n_pad"], 0,
                                                     ptr(self._scratch_counter()), ptr(ws), stream()),
                   "gpmdm_pf_propagate_lowlat_f64")
+        elif self._use_kstar_cache(pk["dyn_max_n_pad"], kstar_cache):
+            ws = self._kstar_workspace(pk["dyn_max_n_pad"])
+            check(lib.gpmdm_pf_propagate_cached_f64(ctypes.byref(pk["dyn"]), ptr(Xs), ptr(perm), ptr(tiles), ptr(n_tiles), P,
+                                                    None, None, ptr(mean), ptr(var), pk["dyn_max_n_pad"],
+                                                    ptr(self._scratch_counter()), ptr(ws), ws.numel() * 8, stream()),
+                  "gpmdm_pf_propagate_cached_f64")
         else:
             check(lib.gpmdm_pf_propagate_f64(ctypes.byref(pk["dyn"]), ptr(Xs), ptr(perm), ptr(tiles), ptr(n_tiles), P,
                                              None, None, ptr(mean), ptr(var), ptr(self._scratch_counter()), stream()),

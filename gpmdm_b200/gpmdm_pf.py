@@ -113,6 +113,10 @@ class GPMDM_PF:
         self._lowlat = gpmdm._use_lowlat(self._num_particles, low_latency)
         self._kstar_cache = (precision == "fp64" and not self._lowlat
                              and gpmdm._use_kstar_cache(self._packed["obs_n_pad"], kstar_cache))
+        # ... and the dynamics kernel shares that scratch when its class blocks are large enough for the cache to pay
+        # (same rule as csrc/pf_step.cu: >= 4 column panels, no block larger than the observation block)
+        self._kstar_cache_dyn = (self._kstar_cache and self._packed["dyn_max_n_pad"] >= 4 * _cabi.TILE_N
+                                 and self._packed["dyn_max_n_pad"] <= self._packed["obs_n_pad"])
         self._native_step = bool(native_step) and precision == "fp64"
         # small-cloud step: draws+transition+bucketing and normalise+cdf+resample+summaries as two single-CTA kernels
         self._small = (self._native_step and self._lowlat and self._world == 1
@@ -309,6 +313,12 @@ class GPMDM_PF:
                                                     ptr(self._tiles), ptr(self._n_tiles), Pl, ptr(eps), ptr(x_new_l), None,
                                                     None, self._packed["dyn_max_n_pad"], self._seg_dyn, ptr(self._counter),
                                                     ptr(self._ws_lowlat), st), "gpmdm_pf_propagate_lowlat_f64")
+        elif self._kstar_cache_dyn:
+            check(lib.gpmdm_pf_propagate_cached_f64(ctypes.byref(self._packed["dyn"]), ptr(x_prev), ptr(self._perm),
+                                                    ptr(self._tiles), ptr(self._n_tiles), Pl, ptr(eps), ptr(x_new_l), None,
+                                                    None, self._packed["dyn_max_n_pad"], ptr(self._counter),
+                                                    ptr(self._ws_kstar), self._ws_kstar.numel() * 8, st),
+                  "gpmdm_pf_propagate_cached_f64")
         else:
             check(lib.gpmdm_pf_propagate_f64(ctypes.byref(self._packed["dyn"]), ptr(x_prev), ptr(self._perm),
                                              ptr(self._tiles), ptr(self._n_tiles), Pl, ptr(eps), ptr(x_new_l), None, None,

@@ -153,6 +153,13 @@ int gpmdm_pf_observe_cached_f64(const gpmdm_gp_model* obs, const double* x, int6
                                 double ll_const, double* ll, double* mu_out, double* v_out, int64_t n_pad,
                                 int32_t* tile_counter, void* kstar_ws, int64_t kstar_ws_bytes, void* stream);
 
+/* gpmdm_pf_propagate_f64 with the same per-CTA K* cache (max_n_pad = largest padded block of `dyn`; the scratch may be
+ * the one passed to gpmdm_pf_observe_cached_f64, the two calls of a step run one after the other).  Bit-identical. */
+int gpmdm_pf_propagate_cached_f64(const gpmdm_gp_model* dyn, const double* x_prev, const int32_t* perm,
+                                  const int32_t* tiles, const int32_t* n_tiles, int64_t P, const double* eps,
+                                  double* x_new, double* mean_out, double* var_out, int64_t max_n_pad,
+                                  int32_t* tile_counter, void* kstar_ws, int64_t kstar_ws_bytes, void* stream);
+
 /* Mean and log-likelihood only, with the predictive variances v_in [P] supplied by the caller (the tf32 variant
  * computes them on tcgen05 tensor cores): the N x D mean contraction stays in fp64 because alpha = K^-1 Y cancels
  * heavily; it is 2ND of the 2N^2 + 2ND flops.  The blocks of `obs` may have L == NULL for this call. */

@@ -114,6 +114,10 @@ def test_cfg3_dynamics_gp_vs_oracle(cfg3):
             mean, var = model.map_x_dynamics_for_class(xs.cuda(), c, low_latency=low)
             assert scaled_err(mean.cpu(), mean_o, sc) < TOL
             assert scaled_err(var.cpu(), var_o, prior.unsqueeze(1) * lam_x.unsqueeze(0)) < 4 * TOL
+        # the K* cache instance of the dynamics kernel (10 column panels per class block here) against the on-the-fly one
+        m_c, v_c = model.map_x_dynamics_for_class(xs.cuda(), c, low_latency=False, kstar_cache=True)
+        m_f, v_f = model.map_x_dynamics_for_class(xs.cuda(), c, low_latency=False, kstar_cache=False)
+        assert torch.equal(m_c, m_f) and torch.equal(v_c, v_f)
 
 
 @pytest.mark.parametrize("mode", ["cached", "lowlat"])
