@@ -88,7 +88,7 @@ struct PredictParams {
     double* mean_out;
     double* var_out;
     // observation epilogue
-    const double* v_in;  // mean-only mode: variances supplied (tf32 variant), skip the quadratic form
+    const double* v_in;  // mean-only mode: variances supplied (tensor-core variants), skip the quadratic form
     const double* z;
     double ll_const;  // 2 sum_j log lambda_j - c32
     double* ll;
@@ -311,7 +311,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gp_predict_kernel(const PredictPa
         const int nkc = (int)((gbk.n + KC - 1) / KC);
         const int nq = n_pad / TN;               // column tiles of L
         const int nct = nq + prm.alpha_ld / TN;  // + column tiles of alpha
-        const int ct0 = (KIND == 0 && prm.v_in) ? nq : 0;  // mean-only mode starts at the alpha tiles
+        const int ct0 = prm.v_in ? nq : 0;  // mean-only mode (variances supplied) starts at the alpha tiles
         int ct_begin = ct0, ct_end = nct;
         int kfirst = -1, kend = nkc;  // k-chunk range of the work item (split mode: one segment of one column tile)
         if (prm.split) {
@@ -400,7 +400,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gp_predict_kernel(const PredictPa
         ChunkCursor cur;
         cur.init(nq, ct_end, nkc, prm.tri, ct_begin, gbk, kfirst, prm.split ? kend : -1);
         double qacc = 0.0, sacc = 0.0, vrow = 0.0;
-        if (KIND == 0 && prm.v_in) vrow = pidx >= 0 ? prm.v_in[pidx] : 1.0;
+        if (prm.v_in) vrow = pidx >= 0 ? prm.v_in[pidx] : 1.0;
 
         for (int ct = ct_begin; ct < ct_end; ct++) {
             double acc[NJ][2];
@@ -734,7 +734,7 @@ using namespace gpmdm;
 static int propagate_impl(const gpmdm_gp_model* dyn, const double* x_prev, const int32_t* perm, const int32_t* tiles,
                           const int32_t* n_tiles, int64_t P, const double* eps, double* x_new, double* mean_out,
                           double* var_out, int32_t* tile_counter, void* stream, void* kstar_ws, int64_t kstar_ws_bytes,
-                          int64_t max_n_pad) {
+                          int64_t max_n_pad, const double* v_in = nullptr) {
     if (int rc = validate_model(dyn, 1)) return rc;
     GPMDM_REQUIRE(P >= 0 && P < (1ll << 31), GPMDM_E_INVALID, "P = %lld out of range", (long long)P);
     if (P == 0) return 0;
@@ -755,6 +755,7 @@ static int propagate_impl(const gpmdm_gp_model* dyn, const double* x_prev, const
     prm.x_new = x_new;
     prm.mean_out = mean_out;
     prm.var_out = var_out;
+    prm.v_in = v_in;
     cudaError_t e = cudaMemsetAsync(tile_counter, 0, 2 * sizeof(int32_t), st);
     GPMDM_REQUIRE(e == cudaSuccess, (int)e, "cudaMemsetAsync: %s", cudaGetErrorString(e));
     const long long max_tiles = (P + TM - 1) / TM + dyn->n_blocks;
@@ -815,6 +816,15 @@ extern "C" int gpmdm_pf_observe_cached_f64(const gpmdm_gp_model* obs, const doub
     GPMDM_REQUIRE(n_pad > 0 && n_pad % TN == 0, GPMDM_E_INVALID, "n_pad must be the block's padded size (multiple of %d)", TN);
     return observe_impl(obs, x, P, z, ll_const, nullptr, ll, mu_out, v_out, tile_counter, stream, kstar_ws,
                         kstar_ws_bytes, n_pad);
+}
+
+extern "C" int gpmdm_pf_propagate_meanonly_f64(const gpmdm_gp_model* dyn, const double* x_prev, const int32_t* perm,
+                                               const int32_t* tiles, const int32_t* n_tiles, int64_t P, const double* eps,
+                                               const double* v_in, double* x_new, double* mean_out, double* var_out,
+                                               int32_t* tile_counter, void* stream) {
+    GPMDM_REQUIRE(v_in != nullptr, GPMDM_E_INVALID, "v_in is required");
+    return propagate_impl(dyn, x_prev, perm, tiles, n_tiles, P, eps, x_new, mean_out, var_out, tile_counter, stream, nullptr,
+                          0, 0, v_in);
 }
 
 extern "C" int gpmdm_pf_loglik_f64(const gpmdm_gp_model* obs, const double* x, int64_t P, const double* z,

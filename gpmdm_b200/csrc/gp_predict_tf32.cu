@@ -85,7 +85,8 @@ template <int CG>
 struct __align__(1024) SmemT {
     unsigned char A[Ring<CG>::A][2][A_HALF_BYTES];        // [stage][hi|lo]
     unsigned char B[Ring<CG>::B][2][B_HALF_BYTES / CG];   // [stage][hi|lo], this CTA's share of the 256 rows
-    float coords[2][32 * CREC];                           // the generators' double buffer: one chunk of training records
+    float coords[2][2][32 * CREC];                        // the generators' double buffer: one chunk of training records
+                                                          // ([1]: the linear-kernel records of the dynamics GP)
     uint64_t a_full[Ring<CG>::A], a_empty[Ring<CG>::A], b_full[Ring<CG>::B], b_empty[Ring<CG>::B], t_full[2], t_empty[2];
     uint32_t tmem_base;
 };
@@ -107,6 +108,12 @@ struct Params {
     double* v_out;
     int32_t* round_counter;  // device scratch (zeroed by the call), NULL = no round synchronisation
     int32_t* status;         // particles whose variance was not a positive finite number (NULL = not counted)
+    // KIND 1 (dynamics GP): class-homogeneous 128-particle tiles over per-class blocks
+    const gpmdm_tc_block* dblocks;  // device, one per class
+    const int32_t* perm;            // particles ordered by (class, index)
+    const int32_t* tiles;           // {block, first position in perm, count, 0} per tile
+    const int32_t* n_tiles_dev;     // device int
+    const double* lin_c2;           // [d + 1]
 };
 
 // element (row, k) of a [rows x KC] operand tile in the canonical no-swizzle K-major layout, in elements
@@ -259,7 +266,16 @@ __device__ __forceinline__ void mbar_wait_b(uint64_t* bar, uint32_t parity) {
     __trap();
 }
 
-template <int DL, int MODE, int CG>
+// What one work unit (a 128-particle tile) runs against: the observation GP's single block, or -- KIND 1, the dynamics GP
+// (gpmdm.py:1032-1068) -- the block of the tile's class, with the particles reached through the class-sorted permutation.
+struct Unit {
+    const float* coords;
+    const float* lin;
+    const unsigned char* wt;
+    int nq, nkc, nct, first, count;
+};
+
+template <int DL, int MODE, int CG, int KIND = 0>
 __global__ void __launch_bounds__(NTHREADS, 1) observe_tf32_kernel(const Params prm) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     SmemT<CG>& s = *reinterpret_cast<SmemT<CG>*>(smem_raw);
@@ -270,10 +286,24 @@ __global__ void __launch_bounds__(NTHREADS, 1) observe_tf32_kernel(const Params 
     constexpr int BH = B_HALF_BYTES / CG;                    // bytes of one piece (hi or lo) of this CTA's share of a W tile
     // accumulator buffers: two in tf32 mode; one in F16X2 mode, where D1 | D2 fill all 512 TMEM columns
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int nq = prm.n_pad / TN, nkc = prm.n_pad / KCm;
-    // + one alpha tile (dout <= 256) when a mean is wanted (tf32 mode only: the fp16 split is used for variances)
-    const int nct = nq + ((!F16 && (prm.ll || prm.mu_out)) ? 1 : 0);
-    const int n_tiles = (int)((prm.P + TM - 1) / TM);
+    static_assert(KIND == 0 || CG == 1, "the two tiles of a CTA pair would belong to different class blocks");
+    // + one alpha tile (dout <= 256) when a mean is wanted (tf32 observation mode only: the variants compute variances)
+    const int n_tiles = KIND == 1 ? __ldg(prm.n_tiles_dev) : (int)((prm.P + TM - 1) / TM);
+    auto unit = [&](int t) {
+        Unit un;
+        if (KIND == 1) {
+            const gpmdm_tc_block b = prm.dblocks[prm.tiles[4 * t]];
+            un.coords = b.coords, un.lin = b.lin, un.wt = reinterpret_cast<const unsigned char*>(b.wtiles);
+            un.nq = (int)(b.n_pad / TN), un.nkc = (int)(b.n_pad / KCm), un.nct = un.nq;
+            un.first = prm.tiles[4 * t + 1], un.count = prm.tiles[4 * t + 2];
+        } else {
+            un.coords = prm.coords, un.lin = nullptr, un.wt = reinterpret_cast<const unsigned char*>(prm.wtiles);
+            un.nq = prm.n_pad / TN, un.nkc = prm.n_pad / KCm;
+            un.nct = un.nq + ((!F16 && (prm.ll || prm.mu_out)) ? 1 : 0);
+            un.first = t * TM, un.count = TM;
+        }
+        return un;
+    };
     // work units: particle tiles (CG = 1), or PAIRS of particle tiles 2u, 2u+1 handled by the two CTAs of a cluster
     const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;
     const bool leader = rank == 0;
@@ -320,19 +350,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) observe_tf32_kernel(const Params 
     };
 
     // chunk count of column tile ct: W tiles are lower triangular (k < 256 (J+1)); the alpha tile needs all k
-    auto chunks_of = [&](int ct) { return ct < nq ? (ct + 1) * (TN / KCm) : nkc; };
+    auto chunks_of = [&](const Unit& un, int ct) { return ct < un.nq ? (ct + 1) * (TN / KCm) : un.nkc; };
 
     if (warp == 0) {
         // ===================== TMA producer =====================
         if (lane == 0) {
             uint32_t g = 0;
             int rounds = 0;
-            const unsigned char* wt = reinterpret_cast<const unsigned char*>(prm.wtiles);
             const unsigned char* at = reinterpret_cast<const unsigned char*>(prm.atiles);
             for (int u = unit0; u < n_units; u += unit_stride) {
-                for (int ct = 0; ct < nct; ct++) {
-                    const unsigned char* base = ct < nq ? wt + wtile_offset_kc(ct, KCm) * (2 * B_HALF_BYTES) : at;
-                    const int nch = chunks_of(ct);
+                const Unit un = unit(tile_of(u) < n_tiles ? tile_of(u) : n_tiles - 1);
+                for (int ct = 0; ct < un.nct; ct++) {
+                    const unsigned char* base = ct < un.nq ? un.wt + wtile_offset_kc(ct, KCm) * (2 * B_HALF_BYTES) : at;
+                    const int nch = chunks_of(un, ct);
                     for (int kc = 0; kc < nch; kc++, g++) {
                         const int st = g % BST;
                         wait(&s.b_empty[st], ((g / BST) & 1) ^ 1);
@@ -367,14 +397,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) observe_tf32_kernel(const Params 
         // ===================== MMA issuer (the pair's leader CTA issues for both) =====================
         if (lane == 0 && leader) {
             uint32_t g = 0, tcount = 0;
-            for (int u = unit0; u < n_units; u += unit_stride)
-                for (int ct = 0; ct < nct; ct++, tcount++) {
+            for (int u = unit0; u < n_units; u += unit_stride) {
+                const Unit un = unit(tile_of(u) < n_tiles ? tile_of(u) : n_tiles - 1);
+                for (int ct = 0; ct < un.nct; ct++, tcount++) {
                     const int acc = F16 ? 0 : (tcount & 1);
                     const uint32_t use = F16 ? tcount : (tcount >> 1);     // how often this buffer has been used before
                     wait(&s.t_empty[acc], (use & 1) ^ 1);  // epilogue drained this accumulator
                     tc_fence_after();
                     const uint32_t d_tmem = tmem + (uint32_t)acc * TN;
-                    const int nch = chunks_of(ct);
+                    const int nch = chunks_of(un, ct);
                     for (int kc = 0; kc < nch; kc++, g++) {
                         const int sa = g % AST, sb = g % BST;
                         wait(&s.a_full[sa], (g / AST) & 1);
@@ -419,6 +450,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) observe_tf32_kernel(const Params 
                     if (CG == 2) umma_commit_2cta(&s.t_full[acc]);
                     else umma_commit(&s.t_full[acc]);  // accumulator complete
                 }
+            }
         }
     } else if (CG == 2 && !leader && (warp == 2 || warp == 3)) {
         // ===================== relays (second CTA of a pair): local "full" -> the leader's barrier =====================
@@ -426,9 +458,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) observe_tf32_kernel(const Params 
         // copies, and one thread per ring forwards each completion with a single remote arrive.
         if (lane == 0) {
             uint32_t g = 0;
-            for (int u = unit0; u < n_units; u += unit_stride)
-                for (int ct = 0; ct < nct; ct++) {
-                    const int nch = chunks_of(ct);
+            for (int u = unit0; u < n_units; u += unit_stride) {
+                const Unit un = unit(tile_of(u) < n_tiles ? tile_of(u) : n_tiles - 1);
+                for (int ct = 0; ct < un.nct; ct++) {
+                    const int nch = chunks_of(un, ct);
                     for (int kc = 0; kc < nch; kc++, g++) {
                         if (warp == 2) {
                             const int sa = g % AST;
@@ -441,6 +474,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) observe_tf32_kernel(const Params 
                         }
                     }
                 }
+            }
         }
     } else if (warp >= GEN_WARP0 && warp < EPI_WARP0) {
         // ===================== K* generators =====================
@@ -456,30 +490,54 @@ __global__ void __launch_bounds__(NTHREADS, 1) observe_tf32_kernel(const Params 
         // 12 % of them that missed L1 were the kernel's largest stall, profiles/ncu_observe_f16x2_kernel_r02.txt.)
         constexpr int CHUNK_FLOATS = KCm * CREC;  // 256 (fp16) / 128 (tf32)
         uint32_t g = 0;
-        if (gt < CHUNK_FLOATS) s.coords[0][gt] = __ldg(prm.coords + gt);  // chunk 0 of the first column tile
+        if (unit0 < n_units && gt < CHUNK_FLOATS) {  // chunk 0 of the first unit
+            const Unit un0 = unit(tile_of(unit0) < n_tiles ? tile_of(unit0) : n_tiles - 1);
+            s.coords[0][0][gt] = __ldg(un0.coords + gt);
+            if (KIND == 1) s.coords[0][1][gt] = __ldg(un0.lin + gt);
+        }
         named_bar_sync(1, NGEN);
         for (int u = unit0; u < n_units; u += unit_stride) {
-            long long p = (long long)tile_of(u) * TM + row;
-            if (p >= prm.P) p = prm.P - 1;
+            const Unit un = unit(tile_of(u) < n_tiles ? tile_of(u) : n_tiles - 1);
+            // the records that follow this unit's last chunk: chunk 0 of the next unit's block
+            const float *nxt_c = un.coords, *nxt_l = un.lin;
+            if (KIND == 1 && u + unit_stride < n_units) {
+                const Unit nu = unit(tile_of(u + unit_stride) < n_tiles ? tile_of(u + unit_stride) : n_tiles - 1);
+                nxt_c = nu.coords, nxt_l = nu.lin;
+            }
+            long long p;
+            if (KIND == 1) p = prm.perm[un.first + (row < un.count ? row : un.count - 1)];
+            else {
+                p = (long long)tile_of(u) * TM + row;
+                if (p >= prm.P) p = prm.P - 1;
+            }
             // particle coordinates, negated and duplicated into both halves of a packed f32x2 register
-            float2 nb[DL];
+            float2 nb[DL], xp[KIND == 1 ? DL : 1];
+            float c2last = 0.f;
 #pragma unroll
             for (int j = 0; j < DL; j++) {
-                const float bj = (float)(prm.x[p * DL + j] / prm.ls[j] * SQRT_LOG2E);
+                const double xj = prm.x[p * DL + j];
+                const float bj = (float)(xj / prm.ls[j] * SQRT_LOG2E);
                 nb[j] = make_float2(-bj, -bj);
+                if (KIND == 1) xp[j] = make_float2((float)xj, (float)xj);
             }
-            for (int ct = 0; ct < nct; ct++) {
-                const int nch = chunks_of(ct);
+            if (KIND == 1) c2last = (float)prm.lin_c2[DL];
+            for (int ct = 0; ct < un.nct; ct++) {
+                const int nch = chunks_of(un, ct);
                 for (int kc = 0; kc < nch; kc++, g++) {
                     const int sa = g % AST;
-                    // the next chunk of this thread's walk (every column tile, and every unit, starts again at k = 0)
-                    const int kn = kc + 1 < nch ? kc + 1 : 0;
-                    float cnext = 0.f;
-                    if (gt < CHUNK_FLOATS) cnext = __ldg(prm.coords + (long long)kn * CHUNK_FLOATS + gt);
+                    // the next chunk of this thread's walk (every column tile starts again at k = 0)
+                    const bool last = kc + 1 == nch && ct + 1 == un.nct;
+                    const long long noff = (long long)(kc + 1 < nch ? kc + 1 : 0) * CHUNK_FLOATS + gt;
+                    float cnext = 0.f, lnext = 0.f;
+                    if (gt < CHUNK_FLOATS) {
+                        cnext = __ldg((last ? nxt_c : un.coords) + noff);
+                        if (KIND == 1) lnext = __ldg((last ? nxt_l : un.lin) + noff);
+                    }
                     float kv[KPT];
                     // records are stored per PAIR of training rows as [j][2] (a_k[j], a_k+1[j]): one 64-bit element feeds
                     // the packed fp32x2 pipe (sm_100 FADD2 / FFMA2), two K* entries per instruction
-                    const float2* rec = reinterpret_cast<const float2*>(s.coords[g & 1]) + (khalf * KPT) / 2 * CREC;
+                    const float2* rec = reinterpret_cast<const float2*>(s.coords[g & 1][0]) + (khalf * KPT) / 2 * CREC;
+                    const float2* lrec = reinterpret_cast<const float2*>(s.coords[g & 1][1]) + (khalf * KPT) / 2 * CREC;
 #pragma unroll
                     for (int kk = 0; kk < KPT; kk += 2) {
                         float2 a[CREC];
@@ -497,8 +555,22 @@ __global__ void __launch_bounds__(NTHREADS, 1) observe_tf32_kernel(const Params 
                         }
                         kv[kk] = ex2_approx(-dist.x);
                         kv[kk + 1] = ex2_approx(-dist.y);
+                        if (KIND == 1) {  // + the linear kernel [x_i, 1] diag(c^2) [x_p, 1]^T (gpmdm.py:545-548)
+                            float2 lin = make_float2(c2last, c2last);
+#pragma unroll
+                            for (int q = 0; q < (DL + 1) / 2; q++) {
+                                const float4 r4 = *reinterpret_cast<const float4*>(lrec + (kk / 2) * CREC + 2 * q);
+                                lin = __ffma2_rn(make_float2(r4.x, r4.y), xp[2 * q], lin);
+                                if (2 * q + 1 < DL) lin = __ffma2_rn(make_float2(r4.z, r4.w), xp[2 * q + 1], lin);
+                            }
+                            kv[kk] += lin.x;
+                            kv[kk + 1] += lin.y;
+                        }
                     }
-                    if (gt < CHUNK_FLOATS) s.coords[(g + 1) & 1][gt] = cnext;
+                    if (gt < CHUNK_FLOATS) {
+                        s.coords[(g + 1) & 1][0][gt] = cnext;
+                        if (KIND == 1) s.coords[(g + 1) & 1][1][gt] = lnext;
+                    }
                     named_bar_sync(1, NGEN);  // next chunk's records visible; nobody still reads the buffer written next time
                     wait(&s.a_empty[sa], ((g / AST) & 1) ^ 1);
                     if (F16) {
@@ -550,17 +622,25 @@ __global__ void __launch_bounds__(NTHREADS, 1) observe_tf32_kernel(const Params 
         const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
         uint32_t tcount = 0;
         for (int u = unit0; u < n_units; u += unit_stride) {
-            const long long p = (long long)tile_of(u) * TM + et;
-            const bool valid = p < prm.P;
+            const Unit un = unit(tile_of(u) < n_tiles ? tile_of(u) : n_tiles - 1);
+            long long p;
+            bool valid;
+            if (KIND == 1) {
+                valid = et < un.count;
+                p = prm.perm[un.first + (valid ? et : un.count - 1)];
+            } else {
+                p = (long long)tile_of(u) * TM + et;
+                valid = p < prm.P;
+            }
             float q = 0.f;
             double S = 0.0;
-            for (int ct = 0; ct < nct; ct++, tcount++) {
+            for (int ct = 0; ct < un.nct; ct++, tcount++) {
                 const int acc = F16 ? 0 : (tcount & 1);
                 const uint32_t use = F16 ? tcount : (tcount >> 1);
                 wait(&s.t_full[acc], use & 1);
                 tc_fence_after();
                 const uint32_t taddr = tmem + lane_base + (uint32_t)acc * TN;
-                if (ct < nq) {
+                if (ct < un.nq) {
 #pragma unroll 1
                     for (int cb = 0; cb < TN; cb += 32) {
                         float v[32];
@@ -603,7 +683,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) observe_tf32_kernel(const Params 
                 else mbar_arrive(&s.t_empty[acc]);
             }
             if (valid) {
-                const double v = 1.0 - (double)q;
+                double prior = 1.0;
+                if (KIND == 1) {  // 1 + [x, 1] diag(c^2) [x, 1]^T (gpmdm.py:1092-1101)
+#pragma unroll
+                    for (int j = 0; j < DL; j++) {
+                        const double xj = prm.x[p * DL + j];
+                        prior = fma(prm.lin_c2[j] * xj, xj, prior);
+                    }
+                    prior += prm.lin_c2[DL];
+                }
+                const double v = prior - (double)q;
                 if (prm.status && !(v > 0.0 && v < INFINITY)) atomicAdd(prm.status, 1);
                 if (prm.ll) prm.ll[p] = -0.5 * S / v - (double)prm.dout * log(v) + prm.ll_const;
                 if (prm.v_out) prm.v_out[p] = v;
@@ -700,14 +789,14 @@ static bool use_cluster(long long tiles) {
     return e && e[0] == '1' && tiles >= 4;
 }
 
-template <int DL, int MODE, int CG>
+template <int DL, int MODE, int CG, int KIND = 0>
 static int launch_cg(const Params& prm, int grid, cudaStream_t st) {
     // the opt-in to > 48 KB of dynamic shared memory is per function AND per device
     static bool configured[64] = {};  // per instantiation
     int dev = 0;
     cudaGetDevice(&dev);
     dev = (dev >= 0 && dev < 64) ? dev : 0;
-    auto kern = observe_tf32_kernel<DL, MODE, CG>;
+    auto kern = observe_tf32_kernel<DL, MODE, CG, KIND>;
     if (!configured[dev]) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemT<CG>));
         if (e != cudaSuccess) {
@@ -995,5 +1084,45 @@ extern "C" int gpmdm_pf_observe_f16x2(const gpmdm_gp_model_tf32* m, const double
         case 7: return tf32::launch<7, tf32::MODE_F16X2>(prm, tiles, sms, st);
         case 8: return tf32::launch<8, tf32::MODE_F16X2>(prm, tiles, sms, st);
     }
+    return GPMDM_E_UNSUPPORTED;
+}
+
+extern "C" int gpmdm_pf_dynvar_tc(const gpmdm_tc_block* blocks, int32_t n_blocks, int32_t d, int32_t mode,
+                                  const double* lengthscales, const double* lin_c2, const double* x_prev,
+                                  const int32_t* perm, const int32_t* tiles128, const int32_t* n_tiles128, int64_t P,
+                                  double* v_out, int32_t* tile_counter, void* stream) {
+    GPMDM_REQUIRE(blocks && lengthscales && lin_c2, GPMDM_E_INVALID, "null model field");
+    GPMDM_REQUIRE(n_blocks >= 1 && d >= 1 && d <= GPMDM_MAX_LATENT && (mode == 0 || mode == 1), GPMDM_E_UNSUPPORTED,
+                  "bad sizes n_blocks=%d d=%d mode=%d", n_blocks, d, mode);
+    GPMDM_REQUIRE(P >= 0 && P < (1ll << 31), GPMDM_E_INVALID, "P out of range");
+    if (P == 0) return 0;
+    GPMDM_REQUIRE(x_prev && perm && tiles128 && n_tiles128 && v_out, GPMDM_E_INVALID, "null argument");
+    tf32::Params prm{};
+    prm.dblocks = blocks;
+    prm.d = d;
+    prm.ls = lengthscales;
+    prm.lin_c2 = lin_c2;
+    prm.x = x_prev;
+    prm.P = P;
+    prm.perm = perm;
+    prm.tiles = tiles128;
+    prm.n_tiles_dev = n_tiles128;
+    prm.v_out = v_out;
+    prm.status = tile_counter ? tile_counter + 2 : nullptr;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const long long max_tiles = (P + tf32::TM - 1) / tf32::TM + n_blocks;
+    const int grid = (int)(max_tiles < sms ? max_tiles : sms);
+    cudaStream_t st = (cudaStream_t)stream;
+#define GPMDM_DYN_CASE(DL)                                                                          \
+    case DL:                                                                                        \
+        return mode == 1 ? tf32::launch_cg<DL, tf32::MODE_F16X2, 1, 1>(prm, grid, st)               \
+                         : tf32::launch_cg<DL, tf32::MODE_TF32X3, 1, 1>(prm, grid, st);
+    switch (d) {
+        GPMDM_DYN_CASE(1) GPMDM_DYN_CASE(2) GPMDM_DYN_CASE(3) GPMDM_DYN_CASE(4)
+        GPMDM_DYN_CASE(5) GPMDM_DYN_CASE(6) GPMDM_DYN_CASE(7) GPMDM_DYN_CASE(8)
+    }
+#undef GPMDM_DYN_CASE
     return GPMDM_E_UNSUPPORTED;
 }

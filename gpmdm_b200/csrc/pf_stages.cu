@@ -58,9 +58,37 @@ __global__ void __launch_bounds__(RB) bucket_count_kernel(const int64_t* __restr
     for (int i = threadIdx.x; i < C; i += blockDim.x) counts[(long long)i * nb + blockIdx.x] = sh_cnt[i];
 }
 
+// writes the class-homogeneous tile table {block, first, count, 0} for tiles of `tile_p` particles
+__device__ __forceinline__ void write_tile_table(const int* cls_start, int* tile_start, int C, int tile_p,
+                                                 int32_t* __restrict__ tiles, int32_t* __restrict__ n_tiles) {
+    if (threadIdx.x == 0) {
+        int t = 0;
+        for (int c = 0; c < C; c++) {
+            tile_start[c] = t;
+            t += (cls_start[c + 1] - cls_start[c] + tile_p - 1) / tile_p;
+        }
+        tile_start[C] = t;
+        n_tiles[0] = t;
+    }
+    __syncthreads();
+    for (int c = 0; c < C; c++) {
+        const int nt = tile_start[c + 1] - tile_start[c];
+        const int cnt = cls_start[c + 1] - cls_start[c];
+        for (int t = threadIdx.x; t < nt; t += blockDim.x) {
+            int32_t* d = tiles + 4ll * (tile_start[c] + t);
+            d[0] = c;
+            d[1] = cls_start[c] + t * tile_p;
+            d[2] = min(tile_p, cnt - t * tile_p);
+            d[3] = 0;
+        }
+    }
+    __syncthreads();
+}
+
 __global__ void __launch_bounds__(1024) bucket_scan_kernel(int32_t* __restrict__ counts /*in: counts, out: offsets*/,
                                                            int C, int nb, int32_t* __restrict__ tiles,
-                                                           int32_t* __restrict__ n_tiles) {
+                                                           int32_t* __restrict__ n_tiles, int32_t* __restrict__ tiles2,
+                                                           int32_t* __restrict__ n_tiles2, int tile_p2) {
     // exclusive scan over the class-major [C][nb] array, 1024 entries per pass: shuffle scan inside each warp, the 32
     // warp totals scanned by warp 0, running carry across passes
     __shared__ int wtot[32];
@@ -101,28 +129,10 @@ __global__ void __launch_bounds__(1024) bucket_scan_kernel(int32_t* __restrict__
         if (threadIdx.x == 1023) carry = excl + v;
         __syncthreads();
     }
-    if (threadIdx.x == 0) {
-        cls_start[C] = carry;
-        int t = 0;
-        for (int c = 0; c < C; c++) {
-            tile_start[c] = t;
-            t += (cls_start[c + 1] - cls_start[c] + GPMDM_TILE_P - 1) / GPMDM_TILE_P;
-        }
-        tile_start[C] = t;
-        n_tiles[0] = t;
-    }
+    if (threadIdx.x == 0) cls_start[C] = carry;
     __syncthreads();
-    for (int c = 0; c < C; c++) {
-        const int nt = tile_start[c + 1] - tile_start[c];
-        const int cnt = cls_start[c + 1] - cls_start[c];
-        for (int t = threadIdx.x; t < nt; t += blockDim.x) {
-            int32_t* d = tiles + 4ll * (tile_start[c] + t);
-            d[0] = c;
-            d[1] = cls_start[c] + t * GPMDM_TILE_P;
-            d[2] = min(GPMDM_TILE_P, cnt - t * GPMDM_TILE_P);
-            d[3] = 0;
-        }
-    }
+    write_tile_table(cls_start, tile_start, C, GPMDM_TILE_P, tiles, n_tiles);
+    if (tiles2) write_tile_table(cls_start, tile_start, C, tile_p2, tiles2, n_tiles2);  // e.g. 128 for the tcgen05 kernels
 }
 
 __global__ void __launch_bounds__(RB) bucket_scatter_kernel(const int64_t* __restrict__ cls, long long P, int C,
@@ -367,18 +377,25 @@ extern "C" int gpmdm_pf_transition_f64(const int64_t* c_prev, const double* T, c
     return check_launch("transition_kernel");
 }
 
-extern "C" int gpmdm_pf_bucket_by_class(const int64_t* classes, int64_t P, int32_t C, int32_t* perm, int32_t* tiles,
-                                        int32_t* n_tiles, void* workspace, void* stream) {
+extern "C" int gpmdm_pf_bucket_by_class2(const int64_t* classes, int64_t P, int32_t C, int32_t* perm, int32_t* tiles,
+                                         int32_t* n_tiles, int32_t* tiles128, int32_t* n_tiles128, void* workspace,
+                                         void* stream) {
     GPMDM_REQUIRE(P > 0 && P < (1ll << 31) && C >= 1 && C <= 1024, GPMDM_E_INVALID, "bad sizes P=%lld C=%d",
                   (long long)P, C);
     GPMDM_REQUIRE(classes && perm && tiles && n_tiles && workspace, GPMDM_E_INVALID, "null argument");
+    GPMDM_REQUIRE((tiles128 == nullptr) == (n_tiles128 == nullptr), GPMDM_E_INVALID, "tiles128 and n_tiles128 go together");
     cudaStream_t st = (cudaStream_t)stream;
     const int nb = nblocks(P, RB * BSUB);
     int32_t* counts = reinterpret_cast<int32_t*>(static_cast<char*>(workspace) + 256);
     bucket_count_kernel<<<nb, RB, C * sizeof(int), st>>>(classes, P, C, nb, counts);
-    bucket_scan_kernel<<<1, 1024, 2 * (C + 1) * sizeof(int), st>>>(counts, C, nb, tiles, n_tiles);
+    bucket_scan_kernel<<<1, 1024, 2 * (C + 1) * sizeof(int), st>>>(counts, C, nb, tiles, n_tiles, tiles128, n_tiles128, 128);
     bucket_scatter_kernel<<<nb, RB, 33 * C * sizeof(int), st>>>(classes, P, C, nb, counts, perm);
     return check_launch("bucket_by_class");
+}
+
+extern "C" int gpmdm_pf_bucket_by_class(const int64_t* classes, int64_t P, int32_t C, int32_t* perm, int32_t* tiles,
+                                        int32_t* n_tiles, void* workspace, void* stream) {
+    return gpmdm_pf_bucket_by_class2(classes, P, C, perm, tiles, n_tiles, nullptr, nullptr, workspace, stream);
 }
 
 extern "C" int gpmdm_pf_normalize_f64(const double* ll, int64_t P, double* lw, double* w, double* stats_out,

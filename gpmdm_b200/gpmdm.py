@@ -811,6 +811,39 @@ class GPMDM(torch.nn.Module):
                            ll_const_terms=(2.0 * torch.sum(self._d("y_log_lambdas"))).item())
         return cache[kind]
 
+    @torch.no_grad()
+    def packed_model_tc_dyn(self, kind="tf32"):
+        """Operands of the tensor-core dynamics-variance kernel (include/gpmdm_b200.h: gpmdm_tc_block), one block per
+        class: the whitening factor W_c = L_c^-1 of the class block K_c + 1e-6 I (gpmdm.py:1301-1303) as tensor-core tiles,
+        and the training records (RBF coordinates pre-scaled by sqrt(log2 e) / l, linear-kernel terms c_k^2 x_ik)."""
+        cache = self.__dict__.setdefault("_packed_tc_dyn", {})
+        if kind in cache and cache[kind]["version"] == self._factors_version:
+            return cache[kind]
+        key = "wtiles" if kind == "tf32" else "wtiles_f16"
+        offs = self.class_pair_offsets()
+        ls = torch.exp(self._d("x_log_lengthscales")).contiguous()
+        c2 = (torch.exp(self._d("x_log_lin_coeff")) ** 2).contiguous()
+        d = self.d
+
+        def pairs(M, n_pad):  # [n, d] fp64 -> [n_pad / 2, 8, 2] fp32: rows interleaved in pairs per coordinate
+            out = torch.zeros(n_pad, 8, dtype=torch.float32, device=self.device)
+            out[:M.shape[0], :d] = M.to(torch.float32)
+            return out.view(n_pad // 2, 2, 8).transpose(1, 2).contiguous()
+
+        rows, keep = [], [ls, c2]
+        for c in range(self.n_classes):
+            blk = self._dyn_blks[c]
+            Xc = self._Xin[offs[c]:offs[c + 1]]
+            if blk.get(key) is None:  # not part of the precompute: factor the class block (again) for its W tiles only
+                blk[key] = self._factor_block(lambda: self._dyn_kernel_matrix(c), self._Xout[offs[c]:offs[c + 1]].contiguous(),
+                                              (kind,))[key]
+            coords, lin = pairs(Xc / ls * 1.2011224087864498, blk["n_pad"]), pairs(Xc * c2[:d], blk["n_pad"])
+            keep += [coords, lin, blk[key]]
+            rows.append([coords.data_ptr(), lin.data_ptr(), blk[key].data_ptr(), blk["n"], blk["n_pad"]])
+        table = torch.tensor(rows, dtype=torch.int64, device=self.device)
+        cache[kind] = dict(version=self._factors_version, table=table, keep=keep, ls=ls, c2=c2, mode=0 if kind == "tf32" else 1)
+        return cache[kind]
+
     LOWLAT_MAX_TILES = 110  # below this many 64-particle tiles (of 148 SMs) the column tiles are split over CTAs
 
     def _use_lowlat(self, P, low_latency):
@@ -896,7 +929,12 @@ class GPMDM(torch.nn.Module):
         return (mu + torch.tensor(self.meanY, dtype=F64, device=self.device)).to(self.dtype), var.to(self.dtype)
 
     @torch.no_grad()
-    def map_x_dynamics_for_class(self, Xstar, class_index: int, flg_noise=False, low_latency=None, kstar_cache=None):
+    def map_x_dynamics_for_class(self, Xstar, class_index: int, flg_noise=False, low_latency=None, kstar_cache=None,
+                                 precision="fp64"):
+        """gpmdm.py:1032-1068.  `precision` "tf32" / "f16x2": the variance prior - |W_c k*|^2 on the tensor cores
+        (gpmdm_pf_dynvar_tc), the mean in fp64 on the alpha tiles only -- what GPMDM_PF(precision=...) runs per step."""
+        if precision not in ("fp64", "tf32", "f16x2"):
+            raise ValueError(f"unknown precision {precision!r}")
         lib = _cabi.lib()
         pk = self.packed_models()
         if pk["dyn"] is None:
@@ -913,7 +951,22 @@ class GPMDM(torch.nn.Module):
         tiles = torch.stack([torch.full_like(t, class_index), t * TILE_P, torch.clamp(P - t * TILE_P, max=TILE_P),
                              torch.zeros_like(t)], 1).contiguous()
         n_tiles = torch.tensor([nt], dtype=torch.int32, device=self.device)
-        if self._use_lowlat(P, low_latency):
+        if precision != "fp64":
+            tc = self.packed_model_tc_dyn(precision)
+            nt2 = (P + 127) // 128
+            t2 = torch.arange(nt2, dtype=torch.int32, device=self.device)
+            tiles2 = torch.stack([torch.full_like(t2, class_index), t2 * 128, torch.clamp(P - t2 * 128, max=128),
+                                  torch.zeros_like(t2)], 1).contiguous()
+            n_tiles2 = torch.tensor([nt2], dtype=torch.int32, device=self.device)
+            v = torch.empty(P, dtype=F64, device=self.device)
+            check(lib.gpmdm_pf_dynvar_tc(ptr(tc["table"]), self.n_classes, self.d, tc["mode"], ptr(tc["ls"]), ptr(tc["c2"]),
+                                         ptr(Xs), ptr(perm), ptr(tiles2), ptr(n_tiles2), P, ptr(v),
+                                         ptr(self._scratch_counter()), stream()), "gpmdm_pf_dynvar_tc")
+            check(lib.gpmdm_pf_propagate_meanonly_f64(ctypes.byref(pk["dyn"]), ptr(Xs), ptr(perm), ptr(tiles), ptr(n_tiles),
+                                                      P, None, ptr(v), None, ptr(mean), ptr(var),
+                                                      ptr(self._scratch_counter()), stream()),
+                  "gpmdm_pf_propagate_meanonly_f64")
+        elif self._use_lowlat(P, low_latency):
             ws = self._lowlat_workspace(P, pk["dyn_max_n_pad"], self.d)
             check(lib.gpmdm_pf_propagate_lowlat_f64(ctypes.byref(pk["dyn"]), ptr(Xs), ptr(perm), ptr(tiles), ptr(n_tiles),
                                                     P, None, None, ptr(mean), ptr(var), pk["dyn_max_n_pad"], 0,

@@ -106,6 +106,7 @@ class GPMDM_PF:
 
         self._packed = gpmdm.packed_models(self._tri, with_obs_L=(precision == "fp64"))
         self._packed_tf32 = gpmdm.packed_model_tf32(precision) if precision != "fp64" else None
+        self._tc_dyn = None  # tensor-core variants in fused mode: the dynamics variance runs on tcgen05 as well
         c32 = float(0.5 * self._gpmdm.D * _LOG_2PI)  # fp32 product, as gpmdm_pf.py:191
         self._ll_const = self._packed["ll_const_terms"] - c32
         # the mode is chosen from the TOTAL particle count: the two decompositions sum over k in different orders, so a
@@ -118,6 +119,8 @@ class GPMDM_PF:
         self._kstar_cache_dyn = (self._kstar_cache and self._packed["dyn_max_n_pad"] >= 4 * _cabi.TILE_N
                                  and self._packed["dyn_max_n_pad"] <= self._packed["obs_n_pad"])
         self._native_step = bool(native_step) and precision == "fp64"
+        if precision != "fp64" and not self._lowlat:
+            self._tc_dyn = gpmdm.packed_model_tc_dyn(precision)
         # small-cloud step: draws+transition+bucketing and normalise+cdf+resample+summaries as two single-CTA kernels
         self._small = (self._native_step and self._lowlat and self._world == 1
                        and self._num_particles <= int(self._lib.gpmdm_pf_small_max_particles()))
@@ -138,6 +141,9 @@ class GPMDM_PF:
         self._E, self._eps, self._u = e(Pl, C), e(Pl, d), e(P)
         self._stats = e(2)
         self._v_buf = e(Pl)
+        if self._tc_dyn is not None:  # 128-particle class-homogeneous tiles + the dynamics variances
+            self._tiles128, self._n_tiles128 = e(Pl // 128 + C + 1, 4, dt=torch.int32), e(1, dt=torch.int32)
+            self._v_dyn = e(Pl)
         self._summary = e(C + d + 1)
         self._summary_step = -1
         if self._small:
@@ -306,23 +312,38 @@ class GPMDM_PF:
         # -- class transition, bucketing, dynamics draw, observation likelihood (local particles)
         check(lib.gpmdm_pf_transition_f64(ptr(c_prev), ptr(self._markov_switching_model), ptr(E), Pl, C, ptr(c_new_l), st),
               "gpmdm_pf_transition_f64")
-        check(lib.gpmdm_pf_bucket_by_class(ptr(c_new_l), Pl, C, ptr(self._perm), ptr(self._tiles), ptr(self._n_tiles),
-                                           ptr(self._ws), st), "gpmdm_pf_bucket_by_class")
-        if self._lowlat:
-            check(lib.gpmdm_pf_propagate_lowlat_f64(ctypes.byref(self._packed["dyn"]), ptr(x_prev), ptr(self._perm),
-                                                    ptr(self._tiles), ptr(self._n_tiles), Pl, ptr(eps), ptr(x_new_l), None,
-                                                    None, self._packed["dyn_max_n_pad"], self._seg_dyn, ptr(self._counter),
-                                                    ptr(self._ws_lowlat), st), "gpmdm_pf_propagate_lowlat_f64")
-        elif self._kstar_cache_dyn:
-            check(lib.gpmdm_pf_propagate_cached_f64(ctypes.byref(self._packed["dyn"]), ptr(x_prev), ptr(self._perm),
-                                                    ptr(self._tiles), ptr(self._n_tiles), Pl, ptr(eps), ptr(x_new_l), None,
-                                                    None, self._packed["dyn_max_n_pad"], ptr(self._counter),
-                                                    ptr(self._ws_kstar), self._ws_kstar.numel() * 8, st),
-                  "gpmdm_pf_propagate_cached_f64")
+        if self._tc_dyn is not None:
+            # tensor-core variants: variances prior - |W_c k|^2 on tcgen05 per class block, then means + draw in fp64 on the
+            # alpha tiles only
+            tc = self._tc_dyn
+            check(lib.gpmdm_pf_bucket_by_class2(ptr(c_new_l), Pl, C, ptr(self._perm), ptr(self._tiles), ptr(self._n_tiles),
+                                                ptr(self._tiles128), ptr(self._n_tiles128), ptr(self._ws), st),
+                  "gpmdm_pf_bucket_by_class2")
+            check(lib.gpmdm_pf_dynvar_tc(ptr(tc["table"]), C, d, tc["mode"], ptr(tc["ls"]), ptr(tc["c2"]), ptr(x_prev),
+                                         ptr(self._perm), ptr(self._tiles128), ptr(self._n_tiles128), Pl, ptr(self._v_dyn),
+                                         ptr(self._counter), st), "gpmdm_pf_dynvar_tc")
+            check(lib.gpmdm_pf_propagate_meanonly_f64(ctypes.byref(self._packed["dyn"]), ptr(x_prev), ptr(self._perm),
+                                                      ptr(self._tiles), ptr(self._n_tiles), Pl, ptr(eps), ptr(self._v_dyn),
+                                                      ptr(x_new_l), None, None, ptr(self._counter), st),
+                  "gpmdm_pf_propagate_meanonly_f64")
         else:
-            check(lib.gpmdm_pf_propagate_f64(ctypes.byref(self._packed["dyn"]), ptr(x_prev), ptr(self._perm),
-                                             ptr(self._tiles), ptr(self._n_tiles), Pl, ptr(eps), ptr(x_new_l), None, None,
-                                             ptr(self._counter), st), "gpmdm_pf_propagate_f64")
+            check(lib.gpmdm_pf_bucket_by_class(ptr(c_new_l), Pl, C, ptr(self._perm), ptr(self._tiles), ptr(self._n_tiles),
+                                               ptr(self._ws), st), "gpmdm_pf_bucket_by_class")
+            if self._lowlat:
+                check(lib.gpmdm_pf_propagate_lowlat_f64(ctypes.byref(self._packed["dyn"]), ptr(x_prev), ptr(self._perm),
+                                                        ptr(self._tiles), ptr(self._n_tiles), Pl, ptr(eps), ptr(x_new_l), None,
+                                                        None, self._packed["dyn_max_n_pad"], self._seg_dyn, ptr(self._counter),
+                                                        ptr(self._ws_lowlat), st), "gpmdm_pf_propagate_lowlat_f64")
+            elif self._kstar_cache_dyn:
+                check(lib.gpmdm_pf_propagate_cached_f64(ctypes.byref(self._packed["dyn"]), ptr(x_prev), ptr(self._perm),
+                                                        ptr(self._tiles), ptr(self._n_tiles), Pl, ptr(eps), ptr(x_new_l), None,
+                                                        None, self._packed["dyn_max_n_pad"], ptr(self._counter),
+                                                        ptr(self._ws_kstar), self._ws_kstar.numel() * 8, st),
+                      "gpmdm_pf_propagate_cached_f64")
+            else:
+                check(lib.gpmdm_pf_propagate_f64(ctypes.byref(self._packed["dyn"]), ptr(x_prev), ptr(self._perm),
+                                                 ptr(self._tiles), ptr(self._n_tiles), Pl, ptr(eps), ptr(x_new_l), None, None,
+                                                 ptr(self._counter), st), "gpmdm_pf_propagate_f64")
         prof = getattr(self, "_profile_events", None)
         if prof is not None:  # bench.py: CUDA events around the dominant kernel, on the launching stream
             ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))

@@ -272,6 +272,37 @@ int gpmdm_pack_whitened_f16x2(const double* W, int64_t n, int64_t n_pad, void* w
 int gpmdm_pf_observe_f16x2(const gpmdm_gp_model_tf32* obs, const double* x, int64_t P, double* v_out,
                            int32_t* tile_counter, void* stream);
 
+/* ---- dynamics GP variance on the tensor cores (precision "tf32" / "f16x2"; gpmdm.py:1032-1068) ----------------------
+ * The same tcgen05 kernel run per class block: var_p = prior_p - |W_c k|^2 with W_c = L_c^-1 (K_c = L_c L_c^T the class
+ * block incl. the 1e-6 jitter, gpmdm.py:1301-1303), k = RBF + linear cross-kernel generated on the fly, prior_p =
+ * 1 + [x,1] diag(c^2) [x,1]^T.  Particles are reached through gpmdm_pf_bucket_by_class2's permutation in class-homogeneous
+ * tiles of 128.  The means (and the draw) follow in fp64 on the alpha tile only: gpmdm_pf_propagate_meanonly_f64.
+ *   coords / lin [n_pad/2, 8, 2] fp32: sqrt(log2 e) x_i / lengthscale and c_k^2 x_i[k], rows interleaved in pairs as for
+ *   gpmdm_gp_model_tf32; wtiles from gpmdm_pack_whitened_tf32 (mode 0) / gpmdm_pack_whitened_f16x2 (mode 1). */
+typedef struct gpmdm_tc_block {
+    const float* coords;
+    const float* lin;
+    const void* wtiles;
+    int64_t n;
+    int64_t n_pad;
+} gpmdm_tc_block;
+
+/* gpmdm_pf_bucket_by_class plus a second tile table with 128-particle tiles (tiles128 [P/128 + C, 4], n_tiles128 [1]). */
+int gpmdm_pf_bucket_by_class2(const int64_t* classes, int64_t P, int32_t C, int32_t* perm, int32_t* tiles,
+                              int32_t* n_tiles, int32_t* tiles128, int32_t* n_tiles128, void* workspace, void* stream);
+/* v_out [P] (indexed by particle) = prior - |W_c k|^2, i.e. the dynamics variance before the lambda^-2 scaling.
+ * blocks: DEVICE array of n_blocks structs; mode 0 = tf32 x 3, 1 = fp16 split; tile_counter as for the predict calls
+ * (word [2] counts non-positive variances). */
+int gpmdm_pf_dynvar_tc(const gpmdm_tc_block* blocks, int32_t n_blocks, int32_t d, int32_t mode, const double* lengthscales,
+                       const double* lin_c2, const double* x_prev, const int32_t* perm, const int32_t* tiles128,
+                       const int32_t* n_tiles128, int64_t P, double* v_out, int32_t* tile_counter, void* stream);
+/* gpmdm_pf_propagate_f64 with the variances supplied (v_in [P], before the lambda^-2 scaling): only the alpha tile of each
+ * class block is contracted (2 N_c d of the 2 N_c^2 + 2 N_c d flops), then x_new = eps * sqrt(v lambda^-2) + mean. */
+int gpmdm_pf_propagate_meanonly_f64(const gpmdm_gp_model* dyn, const double* x_prev, const int32_t* perm,
+                                    const int32_t* tiles, const int32_t* n_tiles, int64_t P, const double* eps,
+                                    const double* v_in, double* x_new, double* mean_out, double* var_out,
+                                    int32_t* tile_counter, void* stream);
+
 /* ---- one filter step as two calls (GPMDM_PF._update, gpmdm_pf.py:126-135) ----------------------------------
  * The host-side sequence of the stage entry points above, issued from native code so that a step costs two FFI calls
  * instead of ~twelve (with 100 particles the step is launch-latency bound).  `local` = draws, transition, bucketing,
