@@ -57,9 +57,9 @@ _SIGNATURES = {
     "gpmdm_pf_transition_f64": (ctypes.c_int, [_ptr, _ptr, _ptr, _i64, _i32, _ptr, _ptr]),
     "gpmdm_pf_bucket_by_class": (ctypes.c_int, [_ptr, _i64, _i32, _ptr, _ptr, _ptr, _ptr, _ptr]),
     "gpmdm_pf_bucket_by_class2": (ctypes.c_int, [_ptr, _i64, _i32, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr]),
-    "gpmdm_pf_dynvar_tc": (ctypes.c_int, [_ptr, _i32, _i32, _i32, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _i64, _ptr, _ptr, _ptr]),
-    "gpmdm_pf_propagate_meanonly_f64": (ctypes.c_int, [ctypes.POINTER(GpModel), _ptr, _ptr, _ptr, _ptr, _i64, _ptr, _ptr,
-                                                       _ptr, _ptr, _ptr, _ptr, _ptr]),
+    "gpmdm_pf_dynvar_tc": (ctypes.c_int, [_ptr, _i32, _i32, _i32, _ptr, _ptr, _ptr, _ptr, _ptr, _i64, _ptr, _ptr]),
+    "gpmdm_pf_propagate_meanonly_f64": (ctypes.c_int, [ctypes.POINTER(GpModel), _ptr, _ptr, _ptr, _ptr, _ptr, _i64, _ptr,
+                                                       _ptr, _ptr, _ptr, _ptr, _ptr, _ptr]),
     "gpmdm_pf_propagate_f64": (ctypes.c_int, [ctypes.POINTER(GpModel), _ptr, _ptr, _ptr, _ptr, _i64, _ptr, _ptr,
                                               _ptr, _ptr, _ptr, _ptr]),
     "gpmdm_pf_observe_f64": (ctypes.c_int, [ctypes.POINTER(GpModel), _ptr, _i64, _ptr, _f64, _ptr, _ptr, _ptr,

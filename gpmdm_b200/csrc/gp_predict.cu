@@ -89,6 +89,9 @@ struct PredictParams {
     double* var_out;
     // observation epilogue
     const double* v_in;  // mean-only mode: variances supplied (tensor-core variants), skip the quadratic form
+    // dynamics GP in mean-only mode: v_in holds 1 - |W_c k_rbf|^2 only; the low-rank (linear kernel) part of the variance
+    // is finished here from the d + 1 extra alpha columns G_c = K_c^-1 [X,1] diag(c^2) and H_c = diag(c^2) [X,1]^T G_c
+    const double* lr_h;  // [n_blocks][d + 1][d + 1]
     const double* z;
     double ll_const;  // 2 sum_j log lambda_j - c32
     double* ll;
@@ -486,7 +489,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) gp_predict_kernel(const PredictPa
     }
 #define GPMDM_ALL_GROUPS(jg) true
 #define GPMDM_SOME_GROUPS(jg) ((jg) < jlim)
-            const int jlim = ct < nq ? NJ : (min(TN, prm.dout - (ct - nq) * TN) + 7) / 8;  // 8-column blocks in use
+            // 8-column blocks in use (mean-only dynamics: + the d + 1 columns of G_c)
+            const int dcols = (KIND == 1 && prm.lr_h) ? 2 * DL + 1 : prm.dout;
+            const int jlim = ct < nq ? NJ : (min(TN, dcols - (ct - nq) * TN) + 7) / 8;
             if (jlim > NJ - 8) {
                 constexpr int jlim8 = NJ;
                 GPMDM_K_LOOP(GPMDM_ALL_GROUPS)
@@ -530,6 +535,26 @@ __global__ void __launch_bounds__(NTHREADS, 1) gp_predict_kernel(const PredictPa
                 }
             } else {
                 const int cbase = (ct - nq) * TN;
+                if (KIND == 1 && prm.lr_h && ct == nq) {
+                    // var = u + x~^T S x~ - 2 t x~ + x~^T H_c x~,  t = k^T G_c = accumulator columns d .. 2d of this row
+                    // (include/gpmdm_b200.h, "dynamics GP variance on the tensor cores"); a row's columns live in its quad
+                    double corr = 0.0, xhx = 0.0;
+                    const double* H = prm.lr_h + (long long)blk * (DL + 1) * (DL + 1);
+#pragma unroll
+                    for (int i = 0; i <= DL; i++) {
+                        const int col = DL + i;  // compile-time after unrolling
+                        const double xi = i < DL ? pr.x[(KIND == 1 && i < DL) ? i : 0] : 1.0;
+                        if (c == ((col & 7) >> 1)) corr = fma(acc[col >> 3][col & 1], xi, corr);
+                        double hrow = __ldg(H + i * (DL + 1) + DL);
+#pragma unroll
+                        for (int j = 0; j < DL; j++) hrow = fma(__ldg(H + i * (DL + 1) + j), pr.x[KIND == 1 ? j : 0], hrow);
+                        xhx = fma(hrow, xi, xhx);
+                    }
+                    corr += __shfl_xor_sync(0xffffffffu, corr, 1);
+                    corr += __shfl_xor_sync(0xffffffffu, corr, 2);
+                    vrow = vrow + (prior - 1.0) - 2.0 * corr + xhx;
+                    if (c == 0 && pidx >= 0 && !(vrow > 0.0 && vrow < INFINITY)) atomicAdd(prm.status, 1);
+                }
 #pragma unroll
                 for (int j = 0; j < NJ; j++) {
 #pragma unroll
@@ -734,7 +759,7 @@ using namespace gpmdm;
 static int propagate_impl(const gpmdm_gp_model* dyn, const double* x_prev, const int32_t* perm, const int32_t* tiles,
                           const int32_t* n_tiles, int64_t P, const double* eps, double* x_new, double* mean_out,
                           double* var_out, int32_t* tile_counter, void* stream, void* kstar_ws, int64_t kstar_ws_bytes,
-                          int64_t max_n_pad, const double* v_in = nullptr) {
+                          int64_t max_n_pad, const double* v_in = nullptr, const double* lr_h = nullptr) {
     if (int rc = validate_model(dyn, 1)) return rc;
     GPMDM_REQUIRE(P >= 0 && P < (1ll << 31), GPMDM_E_INVALID, "P = %lld out of range", (long long)P);
     if (P == 0) return 0;
@@ -756,6 +781,7 @@ static int propagate_impl(const gpmdm_gp_model* dyn, const double* x_prev, const
     prm.mean_out = mean_out;
     prm.var_out = var_out;
     prm.v_in = v_in;
+    prm.lr_h = lr_h;
     cudaError_t e = cudaMemsetAsync(tile_counter, 0, 2 * sizeof(int32_t), st);
     GPMDM_REQUIRE(e == cudaSuccess, (int)e, "cudaMemsetAsync: %s", cudaGetErrorString(e));
     const long long max_tiles = (P + TM - 1) / TM + dyn->n_blocks;
@@ -818,13 +844,14 @@ extern "C" int gpmdm_pf_observe_cached_f64(const gpmdm_gp_model* obs, const doub
                         kstar_ws_bytes, n_pad);
 }
 
-extern "C" int gpmdm_pf_propagate_meanonly_f64(const gpmdm_gp_model* dyn, const double* x_prev, const int32_t* perm,
-                                               const int32_t* tiles, const int32_t* n_tiles, int64_t P, const double* eps,
-                                               const double* v_in, double* x_new, double* mean_out, double* var_out,
-                                               int32_t* tile_counter, void* stream) {
-    GPMDM_REQUIRE(v_in != nullptr, GPMDM_E_INVALID, "v_in is required");
+extern "C" int gpmdm_pf_propagate_meanonly_f64(const gpmdm_gp_model* dyn, const double* lowrank_h, const double* x_prev,
+                                               const int32_t* perm, const int32_t* tiles, const int32_t* n_tiles,
+                                               int64_t P, const double* eps, const double* u_in, double* x_new,
+                                               double* mean_out, double* var_out, int32_t* tile_counter, void* stream) {
+    GPMDM_REQUIRE(u_in != nullptr && lowrank_h != nullptr, GPMDM_E_INVALID, "u_in and lowrank_h are required");
+    GPMDM_REQUIRE(dyn && 2 * dyn->d + 1 <= dyn->alpha_ld, GPMDM_E_INVALID, "alpha tile too narrow for [alpha | G]");
     return propagate_impl(dyn, x_prev, perm, tiles, n_tiles, P, eps, x_new, mean_out, var_out, tile_counter, stream, nullptr,
-                          0, 0, v_in);
+                          0, 0, u_in, lowrank_h);
 }
 
 extern "C" int gpmdm_pf_loglik_f64(const gpmdm_gp_model* obs, const double* x, int64_t P, const double* z,

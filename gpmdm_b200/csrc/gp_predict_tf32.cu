@@ -85,8 +85,7 @@ template <int CG>
 struct __align__(1024) SmemT {
     unsigned char A[Ring<CG>::A][2][A_HALF_BYTES];        // [stage][hi|lo]
     unsigned char B[Ring<CG>::B][2][B_HALF_BYTES / CG];   // [stage][hi|lo], this CTA's share of the 256 rows
-    float coords[2][2][32 * CREC];                        // the generators' double buffer: one chunk of training records
-                                                          // ([1]: the linear-kernel records of the dynamics GP)
+    float coords[2][32 * CREC];                           // the generators' double buffer: one chunk of training records
     uint64_t a_full[Ring<CG>::A], a_empty[Ring<CG>::A], b_full[Ring<CG>::B], b_empty[Ring<CG>::B], t_full[2], t_empty[2];
     uint32_t tmem_base;
 };
@@ -113,7 +112,6 @@ struct Params {
     const int32_t* perm;            // particles ordered by (class, index)
     const int32_t* tiles;           // {block, first position in perm, count, 0} per tile
     const int32_t* n_tiles_dev;     // device int
-    const double* lin_c2;           // [d + 1]
 };
 
 // element (row, k) of a [rows x KC] operand tile in the canonical no-swizzle K-major layout, in elements
@@ -270,7 +268,6 @@ __device__ __forceinline__ void mbar_wait_b(uint64_t* bar, uint32_t parity) {
 // (gpmdm.py:1032-1068) -- the block of the tile's class, with the particles reached through the class-sorted permutation.
 struct Unit {
     const float* coords;
-    const float* lin;
     const unsigned char* wt;
     int nq, nkc, nct, first, count;
 };
@@ -293,11 +290,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) observe_tf32_kernel(const Params 
         Unit un;
         if (KIND == 1) {
             const gpmdm_tc_block b = prm.dblocks[prm.tiles[4 * t]];
-            un.coords = b.coords, un.lin = b.lin, un.wt = reinterpret_cast<const unsigned char*>(b.wtiles);
+            un.coords = b.coords, un.wt = reinterpret_cast<const unsigned char*>(b.wtiles);
             un.nq = (int)(b.n_pad / TN), un.nkc = (int)(b.n_pad / KCm), un.nct = un.nq;
             un.first = prm.tiles[4 * t + 1], un.count = prm.tiles[4 * t + 2];
         } else {
-            un.coords = prm.coords, un.lin = nullptr, un.wt = reinterpret_cast<const unsigned char*>(prm.wtiles);
+            un.coords = prm.coords, un.wt = reinterpret_cast<const unsigned char*>(prm.wtiles);
             un.nq = prm.n_pad / TN, un.nkc = prm.n_pad / KCm;
             un.nct = un.nq + ((!F16 && (prm.ll || prm.mu_out)) ? 1 : 0);
             un.first = t * TM, un.count = TM;
@@ -492,17 +489,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) observe_tf32_kernel(const Params 
         uint32_t g = 0;
         if (unit0 < n_units && gt < CHUNK_FLOATS) {  // chunk 0 of the first unit
             const Unit un0 = unit(tile_of(unit0) < n_tiles ? tile_of(unit0) : n_tiles - 1);
-            s.coords[0][0][gt] = __ldg(un0.coords + gt);
-            if (KIND == 1) s.coords[0][1][gt] = __ldg(un0.lin + gt);
+            s.coords[0][gt] = __ldg(un0.coords + gt);
         }
         named_bar_sync(1, NGEN);
         for (int u = unit0; u < n_units; u += unit_stride) {
             const Unit un = unit(tile_of(u) < n_tiles ? tile_of(u) : n_tiles - 1);
             // the records that follow this unit's last chunk: chunk 0 of the next unit's block
-            const float *nxt_c = un.coords, *nxt_l = un.lin;
+            const float* nxt_c = un.coords;
             if (KIND == 1 && u + unit_stride < n_units) {
                 const Unit nu = unit(tile_of(u + unit_stride) < n_tiles ? tile_of(u + unit_stride) : n_tiles - 1);
-                nxt_c = nu.coords, nxt_l = nu.lin;
+                nxt_c = nu.coords;
             }
             long long p;
             if (KIND == 1) p = prm.perm[un.first + (row < un.count ? row : un.count - 1)];
@@ -511,16 +507,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) observe_tf32_kernel(const Params 
                 if (p >= prm.P) p = prm.P - 1;
             }
             // particle coordinates, negated and duplicated into both halves of a packed f32x2 register
-            float2 nb[DL], xp[KIND == 1 ? DL : 1];
-            float c2last = 0.f;
+            float2 nb[DL];
 #pragma unroll
             for (int j = 0; j < DL; j++) {
                 const double xj = prm.x[p * DL + j];
                 const float bj = (float)(xj / prm.ls[j] * SQRT_LOG2E);
                 nb[j] = make_float2(-bj, -bj);
-                if (KIND == 1) xp[j] = make_float2((float)xj, (float)xj);
             }
-            if (KIND == 1) c2last = (float)prm.lin_c2[DL];
             for (int ct = 0; ct < un.nct; ct++) {
                 const int nch = chunks_of(un, ct);
                 for (int kc = 0; kc < nch; kc++, g++) {
@@ -528,16 +521,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) observe_tf32_kernel(const Params 
                     // the next chunk of this thread's walk (every column tile starts again at k = 0)
                     const bool last = kc + 1 == nch && ct + 1 == un.nct;
                     const long long noff = (long long)(kc + 1 < nch ? kc + 1 : 0) * CHUNK_FLOATS + gt;
-                    float cnext = 0.f, lnext = 0.f;
-                    if (gt < CHUNK_FLOATS) {
-                        cnext = __ldg((last ? nxt_c : un.coords) + noff);
-                        if (KIND == 1) lnext = __ldg((last ? nxt_l : un.lin) + noff);
-                    }
+                    float cnext = 0.f;
+                    if (gt < CHUNK_FLOATS) cnext = __ldg((last ? nxt_c : un.coords) + noff);
                     float kv[KPT];
                     // records are stored per PAIR of training rows as [j][2] (a_k[j], a_k+1[j]): one 64-bit element feeds
                     // the packed fp32x2 pipe (sm_100 FADD2 / FFMA2), two K* entries per instruction
-                    const float2* rec = reinterpret_cast<const float2*>(s.coords[g & 1][0]) + (khalf * KPT) / 2 * CREC;
-                    const float2* lrec = reinterpret_cast<const float2*>(s.coords[g & 1][1]) + (khalf * KPT) / 2 * CREC;
+                    const float2* rec = reinterpret_cast<const float2*>(s.coords[g & 1]) + (khalf * KPT) / 2 * CREC;
 #pragma unroll
                     for (int kk = 0; kk < KPT; kk += 2) {
                         float2 a[CREC];
@@ -555,22 +544,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) observe_tf32_kernel(const Params 
                         }
                         kv[kk] = ex2_approx(-dist.x);
                         kv[kk + 1] = ex2_approx(-dist.y);
-                        if (KIND == 1) {  // + the linear kernel [x_i, 1] diag(c^2) [x_p, 1]^T (gpmdm.py:545-548)
-                            float2 lin = make_float2(c2last, c2last);
-#pragma unroll
-                            for (int q = 0; q < (DL + 1) / 2; q++) {
-                                const float4 r4 = *reinterpret_cast<const float4*>(lrec + (kk / 2) * CREC + 2 * q);
-                                lin = __ffma2_rn(make_float2(r4.x, r4.y), xp[2 * q], lin);
-                                if (2 * q + 1 < DL) lin = __ffma2_rn(make_float2(r4.z, r4.w), xp[2 * q + 1], lin);
-                            }
-                            kv[kk] += lin.x;
-                            kv[kk + 1] += lin.y;
-                        }
                     }
-                    if (gt < CHUNK_FLOATS) {
-                        s.coords[(g + 1) & 1][0][gt] = cnext;
-                        if (KIND == 1) s.coords[(g + 1) & 1][1][gt] = lnext;
-                    }
+                    if (gt < CHUNK_FLOATS) s.coords[(g + 1) & 1][gt] = cnext;
                     named_bar_sync(1, NGEN);  // next chunk's records visible; nobody still reads the buffer written next time
                     wait(&s.a_empty[sa], ((g / AST) & 1) ^ 1);
                     if (F16) {
@@ -683,17 +658,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) observe_tf32_kernel(const Params 
                 else mbar_arrive(&s.t_empty[acc]);
             }
             if (valid) {
-                double prior = 1.0;
-                if (KIND == 1) {  // 1 + [x, 1] diag(c^2) [x, 1]^T (gpmdm.py:1092-1101)
-#pragma unroll
-                    for (int j = 0; j < DL; j++) {
-                        const double xj = prm.x[p * DL + j];
-                        prior = fma(prm.lin_c2[j] * xj, xj, prior);
-                    }
-                    prior += prm.lin_c2[DL];
-                }
-                const double v = prior - (double)q;
-                if (prm.status && !(v > 0.0 && v < INFINITY)) atomicAdd(prm.status, 1);
+                // KIND 1: the RBF part 1 - |W_c k_rbf|^2 only; the linear-kernel part of the class-block variance is
+                // low rank and is added exactly, in fp64, by gpmdm_pf_propagate_meanonly_f64 (which also counts faults)
+                const double v = 1.0 - (double)q;
+                if (KIND == 0 && prm.status && !(v > 0.0 && v < INFINITY)) atomicAdd(prm.status, 1);
                 if (prm.ll) prm.ll[p] = -0.5 * S / v - (double)prm.dout * log(v) + prm.ll_const;
                 if (prm.v_out) prm.v_out[p] = v;
             }
@@ -1088,27 +1056,25 @@ extern "C" int gpmdm_pf_observe_f16x2(const gpmdm_gp_model_tf32* m, const double
 }
 
 extern "C" int gpmdm_pf_dynvar_tc(const gpmdm_tc_block* blocks, int32_t n_blocks, int32_t d, int32_t mode,
-                                  const double* lengthscales, const double* lin_c2, const double* x_prev,
-                                  const int32_t* perm, const int32_t* tiles128, const int32_t* n_tiles128, int64_t P,
-                                  double* v_out, int32_t* tile_counter, void* stream) {
-    GPMDM_REQUIRE(blocks && lengthscales && lin_c2, GPMDM_E_INVALID, "null model field");
+                                  const double* lengthscales, const double* x_prev, const int32_t* perm,
+                                  const int32_t* tiles128, const int32_t* n_tiles128, int64_t P, double* u_out,
+                                  void* stream) {
+    GPMDM_REQUIRE(blocks && lengthscales, GPMDM_E_INVALID, "null model field");
     GPMDM_REQUIRE(n_blocks >= 1 && d >= 1 && d <= GPMDM_MAX_LATENT && (mode == 0 || mode == 1), GPMDM_E_UNSUPPORTED,
                   "bad sizes n_blocks=%d d=%d mode=%d", n_blocks, d, mode);
     GPMDM_REQUIRE(P >= 0 && P < (1ll << 31), GPMDM_E_INVALID, "P out of range");
     if (P == 0) return 0;
-    GPMDM_REQUIRE(x_prev && perm && tiles128 && n_tiles128 && v_out, GPMDM_E_INVALID, "null argument");
+    GPMDM_REQUIRE(x_prev && perm && tiles128 && n_tiles128 && u_out, GPMDM_E_INVALID, "null argument");
     tf32::Params prm{};
     prm.dblocks = blocks;
     prm.d = d;
     prm.ls = lengthscales;
-    prm.lin_c2 = lin_c2;
     prm.x = x_prev;
     prm.P = P;
     prm.perm = perm;
     prm.tiles = tiles128;
     prm.n_tiles_dev = n_tiles128;
-    prm.v_out = v_out;
-    prm.status = tile_counter ? tile_counter + 2 : nullptr;
+    prm.v_out = u_out;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);

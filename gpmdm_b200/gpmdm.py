@@ -775,7 +775,8 @@ class GPMDM(torch.nn.Module):
             dyn = model(dblks, self.d, self.d, TILE_N, 1, ls_x, c2, lam_x)
         else:
             dyn = None
-        self._packed = dict(tri=tri, obs=obs, obs_has_L=with_obs_L, dyn=dyn, keep=keep, obs_n_pad=oblk["n_pad"],
+        self._packed = dict(tri=tri, obs=obs, obs_has_L=with_obs_L, dyn=dyn, dyn_blocks=dblks if dyn is not None else None,
+                            keep=keep, obs_n_pad=oblk["n_pad"],
                             dyn_max_n_pad=max(b["n_pad"] for b in dblks) if dyn is not None else 0,
                             ll_const_terms=(2.0 * torch.sum(self._d("y_log_lambdas"))).item())
         return self._packed
@@ -813,35 +814,50 @@ class GPMDM(torch.nn.Module):
 
     @torch.no_grad()
     def packed_model_tc_dyn(self, kind="tf32"):
-        """Operands of the tensor-core dynamics-variance kernel (include/gpmdm_b200.h: gpmdm_tc_block), one block per
-        class: the whitening factor W_c = L_c^-1 of the class block K_c + 1e-6 I (gpmdm.py:1301-1303) as tensor-core tiles,
-        and the training records (RBF coordinates pre-scaled by sqrt(log2 e) / l, linear-kernel terms c_k^2 x_ik)."""
+        """Operands of the tensor-core dynamics variance (include/gpmdm_b200.h, "dynamics GP variance on the tensor
+        cores"), one block per class with K_c = L_c L_c^T the class block incl. the 1e-6 jitter (gpmdm.py:1301-1303):
+          table   gpmdm_tc_block per class: W_c = L_c^-1 as tensor-core tiles + the RBF training records
+          model   the dynamics gpmdm_gp_model with alpha tiles [alpha_c | G_c], G_c = K_c^-1 [X_in, 1] diag(c^2)
+          H       [C, d+1, d+1]: diag(c^2) [X_in, 1]^T G_c"""
         cache = self.__dict__.setdefault("_packed_tc_dyn", {})
         if kind in cache and cache[kind]["version"] == self._factors_version:
             return cache[kind]
+        lib = _cabi.lib()
+        pk = self.packed_models()
+        if pk["dyn"] is None:
+            raise ValueError("fused dynamics prediction supports dyn_back_step == 1 only")
         key = "wtiles" if kind == "tf32" else "wtiles_f16"
         offs = self.class_pair_offsets()
         ls = torch.exp(self._d("x_log_lengthscales")).contiguous()
         c2 = (torch.exp(self._d("x_log_lin_coeff")) ** 2).contiguous()
+        lam = (torch.exp(self._d("x_log_lambdas")) ** -2).contiguous()
         d = self.d
-
-        def pairs(M, n_pad):  # [n, d] fp64 -> [n_pad / 2, 8, 2] fp32: rows interleaved in pairs per coordinate
-            out = torch.zeros(n_pad, 8, dtype=torch.float32, device=self.device)
-            out[:M.shape[0], :d] = M.to(torch.float32)
-            return out.view(n_pad // 2, 2, 8).transpose(1, 2).contiguous()
-
-        rows, keep = [], [ls, c2]
+        rows, mrows, Hs, keep = [], [], [], [ls, c2, lam]
         for c in range(self.n_classes):
-            blk = self._dyn_blks[c]
             Xc = self._Xin[offs[c]:offs[c + 1]]
-            if blk.get(key) is None:  # not part of the precompute: factor the class block (again) for its W tiles only
-                blk[key] = self._factor_block(lambda: self._dyn_kernel_matrix(c), self._Xout[offs[c]:offs[c + 1]].contiguous(),
-                                              (kind,))[key]
-            coords, lin = pairs(Xc / ls * 1.2011224087864498, blk["n_pad"]), pairs(Xc * c2[:d], blk["n_pad"])
-            keep += [coords, lin, blk[key]]
-            rows.append([coords.data_ptr(), lin.data_ptr(), blk[key].data_ptr(), blk["n"], blk["n_pad"]])
+            n = Xc.shape[0]
+            XS = torch.cat([Xc, torch.ones(n, 1, dtype=F64, device=self.device)], 1) * c2  # [X_in, 1] diag(c^2)
+            fb = self._factor_block(lambda: self._dyn_kernel_matrix(c),
+                                    torch.cat([self._Xout[offs[c]:offs[c + 1]], XS], 1).contiguous(), (kind,))
+            n_pad = fb["n_pad"]
+            Hs.append(XS.t() @ fb["A"][:, d:])
+            alpha = torch.empty(int(lib.gpmdm_alpha_bytes(n_pad, TILE_N)) // 8, dtype=F64, device=self.device)
+            check(lib.gpmdm_pack_alpha_f64(ptr(fb["A"]), n, n_pad, 2 * d + 1, TILE_N, ptr(alpha), stream()),
+                  "gpmdm_pack_alpha_f64")
+            coords = torch.zeros(n_pad, 8, dtype=torch.float32, device=self.device)
+            coords[:n, :d] = (Xc / ls * 1.2011224087864498).to(torch.float32)  # sqrt(log2 e)
+            coords = coords.view(n_pad // 2, 2, 8).transpose(1, 2).contiguous()  # [pair][coordinate][row in pair]
+            base = pk["dyn_blocks"][c]  # fp64 training records (and the quadratic-form panels, unused here)
+            keep += [coords, fb[key], alpha]
+            rows.append([coords.data_ptr(), fb[key].data_ptr(), n, n_pad])
+            mrows.append([base["coords"].data_ptr(), base["L"].data_ptr(), alpha.data_ptr(), n, n_pad])
         table = torch.tensor(rows, dtype=torch.int64, device=self.device)
-        cache[kind] = dict(version=self._factors_version, table=table, keep=keep, ls=ls, c2=c2, mode=0 if kind == "tf32" else 1)
+        mtable = torch.tensor(mrows, dtype=torch.int64, device=self.device)
+        H = torch.stack(Hs).contiguous()
+        model = GpModel(blocks=mtable.data_ptr(), n_blocks=self.n_classes, d=d, dout=d, alpha_ld=TILE_N, kind=1, tri=1,
+                        lengthscales=ls.data_ptr(), lin_c2=c2.data_ptr(), lambdas=lam.data_ptr())
+        cache[kind] = dict(version=self._factors_version, table=table, model=model, H=H, ls=ls, keep=keep + [mtable, pk],
+                           mode=0 if kind == "tf32" else 1)
         return cache[kind]
 
     LOWLAT_MAX_TILES = 110  # below this many 64-particle tiles (of 148 SMs) the column tiles are split over CTAs
@@ -959,11 +975,10 @@ class GPMDM(torch.nn.Module):
                                   torch.zeros_like(t2)], 1).contiguous()
             n_tiles2 = torch.tensor([nt2], dtype=torch.int32, device=self.device)
             v = torch.empty(P, dtype=F64, device=self.device)
-            check(lib.gpmdm_pf_dynvar_tc(ptr(tc["table"]), self.n_classes, self.d, tc["mode"], ptr(tc["ls"]), ptr(tc["c2"]),
-                                         ptr(Xs), ptr(perm), ptr(tiles2), ptr(n_tiles2), P, ptr(v),
-                                         ptr(self._scratch_counter()), stream()), "gpmdm_pf_dynvar_tc")
-            check(lib.gpmdm_pf_propagate_meanonly_f64(ctypes.byref(pk["dyn"]), ptr(Xs), ptr(perm), ptr(tiles), ptr(n_tiles),
-                                                      P, None, ptr(v), None, ptr(mean), ptr(var),
+            check(lib.gpmdm_pf_dynvar_tc(ptr(tc["table"]), self.n_classes, self.d, tc["mode"], ptr(tc["ls"]), ptr(Xs), ptr(perm),
+                                         ptr(tiles2), ptr(n_tiles2), P, ptr(v), stream()), "gpmdm_pf_dynvar_tc")
+            check(lib.gpmdm_pf_propagate_meanonly_f64(ctypes.byref(tc["model"]), ptr(tc["H"]), ptr(Xs), ptr(perm), ptr(tiles),
+                                                      ptr(n_tiles), P, None, ptr(v), None, ptr(mean), ptr(var),
                                                       ptr(self._scratch_counter()), stream()),
                   "gpmdm_pf_propagate_meanonly_f64")
         elif self._use_lowlat(P, low_latency):

@@ -313,16 +313,16 @@ class GPMDM_PF:
         check(lib.gpmdm_pf_transition_f64(ptr(c_prev), ptr(self._markov_switching_model), ptr(E), Pl, C, ptr(c_new_l), st),
               "gpmdm_pf_transition_f64")
         if self._tc_dyn is not None:
-            # tensor-core variants: variances prior - |W_c k|^2 on tcgen05 per class block, then means + draw in fp64 on the
-            # alpha tiles only
+            # tensor-core variants: the O(N_c^2) part of the variance, 1 - |W_c k_rbf|^2, on tcgen05 per class block; the
+            # low-rank (linear kernel) part, the means and the draw in fp64 on the alpha tiles only
             tc = self._tc_dyn
             check(lib.gpmdm_pf_bucket_by_class2(ptr(c_new_l), Pl, C, ptr(self._perm), ptr(self._tiles), ptr(self._n_tiles),
                                                 ptr(self._tiles128), ptr(self._n_tiles128), ptr(self._ws), st),
                   "gpmdm_pf_bucket_by_class2")
-            check(lib.gpmdm_pf_dynvar_tc(ptr(tc["table"]), C, d, tc["mode"], ptr(tc["ls"]), ptr(tc["c2"]), ptr(x_prev),
-                                         ptr(self._perm), ptr(self._tiles128), ptr(self._n_tiles128), Pl, ptr(self._v_dyn),
-                                         ptr(self._counter), st), "gpmdm_pf_dynvar_tc")
-            check(lib.gpmdm_pf_propagate_meanonly_f64(ctypes.byref(self._packed["dyn"]), ptr(x_prev), ptr(self._perm),
+            check(lib.gpmdm_pf_dynvar_tc(ptr(tc["table"]), C, d, tc["mode"], ptr(tc["ls"]), ptr(x_prev), ptr(self._perm),
+                                         ptr(self._tiles128), ptr(self._n_tiles128), Pl, ptr(self._v_dyn), st),
+                  "gpmdm_pf_dynvar_tc")
+            check(lib.gpmdm_pf_propagate_meanonly_f64(ctypes.byref(tc["model"]), ptr(tc["H"]), ptr(x_prev), ptr(self._perm),
                                                       ptr(self._tiles), ptr(self._n_tiles), Pl, ptr(eps), ptr(self._v_dyn),
                                                       ptr(x_new_l), None, None, ptr(self._counter), st),
                   "gpmdm_pf_propagate_meanonly_f64")

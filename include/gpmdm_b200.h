@@ -273,15 +273,20 @@ int gpmdm_pf_observe_f16x2(const gpmdm_gp_model_tf32* obs, const double* x, int6
                            int32_t* tile_counter, void* stream);
 
 /* ---- dynamics GP variance on the tensor cores (precision "tf32" / "f16x2"; gpmdm.py:1032-1068) ----------------------
- * The same tcgen05 kernel run per class block: var_p = prior_p - |W_c k|^2 with W_c = L_c^-1 (K_c = L_c L_c^T the class
- * block incl. the 1e-6 jitter, gpmdm.py:1301-1303), k = RBF + linear cross-kernel generated on the fly, prior_p =
- * 1 + [x,1] diag(c^2) [x,1]^T.  Particles are reached through gpmdm_pf_bucket_by_class2's permutation in class-homogeneous
- * tiles of 128.  The means (and the draw) follow in fp64 on the alpha tile only: gpmdm_pf_propagate_meanonly_f64.
- *   coords / lin [n_pad/2, 8, 2] fp32: sqrt(log2 e) x_i / lengthscale and c_k^2 x_i[k], rows interleaved in pairs as for
- *   gpmdm_gp_model_tf32; wtiles from gpmdm_pack_whitened_tf32 (mode 0) / gpmdm_pack_whitened_f16x2 (mode 1). */
+ * The class block K_c (incl. the 1e-6 jitter, gpmdm.py:1301-1303) = L_c L_c^T, W_c = L_c^-1, and the cross-kernel is
+ * k = k_rbf + X~ S x~ (X~ = [X_in, 1], S = diag(c^2), x~ = [x, 1]; gpmdm.py:545-548), so
+ *     var = prior - |W_c k|^2 = (1 - |W_c k_rbf|^2)  +  x~^T S x~ - 2 (k^T G_c) x~ + x~^T H_c x~,
+ *     G_c = K_c^-1 X~ S  [N_c, d+1],   H_c = S X~^T G_c  [d+1, d+1].
+ * Only the first term needs O(N_c^2) work: it runs on tcgen05 with entries k_rbf <= 1 (gpmdm_pf_dynvar_tc, the
+ * observation kernel per class block, particles reached through gpmdm_pf_bucket_by_class2's permutation in
+ * class-homogeneous tiles of 128).  The low-rank remainder is exact fp64: gpmdm_pf_propagate_meanonly_f64 contracts k with
+ * the alpha tile [alpha_c | G_c] (2 N_c (2d+1) flops) and finishes the variance, the mean and the draw.  Keeping the linear
+ * kernel (entries ~ |x|^2 c^2, all of one sign) off the tensor cores is what keeps their rounding error relative to 1
+ * instead of to the prior.
+ *   coords [n_pad/2, 8, 2] fp32: sqrt(log2 e) x_i / lengthscale, rows interleaved in pairs as for gpmdm_gp_model_tf32;
+ *   wtiles from gpmdm_pack_whitened_tf32 (mode 0) / gpmdm_pack_whitened_f16x2 (mode 1). */
 typedef struct gpmdm_tc_block {
     const float* coords;
-    const float* lin;
     const void* wtiles;
     int64_t n;
     int64_t n_pad;
@@ -290,18 +295,19 @@ typedef struct gpmdm_tc_block {
 /* gpmdm_pf_bucket_by_class plus a second tile table with 128-particle tiles (tiles128 [P/128 + C, 4], n_tiles128 [1]). */
 int gpmdm_pf_bucket_by_class2(const int64_t* classes, int64_t P, int32_t C, int32_t* perm, int32_t* tiles,
                               int32_t* n_tiles, int32_t* tiles128, int32_t* n_tiles128, void* workspace, void* stream);
-/* v_out [P] (indexed by particle) = prior - |W_c k|^2, i.e. the dynamics variance before the lambda^-2 scaling.
- * blocks: DEVICE array of n_blocks structs; mode 0 = tf32 x 3, 1 = fp16 split; tile_counter as for the predict calls
- * (word [2] counts non-positive variances). */
+/* u_out [P] (indexed by particle) = 1 - |W_c k_rbf|^2.  blocks: DEVICE array of n_blocks structs; mode 0 = tf32 x 3,
+ * 1 = fp16 split. */
 int gpmdm_pf_dynvar_tc(const gpmdm_tc_block* blocks, int32_t n_blocks, int32_t d, int32_t mode, const double* lengthscales,
-                       const double* lin_c2, const double* x_prev, const int32_t* perm, const int32_t* tiles128,
-                       const int32_t* n_tiles128, int64_t P, double* v_out, int32_t* tile_counter, void* stream);
-/* gpmdm_pf_propagate_f64 with the variances supplied (v_in [P], before the lambda^-2 scaling): only the alpha tile of each
- * class block is contracted (2 N_c d of the 2 N_c^2 + 2 N_c d flops), then x_new = eps * sqrt(v lambda^-2) + mean. */
-int gpmdm_pf_propagate_meanonly_f64(const gpmdm_gp_model* dyn, const double* x_prev, const int32_t* perm,
-                                    const int32_t* tiles, const int32_t* n_tiles, int64_t P, const double* eps,
-                                    const double* v_in, double* x_new, double* mean_out, double* var_out,
-                                    int32_t* tile_counter, void* stream);
+                       const double* x_prev, const int32_t* perm, const int32_t* tiles128, const int32_t* n_tiles128,
+                       int64_t P, double* u_out, void* stream);
+/* gpmdm_pf_propagate_f64 with the O(N_c^2) part of the variance supplied: u_in [P] from gpmdm_pf_dynvar_tc.  `dyn` is a
+ * dynamics model whose alpha matrices carry d + 1 extra columns G_c after the d of alpha_c; lowrank_h = DEVICE
+ * [n_blocks, d+1, d+1] doubles (H_c, row major).  Only the alpha tile of each class block is contracted; then
+ * x_new = eps * sqrt(var lambda^-2) + mean.  tile_counter word [2] counts non-positive variances. */
+int gpmdm_pf_propagate_meanonly_f64(const gpmdm_gp_model* dyn, const double* lowrank_h, const double* x_prev,
+                                    const int32_t* perm, const int32_t* tiles, const int32_t* n_tiles, int64_t P,
+                                    const double* eps, const double* u_in, double* x_new, double* mean_out,
+                                    double* var_out, int32_t* tile_counter, void* stream);
 
 /* ---- one filter step as two calls (GPMDM_PF._update, gpmdm_pf.py:126-135) ----------------------------------
  * The host-side sequence of the stage entry points above, issued from native code so that a step costs two FFI calls
