@@ -201,3 +201,67 @@ def test_transition_bit_exact(case):
                                                 _cabi.stream()), "transition")
         assert torch.equal(out.cpu(), torch.as_tensor(s["c_new"]))
         classes = dev(s["classes_post"], torch.int64)
+
+
+def test_achieved_errors_report(case):
+    """Not a new bound: records what the CUDA path ACHIEVES against each reference fixture (every recorded step, the
+    reference's own post-dynamics states and inverses) -- max / median errors of means, variances, log-likelihoods -- as one
+    JSON line per fixture in gpurun_out/parity_achieved.jsonl (copied to profiles/ per round)."""
+    import json
+    import os
+
+    from gpmdm_b200 import _cabi
+    from oracle import gpmdm_oracle as orc
+
+    g, model = case
+    lib = _cabi.lib()
+    model._packed = None
+    pk = model.packed_models(True)
+    lam_y = torch.exp(g.spec.y_log_lambdas) ** -2
+    lam_x = torch.exp(g.spec.x_log_lambdas) ** -2
+    ll_const = float(2.0 * torch.sum(g.spec.y_log_lambdas)) - orc.c32_constant(g.spec.D)
+    rec = {"fixture": g.name if hasattr(g, "name") else str(g.spec.N), "N": int(g.spec.N), "P": int(g.P), "C": int(g.C),
+           "d": int(g.spec.d), "D": int(g.spec.D), "steps": int(g.steps)}
+    acc = {k: [] for k in ("mu", "v", "ll_all", "ll_v>1e-2", "dyn_mean", "dyn_var", "v_ref")}
+    for t in range(g.steps):
+        s = g.step(t)
+        x_ref = (t64(s["eps"]) * t64(s["dyn_std"]) + t64(s["dyn_mean"])).cuda().contiguous()
+        P = x_ref.shape[0]
+        ll = torch.empty(P, dtype=torch.float64, device="cuda")
+        mu = torch.empty(P, g.spec.D, dtype=torch.float64, device="cuda")
+        v = torch.empty(P, dtype=torch.float64, device="cuda")
+        counter = torch.zeros(4, dtype=torch.int32, device="cuda")
+        _cabi.check(lib.gpmdm_pf_observe_f64(ctypes.byref(pk["obs"]), x_ref.data_ptr(), P, dev(s["z"]).data_ptr(), ll_const,
+                                             ll.data_ptr(), mu.data_ptr(), v.data_ptr(), counter.data_ptr(),
+                                             _cabi.stream()), "observe")
+        scale = torch.clamp(torch.abs(t64(s["mu"])).max(dim=1, keepdim=True).values, min=1e-3)
+        acc["mu"].append((torch.abs(mu.cpu() - t64(s["mu"])) / scale).max(dim=1).values)
+        v_ref = t64(s["var"])[:, 0] / lam_y[0]
+        acc["v"].append(torch.abs(v.cpu() - v_ref))
+        acc["v_ref"].append(v_ref)
+        rel = torch.abs(ll.cpu() - t64(s["ll"])) / torch.abs(t64(s["ll"]))
+        acc["ll_all"].append(rel)
+        acc["ll_v>1e-2"].append(rel[v_ref > 1e-2])
+        x_prev = t64(g.z["init_states"]) if t == 0 else t64(g.step(t - 1)["states_post"])
+        c_new = torch.as_tensor(s["c_new"])
+        for c in range(g.C):
+            rows = torch.nonzero(c_new == c).squeeze(-1)
+            if rows.numel() == 0:
+                continue
+            mean, var = model.map_x_dynamics_for_class(x_prev[rows].cuda(), c)
+            ref_mean, ref_var = t64(s["dyn_mean"])[rows], t64(s["dyn_std"])[rows] ** 2
+            sc = torch.clamp(torch.abs(ref_mean).max(dim=1, keepdim=True).values, min=1e-3)
+            acc["dyn_mean"].append((torch.abs(mean.cpu() - ref_mean) / sc).flatten())
+            prior = orc.x_diag_kernel(g.spec, x_prev[rows]).unsqueeze(1) * lam_x.unsqueeze(0)
+            acc["dyn_var"].append((torch.abs(var.cpu() - ref_var) / prior).flatten())
+    for k, parts in acc.items():
+        a = torch.cat([p.flatten() for p in parts]) if parts else torch.zeros(0)
+        if k == "v_ref":
+            rec["v_ref_min"], rec["v_ref_median"] = float(a.min()), float(a.median())
+        elif a.numel():
+            rec[k] = {"max": float(a.max()), "median": float(a.median()), "n": int(a.numel())}
+    model._packed = None
+    assert rec["mu"]["max"] < TOL and rec["v"]["max"] < TOL and rec["dyn_mean"]["max"] < TOL and rec["dyn_var"]["max"] < TOL
+    if os.path.isdir("gpurun_out"):
+        with open("gpurun_out/parity_achieved.jsonl", "a") as fh:
+            fh.write(json.dumps(rec) + "\n")
