@@ -71,7 +71,7 @@ _SIGNATURES = {
                                                      _ptr, _ptr, _i64, _ptr, _ptr, _i64, _ptr]),
     "gpmdm_pf_loglik_f64": (ctypes.c_int, [ctypes.POINTER(GpModel), _ptr, _i64, _ptr, _f64, _ptr, _ptr, _ptr, _ptr,
                                            _ptr]),
-    "gpmdm_predict_lowlat_workspace_bytes": (_i64, [_i64, _i64, _i32, _i32]),
+    "gpmdm_predict_lowlat_workspace_bytes": (_i64, [_i64, _i64, _i32, _i32, _i32]),
     "gpmdm_predict_lowlat_pick_segment": (_i32, [_i64, _i64, _i32, _i32]),
     "gpmdm_pf_observe_lowlat_f64": (ctypes.c_int, [ctypes.POINTER(GpModel), _ptr, _i64, _ptr, _f64, _ptr, _ptr, _ptr,
                                                    _ptr, _i64, _i32, _ptr, _ptr, _ptr]),
@@ -129,7 +129,7 @@ def lib() -> ctypes.CDLL:
         for name, (res, args) in _SIGNATURES.items():
             fn = getattr(handle, name)  # AttributeError if the build is stale
             fn.restype, fn.argtypes = res, args
-        if handle.gpmdm_abi_version() != 3:
+        if handle.gpmdm_abi_version() != 4:
             raise RuntimeError("libgpmdm_sm100a.so ABI version mismatch; rebuild")
         _lib = handle
     return _lib

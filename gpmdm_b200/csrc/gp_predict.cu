@@ -250,8 +250,27 @@ struct ChunkCursor {
 // tile: with the triangular packing a K* entry is used by nq/2 column tiles on average, so the fp64 datapath the
 // DMMAs run on is relieved of ~97 % of the exp work.  Each lane reads back only what it wrote itself: no barrier,
 // no fence.  Values are bit-identical to the on-the-fly instantiation (same function, same inputs).
-template <int KIND, int DL, bool CACHE>
+#ifdef GPMDM_TIMELINE  /* diagnostic build (tools/lowlat_timeline.py): per-item time stamps of the work-item loop */
+constexpr int TL_ITEMS = 64, TL_WORDS = 8;
+__device__ unsigned long long g_timeline[160 * TL_ITEMS * TL_WORDS];
+__device__ int g_timeline_n[160];
+__device__ __forceinline__ unsigned long long tl_now() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+#define GPMDM_TL(slot)                                                                                     \
+    if (tid == 0 && tl_i < TL_ITEMS) g_timeline[((long long)blockIdx.x * TL_ITEMS + tl_i) * TL_WORDS + (slot)] = tl_now();
+#else
+#define GPMDM_TL(slot)
+#endif
+
+// SPLIT (low-latency launches, CACHE only): the K* slices come from kstar_fill_kernel (one slice per particle TILE, shared by
+// all the tile's work items), and warps whose 8 particle rows lie beyond the tile's count skip the fragment loads, the MMAs
+// and the epilogues -- they only keep the ring's barriers moving -- so a ragged tile costs its rows rounded up to 8, not 64.
+template <int KIND, int DL, bool CACHE, bool SPLIT = false>
 __global__ void __launch_bounds__(NTHREADS, 1) gp_predict_kernel(const PredictParams prm) {
+    static_assert(!SPLIT || CACHE, "the low-latency instantiation reads the shared K* slices");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     Smem& s = *reinterpret_cast<Smem*>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -279,11 +298,28 @@ __global__ void __launch_bounds__(NTHREADS, 1) gp_predict_kernel(const PredictPa
 
     const int total_items = prm.split ? total_tiles * prm.max_nct * prm.nseg : total_tiles;
     int rounds_done = 0;
+#ifdef GPMDM_TIMELINE
+    int tl_i = -1;
+    const unsigned long long tl_enter = tl_now();
+#endif
     for (;;) {
+#ifdef GPMDM_TIMELINE
+        tl_i++;
+        GPMDM_TL(0)
+#endif
         if (tid == 0) s.tile = atomicAdd(prm.counter, 1);
         __syncthreads();
         const int item = s.tile;
         __syncthreads();
+#ifdef GPMDM_TIMELINE
+        GPMDM_TL(1)
+        if (tid == 0 && tl_i < TL_ITEMS) {
+            g_timeline[((long long)blockIdx.x * TL_ITEMS + tl_i) * TL_WORDS + 6] = (unsigned long long)(unsigned)item;
+            g_timeline[((long long)blockIdx.x * TL_ITEMS + tl_i) * TL_WORDS + 7] = tl_enter;
+            g_timeline[((long long)blockIdx.x * TL_ITEMS + tl_i) * TL_WORDS + 2] = 0;
+            g_timeline_n[blockIdx.x] = tl_i + 1;
+        }
+#endif
         if (item >= total_items) {
             // leaving: satisfy every later round so that nobody waits for this CTA
             if (prm.round_sync && tid == 0) atomicAdd(prm.counter + 1, 1 << 20);  // > any target (n_tiles < 2^20)
@@ -326,6 +362,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gp_predict_kernel(const PredictPa
             kend = min(kfirst + prm.seg_chunks, nkc);
         }
 
+        const bool active = !SPLIT || warp * 8 < count;  // warp-uniform
         // ---- this lane's particle row --------------------------------------------------------------------
         ParticleRec<KIND, DL> pr;
         int pidx;
@@ -380,8 +417,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) gp_predict_kernel(const PredictPa
         constexpr int KCHUNK = TM * KC;  // doubles per chunk in the cache: [warp][k4][lane]
         if (CACHE) {
             if ((long long)n_pad * TM > prm.kcache_stride) __trap();  // workspace sized for a smaller block
-            kc = prm.kcache + (long long)blockIdx.x * prm.kcache_stride + warp * (KC / 4 * 32) + lane;
-            for (int k = 0; k < nkc; k++) {
+            kc = prm.kcache + (long long)(SPLIT ? t : (int)blockIdx.x) * prm.kcache_stride + warp * (KC / 4 * 32) + lane;
+            for (int k = 0; !SPLIT && k < nkc; k++) {
                 double g[KC / 4];
                 kstar_multi<KIND, DL, KC / 4>(gbk.coords + (long long)(k * KC + c) * REC, 4 * REC, pr, c2last, exptab, g);
 #pragma unroll
@@ -392,10 +429,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) gp_predict_kernel(const PredictPa
         // ---- A fragments of the first chunk: a[k4] = K*[row 8 w + r][k = 4 k4 + c] -----------------------------
         double a[KC / 4];
         mbar_wait(&s.full[cst], cph);
+        GPMDM_TL(2)
         if (CACHE) {
-            const int k0 = (prm.tri && ct_begin < nq) ? ct_begin * (TN / KC) : 0;
+            const int k0 = kfirst >= 0 ? kfirst : ((prm.tri && ct_begin < nq) ? ct_begin * (TN / KC) : 0);
 #pragma unroll
-            for (int i = 0; i < KC / 4; i++) a[i] = __ldcg(kc + (long long)k0 * KCHUNK + i * 32);
+            for (int i = 0; i < KC / 4; i++) a[i] = active ? __ldcg(kc + (long long)k0 * KCHUNK + i * 32) : 0.0;
         } else {
             kstar_multi<KIND, DL, KC / 4>(&s.R[cst][c * REC], 4 * REC, pr, c2last, exptab, a);
         }
@@ -456,7 +494,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gp_predict_kernel(const PredictPa
         if (has_next) { GPMDM_ADVANCE(stn, phn) }                                                                \
         /* K* cache: the next chunk's fragments are requested now and consumed after the MMA blocks */           \
         double an[KC / 4];                                                                                       \
-        if (CACHE) {                                                                                             \
+        if (CACHE && active) {                                                                                   \
             const int kn = !has_next ? k : (k + 1 < kend ? k + 1 : cur.kbeg(ct + 1));                            \
             _Pragma("unroll") for (int i = 0; i < KC / 4; i++) an[i] = __ldcg(kc + (long long)kn * KCHUNK + i * 32); \
         }                                                                                                        \
@@ -464,10 +502,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) gp_predict_kernel(const PredictPa
         const uint32_t ready = has_next ? mbar_test(&s.full[stn], phn) : 1u;                                     \
         /* B fragments are software-pipelined one group of 8 column blocks ahead of the MMAs that use them */      \
         double bq[8];                                                                                            \
-        if (GROUP_ON(0)) {                                                                                       \
+        if (active && GROUP_ON(0)) {                                                                             \
             _Pragma("unroll") for (int j = 0; j < 8; j++) bq[j] = s.B[st][c][j * 8 + r];                         \
         }                                                                                                        \
-        _Pragma("unroll") for (int k4 = 0; k4 < KC / 4; k4++) {                                                  \
+        if (active) _Pragma("unroll") for (int k4 = 0; k4 < KC / 4; k4++) {                                      \
             const double ak = a[k4];                                                                             \
             _Pragma("unroll") for (int jg = 0; jg < NJ; jg += 8) {                                               \
                 if (GROUP_ON(jg)) {                                                                              \
@@ -482,7 +520,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gp_predict_kernel(const PredictPa
         }                                                                                                        \
         /* the next chunk's four A fragments: four independent exp chains in one block */                        \
         if (!ready) mbar_wait(&s.full[stn], phn);                                                                \
-        GPMDM_MAIN_LOOP_KSTAR                                                                                    \
+        if (active) { GPMDM_MAIN_LOOP_KSTAR }                                                                    \
         __syncwarp();                                                                                            \
         if (lane == 0) mbar_arrive(&s.empty[st]); /* this warp is done with the ring slot */                     \
         GPMDM_ADVANCE(cst, cph)                                                                                  \
@@ -501,11 +539,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) gp_predict_kernel(const PredictPa
             }
 #undef GPMDM_K_LOOP
 #undef constexpr_next_group
+            GPMDM_TL(3)
 #undef GPMDM_ALL_GROUPS
 #undef GPMDM_SOME_GROUPS
 
             // ---- epilogues (per warp; a row's columns live in the 4 lanes of a quad) -------------------------
-            if (ct < nq) {
+            if (!active) {
+                // nothing to finish for this warp
+            } else if (ct < nq) {
                 // q[p] += sum_n C[p,n] * K*[p,n] over this tile's columns (K* regenerated per element)
 #pragma unroll
                 for (int j = 0; j < NJ; j++) {  // fully unrolled: acc[][] must stay in registers
@@ -591,6 +632,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gp_predict_kernel(const PredictPa
                 }
             }
         }
+        GPMDM_TL(4)
         // Round synchronisation (observation kernel, several uniform tiles per CTA): every CTA waits, with a bounded
         // number of polls, until all CTAs have finished the same number of tiles.  Within one round the CTAs walk L in
         // lockstep and it is read from HBM once (L2 hit 97 %); without re-alignment they drift beyond the reach of
@@ -607,6 +649,58 @@ __global__ void __launch_bounds__(NTHREADS, 1) gp_predict_kernel(const PredictPa
             }
             __syncthreads();
         }
+    }
+}
+
+// Low-latency launches: the K* slice of every particle TILE ([chunk][warp][k4][lane] = the order gp_predict_kernel's lanes
+// consume A fragments in), written once by a wide grid and read by all the tile's (column tile, k segment) work items.
+// Same function, same inputs as the per-CTA fill of the fused CACHE instantiation: the values are bit-identical.
+constexpr int FILL_CHUNKS = 8;  // k-chunks per CTA
+template <int KIND, int DL>
+__global__ void __launch_bounds__(NTHREADS) kstar_fill_kernel(const PredictParams prm) {
+    __shared__ double exptab[64];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int r = lane >> 2, c = lane & 3;
+    constexpr int REC = rec_width(KIND, DL);
+    if (tid < 64) exptab[tid] = c_exp_table[tid];
+    __syncthreads();
+    const int total_tiles = prm.tiles ? *prm.n_tiles : (int)((prm.P + TM - 1) / TM);
+    const int t = blockIdx.x;
+    if (t >= total_tiles) return;
+    int blk = 0, first = t * TM, count;
+    if (prm.tiles) {
+        blk = prm.tiles[4 * t + 0];
+        first = prm.tiles[4 * t + 1];
+        count = prm.tiles[4 * t + 2];
+    } else {
+        const long long rem = prm.P - (long long)first;
+        count = rem < TM ? (int)rem : TM;
+    }
+    if (warp * 8 >= count) return;  // rows beyond the tile's count: their slots are never read
+    const gpmdm_gp_block gbk = prm.blocks[blk];
+    if ((long long)gbk.n_pad * TM > prm.kcache_stride) __trap();
+    const int nkc = (int)((gbk.n + KC - 1) / KC);
+    const double c2last = KIND == 1 ? prm.lin_c2[DL] : 0.0;
+    ParticleRec<KIND, DL> pr;
+    {
+        const int row = warp * 8 + r;
+        const int m = row < count ? row : count - 1;
+        const int p = prm.perm ? prm.perm[first + m] : first + m;
+#pragma unroll
+        for (int j = 0; j < DL; j++) {
+            const double xj = prm.x[(long long)p * DL + j];
+            pr.b[j] = xj / prm.ls[j];
+            if (KIND == 1) pr.x[j] = xj;
+        }
+    }
+    constexpr int KCHUNK = TM * KC;
+    double* kc = prm.kcache + (long long)t * prm.kcache_stride + warp * (KC / 4 * 32) + lane;
+    const int k1 = min(nkc, ((int)blockIdx.y + 1) * FILL_CHUNKS);
+    for (int k = (int)blockIdx.y * FILL_CHUNKS; k < k1; k++) {
+        double g[KC / 4];
+        kstar_multi<KIND, DL, KC / 4>(gbk.coords + (long long)(k * KC + c) * REC, 4 * REC, pr, c2last, exptab, g);
+#pragma unroll
+        for (int i = 0; i < KC / 4; i++) __stcg(kc + (long long)k * KCHUNK + i * 32, g[i]);
     }
 }
 
@@ -665,14 +759,14 @@ __global__ void __launch_bounds__(128) predict_finalize_kernel(const PredictPara
 }
 
 // ---- host side -------------------------------------------------------------------------------------
-template <int KIND, int DL, bool CACHE = false>
+template <int KIND, int DL, bool CACHE = false, bool SPLIT = false>
 static int launch_instance(const PredictParams& prm, int grid, cudaStream_t st) {
     // the opt-in to > 48 KB of dynamic shared memory is per function AND per device
     static bool configured[64] = {};  // per instantiation
     int dev = 0;
     cudaGetDevice(&dev);
     dev = (dev >= 0 && dev < 64) ? dev : 0;
-    auto kern = gp_predict_kernel<KIND, DL, CACHE>;
+    auto kern = gp_predict_kernel<KIND, DL, CACHE, SPLIT>;
     if (!configured[dev]) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
         if (e != cudaSuccess) {
@@ -696,6 +790,31 @@ static int dispatch_d_cached(const PredictParams& prm, int grid, cudaStream_t st
         case 6: return launch_instance<KIND, 6, true>(prm, grid, st);
         case 7: return launch_instance<KIND, 7, true>(prm, grid, st);
         case 8: return launch_instance<KIND, 8, true>(prm, grid, st);
+    }
+    set_error("latent dimension %d outside [1, %d]", prm.d, MAXD);
+    return GPMDM_E_UNSUPPORTED;
+}
+
+// low-latency launches: K* slices per particle tile (kstar_fill_kernel), then the (tile, column tile, k segment) items
+template <int KIND, int DL>
+static int launch_split(const PredictParams& prm, int grid, int tiles_bound, int max_nkc, cudaStream_t st) {
+    kstar_fill_kernel<KIND, DL><<<dim3((unsigned)tiles_bound, (unsigned)((max_nkc + FILL_CHUNKS - 1) / FILL_CHUNKS)), NTHREADS, 0,
+                                  st>>>(prm);
+    if (int rc = check_launch("kstar_fill_kernel")) return rc;
+    return launch_instance<KIND, DL, true, true>(prm, grid, st);
+}
+
+template <int KIND>
+static int dispatch_d_split(const PredictParams& prm, int grid, int tiles_bound, int max_nkc, cudaStream_t st) {
+    switch (prm.d) {
+        case 1: return launch_split<KIND, 1>(prm, grid, tiles_bound, max_nkc, st);
+        case 2: return launch_split<KIND, 2>(prm, grid, tiles_bound, max_nkc, st);
+        case 3: return launch_split<KIND, 3>(prm, grid, tiles_bound, max_nkc, st);
+        case 4: return launch_split<KIND, 4>(prm, grid, tiles_bound, max_nkc, st);
+        case 5: return launch_split<KIND, 5>(prm, grid, tiles_bound, max_nkc, st);
+        case 6: return launch_split<KIND, 6>(prm, grid, tiles_bound, max_nkc, st);
+        case 7: return launch_split<KIND, 7>(prm, grid, tiles_bound, max_nkc, st);
+        case 8: return launch_split<KIND, 8>(prm, grid, tiles_bound, max_nkc, st);
     }
     set_error("latent dimension %d outside [1, %d]", prm.d, MAXD);
     return GPMDM_E_UNSUPPORTED;
@@ -914,15 +1033,19 @@ static void choose_segments(int64_t max_n_pad, int32_t seg_chunks, int& seg, int
     nseg = (int)((nkc + sg - 1) / sg);
 }
 
-extern "C" int64_t gpmdm_predict_lowlat_workspace_bytes(int64_t P, int64_t max_n_pad, int32_t dout, int32_t seg_chunks) {
+// workspace = per-(column tile, segment) partial sums [max_nq * nseg][P], per-segment means [nseg][P][dout], and the K*
+// slices of the particle tiles [(P / 64 rounded up) + n_blocks][max_n_pad * 64]
+extern "C" int64_t gpmdm_predict_lowlat_workspace_bytes(int64_t P, int64_t max_n_pad, int32_t dout, int32_t seg_chunks,
+                                                        int32_t n_blocks) {
     int seg, nseg;
     choose_segments(max_n_pad, seg_chunks, seg, nseg);
-    return ((max_n_pad / TN) * P + P * (int64_t)dout) * nseg * 8;
+    const int64_t tiles_bound = (P + TM - 1) / TM + (n_blocks > 0 ? n_blocks : 1);
+    return (((max_n_pad / TN) * P + P * (int64_t)dout) * nseg + tiles_bound * max_n_pad * TM) * 8;
 }
 
 // Segment length that minimises the modelled makespan of the item grid of ONE launch on this device: `n_tiles` particle
 // tiles against a block of n_pad rows (alpha_ld / 256 mean tiles) -- waves of #SMs items, each item costing its chunks
-// (~2.5 us per [16 x 256] chunk at the uncached DMMA rate) plus a fixed ~8 us (item fetch, first TMA round trip, Hadamard
+// (~2.25 us per [16 x 256] chunk at the DMMA rate with the shared K* slices) plus a fixed ~8 us (item fetch, first TMA round trip, Hadamard
 // epilogue, partial-sum writes).  With 100 particles and N = 2000 it turns 88 items of 16 chunks (148 SMs: 60 % busy, 57 us)
 // into 148 items of 10.
 extern "C" int32_t gpmdm_predict_lowlat_pick_segment(int64_t n_tiles, int64_t n_pad, int32_t alpha_ld, int32_t tri) {
@@ -930,7 +1053,7 @@ extern "C" int32_t gpmdm_predict_lowlat_pick_segment(int64_t n_tiles, int64_t n_
     const long long nkc = n_pad / KC, nq = n_pad / TN, na = alpha_ld / TN;
     int dflt, nseg_d;
     choose_segments(n_pad, 0, dflt, nseg_d);
-    const double t_chunk = 2.5, t_item = 8.0;
+    const double t_chunk = 2.25, t_item = 8.0;
     double best = 1e300;
     int best_seg = dflt;
     for (long long sg = dflt; sg >= 4; sg--) {
@@ -962,9 +1085,12 @@ static int run_split(PredictParams& prm, int64_t max_n_pad, int32_t seg_chunks, 
     GPMDM_REQUIRE(e == cudaSuccess, (int)e, "cudaMemsetAsync: %s", cudaGetErrorString(e));
     e = cudaMemsetAsync(prm.counter, 0, 2 * sizeof(int32_t), st);
     GPMDM_REQUIRE(e == cudaSuccess, (int)e, "cudaMemsetAsync: %s", cudaGetErrorString(e));
-    const long long items = ((prm.P + TM - 1) / TM + prm.n_blocks) * prm.max_nct * prm.nseg;
+    const long long tiles_bound = (prm.P + TM - 1) / TM + prm.n_blocks;
+    prm.kcache = prm.mu_ws + (long long)prm.nseg * prm.P * prm.dout;
+    prm.kcache_stride = (long long)max_n_pad * TM;  // the kernels trap if a block on the device is larger
+    const long long items = tiles_bound * prm.max_nct * prm.nseg;
     const int grid = (int)(items < num_sms() ? items : num_sms());
-    if (int rc = dispatch_d<KIND>(prm, grid, st)) return rc;
+    if (int rc = dispatch_d_split<KIND>(prm, grid, (int)tiles_bound, (int)(max_n_pad / KC), st)) return rc;
     predict_finalize_kernel<KIND><<<(unsigned)((prm.P + 3) / 4), 128, 0, st>>>(prm, max_nq);
     return check_launch("predict_finalize_kernel");
 }
@@ -1019,3 +1145,15 @@ extern "C" int gpmdm_pf_propagate_lowlat_f64(const gpmdm_gp_model* dyn, const do
     prm.var_out = var_out;
     return run_split<1>(prm, max_n_pad, seg_chunks, workspace, (cudaStream_t)stream);
 }
+
+#ifdef GPMDM_TIMELINE
+// diagnostic build only: copies out and clears the per-item time stamps ([160][64][8] words, [160] counts)
+extern "C" int gpmdm_debug_timeline(unsigned long long* host_words, int* host_counts) {
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(host_words, gpmdm::g_timeline, sizeof(unsigned long long) * 160 * gpmdm::TL_ITEMS * gpmdm::TL_WORDS);
+    cudaMemcpyFromSymbol(host_counts, gpmdm::g_timeline_n, sizeof(int) * 160);
+    static int zeros[160];
+    cudaMemcpyToSymbol(gpmdm::g_timeline_n, zeros, sizeof(zeros));
+    return 0;
+}
+#endif

@@ -876,7 +876,7 @@ class GPMDM(torch.nn.Module):
         return buf
 
     def _lowlat_workspace(self, P, max_n_pad, dout):
-        need = int(_cabi.lib().gpmdm_predict_lowlat_workspace_bytes(P, max_n_pad, dout, 0)) // 8 + 1
+        need = int(_cabi.lib().gpmdm_predict_lowlat_workspace_bytes(P, max_n_pad, dout, 0, self.n_classes)) // 8 + 1
         return self._stream_scratch("lowlat", need, torch.float64)
 
     # ---- prediction (gpmdm.py:923-963, 1032-1068) ----------------------------------------------------------

@@ -178,8 +178,8 @@ class GPMDM_PF:
                                                                             int(self._tri)))
             self._seg_dyn = int(self._lib.gpmdm_predict_lowlat_pick_segment(max(tiles, min(C, P)), self._packed["dyn_max_n_pad"],
                                                                             _cabi.TILE_N, int(self._tri)))
-            need = max(int(self._lib.gpmdm_predict_lowlat_workspace_bytes(Pl, self._packed["obs_n_pad"], self.observation_dim, self._seg_obs)),
-                       int(self._lib.gpmdm_predict_lowlat_workspace_bytes(Pl, self._packed["dyn_max_n_pad"], d, self._seg_dyn)))
+            need = max(int(self._lib.gpmdm_predict_lowlat_workspace_bytes(Pl, self._packed["obs_n_pad"], self.observation_dim, self._seg_obs, 1)),
+                       int(self._lib.gpmdm_predict_lowlat_workspace_bytes(Pl, self._packed["dyn_max_n_pad"], d, self._seg_dyn, C)))
             self._ws_lowlat = torch.empty(need // 8 + 1, dtype=torch.float64, device=dev)
         # scratch is owned by the filter instance (two filters on one model may run on different streams)
         self._ws_kstar = None

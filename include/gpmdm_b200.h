@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define GPMDM_ABI_VERSION 3
+#define GPMDM_ABI_VERSION 4
 
 #define GPMDM_E_INVALID (-1)     /* bad size / null pointer / unsupported dimension            */
 #define GPMDM_E_UNSUPPORTED (-2) /* valid request outside this build's limits (d > 8, ...)      */
@@ -174,8 +174,12 @@ int gpmdm_pf_loglik_f64(const gpmdm_gp_model* obs, const double* x, int64_t P, c
  * max_n_pad: largest n_pad over the model's blocks.  seg_chunks: k-segment length in 16-row chunks, 0 = the default rule
  * (a function of max_n_pad only, so results do not depend on the batch); a caller that knows the whole cloud may pass
  * gpmdm_predict_lowlat_pick_segment(...) to fill the SMs in whole waves (results depend on the value only through the
- * summation order over k).  workspace: gpmdm_predict_lowlat_workspace_bytes(P, max_n_pad, dout, seg_chunks). */
-int64_t gpmdm_predict_lowlat_workspace_bytes(int64_t P, int64_t max_n_pad, int32_t dout, int32_t seg_chunks);
+ * summation order over k).  The cross-kernel K* of every particle tile is evaluated once, by a wide first kernel, into the
+ * workspace and shared by all the tile's work items; warps of a ragged tile whose 8 particle rows lie beyond its count issue
+ * no MMAs (100 particles cost 104 rows of work, not 128).
+ * workspace: gpmdm_predict_lowlat_workspace_bytes(P, max_n_pad, dout, seg_chunks, n_blocks of the model). */
+int64_t gpmdm_predict_lowlat_workspace_bytes(int64_t P, int64_t max_n_pad, int32_t dout, int32_t seg_chunks,
+                                             int32_t n_blocks);
 int32_t gpmdm_predict_lowlat_pick_segment(int64_t n_tiles, int64_t n_pad, int32_t alpha_ld, int32_t tri);
 int gpmdm_pf_observe_lowlat_f64(const gpmdm_gp_model* obs, const double* x, int64_t P, const double* z, double ll_const,
                                 const double* v_in, double* ll, double* mu_out, double* v_out, int64_t max_n_pad,

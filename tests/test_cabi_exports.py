@@ -29,7 +29,7 @@ def test_library_builds_and_exports_every_declared_symbol():
     handle = ctypes.CDLL(path)
     for name in declared_symbols():
         assert hasattr(handle, name), f"{name} declared in include/gpmdm_b200.h but not exported"
-    assert handle.gpmdm_abi_version() == 3
+    assert handle.gpmdm_abi_version() == 4
 
 
 def test_binding_table_matches_header():

@@ -68,8 +68,8 @@ def test_guard_bands_survive_every_predict_mode(small, P):
     check(lib.gpmdm_pf_propagate_f64(ctypes.byref(pk["dyn"]), ptr(xs), ptr(perm), ptr(tiles), ptr(n_tiles), P, ptr(eps),
                                      ptr(x_new), ptr(mean), ptr(var), ptr(counter), stream()), "propagate")
     seg = 0 if P % 2 else 5  # the default segmentation rule, and an explicit (short) segment length
-    ll_ws = G("lowlat_ws", max(int(lib.gpmdm_predict_lowlat_workspace_bytes(P, pk["dyn_max_n_pad"], d, seg)),
-                               int(lib.gpmdm_predict_lowlat_workspace_bytes(P, pk["obs_n_pad"], D, seg))) // 8)
+    ll_ws = G("lowlat_ws", max(int(lib.gpmdm_predict_lowlat_workspace_bytes(P, pk["dyn_max_n_pad"], d, seg, C)),
+                               int(lib.gpmdm_predict_lowlat_workspace_bytes(P, pk["obs_n_pad"], D, seg, 1))) // 8)
     x_new2 = G("x_new_lowlat", P * d)
     check(lib.gpmdm_pf_propagate_lowlat_f64(ctypes.byref(pk["dyn"]), ptr(xs), ptr(perm), ptr(tiles), ptr(n_tiles), P,
                                             ptr(eps), ptr(x_new2), None, None, pk["dyn_max_n_pad"], seg, ptr(counter), ptr(ll_ws),

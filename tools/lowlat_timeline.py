@@ -1,0 +1,114 @@
+"""Diagnostic: per-item timeline of the low-latency (split) instance of gp_predict_kernel at the reference's operating
+point (100 particles, N_train = 2 000 by default).
+
+  python tools/lowlat_timeline.py --build     (here: compiles csrc/gp_predict.cu with -DGPMDM_TIMELINE into
+                                               gpmdm_b200/lib/libgpmdm_sm100a_timeline.so; travels to the GPU box)
+  python tools/lowlat_timeline.py             (GPU: runs the observation launch a few times, prints one JSON line)
+
+Stamps (globaltimer, ns) per CTA and work item: loop top, item fetched, first chunk landed, k loop done, epilogue done."""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+LIB = os.path.join(ROOT, "gpmdm_b200", "lib", "libgpmdm_sm100a_timeline.so")
+
+
+def build():
+    from gpmdm_b200 import build as b
+
+    b.build()
+    obj = os.path.join(b.LIB_DIR, "gp_predict_timeline.o")
+    subprocess.check_call([b._nvcc(), *b.NVCC_FLAGS, "-DGPMDM_TIMELINE", "-I", b.INCLUDE, "-c",
+                           os.path.join(b.CSRC, "gp_predict.cu"), "-o", obj])
+    objs = [os.path.join(b.LIB_DIR, os.path.basename(s)[:-3] + ".o") for s in b.sources() if not s.endswith("gp_predict.cu")]
+    subprocess.check_call([b._nvcc(), "-shared", "-o", LIB, obj, *objs, "-gencode", "arch=compute_100a,code=sm_100a"])
+    print(LIB)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--build", action="store_true")
+    ap.add_argument("--classes", type=int, default=2)
+    ap.add_argument("--seqs-per-class", type=int, default=10)
+    ap.add_argument("--frames", type=int, default=100)
+    ap.add_argument("--particles", type=int, default=100)
+    ap.add_argument("--seg", type=int, default=-1, help="segment length in chunks (-1: the filter's own choice)")
+    o = ap.parse_args()
+    if o.build:
+        return build()
+    os.environ["GPMDM_LIBRARY"] = LIB
+    import numpy as np
+    import torch
+
+    import bench
+    from gpmdm_b200 import _cabi
+
+    a = argparse.Namespace(classes=o.classes, seqs_per_class=o.seqs_per_class, frames=o.frames, latent=3, obs_dim=62)
+    wl, X0, hp = bench.synthetic_inputs(a)
+    model = bench.build_product_model(a, wl, X0, hp)
+    lib = _cabi.lib()
+    lib.gpmdm_debug_timeline.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+    pk = model.packed_models()
+    P = o.particles
+    g = torch.Generator().manual_seed(1)
+    idx = torch.randint(0, X0.shape[0], (P,), generator=g)
+    xs = (torch.tensor(X0[idx.numpy()]) + 0.1 * torch.randn(P, 3, dtype=torch.float64, generator=g)).cuda().contiguous()
+    n_pad = pk["obs_n_pad"]
+    seg = o.seg if o.seg >= 0 else int(lib.gpmdm_predict_lowlat_pick_segment((P + 63) // 64, n_pad, 256, 1))
+    ws = torch.empty(int(lib.gpmdm_predict_lowlat_workspace_bytes(P, n_pad, 62, seg, 1)) // 8 + 1, dtype=torch.float64, device="cuda")
+    z = torch.tensor(wl.test_trials[0][1][0], dtype=torch.float64, device="cuda")
+    ll = torch.empty(P, dtype=torch.float64, device="cuda")
+    counter = torch.zeros(4, dtype=torch.int32, device="cuda")
+    words = np.zeros(160 * 64 * 8, dtype=np.uint64)
+    counts = np.zeros(160, dtype=np.int32)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    for it in range(5):
+        ev[0].record()
+        _cabi.check(lib.gpmdm_pf_observe_lowlat_f64(ctypes.byref(pk["obs"]), xs.data_ptr(), P, z.data_ptr(), 0.0, None,
+                                                    ll.data_ptr(), None, None, n_pad, seg, counter.data_ptr(), ws.data_ptr(),
+                                                    _cabi.stream()), "observe_lowlat")
+        ev[1].record()
+        torch.cuda.synchronize()
+        lib.gpmdm_debug_timeline(words.ctypes.data, counts.ctypes.data)
+    w = words.reshape(160, 64, 8).astype(np.int64)
+    ctas = [b for b in range(160) if counts[b] > 0]
+    t_enter = min(int(w[b, 0, 7]) for b in ctas)
+    rows = []
+    for b in ctas:
+        for i in range(min(int(counts[b]), 64)):
+            r = w[b, i]
+            if r[2] == 0:
+                rows.append(dict(cta=b, item=int(r[6]), empty=True, top=int(r[0] - t_enter), fetched=int(r[1] - t_enter)))
+            else:
+                rows.append(dict(cta=b, item=int(r[6]), empty=False, top=int(r[0] - t_enter), fetched=int(r[1] - t_enter),
+                                 first_chunk=int(r[2] - t_enter), loop_done=int(r[3] - t_enter), epi_done=int(r[4] - t_enter)))
+    real = [r for r in rows if not r["empty"]]
+    out = {
+        "workload": f"observation GP, low-latency items, N={X0.shape[0]} n_pad={n_pad} P={P} seg_chunks={seg}",
+        "launch_ms_events": ev[0].elapsed_time(ev[1]), "ctas": len(ctas), "items_real": len(real),
+        "items_empty": len(rows) - len(real),
+        "cta_enter_spread_ns": max(int(w[b, 0, 7]) for b in ctas) - t_enter,
+        "last_epilogue_done_ns": max(r["epi_done"] for r in real),
+        "last_loop_top_ns": max(r["top"] for r in rows),
+        "median": {k: float(np.median([r[k2] - r[k1] for r in real])) for k, k1, k2 in
+                   (("fetch_ns", "top", "fetched"), ("prologue_ns", "fetched", "first_chunk"),
+                    ("k_loop_ns", "first_chunk", "loop_done"), ("epilogue_ns", "loop_done", "epi_done"))},
+        "max": {k: float(np.max([r[k2] - r[k1] for r in real])) for k, k1, k2 in
+                (("fetch_ns", "top", "fetched"), ("prologue_ns", "fetched", "first_chunk"),
+                 ("k_loop_ns", "first_chunk", "loop_done"), ("epilogue_ns", "loop_done", "epi_done"))},
+        "empty_fetch_median_ns": float(np.median([r["fetched"] - r["top"] for r in rows if r["empty"]])) if len(rows) > len(real) else None,
+        "per_cta_items": sorted(((b, int(counts[b])) for b in ctas), key=lambda t: -t[1])[:8],
+        "slowest_ctas": sorted(({"cta": b, "done": max(r["epi_done"] for r in real if r["cta"] == b),
+                                 "items": [(r["item"], r["epi_done"] - r["fetched"]) for r in real if r["cta"] == b]}
+                                for b in set(r["cta"] for r in real)), key=lambda t: -t["done"])[:4],
+    }
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()
