@@ -31,6 +31,11 @@ class GpModelTf32(ctypes.Structure):
                 ("dout", _i32), ("lengthscales", _ptr), ("lambdas", _ptr)]
 
 
+class PfSmallIo(ctypes.Structure):
+    """struct gpmdm_pf_small_io"""
+    _fields_ = [("z_src", _ptr), ("summary_dst", _ptr), ("probs_dst", _ptr), ("frame", _ptr)]
+
+
 class PfStepArgs(ctypes.Structure):
     """struct gpmdm_pf_step_args"""
     _fields_ = [("dyn", ctypes.POINTER(GpModel)), ("obs", ctypes.POINTER(GpModel)),
@@ -80,7 +85,7 @@ _SIGNATURES = {
     "gpmdm_pf_step_local_f64": (ctypes.c_int, [ctypes.POINTER(PfStepArgs), _ptr]),
     "gpmdm_pf_step_global_f64": (ctypes.c_int, [ctypes.POINTER(PfStepArgs), _ptr]),
     "gpmdm_pf_small_max_particles": (_i32, []),
-    "gpmdm_pf_step_small_f64": (ctypes.c_int, [ctypes.POINTER(PfStepArgs), _ptr, _ptr, _ptr]),
+    "gpmdm_pf_step_small_f64": (ctypes.c_int, [ctypes.POINTER(PfStepArgs), _ptr, _ptr, ctypes.POINTER(PfSmallIo), _ptr]),
     "gpmdm_pf_normalize_f64": (ctypes.c_int, [_ptr, _i64, _ptr, _ptr, _ptr, _ptr, _ptr]),
     "gpmdm_pf_cdf_f64": (ctypes.c_int, [_ptr, _i64, _i32, _ptr, _ptr, _ptr]),
     "gpmdm_pf_resample_f64": (ctypes.c_int, [_ptr, _i64, _ptr, _i64, _ptr, _ptr, _i32, _ptr, _ptr, _ptr, _ptr]),

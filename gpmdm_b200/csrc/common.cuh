@@ -12,6 +12,16 @@ namespace gpmdm {
 void set_error(const char* fmt, ...);
 int check_launch(const char* what);
 
+// the low-latency predict launches (gp_predict.cu) for callers inside the library that issue a fixed launch sequence:
+// counters_zero = tile_counter[0..1] are already zero on the stream (every finalize kernel leaves them zeroed)
+int observe_lowlat_impl(const gpmdm_gp_model* obs, const double* x, int64_t P, const double* z, double ll_const,
+                        const double* v_in, double* ll, double* mu_out, double* v_out, int64_t max_n_pad, int32_t seg_chunks,
+                        int32_t* tile_counter, void* workspace, void* stream, bool counters_zero);
+int propagate_lowlat_impl(const gpmdm_gp_model* dyn, const double* x_prev, const int32_t* perm, const int32_t* tiles,
+                          const int32_t* n_tiles, int64_t P, const double* eps, double* x_new, double* mean_out,
+                          double* var_out, int64_t max_n_pad, int32_t seg_chunks, int32_t* tile_counter, void* workspace,
+                          void* stream, bool counters_zero);
+
 #define GPMDM_REQUIRE(cond, code, ...)      \
     do {                                    \
         if (!(cond)) {                      \

@@ -354,11 +354,29 @@ __global__ void __launch_bounds__(NTHREADS, 1) gp_predict_kernel(const PredictPa
         int ct_begin = ct0, ct_end = nct;
         int kfirst = -1, kend = nkc;  // k-chunk range of the work item (split mode: one segment of one column tile)
         if (prm.split) {
-            if (item_ct < ct0 || item_ct >= nct) continue;  // this block has fewer column tiles (uniform for the CTA)
+            // Every (tile, column tile, segment) item owns one slot of the partial-sum workspace for its tile's particles:
+            // qpart[ct][s] when ct indexes a column tile of the LARGEST block, mu_ws[s] when ct is one of this block's alpha
+            // tiles.  An item with nothing to compute (the block is smaller, or the segment starts beyond its rows) writes
+            // the zeros itself, so the workspace needs no memset between launches.
+            kfirst = ((prm.tri && item_ct < nq) ? item_ct * (TN / KC) : 0) + item_s * prm.seg_chunks;
+            const bool is_l = item_ct >= ct0 && item_ct < nq, is_a = item_ct >= nq && item_ct < nct;
+            const int max_nq = prm.max_nct - prm.alpha_ld / TN;
+            if (item_ct < max_nq && !(is_l && kfirst < nkc))
+                for (int m = tid; m < count; m += NTHREADS) {
+                    const int p = prm.perm ? prm.perm[first + m] : first + m;
+                    prm.qpart[((long long)item_ct * prm.nseg + item_s) * prm.P + p] = 0.0;
+                }
+            if (is_a && kfirst >= nkc) {
+                const int c0 = (item_ct - nq) * TN, c1 = min(prm.dout, c0 + TN);
+                for (int i = tid; i < count * (c1 - c0); i += NTHREADS) {
+                    const int m = i / (c1 - c0), col = c0 + i % (c1 - c0);
+                    const int p = prm.perm ? prm.perm[first + m] : first + m;
+                    prm.mu_ws[((long long)item_s * prm.P + p) * prm.dout + col] = 0.0;
+                }
+            }
+            if (!(is_l || is_a) || kfirst >= nkc) continue;  // uniform for the CTA
             ct_begin = item_ct;
             ct_end = item_ct + 1;
-            kfirst = ((prm.tri && item_ct < nq) ? item_ct * (TN / KC) : 0) + item_s * prm.seg_chunks;
-            if (kfirst >= nkc) continue;  // ... or fewer segments
             kend = min(kfirst + prm.seg_chunks, nkc);
         }
 
@@ -711,6 +729,9 @@ template <int KIND>
 __global__ void __launch_bounds__(128) predict_finalize_kernel(const PredictParams prm, int max_nq) {
     const long long p = (long long)blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
+    // the item kernel is done with the hand-out counter: leave it zeroed for the next low-latency launch of a fixed sequence
+    // (csrc/pf_small.cu issues the dynamics and the observation launch back to back without memset nodes in between)
+    if (blockIdx.x == 0 && threadIdx.x == 0) prm.counter[0] = 0, prm.counter[1] = 0;
     if (p >= prm.P) return;
     const int d = prm.d;
     // fixed order: lane l adds entries l, l + 32, ...; then a shuffle tree
@@ -1070,35 +1091,44 @@ extern "C" int32_t gpmdm_predict_lowlat_pick_segment(int64_t n_tiles, int64_t n_
     return best_seg;
 }
 
+// counters_zero: the caller guarantees tile_counter[0..1] == 0 on the stream (a previous finalize kernel, or its own kernel).
 template <int KIND>
-static int run_split(PredictParams& prm, int64_t max_n_pad, int32_t seg_chunks, void* workspace, cudaStream_t st) {
+static int run_split(PredictParams& prm, int64_t max_n_pad, int32_t seg_chunks, void* workspace, cudaStream_t st,
+                     bool counters_zero) {
     GPMDM_REQUIRE(workspace != nullptr && max_n_pad > 0 && max_n_pad % TN == 0, GPMDM_E_INVALID,
                   "low-latency mode needs a workspace and max_n_pad (multiple of %d)", TN);
     const int max_nq = (int)(max_n_pad / TN);
     prm.split = 1;
     prm.max_nct = max_nq + prm.alpha_ld / TN;
     choose_segments(max_n_pad, seg_chunks, prm.seg_chunks, prm.nseg);
+    // every slot of the partial-sum workspace is written by the item that owns it (zeros included): no memset
     prm.qpart = static_cast<double*>(workspace);
     prm.mu_ws = prm.qpart + (long long)max_nq * prm.nseg * prm.P;
-    // segments a (smaller) block does not have contribute zeros
-    cudaError_t e = cudaMemsetAsync(prm.qpart, 0, ((size_t)max_nq * prm.P + (size_t)prm.P * prm.dout) * prm.nseg * 8, st);
-    GPMDM_REQUIRE(e == cudaSuccess, (int)e, "cudaMemsetAsync: %s", cudaGetErrorString(e));
-    e = cudaMemsetAsync(prm.counter, 0, 2 * sizeof(int32_t), st);
-    GPMDM_REQUIRE(e == cudaSuccess, (int)e, "cudaMemsetAsync: %s", cudaGetErrorString(e));
+    if (!counters_zero) {
+        cudaError_t e = cudaMemsetAsync(prm.counter, 0, 2 * sizeof(int32_t), st);
+        GPMDM_REQUIRE(e == cudaSuccess, (int)e, "cudaMemsetAsync: %s", cudaGetErrorString(e));
+    }
     const long long tiles_bound = (prm.P + TM - 1) / TM + prm.n_blocks;
-    prm.kcache = prm.mu_ws + (long long)prm.nseg * prm.P * prm.dout;
-    prm.kcache_stride = (long long)max_n_pad * TM;  // the kernels trap if a block on the device is larger
     const long long items = tiles_bound * prm.max_nct * prm.nseg;
     const int grid = (int)(items < num_sms() ? items : num_sms());
-    if (int rc = dispatch_d_split<KIND>(prm, grid, (int)tiles_bound, (int)(max_n_pad / KC), st)) return rc;
+    // Shared K* slices (one more launch, ~10 us) pay once the launch has enough chunks per SM: a chunk costs ~2.38 us with
+    // them, ~2.55 us with the exponentials evaluated inside the k loop.  The A fragments are bit-identical either way.
+    const long long chunks_per_tile = (long long)max_nq * (max_n_pad / KC) / (prm.tri ? 2 : 1);
+    const bool shared_kstar = ((prm.P + TM - 1) / TM) * chunks_per_tile >= 128ll * num_sms();
+    if (shared_kstar) {
+        prm.kcache = prm.mu_ws + (long long)prm.nseg * prm.P * prm.dout;
+        prm.kcache_stride = (long long)max_n_pad * TM;  // the kernels trap if a block on the device is larger
+        if (int rc = dispatch_d_split<KIND>(prm, grid, (int)tiles_bound, (int)(max_n_pad / KC), st)) return rc;
+    } else {
+        if (int rc = dispatch_d<KIND>(prm, grid, st)) return rc;
+    }
     predict_finalize_kernel<KIND><<<(unsigned)((prm.P + 3) / 4), 128, 0, st>>>(prm, max_nq);
     return check_launch("predict_finalize_kernel");
 }
 
-extern "C" int gpmdm_pf_observe_lowlat_f64(const gpmdm_gp_model* obs, const double* x, int64_t P, const double* z,
-                                           double ll_const, const double* v_in, double* ll, double* mu_out,
-                                           double* v_out, int64_t max_n_pad, int32_t seg_chunks, int32_t* tile_counter,
-                                           void* workspace, void* stream) {
+int gpmdm::observe_lowlat_impl(const gpmdm_gp_model* obs, const double* x, int64_t P, const double* z, double ll_const,
+                               const double* v_in, double* ll, double* mu_out, double* v_out, int64_t max_n_pad,
+                               int32_t seg_chunks, int32_t* tile_counter, void* workspace, void* stream, bool counters_zero) {
     if (int rc = validate_model(obs, 0)) return rc;
     GPMDM_REQUIRE(P >= 0 && P < (1ll << 31), GPMDM_E_INVALID, "P = %lld out of range", (long long)P);
     if (P == 0) return 0;
@@ -1117,13 +1147,21 @@ extern "C" int gpmdm_pf_observe_lowlat_f64(const gpmdm_gp_model* obs, const doub
     prm.ll = ll;
     prm.mu_out = mu_out;
     prm.v_out = v_out;
-    return run_split<0>(prm, max_n_pad, seg_chunks, workspace, (cudaStream_t)stream);
+    return run_split<0>(prm, max_n_pad, seg_chunks, workspace, (cudaStream_t)stream, counters_zero);
 }
 
-extern "C" int gpmdm_pf_propagate_lowlat_f64(const gpmdm_gp_model* dyn, const double* x_prev, const int32_t* perm,
-                                             const int32_t* tiles, const int32_t* n_tiles, int64_t P, const double* eps,
-                                             double* x_new, double* mean_out, double* var_out, int64_t max_n_pad,
-                                             int32_t seg_chunks, int32_t* tile_counter, void* workspace, void* stream) {
+extern "C" int gpmdm_pf_observe_lowlat_f64(const gpmdm_gp_model* obs, const double* x, int64_t P, const double* z,
+                                           double ll_const, const double* v_in, double* ll, double* mu_out,
+                                           double* v_out, int64_t max_n_pad, int32_t seg_chunks, int32_t* tile_counter,
+                                           void* workspace, void* stream) {
+    return observe_lowlat_impl(obs, x, P, z, ll_const, v_in, ll, mu_out, v_out, max_n_pad, seg_chunks, tile_counter, workspace,
+                               stream, false);
+}
+
+int gpmdm::propagate_lowlat_impl(const gpmdm_gp_model* dyn, const double* x_prev, const int32_t* perm, const int32_t* tiles,
+                                 const int32_t* n_tiles, int64_t P, const double* eps, double* x_new, double* mean_out,
+                                 double* var_out, int64_t max_n_pad, int32_t seg_chunks, int32_t* tile_counter, void* workspace,
+                                 void* stream, bool counters_zero) {
     if (int rc = validate_model(dyn, 1)) return rc;
     GPMDM_REQUIRE(P >= 0 && P < (1ll << 31), GPMDM_E_INVALID, "P = %lld out of range", (long long)P);
     if (P == 0) return 0;
@@ -1143,7 +1181,15 @@ extern "C" int gpmdm_pf_propagate_lowlat_f64(const gpmdm_gp_model* dyn, const do
     prm.x_new = x_new;
     prm.mean_out = mean_out;
     prm.var_out = var_out;
-    return run_split<1>(prm, max_n_pad, seg_chunks, workspace, (cudaStream_t)stream);
+    return run_split<1>(prm, max_n_pad, seg_chunks, workspace, (cudaStream_t)stream, counters_zero);
+}
+
+extern "C" int gpmdm_pf_propagate_lowlat_f64(const gpmdm_gp_model* dyn, const double* x_prev, const int32_t* perm,
+                                             const int32_t* tiles, const int32_t* n_tiles, int64_t P, const double* eps,
+                                             double* x_new, double* mean_out, double* var_out, int64_t max_n_pad,
+                                             int32_t seg_chunks, int32_t* tile_counter, void* workspace, void* stream) {
+    return propagate_lowlat_impl(dyn, x_prev, perm, tiles, n_tiles, P, eps, x_new, mean_out, var_out, max_n_pad, seg_chunks,
+                                 tile_counter, workspace, stream, false);
 }
 
 #ifdef GPMDM_TIMELINE

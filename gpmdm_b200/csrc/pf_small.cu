@@ -28,6 +28,11 @@ struct SmallPreArgs {
     double *E, *eps, *u;
     int64_t* c_new;
     int32_t *perm, *tiles, *n_tiles;
+    int32_t* tile_counter;               // words [0..1] zeroed for the low-latency launches that follow
+    const double* z_src;                 // frames [*, D] (device or mapped host memory) or NULL
+    const unsigned long long* frame;     // device frame counter or NULL (= frame 0)
+    double* z;                           // [D] device: where the observation kernels read the frame
+    int D;
 };
 
 __global__ void __launch_bounds__(PRE_T, 1) small_pre_kernel(const SmallPreArgs a) {
@@ -37,6 +42,11 @@ __global__ void __launch_bounds__(PRE_T, 1) small_pre_kernel(const SmallPreArgs 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int P = a.P, C = a.C;
     const unsigned long long step = a.step_dev ? *a.step_dev : a.step;
+    if (a.z_src) {  // issued first: a read of mapped host memory is one PCIe round trip, hidden behind the rest
+        const double* src = a.z_src + (a.frame ? (long long)*a.frame : 0ll) * a.D;
+        for (int i = tid; i < a.D; i += PRE_T) a.z[i] = src[i];
+    }
+    if (tid < 2) a.tile_counter[tid] = 0;
     for (int i = tid; i < C * C; i += PRE_T) sT[i] = a.T[i];
     if (tid < 64) cnt[tid] = base[tid] = 0;
     if (a.generate)
@@ -125,6 +135,9 @@ struct SmallPostArgs {
     double* summary;        // [C + d + 1] or NULL
     double* ws;             // gpmdm_workspace_bytes(P, C)
     unsigned long long* step_dev;  // advanced by one when non-null
+    double* summary_dst;    // [*, C + d + 1] device or mapped host memory, row *frame; or NULL
+    double* probs_dst;      // [C] device or NULL
+    unsigned long long* frame;  // advanced by one when non-null
 };
 
 __global__ void __launch_bounds__(RT, 1) small_post_kernel(const SmallPostArgs a) {
@@ -235,7 +248,18 @@ __global__ void __launch_bounds__(RT, 1) small_post_kernel(const SmallPostArgs a
         for (int vb = 0; vb < nb; vb++)
             summaries_block_dev<false>(a.ll, a.lw, a.w, a.c_out, a.x_out, P, a.C, a.d, gm, part + (long long)vb * ncol, vb, wtot);
         summaries_final_dev<false>(part, nb, a.C, a.d, a.summary, sh, cls);
+        if (a.summary_dst || a.probs_dst) {
+            __syncthreads();  // a.summary was written by threads of this CTA
+            const unsigned long long f = a.frame ? *a.frame : 0ull;
+            for (int i = tid; i < ncol; i += RT) {
+                const double v = __ldcg(a.summary + i);
+                if (a.summary_dst) a.summary_dst[f * ncol + i] = v;
+                if (a.probs_dst && i < a.C) a.probs_dst[i] = v;
+            }
+        }
     }
+    __syncthreads();
+    if (a.frame && tid == 0) a.frame[0] += 1ull;
     if (a.step_dev && tid == 0) a.step_dev[0] += 1ull;
 }
 
@@ -251,8 +275,11 @@ using namespace gpmdm;
 
 extern "C" int32_t gpmdm_pf_small_max_particles(void) { return SMALL_P_MAX; }
 
-extern "C" int gpmdm_pf_step_small_f64(const gpmdm_pf_step_args* a, uint64_t* step_dev, double* summary, void* stream) {
+extern "C" int gpmdm_pf_step_small_f64(const gpmdm_pf_step_args* a, uint64_t* step_dev, double* summary,
+                                       const gpmdm_pf_small_io* io, void* stream) {
     GPMDM_REQUIRE(a && a->dyn && a->obs, GPMDM_E_INVALID, "null argument");
+    GPMDM_REQUIRE(!io || summary || !(io->summary_dst || io->probs_dst), GPMDM_E_INVALID,
+                  "summary_dst / probs_dst need the summary buffer");
     GPMDM_REQUIRE(a->P > 0 && a->P <= SMALL_P_MAX && a->lo == 0 && a->n_local == a->P, GPMDM_E_UNSUPPORTED,
                   "the small-cloud step handles 1..%d particles on one rank (P = %lld, local %lld)", SMALL_P_MAX,
                   (long long)a->P, (long long)a->n_local);
@@ -267,12 +294,17 @@ extern "C" int gpmdm_pf_step_small_f64(const gpmdm_pf_step_args* a, uint64_t* st
     pre.P = P, pre.C = a->C, pre.d = a->d, pre.generate = a->generate_draws, pre.systematic = a->systematic;
     pre.T = a->T, pre.c_prev = a->c_prev, pre.E = a->E, pre.eps = a->eps, pre.u = a->u, pre.c_new = a->c_new;
     pre.perm = a->perm, pre.tiles = a->tiles, pre.n_tiles = a->n_tiles;
+    pre.tile_counter = a->tile_counter;
+    pre.z_src = io ? io->z_src : nullptr;
+    pre.frame = io ? reinterpret_cast<const unsigned long long*>(io->frame) : nullptr;
+    pre.z = const_cast<double*>(a->z), pre.D = a->obs->dout;
     small_pre_kernel<<<1, PRE_T, (size_t)a->C * a->C * sizeof(double), st>>>(pre);
     GPMDM_TRY(check_launch("small_pre_kernel"));
-    GPMDM_TRY(gpmdm_pf_propagate_lowlat_f64(a->dyn, a->x_prev, a->perm, a->tiles, a->n_tiles, P, a->eps, a->x_new, nullptr,
-                                            nullptr, a->dyn_max_n_pad, a->dyn_seg_chunks, a->tile_counter, a->lowlat_workspace, stream));
-    GPMDM_TRY(gpmdm_pf_observe_lowlat_f64(a->obs, a->x_new, P, a->z, a->ll_const, nullptr, a->ll, nullptr, nullptr,
-                                          a->obs_n_pad, a->obs_seg_chunks, a->tile_counter, a->lowlat_workspace, stream));
+    // the hand-out counters are zeroed by the pre kernel and again by every finalize kernel: no memset nodes in between
+    GPMDM_TRY(propagate_lowlat_impl(a->dyn, a->x_prev, a->perm, a->tiles, a->n_tiles, P, a->eps, a->x_new, nullptr, nullptr,
+                                    a->dyn_max_n_pad, a->dyn_seg_chunks, a->tile_counter, a->lowlat_workspace, stream, true));
+    GPMDM_TRY(observe_lowlat_impl(a->obs, a->x_new, P, a->z, a->ll_const, nullptr, a->ll, nullptr, nullptr, a->obs_n_pad,
+                                  a->obs_seg_chunks, a->tile_counter, a->lowlat_workspace, stream, true));
     SmallPostArgs post{};
     post.P = P, post.C = a->C, post.d = a->d, post.cdf_mode = a->cdf_mode;
     post.ll = a->ll, post.u = a->u, post.x_new = a->x_new, post.c_new = a->c_new;
@@ -280,6 +312,9 @@ extern "C" int gpmdm_pf_step_small_f64(const gpmdm_pf_step_args* a, uint64_t* st
     post.x_out = a->x_out, post.c_out = a->c_out, post.summary = summary;
     post.ws = static_cast<double*>(a->workspace);
     post.step_dev = reinterpret_cast<unsigned long long*>(step_dev);
+    post.summary_dst = io ? io->summary_dst : nullptr;
+    post.probs_dst = io ? io->probs_dst : nullptr;
+    post.frame = io ? reinterpret_cast<unsigned long long*>(io->frame) : nullptr;
     small_post_kernel<<<1, RT, 0, st>>>(post);
     return check_launch("small_post_kernel");
 }

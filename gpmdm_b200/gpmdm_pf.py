@@ -254,10 +254,13 @@ class GPMDM_PF:
             raise ValueError("Z must be [T, D = %d]" % self.observation_dim)
         Z = Z.contiguous()
         T, C, d = Z.shape[0], self.num_classes, self.latent_dim
-        out = torch.empty(T, C + d + 1, dtype=torch.float64, device=self.device)
-        for t in range(T):
-            self._update(Z[t])
-            out[t].copy_(self._summaries())
+        if self._small and self._use_graph and getattr(self, "_profile_events", None) is None:
+            out = self._replay_many(Z)
+        else:
+            out = torch.empty(T, C + d + 1, dtype=torch.float64, device=self.device)
+            for t in range(T):
+                self._update(Z[t])
+                out[t].copy_(self._summaries())
         self._summary_host_step = -1
         probs = out[:, :C]
         return probs, torch.argmax(probs, dim=1), out[:, C:C + d].to(self.dtype)
@@ -416,13 +419,14 @@ class GPMDM_PF:
         self._step += 1
 
     # ---- small clouds: six kernels per step, replayed from a CUDA graph ------------------------------------------------
-    def _issue_small(self, par, generate, E, eps, u):
+    def _issue_small(self, par, generate, E, eps, u, io=None):
         a = self._step_args
         a.generate_draws, a.step, a.z = int(generate), self._step, ptr(self._z_buf)
         a.x_prev, a.c_prev, a.E, a.eps, a.u = ptr(self._S[par]), ptr(self._Cl[par]), ptr(E), ptr(eps), ptr(u)
         a.ll, a.lw, a.w = ptr(self._LL[par]), ptr(self._LW[par]), ptr(self._W[par])
         a.x_out, a.c_out = ptr(self._S[1 - par]), ptr(self._Cl[1 - par])
-        check(self._lib.gpmdm_pf_step_small_f64(ctypes.byref(a), ptr(self._step_dev), ptr(self._summary), stream()),
+        check(self._lib.gpmdm_pf_step_small_f64(ctypes.byref(a), ptr(self._step_dev), ptr(self._summary),
+                                                ctypes.byref(io) if io is not None else None, stream()),
               "gpmdm_pf_step_small_f64")
 
     def _update_small(self, z, generate, E, eps, u):
@@ -440,7 +444,9 @@ class GPMDM_PF:
         self._finish_small(par)
 
     def _replay_small(self, z):
-        """One frame = one graph launch: [H2D z] -> pre -> dynamics GP -> observation GP -> post -> [D2H summaries]."""
+        """One frame = one graph launch of six kernel nodes: pre (reads z through the mapping of the pinned host buffer) ->
+        dynamics GP (items, finalise) -> observation GP (items, finalise) -> post (writes the summaries into the pinned
+        host buffer and the class posterior into its device buffer).  No copy or memset nodes."""
         par = self._par
         if self._particle_states.data_ptr() != self._S[par].data_ptr():
             self._S[par].copy_(self._particle_states)
@@ -454,17 +460,53 @@ class GPMDM_PF:
         self._graph_done.synchronize()  # the previous replay has consumed / produced the pinned buffers
         np.copyto(self._z_graph_np, src, casting="same_kind")
         if self._graphs[par] is None:  # every kernel has run at least once (function attributes are set): capture
+            io = _cabi.PfSmallIo(z_src=self._z_graph_pin.data_ptr(), summary_dst=self._summary_pin.data_ptr(),
+                                 probs_dst=ptr(self._probs[par]), frame=None)
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
-                self._z_buf.copy_(self._z_graph_pin, non_blocking=True)
-                self._issue_small(par, True, self._E, self._eps, self._u)
-                self._summary_pin.copy_(self._summary, non_blocking=True)
-                self._probs[par].copy_(self._summary[:self.num_classes])
+                self._issue_small(par, True, self._E, self._eps, self._u, io)
             self._graphs[par] = g
         self._graphs[par].replay()
         self._graph_done.record()
         self._finish_small(par)
         self._summary_host_step, self._probs_par = self._step, par
+
+    def _replay_many(self, Z):
+        """update_many for a small cloud: the frames sit in a persistent device buffer, a device frame counter selects the
+        row the pre kernel reads and the row of the output the post kernel writes, and the T steps are T replays of the
+        same six-kernel graph (one per buffer parity) with no host synchronisation in between."""
+        T, ncol = Z.shape[0], self.num_classes + self.latent_dim + 1
+        if getattr(self, "_many_cap", 0) < T:  # (re)allocate the frame / output buffers; graphs hold their addresses
+            self._many_cap = max(T, 256)
+            self._many_z = torch.empty(self._many_cap, self.observation_dim, dtype=torch.float64, device=self.device)
+            self._many_out = torch.empty(self._many_cap, ncol, dtype=torch.float64, device=self.device)
+            self._many_frame = torch.zeros(1, dtype=torch.int64, device=self.device)
+            self._many_graphs = [None, None]
+        self._many_z[:T].copy_(Z)
+        self._many_frame.zero_()
+        for t in range(T):
+            par = self._par
+            if self._small_steps < 2:  # every kernel has to have run once outside a capture
+                self._update(self._many_z[t])
+                self._many_out[t].copy_(self._summaries())
+                self._many_frame.add_(1)
+                continue
+            if self._particle_states.data_ptr() != self._S[par].data_ptr():
+                self._S[par].copy_(self._particle_states)
+            if self._particle_classes.data_ptr() != self._Cl[par].data_ptr():
+                self._Cl[par].copy_(self._particle_classes)
+            if self._step_dev_host != self._step:
+                self._step_dev.fill_(self._step)
+            if self._many_graphs[par] is None:
+                io = _cabi.PfSmallIo(z_src=ptr(self._many_z), summary_dst=ptr(self._many_out), probs_dst=None,
+                                     frame=ptr(self._many_frame))
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._issue_small(par, True, self._E, self._eps, self._u, io)
+                self._many_graphs[par] = g
+            self._many_graphs[par].replay()
+            self._finish_small(par)
+        return self._many_out[:T].clone()
 
     def _finish_small(self, par):
         self._small_steps += 1

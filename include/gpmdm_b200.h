@@ -370,9 +370,24 @@ int gpmdm_pf_step_global_f64(const gpmdm_pf_step_args* a, void* stream);
  *   step_dev  device uint64 (may be NULL): when given, the Philox step key is read from it instead of a->step and it is
  *             advanced by one at the end of the step, so the launch sequence has no per-step host parameter and can be
  *             captured once into a CUDA graph and replayed per frame (gpmdm_b200/gpmdm_pf.py does).
- *   summary   device [C + d + 1] (may be NULL): the outputs of gpmdm_pf_summaries_f64 for the post-step state. */
+ *   summary   device [C + d + 1] (may be NULL): the outputs of gpmdm_pf_summaries_f64 for the post-step state.
+ *   io        (may be NULL) observation source / result destinations handled INSIDE the step's first and last kernel, so
+ *             that a frame is six kernel nodes and nothing else (no memset, no copy nodes):
+ *               z_src        frames [*, D], device memory or page-locked host memory (read through the mapping): frame
+ *                            number *frame (0 if frame is NULL) is copied into a->z by the first kernel
+ *               summary_dst  [*, C + d + 1], device or page-locked host memory: row *frame receives the summary
+ *               probs_dst    device [C]: copy of the class posterior
+ *               frame        device uint64 frame counter, advanced by one at the end of the step
+ *             (summary must be non-NULL when summary_dst or probs_dst is given). */
+typedef struct gpmdm_pf_small_io {
+    const double* z_src;
+    double* summary_dst;
+    double* probs_dst;
+    uint64_t* frame;
+} gpmdm_pf_small_io;
 int32_t gpmdm_pf_small_max_particles(void);
-int gpmdm_pf_step_small_f64(const gpmdm_pf_step_args* a, uint64_t* step_dev, double* summary, void* stream);
+int gpmdm_pf_step_small_f64(const gpmdm_pf_step_args* a, uint64_t* step_dev, double* summary, const gpmdm_pf_small_io* io,
+                            void* stream);
 
 /* ---- training-side kernel matrices (gpmdm.py:381-548, 311-340, 550-628) ------------------------
  * K = exp(-|(x_i-x_j)/l|^2) [+ [x_i,1]diag(c^2)[x_j,1]^T if kind 1] [+ noise2 on the diagonal],

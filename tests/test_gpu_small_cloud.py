@@ -103,7 +103,9 @@ def test_update_many_equals_frame_by_frame_updates(setup, P):
     T = synthetic.markov_matrix(spec.n_classes)
     trial = np.concatenate([wl.test_trials[0][1], wl.test_trials[1][1]], 0)
     a, b = GPMDM_PF(model, T, P, seed=4), GPMDM_PF(model, T, P, seed=4)
-    probs, cls, means = a.update_many(trial)
+    k = 7  # two calls: the second one reuses the captured graphs and the frame buffers of the first
+    parts = [a.update_many(trial[:k]), a.update_many(trial[k:])]
+    probs, cls, means = (torch.cat([p[i] for p in parts]) for i in range(3))
     for t, z in enumerate(trial):
         b.update(z)
         assert torch.equal(b.class_probabilities(), probs[t]) and b.get_most_likely_class() == int(cls[t])

@@ -30,6 +30,41 @@ def build():
     print(LIB)
 
 
+def fused(o, lib, pk, model, X0, wl):
+    import numpy as np
+    import torch
+
+    from gpmdm_b200 import _cabi
+
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    P = 64 * sms
+    g = torch.Generator().manual_seed(1)
+    idx = torch.randint(0, X0.shape[0], (P,), generator=g)
+    xs = (torch.tensor(X0[idx.numpy()]) + 0.1 * torch.randn(P, 3, dtype=torch.float64, generator=g)).cuda().contiguous()
+    n_pad = pk["obs_n_pad"]
+    kws = torch.empty(sms * n_pad * 64, dtype=torch.float64, device="cuda")
+    z = torch.tensor(wl.test_trials[0][1][0], dtype=torch.float64, device="cuda")
+    ll = torch.empty(P, dtype=torch.float64, device="cuda")
+    counter = torch.zeros(4, dtype=torch.int32, device="cuda")
+    words = np.zeros(160 * 64 * 8, dtype=np.uint64)
+    counts = np.zeros(160, dtype=np.int32)
+    for it in range(3):
+        _cabi.check(lib.gpmdm_pf_observe_cached_f64(ctypes.byref(pk["obs"]), xs.data_ptr(), P, z.data_ptr(), 0.0, ll.data_ptr(),
+                                                    None, None, n_pad, counter.data_ptr(), kws.data_ptr(), kws.numel() * 8,
+                                                    _cabi.stream()), "observe_cached")
+        torch.cuda.synchronize()
+        lib.gpmdm_debug_timeline(words.ctypes.data, counts.ctypes.data)
+    clk = subprocess.run(["nvidia-smi", "--query-gpu=clocks.sm", "--format=csv,noheader,nounits"], capture_output=True, text=True).stdout.strip()
+    w = words.reshape(160, 64, 8).astype(np.int64)
+    N = X0.shape[0]
+    nkc, nq = (N + 15) // 16, n_pad // 256
+    chunks = sum(nkc - 16 * J for J in range(nq) if nkc > 16 * J)
+    tile_ns = [int(w[b, 0, 4] - w[b, 0, 2]) for b in range(sms) if counts[b] > 0 and w[b, 0, 2] > 0]
+    print(json.dumps({"workload": f"observation GP, fused cached launch, N={N} n_pad={n_pad} P={P} (one tile per SM)",
+                      "tile_ns_median": float(np.median(tile_ns)), "chunks_of_L_per_tile": chunks,
+                      "ns_per_chunk_incl_cache_fill_and_alpha_tile": float(np.median(tile_ns)) / chunks, "sm_clock_mhz_after": clk}))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--build", action="store_true")
@@ -38,6 +73,7 @@ def main():
     ap.add_argument("--frames", type=int, default=100)
     ap.add_argument("--particles", type=int, default=100)
     ap.add_argument("--seg", type=int, default=-1, help="segment length in chunks (-1: the filter's own choice)")
+    ap.add_argument("--fused", action="store_true", help="time the fused cached launch on 148 full tiles instead")
     o = ap.parse_args()
     if o.build:
         return build()
@@ -55,6 +91,8 @@ def main():
     lib.gpmdm_debug_timeline.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
     pk = model.packed_models()
     P = o.particles
+    if o.fused:
+        return fused(o, lib, pk, model, X0, wl)
     g = torch.Generator().manual_seed(1)
     idx = torch.randint(0, X0.shape[0], (P,), generator=g)
     xs = (torch.tensor(X0[idx.numpy()]) + 0.1 * torch.randn(P, 3, dtype=torch.float64, generator=g)).cuda().contiguous()
@@ -88,7 +126,9 @@ def main():
                 rows.append(dict(cta=b, item=int(r[6]), empty=False, top=int(r[0] - t_enter), fetched=int(r[1] - t_enter),
                                  first_chunk=int(r[2] - t_enter), loop_done=int(r[3] - t_enter), epi_done=int(r[4] - t_enter)))
     real = [r for r in rows if not r["empty"]]
+    clk = subprocess.run(["nvidia-smi", "--query-gpu=clocks.sm", "--format=csv,noheader,nounits"], capture_output=True, text=True).stdout.strip()
     out = {
+        "sm_clock_mhz_after": clk,
         "workload": f"observation GP, low-latency items, N={X0.shape[0]} n_pad={n_pad} P={P} seg_chunks={seg}",
         "launch_ms_events": ev[0].elapsed_time(ev[1]), "ctas": len(ctas), "items_real": len(real),
         "items_empty": len(rows) - len(real),
