@@ -12,6 +12,7 @@ import torch
 
 from . import build as _build
 
+ABI_VERSION = 4  # GPMDM_ABI_VERSION of include/gpmdm_b200.h this binding was written against
 _i32, _i64, _u64, _f64, _ptr = ctypes.c_int32, ctypes.c_int64, ctypes.c_uint64, ctypes.c_double, ctypes.c_void_p
 
 TILE_P = 64    # GPMDM_TILE_P: particles per predict tile
@@ -134,7 +135,7 @@ def lib() -> ctypes.CDLL:
         for name, (res, args) in _SIGNATURES.items():
             fn = getattr(handle, name)  # AttributeError if the build is stale
             fn.restype, fn.argtypes = res, args
-        if handle.gpmdm_abi_version() != 4:
+        if handle.gpmdm_abi_version() != ABI_VERSION:
             raise RuntimeError("libgpmdm_sm100a.so ABI version mismatch; rebuild")
         _lib = handle
     return _lib

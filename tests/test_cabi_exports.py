@@ -29,7 +29,8 @@ def test_library_builds_and_exports_every_declared_symbol():
     handle = ctypes.CDLL(path)
     for name in declared_symbols():
         assert hasattr(handle, name), f"{name} declared in include/gpmdm_b200.h but not exported"
-    assert handle.gpmdm_abi_version() == 4
+    assert handle.gpmdm_abi_version() == _cabi.ABI_VERSION
+    assert "#define GPMDM_ABI_VERSION %d" % _cabi.ABI_VERSION in open(os.path.join(ROOT, "include", "gpmdm_b200.h")).read()
 
 
 def test_binding_table_matches_header():
