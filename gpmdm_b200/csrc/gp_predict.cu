@@ -40,6 +40,8 @@
 //     block sizes balance across SMs.  Row results do not depend on tile assignment.
 #include <math.h>
 
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "fast_exp.cuh"
 
@@ -1114,7 +1116,9 @@ static int run_split(PredictParams& prm, int64_t max_n_pad, int32_t seg_chunks, 
     // Shared K* slices (one more launch, ~10 us) pay once the launch has enough chunks per SM: a chunk costs ~2.38 us with
     // them, ~2.55 us with the exponentials evaluated inside the k loop.  The A fragments are bit-identical either way.
     const long long chunks_per_tile = (long long)max_nq * (max_n_pad / KC) / (prm.tri ? 2 : 1);
-    const bool shared_kstar = ((prm.P + TM - 1) / TM) * chunks_per_tile >= 128ll * num_sms();
+    bool shared_kstar = ((prm.P + TM - 1) / TM) * chunks_per_tile >= 128ll * num_sms();
+    if (const char* force = getenv("GPMDM_LOWLAT_KSTAR"))  // tests: "shared" / "inline" force either instantiation
+        shared_kstar = force[0] == 's' ? true : (force[0] == 'i' ? false : shared_kstar);
     if (shared_kstar) {
         prm.kcache = prm.mu_ws + (long long)prm.nseg * prm.P * prm.dout;
         prm.kcache_stride = (long long)max_n_pad * TM;  // the kernels trap if a block on the device is larger

@@ -42,7 +42,7 @@ def small():
 
 
 @pytest.mark.parametrize("P", [1, 63, 65, 130, 1000, 9500])
-def test_guard_bands_survive_every_predict_mode(small, P):
+def test_guard_bands_survive_every_predict_mode(small, P, monkeypatch):
     spec, wl, model = small
     lib = _cabi.lib()
     pk = model.packed_models()
@@ -70,10 +70,15 @@ def test_guard_bands_survive_every_predict_mode(small, P):
     seg = 0 if P % 2 else 5  # the default segmentation rule, and an explicit (short) segment length
     ll_ws = G("lowlat_ws", max(int(lib.gpmdm_predict_lowlat_workspace_bytes(P, pk["dyn_max_n_pad"], d, seg, C)),
                                int(lib.gpmdm_predict_lowlat_workspace_bytes(P, pk["obs_n_pad"], D, seg, 1))) // 8)
-    x_new2 = G("x_new_lowlat", P * d)
-    check(lib.gpmdm_pf_propagate_lowlat_f64(ctypes.byref(pk["dyn"]), ptr(xs), ptr(perm), ptr(tiles), ptr(n_tiles), P,
-                                            ptr(eps), ptr(x_new2), None, None, pk["dyn_max_n_pad"], seg, ptr(counter), ptr(ll_ws),
-                                            stream()), "propagate lowlat")
+    # low latency, with the K* evaluated inside the work items and with the shared per-tile slices: bit-identical
+    x_new2, x_new3 = G("x_new_lowlat", P * d), G("x_new_lowlat_shared", P * d)
+    for mode, out in (("inline", x_new2), ("shared", x_new3)):
+        monkeypatch.setenv("GPMDM_LOWLAT_KSTAR", mode)
+        ll_ws.fill_(float("nan"))  # the workspace is never memset: every slot a finalize kernel reads must have been written
+        check(lib.gpmdm_pf_propagate_lowlat_f64(ctypes.byref(pk["dyn"]), ptr(xs), ptr(perm), ptr(tiles), ptr(n_tiles), P,
+                                                ptr(eps), ptr(out), None, None, pk["dyn_max_n_pad"], seg, ptr(counter), ptr(ll_ws),
+                                                stream()), "propagate lowlat " + mode)
+    assert torch.equal(x_new2, x_new3) and bool(torch.isfinite(x_new2).all())
     # observation: fused, cached, low latency
     outs = []
     for mode in ("fused", "cached", "lowlat"):
@@ -88,8 +93,15 @@ def test_guard_bands_survive_every_predict_mode(small, P):
             check(lib.gpmdm_pf_observe_cached_f64(ctypes.byref(pk["obs"]), ptr(xs), P, ptr(z), 0.5, ptr(ll), ptr(mu), ptr(v),
                                                   pk["obs_n_pad"], ptr(counter), ptr(kws), kws.numel() * 8, stream()), mode)
         else:
-            check(lib.gpmdm_pf_observe_lowlat_f64(ctypes.byref(pk["obs"]), ptr(xs), P, ptr(z), 0.5, None, ptr(ll), ptr(mu),
-                                                  ptr(v), pk["obs_n_pad"], seg, ptr(counter), ptr(ll_ws), stream()), mode)
+            res = []
+            for kmode in ("inline", "shared"):
+                monkeypatch.setenv("GPMDM_LOWLAT_KSTAR", kmode)
+                ll_ws.fill_(float("nan"))
+                check(lib.gpmdm_pf_observe_lowlat_f64(ctypes.byref(pk["obs"]), ptr(xs), P, ptr(z), 0.5, None, ptr(ll), ptr(mu),
+                                                      ptr(v), pk["obs_n_pad"], seg, ptr(counter), ptr(ll_ws), stream()), mode)
+                res.append((ll.clone(), mu.clone(), v.clone()))
+            monkeypatch.delenv("GPMDM_LOWLAT_KSTAR")
+            assert all(torch.equal(a, b) for a, b in zip(*res)) and bool(torch.isfinite(res[0][0]).all())
         outs.append((ll.clone(), mu.clone(), v.clone()))
     # stages
     lw, w, cdf, stats = G("lw", P), G("w", P), G("cdf", P), G("stats", 2)
