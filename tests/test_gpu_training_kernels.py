@@ -21,7 +21,7 @@ def small():
 
 def test_y_kernel_build_matches_reference_expression(small):
     spec, wl, model = small
-    K = model.get_y_kernel(model.X, model.X).cpu()
+    K = model.get_y_kernel(model.X, model.X).detach().cpu()
     K_o = orc.y_kernel(spec, spec.X, spec.X)
     assert float(torch.max(torch.abs(K - K_o))) < 1e-12
     K2 = model.get_y_kernel(model.X, model.X, flg_noise=False).cpu()
