@@ -444,6 +444,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gp_predict_kernel(const PredictPa
 #pragma unroll
                 for (int i = 0; i < KC / 4; i++) __stcg(kc + (long long)k * KCHUNK + i * 32, g[i]);
             }
+            __syncwarp();  // the Hadamard epilogue reads slots written by the other lanes of this warp
         }
 
         // ---- A fragments of the first chunk: a[k4] = K*[row 8 w + r][k = 4 k4 + c] -----------------------------
@@ -472,7 +473,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gp_predict_kernel(const PredictPa
             // The Hadamard epilogue of a tile of L re-reads the tile's 256 training records from global memory, 64
             // dependent iterations per lane: request them into L1 now (it is otherwise idle: B arrives by TMA, K* by
             // ld.cg), so that the epilogue does not pay 64 L2 round trips (~30 us per column tile).
-            if (ct < nq) {
+            if (ct < nq && !CACHE) {
                 const char* recs = reinterpret_cast<const char*>(gbk.coords + (long long)ct * TN * REC);
                 for (int off = tid * 128; off < TN * REC * 8; off += NTHREADS * 128)
                     asm volatile("prefetch.global.L1 [%0];" ::"l"(recs + off));
@@ -567,9 +568,27 @@ __global__ void __launch_bounds__(NTHREADS, 1) gp_predict_kernel(const PredictPa
             if (!active) {
                 // nothing to finish for this warp
             } else if (ct < nq) {
-                // q[p] += sum_n C[p,n] * K*[p,n] over this tile's columns (K* regenerated per element)
+                // q[p] += sum_n C[p,n] * K*[p,n] over this tile's columns
+                if (CACHE) {
+                    // K*[row][n] sits in the slices: column n = 16 kk + 4 k4 + c' was written (as an A fragment) by lane
+                    // 4 r + c' of this warp -- this lane's columns 8 j + 2 c + {0, 1} are two adjacent doubles.  Same
+                    // function, same inputs as kstar_pair below: the bits are the same, the 64 exponentials per lane and
+                    // column tile are not spent.  Columns in k-chunks beyond the block's rows (never filled) multiply
+                    // accumulators that are exactly zero: skipped.
+                    const double* kb = kc - lane + (long long)(ct * (TN / KC)) * KCHUNK + r * 4 + 2 * (c & 1) + (c >> 1) * 32;
+                    const int jmax = 2 * (nkc - ct * (TN / KC));
 #pragma unroll
-                for (int j = 0; j < NJ; j++) {  // fully unrolled: acc[][] must stay in registers
+                    for (int j = 0; j < NJ; j++) {  // fully unrolled: acc[][] must stay in registers
+                        if (j < jmax) {
+                            const double* q = kb + (long long)(j >> 1) * KCHUNK + (j & 1) * 64;
+                            const double k0 = __ldcg(q), k1 = __ldcg(q + 1);
+                            qacc = fma(acc[j][0], k0, qacc);
+                            qacc = fma(acc[j][1], k1, qacc);
+                        }
+                    }
+                } else
+#pragma unroll
+                for (int j = 0; j < NJ; j++) {  // fully unrolled: acc[][] must stay in registers (K* regenerated per element)
                     const int n = ct * TN + j * 8 + c * 2;
                     double rec0[REC_MAX], rec1[REC_MAX];
                     load_record<KIND, DL>(gbk.coords + (long long)n * REC, rec0);
