@@ -47,7 +47,16 @@ def build_reference_model(ref, C, d, D, seqs_per_class, frames, sigma_n, adam_st
     return model, wl
 
 
-def run_case(name, cfg):
+# The reference's own operating point (notebooks/test_gpmdm_pf.ipynb: 100 particles; BASELINE configs[0] shape) at
+# N_train = 2 000.  Compact fixture: the reference's inputs and stage outputs only -- no inverses (32 MB) and no Y (regenerated
+# from the seeded generator, pinned by its sha256) -- so the CUDA path is compared with the reference directly, using its
+# own factors.
+SCALE_CASES = {
+    "scale_cfg1_n2000_p100": (2, 3, 62, 10, 100, 100, 3, 1e-1, 0, 21),
+}
+
+
+def run_case(name, cfg, compact=False):
     C, d, D, spc, frames, P, steps, sigma_n, adam_steps, seed = cfg
     ref = ref_shim.load_reference()
     import gpmdm.gpmdm_pf as ref_pf_module  # the reference module (resolved via ref_shim's sys.path)
@@ -62,10 +71,17 @@ def run_case(name, cfg):
         for k in ("y_log_lengthscales", "y_log_lambdas", "y_log_sigma_n", "x_log_lengthscales",
                   "x_log_lambdas", "x_log_sigma_n", "x_log_lin_coeff"):
             out[k] = getattr(model, k).detach().numpy().copy()
-        out["Ky_inv"] = model.Ky_inv.detach().numpy().copy()
+        if compact:
+            import hashlib
+
+            out["Y_sha256"] = np.frombuffer(hashlib.sha256(np.ascontiguousarray(out["Y"]).tobytes()).digest(), dtype=np.uint8)
+            out["gen_cfg"] = np.array([C, D, spc, frames, seed])  # synthetic.make_sequences(C, D, spc, frames, seed=seed, 1, 8)
+            del out["Y"]
+        else:
+            out["Ky_inv"] = model.Ky_inv.detach().numpy().copy()
         # diagonal blocks of the reference's dense per-class inverses (+ check the off-block claim)
         s = 0
-        for c in range(C):
+        for c in range(0 if compact else C):
             n = sum(len(q) - 1 for q in model.class_aware_observations_list[c])
             full = model.Kx_inv_class[c].detach()
             out[f"Kx_inv_block_{c}"] = full[s:s + n, s:s + n].numpy().copy()
@@ -144,6 +160,8 @@ def main():
     torch.set_num_threads(8)
     for name, cfg in CASES.items():
         run_case(name, cfg)
+    for name, cfg in SCALE_CASES.items():
+        run_case(name, cfg, compact=True)
 
 
 if __name__ == "__main__":

@@ -265,3 +265,63 @@ def test_achieved_errors_report(case):
     if os.path.isdir("gpurun_out"):
         with open("gpurun_out/parity_achieved.jsonl", "a") as fh:
             fh.write(json.dumps(rec) + "\n")
+
+
+def test_cfg1_scale_filter_against_the_reference_directly():
+    """The reference's own operating point (100 particles) at N_train = 2 000: the CUDA filter with the factors the PRODUCT
+    computes itself (Cholesky -> triangular inverse -> packed panels) against the stage outputs the unmodified reference
+    recorded (tests/golden/scale_cfg1_n2000_p100.npz: no inverses in the fixture, nothing goes through the oracle's
+    arithmetic).  Stage-wise, every step started from the reference's state: classes and ancestors exact; means,
+    variances, log-likelihoods at the tolerance two different factorisations of K (cond ~ 1e6) allow."""
+    import json
+    import os
+
+    from gpmdm_b200 import GPMDM_PF
+    from oracle import gpmdm_oracle as orc
+
+    g = Golden("scale_cfg1_n2000_p100")
+    model = product_model_from_spec(g.spec)
+    lam_y = torch.exp(g.spec.y_log_lambdas) ** -2
+    lam_x = torch.exp(g.spec.x_log_lambdas) ** -2
+    rec = {"fixture": g.name, "N": int(g.spec.N), "P": int(g.P), "factors": "the product's own"}
+    worst = {k: 0.0 for k in ("mu", "v", "dyn_mean", "dyn_var", "ll_v>1e-3", "x_new")}
+    for low_latency, graph in ((True, False), (False, False)):
+        pf = GPMDM_PF(model, g.T, g.P, init_indices=g.init_idx, cdf_order="sequential", low_latency=low_latency, cuda_graph=graph)
+        assert torch.equal(pf._particle_states.cpu(), t64(g.z["init_states"]))
+        for t in range(g.steps):
+            s = g.step(t)
+            pf.update(s["z"], draws=(s["E"], s["eps"], s["u"]))
+            assert torch.equal(pf.last_pre_resample_classes.cpu(), torch.as_tensor(s["c_new"]))
+            x_ref = t64(s["eps"]) * t64(s["dyn_std"]) + t64(s["dyn_mean"])
+            worst["x_new"] = max(worst["x_new"], float(torch.max(torch.abs(pf.last_pre_resample_states.cpu() - x_ref))))
+            # the two GPs on the reference's own inputs
+            x_prev = t64(g.z["init_states"]) if t == 0 else t64(g.step(t - 1)["states_post"])
+            c_new = torch.as_tensor(s["c_new"])
+            for c in range(g.C):
+                rows = torch.nonzero(c_new == c).squeeze(-1)
+                if rows.numel() == 0:
+                    continue
+                mean, var = model.map_x_dynamics_for_class(x_prev[rows].cuda(), c, low_latency=low_latency)
+                ref_mean, ref_var = t64(s["dyn_mean"])[rows], t64(s["dyn_std"])[rows] ** 2
+                sc = torch.clamp(torch.abs(ref_mean).max(dim=1, keepdim=True).values, min=1e-3)
+                prior = orc.x_diag_kernel(g.spec, x_prev[rows]).unsqueeze(1) * lam_x.unsqueeze(0)
+                worst["dyn_mean"] = max(worst["dyn_mean"], scaled_err(mean.cpu(), ref_mean, sc))
+                worst["dyn_var"] = max(worst["dyn_var"], scaled_err(var.cpu(), ref_var, prior))
+            mu, var = model.map_x_to_y(x_ref.cuda(), low_latency=low_latency)
+            sc = torch.clamp(torch.abs(t64(s["mu"])).max(dim=1, keepdim=True).values, min=1e-3)
+            worst["mu"] = max(worst["mu"], scaled_err(mu.cpu(), s["mu"], sc))
+            worst["v"] = max(worst["v"], scaled_err(var.cpu(), s["var"], lam_y.unsqueeze(0).expand(var.shape)))
+            # log-likelihoods of the filter step on ITS states (x' differs from the reference's by worst["x_new"])
+            v_ref = t64(s["var"])[:, 0] / lam_y[0]
+            ok = v_ref > 1e-3
+            worst["ll_v>1e-3"] = max(worst["ll_v>1e-3"], rel_err(pf._log_likelihoods.cpu()[ok], t64(s["ll"])[ok]))
+            assert pf.get_most_likely_class() == int(s["argmax"])
+            assert torch.equal(pf.last_ancestors.cpu(), torch.as_tensor(s["anc"]))
+            pf._particle_states = dev(s["states_post"])
+            pf._particle_classes = dev(s["classes_post"], torch.int64)
+    rec.update(worst)
+    if os.path.isdir("gpurun_out"):
+        with open("gpurun_out/parity_achieved.jsonl", "a") as fh:
+            fh.write(json.dumps(rec) + "\n")
+    assert worst["mu"] < 1e-7 and worst["v"] < 1e-7 and worst["dyn_mean"] < 1e-7 and worst["dyn_var"] < 1e-7, worst
+    assert worst["x_new"] < 1e-6 and worst["ll_v>1e-3"] < 1e-4, worst

@@ -115,3 +115,38 @@ def test_c32_constant():
 def test_divide_into_n_parts():
     assert orc.divide_into_n_parts(64, 3) == [22, 21, 21]
     assert orc.divide_into_n_parts(100, 2) == [50, 50]
+
+
+def test_cfg1_scale_fixture_with_own_factors():
+    """The reference's own operating point at N_train = 2 000 (100 particles, 3 frames; tests/golden/scale_cfg1_n2000_p100.npz
+    holds the reference's inputs and stage outputs, no inverses): the oracle with factors computed by ITSELF reproduces the
+    reference's transition exactly, its observation GP to 1e-12 (same op sequence) and its dynamics GP to 4e-9 of the prior
+    (per-block factorisation vs the reference's dense masked inverse)."""
+    from tests.helpers import Golden
+
+    g = Golden("scale_cfg1_n2000_p100")
+    m = g.spec
+    assert m.N == 2000 and g.P == 100
+    f = orc.precompute_factors(m)
+    states, classes = t64(g.z["init_states"]), torch.as_tensor(g.z["init_classes"])
+    T = g.T.to(torch.float64)
+    lam_x, lam_y = torch.exp(m.x_log_lambdas) ** -2, torch.exp(m.y_log_lambdas) ** -2
+    for t in range(g.steps):
+        s = g.step(t)
+        E, eps, u = t64(s["E"]), t64(s["eps"]), t64(s["u"])
+        c_new = orc.transition(classes, T, E)
+        assert torch.equal(c_new, torch.as_tensor(s["c_new"]))
+        _, dmean, dvar = orc.dynamics_draw(m, f, states, c_new, eps)
+        scale = torch.clamp(torch.abs(t64(s["dyn_mean"])).max(dim=1, keepdim=True).values, min=1e-3)
+        assert scaled_err(dmean, s["dyn_mean"], scale) < 4e-9
+        prior = orc.x_diag_kernel(m, states).unsqueeze(1) * lam_x.unsqueeze(0)
+        assert scaled_err(dvar, t64(s["dyn_std"]) ** 2, prior) < 4e-9
+        x_ref = eps * t64(s["dyn_std"]) + t64(s["dyn_mean"])
+        mu, var, v = orc.map_x_to_y(m, f, x_ref)
+        assert scaled_err(mu, s["mu"], torch.clamp(torch.abs(t64(s["mu"])).max(dim=1, keepdim=True).values, min=1e-3)) < 1e-12
+        assert scaled_err(var, s["var"], lam_y.unsqueeze(0).expand_as(var)) < 1e-12
+        ll = orc.log_likelihoods_fused(mu, v, t64(s["z"]), m.y_log_lambdas)
+        ok = t64(s["var"])[:, 0] / lam_y[0] > 1e-3
+        assert rel_err(ll[ok], t64(s["ll"])[ok]) < 1e-9
+        assert torch.equal(orc.resample(t64(s["w"]), u), torch.as_tensor(s["anc"]))
+        states, classes = t64(s["states_post"]), torch.as_tensor(s["classes_post"])
