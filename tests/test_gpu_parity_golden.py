@@ -271,8 +271,8 @@ def test_cfg1_scale_filter_against_the_reference_directly():
     """The reference's own operating point (100 particles) at N_train = 2 000: the CUDA filter with the factors the PRODUCT
     computes itself (Cholesky -> triangular inverse -> packed panels) against the stage outputs the unmodified reference
     recorded (tests/golden/scale_cfg1_n2000_p100.npz: no inverses in the fixture, nothing goes through the oracle's
-    arithmetic).  Stage-wise, every step started from the reference's state: classes and ancestors exact; means,
-    variances, log-likelihoods at the tolerance two different factorisations of K (cond ~ 1e6) allow."""
+    arithmetic).  Stage-wise, every step started from the reference's state: classes and ancestors exact; means and
+    variances at north_star's 1e-9 (of the row scale / of the prior) although the two sides factor K differently."""
     import json
     import os
 
@@ -323,5 +323,7 @@ def test_cfg1_scale_filter_against_the_reference_directly():
     if os.path.isdir("gpurun_out"):
         with open("gpurun_out/parity_achieved.jsonl", "a") as fh:
             fh.write(json.dumps(rec) + "\n")
-    assert worst["mu"] < 1e-7 and worst["v"] < 1e-7 and worst["dyn_mean"] < 1e-7 and worst["dyn_var"] < 1e-7, worst
-    assert worst["x_new"] < 1e-6 and worst["ll_v>1e-3"] < 1e-4, worst
+    # north_star's 1e-9 holds here even with different factorisations on the two sides (achieved: 2e-12 / 2e-12 / 2e-10 /
+    # 7e-10); x' and ll carry the variance tolerance through sqrt(v) and 1/v at v ~ 5e-4
+    assert worst["mu"] < TOL and worst["v"] < TOL and worst["dyn_mean"] < TOL and worst["dyn_var"] < 4e-9, worst
+    assert worst["x_new"] < 5e-6 and worst["ll_v>1e-3"] < 1e-4, worst
