@@ -1,0 +1,69 @@
+"""The reference's published training run, on the GPU: 2-class model, d = 4, D = 35, 19 sequences (~2 000 frames at 30 fps),
+500 Adam steps at lr 0.01 (notebooks/train_gpmdm.ipynb cells 1-5; the paper quotes ~45 min on a 2017 laptop CPU, the notebook
+log 16-49 s per 10 steps).  Synthetic sequences of that shape; prints one JSON line with the wall time of
+`GPMDM.train_adam(500)` (every step = CUDA kernel-matrix build + torch.linalg Cholesky + closed-form backward + the CUDA
+gradient kernels + Adam), the loss trajectory's ends, the factor precompute that follows, and a filter trial on the trained
+model.   python tools/train_bench.py [--steps 500] [--frames 105]"""
+import argparse
+import json
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+
+from gpmdm_b200 import GPMDM, GPMDM_PF, synthetic
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--steps", type=int, default=500)
+    ap.add_argument("--frames", type=int, default=105)
+    ap.add_argument("--seqs", type=int, default=19)
+    ap.add_argument("--latent", type=int, default=4)
+    ap.add_argument("--obs-dim", type=int, default=35)
+    ap.add_argument("--classes", type=int, default=2)
+    o = ap.parse_args()
+    C, d, D = o.classes, o.latent, o.obs_dim
+    per_class = [o.seqs // C + (1 if c < o.seqs % C else 0) for c in range(C)]
+    wl = synthetic.make_sequences(C, D, max(per_class), o.frames, seed=3, n_test_trials=2 * C, test_frames=150)
+    hp = synthetic.notebook_hyperparameters(D, d, sigma_n=1e-2)
+    m = GPMDM(D=D, d=d, n_classes=C, dyn_target="full", dyn_back_step=1, **hp)
+    for c in range(C):
+        for s in wl.sequences[c][:per_class[c]]:
+            m.add_data(s, c)
+    m.init_X()
+    N = sum(per_class) * o.frames
+    for _ in range(2):  # warm-up: CUDA context, cuSOLVER handles, kernel attributes
+        m.gpdm_loss(m._Y_device(), N, 1).backward()
+    torch.cuda.synchronize()
+    t0 = time.time()
+    losses = m.train_adam(o.steps, 0, lr=0.01)
+    torch.cuda.synchronize()
+    t_train = time.time() - t0
+    t0 = time.time()
+    m._precompute_kernel_inverses()
+    torch.cuda.synchronize()
+    t_factors = time.time() - t0
+    pf = GPMDM_PF(m, synthetic.markov_matrix(C), 100, seed=0)
+    hits = frames = 0
+    for cls, trial in wl.test_trials:
+        pf.reset()
+        for z in trial:
+            pf.update(z)
+            hits += int(pf.get_most_likely_class() == cls)
+            frames += 1
+    print(json.dumps({
+        "workload": f"{C}-class GPMDM, d={d}, D={D}, {sum(per_class)} sequences x {o.frames} frames (N_train={N}), "
+                    f"{o.steps} Adam steps, lr 0.01, fp64",
+        "train_wall_s": t_train, "ms_per_adam_step": 1e3 * t_train / max(o.steps, 1), "loss_first": losses[0],
+        "loss_last": losses[-1], "loss_finite": bool(np.isfinite(losses).all()), "factor_precompute_s": t_factors,
+        "filter_frame_accuracy_on_trained_model": hits / max(frames, 1), "filter_frames": frames,
+        "reference_published": {"train_wall": "~45 min for 500 Adam steps (paper 4.2, 2017 laptop CPU)",
+                                "per_10_steps_s": "16-49 (train_gpmdm.ipynb cell 5 output)"}}))
+
+
+if __name__ == "__main__":
+    main()
