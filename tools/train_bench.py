@@ -25,10 +25,14 @@ def main():
     ap.add_argument("--latent", type=int, default=4)
     ap.add_argument("--obs-dim", type=int, default=35)
     ap.add_argument("--classes", type=int, default=2)
+    ap.add_argument("--noise", type=float, default=0.3, help="observation noise std of the synthetic sequences (signal amplitude ~2): "
+                    "with the generator's default 0.02 Adam drives sigma_n_x to 7e-3 within 200 steps and the dynamics variance "
+                    "prior - k^T K^-1 k of particles near the data falls below the fp64 noise floor of that expression -- "
+                    "negative, i.e. NaN states, in the reference's formulation as much as here (variance_faults counts them)")
     o = ap.parse_args()
     C, d, D = o.classes, o.latent, o.obs_dim
     per_class = [o.seqs // C + (1 if c < o.seqs % C else 0) for c in range(C)]
-    wl = synthetic.make_sequences(C, D, max(per_class), o.frames, seed=3, n_test_trials=2 * C, test_frames=150)
+    wl = synthetic.make_sequences(C, D, max(per_class), o.frames, seed=3, n_test_trials=2 * C, test_frames=150, noise=o.noise)
     hp = synthetic.notebook_hyperparameters(D, d, sigma_n=1e-2)
     m = GPMDM(D=D, d=d, n_classes=C, dyn_target="full", dyn_back_step=1, **hp)
     for c in range(C):
@@ -71,7 +75,7 @@ def main():
     hits, frames = checkpoints[str(o.steps)]["frame_accuracy"], checkpoints[str(o.steps)]["frames"]
     print(json.dumps({
         "workload": f"{C}-class GPMDM, d={d}, D={D}, {sum(per_class)} sequences x {o.frames} frames (N_train={N}), "
-                    f"{o.steps} Adam steps, lr 0.01, fp64",
+                    f"{o.steps} Adam steps, lr 0.01, fp64, synthetic observation noise {o.noise}",
         "train_wall_s": t_train, "ms_per_adam_step": 1e3 * t_train / max(o.steps, 1), "loss_first": losses[0],
         "loss_last": losses[-1], "loss_finite": bool(np.isfinite(losses).all()), "factor_precompute_s": t_factors,
         "filter_frame_accuracy_on_trained_model": hits, "filter_frames": frames, "checkpoints": checkpoints,
