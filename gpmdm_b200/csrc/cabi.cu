@@ -1,8 +1,6 @@
 // Error plumbing, version, factor packing and the DMMA peak probe of libgpmdm_sm100a.so.
 #include <stdarg.h>
 
-#include <stdlib.h>
-
 #include "common.cuh"
 
 namespace gpmdm {
@@ -14,13 +12,6 @@ void set_error(const char* fmt, ...) {
     va_start(ap, fmt);
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
-}
-
-static thread_local bool g_launch_pdl = false;
-bool launch_pdl() { return g_launch_pdl; }
-void set_launch_pdl(bool on) {
-    static const bool disabled = [] { const char* e = getenv("GPMDM_PDL"); return e && e[0] == '0'; }();
-    g_launch_pdl = on && !disabled;
 }
 
 int check_launch(const char* what) {

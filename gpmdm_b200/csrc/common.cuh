@@ -22,28 +22,6 @@ int propagate_lowlat_impl(const gpmdm_gp_model* dyn, const double* x_prev, const
                           double* var_out, int64_t max_n_pad, int32_t seg_chunks, int32_t* tile_counter, void* workspace,
                           void* stream, bool counters_zero);
 
-// ---- programmatic dependent launch (PDL) ---------------------------------------------------------------------
-// The kernels of a latency-bound fixed sequence (csrc/pf_small.cu: six kernels per frame) are launched with the
-// programmatic-stream-serialization attribute: a kernel's CTAs may become resident -- and run their prologue (shared-memory
-// tables, mbarrier set-up) -- while the previous kernel of the stream is still draining.  Every such kernel calls
-// pdl_launch_dependents() first and pdl_wait() before it touches anything a predecessor wrote (griddepcontrol.wait returns
-// once ALL prerequisite grids have completed and their memory is visible; it is a no-op for a normally launched kernel).
-// launch_pdl() is set around the sequence by its issuer; the launch sites below consult it.
-bool launch_pdl();
-void set_launch_pdl(bool on);
-
-template <typename... KArgs, typename... Args>
-static inline cudaError_t launch_kernel(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = grid, cfg.blockDim = block, cfg.dynamicSmemBytes = smem, cfg.stream = st;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    at[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = at;
-    cfg.numAttrs = launch_pdl() ? 1 : 0;
-    return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
-}
-
 #define GPMDM_REQUIRE(cond, code, ...)      \
     do {                                    \
         if (!(cond)) {                      \
@@ -53,9 +31,6 @@ static inline cudaError_t launch_kernel(void (*kern)(KArgs...), dim3 grid, dim3 
     } while (0)
 
 // ---- PTX wrappers -----------------------------------------------------------------------------
-__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
-__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }

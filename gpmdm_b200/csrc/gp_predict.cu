@@ -290,9 +290,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gp_predict_kernel(const PredictPa
         mbar_fence_init();
     }
     if (tid < 64) s.exptab[tid] = c_exp_table[tid];
-    pdl_launch_dependents();
     __syncthreads();
-    pdl_wait();  // everything above ran while the previous kernel of a PDL sequence was draining (common.cuh)
     const double* exptab = s.exptab;
 
     const int total_tiles = prm.tiles ? *prm.n_tiles : (int)((prm.P + TM - 1) / TM);
@@ -704,9 +702,7 @@ __global__ void __launch_bounds__(NTHREADS) kstar_fill_kernel(const PredictParam
     const int r = lane >> 2, c = lane & 3;
     constexpr int REC = rec_width(KIND, DL);
     if (tid < 64) exptab[tid] = c_exp_table[tid];
-    pdl_launch_dependents();
     __syncthreads();
-    pdl_wait();
     const int total_tiles = prm.tiles ? *prm.n_tiles : (int)((prm.P + TM - 1) / TM);
     const int t = blockIdx.x;
     if (t >= total_tiles) return;
@@ -754,8 +750,6 @@ template <int KIND>
 __global__ void __launch_bounds__(128) predict_finalize_kernel(const PredictParams prm, int max_nq) {
     const long long p = (long long)blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
-    pdl_launch_dependents();
-    pdl_wait();
     // the item kernel is done with the hand-out counter: leave it zeroed for the next low-latency launch of a fixed sequence
     // (csrc/pf_small.cu issues the dynamics and the observation launch back to back without memset nodes in between)
     if (blockIdx.x == 0 && threadIdx.x == 0) prm.counter[0] = 0, prm.counter[1] = 0;
@@ -823,11 +817,7 @@ static int launch_instance(const PredictParams& prm, int grid, cudaStream_t st) 
         }
         configured[dev] = true;
     }
-    cudaError_t le = launch_kernel(kern, dim3(grid), dim3(NTHREADS), sizeof(Smem), st, prm);
-    if (le != cudaSuccess) {
-        set_error("gp_predict_kernel: %s", cudaGetErrorString(le));
-        return (int)le;
-    }
+    kern<<<grid, NTHREADS, sizeof(Smem), st>>>(prm);
     return check_launch("gp_predict_kernel");
 }
 
@@ -850,12 +840,8 @@ static int dispatch_d_cached(const PredictParams& prm, int grid, cudaStream_t st
 // low-latency launches: K* slices per particle tile (kstar_fill_kernel), then the (tile, column tile, k segment) items
 template <int KIND, int DL>
 static int launch_split(const PredictParams& prm, int grid, int tiles_bound, int max_nkc, cudaStream_t st) {
-    cudaError_t le = launch_kernel(kstar_fill_kernel<KIND, DL>,
-                                   dim3((unsigned)tiles_bound, (unsigned)((max_nkc + FILL_CHUNKS - 1) / FILL_CHUNKS)), dim3(NTHREADS), 0, st, prm);
-    if (le != cudaSuccess) {
-        set_error("kstar_fill_kernel: %s", cudaGetErrorString(le));
-        return (int)le;
-    }
+    kstar_fill_kernel<KIND, DL><<<dim3((unsigned)tiles_bound, (unsigned)((max_nkc + FILL_CHUNKS - 1) / FILL_CHUNKS)), NTHREADS, 0,
+                                  st>>>(prm);
     if (int rc = check_launch("kstar_fill_kernel")) return rc;
     return launch_instance<KIND, DL, true, true>(prm, grid, st);
 }
@@ -1159,11 +1145,7 @@ static int run_split(PredictParams& prm, int64_t max_n_pad, int32_t seg_chunks, 
     } else {
         if (int rc = dispatch_d<KIND>(prm, grid, st)) return rc;
     }
-    cudaError_t le = launch_kernel(predict_finalize_kernel<KIND>, dim3((unsigned)((prm.P + 3) / 4)), dim3(128), 0, st, prm, max_nq);
-    if (le != cudaSuccess) {
-        set_error("predict_finalize_kernel: %s", cudaGetErrorString(le));
-        return (int)le;
-    }
+    predict_finalize_kernel<KIND><<<(unsigned)((prm.P + 3) / 4), 128, 0, st>>>(prm, max_nq);
     return check_launch("predict_finalize_kernel");
 }
 

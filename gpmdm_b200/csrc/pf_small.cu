@@ -41,8 +41,6 @@ __global__ void __launch_bounds__(PRE_T, 1) small_pre_kernel(const SmallPreArgs 
     __shared__ int wc[32 * 64];                       // per-warp class counts of the current 1024-particle sub-block
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int P = a.P, C = a.C;
-    pdl_launch_dependents();
-    pdl_wait();  // (direct launches: the previous frame's post kernel wrote the cloud and the step key)
     const unsigned long long step = a.step_dev ? *a.step_dev : a.step;
     if (a.z_src) {  // issued first: a read of mapped host memory is one PCIe round trip, hidden behind the rest
         const double* src = a.z_src + (a.frame ? (long long)*a.frame : 0ll) * a.D;
@@ -152,8 +150,6 @@ __global__ void __launch_bounds__(RT, 1) small_post_kernel(const SmallPostArgs a
     __shared__ double sbuf[SMALL_P_MAX + 1];
     const int tid = threadIdx.x;
     const long long P = a.P;
-    pdl_launch_dependents();
-    pdl_wait();
     const int nb = (int)((P + RB - 1) / RB);
     double* scal = a.ws;                                                          // [0] max [1] sum [2] cdf total [3] max(ll + lw)
     double* part = reinterpret_cast<double*>(reinterpret_cast<char*>(a.ws) + 256);  // per-block partials (global: read back by all threads)
@@ -302,13 +298,7 @@ extern "C" int gpmdm_pf_step_small_f64(const gpmdm_pf_step_args* a, uint64_t* st
     pre.z_src = io ? io->z_src : nullptr;
     pre.frame = io ? reinterpret_cast<const unsigned long long*>(io->frame) : nullptr;
     pre.z = const_cast<double*>(a->z), pre.D = a->obs->dout;
-    // the six kernels form a PDL chain (common.cuh): each one's launch and prologue overlap the previous one's tail
-    struct PdlScope {
-        PdlScope() { set_launch_pdl(true); }
-        ~PdlScope() { set_launch_pdl(false); }
-    } pdl_scope;
-    cudaError_t le = launch_kernel(small_pre_kernel, dim3(1), dim3(PRE_T), (size_t)a->C * a->C * sizeof(double), st, pre);
-    GPMDM_REQUIRE(le == cudaSuccess, (int)le, "small_pre_kernel: %s", cudaGetErrorString(le));
+    small_pre_kernel<<<1, PRE_T, (size_t)a->C * a->C * sizeof(double), st>>>(pre);
     GPMDM_TRY(check_launch("small_pre_kernel"));
     // the hand-out counters are zeroed by the pre kernel and again by every finalize kernel: no memset nodes in between
     GPMDM_TRY(propagate_lowlat_impl(a->dyn, a->x_prev, a->perm, a->tiles, a->n_tiles, P, a->eps, a->x_new, nullptr, nullptr,
@@ -325,7 +315,6 @@ extern "C" int gpmdm_pf_step_small_f64(const gpmdm_pf_step_args* a, uint64_t* st
     post.summary_dst = io ? io->summary_dst : nullptr;
     post.probs_dst = io ? io->probs_dst : nullptr;
     post.frame = io ? reinterpret_cast<unsigned long long*>(io->frame) : nullptr;
-    le = launch_kernel(small_post_kernel, dim3(1), dim3(RT), 0, st, post);
-    GPMDM_REQUIRE(le == cudaSuccess, (int)le, "small_post_kernel: %s", cudaGetErrorString(le));
+    small_post_kernel<<<1, RT, 0, st>>>(post);
     return check_launch("small_post_kernel");
 }
