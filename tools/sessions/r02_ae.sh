@@ -1,7 +1,7 @@
 #!/bin/bash
 # Round 2, GPU session AE: programmatic dependent launch for the six-kernel small-cloud frame: small-cloud tests first (under a
-# (The PDL code this session measured lives in commit 2ab1e80 only: it was 8 % slower and was reverted; GPMDM_PDL has no effect now.)
 # timeout), trial driver with and without PDL, then the suite.
+# (The PDL code this session measured lives in commit 2ab1e80 only: it was 8 % slower and was reverted; GPMDM_PDL has no effect now.)
 mkdir -p gpurun_out
 timeout 300 python -m pytest tests/test_gpu_small_cloud.py -m gpu -q -x 2>&1 | tail -5
 rm -f gpurun_out/trials_r02ae.jsonl
