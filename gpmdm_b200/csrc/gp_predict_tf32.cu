@@ -53,15 +53,10 @@ constexpr int ASTAGES = GPMDM_TC_ASTAGES;  // ring depths of the single-CTA vari
 constexpr int BSTAGES = GPMDM_TC_BSTAGES;
 constexpr int A_HALF_BYTES = TM * 16 * 4;   // bytes in the hi (or lo) part of an A stage: 8 KB in both modes
 constexpr int B_HALF_BYTES = TN * 16 * 4;   // bytes in the hi (or lo) part of a B stage / packed tile: 16 KB
-// Thread roles: warp 0 TMA, warp 1 MMA issue + TMEM, warps 2-3 relays (CTA pairs), then the K* generators, then four
-// epilogue warps.  Generators: 8 warps up to d = 4; 16 warps from d = 5 -- a K* entry costs ~2 d + 6 instructions and with two
-// generator warps per scheduler the per-chunk dependency chain (record broadcast -> distance -> ex2 -> split -> store), not the
-// shared-memory pipe, set the pace at d = 8 (ncu at cfg4 sizes: tensor pipe 57 % vs 67 % at d = 3,
-// profiles/ncu_observe_f16x2_kernel_cfg4_r02.txt).
+constexpr int NGEN = 256;                // generator threads
 constexpr int NEPI = 128;                // epilogue threads
-constexpr int GEN_WARP0 = 4;
-__host__ __device__ constexpr int ngen(int dl) { return dl >= 5 ? 512 : 256; }   // generator threads
-__host__ __device__ constexpr int nthreads(int dl) { return GEN_WARP0 * 32 + ngen(dl) + NEPI; }
+constexpr int NTHREADS = 512;
+constexpr int GEN_WARP0 = 4, EPI_WARP0 = 12;
 constexpr int CREC = 8;                  // floats per training record (a_i padded to 8)
 // k per chunk: 16 tf32 (2 MMA k-steps of 8) or 32 fp16 (2 k-steps of 16) -- 64 operand bytes per row either way, i.e.
 // four 16-byte core-matrix rows along K, so stages, tiles and descriptors have the same byte geometry in both modes
@@ -278,8 +273,7 @@ struct Unit {
 };
 
 template <int DL, int MODE, int CG, int KIND = 0>
-__global__ void __launch_bounds__(nthreads(DL), 1) observe_tf32_kernel(const Params prm) {
-    constexpr int NGEN = ngen(DL), EPI_WARP0 = GEN_WARP0 + NGEN / 32;
+__global__ void __launch_bounds__(NTHREADS, 1) observe_tf32_kernel(const Params prm) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     SmemT<CG>& s = *reinterpret_cast<SmemT<CG>*>(smem_raw);
     using G = Geo<MODE>;
@@ -482,11 +476,11 @@ __global__ void __launch_bounds__(nthreads(DL), 1) observe_tf32_kernel(const Par
     } else if (warp >= GEN_WARP0 && warp < EPI_WARP0) {
         // ===================== K* generators =====================
         const int gt = tid - GEN_WARP0 * 32;
-        const int row = gt & (TM - 1), khalf = gt >> 7;  // KPT consecutive k per thread: part `khalf` of the chunk
+        const int row = gt & (TM - 1), khalf = gt >> 7;  // KCm / 2 consecutive k per thread
         // exp(-|a - b|^2) = 2^(-|s a - s b|^2), s = sqrt(log2 e): the training coordinates arrive pre-scaled by s
         // (GPMDM.packed_model_tf32) and the particle's are scaled here, so a K* entry is the distance + ONE ex2.approx
         constexpr double SQRT_LOG2E = 1.2011224087864498;
-        constexpr int KPT = KCm / (NGEN / TM);           // k per thread and chunk: 8 or 4 (tf32) / 16 or 8 (fp16)
+        constexpr int KPT = KCm / 2;                     // k per thread and chunk: 8 (tf32) / 16 (fp16)
         // The chunk's KCm training records (KCm x 8 floats, contiguous) are staged in shared memory by the 256 generator
         // threads themselves -- one coalesced 4-byte load per thread, issued a whole chunk ahead -- and read back as
         // warp-wide broadcasts.  (Every thread used to pull its 8-16 records through L1 with 16-byte loads: at d = 8 the
@@ -780,11 +774,11 @@ static int launch_cg(const Params& prm, int grid, cudaStream_t st) {
         configured[dev] = true;
     }
     if (CG == 1) {
-        kern<<<grid, nthreads(DL), sizeof(SmemT<CG>), st>>>(prm);
+        kern<<<grid, NTHREADS, sizeof(SmemT<CG>), st>>>(prm);
     } else {
         cudaLaunchConfig_t cfg{};
         cfg.gridDim = dim3((unsigned)grid);
-        cfg.blockDim = dim3(nthreads(DL));
+        cfg.blockDim = dim3(NTHREADS);
         cfg.dynamicSmemBytes = sizeof(SmemT<CG>);
         cfg.stream = st;
         cudaLaunchAttribute attr[1];
