@@ -476,11 +476,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) observe_tf32_kernel(const Params 
     } else if (warp >= GEN_WARP0 && warp < EPI_WARP0) {
         // ===================== K* generators =====================
         const int gt = tid - GEN_WARP0 * 32;
-        const int row = gt & (TM - 1), khalf = gt >> 7;  // KCm / 2 consecutive k per thread
+        // Each thread generates TWO particle rows (row0, row0 + 64) x a quarter of the chunk's k: a training record read from
+        // shared memory (a warp-wide broadcast: one wavefront for 16 useful bytes) then serves two K* entries, which halves
+        // the generators' record loads -- at d = 8 they were as many shared-memory wavefronts as the tensor core's own operand
+        // reads (27 G vs 26 G, profiles/ncu_observe_f16x2_kernel_cfg4_r02.txt), on the pipe that bounds the kernel.
+        const int row0 = gt & 63, kq = gt >> 6;
         // exp(-|a - b|^2) = 2^(-|s a - s b|^2), s = sqrt(log2 e): the training coordinates arrive pre-scaled by s
         // (GPMDM.packed_model_tf32) and the particle's are scaled here, so a K* entry is the distance + ONE ex2.approx
         constexpr double SQRT_LOG2E = 1.2011224087864498;
-        constexpr int KPT = KCm / 2;                     // k per thread and chunk: 8 (tf32) / 16 (fp16)
+        constexpr int KPT = KCm / 4;                     // k per thread, row and chunk: 4 (tf32) / 8 (fp16)
         // The chunk's KCm training records (KCm x 8 floats, contiguous) are staged in shared memory by the 256 generator
         // threads themselves -- one coalesced 4-byte load per thread, issued a whole chunk ahead -- and read back as
         // warp-wide broadcasts.  (Every thread used to pull its 8-16 records through L1 with 16-byte loads: at d = 8 the
@@ -500,19 +504,23 @@ __global__ void __launch_bounds__(NTHREADS, 1) observe_tf32_kernel(const Params 
                 const Unit nu = unit(tile_of(u + unit_stride) < n_tiles ? tile_of(u + unit_stride) : n_tiles - 1);
                 nxt_c = nu.coords;
             }
-            long long p;
-            if (KIND == 1) p = prm.perm[un.first + (row < un.count ? row : un.count - 1)];
-            else {
-                p = (long long)tile_of(u) * TM + row;
-                if (p >= prm.P) p = prm.P - 1;
-            }
             // particle coordinates, negated and duplicated into both halves of a packed f32x2 register
-            float2 nb[DL];
+            float2 nb[2][DL];
 #pragma unroll
-            for (int j = 0; j < DL; j++) {
-                const double xj = prm.x[p * DL + j];
-                const float bj = (float)(xj / prm.ls[j] * SQRT_LOG2E);
-                nb[j] = make_float2(-bj, -bj);
+            for (int r = 0; r < 2; r++) {
+                const int row = row0 + 64 * r;
+                long long p;
+                if (KIND == 1) p = prm.perm[un.first + (row < un.count ? row : un.count - 1)];
+                else {
+                    p = (long long)tile_of(u) * TM + row;
+                    if (p >= prm.P) p = prm.P - 1;
+                }
+#pragma unroll
+                for (int j = 0; j < DL; j++) {
+                    const double xj = prm.x[p * DL + j];
+                    const float bj = (float)(xj / prm.ls[j] * SQRT_LOG2E);
+                    nb[r][j] = make_float2(-bj, -bj);
+                }
             }
             for (int ct = 0; ct < un.nct; ct++) {
                 const int nch = chunks_of(un, ct);
@@ -523,10 +531,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) observe_tf32_kernel(const Params 
                     const long long noff = (long long)(kc + 1 < nch ? kc + 1 : 0) * CHUNK_FLOATS + gt;
                     float cnext = 0.f;
                     if (gt < CHUNK_FLOATS) cnext = __ldg((last ? nxt_c : un.coords) + noff);
-                    float kv[KPT];
+                    float kv[2][KPT];
                     // records are stored per PAIR of training rows as [j][2] (a_k[j], a_k+1[j]): one 64-bit element feeds
                     // the packed fp32x2 pipe (sm_100 FADD2 / FFMA2), two K* entries per instruction
-                    const float2* rec = reinterpret_cast<const float2*>(s.coords[g & 1]) + (khalf * KPT) / 2 * CREC;
+                    const float2* rec = reinterpret_cast<const float2*>(s.coords[g & 1]) + (kq * KPT) / 2 * CREC;
 #pragma unroll
                     for (int kk = 0; kk < KPT; kk += 2) {
                         float2 a[CREC];
@@ -536,52 +544,57 @@ __global__ void __launch_bounds__(NTHREADS, 1) observe_tf32_kernel(const Params 
                             a[2 * q] = make_float2(r4.x, r4.y);
                             a[2 * q + 1] = make_float2(r4.z, r4.w);
                         }
-                        float2 dist = make_float2(0.f, 0.f);
 #pragma unroll
-                        for (int j = 0; j < DL; j++) {
-                            const float2 tdiff = __fadd2_rn(a[j], nb[j]);
-                            dist = __ffma2_rn(tdiff, tdiff, dist);
+                        for (int r = 0; r < 2; r++) {
+                            float2 dist = make_float2(0.f, 0.f);
+#pragma unroll
+                            for (int j = 0; j < DL; j++) {
+                                const float2 tdiff = __fadd2_rn(a[j], nb[r][j]);
+                                dist = __ffma2_rn(tdiff, tdiff, dist);
+                            }
+                            kv[r][kk] = ex2_approx(-dist.x);
+                            kv[r][kk + 1] = ex2_approx(-dist.y);
                         }
-                        kv[kk] = ex2_approx(-dist.x);
-                        kv[kk + 1] = ex2_approx(-dist.y);
                     }
                     if (gt < CHUNK_FLOATS) s.coords[(g + 1) & 1][gt] = cnext;
                     named_bar_sync(1, NGEN);  // next chunk's records visible; nobody still reads the buffer written next time
                     wait(&s.a_empty[sa], ((g / AST) & 1) ^ 1);
                     if (F16) {
-                        // a = hi + 2^-11 lo: 16 consecutive k of one row = two 16-byte core-matrix rows per piece
+                        // a = hi + 2^-11 lo: 8 consecutive k of one row = one 16-byte core-matrix row per piece
+                        static_assert(!F16 || KPT == 8, "one core-matrix row per thread, row and piece");
                         __half* ah = reinterpret_cast<__half*>(&s.A[sa][0][0]);
                         __half* al = reinterpret_cast<__half*>(&s.A[sa][1][0]);
 #pragma unroll
-                        for (int q = 0; q < KPT / 8; q++) {
+                        for (int r = 0; r < 2; r++) {
                             // packed conversions (two values per F2FP): scalar fp32 <-> fp16 conversions run at a
                             // fraction of the rate
                             __half2 hi[4], lo[4];
 #pragma unroll
                             for (int i = 0; i < 4; i++) {
-                                const float k0 = kv[q * 8 + 2 * i], k1 = kv[q * 8 + 2 * i + 1];
+                                const float k0 = kv[r][2 * i], k1 = kv[r][2 * i + 1];
                                 hi[i] = __floats2half2_rn(k0, k1);
                                 const float2 hb = __half22float2(hi[i]);
                                 lo[i] = __floats2half2_rn(fmaf(hb.x, -2048.f, k0 * 2048.f), fmaf(hb.y, -2048.f, k1 * 2048.f));
                             }
-                            const int idx = tile_index<MODE>(row, khalf * KPT + q * 8);
+                            const int idx = tile_index<MODE>(row0 + 64 * r, kq * KPT);
                             *reinterpret_cast<uint4*>(ah + idx) = make_uint4(*reinterpret_cast<uint32_t*>(&hi[0]), *reinterpret_cast<uint32_t*>(&hi[1]),
                                                                              *reinterpret_cast<uint32_t*>(&hi[2]), *reinterpret_cast<uint32_t*>(&hi[3]));
                             *reinterpret_cast<uint4*>(al + idx) = make_uint4(*reinterpret_cast<uint32_t*>(&lo[0]), *reinterpret_cast<uint32_t*>(&lo[1]),
                                                                              *reinterpret_cast<uint32_t*>(&lo[2]), *reinterpret_cast<uint32_t*>(&lo[3]));
                         }
                     } else {
+                        static_assert(F16 || KPT == 4, "one core-matrix row per thread, row and piece");
                         float* ah = reinterpret_cast<float*>(&s.A[sa][0][0]);
                         float* al = reinterpret_cast<float*>(&s.A[sa][1][0]);
 #pragma unroll
-                        for (int q = 0; q < KPT / 4; q++) {
+                        for (int r = 0; r < 2; r++) {
                             float hi[4], lo[4];
 #pragma unroll
                             for (int i = 0; i < 4; i++) {
-                                hi[i] = to_tf32(kv[q * 4 + i]);
-                                lo[i] = to_tf32(kv[q * 4 + i] - hi[i]);
+                                hi[i] = to_tf32(kv[r][i]);
+                                lo[i] = to_tf32(kv[r][i] - hi[i]);
                             }
-                            const int idx = tile_index<MODE>(row, khalf * KPT + q * 4);
+                            const int idx = tile_index<MODE>(row0 + 64 * r, kq * KPT);
                             *reinterpret_cast<float4*>(ah + idx) = make_float4(hi[0], hi[1], hi[2], hi[3]);
                             *reinterpret_cast<float4*>(al + idx) = make_float4(lo[0], lo[1], lo[2], lo[3]);
                         }
