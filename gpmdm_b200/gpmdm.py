@@ -100,14 +100,70 @@ class _KernelBuild(torch.autograd.Function):
 
 # ------------------------------------------------------------------------------------------------
 # K^-1 from a lower Cholesky factor as GEMM-shaped block recursions (cuBLAS DGEMM runs at ~36 TF/s on B200,
-# cuSOLVER's potri at ~10: 534 ms at N = 20 k).  2/3 N^3 flops each; the leaves are plain library calls.
+# cuSOLVER's potri at ~10: 534 ms at N = 20 k); the leaves are plain library calls.  Products with a triangular operand
+# recurse on the triangle (`_mm_right_lower_`, `_mm_left_lower_`, `_syrk_t_add_`), so that only the leaf blocks multiply
+# structural zeros: ~N^3/3 flops for the triangular inverse and for L^-T L^-1 each, instead of 2/3 N^3 with dense GEMMs.
 # ------------------------------------------------------------------------------------------------
 _INV_LEAF = 2560
+_TRMM_LEAF = 1024
 
 
 def _split(n: int) -> int:
     h = (n // 2 + 127) // 128 * 128
     return h if h < n else n // 2
+
+
+def _mm_right_lower_(X, A):
+    """X <- X A in place; A lower triangular with an explicit zero upper part."""
+    k = A.shape[0]
+    if k <= _TRMM_LEAF:
+        X.copy_(torch.mm(X, A))
+        return
+    h = _split(k)
+    X1, X2 = X[:, :h], X[:, h:]
+    _mm_right_lower_(X1, A[:h, :h])
+    X1.addmm_(X2, A[h:, :h])  # the original X2
+    _mm_right_lower_(X2, A[h:, h:])
+
+
+def _mm_left_lower_(C, X):
+    """X <- C X in place; C lower triangular with an explicit zero upper part."""
+    k = C.shape[0]
+    if k <= _TRMM_LEAF:
+        X.copy_(torch.mm(C, X))
+        return
+    h = _split(k)
+    X1, X2 = X[:h], X[h:]
+    _mm_left_lower_(C[h:, h:], X2)
+    X2.addmm_(C[h:, :h], X1)  # the original X1
+    _mm_left_lower_(C[:h, :h], X1)
+
+
+def _mm_right_lower_into(Y, A, out):
+    """out <- Y A; A lower triangular with an explicit zero upper part (Y, out may be strided views)."""
+    k = A.shape[0]
+    if k <= _TRMM_LEAF:
+        torch.mm(Y, A, out=out)
+        return
+    h = _split(k)
+    _mm_right_lower_into(Y[:, :h], A[:h, :h], out[:, :h])
+    out[:, :h].addmm_(Y[:, h:], A[h:, :h])
+    _mm_right_lower_into(Y[:, h:], A[h:, h:], out[:, h:])
+
+
+def _syrk_t_add_(X, out):
+    """out += X^T X (out square, symmetric): the off-diagonal blocks are computed once and mirrored."""
+    k = X.shape[1]
+    if k <= 2 * _TRMM_LEAF:
+        out.addmm_(X.t(), X)
+        return
+    h = _split(k)
+    X1, X2 = X[:, :h], X[:, h:]
+    _syrk_t_add_(X1, out[:h, :h])
+    _syrk_t_add_(X2, out[h:, h:])
+    T = torch.mm(X2.t(), X1)
+    out[h:, :h].add_(T)
+    out[:h, h:].add_(T.t())
 
 
 def _tril_inverse_into(L, out):
@@ -120,8 +176,11 @@ def _tril_inverse_into(L, out):
     _tril_inverse_into(L[:h, :h], out[:h, :h])
     _tril_inverse_into(L[h:, h:], out[h:, h:])
     # [[A, 0], [B, C]]^-1 = [[A^-1, 0], [-C^-1 B A^-1, C^-1]]
-    torch.mm(out[h:, h:], torch.mm(L[h:, :h], out[:h, :h]), out=out[h:, :h])
-    out[h:, :h].neg_()
+    B = out[h:, :h]
+    B.copy_(L[h:, :h])
+    _mm_right_lower_(B, out[:h, :h])
+    _mm_left_lower_(out[h:, h:], B)
+    B.neg_()
 
 
 def _gram_of_tril_into(Li, out):
@@ -133,9 +192,9 @@ def _gram_of_tril_into(Li, out):
     h = _split(n)
     A, X, C = Li[:h, :h], Li[h:, :h], Li[h:, h:]
     _gram_of_tril_into(A, out[:h, :h])
-    out[:h, :h].addmm_(X.t(), X)
+    _syrk_t_add_(X, out[:h, :h])
     _gram_of_tril_into(C, out[h:, h:])
-    torch.mm(X.t(), C, out=out[:h, h:])
+    _mm_right_lower_into(X.t(), C, out[:h, h:])
     out[h:, :h].copy_(out[:h, h:].t())
 
 
@@ -158,13 +217,15 @@ def spd_inverse_from_cholesky(L):
 # Pure torch (cuSOLVER potrf + cuBLAS DGEMM on the device); device agnostic, so the CPU suite checks the algebra.
 # ------------------------------------------------------------------------------------------------
 _TRINV_LEAF = 1024
+_PANEL_ROW_BLOCK = 2048  # row blocks of a column panel's GEMM below its diagonal block
 PANEL_LD = 260  # GPMDM_PANEL_LD
 
 
 def tril_inverse_inplace(L):
     """L <- L^-1 for a lower-triangular L whose strict upper part is zero (stays zero).
-    [[A, 0], [B, C]]^-1 = [[A^-1, 0], [-C^-1 B A^-1, C^-1]], recursively, with one temporary of a quarter of the
-    matrix at the top level (GEMM-shaped: DGEMM runs at ~36 TF/s on B200, TRSM / cuSOLVER's trtri well below)."""
+    [[A, 0], [B, C]]^-1 = [[A^-1, 0], [-C^-1 B A^-1, C^-1]], recursively; the two products recurse on their triangular
+    operand in place (temporaries: one leaf-wide strip), GEMM-shaped throughout: DGEMM runs at ~36 TF/s on B200, TRSM /
+    cuSOLVER's trtri well below."""
     n = L.shape[0]
     if n <= _TRINV_LEAF:
         L.copy_(torch.linalg.solve_triangular(L, torch.eye(n, dtype=L.dtype, device=L.device), upper=False))
@@ -173,9 +234,8 @@ def tril_inverse_inplace(L):
     A, B, C = L[:h, :h], L[h:, :h], L[h:, h:]
     tril_inverse_inplace(A)
     tril_inverse_inplace(C)
-    T = torch.mm(B, A)
-    torch.mm(C, T, out=B)
-    del T
+    _mm_right_lower_(B, A)
+    _mm_left_lower_(C, B)
     B.neg_()
     return L
 
@@ -205,8 +265,16 @@ def quadform_panels_from_tril_inverse(Linv, n_pad: int, tri: bool, out=None):
         r0 = c0 if tri else 0
         off = panel_row_offset(J, n_pad, tri) * PANEL_LD
         dst = out[off:off + (n_pad - r0) * PANEL_LD].view(n_pad - r0, PANEL_LD)[:n - r0, :w]
-        # K^-1[i, j] = sum_{k >= max(i, j)} Linv[k, i] Linv[k, j];  j >= c0 here, so k runs over rows c0.. only
-        torch.mm(Linv[c0:, r0:].t(), Linv[c0:, c0:c0 + w], out=dst)
+        # K^-1[i, j] = sum_{k >= max(i, j)} Linv[k, i] Linv[k, j];  j >= c0 here, so k runs over rows c0.. only -- and for
+        # the rows i >= r of a row block over k >= r only (below the panel's diagonal block Linv[k, i] = 0 for k < i)
+        if tri:
+            r = c0
+            while r < n:
+                r1 = min(n, r + (w if r == c0 else _PANEL_ROW_BLOCK))
+                torch.mm(Linv[r:, r:r1].t(), Linv[r:, c0:c0 + w], out=dst[r - r0:r1 - r0])
+                r = r1
+        else:
+            torch.mm(Linv[c0:, r0:].t(), Linv[c0:, c0:c0 + w], out=dst)
         if tri:
             dst[w:].mul_(2.0)
             diag = dst[:w]

@@ -48,6 +48,7 @@ def test_logdet_trace_closed_form_backward_matches_autograd(offsets, monkeypatch
 @pytest.mark.parametrize("n", [1, 15, 16, 100, 257])
 def test_spd_inverse_from_cholesky_block_recursion(n, monkeypatch):
     monkeypatch.setattr(G, "_INV_LEAF", 16)
+    monkeypatch.setattr(G, "_TRMM_LEAF", 8)
     gen = torch.Generator().manual_seed(n)
     K = spd(n, gen)
     L = torch.linalg.cholesky(K)
@@ -59,10 +60,37 @@ def test_spd_inverse_from_cholesky_block_recursion(n, monkeypatch):
     assert float((Kinv @ K - torch.eye(n, dtype=F64)).abs().max()) < 1e-10
 
 
+@pytest.mark.parametrize("n", [1, 9, 40, 131])
+def test_products_with_a_triangular_operand_recurse_on_the_triangle(n, monkeypatch):
+    """X A, C X (in place and into a strided output) and X^T X as block recursions that skip the structural zeros: equal
+    to the dense products to rounding, for sizes below, at and far above the leaf."""
+    monkeypatch.setattr(G, "_TRMM_LEAF", 8)
+    gen = torch.Generator().manual_seed(100 + n)
+    A = torch.tril(torch.randn(n, n, dtype=F64, generator=gen))
+    X = torch.randn(23, n, dtype=F64, generator=gen)
+    Z = torch.randn(n, 17, dtype=F64, generator=gen)
+    tol = 1e-13 * n * float(A.abs().max())
+    Y = X.clone()
+    G._mm_right_lower_(Y, A)
+    assert float((Y - X @ A).abs().max()) < tol * float(X.abs().max())
+    Y = Z.clone()
+    G._mm_left_lower_(A, Y)
+    assert float((Y - A @ Z).abs().max()) < tol * float(Z.abs().max())
+    big = torch.zeros(30, 2 * n + 3, dtype=F64)
+    G._mm_right_lower_into(X.t().contiguous().t(), A, big[4:27, 2:2 + n])  # column-major input, strided output
+    assert float((big[4:27, 2:2 + n] - X @ A).abs().max()) < tol * float(X.abs().max())
+    assert float(big[:4].abs().max()) == 0.0 and float(big[:, 2 + n:].abs().max()) == 0.0
+    out = torch.eye(n, dtype=F64)
+    G._syrk_t_add_(X, out)
+    assert float((out - (torch.eye(n, dtype=F64) + X.t() @ X)).abs().max()) < 1e-13 * 23 * float(X.abs().max()) ** 2
+    assert torch.equal(out, out.t())
+
+
 # ---- factor precompute without dense intermediates (gpmdm.py:1284-1305 -> GPMDM._factor_block) -------------------------
 @pytest.mark.parametrize("n", [1, 7, 256, 300, 700])
 def test_tril_inverse_in_place(n, monkeypatch):
     monkeypatch.setattr(G, "_TRINV_LEAF", 64)
+    monkeypatch.setattr(G, "_TRMM_LEAF", 16)
     gen = torch.Generator().manual_seed(n)
     L = torch.linalg.cholesky(spd(n, gen))
     out = G.tril_inverse_inplace(L.clone())
@@ -77,6 +105,8 @@ def test_quadform_panels_straight_from_the_triangular_inverse(n, tri, monkeypatc
     """Panels built by one GEMM per column panel from L^-1 hold exactly the layout gpmdm_pack_quadform_f64 writes from a
     dense inverse (include/gpmdm_b200.h: gpmdm_gp_block), and k^T Q k == k^T K^-1 k."""
     monkeypatch.setattr(G, "_TRINV_LEAF", 64)
+    monkeypatch.setattr(G, "_TRMM_LEAF", 16)
+    monkeypatch.setattr(G, "_PANEL_ROW_BLOCK", 96)  # several row blocks below a panel's diagonal block
     gen = torch.Generator().manual_seed(n + 1)
     K = spd(n, gen) / n
     Kinv = torch.linalg.inv(K)
