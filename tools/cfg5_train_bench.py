@@ -34,6 +34,7 @@ def main():
     ap.add_argument("--classes", type=int, default=8)
     ap.add_argument("--seqs-per-class", type=int, default=25)
     ap.add_argument("--frames", type=int, default=100)
+    ap.add_argument("--profile", action="store_true", help="also print the top CUDA kernels of one forward + backward (torch.profiler) to stderr")
     o = ap.parse_args()
     a = argparse.Namespace(classes=o.classes, seqs_per_class=o.seqs_per_class, frames=o.frames, latent=3, obs_dim=62)
     from gpmdm_b200 import GPMDM
@@ -94,7 +95,14 @@ def main():
 
     t = timed(step, reps=2)
     out["gpdm_loss_fwd_bwd_ms"] = t
-    out["loss"] = float(step())
+    out["loss"] = float(step().detach())
+    if o.profile:
+        from torch.profiler import ProfilerActivity, profile
+
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            step()
+            torch.cuda.synchronize()
+        print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=25, max_name_column_width=70), file=sys.stderr)
     for k in list(out):
         if k.endswith("_gbs"):
             out[k.replace("_gbs", "_frac_of_hbm_peak")] = out[k] / HBM_PEAK
