@@ -104,8 +104,8 @@ class _KernelBuild(torch.autograd.Function):
 # recurse on the triangle (`_mm_right_lower_`, `_mm_left_lower_`, `_syrk_t_add_`), so that only the leaf blocks multiply
 # structural zeros: ~N^3/3 flops for the triangular inverse and for L^-T L^-1 each, instead of 2/3 N^3 with dense GEMMs.
 # ------------------------------------------------------------------------------------------------
-_INV_LEAF = 2560
-_TRMM_LEAF = 1024
+_INV_LEAF = 1280   # (tools/leaf_sweep.py at N = 20 000: 2560 / 1024 -> 199 ms, 1280 / 512 -> 191 ms for K^-1 from L)
+_TRMM_LEAF = 512
 
 
 def _split(n: int) -> int:
