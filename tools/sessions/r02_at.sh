@@ -3,7 +3,7 @@
 mkdir -p gpurun_out
 CMD="python tools/run_trials.py --trials 1 --no-graph"
 timeout 300 $CMD > gpurun_out/plain_r02at.log 2>&1 &&
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:gpmdm --csv --log-file gpurun_out/launches_small_r02at.csv $CMD > gpurun_out/ncu_small_at.log 2>&1
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k "regex:gp_predict_kernel|small_pre_kernel|small_post_kernel|predict_finalize_kernel|kstar_fill_kernel" --csv --log-file gpurun_out/launches_small_r02at.csv $CMD > gpurun_out/ncu_small_at.log 2>&1
 python - <<'PY'
 import csv, collections
 rows = list(csv.reader(open("gpurun_out/launches_small_r02at.csv")))
