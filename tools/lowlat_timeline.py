@@ -74,6 +74,7 @@ def main():
     ap.add_argument("--particles", type=int, default=100)
     ap.add_argument("--seg", type=int, default=-1, help="segment length in chunks (-1: the filter's own choice)")
     ap.add_argument("--fused", action="store_true", help="time the fused cached launch on 148 full tiles instead")
+    ap.add_argument("--dynamics", action="store_true", help="the dynamics GP's low-latency launch instead of the observation GP's")
     o = ap.parse_args()
     if o.build:
         return build()
@@ -105,8 +106,30 @@ def main():
     words = np.zeros(160 * 64 * 8, dtype=np.uint64)
     counts = np.zeros(160, dtype=np.int32)
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    if o.dynamics:
+        C = o.classes
+        cls = torch.randint(0, C, (P,), generator=g).cuda()
+        perm = torch.empty(P, dtype=torch.int32, device="cuda")
+        tiles = torch.empty((P // 64 + C + 1) * 4, dtype=torch.int32, device="cuda")
+        n_tiles = torch.empty(1, dtype=torch.int32, device="cuda")
+        sws = torch.empty(int(lib.gpmdm_workspace_bytes(P, C)) // 8 + 1, dtype=torch.float64, device="cuda")
+        _cabi.check(lib.gpmdm_pf_bucket_by_class(cls.data_ptr(), P, C, perm.data_ptr(), tiles.data_ptr(), n_tiles.data_ptr(),
+                                                 sws.data_ptr(), _cabi.stream()), "bucket")
+        n_pad = pk["dyn_max_n_pad"]
+        seg = o.seg if o.seg >= 0 else int(lib.gpmdm_predict_lowlat_pick_segment(max((P + 63) // 64, min(C, P)), n_pad, 256, 1))
+        ws = torch.empty(int(lib.gpmdm_predict_lowlat_workspace_bytes(P, n_pad, 3, seg, C)) // 8 + 1, dtype=torch.float64, device="cuda")
+        eps = torch.randn(P, 3, dtype=torch.float64, generator=g).cuda()
+        x_new = torch.empty(P, 3, dtype=torch.float64, device="cuda")
     for it in range(5):
         ev[0].record()
+        if o.dynamics:
+            _cabi.check(lib.gpmdm_pf_propagate_lowlat_f64(ctypes.byref(pk["dyn"]), xs.data_ptr(), perm.data_ptr(), tiles.data_ptr(),
+                                                          n_tiles.data_ptr(), P, eps.data_ptr(), x_new.data_ptr(), None, None, n_pad,
+                                                          seg, counter.data_ptr(), ws.data_ptr(), _cabi.stream()), "propagate_lowlat")
+            ev[1].record()
+            torch.cuda.synchronize()
+            lib.gpmdm_debug_timeline(words.ctypes.data, counts.ctypes.data)
+            continue
         _cabi.check(lib.gpmdm_pf_observe_lowlat_f64(ctypes.byref(pk["obs"]), xs.data_ptr(), P, z.data_ptr(), 0.0, None,
                                                     ll.data_ptr(), None, None, n_pad, seg, counter.data_ptr(), ws.data_ptr(),
                                                     _cabi.stream()), "observe_lowlat")
@@ -129,7 +152,7 @@ def main():
     clk = subprocess.run(["nvidia-smi", "--query-gpu=clocks.sm", "--format=csv,noheader,nounits"], capture_output=True, text=True).stdout.strip()
     out = {
         "sm_clock_mhz_after": clk,
-        "workload": f"observation GP, low-latency items, N={X0.shape[0]} n_pad={n_pad} P={P} seg_chunks={seg}",
+        "workload": f"{'dynamics' if o.dynamics else 'observation'} GP, low-latency items, N={X0.shape[0]} n_pad={n_pad} P={P} seg_chunks={seg}",
         "launch_ms_events": ev[0].elapsed_time(ev[1]), "ctas": len(ctas), "items_real": len(real),
         "items_empty": len(rows) - len(real),
         "cta_enter_spread_ns": max(int(w[b, 0, 7]) for b in ctas) - t_enter,
