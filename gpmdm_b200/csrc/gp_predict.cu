@@ -263,8 +263,14 @@ __device__ __forceinline__ unsigned long long tl_now() {
 }
 #define GPMDM_TL(slot)                                                                                     \
     if (tid == 0 && tl_i < TL_ITEMS) g_timeline[((long long)blockIdx.x * TL_ITEMS + tl_i) * TL_WORDS + (slot)] = tl_now();
+// first start / last end of the item, fill and finalize kernels of the LAST launch of each kind (node timeline of a frame)
+__device__ unsigned long long g_node_stamps[16];  // [2 id] start (min), [2 id + 1] end (max); id = kernel (0 items, 1 finalize, 2 fill) * 2 + KIND
+#define GPMDM_NODE_BEGIN(id) if (threadIdx.x == 0) atomicMin(&g_node_stamps[2 * (id)], tl_now());
+#define GPMDM_NODE_END(id) if (threadIdx.x == 0) atomicMax(&g_node_stamps[2 * (id) + 1], tl_now());
 #else
 #define GPMDM_TL(slot)
+#define GPMDM_NODE_BEGIN(id)
+#define GPMDM_NODE_END(id)
 #endif
 
 // SPLIT (low-latency launches, CACHE only): the K* slices come from kstar_fill_kernel (one slice per particle TILE, shared by
@@ -300,6 +306,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gp_predict_kernel(const PredictPa
 
     const int total_items = prm.split ? total_tiles * prm.max_nct * prm.nseg : total_tiles;
     int rounds_done = 0;
+    GPMDM_NODE_BEGIN(0 * 2 + KIND)
 #ifdef GPMDM_TIMELINE
     int tl_i = -1;
     const unsigned long long tl_enter = tl_now();
@@ -325,6 +332,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gp_predict_kernel(const PredictPa
         if (item >= total_items) {
             // leaving: satisfy every later round so that nobody waits for this CTA
             if (prm.round_sync && tid == 0) atomicAdd(prm.counter + 1, 1 << 20);  // > any target (n_tiles < 2^20)
+            GPMDM_NODE_END(0 * 2 + KIND)
             break;
         }
         // split mode: items are ordered column tile first, so the longest (ct = 0 of every particle tile) start first
@@ -750,6 +758,7 @@ template <int KIND>
 __global__ void __launch_bounds__(128) predict_finalize_kernel(const PredictParams prm, int max_nq) {
     const long long p = (long long)blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
+    GPMDM_NODE_BEGIN(1 * 2 + KIND)
     // the item kernel is done with the hand-out counter: leave it zeroed for the next low-latency launch of a fixed sequence
     // (csrc/pf_small.cu issues the dynamics and the observation launch back to back without memset nodes in between)
     if (blockIdx.x == 0 && threadIdx.x == 0) prm.counter[0] = 0, prm.counter[1] = 0;
@@ -798,6 +807,7 @@ __global__ void __launch_bounds__(128) predict_finalize_kernel(const PredictPara
             if (prm.var_out) prm.var_out[o] = var;
         }
     }
+    GPMDM_NODE_END(1 * 2 + KIND)  // (by the first warp of every block; the other warps finish within a few hundred ns of it)
 }
 
 // ---- host side -------------------------------------------------------------------------------------
@@ -1217,6 +1227,16 @@ extern "C" int gpmdm_pf_propagate_lowlat_f64(const gpmdm_gp_model* dyn, const do
 
 #ifdef GPMDM_TIMELINE
 // diagnostic build only: copies out and clears the per-item time stamps ([160][64][8] words, [160] counts)
+// node stamps ([16] words) of the last item / finalize launches; reset to (max, 0) pairs afterwards
+extern "C" int gpmdm_debug_node_stamps(unsigned long long* host16) {
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(host16, gpmdm::g_node_stamps, sizeof(unsigned long long) * 16);
+    unsigned long long init[16];
+    for (int i = 0; i < 16; i++) init[i] = (i & 1) ? 0ull : ~0ull;
+    cudaMemcpyToSymbol(gpmdm::g_node_stamps, init, sizeof(init));
+    return 0;
+}
+
 extern "C" int gpmdm_debug_timeline(unsigned long long* host_words, int* host_counts) {
     cudaDeviceSynchronize();
     cudaMemcpyFromSymbol(host_words, gpmdm::g_timeline, sizeof(unsigned long long) * 160 * gpmdm::TL_ITEMS * gpmdm::TL_WORDS);

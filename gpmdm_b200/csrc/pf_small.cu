@@ -16,6 +16,18 @@
 
 namespace gpmdm {
 
+#ifdef GPMDM_TIMELINE  /* diagnostic build (tools/lowlat_timeline.py --frame): start / end of the pre and post kernels */
+__device__ unsigned long long g_small_stamps[4];
+__device__ __forceinline__ unsigned long long small_now() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+#define GPMDM_SMALL_STAMP(i) if (threadIdx.x == 0) g_small_stamps[i] = small_now();
+#else
+#define GPMDM_SMALL_STAMP(i)
+#endif
+
 constexpr int SMALL_P_MAX = 4096;  // 4 reduction blocks; one CTA of 1024 threads holds 4 particles per thread
 constexpr int PRE_T = 1024;
 
@@ -41,6 +53,7 @@ __global__ void __launch_bounds__(PRE_T, 1) small_pre_kernel(const SmallPreArgs 
     __shared__ int wc[32 * 64];                       // per-warp class counts of the current 1024-particle sub-block
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int P = a.P, C = a.C;
+    GPMDM_SMALL_STAMP(0)
     const unsigned long long step = a.step_dev ? *a.step_dev : a.step;
     if (a.z_src) {  // issued first: a read of mapped host memory is one PCIe round trip, hidden behind the rest
         const double* src = a.z_src + (a.frame ? (long long)*a.frame : 0ll) * a.D;
@@ -120,6 +133,7 @@ __global__ void __launch_bounds__(PRE_T, 1) small_pre_kernel(const SmallPreArgs 
         if (c >= 0) a.perm[cls_start[c] + wc[warp * C + c] + rank] = sub * PRE_T + tid;
         __syncthreads();
     }
+    GPMDM_SMALL_STAMP(1)
 }
 
 struct SmallPostArgs {
@@ -150,6 +164,7 @@ __global__ void __launch_bounds__(RT, 1) small_post_kernel(const SmallPostArgs a
     __shared__ double sbuf[SMALL_P_MAX + 1];
     const int tid = threadIdx.x;
     const long long P = a.P;
+    GPMDM_SMALL_STAMP(2)
     const int nb = (int)((P + RB - 1) / RB);
     double* scal = a.ws;                                                          // [0] max [1] sum [2] cdf total [3] max(ll + lw)
     double* part = reinterpret_cast<double*>(reinterpret_cast<char*>(a.ws) + 256);  // per-block partials (global: read back by all threads)
@@ -261,6 +276,7 @@ __global__ void __launch_bounds__(RT, 1) small_post_kernel(const SmallPostArgs a
     __syncthreads();
     if (a.frame && tid == 0) a.frame[0] += 1ull;
     if (a.step_dev && tid == 0) a.step_dev[0] += 1ull;
+    GPMDM_SMALL_STAMP(3)
 }
 
 }  // namespace gpmdm
@@ -318,3 +334,11 @@ extern "C" int gpmdm_pf_step_small_f64(const gpmdm_pf_step_args* a, uint64_t* st
     small_post_kernel<<<1, RT, 0, st>>>(post);
     return check_launch("small_post_kernel");
 }
+
+#ifdef GPMDM_TIMELINE
+extern "C" int gpmdm_debug_small_stamps(unsigned long long* host4) {
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(host4, gpmdm::g_small_stamps, sizeof(unsigned long long) * 4);
+    return 0;
+}
+#endif

@@ -22,12 +22,54 @@ def build():
     from gpmdm_b200 import build as b
 
     b.build()
-    obj = os.path.join(b.LIB_DIR, "gp_predict_timeline.o")
-    subprocess.check_call([b._nvcc(), *b.NVCC_FLAGS, "-DGPMDM_TIMELINE", "-I", b.INCLUDE, "-c",
-                           os.path.join(b.CSRC, "gp_predict.cu"), "-o", obj])
-    objs = [os.path.join(b.LIB_DIR, os.path.basename(s)[:-3] + ".o") for s in b.sources() if not s.endswith("gp_predict.cu")]
-    subprocess.check_call([b._nvcc(), "-shared", "-o", LIB, obj, *objs, "-gencode", "arch=compute_100a,code=sm_100a"])
+    tl_srcs = ("gp_predict.cu", "pf_small.cu")
+    objs = []
+    for name in tl_srcs:
+        obj = os.path.join(b.LIB_DIR, name[:-3] + "_timeline.o")
+        subprocess.check_call([b._nvcc(), *b.NVCC_FLAGS, "-DGPMDM_TIMELINE", "-I", b.INCLUDE, "-c", os.path.join(b.CSRC, name), "-o", obj])
+        objs.append(obj)
+    objs += [os.path.join(b.LIB_DIR, os.path.basename(s)[:-3] + ".o") for s in b.sources() if os.path.basename(s) not in tl_srcs]
+    subprocess.check_call([b._nvcc(), "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a"])
     print(LIB)
+
+
+def frame(o, lib, model, wl):
+    """Node timeline of ONE graph-replayed frame of the small-cloud step: start / end of each of the six kernels."""
+    import numpy as np
+    import torch
+
+    from gpmdm_b200 import GPMDM_PF, synthetic
+
+    lib.gpmdm_debug_node_stamps.argtypes = [ctypes.c_void_p]
+    lib.gpmdm_debug_small_stamps.argtypes = [ctypes.c_void_p]
+    pf = GPMDM_PF(model, synthetic.markov_matrix(o.classes), o.particles, seed=0)
+    trial = wl.test_trials[0][1]
+    for z in trial[:20]:
+        pf.update(z)
+        pf.get_most_likely_class()
+    node, small = np.zeros(16, dtype=np.uint64), np.zeros(4, dtype=np.uint64)
+    frames = []
+    for z in trial[20:40]:
+        lib.gpmdm_debug_node_stamps(node.ctypes.data)  # reset
+        pf.update(z)
+        pf.get_most_likely_class()
+        lib.gpmdm_debug_node_stamps(node.ctypes.data)
+        lib.gpmdm_debug_small_stamps(small.ctypes.data)
+        n, s_ = node.astype(np.int64), small.astype(np.int64)
+        t0 = int(s_[0])
+        ev = {"pre": (0, int(s_[1]) - t0), "dyn_items": (int(n[2]) - t0, int(n[3]) - t0), "dyn_finalize": (int(n[6]) - t0, int(n[7]) - t0),
+              "obs_items": (int(n[0]) - t0, int(n[1]) - t0), "obs_finalize": (int(n[4]) - t0, int(n[5]) - t0),
+              "post": (int(s_[2]) - t0, int(s_[3]) - t0)}
+        frames.append(ev)
+    names = ["pre", "dyn_items", "dyn_finalize", "obs_items", "obs_finalize", "post"]
+    med = {k: [float(np.median([f[k][i] for f in frames])) for i in (0, 1)] for k in names}
+    out = {"workload": f"small-cloud frame, graph replay, P={o.particles}, N={model.X.shape[0]}: first start / last end of each kernel, ns after "
+                       "the pre kernel's start (medians over 20 frames; %globaltimer)",
+           "kernels": med,
+           "durations_ns": {k: med[k][1] - med[k][0] for k in names},
+           "gaps_ns": {f"{a}->{b}": med[b][0] - med[a][1] for a, b in zip(names[:-1], names[1:])},
+           "frame_ns": med["post"][1]}
+    print(json.dumps(out))
 
 
 def fused(o, lib, pk, model, X0, wl):
@@ -74,6 +116,7 @@ def main():
     ap.add_argument("--particles", type=int, default=100)
     ap.add_argument("--seg", type=int, default=-1, help="segment length in chunks (-1: the filter's own choice)")
     ap.add_argument("--fused", action="store_true", help="time the fused cached launch on 148 full tiles instead")
+    ap.add_argument("--frame", action="store_true", help="node timeline of one graph-replayed small-cloud frame")
     ap.add_argument("--dynamics", action="store_true", help="the dynamics GP's low-latency launch instead of the observation GP's")
     o = ap.parse_args()
     if o.build:
@@ -94,6 +137,8 @@ def main():
     P = o.particles
     if o.fused:
         return fused(o, lib, pk, model, X0, wl)
+    if o.frame:
+        return frame(o, lib, model, wl)
     g = torch.Generator().manual_seed(1)
     idx = torch.randint(0, X0.shape[0], (P,), generator=g)
     xs = (torch.tensor(X0[idx.numpy()]) + 0.1 * torch.randn(P, 3, dtype=torch.float64, generator=g)).cuda().contiguous()
