@@ -176,8 +176,11 @@ class GPMDM_PF:
             # (from the TOTAL particle count, never from this rank's share: the choice fixes the summation order over k)
             self._seg_obs = int(self._lib.gpmdm_predict_lowlat_pick_segment(tiles, self._packed["obs_n_pad"], _cabi.TILE_N,
                                                                             int(self._tri)))
-            self._seg_dyn = int(self._lib.gpmdm_predict_lowlat_pick_segment(max(tiles, min(C, P)), self._packed["dyn_max_n_pad"],
-                                                                            _cabi.TILE_N, int(self._tri)))
+            # dynamics tiles are class-homogeneous: a cloud of `tiles` full tiles usually leaves one more ragged one (100
+            # particles, 70 / 30 over two classes: 64 + 6 + 30), and the initial cloud populates every class
+            self._seg_dyn = int(self._lib.gpmdm_predict_lowlat_pick_segment(max(tiles + (1 if C > 1 else 0), min(C, P)),
+                                                                            self._packed["dyn_max_n_pad"], _cabi.TILE_N,
+                                                                            int(self._tri)))
             need = max(int(self._lib.gpmdm_predict_lowlat_workspace_bytes(Pl, self._packed["obs_n_pad"], self.observation_dim, self._seg_obs, 1)),
                        int(self._lib.gpmdm_predict_lowlat_workspace_bytes(Pl, self._packed["dyn_max_n_pad"], d, self._seg_dyn, C)))
             self._ws_lowlat = torch.empty(need // 8 + 1, dtype=torch.float64, device=dev)
