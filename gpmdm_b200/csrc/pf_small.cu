@@ -167,8 +167,10 @@ __global__ void __launch_bounds__(RT, 1) small_post_kernel(const SmallPostArgs a
     GPMDM_SMALL_STAMP(2)
     const int nb = (int)((P + RB - 1) / RB);
     double* scal = a.ws;                                                          // [0] max [1] sum [2] cdf total [3] max(ll + lw)
-    double* part = reinterpret_cast<double*>(reinterpret_cast<char*>(a.ws) + 256);  // per-block partials (global: read back by all threads
-                                                                                     // with the ld.global.cg loads of pf_stages.cuh)
+    // per-block partials (at most 4 blocks of 1024 particles) in shared memory: the staged kernels hand them from launch to
+    // launch through global memory; inside one CTA every such hand-over would be an L2 round trip
+    __shared__ double part_s[(SMALL_P_MAX / RB) * SUMM_COLS];
+    double* part = part_s;
     // ---- lw = ll - max, w = exp(lw) / sum (gpmdm_pf.py:200-204) ----
     for (int vb = 0; vb < nb; vb++) {
         const double v = block_max_dev<false>(a.ll, nullptr, P, vb, sh);

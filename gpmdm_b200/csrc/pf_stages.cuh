@@ -46,14 +46,18 @@ __device__ __forceinline__ double block_max(double v, double* sh) {
 }
 
 // NC = true: the array is read-only for the whole kernel (non-coherent path, ld.global.nc).  NC = false: it may have been
-// written earlier in the SAME kernel (the fused single-CTA kernels of pf_small.cu): coherent L2 loads.
+// written earlier in the SAME kernel by the SAME thread block -- the fused single-CTA kernels of pf_small.cu, the only
+// users: ordinary generic loads, which the block's own earlier stores are visible to after a __syncthreads (one SM, one
+// L1) and which also accept shared-memory pointers (the block partials of the small post kernel live there).
 template <bool NC>
 __device__ __forceinline__ double ld1(const double* p) {
-    return NC ? __ldg(p) : __ldcg(p);
+    if (NC) return __ldg(p);
+    return *p;
 }
 template <bool NC>
 __device__ __forceinline__ double2 ld2(const double* p) {
-    return NC ? __ldg(reinterpret_cast<const double2*>(p)) : __ldcg(reinterpret_cast<const double2*>(p));
+    if (NC) return __ldg(reinterpret_cast<const double2*>(p));
+    return *reinterpret_cast<const double2*>(p);
 }
 // 4 consecutive doubles per thread as two 16-byte accesses (arrays come from the caller 16-byte aligned and `base`
 // is a multiple of 4); the ragged tail of the array falls back to scalar accesses.
@@ -313,7 +317,7 @@ __device__ __forceinline__ void summaries_block_dev(const double* ll, const doub
     for (int k = 0; k < 4; k++) {
         const bool ok = base + k < n;
         e[k] = ok ? exp((vll[k] + vlw[k]) - m) : 0.0;
-        cc[k] = ok ? (int)(NC ? __ldg(c_post + base + k) : __ldcg(c_post + base + k)) : -1;
+        cc[k] = ok ? (int)(NC ? __ldg(c_post + base + k) : c_post[base + k]) : -1;
     }
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int ncol = C + d + 1;

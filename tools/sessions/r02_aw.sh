@@ -1,5 +1,5 @@
 #!/bin/bash
-# Round 2, GPU session AW: dynamics segment choice for one more ragged tile; post kernel's partials in shared memory:
+# Round 2, GPU sessions AW / AY: dynamics segment choice for one more ragged tile; post kernel with generic loads and its block partials in shared memory:
 # small-cloud tests, frame timeline, trial driver, suite.
 mkdir -p gpurun_out
 timeout 300 python -m pytest tests/test_gpu_small_cloud.py -m gpu -q -x 2>&1 | tail -3
