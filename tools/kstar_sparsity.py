@@ -5,7 +5,8 @@ sees at each frame, computes per (64-particle tile, 16-row chunk of training row
 entries are all below `thr` contributes less than thr * max|K^-1| to k^T K^-1 k and to the means and could be skipped; a
 256-column tile all of whose chunks are below it drops out of the quadratic form entirely.  Prints one JSON line with the
 live fractions and the implied share of the triangular (k-chunk, column-tile) work, in the filter's own particle order and
-with the particles additionally sorted along the first latent coordinate inside each class.
+with the particles additionally sorted along the first latent coordinate inside each class, and with BOTH the training
+rows and the particles in Z-order (Morton code of the scaled latents).
    python tools/kstar_sparsity.py [--frames 6] [--particles 37888]"""
 import argparse
 import json
@@ -40,6 +41,18 @@ def work_share(live):
     return float(live.double().mean()), float(ct_live.double().mean()), float(done / total)
 
 
+def morton_key(Z, bits=10):
+    """Morton (Z-order) code of the first three coordinates of Z [n, d], quantised to `bits` bits each."""
+    Z = Z[:, :3]
+    lo, hi = Z.min(0).values, Z.max(0).values
+    q = ((Z - lo) / (hi - lo + 1e-300) * (2 ** bits - 1)).long().clamp(0, 2 ** bits - 1)
+    key = torch.zeros(Z.shape[0], dtype=torch.long, device=Z.device)
+    for b in range(bits):
+        for c in range(q.shape[1]):
+            key |= ((q[:, c] >> b) & 1) << (3 * b + c)
+    return key
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--classes", type=int, default=8)
@@ -67,8 +80,13 @@ def main():
         key = c[:P].double() * 1e6 + B[:, 0]      # class-major, then along the first latent coordinate
         Bs = B[torch.argsort(key)]
         row = {"frame": t}
-        for name, Bx in (("filter_order", B), ("sorted", Bs)):
-            cm = chunk_max(A, Bx)
+        # both sides in Z-order: training rows by the Morton code of their scaled latents, particles class-major then Morton
+        Am = A[torch.argsort(morton_key(A))]
+        lo, hi = A.min(0).values, A.max(0).values
+        Bq = torch.max(torch.min(B, hi), lo)
+        Bm = B[torch.argsort(c[:P] * (1 << 40) + morton_key(torch.cat([Bq, lo[None], hi[None]]))[:P])]
+        for name, Ax, Bx in (("filter_order", A, B), ("sorted", A, Bs), ("both_morton_sorted", Am, Bm)):
+            cm = chunk_max(Ax, Bx)
             row[name] = {str(thr): dict(zip(("chunks_live", "column_tiles_live", "work_share"), work_share(cm >= thr)))
                          for thr in (1e-30, 1e-20)}
         d2 = torch.cdist(B[:4096], A) ** 2

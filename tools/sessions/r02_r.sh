@@ -8,5 +8,5 @@ import json
 d=json.load(open('gpurun_out/kstar_sparsity_r02.json'))
 print(d['workload'])
 for r in d['frames']:
-    print(r['frame'], r['entries_below_1e-30'], {k:{t:[round(x,3) for x in v.values()] for t,v in r[k].items()} for k in ('filter_order','sorted')})
+    print(r['frame'], r['entries_below_1e-30'], {k:{t:[round(x,3) for x in v.values()] for t,v in r[k].items()} for k in ('filter_order','sorted','both_morton_sorted')})
 PY
