@@ -51,7 +51,10 @@ constexpr int TM = GPMDM_TILE_P;  // particles per tile (8 warps x 8 rows)
 constexpr int TN = GPMDM_TILE_N;  // columns per column tile
 constexpr int KC = 16;            // k rows per chunk
 constexpr int STAGES = 6;         // B / record ring depth (TMA)
-constexpr int AHEAD = 3;          // chunks in flight ahead of the consumers
+#ifndef GPMDM_AHEAD
+#define GPMDM_AHEAD 3             /* tuning experiments: GPMDM_NVCC_EXTRA=-DGPMDM_AHEAD=.. python -m gpmdm_b200.build --force */
+#endif
+constexpr int AHEAD = GPMDM_AHEAD;  // chunks in flight ahead of the consumers
 constexpr int LDB = GPMDM_PANEL_LD;  // = TN + 4
 static_assert(LDB == TN + 4, "panel pitch");
 constexpr int NTHREADS = 256;
